@@ -1,0 +1,134 @@
+"""Generate golden fixtures from the LIVE reference (runs only where /root/reference exists).
+
+    python tests/golden/make_golden.py        # rewrites tests/golden/ref_*.npz
+
+What can be imported from the reference in this container:
+  lib/pair_matching/RT_transform.py  (needs a 3-line numpy-2 shim for np.float/np.maximum_sctype)
+  lib/pair_matching/flow.py:calc_flow, lib/utils/projection.py, lib/utils/pose_error.py:add/adi,
+  lib/utils/image.py:transform
+MXNet / glumpy are not installable offline, so the zoom ops, the network and the renderer have no
+reference-generated fixtures (parity unpinned there).
+Nothing from the reference is copied: this script only *calls* it and stores inputs/outputs.
+"""
+import doctest
+import os
+import sys
+
+import numpy as np
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def import_reference():
+    if not os.path.isdir(REF):
+        raise SystemExit("reference not present; fixtures are committed, nothing to do")
+    # numpy-2 shim (RT_transform.py:236-237 uses np.float / np.maximum_sctype at import time)
+    np.float = float
+    np.int = int
+    np.maximum_sctype = lambda t: np.float64
+    sys.path.insert(0, REF)
+    from lib.pair_matching import RT_transform as RT
+    from lib.pair_matching.flow import calc_flow
+    from lib.utils import pose_error
+    from lib.utils import projection
+    return RT, calc_flow, pose_error, projection
+
+
+def rand_rot(rng):
+    q = rng.normal(size=4)
+    q /= np.linalg.norm(q)
+    w, x, y, z = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def main():
+    RT, calc_flow, pose_error, projection = import_reference()
+    res = doctest.testmod(RT)
+    print("RT_transform doctests:", res)
+    assert res.failed == 0 and res.attempted >= 20
+
+    rng = np.random.default_rng(1234)
+    N = 64
+    pose_src = np.zeros((N, 3, 4))
+    quat = rng.normal(size=(N, 4)) * 0.2 + np.array([1.0, 0, 0, 0])
+    quat[:8] = rng.normal(size=(8, 4))  # big rotations too
+    trans = rng.normal(size=(N, 3)) * np.array([0.05, 0.05, 0.2])
+    T_means = np.array([0.01, -0.02, 0.03])
+    T_stds = np.array([0.5, 0.7, 1.3])
+    out = {}
+    for k in range(N):
+        pose_src[k, :, :3] = rand_rot(rng)
+        pose_src[k, :, 3] = [rng.uniform(-0.2, 0.2), rng.uniform(-0.2, 0.2), rng.uniform(0.4, 1.5)]
+    for coord in ("MODEL", "CAMERA", "CAMERA_NEW"):
+        po = np.zeros((N, 3, 4))
+        po_norm = np.zeros((N, 3, 4))
+        Rd = np.zeros((N, 3, 3))
+        Td = np.zeros((N, 3))
+        for k in range(N):
+            po[k] = RT.RT_transform(pose_src[k], quat[k], trans[k], np.zeros(3), np.ones(3), coord)
+            po_norm[k] = RT.RT_transform(pose_src[k], quat[k], trans[k], T_means, T_stds, coord)
+            r, t = RT.calc_RT_delta(pose_src[k], po_norm[k], T_means, T_stds, coord, "MATRIX")
+            Rd[k], Td[k] = r, t
+        out["pose_out_" + coord] = po
+        out["pose_out_norm_" + coord] = po_norm
+        out["R_delta_" + coord] = Rd
+        out["T_delta_" + coord] = Td
+    # quat2mat known answers from the docstring examples (RT_transform.py:397-404)
+    out["quat2mat_in"] = np.array([[1.0, 0, 0, 0], [0, 1.0, 0, 0]])
+    out["quat2mat_out"] = np.stack([RT.quat2mat(q) for q in out["quat2mat_in"]])
+    np.savez_compressed(os.path.join(HERE, "ref_se3.npz"), pose_src=pose_src, quat=quat, trans=trans,
+                        T_means=T_means, T_stds=T_stds, **out)
+
+    # ---- calc_flow (lib/pair_matching/flow.py:12-63) on a small synthetic depth pair
+    H, W = 60, 80
+    K = np.array([[572.4114 / 8, 0, 325.2611 / 8], [0, 573.57043 / 8, 242.04899 / 8], [0, 0, 1]])
+    yy, xx = np.mgrid[0:H, 0:W]
+    depth_src = np.zeros((H, W), np.float32)
+    blob = ((xx - 40) ** 2 / 400.0 + (yy - 30) ** 2 / 250.0) < 1
+    depth_src[blob] = (0.8 + 0.002 * (xx - 40) + 0.001 * (yy - 30))[blob]
+    ps = np.zeros((3, 4)); ps[:, :3] = np.eye(3); ps[:, 3] = [0, 0, 0]
+    pt = np.zeros((3, 4)); pt[:, :3] = rand_rot(np.random.default_rng(5)) * 0 + np.eye(3)
+    ang = 0.05
+    pt[:, :3] = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]])
+    pt[:, 3] = [0.01, -0.005, 0.02]
+    # target depth = source surface seen from the target pose: splat
+    X = projection.backproject_camera(depth_src, K)
+    T = projection.se3_mul(pt, projection.se3_inverse(ps))
+    Xp = T[:, :3] @ X + T[:, 3:4]
+    depth_tgt = np.zeros((H, W), np.float32)
+    uvw = K @ Xp
+    for k in range(X.shape[1]):
+        if depth_src.flat[k] == 0:
+            continue
+        u, v = int(round(uvw[0, k] / uvw[2, k])), int(round(uvw[1, k] / uvw[2, k]))
+        if 0 <= u < W and 0 <= v < H:
+            depth_tgt[v, u] = uvw[2, k]
+    flow, visible, _ = calc_flow(depth_src, ps, pt, K, depth_tgt)
+    np.savez_compressed(os.path.join(HERE, "ref_flow.npz"), depth_src=depth_src, depth_tgt=depth_tgt,
+                        pose_src=ps, pose_tgt=pt, K=K, flow=flow.astype(np.float32),
+                        visible=visible.astype(np.float32))
+
+    # ---- ADD / ADI (lib/utils/pose_error.py:72-108)
+    pts = rng.normal(size=(500, 3)) * 0.03
+    Re, Rg = rand_rot(rng), rand_rot(rng)
+    te, tg = rng.normal(size=(3, 1)) * 0.01 + [[0], [0], [0.8]], np.array([[0.0], [0.0], [0.8]])
+    np.savez_compressed(os.path.join(HERE, "ref_pose_error.npz"), pts=pts, R_est=Re, t_est=te, R_gt=Rg, t_gt=tg,
+                        add=pose_error.add(Re, te, Rg, tg, pts), adi=pose_error.adi(Re, te, Rg, tg, pts))
+
+    # ---- image.transform (lib/utils/image.py:583-594)
+    try:
+        from lib.utils.image import transform
+        im = rng.integers(0, 256, size=(6, 8, 3)).astype(np.uint8)
+        pm = np.array([123.68, 116.779, 103.939])
+        np.savez_compressed(os.path.join(HERE, "ref_transform.npz"), im=im, pixel_means=pm,
+                            out=transform(im, pm).astype(np.float32))
+    except Exception as e:  # cv2 / other imports of image.py may be missing
+        print("image.transform not importable:", e)
+    print("golden fixtures written to", HERE)
+
+
+if __name__ == "__main__":
+    main()
