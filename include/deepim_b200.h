@@ -1,0 +1,209 @@
+/*
+ * deepim_b200.h -- C ABI of libdeepim_b200.so (hand-written sm_100a CUDA, no CPU fallback).
+ *
+ * Drop-in boundary for the mx-DeepIM render-and-compare hot path.  Each entry point names the
+ * reference interface it replaces (paths relative to the mx-DeepIM repo).  The reference binds its
+ * native/GPU pieces from Python (mx.operator.CustomOp classes in deepim/operator_py/, the Cython
+ * wrapper lib/flow_c/gpu_flow.pyx, the glumpy renderer class); the matching binding here is the
+ * ctypes stub shown in INTEGRATION.md and shipped as mx-deepim_b200/deepim_b200/_capi.py.
+ *
+ * Conventions
+ *   - all tensor pointers are DEVICE pointers owned by the caller, contiguous, NCHW float32 unless
+ *     noted; "host" in a parameter comment means a host pointer (small attribute arrays);
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it and allocates
+ *     nothing (all scratch is sized by dim_ctx_create); one context per device, not thread-safe;
+ *   - return 0 on success, non-zero on error; dim_last_error() gives the message
+ *     (the reference ops raise Python exceptions instead; the Python shims re-raise);
+ *   - H, W are fixed per context (480 x 640 in every shipped config).
+ */
+#ifndef DEEPIM_B200_H_
+#define DEEPIM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define DIM_API
+#else
+#define DIM_API __attribute__((visibility("default")))
+#endif
+
+typedef struct dim_ctx dim_ctx;
+
+#define DIM_ABI_VERSION 1
+DIM_API int32_t dim_abi_version(void);
+DIM_API const char *dim_last_error(void);
+
+/* Context: owns meshes, weights and all scratch.  max_verts/max_faces bound the largest mesh.
+ * Replaces the per-process state of Render_Py.__init__ (lib/render_glumpy/render_py_multi.py:54-99)
+ * and of the MXNet executor (deepim/core/tester.py:41-43). */
+DIM_API int32_t dim_ctx_create(int32_t device, int32_t max_batch, int32_t height, int32_t width,
+                               int32_t max_classes, int32_t max_verts, int32_t max_faces,
+                               dim_ctx **out);
+DIM_API void dim_ctx_destroy(dim_ctx *ctx);
+
+/* Upload one class mesh (host pointers).  verts f32[V,3] metres, uvs f32[V,2], faces i32[F,3],
+ * tex u8[Th,Tw,3] RGB with row 0 = v 0 (i.e. already flipped as render_py_multi.py:76 does).
+ * Replaces data.objload + gloo.Program.bind + u_texture upload (render_py_multi.py:72-76). */
+DIM_API int32_t dim_mesh_upload(dim_ctx *ctx, int32_t cls_idx, const float *verts_host,
+                                const float *uvs_host, int32_t V, const int32_t *faces_host,
+                                int32_t F, const uint8_t *tex_host, int32_t Th, int32_t Tw);
+
+/* Rasterise B instances.  Replaces Render_Py.render (render_py_multi.py:101-129) plus the
+ * post-render glue (deepim/core/tester.py:185-188,433-442; lib/utils/image.py:583-594).
+ *   cls_idx i32[B] (device), pose f32[B,3,4] (device), K9 host f32[9], pixel_means_rgb host f64[3]
+ *   trunc_u8: 1 = test path (uint8 truncation, tester.py:188), 0 = train path
+ *   outputs (each may be NULL):
+ *     out_image f32[B,3,H,W] RGB - means;  out_depth f32[B,1,H,W] metres;  out_mask f32[B,1,H,W]
+ *     out_bgr f32[B,H,W,3] BGR in [0,255] (the Render_Py return layout);
+ *     out_bbox i32[B,4] x0,x1,y0,y1 of out_mask (min/max nonzero col/row; -1 when empty). */
+DIM_API int32_t dim_render(dim_ctx *ctx, const int32_t *cls_idx, const float *pose, int32_t B,
+                           const float *K9_host, float znear, float zfar,
+                           const double *pixel_means_rgb_host, int32_t trunc_u8, float *out_image,
+                           float *out_depth, float *out_mask, float *out_bgr, int32_t *out_bbox,
+                           void *stream);
+
+/* ZoomMask forward (deepim/operator_py/zoom_mask.py:29-112).
+ * in : mask_observed, mask_gt_observed, mask_rendered f32[B,1,H,W]; src_pose f32[B,3,4]; K9 host
+ * out: 3 zoomed masks f32[B,1,H,W] (any may be NULL), zoom_factor f32[B,4],
+ *      bbox i32[B,8] = observed x0,x1,y0,y1, rendered x0,x1,y0,y1 (may be NULL),
+ *      status i32[B] (may be NULL): 1 where the observed mask is empty (the reference raises). */
+DIM_API int32_t dim_zoom_mask_fwd(dim_ctx *ctx, const float *mask_observed,
+                                  const float *mask_gt_observed, const float *mask_rendered,
+                                  const float *src_pose, int32_t B, const float *K9_host,
+                                  float *zoom_mask_observed, float *zoom_mask_gt_observed,
+                                  float *zoom_mask_rendered, float *zoom_factor, int32_t *bbox,
+                                  int32_t *status, void *stream);
+
+/* ZoomImageWithFactor forward (zoom_image_with_factor.py:31-65). pixel_means_rgb host f32[3] is the
+ * already-reversed attr (l.79-81).  images f32[B,3,H,W]. */
+DIM_API int32_t dim_zoom_image_with_factor_fwd(dim_ctx *ctx, const float *zoom_factor,
+                                               const float *image_observed,
+                                               const float *image_rendered, int32_t B,
+                                               const float *pixel_means_rgb_host,
+                                               float *zoom_image_observed,
+                                               float *zoom_image_rendered, void *stream);
+
+/* ZoomMaskWithFactor forward (zoom_mask_with_factor.py:29-64): mask f32[B,1,H,W]. */
+DIM_API int32_t dim_zoom_mask_with_factor_fwd(dim_ctx *ctx, const float *zoom_factor,
+                                              const float *mask, int32_t B, int32_t b_inv_zoom,
+                                              float *zoom_mask, void *stream);
+
+/* ZoomFlow forward (zoom_flow.py:28-71): flow f32[B,2,H,W]; flow_weights/zoom_flow_weights
+ * f32[B,1,H,W] used only when b_inv_zoom == 0 (may be NULL). */
+DIM_API int32_t dim_zoom_flow_fwd(dim_ctx *ctx, const float *zoom_factor, const float *flow,
+                                  const float *flow_weights, int32_t B, int32_t b_inv_zoom,
+                                  float *zoom_flow, float *zoom_flow_weights, void *stream);
+
+/* ZoomDepth forward (zoom_depth.py:24-44): depth f32[B,1,H,W] x2. */
+DIM_API int32_t dim_zoom_depth_fwd(dim_ctx *ctx, const float *zoom_factor,
+                                   const float *depth_observed, const float *depth_rendered,
+                                   int32_t B, float *zoom_depth_observed,
+                                   float *zoom_depth_rendered, void *stream);
+
+/* ZoomTrans forward / backward (zoom_trans.py:22-74): trans f32[B,3]. */
+DIM_API int32_t dim_zoom_trans_fwd(dim_ctx *ctx, const float *zoom_factor, const float *trans_delta,
+                                   int32_t B, int32_t b_inv_zoom, float *zoom_trans_delta,
+                                   void *stream);
+DIM_API int32_t dim_zoom_trans_bwd(dim_ctx *ctx, const float *zoom_factor, const float *out_grad,
+                                   int32_t B, int32_t b_inv_zoom, int32_t b_zoom_grad,
+                                   float *trans_grad, void *stream);
+
+/* mask_observed := end-exclusive bbox rectangle of mask_rendered
+ * (lib/pair_matching/data_pair.py:93-105).  bbox i32[B,4] as written by dim_render. */
+DIM_API int32_t dim_update_mask_box(dim_ctx *ctx, const int32_t *bbox, int32_t B,
+                                    float *mask_observed, void *stream);
+
+/* SE(3) compose in float64 (lib/pair_matching/RT_transform.py:127-151).
+ * pose_src f64[B,3,4], se3 f32[B,7] = (quat w,x,y,z un-normalised, trans), T_means/T_stds host
+ * f64[3], rot_coord 0 MODEL / 1 CAMERA / 2 CAMERA_NEW; pose_out f64[B,3,4]. */
+DIM_API int32_t dim_se3_compose(dim_ctx *ctx, const double *pose_src, const float *se3, int32_t B,
+                                const double *T_means_host, const double *T_stds_host,
+                                int32_t rot_coord, double *pose_out, void *stream);
+
+/* Reprojection-flow labels (lib/flow_c/gpu_flow_kernel.cu:32-69 flow_kernel, gpu_flow.pyx:24-41).
+ * depth_src, depth_tgt f32[B,1,H,W]; KT f32[B,3,4] = K.T_src->tgt; Kinv host f32[9];
+ * flow f32[B,2,H,W] (dh,dw), valid f32[B,1,H,W]. */
+DIM_API int32_t dim_flow_fwd(dim_ctx *ctx, const float *depth_src, const float *depth_tgt,
+                             const float *KT, const float *Kinv_host, int32_t B, float *flow,
+                             float *valid, void *stream);
+
+/* Transform3D forward / backward (deepim/operator_py/transform3d.py:34-151).
+ * point_cloud f32[B,3,N], rotation f32[B,4], translation f32[B,3], pose_src f32[B,3,4]. */
+DIM_API int32_t dim_transform3d_fwd(dim_ctx *ctx, const float *point_cloud, const float *rotation,
+                                    const float *translation, const float *pose_src, int32_t B,
+                                    int32_t N, const float *T_means_host, const float *T_stds_host,
+                                    int32_t rot_coord, float *out_points, void *stream);
+DIM_API int32_t dim_transform3d_bwd(dim_ctx *ctx, const float *out_grad, const float *point_cloud,
+                                    const float *rotation, const float *translation,
+                                    const float *pose_src, int32_t B, int32_t N,
+                                    const float *T_means_host, const float *T_stds_host,
+                                    int32_t rot_coord, float *rot_grad, float *trans_grad,
+                                    void *stream);
+
+/* FlowNetS weights (deepim/symbols/deepIM_flownet.py:63-116,716-717; MXNet layouts: Convolution
+ * (Cout,Cin,kh,kw), FullyConnected (out,in)).  Host float32 pointers, 14 (weight,bias) pairs in the
+ * order flow_conv1, conv2, conv3, conv3_1, conv4, conv4_1, conv5, conv5_1, conv6, conv6_1, fc6,
+ * fc7, rot, trans.  Replaces load_param + Module.init_params (deepim/core/tester.py:41-43). */
+DIM_API int32_t dim_net_load(dim_ctx *ctx, const float *const *weights_host,
+                             const float *const *biases_host);
+
+/* precision of the conv stack */
+#define DIM_PREC_BF16 0   /* one bf16 tcgen05 pass, fp32 accumulate (throughput mode)          */
+#define DIM_PREC_BF16X3 1 /* hi/lo split, 3 tcgen05 passes, ~fp32 accuracy (parity mode)       */
+
+/* Encoder + fc + heads on already-zoomed blobs (get_convs, deepIM_flownet.py:53-116; heads
+ * l.716-717): inputs f32 NCHW as the op surface produces them; rot f32[B,4] raw quaternion,
+ * trans f32[B,3] zoomed translation. */
+DIM_API int32_t dim_net_fwd(dim_ctx *ctx, const float *zoom_image_observed,
+                            const float *zoom_image_rendered, const float *zoom_mask_observed,
+                            const float *zoom_mask_rendered, int32_t B, int32_t precision,
+                            float *rot, float *trans, void *stream);
+
+/* The fused test-time loop (deepim/core/tester.py:340-485 with FAST_TEST / UPDATE_MASK
+ * box_rendered): n_iter x (render -> bbox+zoom -> FlowNetS -> ZoomTrans^-1 -> RT_transform),
+ * everything on the device, no host sync.
+ *   image_observed f32[B,3,H,W] RGB-mean (constant over iterations)
+ *   cls_idx i32[B]; pose_init f64[B,3,4]
+ *   outputs (device): poses f64[n_iter,B,3,4], se3 f32[n_iter,B,7], zoom_factor f32[n_iter,B,4],
+ *   bbox i32[n_iter,B,8]; any of the last three may be NULL.
+ *   pose_override f64[n_iter,B,3,4] or NULL: when given, iteration `it` starts from
+ *   pose_override[it] instead of the previous estimate (teacher forcing for parity tests). */
+DIM_API int32_t dim_refine(dim_ctx *ctx, const float *image_observed, const int32_t *cls_idx,
+                           const double *pose_init, int32_t B, int32_t n_iter, const float *K9_host,
+                           float znear, float zfar, const double *pixel_means_rgb_host,
+                           int32_t precision, const double *pose_override, double *poses,
+                           float *se3, float *zoom_factor, int32_t *bbox, void *stream);
+
+/* Host-buffer convenience around dim_refine (what deepim/core/tester.py:pred_eval would call):
+ * image_observed_u8 host u8[B,H,W,3] BGR (as cv2.imread returns; transformed on device as
+ * lib/utils/image.py:583-594), cls_idx host, pose_init host f64; poses_out host f64[n_iter,B,3,4].
+ * Pinned buffers are recommended.  Synchronises the stream before returning. */
+DIM_API int32_t dim_refine_host(dim_ctx *ctx, const uint8_t *image_observed_u8_host,
+                                const int32_t *cls_idx_host, const double *pose_init_host,
+                                int32_t B, int32_t n_iter, const float *K9_host, float znear,
+                                float zfar, const double *pixel_means_rgb_host, int32_t precision,
+                                double *poses_out_host, float *se3_out_host, void *stream);
+
+/* BGR u8 HWC -> RGB-mean f32 CHW on device (lib/utils/image.py:583-594 transform). */
+DIM_API int32_t dim_transform_image_u8(dim_ctx *ctx, const uint8_t *bgr_u8, int32_t B,
+                                       const double *pixel_means_rgb_host, float *image,
+                                       void *stream);
+
+/* Test hooks (not part of the drop-in surface): copy the bf16 NHWC activation buffer feeding conv
+ * layer idx (10 = fc6 input) to the host, and its geometry
+ * out8 = rows, cols, C, py, px, Ho, Wo, Cout. */
+DIM_API int32_t dim_debug_activation(dim_ctx *ctx, int32_t idx, int32_t lo, void *host_dst,
+                                     uint64_t bytes);
+DIM_API int32_t dim_debug_layer_geometry(dim_ctx *ctx, int32_t idx, int32_t *out8);
+
+/* number of kernel launches issued by this library since the counter was last reset */
+DIM_API int64_t dim_launch_count(int32_t reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPIM_B200_H_ */

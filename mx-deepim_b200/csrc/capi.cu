@@ -1,0 +1,350 @@
+// capi.cu -- the extern "C" surface declared in include/deepim_b200.h.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace dim {
+
+static thread_local char g_err[1024] = "";
+long long g_launches = 0;
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// implemented in raster.cu / zoom.cu / geom.cu / net.cu
+int render_launch(dim_ctx *, const int *, const float *, int, const float *, float, float, const double *, int, float *,
+                  float *, float *, float *, int *, cudaStream_t);
+int zoom_gather_launch(dim_ctx *, int mode, const float *src, float *dst, const float *zf, int B, int C, int inv,
+                       const float *param, cudaStream_t);
+int zoom_factor_launch(dim_ctx *, const float *, const float *, int C, const float *, int B, const float *K9, float *,
+                       int *, int *, cudaStream_t);
+int zoom_factor_from_ren_launch(dim_ctx *, const int *, const float *, int B, const float *K9, float *, int *, int *,
+                                cudaStream_t);
+int box_mask_launch(dim_ctx *, const int *, int B, float *, cudaStream_t);
+int zoom_fused_launch(dim_ctx *, const float *, const float *, const float *, const float *, const float *, int B,
+                      int Hs, int Ws, int pad, __nv_bfloat16 *, __nv_bfloat16 *, cudaStream_t);
+int pack_nhwc8_launch(dim_ctx *, const float *, const float *, const float *, const float *, int B, int Hs, int Ws,
+                      int pad, __nv_bfloat16 *, __nv_bfloat16 *, cudaStream_t);
+int flow_launch(dim_ctx *, const float *, const float *, const float *, const float *, int B, float *, float *,
+                cudaStream_t);
+int se3_compose_launch(const double *, const float *, int B, const double *, const double *, int, double *, float *,
+                       cudaStream_t);
+int f64_to_f32_launch(const double *, float *, int n, cudaStream_t);
+int zoom_trans_launch(const float *, const float *, int B, int mul, int scale_xy, float *, cudaStream_t);
+int transform3d_fwd_launch(const float *, const float *, const float *, const float *, int, int, const float *,
+                           const float *, int, float *, cudaStream_t);
+int transform3d_bwd_launch(const float *, const float *, const float *, const float *, const float *, int, int,
+                           const float *, const float *, int, float *, float *, cudaStream_t);
+int transform_u8_launch(dim_ctx *, const uint8_t *, int B, const double *, float *, cudaStream_t);
+int net_create(dim_ctx *);
+void net_destroy(dim_ctx *);
+int net_load(dim_ctx *, const float *const *, const float *const *);
+void net_input_geometry(dim_ctx *, int *rows, int *cols, int *pad, __nv_bfloat16 **hi, __nv_bfloat16 **lo);
+int net_forward(dim_ctx *, int B, int precision, const float *zoom_factor, float *rot, float *trans, float *se3,
+                cudaStream_t);
+int net_debug_activation(dim_ctx *, int idx, int lo, void *host_dst, size_t bytes);
+void net_layer_geometry(dim_ctx *, int idx, int *out);
+
+template <typename T>
+static int ctx_alloc(dim_ctx *ctx, T **p, size_t n) {
+  void *q = nullptr;
+  DIM_CHECK(cudaMalloc(&q, n * sizeof(T)));
+  ctx->owned.push_back(q);
+  *p = reinterpret_cast<T *>(q);
+  return 0;
+}
+
+}  // namespace dim
+
+using namespace dim;
+
+extern "C" {
+
+DIM_API int32_t dim_abi_version(void) { return DIM_ABI_VERSION; }
+DIM_API const char *dim_last_error(void) { return g_err; }
+DIM_API int64_t dim_launch_count(int32_t reset) {
+  long long v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+DIM_API int32_t dim_ctx_create(int32_t device, int32_t max_batch, int32_t H, int32_t W, int32_t max_classes,
+                               int32_t max_verts, int32_t max_faces, dim_ctx **out) {
+  DIM_REQUIRE(out != nullptr, "dim_ctx_create: out is NULL");
+  DIM_REQUIRE(max_batch >= 1 && H >= 16 && W >= 16 && (W % 4) == 0, "dim_ctx_create: bad sizes");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    set_error("dim_ctx_create: no CUDA device available (%s); this library has no CPU fallback",
+              cudaGetErrorString(e));
+    return 10;
+  }
+  DIM_CHECK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  DIM_CHECK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("dim_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+              prop.minor);
+    return 11;
+  }
+  dim_ctx *ctx = new dim_ctx();
+  ctx->device = device; ctx->max_batch = max_batch; ctx->H = H; ctx->W = W;
+  ctx->max_classes = max_classes; ctx->max_verts = max_verts; ctx->max_faces = max_faces;
+  ctx->num_sms = prop.multiProcessorCount;
+  const size_t P = (size_t)H * W, Bm = (size_t)max_batch;
+  int rc = 0;
+  rc |= ctx_alloc(ctx, &ctx->meshes, (size_t)max_classes);
+  rc |= ctx_alloc(ctx, &ctx->pverts, Bm * (size_t)max_verts);
+  rc |= ctx_alloc(ctx, &ctx->vis, Bm * P);
+  rc |= ctx_alloc(ctx, &ctx->vbox, Bm * 4);
+  rc |= ctx_alloc(ctx, &ctx->bbox8, Bm * 8);
+  rc |= ctx_alloc(ctx, &ctx->status, Bm);
+  rc |= ctx_alloc(ctx, &ctx->zoom_factor, Bm * 4);
+  rc |= ctx_alloc(ctx, &ctx->image_rendered, Bm * 3 * P);
+  rc |= ctx_alloc(ctx, &ctx->depth_rendered, Bm * P);
+  rc |= ctx_alloc(ctx, &ctx->mask_rendered, Bm * P);
+  rc |= ctx_alloc(ctx, &ctx->bbox_ren, Bm * 4);
+  rc |= ctx_alloc(ctx, &ctx->pose_cur, Bm * 12);
+  rc |= ctx_alloc(ctx, &ctx->pose_cur_f32, Bm * 12);
+  rc |= ctx_alloc(ctx, &ctx->se3_cur, Bm * 7);
+  rc |= ctx_alloc(ctx, &ctx->image_observed_f32, Bm * 3 * P);
+  rc |= ctx_alloc(ctx, &ctx->image_observed_u8, Bm * 3 * P);
+  rc |= ctx_alloc(ctx, &ctx->cls_dev, Bm);
+  rc |= ctx_alloc(ctx, &ctx->poses_dev, 8 * Bm * 12);
+  rc |= ctx_alloc(ctx, &ctx->se3_hist_dev, 8 * Bm * 7);
+  if (rc) { dim_ctx_destroy(ctx); return 12; }
+  ctx->meshes_host.assign(max_classes, MeshDev{nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0});
+  DIM_CHECK(cudaMemset(ctx->meshes, 0, sizeof(MeshDev) * max_classes));
+  DIM_CHECK(cudaMemset(ctx->vis, 0xFF, sizeof(unsigned long long) * Bm * P));  // all pixels empty
+  DIM_CHECK(cudaMemset(ctx->pverts, 0, sizeof(PVert) * Bm * max_verts));
+  if (net_create(ctx)) { dim_ctx_destroy(ctx); return 13; }
+  DIM_CHECK(cudaDeviceSynchronize());
+  *out = ctx;
+  return 0;
+}
+
+DIM_API void dim_ctx_destroy(dim_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  net_destroy(ctx);
+  for (void *p : ctx->owned) cudaFree(p);
+  delete ctx;
+}
+
+DIM_API int32_t dim_mesh_upload(dim_ctx *ctx, int32_t cls, const float *verts, const float *uvs, int32_t V,
+                                const int32_t *faces, int32_t F, const uint8_t *tex, int32_t Th, int32_t Tw) {
+  DIM_REQUIRE(ctx && cls >= 0 && cls < ctx->max_classes, "dim_mesh_upload: bad class index");
+  DIM_REQUIRE(V > 0 && V <= ctx->max_verts && F > 0 && F <= ctx->max_faces, "dim_mesh_upload: mesh exceeds ctx limits");
+  for (int32_t i = 0; i < 3 * F; ++i) DIM_REQUIRE(faces[i] >= 0 && faces[i] < V, "dim_mesh_upload: face index out of range");
+  MeshDev m;
+  float *dv, *du; int *df; uint8_t *dt;
+  if (ctx_alloc(ctx, &dv, (size_t)3 * V) || ctx_alloc(ctx, &du, (size_t)2 * V) || ctx_alloc(ctx, &df, (size_t)3 * F) ||
+      ctx_alloc(ctx, &dt, (size_t)3 * Th * Tw))
+    return 12;
+  DIM_CHECK(cudaMemcpy(dv, verts, sizeof(float) * 3 * V, cudaMemcpyHostToDevice));
+  DIM_CHECK(cudaMemcpy(du, uvs, sizeof(float) * 2 * V, cudaMemcpyHostToDevice));
+  DIM_CHECK(cudaMemcpy(df, faces, sizeof(int) * 3 * F, cudaMemcpyHostToDevice));
+  DIM_CHECK(cudaMemcpy(dt, tex, (size_t)3 * Th * Tw, cudaMemcpyHostToDevice));
+  m.verts = dv; m.uvs = du; m.faces = df; m.tex = dt; m.V = V; m.F = F; m.Th = Th; m.Tw = Tw;
+  ctx->meshes_host[cls] = m;
+  DIM_CHECK(cudaMemcpy(ctx->meshes + cls, &m, sizeof(MeshDev), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+DIM_API int32_t dim_render(dim_ctx *ctx, const int32_t *cls_idx, const float *pose, int32_t B, const float *K9,
+                           float zn, float zf, const double *means, int32_t trunc_u8, float *out_image,
+                           float *out_depth, float *out_mask, float *out_bgr, int32_t *out_bbox, void *stream) {
+  DIM_REQUIRE(ctx && cls_idx && pose && K9, "dim_render: NULL argument");
+  return render_launch(ctx, cls_idx, pose, B, K9, zn, zf, means, trunc_u8, out_image, out_depth, out_mask, out_bgr,
+                       out_bbox, (cudaStream_t)stream);
+}
+
+DIM_API int32_t dim_zoom_mask_fwd(dim_ctx *ctx, const float *mo, const float *mgt, const float *mr,
+                                  const float *src_pose, int32_t B, const float *K9, float *zmo, float *zmgt,
+                                  float *zmr, float *zoom_factor, int32_t *bbox, int32_t *status, void *stream) {
+  DIM_REQUIRE(ctx && mo && mgt && mr && src_pose && K9 && zoom_factor, "dim_zoom_mask_fwd: NULL argument");
+  DIM_REQUIRE(B >= 1 && B <= ctx->max_batch, "dim_zoom_mask_fwd: batch exceeds max_batch");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = zoom_factor_launch(ctx, mgt, mr, 1, src_pose, B, K9, zoom_factor, bbox, status, st)) return rc;
+  if (zmo) if (int rc = zoom_gather_launch(ctx, 1, mo, zmo, zoom_factor, B, 1, 0, nullptr, st)) return rc;
+  if (zmgt) if (int rc = zoom_gather_launch(ctx, 1, mgt, zmgt, zoom_factor, B, 1, 0, nullptr, st)) return rc;
+  // rendered mask is binarised at 0.2 before sampling (zoom_mask.py:39-42)
+  if (zmr) if (int rc = zoom_gather_launch(ctx, 2, mr, zmr, zoom_factor, B, 1, 0, nullptr, st)) return rc;
+  return 0;
+}
+
+DIM_API int32_t dim_zoom_image_with_factor_fwd(dim_ctx *ctx, const float *zoom_factor, const float *io,
+                                               const float *ir, int32_t B, const float *means, float *zio,
+                                               float *zir, void *stream) {
+  DIM_REQUIRE(ctx && zoom_factor && io && ir && means && zio && zir, "dim_zoom_image_with_factor_fwd: NULL argument");
+  DIM_REQUIRE(B >= 1 && B <= ctx->max_batch, "batch exceeds max_batch");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = zoom_gather_launch(ctx, 3, io, zio, zoom_factor, B, 3, 0, means, st)) return rc;
+  return zoom_gather_launch(ctx, 3, ir, zir, zoom_factor, B, 3, 0, means, st);
+}
+
+DIM_API int32_t dim_zoom_mask_with_factor_fwd(dim_ctx *ctx, const float *zoom_factor, const float *mask, int32_t B,
+                                              int32_t inv, float *out, void *stream) {
+  DIM_REQUIRE(ctx && zoom_factor && mask && out, "dim_zoom_mask_with_factor_fwd: NULL argument");
+  return zoom_gather_launch(ctx, 2, mask, out, zoom_factor, B, 1, inv, nullptr, (cudaStream_t)stream);
+}
+
+DIM_API int32_t dim_zoom_flow_fwd(dim_ctx *ctx, const float *zoom_factor, const float *flow, const float *fw,
+                                  int32_t B, int32_t inv, float *zflow, float *zfw, void *stream) {
+  DIM_REQUIRE(ctx && zoom_factor && flow && zflow, "dim_zoom_flow_fwd: NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = zoom_gather_launch(ctx, inv ? 4 : 6, flow, zflow, zoom_factor, B, 2, inv, nullptr, st)) return rc;
+  if (!inv && fw && zfw) return zoom_gather_launch(ctx, 5, fw, zfw, zoom_factor, B, 1, 0, nullptr, st);
+  return 0;
+}
+
+DIM_API int32_t dim_zoom_depth_fwd(dim_ctx *ctx, const float *zoom_factor, const float *dobs, const float *dren,
+                                   int32_t B, float *zobs, float *zren, void *stream) {
+  DIM_REQUIRE(ctx && zoom_factor && dobs && dren && zobs && zren, "dim_zoom_depth_fwd: NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = zoom_gather_launch(ctx, 0, dobs, zobs, zoom_factor, B, 1, 0, nullptr, st)) return rc;
+  return zoom_gather_launch(ctx, 0, dren, zren, zoom_factor, B, 1, 0, nullptr, st);
+}
+
+DIM_API int32_t dim_zoom_trans_fwd(dim_ctx *ctx, const float *zoom_factor, const float *trans, int32_t B, int32_t inv,
+                                   float *out, void *stream) {
+  DIM_REQUIRE(ctx && zoom_factor && trans && out, "dim_zoom_trans_fwd: NULL argument");
+  return zoom_trans_launch(zoom_factor, trans, B, inv ? 1 : 0, 1, out, (cudaStream_t)stream);
+}
+DIM_API int32_t dim_zoom_trans_bwd(dim_ctx *ctx, const float *zoom_factor, const float *og, int32_t B, int32_t inv,
+                                   int32_t zoom_grad, float *out, void *stream) {
+  DIM_REQUIRE(ctx && zoom_factor && og && out, "dim_zoom_trans_bwd: NULL argument");
+  return zoom_trans_launch(zoom_factor, og, B, inv ? 1 : 0, zoom_grad ? 1 : 0, out, (cudaStream_t)stream);
+}
+
+DIM_API int32_t dim_update_mask_box(dim_ctx *ctx, const int32_t *bbox, int32_t B, float *mask, void *stream) {
+  DIM_REQUIRE(ctx && bbox && mask, "dim_update_mask_box: NULL argument");
+  return box_mask_launch(ctx, bbox, B, mask, (cudaStream_t)stream);
+}
+
+DIM_API int32_t dim_se3_compose(dim_ctx *ctx, const double *pose_src, const float *se3, int32_t B, const double *Tm,
+                                const double *Ts, int32_t rot_coord, double *pose_out, void *stream) {
+  DIM_REQUIRE(ctx && pose_src && se3 && Tm && Ts && pose_out, "dim_se3_compose: NULL argument");
+  DIM_REQUIRE(rot_coord >= 0 && rot_coord <= 2, "dim_se3_compose: unknown rot_coord");
+  return se3_compose_launch(pose_src, se3, B, Tm, Ts, rot_coord, pose_out, nullptr, (cudaStream_t)stream);
+}
+
+DIM_API int32_t dim_flow_fwd(dim_ctx *ctx, const float *ds, const float *dt, const float *KT, const float *Kinv,
+                             int32_t B, float *flow, float *valid, void *stream) {
+  DIM_REQUIRE(ctx && ds && dt && KT && Kinv && flow && valid, "dim_flow_fwd: NULL argument");
+  return flow_launch(ctx, ds, dt, KT, Kinv, B, flow, valid, (cudaStream_t)stream);
+}
+
+DIM_API int32_t dim_transform3d_fwd(dim_ctx *ctx, const float *pc, const float *rot, const float *tr,
+                                    const float *ps, int32_t B, int32_t N, const float *Tm, const float *Ts,
+                                    int32_t rot_coord, float *out, void *stream) {
+  DIM_REQUIRE(ctx && pc && rot && tr && ps && Tm && Ts && out, "dim_transform3d_fwd: NULL argument");
+  return transform3d_fwd_launch(pc, rot, tr, ps, B, N, Tm, Ts, rot_coord, out, (cudaStream_t)stream);
+}
+DIM_API int32_t dim_transform3d_bwd(dim_ctx *ctx, const float *og, const float *pc, const float *rot, const float *tr,
+                                    const float *ps, int32_t B, int32_t N, const float *Tm, const float *Ts,
+                                    int32_t rot_coord, float *rg, float *tg, void *stream) {
+  DIM_REQUIRE(ctx && og && pc && rot && tr && ps && Tm && Ts && rg && tg, "dim_transform3d_bwd: NULL argument");
+  return transform3d_bwd_launch(og, pc, rot, tr, ps, B, N, Tm, Ts, rot_coord, rg, tg, (cudaStream_t)stream);
+}
+
+DIM_API int32_t dim_net_load(dim_ctx *ctx, const float *const *W, const float *const *Bv) {
+  DIM_REQUIRE(ctx && W && Bv, "dim_net_load: NULL argument");
+  return net_load(ctx, W, Bv);
+}
+
+DIM_API int32_t dim_net_fwd(dim_ctx *ctx, const float *zio, const float *zir, const float *zmo, const float *zmr,
+                            int32_t B, int32_t precision, float *rot, float *trans, void *stream) {
+  DIM_REQUIRE(ctx && zio && zir && zmo && zmr && rot && trans, "dim_net_fwd: NULL argument");
+  DIM_REQUIRE(B >= 1 && B <= ctx->max_batch, "dim_net_fwd: batch exceeds max_batch");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rows, cols, pad; __nv_bfloat16 *hi, *lo;
+  net_input_geometry(ctx, &rows, &cols, &pad, &hi, &lo);
+  if (int rc = pack_nhwc8_launch(ctx, zio, zir, zmo, zmr, B, rows, cols, pad, hi,
+                                 precision == DIM_PREC_BF16X3 ? lo : nullptr, st))
+    return rc;
+  return net_forward(ctx, B, precision, nullptr, rot, trans, nullptr, st);
+}
+
+DIM_API int32_t dim_transform_image_u8(dim_ctx *ctx, const uint8_t *bgr, int32_t B, const double *means, float *image,
+                                       void *stream) {
+  DIM_REQUIRE(ctx && bgr && means && image, "dim_transform_image_u8: NULL argument");
+  return transform_u8_launch(ctx, bgr, B, means, image, (cudaStream_t)stream);
+}
+
+DIM_API int32_t dim_refine(dim_ctx *ctx, const float *image_observed, const int32_t *cls_idx, const double *pose_init,
+                           int32_t B, int32_t n_iter, const float *K9, float zn, float zf, const double *means,
+                           int32_t precision, const double *pose_override, double *poses, float *se3,
+                           float *zoom_factor, int32_t *bbox, void *stream) {
+  DIM_REQUIRE(ctx && image_observed && cls_idx && pose_init && K9 && means && poses, "dim_refine: NULL argument");
+  DIM_REQUIRE(B >= 1 && B <= ctx->max_batch, "dim_refine: batch exceeds max_batch");
+  DIM_REQUIRE(n_iter >= 1, "dim_refine: n_iter must be >= 1");
+  cudaStream_t st = (cudaStream_t)stream;
+  const double Tm[3] = {0, 0, 0}, Ts[3] = {1, 1, 1};  // trans_means / trans_stds of the shipped config
+  const float means_f[3] = {(float)means[0], (float)means[1], (float)means[2]};
+  int rows, cols, pad; __nv_bfloat16 *hi, *lo;
+  net_input_geometry(ctx, &rows, &cols, &pad, &hi, &lo);
+  const double *pose_src = pose_init;
+  for (int it = 0; it < n_iter; ++it) {
+    if (pose_override) pose_src = pose_override + (size_t)it * B * 12;
+    // src_pose blob is float32 (nd.array), the host pose stays float64 (tester.py:391)
+    if (int rc = f64_to_f32_launch(pose_src, ctx->pose_cur_f32, B * 12, st)) return rc;
+    // render at the current pose (tester.py:427-442); mask_observed := box(mask_rendered) is analytic
+    if (int rc = render_launch(ctx, cls_idx, ctx->pose_cur_f32, B, K9, zn, zf, means, 1, ctx->image_rendered, nullptr,
+                               ctx->mask_rendered, nullptr, nullptr, st))
+      return rc;
+    float *zf_it = zoom_factor ? zoom_factor + (size_t)it * B * 4 : ctx->zoom_factor;
+    int *bbox_it = bbox ? bbox + (size_t)it * B * 8 : nullptr;
+    if (int rc = zoom_factor_from_ren_launch(ctx, ctx->bbox_ren, ctx->pose_cur_f32, B, K9, zf_it, bbox_it, ctx->status, st))
+      return rc;
+    if (int rc = zoom_fused_launch(ctx, image_observed, ctx->image_rendered, ctx->mask_rendered, zf_it, means_f, B,
+                                   rows, cols, pad, hi, precision == DIM_PREC_BF16X3 ? lo : nullptr, st))
+      return rc;
+    float *se3_it = se3 ? se3 + (size_t)it * B * 7 : ctx->se3_cur;
+    if (int rc = net_forward(ctx, B, precision, zf_it, nullptr, nullptr, se3_it, st)) return rc;
+    double *pose_out = poses + (size_t)it * B * 12;
+    if (int rc = se3_compose_launch(pose_src, se3_it, B, Tm, Ts, 1 /*CAMERA*/, pose_out, nullptr, st)) return rc;
+    pose_src = pose_out;
+  }
+  return 0;
+}
+
+DIM_API int32_t dim_refine_host(dim_ctx *ctx, const uint8_t *img_u8, const int32_t *cls_host, const double *pose_host,
+                                int32_t B, int32_t n_iter, const float *K9, float zn, float zf, const double *means,
+                                int32_t precision, double *poses_out, float *se3_out, void *stream) {
+  DIM_REQUIRE(ctx && img_u8 && cls_host && pose_host && K9 && means && poses_out, "dim_refine_host: NULL argument");
+  DIM_REQUIRE(B >= 1 && B <= ctx->max_batch, "dim_refine_host: batch exceeds max_batch");
+  DIM_REQUIRE(n_iter >= 1 && n_iter <= 8, "dim_refine_host: n_iter must be in [1,8]");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t P = (size_t)ctx->H * ctx->W;
+  DIM_CHECK(cudaMemcpyAsync(ctx->image_observed_u8, img_u8, (size_t)B * 3 * P, cudaMemcpyHostToDevice, st));
+  DIM_CHECK(cudaMemcpyAsync(ctx->cls_dev, cls_host, sizeof(int) * B, cudaMemcpyHostToDevice, st));
+  DIM_CHECK(cudaMemcpyAsync(ctx->pose_cur, pose_host, sizeof(double) * B * 12, cudaMemcpyHostToDevice, st));
+  if (int rc = transform_u8_launch(ctx, ctx->image_observed_u8, B, means, ctx->image_observed_f32, st)) return rc;
+  if (int rc = dim_refine(ctx, ctx->image_observed_f32, ctx->cls_dev, ctx->pose_cur, B, n_iter, K9, zn, zf, means,
+                          precision, nullptr, ctx->poses_dev, ctx->se3_hist_dev, nullptr, nullptr, stream))
+    return rc;
+  DIM_CHECK(cudaMemcpyAsync(poses_out, ctx->poses_dev, sizeof(double) * (size_t)n_iter * B * 12, cudaMemcpyDeviceToHost, st));
+  if (se3_out)
+    DIM_CHECK(cudaMemcpyAsync(se3_out, ctx->se3_hist_dev, sizeof(float) * (size_t)n_iter * B * 7, cudaMemcpyDeviceToHost, st));
+  DIM_CHECK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ---- test hooks (not part of the drop-in surface; used by tests/ to look inside the conv tower)
+DIM_API int32_t dim_debug_activation(dim_ctx *ctx, int32_t idx, int32_t lo, void *host_dst, uint64_t bytes) {
+  return net_debug_activation(ctx, idx, lo, host_dst, (size_t)bytes);
+}
+DIM_API int32_t dim_debug_layer_geometry(dim_ctx *ctx, int32_t idx, int32_t *out8) {
+  DIM_REQUIRE(ctx && out8 && idx >= 0 && idx <= 10, "dim_debug_layer_geometry: bad argument");
+  net_layer_geometry(ctx, idx, out8);
+  return 0;
+}
+
+}  // extern "C"

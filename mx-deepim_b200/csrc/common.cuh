@@ -1,0 +1,103 @@
+// common.cuh -- context, error handling and launch bookkeeping shared by all translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/deepim_b200.h"
+
+namespace dim {
+
+void set_error(const char *fmt, ...);
+extern long long g_launches;
+
+#define DIM_CHECK(expr)                                                                  \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      dim::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return 1;                                                                          \
+    }                                                                                    \
+  } while (0)
+
+#define DIM_LAUNCH_CHECK()                                                               \
+  do {                                                                                   \
+    ++dim::g_launches;                                                                   \
+    cudaError_t _e = cudaGetLastError();                                                 \
+    if (_e != cudaSuccess) {                                                             \
+      dim::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return 1;                                                                          \
+    }                                                                                    \
+  } while (0)
+
+#define DIM_REQUIRE(cond, msg)                                        \
+  do {                                                                \
+    if (!(cond)) {                                                    \
+      dim::set_error("%s:%d: %s", __FILE__, __LINE__, msg);           \
+      return 2;                                                       \
+    }                                                                 \
+  } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------------- rasteriser
+struct PVert {  // projected vertex, 24 B
+  int X, Y;     // 24.8 fixed-point screen position
+  float iz;     // 1/Zc
+  float uz, vz; // u/Zc, v/Zc
+  int ok;
+};
+
+struct MeshDev {
+  const float *verts;   // [V,3]
+  const float *uvs;     // [V,2]
+  const int *faces;     // [F,3]
+  const uint8_t *tex;   // [Th,Tw,3]
+  int V, F, Th, Tw;
+};
+
+// ------------------------------------------------------------------------------------ network
+struct ConvLayer {
+  int Cin, Cout, k, stride, pad;
+  int Hin, Win, Hout, Wout;
+  // padded NHWC input buffer geometry (see conv.cu)
+  int Hp, Wp, py, px;
+};
+
+struct NetState;  // conv.cu
+
+}  // namespace dim
+
+struct dim_ctx {
+  int device = 0, max_batch = 0, H = 0, W = 0, max_classes = 0, max_verts = 0, max_faces = 0;
+  int num_sms = 148;
+  // meshes
+  std::vector<dim::MeshDev> meshes_host;
+  dim::MeshDev *meshes = nullptr;  // device table [max_classes]
+  std::vector<void *> owned;       // device allocations to free
+  // raster scratch
+  dim::PVert *pverts = nullptr;          // [max_batch, max_verts]
+  unsigned long long *vis = nullptr;     // [max_batch, H*W]
+  int *vbox = nullptr;                   // [max_batch,4] screen bbox of projected vertices
+  float *colour_lut = nullptr;           // [2][3][256]: trunc / no-trunc, RGB - mean
+  double lut_means[3] = {-1, -1, -1};
+  // zoom scratch
+  int *bbox8 = nullptr;      // [max_batch, 8]
+  int *status = nullptr;     // [max_batch]
+  float *zoom_factor = nullptr;  // [max_batch,4]
+  // refine-loop state
+  float *image_rendered = nullptr, *depth_rendered = nullptr, *mask_rendered = nullptr;
+  int *bbox_ren = nullptr;   // [max_batch,4]
+  double *pose_cur = nullptr;  // [max_batch,3,4]
+  float *pose_cur_f32 = nullptr;
+  float *se3_cur = nullptr;  // [max_batch,7]
+  float *image_observed_f32 = nullptr;  // for dim_refine_host
+  uint8_t *image_observed_u8 = nullptr;
+  int *cls_dev = nullptr;
+  double *poses_dev = nullptr;  // [8, max_batch, 12]
+  float *se3_hist_dev = nullptr;
+  dim::NetState *net = nullptr;
+};

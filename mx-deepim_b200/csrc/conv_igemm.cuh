@@ -1,0 +1,341 @@
+// conv_igemm.cuh -- implicit-GEMM convolution on 5th-gen tensor cores (tcgen05.mma, accumulators in
+// TMEM) fed by TMA (cp.async.bulk.tensor) through an mbarrier ring.  sm_100a only.
+//
+// Replaces the cuDNN Convolution + LeakyReLU(0.1) pairs of the FlowNetS tower
+// (deepim/symbols/deepIM_flownet.py:63-107).
+//
+// Data layout (DESIGN.md "HBM layout"): activations are NHWC bf16 in buffers that carry the
+// convolution's zero border physically ([B, Hp, Wp, C], interior at (py,px)) and images are stacked
+// along the row axis, so one 3-D tensor map (C, cols, B*rows) addresses every tap with in-bounds
+// coordinates.  For a stride-2 layer the buffer is read through four parity views (row parity,
+// col parity): tap (kh,kw) = (2dh+ph, 2dw+pw) of output pixel (g,ow) is element (g+dh, ow+dw) of view
+// (ph,pw).  An M tile is a BW x BH rectangle of output pixels (BW*BH <= 128), i.e. exactly one TMA
+// box per tap, landing in shared memory as the K-major 128B/64B-swizzled operand tile UMMA expects.
+// Weights are [Cout][kh][kw][Cin] bf16 (K-major), one 2-D tensor map.
+//
+// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer
+// (one lane), warps 2..5 = epilogue (TMEM -> registers -> bias + LeakyReLU -> bf16 NHWC stores into
+// the next layer's bordered buffer, or fp32 split-K partials).
+//
+// SPLIT3 = bf16x3 precision mode: operands are hi/lo bf16 pairs (x = hi + lo); each K step issues
+// hi*hi + lo*hi + hi*lo into the same fp32 accumulator (error ~2^-16 relative, near-fp32).
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+
+namespace dim {
+
+struct ConvKParams {
+  CUtensorMap a_map[4];     // activation views (hi); [0] only for stride 1
+  CUtensorMap a_lo_map[4];  // activation views (lo), SPLIT3 only
+  CUtensorMap b_map;        // weights hi
+  CUtensorMap b_lo_map;     // weights lo
+  int KH, KW, stride, cchunks;  // taps and channel chunks (Cin_eff / BLOCK_K)
+  int BW, BH, n_col_tiles;
+  int Hq, Ho, Wo, Bn;           // virtual rows per image, valid output extent, batch
+  int out_Hp, out_Wp, out_py, out_px, Cout;
+  int kblocks, ksplit;
+  uint32_t idesc;
+  float slope;
+  const float *bias;
+  __nv_bfloat16 *out_hi, *out_lo;
+  float *partial;  // [ksplit][Bn*Ho*Wo][Cout] when ksplit > 1
+};
+
+namespace ptx {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)m) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+          "r"(smem_u32(dst)),
+      "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+// --- TMEM
+__device__ __forceinline__ void tmem_alloc(uint32_t *slot_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_smem)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32, issued by ONE thread
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+// arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (lane i of the warp's quadrant)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t *r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major swizzled operand descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp): start>>4 in
+// [0,14), LBO [16,30) (unused for swizzled K-major, set 1), SBO>>4 in [32,46) = 8 rows * row bytes,
+// version 1 at [46,48), layout type at [61,64) (2 = SWIZZLE_128B, 4 = SWIZZLE_64B).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+
+}  // namespace ptx
+
+template <int BLOCK_N, int BLOCK_K, int STAGES, bool SPLIT3>
+struct ConvSmem {
+  static constexpr int A_BYTES = 128 * BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (SPLIT3 ? 2 : 1);
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BLOCK_N, int BLOCK_K, int STAGES, bool SPLIT3>
+__global__ void __launch_bounds__(192) conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
+  using S = ConvSmem<BLOCK_N, BLOCK_K, STAGES, SPLIT3>;
+  constexpr uint32_t LAYOUT = (BLOCK_K == 64) ? 2u : 4u;  // SWIZZLE_128B : SWIZZLE_64B
+  constexpr uint32_t SBO = 8u * BLOCK_K * 2u;
+  constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES * S::STAGE_BYTES);
+  uint64_t *empty_bar = full_bar + STAGES;
+  uint64_t *tmem_full_bar = empty_bar + STAGES;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col_tile = blockIdx.x % p.n_col_tiles, row_tile = blockIdx.x / p.n_col_tiles;
+  const int g0 = row_tile * p.BH, ow0 = col_tile * p.BW;
+  const int n0 = blockIdx.y * BLOCK_N;
+  const int kb_per = (p.kblocks + p.ksplit - 1) / p.ksplit;
+  const int kb0 = blockIdx.z * kb_per;
+  const int kb1 = min(p.kblocks, kb0 + kb_per);
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::fence_barrier_init();
+    ptx::prefetch_tmap(&p.b_map);
+    ptx::prefetch_tmap(&p.a_map[0]);
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const uint32_t tx = (uint32_t)(p.BW * p.BH * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) * (SPLIT3 ? 2u : 1u);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
+        const int tap = kb / p.cchunks, cc = kb - tap * p.cchunks;
+        const int kh = tap / p.KW, kw = tap - kh * p.KW;
+        int view = 0, dr = kh, dc = kw;
+        if (p.stride == 2) {
+          view = ((kh & 1) << 1) | (kw & 1);
+          dr = kh >> 1;
+          dc = kw >> 1;
+        }
+        uint8_t *st = smem + s * S::STAGE_BYTES;
+        ptx::mbar_expect_tx(&full_bar[s], tx);
+        ptx::tma_load_3d(st, &p.a_map[view], &full_bar[s], cc * BLOCK_K, ow0 + dc, g0 + dr);
+        ptx::tma_load_2d(st + S::A_BYTES, &p.b_map, &full_bar[s], kb * BLOCK_K, n0);
+        if (SPLIT3) {
+          ptx::tma_load_3d(st + S::A_BYTES + S::B_BYTES, &p.a_lo_map[view], &full_bar[s], cc * BLOCK_K, ow0 + dc,
+                           g0 + dr);
+          ptx::tma_load_2d(st + 2 * S::A_BYTES + S::B_BYTES, &p.b_lo_map, &full_bar[s], kb * BLOCK_K, n0);
+        }
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        ptx::mbar_wait(&full_bar[s], ph);
+        ptx::tc_fence_after();
+        const uint32_t a_hi = ptx::smem_u32(smem + s * S::STAGE_BYTES);
+        const uint32_t b_hi = a_hi + S::A_BYTES;
+        const uint32_t a_lo = b_hi + S::B_BYTES;
+        const uint32_t b_lo = a_lo + S::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / 16; ++k) {
+          const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
+          const uint64_t da = ptx::umma_desc(a_hi + k * 32, SBO, LAYOUT);
+          const uint64_t db = ptx::umma_desc(b_hi + k * 32, SBO, LAYOUT);
+          ptx::umma_f16(tmem_base, da, db, p.idesc, acc);
+          if (SPLIT3) {
+            const uint64_t dal = ptx::umma_desc(a_lo + k * 32, SBO, LAYOUT);
+            const uint64_t dbl = ptx::umma_desc(b_lo + k * 32, SBO, LAYOUT);
+            ptx::umma_f16(tmem_base, dal, db, p.idesc, 1u);
+            ptx::umma_f16(tmem_base, da, dbl, p.idesc, 1u);
+          }
+        }
+        ptx::umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
+      }
+      ptx::umma_commit(tmem_full_bar);  // accumulator complete
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) are visible to this warp
+    const int m = quad * 32 + lane;
+    const int bh = m / p.BW, bw = m - bh * p.BW;
+    const int g = g0 + bh, ow = ow0 + bw;
+    const int n_img = g / p.Hq, oh = g - n_img * p.Hq;
+    const bool valid = (m < p.BW * p.BH) && (n_img < p.Bn) && (oh < p.Ho) && (ow < p.Wo);
+    ptx::mbar_wait(tmem_full_bar, 0);
+    ptx::tc_fence_after();
+    const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
+    if (p.ksplit > 1) {
+      const size_t opix = ((size_t)n_img * p.Ho + oh) * p.Wo + ow;
+      float *dst = p.partial + ((size_t)blockIdx.z * ((size_t)p.Bn * p.Ho * p.Wo) + opix) * p.Cout + n0;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(trow + c, r);
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<uint4 *>(dst + c + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+        }
+      }
+    } else {
+      const size_t pix = ((size_t)n_img * p.out_Hp + oh + p.out_py) * p.out_Wp + ow + p.out_px;
+      __nv_bfloat16 *dhi = p.out_hi + pix * p.Cout + n0;
+      __nv_bfloat16 *dlo = SPLIT3 ? (p.out_lo + pix * p.Cout + n0) : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(trow + c, r);
+        if (valid) {
+          __align__(16) __nv_bfloat16 h[32];
+          __align__(16) __nv_bfloat16 l[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float v = __uint_as_float(r[j]) + __ldg(p.bias + n0 + c + j);
+            v = v > 0.f ? v : v * p.slope;
+            h[j] = __float2bfloat16_rn(v);
+            if (SPLIT3) l[j] = __float2bfloat16_rn(v - __bfloat162float(h[j]));
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            *reinterpret_cast<uint4 *>(dhi + c + j) = *reinterpret_cast<const uint4 *>(h + j);
+            if (SPLIT3) *reinterpret_cast<uint4 *>(dlo + c + j) = *reinterpret_cast<const uint4 *>(l + j);
+          }
+        }
+      }
+    }
+    ptx::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// split-K finalize: sum partials + bias + LeakyReLU -> bf16 (hi[, lo]) into the bordered NHWC buffer
+__global__ void __launch_bounds__(256) conv_splitk_finalize_kernel(const float *partial, int ksplit, int npix,
+                                                                   int Cout, int Ho, int Wo, int out_Hp, int out_Wp,
+                                                                   int out_py, int out_px, const float *bias,
+                                                                   float slope, __nv_bfloat16 *out_hi,
+                                                                   __nv_bfloat16 *out_lo) {
+  const size_t idx4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (idx4 >= (size_t)npix * Cout) return;
+  const size_t opix = idx4 / Cout;
+  const int c = (int)(idx4 - opix * Cout);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int z = 0; z < ksplit; ++z) {
+    const float4 v = *reinterpret_cast<const float4 *>(partial + (size_t)z * npix * Cout + idx4);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  float v[4] = {acc.x + bias[c], acc.y + bias[c + 1], acc.z + bias[c + 2], acc.w + bias[c + 3]};
+  const int n_img = (int)(opix / ((size_t)Ho * Wo));
+  const int rem = (int)(opix - (size_t)n_img * Ho * Wo);
+  const int oh = rem / Wo, ow = rem - oh * Wo;
+  const size_t pix = ((size_t)n_img * out_Hp + oh + out_py) * out_Wp + ow + out_px;
+  __align__(8) __nv_bfloat16 h[4];
+  __align__(8) __nv_bfloat16 l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float x = v[j] > 0.f ? v[j] : v[j] * slope;
+    h[j] = __float2bfloat16_rn(x);
+    l[j] = __float2bfloat16_rn(x - __bfloat162float(h[j]));
+  }
+  *reinterpret_cast<uint2 *>(out_hi + pix * Cout + c) = *reinterpret_cast<const uint2 *>(h);
+  if (out_lo) *reinterpret_cast<uint2 *>(out_lo + pix * Cout + c) = *reinterpret_cast<const uint2 *>(l);
+}
+
+}  // namespace dim

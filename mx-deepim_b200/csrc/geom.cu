@@ -1,0 +1,372 @@
+// geom.cu -- small geometry kernels (compiled with -fmad=false):
+//   reprojection-flow labels   lib/flow_c/gpu_flow_kernel.cu:32-69 (flow_kernel) -- the reference's
+//                              only native kernel; its host wrapper (l.87-147) does 6 cudaMalloc +
+//                              4 H2D + 2 D2H + 6 cudaFree per call, here inputs/outputs stay resident
+//   SE(3) compose (float64)    lib/pair_matching/RT_transform.py:127-151 (+ quat2mat l.383-429)
+//   ZoomTrans fwd/bwd          deepim/operator_py/zoom_trans.py:22-74
+//   Transform3D fwd/bwd        deepim/operator_py/transform3d.py:34-281
+//   image transform            lib/utils/image.py:583-594
+#include "common.cuh"
+
+namespace dim {
+
+// ------------------------------------------------------------------------------------------ flow
+// HBM-bound: reads depth_src (4 B/px) + a gathered depth_tgt (4 B/px), writes flow (8 B/px) +
+// valid (4 B/px) = 20 B/px algorithmic (6 144 000 B per 480x640 instance).
+__global__ void __launch_bounds__(256) flow_kernel(const float *__restrict__ depth_src,
+                                                   const float *__restrict__ depth_tgt,
+                                                   const float *__restrict__ KT, float i0, float i1, float i2,
+                                                   float i3, float i4, float i5, int H, int W,
+                                                   float *__restrict__ flow, float *__restrict__ valid) {
+  const int b = blockIdx.y;
+  const int q4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (q4 >= H * W) return;
+  const int h = q4 / W, w0 = q4 % W;
+  const size_t P = (size_t)H * W;
+  const float *kt = KT + 12 * b;
+  const float k0 = kt[0], k1 = kt[1], k2 = kt[2], k3 = kt[3], k4 = kt[4], k5 = kt[5], k6 = kt[6], k7 = kt[7],
+              k8 = kt[8], k9 = kt[9], k10 = kt[10], k11 = kt[11];
+  const float4 d4 = *reinterpret_cast<const float4 *>(depth_src + (size_t)b * P + q4);
+  const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+  float fh[4], fw[4], ok[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int w = w0 + k;
+    const float d = dd[k];
+    const float x = (((float)w * i0 + (float)h * i1) + i2) * d;
+    const float y = (((float)w * i3 + (float)h * i4) + i5) * d;
+    const float z = d;
+    fh[k] = 0.f; fw[k] = 0.f; ok[k] = 0.f;
+    if (d > 1e-3f) {
+      const float xp = ((x * k0 + y * k1) + z * k2) + k3;
+      const float yp = ((x * k4 + y * k5) + z * k6) + k7;
+      const float zp = (((x * k8 + y * k9) + z * k10) + k11) + 1e-15f;
+      const float wp = xp / zp, hp = yp / zp;
+      if (wp >= 0.f && wp <= (float)(W - 1) && hp >= 0.f && hp <= (float)(H - 1)) {
+        const int wi = (int)roundf(wp), hi = (int)roundf(hp);
+        const float dt = __ldg(depth_tgt + (size_t)b * P + (size_t)hi * W + wi);
+        if (fabsf(zp - dt) < 3e-3f) {
+          fh[k] = hp - (float)h;
+          fw[k] = wp - (float)w;
+          ok[k] = 1.f;
+        }
+      }
+    }
+  }
+  *reinterpret_cast<float4 *>(flow + ((size_t)b * 2 + 0) * P + q4) = make_float4(fh[0], fh[1], fh[2], fh[3]);
+  *reinterpret_cast<float4 *>(flow + ((size_t)b * 2 + 1) * P + q4) = make_float4(fw[0], fw[1], fw[2], fw[3]);
+  *reinterpret_cast<float4 *>(valid + (size_t)b * P + q4) = make_float4(ok[0], ok[1], ok[2], ok[3]);
+}
+
+int flow_launch(dim_ctx *ctx, const float *depth_src, const float *depth_tgt, const float *KT, const float *Kinv,
+                int B, float *flow, float *valid, cudaStream_t st) {
+  DIM_REQUIRE((ctx->W & 3) == 0, "width must be a multiple of 4");
+  flow_kernel<<<dim3(cdiv(ctx->H * ctx->W / 4, 256), B), 256, 0, st>>>(depth_src, depth_tgt, KT, Kinv[0], Kinv[1],
+                                                                        Kinv[2], Kinv[3], Kinv[4], Kinv[5], ctx->H,
+                                                                        ctx->W, flow, valid);
+  DIM_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------- se3
+__device__ __forceinline__ void quat2mat_f64(const double *q, double *M) {
+  const double w = q[0], x = q[1], y = q[2], z = q[3];
+  const double Nq = w * w + x * x + y * y + z * z;
+  if (Nq < 2.220446049250313e-16 * 4.0) {  // _FLOAT_EPS (RT_transform.py:236-238)
+    M[0] = M[4] = M[8] = 1.0;
+    M[1] = M[2] = M[3] = M[5] = M[6] = M[7] = 0.0;
+    return;
+  }
+  const double s = 2.0 / Nq;
+  const double X = x * s, Y = y * s, Z = z * s;
+  const double wX = w * X, wY = w * Y, wZ = w * Z, xX = x * X, xY = x * Y, xZ = x * Z, yY = y * Y, yZ = y * Z,
+               zZ = z * Z;
+  M[0] = 1.0 - (yY + zZ); M[1] = xY - wZ;         M[2] = xZ + wY;
+  M[3] = xY + wZ;         M[4] = 1.0 - (xX + zZ); M[5] = yZ - wX;
+  M[6] = xZ - wY;         M[7] = yZ + wX;         M[8] = 1.0 - (xX + yY);
+}
+
+__device__ void rt_transform_f64(const double *ps, const double *quat, const double *td, const double *Tm,
+                                 const double *Ts, int rot_coord, double *po) {
+  const double n = sqrt(quat[0] * quat[0] + quat[1] * quat[1] + quat[2] * quat[2] + quat[3] * quat[3]);
+  const double q[4] = {quat[0] / n, quat[1] / n, quat[2] / n, quat[3] / n};
+  double Rd[9];
+  quat2mat_f64(q, Rd);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double acc = 0.0;
+      for (int k = 0; k < 3; ++k)
+        acc += (rot_coord == 0) ? ps[i * 4 + k] * Rd[k * 3 + j] : Rd[i * 3 + k] * ps[k * 4 + j];
+      po[i * 4 + j] = acc;
+    }
+  const double d0 = td[0] * Ts[0] + Tm[0], d1 = td[1] * Ts[1] + Tm[1], d2 = td[2] * Ts[2] + Tm[2];
+  const double sx = ps[3], sy = ps[7], sz = ps[11];
+  const double z2 = sz / exp(d2);
+  po[11] = z2;
+  if (rot_coord == 2) {
+    po[3] = sz * d0 + sx;
+    po[7] = sz * d1 + sy;
+  } else {
+    po[3] = z2 * (d0 + sx / sz);
+    po[7] = z2 * (d1 + sy / sz);
+  }
+}
+
+__global__ void se3_compose_kernel(const double *pose_src, const float *se3, int B, double m0, double m1, double m2,
+                                   double s0, double s1, double s2, int rot_coord, double *pose_out,
+                                   float *pose_out_f32) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double ps[12], po[12];
+  for (int k = 0; k < 12; ++k) ps[k] = pose_src[12 * b + k];
+  const double quat[4] = {(double)se3[7 * b], (double)se3[7 * b + 1], (double)se3[7 * b + 2], (double)se3[7 * b + 3]};
+  const double td[3] = {(double)se3[7 * b + 4], (double)se3[7 * b + 5], (double)se3[7 * b + 6]};
+  const double Tm[3] = {m0, m1, m2}, Ts[3] = {s0, s1, s2};
+  rt_transform_f64(ps, quat, td, Tm, Ts, rot_coord, po);
+  for (int k = 0; k < 12; ++k) {
+    pose_out[12 * b + k] = po[k];
+    if (pose_out_f32) pose_out_f32[12 * b + k] = (float)po[k];
+  }
+}
+
+int se3_compose_launch(const double *pose_src, const float *se3, int B, const double *Tm, const double *Ts,
+                       int rot_coord, double *pose_out, float *pose_out_f32, cudaStream_t st) {
+  se3_compose_kernel<<<cdiv(B, 64), 64, 0, st>>>(pose_src, se3, B, Tm[0], Tm[1], Tm[2], Ts[0], Ts[1], Ts[2],
+                                                  rot_coord, pose_out, pose_out_f32);
+  DIM_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void f64_to_f32_kernel(const double *a, float *b, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) b[i] = (float)a[i];
+}
+int f64_to_f32_launch(const double *a, float *b, int n, cudaStream_t st) {
+  f64_to_f32_kernel<<<cdiv(n, 256), 256, 0, st>>>(a, b, n);
+  DIM_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ ZoomTrans
+__global__ void zoom_trans_kernel(const float *zoom_factor, const float *in, int B, int mul, int scale_xy,
+                                  float *out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float w = zoom_factor[4 * b];
+  const float x = in[3 * b], y = in[3 * b + 1], z = in[3 * b + 2];
+  out[3 * b + 0] = scale_xy ? (mul ? x * w : x / w) : x;
+  out[3 * b + 1] = scale_xy ? (mul ? y * w : y / w) : y;
+  out[3 * b + 2] = z;
+}
+int zoom_trans_launch(const float *zoom_factor, const float *in, int B, int mul, int scale_xy, float *out,
+                      cudaStream_t st) {
+  zoom_trans_kernel<<<cdiv(B, 64), 64, 0, st>>>(zoom_factor, in, B, mul, scale_xy, out);
+  DIM_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------- Transform3D
+// quat2mat_forward (transform3d.py:185-212): identity unless |Nq-1| < 1e-2; float32 inputs, the
+// python arithmetic promotes to float64, result stored float32.
+__device__ __forceinline__ void quat2mat_fwd_t3d(const float *q, float *M) {
+  const float w = q[0], x = q[1], y = q[2], z = q[3];
+  const float Nq = w * w + x * x + y * y + z * z;
+  const double dn = (double)Nq - 1.0;
+  if (!(-1e-2 < dn && dn < 1e-2)) {
+    M[0] = M[4] = M[8] = 1.f;
+    M[1] = M[2] = M[3] = M[5] = M[6] = M[7] = 0.f;
+    return;
+  }
+  const double s = 2.0 / (double)Nq;
+  const double X = x * s, Y = y * s, Z = z * s;
+  const double wX = w * X, wY = w * Y, wZ = w * Z, xX = x * X, xY = x * Y, xZ = x * Z, yY = y * Y, yZ = y * Z,
+               zZ = z * Z;
+  M[0] = (float)(1.0 - (yY + zZ)); M[1] = (float)(xY - wZ);         M[2] = (float)(xZ + wY);
+  M[3] = (float)(xY + wZ);         M[4] = (float)(1.0 - (xX + zZ)); M[5] = (float)(yZ - wX);
+  M[6] = (float)(xZ - wY);         M[7] = (float)(yZ + wX);         M[8] = (float)(1.0 - (xX + yY));
+}
+
+struct T3DParams {
+  const float *points, *rotation, *translation, *pose_src;
+  int B, N, rot_coord;
+  float Tm[3], Ts[3];
+};
+
+__device__ __forceinline__ void t3d_pose(const T3DParams &p, int b, float *Rt, float *Tt, float *Rd_out) {
+  float Rd[9];
+  quat2mat_fwd_t3d(p.rotation + 4 * b, Rd);
+  const float *ps = p.pose_src + 12 * b;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      float acc = 0.f;
+      for (int k = 0; k < 3; ++k)
+        acc += (p.rot_coord == 0) ? ps[i * 4 + k] * Rd[k * 3 + j] : Rd[i * 3 + k] * ps[k * 4 + j];
+      Rt[i * 3 + j] = acc;
+    }
+  const float *td = p.translation + 3 * b;
+  const float d0 = td[0] * p.Ts[0] + p.Tm[0], d1 = td[1] * p.Ts[1] + p.Tm[1], d2 = td[2] * p.Ts[2] + p.Tm[2];
+  const float sx = ps[3], sy = ps[7], sz = ps[11];
+  const float z2 = sz / expf(d2);
+  Tt[2] = z2;
+  if (p.rot_coord == 2) {
+    Tt[0] = sz * d0 + sx;
+    Tt[1] = sz * d1 + sy;
+  } else {
+    Tt[0] = z2 * (d0 + sx / sz);
+    Tt[1] = z2 * (d1 + sy / sz);
+  }
+  if (Rd_out)
+    for (int k = 0; k < 9; ++k) Rd_out[k] = Rd[k];
+}
+
+__global__ void __launch_bounds__(256) transform3d_fwd_kernel(T3DParams p, float *out) {
+  const int b = blockIdx.y;
+  __shared__ float Rt[9], Tt[3];
+  if (threadIdx.x == 0) t3d_pose(p, b, Rt, Tt, nullptr);
+  __syncthreads();
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= p.N) return;
+  const float *pc = p.points + (size_t)b * 3 * p.N;
+  const float x = pc[n], y = pc[p.N + n], z = pc[2 * p.N + n];
+  float *o = out + (size_t)b * 3 * p.N;
+  o[n] = ((Rt[0] * x + Rt[1] * y) + Rt[2] * z) + Tt[0];
+  o[p.N + n] = ((Rt[3] * x + Rt[4] * y) + Rt[5] * z) + Tt[1];
+  o[2 * p.N + n] = ((Rt[6] * x + Rt[7] * y) + Rt[8] * z) + Tt[2];
+}
+
+// backward (transform3d.py:99-281): one block per instance reduces sum_n D (3) and D.P^T (3x3)
+__global__ void __launch_bounds__(256) transform3d_bwd_kernel(T3DParams p, const float *out_grad, float *rot_grad,
+                                                              float *trans_grad) {
+  const int b = blockIdx.x;
+  const float *D = out_grad + (size_t)b * 3 * p.N;
+  const float *pc = p.points + (size_t)b * 3 * p.N;
+  float acc[12];
+  for (int k = 0; k < 12; ++k) acc[k] = 0.f;
+  for (int n = threadIdx.x; n < p.N; n += blockDim.x) {
+    const float d[3] = {D[n], D[p.N + n], D[2 * p.N + n]};
+    const float q[3] = {pc[n], pc[p.N + n], pc[2 * p.N + n]};
+    for (int i = 0; i < 3; ++i) {
+      acc[i] += d[i];
+      for (int j = 0; j < 3; ++j) acc[3 + i * 3 + j] += d[i] * q[j];
+    }
+  }
+  __shared__ float red[12][8];
+  for (int k = 0; k < 12; ++k) {
+    float v = acc[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  float s[12];
+  for (int k = 0; k < 12; ++k) {
+    s[k] = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s[k] += red[k][w];
+  }
+  const float *Dt = s;       // T_tgt_diff (3)
+  const float *RtD = s + 3;  // Rm_tgt_diff (3x3)
+  const float *ps = p.pose_src + 12 * b;
+  // --- T_transform_backward (transform3d.py:153-183)
+  {
+    const float *td = p.translation + 3 * b;
+    const float d0 = td[0] * p.Ts[0] + p.Tm[0], d1 = td[1] * p.Ts[1] + p.Tm[1], d2 = td[2] * p.Ts[2] + p.Tm[2];
+    const float sx = ps[3], sy = ps[7], sz = ps[11];
+    const float z2 = sz / expf(d2);
+    float g0, g1, g2;
+    if (p.rot_coord == 2) {
+      g0 = Dt[0] * (p.Ts[0] * sz);
+      g1 = Dt[1] * (p.Ts[1] * sz);
+      g2 = Dt[2] * (-p.Ts[2] * z2);
+    } else {
+      g0 = Dt[0] * (p.Ts[0] * z2);
+      g1 = Dt[1] * (p.Ts[1] * z2);
+      const float share = -p.Ts[2] * z2;
+      g2 = Dt[0] * (share * (d0 + sx / sz)) + Dt[1] * (share * (d1 + sy / sz)) + Dt[2] * (-p.Ts[2] * z2);
+    }
+    trans_grad[3 * b] = g0; trans_grad[3 * b + 1] = g1; trans_grad[3 * b + 2] = g2;
+  }
+  // --- Rm_delta_diff: model: Rs^T . RtD ; camera: RtD . Rs^T  (l.127-131)
+  float Dm[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      float a = 0.f;
+      for (int k = 0; k < 3; ++k)
+        a += (p.rot_coord == 0) ? ps[k * 4 + i] * RtD[k * 3 + j] : RtD[i * 3 + k] * ps[j * 4 + k];
+      Dm[i * 3 + j] = a;
+    }
+  // --- quat2mat_backward (l.214-281): zero unless |Nq-1| < 1e-4
+  const float *q = p.rotation + 4 * b;
+  const float w = q[0], x = q[1], y = q[2], z = q[3];
+  const float Nq = w * w + x * x + y * y + z * z;
+  const double dn = (double)Nq - 1.0;
+  float *rg = rot_grad + 4 * b;
+  if (!(-1e-4 < dn && dn < 1e-4)) {
+    rg[0] = rg[1] = rg[2] = rg[3] = 0.f;
+    return;
+  }
+  const float Ns = sqrtf(Nq);
+  const float w_ = w / Ns, x_ = x / Ns, y_ = y / Ns, z_ = z / Ns;
+#define DD(i, j) ((double)Dm[(i)*3 + (j)])
+  double wd = -z_ * DD(0, 1) + y_ * DD(0, 2) + z_ * DD(1, 0) - x_ * DD(1, 2) - y_ * DD(2, 0) + x_ * DD(2, 1);
+  double xd = y_ * DD(0, 1) + z_ * DD(0, 2) + y_ * DD(1, 0) - 2 * x_ * DD(1, 1) - w_ * DD(1, 2) + z_ * DD(2, 0) +
+              w_ * DD(2, 1) - 2 * x_ * DD(2, 2);
+  double yd = -2 * y_ * DD(0, 0) + x_ * DD(0, 1) + w_ * DD(0, 2) + x_ * DD(1, 0) + z_ * DD(1, 2) - w_ * DD(2, 0) +
+              z_ * DD(2, 1) - 2 * y_ * DD(2, 2);
+  double zd = -2 * z_ * DD(0, 0) - w_ * DD(0, 1) + x_ * DD(0, 2) + w_ * DD(1, 0) - 2 * z_ * DD(1, 1) +
+              y_ * DD(1, 2) + x_ * DD(2, 0) + y_ * DD(2, 1);
+#undef DD
+  wd *= 2.0; xd *= 2.0; yd *= 2.0; zd *= 2.0;
+  const double Nsd = (double)Ns;
+  const double share = Nsd * Nsd * Nsd * (w * wd + x * xd + y * yd + z * zd);
+  rg[0] = (float)(Nsd * wd - w * share);
+  rg[1] = (float)(Nsd * xd - x * share);
+  rg[2] = (float)(Nsd * yd - y * share);
+  rg[3] = (float)(Nsd * zd - z * share);
+}
+
+static T3DParams make_t3d(const float *pc, const float *rot, const float *tr, const float *ps, int B, int N,
+                          const float *Tm, const float *Ts, int rot_coord) {
+  T3DParams p;
+  p.points = pc; p.rotation = rot; p.translation = tr; p.pose_src = ps; p.B = B; p.N = N; p.rot_coord = rot_coord;
+  for (int k = 0; k < 3; ++k) { p.Tm[k] = Tm[k]; p.Ts[k] = Ts[k]; }
+  return p;
+}
+
+int transform3d_fwd_launch(const float *pc, const float *rot, const float *tr, const float *ps, int B, int N,
+                           const float *Tm, const float *Ts, int rot_coord, float *out, cudaStream_t st) {
+  T3DParams p = make_t3d(pc, rot, tr, ps, B, N, Tm, Ts, rot_coord);
+  transform3d_fwd_kernel<<<dim3(cdiv(N, 256), B), 256, 0, st>>>(p, out);
+  DIM_LAUNCH_CHECK();
+  return 0;
+}
+int transform3d_bwd_launch(const float *og, const float *pc, const float *rot, const float *tr, const float *ps,
+                           int B, int N, const float *Tm, const float *Ts, int rot_coord, float *rot_grad,
+                           float *trans_grad, cudaStream_t st) {
+  T3DParams p = make_t3d(pc, rot, tr, ps, B, N, Tm, Ts, rot_coord);
+  transform3d_bwd_kernel<<<B, 256, 0, st>>>(p, og, rot_grad, trans_grad);
+  DIM_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ image transform
+// u8 BGR HWC -> f32 RGB-mean CHW (lib/utils/image.py:583-594; float64 subtract, float32 store)
+__global__ void __launch_bounds__(256) transform_u8_kernel(const uint8_t *bgr, int H, int W, double m0, double m1,
+                                                           double m2, float *out) {
+  const int b = blockIdx.y;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= H * W) return;
+  const size_t P = (size_t)H * W;
+  const uint8_t *px = bgr + ((size_t)b * P + q) * 3;
+  float *o = out + (size_t)b * 3 * P;
+  o[q] = (float)((double)px[2] - m0);
+  o[P + q] = (float)((double)px[1] - m1);
+  o[2 * P + q] = (float)((double)px[0] - m2);
+}
+int transform_u8_launch(dim_ctx *ctx, const uint8_t *bgr, int B, const double *means, float *out, cudaStream_t st) {
+  transform_u8_kernel<<<dim3(cdiv(ctx->H * ctx->W, 256), B), 256, 0, st>>>(bgr, ctx->H, ctx->W, means[0], means[1],
+                                                                            means[2], out);
+  DIM_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace dim

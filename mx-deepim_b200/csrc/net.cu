@@ -1,0 +1,522 @@
+// net.cu -- FlowNetS encoder + fc + heads on the device (deepim/symbols/deepIM_flownet.py:53-116 and
+// 716-726), weight repacking, tensor-map construction and layer scheduling.
+//
+//   conv tower : 10 x conv_igemm_kernel (tcgen05 + TMA, conv_igemm.cuh), split-K + finalize for the
+//                layers whose tile count cannot fill 148 SMs
+//   fc6        : 81920 -> 256, a pure weight stream (HBM-bound): split-K SIMT kernel, deterministic
+//                two-pass reduction (partials are reduced in fixed order by the head kernel)
+//   head       : fc6 reduce + bias + LeakyReLU -> fc7 -> LeakyReLU -> rot(4), trans(3) ->
+//                ZoomTrans^-1 (zoom_trans.py:30-31) -> se3 (B,7)
+#include <map>
+#include <mutex>
+
+#include "conv_igemm.cuh"
+
+namespace dim {
+
+// FlowNetS tower: name, Cout, Cin, k, stride, pad (deepIM_flownet.py:63-107)
+struct LayerSpec {
+  const char *name;
+  int Cout, Cin, k, stride, pad;
+};
+static const LayerSpec kLayers[10] = {
+    {"flow_conv1", 64, 8, 7, 2, 3},  {"conv2", 128, 64, 5, 2, 2},   {"conv3", 256, 128, 5, 2, 2},
+    {"conv3_1", 256, 256, 3, 1, 1},  {"conv4", 512, 256, 3, 2, 1},  {"conv4_1", 512, 512, 3, 1, 1},
+    {"conv5", 512, 512, 3, 2, 1},    {"conv5_1", 512, 512, 3, 1, 1}, {"conv6", 1024, 512, 3, 2, 1},
+    {"conv6_1", 1024, 1024, 3, 1, 1}};
+
+struct LayerGeom {
+  // logical
+  int Cin, Cout, k, stride, pad, Hin, Win, Ho, Wo;
+  // input buffer: [B, rows, cols, Cbuf] bf16 (conv1: space-to-depth, Cbuf = 32)
+  int rows, cols, Cbuf, py, px;  // py/px: where the producer writes pixel (0,0) (pre-s2d for conv1)
+  // implicit GEMM view
+  int KH, KW, stride_eff, Ceff, Hq;
+  int BLOCK_N, BLOCK_K, BW, BH, n_col_tiles, kblocks;
+};
+
+struct TensorMaps {
+  ConvKParams kp[10];
+  int ksplit[10];
+};
+
+struct NetState {
+  LayerGeom g[10];
+  __nv_bfloat16 *w_hi[10] = {}, *w_lo[10] = {};
+  float *bias[10] = {};
+  __nv_bfloat16 *act_hi[11] = {}, *act_lo[11] = {};  // act[i] = input of layer i, act[10] = fc6 input
+  size_t act_elems_per_image[11] = {};
+  // fc
+  __nv_bfloat16 *fc6_w_bf16 = nullptr;  // [256][81920] in (h,w,c) order
+  float *fc6_w_f32 = nullptr;
+  float *fc6_b = nullptr, *fc7_wT = nullptr, *fc7_b = nullptr, *rot_w = nullptr, *rot_b = nullptr,
+        *trans_w = nullptr, *trans_b = nullptr;
+  float *fc6_partial = nullptr;  // [FC6_SPLITS][max_batch][256]
+  float *conv_partial = nullptr;
+  size_t conv_partial_elems = 0;
+  bool loaded = false;
+  std::map<int, TensorMaps> maps;  // per batch size
+  int max_batch = 0, num_sms = 148;
+};
+
+static constexpr int FC6_K = 1024 * 8 * 10;
+static constexpr int FC6_KC = 512;
+static constexpr int FC6_SPLITS = FC6_K / FC6_KC;  // 160
+
+// --------------------------------------------------------------------------------- geometry
+static void build_geometry(NetState *ns, int H, int W) {
+  int h = H, w = W;
+  for (int i = 0; i < 10; ++i) {
+    const LayerSpec &s = kLayers[i];
+    LayerGeom &g = ns->g[i];
+    g.Cin = s.Cin; g.Cout = s.Cout; g.k = s.k; g.stride = s.stride; g.pad = s.pad;
+    g.Hin = h; g.Win = w;
+    g.Ho = (h + 2 * s.pad - s.k) / s.stride + 1;
+    g.Wo = (w + 2 * s.pad - s.k) / s.stride + 1;
+    int Hp = h + 2 * s.pad, Wp = w + 2 * s.pad;
+    if (s.stride == 2) { Hp += Hp & 1; Wp += Wp & 1; }
+    g.py = g.px = s.pad;
+    if (i == 0) {
+      // conv1 (Cin = 8, 7x7 s2): space-to-depth -> 4x4 stride-1 taps over 32 channels
+      g.rows = Hp / 2; g.cols = Wp / 2; g.Cbuf = 32;
+      g.KH = g.KW = 4; g.stride_eff = 1; g.Ceff = 32; g.Hq = g.rows;
+      g.BLOCK_K = 32; g.BLOCK_N = 64;
+    } else {
+      g.rows = Hp; g.cols = Wp; g.Cbuf = s.Cin;
+      g.KH = g.KW = s.k; g.stride_eff = s.stride; g.Ceff = s.Cin;
+      g.Hq = (s.stride == 2) ? Hp / 2 : Hp;
+      g.BLOCK_K = 64; g.BLOCK_N = 128;
+    }
+    // M tile: BW x BH rectangle of output pixels with BW | Wo and BW*BH <= 128.  Maximise the rows
+    // used; keep boxes at least 8 pixels wide (>= 1 KB contiguous per TMA row) when possible.
+    int best_bw = 0, best_score = -1;
+    for (int pass = 0; pass < 2 && best_bw == 0; ++pass)
+      for (int d = 1; d <= g.Wo && d <= 128; ++d) {
+        if (g.Wo % d) continue;
+        if (pass == 0 && d < 8) continue;
+        const int score = d * (128 / d) * 1000 + d;
+        if (score > best_score) { best_score = score; best_bw = d; }
+      }
+    g.BW = best_bw; g.BH = 128 / best_bw;
+    g.n_col_tiles = g.Wo / g.BW;
+    g.kblocks = g.KH * g.KW * (g.Ceff / g.BLOCK_K);
+    h = g.Ho; w = g.Wo;
+  }
+}
+
+static int choose_ksplit(const NetState *ns, const LayerGeom &g, int B) {
+  const int row_tiles = cdiv(B * g.Hq, g.BH);
+  const int ctas = row_tiles * g.n_col_tiles * (g.Cout / g.BLOCK_N);
+  const int target = 2 * ns->num_sms;
+  if (ctas >= target || g.kblocks < 16) return 1;
+  int ks = cdiv(target, ctas);
+  if (ks > 8) ks = 8;
+  while (ks > 1 && g.kblocks / ks < 8) --ks;
+  // every K slice must be non-empty (an empty slice would publish an unwritten accumulator)
+  while (ks > 1 && (ks - 1) * cdiv(g.kblocks, ks) >= g.kblocks) --ks;
+  return ks;
+}
+
+// --------------------------------------------------------------------------------- tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static int encode_map(CUtensorMap *m, void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
+                      const uint32_t *box, int block_k) {
+  EncodeTiledFn fn = get_encode();
+  DIM_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available (driver too old?)");
+  cuuint64_t gd[5]; cuuint64_t gs[5]; cuuint32_t bx[5]; cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i < rank - 1; ++i) gs[i] = strides_bytes[i];
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, gd, gs, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu %llu %llu box %u %u %u)", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0),
+              box[0], box[1], rank > 2 ? box[2] : 0);
+    return 3;
+  }
+  return 0;
+}
+
+static uint32_t make_idesc(int M, int N) {
+  // cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b_format BF16 (1) @7/@10, K-major both,
+  // n_dim = N>>3 @17, m_dim = M>>4 @24
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+static int build_maps(NetState *ns, int B, TensorMaps &tm) {
+  for (int i = 0; i < 10; ++i) {
+    const LayerGeom &g = ns->g[i];
+    ConvKParams &kp = tm.kp[i];
+    memset(&kp, 0, sizeof(kp));
+    for (int lo = 0; lo < 2; ++lo) {
+      __nv_bfloat16 *base = lo ? ns->act_lo[i] : ns->act_hi[i];
+      CUtensorMap *maps = lo ? kp.a_lo_map : kp.a_map;
+      const uint32_t box[3] = {(uint32_t)g.BLOCK_K, (uint32_t)g.BW, (uint32_t)g.BH};
+      if (g.stride_eff == 1) {
+        const uint64_t dims[3] = {(uint64_t)g.Cbuf, (uint64_t)g.cols, (uint64_t)B * g.rows};
+        const uint64_t str[2] = {(uint64_t)g.Cbuf * 2, (uint64_t)g.cols * g.Cbuf * 2};
+        if (int rc = encode_map(&maps[0], base, 3, dims, str, box, g.BLOCK_K)) return rc;
+        maps[1] = maps[2] = maps[3] = maps[0];
+      } else {
+        for (int ph = 0; ph < 2; ++ph)
+          for (int pw = 0; pw < 2; ++pw) {
+            const uint64_t dims[3] = {(uint64_t)g.Cbuf, (uint64_t)g.cols / 2, (uint64_t)B * g.rows / 2};
+            const uint64_t str[2] = {(uint64_t)2 * g.Cbuf * 2, (uint64_t)2 * g.cols * g.Cbuf * 2};
+            __nv_bfloat16 *vb = base + ((size_t)ph * g.cols + pw) * g.Cbuf;
+            if (int rc = encode_map(&maps[(ph << 1) | pw], vb, 3, dims, str, box, g.BLOCK_K)) return rc;
+          }
+      }
+    }
+    {
+      const uint64_t Ktot = (uint64_t)g.KH * g.KW * g.Ceff;
+      const uint64_t dims[2] = {Ktot, (uint64_t)g.Cout};
+      const uint64_t str[1] = {Ktot * 2};
+      const uint32_t box[2] = {(uint32_t)g.BLOCK_K, (uint32_t)g.BLOCK_N};
+      if (int rc = encode_map(&kp.b_map, ns->w_hi[i], 2, dims, str, box, g.BLOCK_K)) return rc;
+      if (int rc = encode_map(&kp.b_lo_map, ns->w_lo[i], 2, dims, str, box, g.BLOCK_K)) return rc;
+    }
+    kp.KH = g.KH; kp.KW = g.KW; kp.stride = g.stride_eff; kp.cchunks = g.Ceff / g.BLOCK_K;
+    kp.BW = g.BW; kp.BH = g.BH; kp.n_col_tiles = g.n_col_tiles;
+    kp.Hq = g.Hq; kp.Ho = g.Ho; kp.Wo = g.Wo; kp.Bn = B;
+    if (i < 9) {
+      const LayerGeom &nx = ns->g[i + 1];
+      kp.out_Hp = nx.rows; kp.out_Wp = nx.cols; kp.out_py = nx.py; kp.out_px = nx.px;
+    } else {
+      kp.out_Hp = g.Ho; kp.out_Wp = g.Wo; kp.out_py = 0; kp.out_px = 0;
+    }
+    kp.Cout = g.Cout;
+    kp.kblocks = g.kblocks;
+    kp.ksplit = tm.ksplit[i] = choose_ksplit(ns, g, B);
+    kp.idesc = make_idesc(128, g.BLOCK_N);
+    kp.slope = 0.1f;
+    kp.bias = ns->bias[i];
+    kp.out_hi = ns->act_hi[i + 1];
+    kp.out_lo = ns->act_lo[i + 1];
+    kp.partial = ns->conv_partial;
+  }
+  return 0;
+}
+
+// --------------------------------------------------------------------------------- fc6 + head
+// fc6 split-K: CTA s handles k in [s*KC, (s+1)*KC) for all 256 outputs and all B instances.
+// Weight stream (bf16: 42 MB, fp32: 84 MB) is read exactly once, coalesced along k.
+template <bool F32W>
+__global__ void __launch_bounds__(256) fc6_splitk_kernel(const __nv_bfloat16 *__restrict__ act_hi,
+                                                         const __nv_bfloat16 *__restrict__ act_lo,
+                                                         const __nv_bfloat16 *__restrict__ w_bf16,
+                                                         const float *__restrict__ w_f32, int B, int max_batch,
+                                                         float *__restrict__ partial) {
+  constexpr int MAXB = 16;
+  __shared__ float act_s[MAXB][FC6_KC + 4];
+  const int s = blockIdx.x, k0 = s * FC6_KC;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int b0 = 0; b0 < B; b0 += MAXB) {
+    const int nb = min(MAXB, B - b0);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < MAXB * FC6_KC; idx += blockDim.x) {
+      const int b = idx / FC6_KC, k = idx - b * FC6_KC;
+      float v = 0.f;
+      if (b < nb) {
+        const size_t o = (size_t)(b0 + b) * FC6_K + k0 + k;
+        v = __bfloat162float(act_hi[o]);
+        if (act_lo) v += __bfloat162float(act_lo[o]);
+      }
+      act_s[b][k] = v;
+    }
+    __syncthreads();
+    for (int j = warp; j < 256; j += 8) {
+      float acc[MAXB];
+#pragma unroll
+      for (int b = 0; b < MAXB; ++b) acc[b] = 0.f;
+#pragma unroll 4
+      for (int k = lane; k < FC6_KC; k += 32) {
+        const size_t wo = (size_t)j * FC6_K + k0 + k;
+        const float wv = F32W ? w_f32[wo] : __bfloat162float(w_bf16[wo]);
+#pragma unroll
+        for (int b = 0; b < MAXB; ++b) acc[b] = fmaf(wv, act_s[b][k], acc[b]);
+      }
+#pragma unroll
+      for (int b = 0; b < MAXB; ++b) {
+        float v = acc[b];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && b < nb) partial[((size_t)s * max_batch + b0 + b) * 256 + j] = v;
+      }
+    }
+  }
+}
+
+// one CTA per instance
+__global__ void __launch_bounds__(256) head_kernel(const float *__restrict__ partial, int max_batch,
+                                                   const float *__restrict__ fc6_b, const float *__restrict__ fc7_wT,
+                                                   const float *__restrict__ fc7_b, const float *__restrict__ rot_w,
+                                                   const float *__restrict__ rot_b, const float *__restrict__ trans_w,
+                                                   const float *__restrict__ trans_b,
+                                                   const float *__restrict__ zoom_factor /*nullable*/,
+                                                   float *__restrict__ rot_out, float *__restrict__ trans_out,
+                                                   float *__restrict__ se3_out) {
+  __shared__ float h6[256], h7[256], outv[8];
+  const int b = blockIdx.x, j = threadIdx.x;
+  float a = 0.f;
+  for (int s = 0; s < FC6_SPLITS; ++s) a += partial[((size_t)s * max_batch + b) * 256 + j];
+  a += fc6_b[j];
+  h6[j] = a > 0.f ? a : 0.1f * a;
+  __syncthreads();
+  float c = 0.f;
+  for (int k = 0; k < 256; ++k) c = fmaf(h6[k], fc7_wT[k * 256 + j], c);
+  c += fc7_b[j];
+  h7[j] = c > 0.f ? c : 0.1f * c;
+  __syncthreads();
+  const int warp = j >> 5, lane = j & 31;
+  if (warp < 7) {
+    const float *wrow = warp < 4 ? rot_w + warp * 256 : trans_w + (warp - 4) * 256;
+    float v = 0.f;
+    for (int k = lane; k < 256; k += 32) v = fmaf(h7[k], wrow[k], v);
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) outv[warp] = v + (warp < 4 ? rot_b[warp] : trans_b[warp - 4]);
+  }
+  __syncthreads();
+  if (j == 0) {
+    if (rot_out)
+      for (int k = 0; k < 4; ++k) rot_out[4 * b + k] = outv[k];
+    if (trans_out)
+      for (int k = 0; k < 3; ++k) trans_out[3 * b + k] = outv[4 + k];
+    if (se3_out) {
+      // invZoomTrans (zoom_trans.py:30-31, b_inv_zoom=True): wx for both axes
+      const float w = zoom_factor[4 * b];
+      for (int k = 0; k < 4; ++k) se3_out[7 * b + k] = outv[k];
+      se3_out[7 * b + 4] = outv[4] * w;
+      se3_out[7 * b + 5] = outv[5] * w;
+      se3_out[7 * b + 6] = outv[6];
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------- host API
+template <typename T>
+static int dev_alloc(dim_ctx *ctx, T **p, size_t n, bool zero) {
+  void *q = nullptr;
+  DIM_CHECK(cudaMalloc(&q, n * sizeof(T)));
+  if (zero) DIM_CHECK(cudaMemset(q, 0, n * sizeof(T)));
+  ctx->owned.push_back(q);
+  *p = reinterpret_cast<T *>(q);
+  return 0;
+}
+
+int net_create(dim_ctx *ctx) {
+  NetState *ns = new NetState();
+  ctx->net = ns;
+  ns->max_batch = ctx->max_batch;
+  ns->num_sms = ctx->num_sms;
+  build_geometry(ns, ctx->H, ctx->W);
+  for (int i = 0; i <= 10; ++i) {
+    size_t per;
+    if (i < 10) per = (size_t)ns->g[i].rows * ns->g[i].cols * ns->g[i].Cbuf;
+    else per = (size_t)ns->g[9].Ho * ns->g[9].Wo * ns->g[9].Cout;
+    ns->act_elems_per_image[i] = per;
+    // borders must be (and stay) zero: the epilogues only ever write interior pixels
+    if (int rc = dev_alloc(ctx, &ns->act_hi[i], per * ctx->max_batch, true)) return rc;
+    if (int rc = dev_alloc(ctx, &ns->act_lo[i], per * ctx->max_batch, true)) return rc;
+  }
+  DIM_REQUIRE(ns->act_elems_per_image[10] == (size_t)FC6_K, "fc6 input size mismatch (needs 480x640 input)");
+  size_t pmax = 0;
+  for (int B = 1; B <= ctx->max_batch; ++B)
+    for (int i = 0; i < 10; ++i) {
+      int ks = choose_ksplit(ns, ns->g[i], B);
+      if (ks > 1) {
+        size_t e = (size_t)ks * B * ns->g[i].Ho * ns->g[i].Wo * ns->g[i].Cout;
+        pmax = e > pmax ? e : pmax;
+      }
+    }
+  ns->conv_partial_elems = pmax;
+  if (pmax)
+    if (int rc = dev_alloc(ctx, &ns->conv_partial, pmax, false)) return rc;
+  if (int rc = dev_alloc(ctx, &ns->fc6_partial, (size_t)FC6_SPLITS * ctx->max_batch * 256, true)) return rc;
+  return 0;
+}
+
+void net_destroy(dim_ctx *ctx) {
+  delete ctx->net;
+  ctx->net = nullptr;
+}
+
+static void split_bf16(const float *src, size_t n, std::vector<__nv_bfloat16> &hi, std::vector<__nv_bfloat16> &lo) {
+  hi.resize(n);
+  lo.resize(n);
+  for (size_t i = 0; i < n; ++i) {
+    hi[i] = __float2bfloat16_rn(src[i]);
+    lo[i] = __float2bfloat16_rn(src[i] - __bfloat162float(hi[i]));
+  }
+}
+
+template <typename T>
+static int upload(dim_ctx *ctx, T **dst, const std::vector<T> &v) {
+  if (int rc = dev_alloc(ctx, dst, v.size(), false)) return rc;
+  DIM_CHECK(cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int net_load(dim_ctx *ctx, const float *const *W, const float *const *Bv) {
+  NetState *ns = ctx->net;
+  DIM_REQUIRE(ns != nullptr, "net not created");
+  DIM_REQUIRE(!ns->loaded, "dim_net_load: weights already loaded for this context");
+  for (int i = 0; i < 10; ++i) {
+    const LayerGeom &g = ns->g[i];
+    const size_t Ktot = (size_t)g.KH * g.KW * g.Ceff;
+    std::vector<float> packed((size_t)g.Cout * Ktot, 0.f);
+    const float *w = W[i];  // [Cout][Cin][k][k]
+    if (i == 0) {
+      // space-to-depth repack: W'[co][dh][dw][ph*16+pw*8+c] = W[co][c][2dh+ph][2dw+pw] (0 beyond 7x7)
+      for (int co = 0; co < g.Cout; ++co)
+        for (int dh = 0; dh < 4; ++dh)
+          for (int dw = 0; dw < 4; ++dw)
+            for (int ph = 0; ph < 2; ++ph)
+              for (int pw = 0; pw < 2; ++pw)
+                for (int c = 0; c < 8; ++c) {
+                  const int kh = 2 * dh + ph, kw = 2 * dw + pw;
+                  if (kh >= 7 || kw >= 7) continue;
+                  packed[(size_t)co * Ktot + (size_t)(dh * 4 + dw) * 32 + ph * 16 + pw * 8 + c] =
+                      w[(((size_t)co * 8 + c) * 7 + kh) * 7 + kw];
+                }
+    } else {
+      for (int co = 0; co < g.Cout; ++co)
+        for (int c = 0; c < g.Cin; ++c)
+          for (int kh = 0; kh < g.k; ++kh)
+            for (int kw = 0; kw < g.k; ++kw)
+              packed[(size_t)co * Ktot + (size_t)(kh * g.k + kw) * g.Cin + c] =
+                  w[(((size_t)co * g.Cin + c) * g.k + kh) * g.k + kw];
+    }
+    std::vector<__nv_bfloat16> hi, lo;
+    split_bf16(packed.data(), packed.size(), hi, lo);
+    if (int rc = upload(ctx, &ns->w_hi[i], hi)) return rc;
+    if (int rc = upload(ctx, &ns->w_lo[i], lo)) return rc;
+    std::vector<float> bv(Bv[i], Bv[i] + g.Cout);
+    if (int rc = upload(ctx, &ns->bias[i], bv)) return rc;
+  }
+  {  // fc6: (out, c*80 + h*10 + w) -> (out, (h*10+w)*1024 + c)   (NCHW flatten, deepIM_flownet.py:110)
+    std::vector<float> p((size_t)256 * FC6_K);
+    for (int o = 0; o < 256; ++o)
+      for (int c = 0; c < 1024; ++c)
+        for (int hw = 0; hw < 80; ++hw) p[(size_t)o * FC6_K + (size_t)hw * 1024 + c] = W[10][(size_t)o * FC6_K + (size_t)c * 80 + hw];
+    std::vector<__nv_bfloat16> hb(p.size());
+    for (size_t i = 0; i < p.size(); ++i) hb[i] = __float2bfloat16_rn(p[i]);
+    if (int rc = upload(ctx, &ns->fc6_w_bf16, hb)) return rc;
+    if (int rc = upload(ctx, &ns->fc6_w_f32, p)) return rc;
+    if (int rc = upload(ctx, &ns->fc6_b, std::vector<float>(Bv[10], Bv[10] + 256))) return rc;
+    std::vector<float> t((size_t)256 * 256);
+    for (int o = 0; o < 256; ++o)
+      for (int k = 0; k < 256; ++k) t[(size_t)k * 256 + o] = W[11][(size_t)o * 256 + k];
+    if (int rc = upload(ctx, &ns->fc7_wT, t)) return rc;
+    if (int rc = upload(ctx, &ns->fc7_b, std::vector<float>(Bv[11], Bv[11] + 256))) return rc;
+    if (int rc = upload(ctx, &ns->rot_w, std::vector<float>(W[12], W[12] + 4 * 256))) return rc;
+    if (int rc = upload(ctx, &ns->rot_b, std::vector<float>(Bv[12], Bv[12] + 4))) return rc;
+    if (int rc = upload(ctx, &ns->trans_w, std::vector<float>(W[13], W[13] + 3 * 256))) return rc;
+    if (int rc = upload(ctx, &ns->trans_b, std::vector<float>(Bv[13], Bv[13] + 3))) return rc;
+  }
+  ns->loaded = true;
+  return 0;
+}
+
+template <int BN, int BK, int ST, bool S3>
+static int launch_conv(const ConvKParams &kp, dim3 grid, cudaStream_t st) {
+  using S = ConvSmem<BN, BK, ST, S3>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DIM_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<BN, BK, ST, S3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   S::TOTAL));
+    attr_set = true;
+  }
+  conv_igemm_kernel<BN, BK, ST, S3><<<grid, 192, S::TOTAL, st>>>(kp);
+  DIM_LAUNCH_CHECK();
+  return 0;
+}
+
+// where conv1's input buffer expects pixel (i,j) of the 8-channel blob (space-to-depth, pad 3)
+void net_input_geometry(dim_ctx *ctx, int *rows, int *cols, int *pad, __nv_bfloat16 **hi, __nv_bfloat16 **lo) {
+  NetState *ns = ctx->net;
+  *rows = ns->g[0].rows; *cols = ns->g[0].cols; *pad = ns->g[0].py;
+  *hi = ns->act_hi[0]; *lo = ns->act_lo[0];
+}
+
+// runs conv tower + fc6 + head on the already-filled conv1 input buffer
+int net_forward(dim_ctx *ctx, int B, int precision, const float *zoom_factor, float *rot_out, float *trans_out,
+                float *se3_out, cudaStream_t st) {
+  NetState *ns = ctx->net;
+  DIM_REQUIRE(ns && ns->loaded, "dim_net_load has not been called");
+  DIM_REQUIRE(B >= 1 && B <= ctx->max_batch, "batch exceeds max_batch");
+  auto it = ns->maps.find(B);
+  if (it == ns->maps.end()) {
+    TensorMaps tm;
+    if (int rc = build_maps(ns, B, tm)) return rc;
+    it = ns->maps.emplace(B, tm).first;
+  }
+  const TensorMaps &tm = it->second;
+  const bool s3 = precision == DIM_PREC_BF16X3;
+  for (int i = 0; i < 10; ++i) {
+    const LayerGeom &g = ns->g[i];
+    const ConvKParams &kp = tm.kp[i];
+    dim3 grid(cdiv(B * g.Hq, g.BH) * g.n_col_tiles, g.Cout / g.BLOCK_N, kp.ksplit);
+    int rc;
+    if (i == 0) rc = s3 ? launch_conv<64, 32, 6, true>(kp, grid, st) : launch_conv<64, 32, 6, false>(kp, grid, st);
+    else rc = s3 ? launch_conv<128, 64, 3, true>(kp, grid, st) : launch_conv<128, 64, 3, false>(kp, grid, st);
+    if (rc) return rc;
+    if (kp.ksplit > 1) {
+      const int npix = B * g.Ho * g.Wo;
+      const size_t n4 = (size_t)npix * g.Cout / 4;
+      conv_splitk_finalize_kernel<<<(unsigned)cdiv((int)n4, 256), 256, 0, st>>>(
+          ns->conv_partial, kp.ksplit, npix, g.Cout, g.Ho, g.Wo, kp.out_Hp, kp.out_Wp, kp.out_py, kp.out_px,
+          ns->bias[i], 0.1f, ns->act_hi[i + 1], s3 ? ns->act_lo[i + 1] : nullptr);
+      DIM_LAUNCH_CHECK();
+    }
+  }
+  if (s3)
+    fc6_splitk_kernel<true><<<FC6_SPLITS, 256, 0, st>>>(ns->act_hi[10], ns->act_lo[10], nullptr, ns->fc6_w_f32, B,
+                                                        ctx->max_batch, ns->fc6_partial);
+  else
+    fc6_splitk_kernel<false><<<FC6_SPLITS, 256, 0, st>>>(ns->act_hi[10], nullptr, ns->fc6_w_bf16, nullptr, B,
+                                                         ctx->max_batch, ns->fc6_partial);
+  DIM_LAUNCH_CHECK();
+  head_kernel<<<B, 256, 0, st>>>(ns->fc6_partial, ctx->max_batch, ns->fc6_b, ns->fc7_wT, ns->fc7_b, ns->rot_w,
+                                 ns->rot_b, ns->trans_w, ns->trans_b, zoom_factor, rot_out, trans_out, se3_out);
+  DIM_LAUNCH_CHECK();
+  return 0;
+}
+
+// debugging / test hook: copy the bf16 activation buffer (input of layer `idx`, 10 = fc6 input) to host
+int net_debug_activation(dim_ctx *ctx, int idx, int lo, void *host_dst, size_t bytes) {
+  NetState *ns = ctx->net;
+  DIM_REQUIRE(ns && idx >= 0 && idx <= 10, "bad activation index");
+  const size_t have = ns->act_elems_per_image[idx] * ctx->max_batch * 2;
+  DIM_REQUIRE(bytes <= have, "activation copy larger than buffer");
+  DIM_CHECK(cudaMemcpy(host_dst, lo ? ns->act_lo[idx] : ns->act_hi[idx], bytes, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+void net_layer_geometry(dim_ctx *ctx, int idx, int *out /*rows, cols, Cbuf, py, px, Ho, Wo, Cout*/) {
+  NetState *ns = ctx->net;
+  if (idx < 10) {
+    const LayerGeom &g = ns->g[idx];
+    out[0] = g.rows; out[1] = g.cols; out[2] = g.Cbuf; out[3] = g.py; out[4] = g.px; out[5] = g.Ho; out[6] = g.Wo;
+    out[7] = g.Cout;
+  } else {
+    const LayerGeom &g = ns->g[9];
+    out[0] = g.Ho; out[1] = g.Wo; out[2] = g.Cout; out[3] = 0; out[4] = 0; out[5] = 0; out[6] = 0; out[7] = 256;
+  }
+}
+
+}  // namespace dim

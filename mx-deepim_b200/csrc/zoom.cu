@@ -1,0 +1,394 @@
+// zoom.cu -- mask bbox, zoom factor and the bilinear zoom gathers (compiled with -fmad=false).
+//
+// Replaces the Python custom ops of deepim/operator_py/: ZoomMask (zoom_mask.py:29-112),
+// ZoomImageWithFactor (zoom_image_with_factor.py:31-65), ZoomMaskWithFactor
+// (zoom_mask_with_factor.py:29-64), ZoomFlow (zoom_flow.py:28-71), ZoomDepth (zoom_depth.py:24-44)
+// and the MXNet GridGenerator('affine') + BilinearSampler pair they call:
+//     x_t = -1 + j*(2/(W-1)),  x_s = wx*x_t + tx,  x = (x_s+1)*(W-1)/2,  4 taps, zero padding.
+// The reference does the bbox on the host after three full-mask asnumpy() syncs and one
+// GridGenerator launch per sample; here everything stays on the device.
+#include "common.cuh"
+
+namespace dim {
+
+// ------------------------------------------------------------------------------------- bbox
+__global__ void bbox_init_kernel(int *bbox8, int B, int H, int W) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * 2) return;
+  bbox8[4 * t + 0] = W;
+  bbox8[4 * t + 1] = -1;
+  bbox8[4 * t + 2] = H;
+  bbox8[4 * t + 3] = -1;
+}
+
+// one block per (row, instance, which-mask).  valid = sum_c(mask) > 0.3 (zoom_mask.py:36-37), with
+// each channel binarised at 0.2 first for the rendered mask (l.39-43).
+__global__ void __launch_bounds__(160) mask_bbox_kernel(const float *mask_real, const float *mask_ren, int C,
+                                                        int H, int W, int *bbox8) {
+  const int i = blockIdx.x, b = blockIdx.y, which = blockIdx.z;
+  const float *src = (which == 0 ? mask_real : mask_ren) + (size_t)b * C * H * W + (size_t)i * W;
+  int x0 = 0x7fffffff, x1 = -1;
+  for (int j4 = threadIdx.x * 4; j4 < W; j4 += blockDim.x * 4) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < C; ++c) {
+      float4 v = *reinterpret_cast<const float4 *>(src + (size_t)c * H * W + j4);
+      float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s[k] += which ? (e[k] > 0.2f ? 1.f : 0.f) : e[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (s[k] > 0.3f) {
+        x0 = min(x0, j4 + k);
+        x1 = max(x1, j4 + k);
+      }
+  }
+  x0 = __reduce_min_sync(0xffffffffu, x0);
+  x1 = __reduce_max_sync(0xffffffffu, x1);
+  if ((threadIdx.x & 31) == 0 && x1 >= 0) {
+    int *o = bbox8 + (b * 2 + which) * 4;
+    atomicMin(o + 0, x0);
+    atomicMax(o + 1, x1);
+    atomicMin(o + 2, i);
+    atomicMax(o + 3, i);
+  }
+}
+
+// zoom factor, one thread per instance (zoom_mask.py:59-103).  Mixed precision as the reference's
+// numpy 1.x: c = K.t and c_x = c0/c2 in float32, everything after in float64, stored as float32.
+__global__ void zoom_factor_kernel(int *bbox8, const float *src_pose, int B, int H, int W, float k0, float k1,
+                                   float k2, float k3, float k4, float k5, float k6, float k7, float k8,
+                                   float *zoom_factor, int *bbox_out, int *status) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int *bb = bbox8 + 8 * b;
+  if (bb[1] < 0) bb[0] = bb[1] = bb[2] = bb[3] = -1;
+  if (bb[5] < 0) bb[4] = bb[5] = bb[6] = bb[7] = -1;
+  if (bbox_out)
+    for (int k = 0; k < 8; ++k) bbox_out[8 * b + k] = bb[k];
+  float *zf = zoom_factor + 4 * b;
+  if (bb[1] < 0) {  // the reference raises (np.min of an empty array); flag it
+    zf[0] = zf[1] = 1.f;
+    zf[2] = zf[3] = 0.f;
+    if (status) status[b] = 1;
+    return;
+  }
+  if (status) status[b] = 0;
+  const double real_x0 = bb[0], real_x1 = bb[1], real_y0 = bb[2], real_y1 = bb[3];
+  const float *sp = src_pose + 12 * b;
+  const float t0 = sp[3], t1 = sp[7], t2 = sp[11];
+  const float c0 = (k0 * t0 + k1 * t1) + k2 * t2;
+  const float c1 = (k3 * t0 + k4 * t1) + k5 * t2;
+  const float c2 = (k6 * t0 + k7 * t1) + k8 * t2;
+  const float cxf = c0 / c2, cyf = c1 / c2;
+  double ren_x0, ren_x1, ren_y0, ren_y1, zcx, zcy;
+  if (bb[5] < 0) {  // "NO POINT VALID IN MASK rendered" (zoom_mask.py:70-77)
+    ren_x0 = real_x0; ren_x1 = real_x1; ren_y0 = real_y0; ren_y1 = real_y1;
+    zcx = (real_x0 + real_x1) * 0.5;
+    zcy = (real_y0 + real_y1) * 0.5;
+  } else {
+    ren_x0 = bb[4]; ren_x1 = bb[5]; ren_y0 = bb[6]; ren_y1 = bb[7];
+    zcx = (double)cxf;
+    zcy = (double)cyf;
+  }
+  const double left = fmax(zcx - ren_x0, zcx - real_x0);
+  const double right = fmax(ren_x1 - zcx, real_x1 - zcx);
+  const double up = fmax(zcy - ren_y0, zcy - real_y0);
+  const double down = fmax(real_y1 - zcy, ren_y1 - zcy);
+  const double m = fmax(fmax(0.75 * right, 0.75 * left), fmax(up, down));
+  const double crop_height = m * 1.4 * 2;
+  const double wx = crop_height / (double)H;
+  zf[0] = (float)wx;
+  zf[1] = (float)wx;
+  zf[2] = (float)(zcx / (double)W * 2.0 - 1.0);
+  zf[3] = (float)(zcy / (double)H * 2.0 - 1.0);
+}
+
+// ------------------------------------------------------------------------------------ sampler
+struct Tap {
+  int x0, y0;
+  float wx1, wy1;
+};
+
+__device__ __forceinline__ Tap src_coord(int i, int j, float wx, float wy, float tx, float ty, int H, int W,
+                                         float stepx, float stepy) {
+  float xt = -1.0f + (float)j * stepx;
+  float yt = -1.0f + (float)i * stepy;
+  float xs = wx * xt + tx;
+  float ys = wy * yt + ty;
+  float xr = ((xs + 1.0f) * (float)(W - 1)) / 2.0f;
+  float yr = ((ys + 1.0f) * (float)(H - 1)) / 2.0f;
+  float fx0 = floorf(xr), fy0 = floorf(yr);
+  Tap t;
+  t.x0 = fx0 < -4.0f ? -4 : (fx0 > (float)(W + 4) ? W + 4 : (int)fx0);
+  t.y0 = fy0 < -4.0f ? -4 : (fy0 > (float)(H + 4) ? H + 4 : (int)fy0);
+  t.wx1 = 1.0f - (xr - fx0);
+  t.wy1 = 1.0f - (yr - fy0);
+  return t;
+}
+
+template <int BIN>
+__device__ __forceinline__ float fetch(const float *img, int H, int W, int y, int x, float add) {
+  if (x < 0 || x > W - 1 || y < 0 || y > H - 1) return 0.0f;
+  float v = __ldg(img + (size_t)y * W + x);
+  if (BIN) v = v > 0.2f ? 1.0f : 0.0f;
+  return v + add;
+}
+
+template <int BIN>
+__device__ __forceinline__ float bilinear(const float *img, int H, int W, const Tap &t, float add) {
+  float tl = fetch<BIN>(img, H, W, t.y0, t.x0, add);
+  float tr = fetch<BIN>(img, H, W, t.y0, t.x0 + 1, add);
+  float bl = fetch<BIN>(img, H, W, t.y0 + 1, t.x0, add);
+  float br = fetch<BIN>(img, H, W, t.y0 + 1, t.x0 + 1, add);
+  float wx1 = t.wx1, wy1 = t.wy1;
+  return tl * wy1 * wx1 + tr * wy1 * (1.0f - wx1) + bl * (1.0f - wy1) * wx1 + br * (1.0f - wy1) * (1.0f - wx1);
+}
+
+// inverse-zoom affine (zoom_flow.py:35-44): float32 scalars with python numbers -> float64
+__device__ __forceinline__ void inv_affine(const float *zf, int H, int W, float *a) {
+  double wx_in = zf[0], wy_in = zf[1], tx_in = zf[2], ty_in = zf[3];
+  double wx = 1.0 / wx_in, wy = 1.0 / wy_in;
+  double crop_w = wx_in * (double)W, crop_h = wy_in * (double)H;
+  double cx = tx_in * 0.5 * (double)W + 0.5 * (double)W;
+  double cy = ty_in * 0.5 * (double)H + 0.5 * (double)H;
+  a[0] = (float)wx;
+  a[1] = (float)wy;
+  a[2] = (float)(((double)W * 0.5 - cx) / crop_w * 2.0);
+  a[3] = (float)(((double)H * 0.5 - cy) / crop_h * 2.0);
+}
+
+// MODE 0 plain | 1 round | 2 binarise(>0.2) then round | 3 (img+mean) sample - mean |
+//      4 sample * wx | 5 round(sample - 0.45) | 6 sample / wx
+struct ZoomParams {
+  const float *src;
+  float *dst;
+  const float *zoom_factor;  // [B,4]
+  int C, H, W, inv;
+  float param[4];  // per-channel mean for MODE 3
+  float stepx, stepy;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256) zoom_gather_kernel(ZoomParams p) {
+  __shared__ float aff[4];
+  const int b = blockIdx.y;
+  if (threadIdx.x == 0) {
+    const float *zf = p.zoom_factor + 4 * b;
+    if (p.inv) {
+      inv_affine(zf, p.H, p.W, aff);
+    } else {
+      aff[0] = zf[0]; aff[1] = zf[1]; aff[2] = zf[2]; aff[3] = zf[3];
+    }
+  }
+  __syncthreads();
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= p.H * p.W) return;
+  const int i = q / p.W, j = q % p.W;
+  const Tap t = src_coord(i, j, aff[0], aff[1], aff[2], aff[3], p.H, p.W, p.stepx, p.stepy);
+  const float wxf = p.zoom_factor[4 * b];
+  const size_t P = (size_t)p.H * p.W;
+  for (int c = 0; c < p.C; ++c) {
+    const float *img = p.src + ((size_t)b * p.C + c) * P;
+    float v;
+    if (MODE == 1) v = roundf(bilinear<0>(img, p.H, p.W, t, 0.f));
+    else if (MODE == 2) v = roundf(bilinear<1>(img, p.H, p.W, t, 0.f));
+    else if (MODE == 3) v = bilinear<0>(img, p.H, p.W, t, p.param[c]) - p.param[c];
+    else if (MODE == 4) v = bilinear<0>(img, p.H, p.W, t, 0.f) * wxf;
+    else if (MODE == 5) v = roundf(bilinear<0>(img, p.H, p.W, t, 0.f) - 0.45f);
+    else if (MODE == 6) v = bilinear<0>(img, p.H, p.W, t, 0.f) / wxf;
+    else v = bilinear<0>(img, p.H, p.W, t, 0.f);
+    p.dst[((size_t)b * p.C + c) * P + q] = v;
+  }
+}
+
+int zoom_gather_launch(dim_ctx *ctx, int mode, const float *src, float *dst, const float *zoom_factor, int B, int C,
+                       int inv, const float *param, cudaStream_t st) {
+  ZoomParams p;
+  p.src = src; p.dst = dst; p.zoom_factor = zoom_factor; p.C = C; p.H = ctx->H; p.W = ctx->W; p.inv = inv;
+  for (int k = 0; k < 4; ++k) p.param[k] = (param && k < C) ? param[k] : 0.f;
+  p.stepx = (float)(2.0 / (double)(ctx->W - 1));
+  p.stepy = (float)(2.0 / (double)(ctx->H - 1));
+  dim3 grid(cdiv(ctx->H * ctx->W, 256), B);
+  switch (mode) {
+    case 0: zoom_gather_kernel<0><<<grid, 256, 0, st>>>(p); break;
+    case 1: zoom_gather_kernel<1><<<grid, 256, 0, st>>>(p); break;
+    case 2: zoom_gather_kernel<2><<<grid, 256, 0, st>>>(p); break;
+    case 3: zoom_gather_kernel<3><<<grid, 256, 0, st>>>(p); break;
+    case 4: zoom_gather_kernel<4><<<grid, 256, 0, st>>>(p); break;
+    case 5: zoom_gather_kernel<5><<<grid, 256, 0, st>>>(p); break;
+    case 6: zoom_gather_kernel<6><<<grid, 256, 0, st>>>(p); break;
+    default: set_error("zoom_gather: bad mode"); return 2;
+  }
+  DIM_LAUNCH_CHECK();
+  return 0;
+}
+
+int zoom_factor_launch(dim_ctx *ctx, const float *mask_real, const float *mask_ren, int C, const float *src_pose,
+                       int B, const float *K9, float *zoom_factor, int *bbox_out, int *status, cudaStream_t st) {
+  DIM_REQUIRE((ctx->W & 3) == 0, "width must be a multiple of 4");
+  bbox_init_kernel<<<cdiv(2 * B, 128), 128, 0, st>>>(ctx->bbox8, B, ctx->H, ctx->W);
+  DIM_LAUNCH_CHECK();
+  mask_bbox_kernel<<<dim3(ctx->H, B, 2), 160, 0, st>>>(mask_real, mask_ren, C, ctx->H, ctx->W, ctx->bbox8);
+  DIM_LAUNCH_CHECK();
+  zoom_factor_kernel<<<cdiv(B, 64), 64, 0, st>>>(ctx->bbox8, src_pose, B, ctx->H, ctx->W, K9[0], K9[1], K9[2], K9[3],
+                                                  K9[4], K9[5], K9[6], K9[7], K9[8], zoom_factor, bbox_out, status);
+  DIM_LAUNCH_CHECK();
+  return 0;
+}
+
+// zoom factor when both boxes are already known (fused loop: the rendered box comes from the
+// rasteriser, the observed box is the end-exclusive rectangle of it, data_pair.py:93-105)
+__global__ void zoom_factor_from_ren_kernel(const int *bbox_ren, int *bbox8, int B) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int x0 = bbox_ren[4 * b], x1 = bbox_ren[4 * b + 1], y0 = bbox_ren[4 * b + 2], y1 = bbox_ren[4 * b + 3];
+  int *bb = bbox8 + 8 * b;
+  bb[4] = x0; bb[5] = x1; bb[6] = y0; bb[7] = y1;
+  // rectangle [y0:y1, x0:x1] is empty when the mask is a single row/column (or empty)
+  if (x1 < 0 || x1 - 1 < x0 || y1 - 1 < y0) {
+    bb[0] = bb[1] = bb[2] = bb[3] = -1;
+  } else {
+    bb[0] = x0; bb[1] = x1 - 1; bb[2] = y0; bb[3] = y1 - 1;
+  }
+}
+
+int zoom_factor_from_ren_launch(dim_ctx *ctx, const int *bbox_ren, const float *src_pose, int B, const float *K9,
+                                float *zoom_factor, int *bbox_out, int *status, cudaStream_t st) {
+  zoom_factor_from_ren_kernel<<<cdiv(B, 64), 64, 0, st>>>(bbox_ren, ctx->bbox8, B);
+  DIM_LAUNCH_CHECK();
+  zoom_factor_kernel<<<cdiv(B, 64), 64, 0, st>>>(ctx->bbox8, src_pose, B, ctx->H, ctx->W, K9[0], K9[1], K9[2], K9[3],
+                                                  K9[4], K9[5], K9[6], K9[7], K9[8], zoom_factor, bbox_out, status);
+  DIM_LAUNCH_CHECK();
+  return 0;
+}
+
+// mask_observed := 1 on [y0:y1, x0:x1] END-EXCLUSIVE (lib/pair_matching/data_pair.py:93-105)
+__global__ void __launch_bounds__(256) box_mask_kernel(const int *bbox, int H, int W, float *mask) {
+  const int b = blockIdx.y;
+  const int q4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (q4 >= H * W) return;
+  const int i = q4 / W, j = q4 % W;
+  const int x0 = bbox[4 * b], x1 = bbox[4 * b + 1], y0 = bbox[4 * b + 2], y1 = bbox[4 * b + 3];
+  float v[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v[k] = (x1 >= 0 && i >= y0 && i < y1 && j + k >= x0 && j + k < x1) ? 1.f : 0.f;
+  *reinterpret_cast<float4 *>(mask + (size_t)b * H * W + q4) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+int box_mask_launch(dim_ctx *ctx, const int *bbox, int B, float *mask, cudaStream_t st) {
+  box_mask_kernel<<<dim3(cdiv(ctx->H * ctx->W / 4, 256), B), 256, 0, st>>>(bbox, ctx->H, ctx->W, mask);
+  DIM_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------- fused zoom -> NHWC8
+// One thread per output pixel: samples the 6 image planes (with the +mean / -mean dance of
+// zoom_image_with_factor.py:44-62), the rendered mask and the analytic observed box mask with the
+// same taps, applies the graph's /255 (deepIM_flownet.py:53-60) and writes the 8-channel pixel as
+// bf16 (16 B) straight into conv1's zero-bordered, space-to-depth input buffer; `lo` (optional) receives the
+// bf16 residual for the bf16x3 precision mode.
+struct FusedZoomParams {
+  const float *image_observed, *image_rendered, *mask_rendered;  // [B,3,H,W] x2, [B,1,H,W]
+  const int *bbox8;                                              // observed box = bb[0..3] (inclusive)
+  const float *zoom_factor;
+  int H, W, Hs, Ws, pad;  // conv1 input is space-to-depth: [B,Hs,Ws,(ph,pw,c)=32]
+  float mean[3];
+  float stepx, stepy;
+  __nv_bfloat16 *hi, *lo;  // [B,Hp,Wp,8]
+};
+
+__global__ void __launch_bounds__(256) zoom_fused_nhwc8_kernel(FusedZoomParams p) {
+  const int b = blockIdx.y;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= p.H * p.W) return;
+  const int i = q / p.W, j = q % p.W;
+  const float *zf = p.zoom_factor + 4 * b;
+  const Tap t = src_coord(i, j, zf[0], zf[1], zf[2], zf[3], p.H, p.W, p.stepx, p.stepy);
+  const size_t P = (size_t)p.H * p.W;
+  float v[8];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    v[c] = (bilinear<0>(p.image_observed + ((size_t)b * 3 + c) * P, p.H, p.W, t, p.mean[c]) - p.mean[c]) / 255.0f;
+    v[3 + c] = (bilinear<0>(p.image_rendered + ((size_t)b * 3 + c) * P, p.H, p.W, t, p.mean[c]) - p.mean[c]) / 255.0f;
+  }
+  {  // observed mask = rectangle; bb holds its inclusive bbox (x0, x1-1, y0, y1-1)
+    const int *bb = p.bbox8 + 8 * b;
+    const int x0 = bb[0], x1 = bb[1], y0 = bb[2], y1 = bb[3];
+    auto box = [&](int y, int x) -> float {
+      if (x < 0 || x > p.W - 1 || y < 0 || y > p.H - 1) return 0.0f;
+      return (x1 >= 0 && x >= x0 && x <= x1 && y >= y0 && y <= y1) ? 1.0f : 0.0f;
+    };
+    float tl = box(t.y0, t.x0), tr = box(t.y0, t.x0 + 1), bl = box(t.y0 + 1, t.x0), br = box(t.y0 + 1, t.x0 + 1);
+    float wx1 = t.wx1, wy1 = t.wy1;
+    v[6] = roundf(tl * wy1 * wx1 + tr * wy1 * (1.0f - wx1) + bl * (1.0f - wy1) * wx1 +
+                  br * (1.0f - wy1) * (1.0f - wx1));
+  }
+  v[7] = roundf(bilinear<1>(p.mask_rendered + (size_t)b * P, p.H, p.W, t, 0.f));
+  __align__(16) __nv_bfloat16 h[8];
+  __align__(16) __nv_bfloat16 l[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    h[c] = __float2bfloat16_rn(v[c]);
+    l[c] = __float2bfloat16_rn(v[c] - __bfloat162float(h[c]));
+  }
+  const int oi = i + p.pad, oj = j + p.pad;
+  const size_t o = ((((size_t)b * p.Hs + (oi >> 1)) * p.Ws + (oj >> 1)) * 4 + ((oi & 1) * 2 + (oj & 1))) * 8;
+  *reinterpret_cast<uint4 *>(p.hi + o) = *reinterpret_cast<const uint4 *>(h);
+  if (p.lo) *reinterpret_cast<uint4 *>(p.lo + o) = *reinterpret_cast<const uint4 *>(l);
+}
+
+int zoom_fused_launch(dim_ctx *ctx, const float *image_observed, const float *image_rendered,
+                      const float *mask_rendered, const float *zoom_factor, const float *means_rgb, int B, int Hs,
+                      int Ws, int pad, __nv_bfloat16 *hi, __nv_bfloat16 *lo, cudaStream_t st) {
+  FusedZoomParams p;
+  p.image_observed = image_observed; p.image_rendered = image_rendered; p.mask_rendered = mask_rendered;
+  p.bbox8 = ctx->bbox8; p.zoom_factor = zoom_factor;
+  p.H = ctx->H; p.W = ctx->W; p.Hs = Hs; p.Ws = Ws; p.pad = pad;
+  for (int c = 0; c < 3; ++c) p.mean[c] = means_rgb[c];
+  p.stepx = (float)(2.0 / (double)(ctx->W - 1));
+  p.stepy = (float)(2.0 / (double)(ctx->H - 1));
+  p.hi = hi; p.lo = lo;
+  zoom_fused_nhwc8_kernel<<<dim3(cdiv(ctx->H * ctx->W, 256), B), 256, 0, st>>>(p);
+  DIM_LAUNCH_CHECK();
+  return 0;
+}
+
+// NCHW float32 zoomed blobs -> conv1 NHWC8 bf16 input (used by dim_net_fwd on the op surface)
+__global__ void __launch_bounds__(256) pack_nhwc8_kernel(const float *io, const float *ir, const float *mo,
+                                                         const float *mr, int H, int W, int Hs, int Ws, int pad,
+                                                         __nv_bfloat16 *hi, __nv_bfloat16 *lo) {
+  const int b = blockIdx.y;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= H * W) return;
+  const size_t P = (size_t)H * W;
+  float v[8];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    v[c] = io[((size_t)b * 3 + c) * P + q] / 255.0f;
+    v[3 + c] = ir[((size_t)b * 3 + c) * P + q] / 255.0f;
+  }
+  v[6] = mo[(size_t)b * P + q];
+  v[7] = mr[(size_t)b * P + q];
+  __align__(16) __nv_bfloat16 h[8];
+  __align__(16) __nv_bfloat16 l[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    h[c] = __float2bfloat16_rn(v[c]);
+    l[c] = __float2bfloat16_rn(v[c] - __bfloat162float(h[c]));
+  }
+  const int oi = q / W + pad, oj = q % W + pad;
+  const size_t o = ((((size_t)b * Hs + (oi >> 1)) * Ws + (oj >> 1)) * 4 + ((oi & 1) * 2 + (oj & 1))) * 8;
+  *reinterpret_cast<uint4 *>(hi + o) = *reinterpret_cast<const uint4 *>(h);
+  if (lo) *reinterpret_cast<uint4 *>(lo + o) = *reinterpret_cast<const uint4 *>(l);
+}
+
+int pack_nhwc8_launch(dim_ctx *ctx, const float *io, const float *ir, const float *mo, const float *mr, int B,
+                      int Hs, int Ws, int pad, __nv_bfloat16 *hi, __nv_bfloat16 *lo, cudaStream_t st) {
+  pack_nhwc8_kernel<<<dim3(cdiv(ctx->H * ctx->W, 256), B), 256, 0, st>>>(io, ir, mo, mr, ctx->H, ctx->W, Hs, Ws, pad,
+                                                                         hi, lo);
+  DIM_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace dim

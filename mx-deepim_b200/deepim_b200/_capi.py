@@ -1,0 +1,75 @@
+"""ctypes binding of libdeepim_b200.so (include/deepim_b200.h).  No fallback: if the library is
+missing or fails to load, importing this module raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libdeepim_b200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        "libdeepim_b200.so not found at %s -- build it with `python mx-deepim_b200/build.py` "
+        "(there is no CPU / PyTorch fallback for this path)" % LIB_PATH)
+
+lib = C.CDLL(LIB_PATH)
+
+vp, i32, i64, u64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float
+pf32 = C.POINTER(C.c_float)
+pf64 = C.POINTER(C.c_double)
+
+# name -> (restype, argtypes); every symbol declared in include/deepim_b200.h
+SIGNATURES = {
+    "dim_abi_version": (i32, []),
+    "dim_last_error": (C.c_char_p, []),
+    "dim_ctx_create": (i32, [i32, i32, i32, i32, i32, i32, i32, C.POINTER(vp)]),
+    "dim_ctx_destroy": (None, [vp]),
+    "dim_mesh_upload": (i32, [vp, i32, vp, vp, i32, vp, i32, vp, i32, i32]),
+    "dim_render": (i32, [vp, vp, vp, i32, pf32, f32, f32, pf64, i32, vp, vp, vp, vp, vp, vp]),
+    "dim_zoom_mask_fwd": (i32, [vp, vp, vp, vp, vp, i32, pf32, vp, vp, vp, vp, vp, vp, vp]),
+    "dim_zoom_image_with_factor_fwd": (i32, [vp, vp, vp, vp, i32, pf32, vp, vp, vp]),
+    "dim_zoom_mask_with_factor_fwd": (i32, [vp, vp, vp, i32, i32, vp, vp]),
+    "dim_zoom_flow_fwd": (i32, [vp, vp, vp, vp, i32, i32, vp, vp, vp]),
+    "dim_zoom_depth_fwd": (i32, [vp, vp, vp, vp, i32, vp, vp, vp]),
+    "dim_zoom_trans_fwd": (i32, [vp, vp, vp, i32, i32, vp, vp]),
+    "dim_zoom_trans_bwd": (i32, [vp, vp, vp, i32, i32, i32, vp, vp]),
+    "dim_update_mask_box": (i32, [vp, vp, i32, vp, vp]),
+    "dim_se3_compose": (i32, [vp, vp, vp, i32, pf64, pf64, i32, vp, vp]),
+    "dim_flow_fwd": (i32, [vp, vp, vp, vp, pf32, i32, vp, vp, vp]),
+    "dim_transform3d_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, pf32, pf32, i32, vp, vp]),
+    "dim_transform3d_bwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, pf32, pf32, i32, vp, vp, vp]),
+    "dim_net_load": (i32, [vp, C.POINTER(vp), C.POINTER(vp)]),
+    "dim_net_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, vp, vp, vp]),
+    "dim_refine": (i32, [vp, vp, vp, vp, i32, i32, pf32, f32, f32, pf64, i32, vp, vp, vp, vp, vp, vp]),
+    "dim_refine_host": (i32, [vp, vp, vp, vp, i32, i32, pf32, f32, f32, pf64, i32, vp, vp, vp]),
+    "dim_transform_image_u8": (i32, [vp, vp, i32, pf64, vp, vp]),
+    "dim_debug_activation": (i32, [vp, i32, i32, vp, u64]),
+    "dim_debug_layer_geometry": (i32, [vp, i32, C.POINTER(i32)]),
+    "dim_launch_count": (i64, [i32]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)  # AttributeError here = header/library mismatch
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+PREC_BF16 = 0
+PREC_BF16X3 = 1
+ROT_COORD = {"model": 0, "camera": 1, "camera_new": 2}
+
+
+class DeepIMError(RuntimeError):
+    pass
+
+
+def check(rc: int):
+    if rc != 0:
+        raise DeepIMError("libdeepim_b200: rc=%d: %s" % (rc, lib.dim_last_error().decode("utf-8", "replace")))
+
+
+def farr(values, n=None, ctype=C.c_float):
+    vals = [float(v) for v in values]
+    if n is not None and len(vals) != n:
+        raise ValueError("expected %d values, got %d" % (n, len(vals)))
+    return (ctype * len(vals))(*vals)
