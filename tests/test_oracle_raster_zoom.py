@@ -1,0 +1,188 @@
+"""CPU: self-consistency and known-answer tests of the restated (unpinned) parts of the oracle:
+rasteriser conventions (render_py_multi.py:101-160), zoom bbox/factor (zoom_mask.py:29-112),
+sampler semantics, box mask (data_pair.py:93-105)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from deepim_b200 import synth
+
+K = synth.K_LINEMOD
+
+
+def _quad_mesh(z=1.0, half=0.1, n=1):
+    # planar quad facing the camera made of 2 triangles sharing the diagonal
+    v = np.array([[-half, -half, 0], [half, -half, 0], [half, half, 0], [-half, half, 0]], np.float32)
+    uv = np.array([[0, 0], [1, 0], [1, 1], [0, 1]], np.float32)
+    f = np.array([[0, 1, 2], [0, 2, 3]], np.int32)
+    tex = np.zeros((4, 4, 3), np.uint8)
+    tex[..., 0] = np.arange(4)[None, :] * 60 + 10
+    tex[..., 1] = np.arange(4)[:, None] * 60 + 20
+    tex[..., 2] = 200
+    return synth.Mesh(v, uv, f, tex)
+
+
+def test_render_pixel_centre_convention_and_depth():
+    # pixel (i,j) samples image-plane point (u,v)=(j,i): a point at (X,Y,Z) lands on u = fx X/Z + cx
+    m = _quad_mesh()
+    pose = np.hstack([np.eye(3), np.array([[0.0], [0.0], [1.0]])])
+    r = O.render(m, pose, K)
+    fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
+    x0, x1 = cx - fx * 0.1, cx + fx * 0.1
+    y0, y1 = cy - fy * 0.1, cy + fy * 0.1
+    cols = np.nonzero(r["mask"].max(0))[0]
+    rows = np.nonzero(r["mask"].max(1))[0]
+    assert cols.min() == int(np.ceil(x0)) and cols.max() == int(np.floor(x1))
+    assert rows.min() == int(np.ceil(y0)) and rows.max() == int(np.floor(y1))
+    assert np.abs(r["depth"][r["mask"] > 0] - 1.0).max() < 3e-7 and np.all(r["depth"][r["mask"] == 0] == 0.0)
+    assert list(r["bbox"]) == [cols.min(), cols.max(), rows.min(), rows.max()]
+    # watertight: the shared diagonal is covered exactly once -> mask is a full rectangle
+    assert r["mask"].sum() == len(cols) * len(rows)
+    # texture orientation: u grows with x (red ramp), v grows with y (green ramp); BGR output
+    inside = r["bgr"][rows.min():rows.max() + 1, cols.min():cols.max() + 1]
+    assert np.all(np.diff(inside[0, :, 2]) >= 0) and inside[0, 0, 2] < inside[0, -1, 2]
+    assert np.all(np.diff(inside[:, 0, 1]) >= 0) and inside[0, 0, 1] < inside[-1, 0, 1]
+    assert np.all(inside[..., 0] == 200)
+
+
+def test_render_exact_edge_ownership():
+    # vertices exactly on pixel centres: each pixel on a shared edge belongs to exactly one triangle,
+    # and the closed/open sides follow the antisymmetric rule (no double cover, no crack)
+    z = 1.0
+    fx, fy, cx, cy = [float(v) for v in (K[0, 0], K[1, 1], K[0, 2], K[1, 2])]
+    def at(u, v):
+        return [(u - cx) * z / fx, (v - cy) * z / fy, 0.0]
+    v = np.array([at(100, 100), at(140, 100), at(140, 130), at(100, 130), at(180, 100), at(180, 130)], np.float32)
+    uv = np.zeros((6, 2), np.float32)
+    f = np.array([[0, 1, 2], [0, 2, 3], [1, 4, 5], [1, 5, 2]], np.int32)
+    tex = np.full((2, 2, 3), 255, np.uint8)
+    pose = np.hstack([np.eye(3), np.array([[0.0], [0.0], [z]])])
+    r = O.render(synth.Mesh(v, uv, f, tex), pose, K)
+    m = r["mask"]
+    ys, xs = np.nonzero(m)
+    # float projection of the hand-made vertices may be off by <1/256 px; the covered area must be a
+    # solid rectangle of 80 x 30 (+-1) pixels with no holes
+    h, w = ys.max() - ys.min() + 1, xs.max() - xs.min() + 1
+    assert m[ys.min():ys.max() + 1, xs.min():xs.max() + 1].all()
+    assert 79 <= w <= 81 and 29 <= h <= 31
+
+
+def test_render_near_far_and_truncation():
+    m = _quad_mesh()
+    pose = np.hstack([np.eye(3), np.array([[0.0], [0.0], [0.2]])])  # closer than ZNEAR
+    assert O.render(m, pose, K)["mask"].sum() == 0
+    pose[2, 3] = 7.0  # beyond ZFAR
+    assert O.render(m, pose, K)["mask"].sum() == 0
+    pose[2, 3] = 1.0
+    a = O.render(m, pose, K, trunc_u8=True)["bgr"]
+    b = O.render(m, pose, K, trunc_u8=False)["bgr"]
+    assert np.all(a == np.floor(b)) and np.all(a == a.astype(np.uint8))
+
+
+def test_image_blob_is_transform_of_bgr():
+    m = synth.make_cube()
+    obs, _ = synth.sample_pose_pairs(1, 0)
+    r = O.render(m, obs[0], K, means_rgb=synth.PIXEL_MEANS_RGB)
+    assert np.array_equal(r["image"], synth.transform_image(r["bgr"]))
+    assert np.array_equal(r["mask"], (r["depth"] > 0.2).astype(np.float32))
+
+
+def test_box_mask_is_end_exclusive():
+    bm = O.box_mask(np.array([10, 20, 5, 9], np.int32), 480, 640)
+    ys, xs = np.nonzero(bm)
+    assert (xs.min(), xs.max(), ys.min(), ys.max()) == (10, 19, 5, 8)
+    assert O.box_mask(np.array([-1, -1, -1, -1], np.int32), 480, 640).sum() == 0
+
+
+def test_zoom_factor_formula():
+    # zoom_mask.py:86-95 with hand-computed numbers (numpy 1.x scalar promotion: float64 after c_x)
+    H, W = 480, 640
+    mo = np.zeros((1, 1, H, W), np.float32); mo[0, 0, 200:260, 300:380] = 1
+    mr = np.zeros((1, 1, H, W), np.float32); mr[0, 0, 210:280, 290:350] = 0.9
+    pose = np.zeros((1, 3, 4), np.float32); pose[0, :, :3] = np.eye(3); pose[0, :, 3] = [0.01, -0.02, 0.9]
+    zo, zg, zr, zf, bbox = O.zoom_mask(mo, mo, mr, pose, K)
+    assert list(bbox[0]) == [300, 379, 200, 259, 290, 349, 210, 279]
+    K32 = K.astype(np.float32)
+    c = K32 @ pose[0, :, 3]
+    cx, cy = np.float64(c[0] / c[2]), np.float64(c[1] / c[2])
+    left, right = max(cx - 290, cx - 300), max(349 - cx, 379 - cx)
+    up, down = max(cy - 210, cy - 200), max(259 - cy, 279 - cy)
+    crop = max(0.75 * right, 0.75 * left, up, down) * 1.4 * 2
+    exp = np.array([crop / H, crop / H, cx / W * 2 - 1, cy / H * 2 - 1]).astype(np.float32)
+    assert np.abs(zf[0] - exp).max() <= 2 * np.finfo(np.float32).eps * np.abs(exp).max()
+    assert set(np.unique(zo)) <= {0.0, 1.0}
+
+
+def test_zoom_factor_empty_rendered_fallback():
+    H, W = 480, 640
+    mo = np.zeros((1, 1, H, W), np.float32); mo[0, 0, 100:200, 100:300] = 1
+    mr = np.zeros((1, 1, H, W), np.float32)
+    pose = np.zeros((1, 3, 4), np.float32); pose[0, :, :3] = np.eye(3); pose[0, :, 3] = [0, 0, 1]
+    _, _, _, zf, bbox = O.zoom_mask(mo, mo, mr, pose, K)
+    assert list(bbox[0, 4:]) == [-1, -1, -1, -1]
+    cx, cy = (100 + 299) * 0.5, (100 + 199) * 0.5
+    crop = max(0.75 * (299 - cx), 0.75 * (cx - 100), cy - 100, 199 - cy) * 1.4 * 2
+    np.testing.assert_allclose(zf[0], [crop / H, crop / H, cx / W * 2 - 1, cy / H * 2 - 1], rtol=1e-6)
+    with pytest.raises(ValueError):
+        O.zoom_mask(mr, mr, mr, pose, K)
+
+
+def test_sampler_matches_torch_grid_sample():
+    # a6: GridGenerator(affine)+BilinearSampler == affine_grid/grid_sample(align_corners=True, zeros)
+    import torch
+    import torch.nn.functional as F
+    yy, xx = np.mgrid[0:480, 0:640].astype(np.float32)
+    img = np.sin(xx / 37.0) * np.cos(yy / 23.0) + 0.002 * xx
+    for aff in ([0.3, 0.3, 0.1, -0.2], [1.5, 1.5, 0.4, 0.3], [1.0, 1.0, 0.0, 0.0]):
+        a = np.array(aff, np.float32)
+        z = O.zoom_plane(img, a, 0)
+        theta = torch.tensor([[[a[0], 0, a[2]], [0, a[1], a[3]]]])
+        g = F.affine_grid(theta, (1, 1, 480, 640), align_corners=True)
+        zt = F.grid_sample(torch.from_numpy(img)[None, None], g, mode="bilinear", padding_mode="zeros",
+                           align_corners=True)[0, 0].numpy()
+        assert np.abs(z - zt).max() < 2e-4
+    ident = O.zoom_plane(img, np.array([1, 1, 0, 0], np.float32), 0)
+    assert np.abs(ident - img).max() < 1e-3
+
+
+def test_round_is_half_away_from_zero():
+    # two-pixel 50/50 blends give exactly 0.5: mx.nd.round == roundf -> 1 (numpy/torch would give 0)
+    img = np.zeros((480, 640), np.float32); img[:, 320:] = 1
+    a = np.array([1.0, 1.0, 1.0 / 639.0, 0.0], np.float32)  # half-pixel shift in x
+    s = O.zoom_plane(img, a, 0)
+    col = np.argmin(np.abs(s[240] - 0.5))
+    if s[240, col] == 0.5:
+        assert O.zoom_plane(img, a, 1)[240, col] == 1.0
+
+
+def test_inverse_zoom_roundtrip():
+    # zoom then inverse zoom of a smooth image returns the original inside the crop (zoom_flow.py:35-44)
+    yy, xx = np.mgrid[0:480, 0:640].astype(np.float32)
+    img = (np.sin(xx / 50.0) + np.cos(yy / 40.0)).astype(np.float32)
+    zf = np.array([0.5, 0.5, 0.1, -0.1], np.float32)
+    z = O.zoom_plane(img, zf, 0)
+    back = O.zoom_plane(z, O.inv_zoom_affine(zf, 480, 640), 0)
+    # the crop covers x in [0.1*320+320 +- 160], y in [-0.1*240+240 +- 120]
+    assert np.abs(back[150:280, 220:480] - img[150:280, 220:480]).max() < 2e-2
+
+
+def test_zoom_trans_roundtrip():
+    zf = np.array([[0.3, 0.3, 0, 0], [0.7, 0.7, 0.1, 0.2]], np.float32)
+    t = np.array([[0.1, -0.2, 0.3], [0.01, 0.02, -0.03]], np.float32)
+    back = O.zoom_trans(zf, O.zoom_trans(zf, t, False), True)
+    np.testing.assert_allclose(back, t, rtol=1e-6)
+    assert np.array_equal(O.zoom_trans(zf, t, True)[:, 2], t[:, 2])
+
+
+def test_net_forward_shapes_and_refine_runs():
+    w = synth.make_weights(0)
+    cube = synth.make_cube()
+    obs, ini = synth.sample_pose_pairs(1, 0)
+    o = O.render(cube, obs[0], K)
+    img_o = synth.transform_image(synth.composite_observed(o["bgr"], o["mask"], 0))[None]
+    res = O.refine(w, [cube], np.array([0], np.int32), img_o, ini, K, n_iter=1, means_rgb=synth.PIXEL_MEANS_RGB.astype(np.float32))
+    assert res["poses"].shape == (1, 1, 3, 4) and res["se3"].shape == (1, 1, 7)
+    assert np.isfinite(res["poses"]).all()
+    R = res["poses"][0, 0, :, :3]
+    np.testing.assert_allclose(R @ R.T, np.eye(3), atol=1e-9)
+    assert res["bbox"][0, 0, 1] >= res["bbox"][0, 0, 0] >= 0
