@@ -200,6 +200,13 @@ DIM_API int32_t dim_debug_activation(dim_ctx *ctx, int32_t idx, int32_t lo, void
                                      uint64_t bytes);
 DIM_API int32_t dim_debug_layer_geometry(dim_ctx *ctx, int32_t idx, int32_t *out8);
 
+/* Stage profiling of dim_refine with CUDA events on the launching stream (used by bench.py for the
+ * live roofline numbers).  enable=1 starts recording; dim_profile_read synchronises the device and
+ * returns accumulated milliseconds since the last read as ms[4] = render, bbox+zoom, conv tower,
+ * fc+head+compose, and the number of recorded iterations. */
+DIM_API int32_t dim_profile_enable(dim_ctx *ctx, int32_t enable);
+DIM_API int32_t dim_profile_read(dim_ctx *ctx, float *ms4, int32_t *iterations);
+
 /* number of kernel launches issued by this library since the counter was last reset */
 DIM_API int64_t dim_launch_count(int32_t reset);
 

@@ -46,7 +46,7 @@ void net_destroy(dim_ctx *);
 int net_load(dim_ctx *, const float *const *, const float *const *);
 void net_input_geometry(dim_ctx *, int *rows, int *cols, int *pad, __nv_bfloat16 **hi, __nv_bfloat16 **lo);
 int net_forward(dim_ctx *, int B, int precision, const float *zoom_factor, float *rot, float *trans, float *se3,
-                cudaStream_t);
+                cudaStream_t, cudaEvent_t after_conv);
 int net_debug_activation(dim_ctx *, int idx, int lo, void *host_dst, size_t bytes);
 void net_layer_geometry(dim_ctx *, int idx, int *out);
 
@@ -133,6 +133,7 @@ DIM_API void dim_ctx_destroy(dim_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   net_destroy(ctx);
+  for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
   for (void *p : ctx->owned) cudaFree(p);
   delete ctx;
 }
@@ -269,7 +270,7 @@ DIM_API int32_t dim_net_fwd(dim_ctx *ctx, const float *zio, const float *zir, co
   if (int rc = pack_nhwc8_launch(ctx, zio, zir, zmo, zmr, B, rows, cols, pad, hi,
                                  precision == DIM_PREC_BF16X3 ? lo : nullptr, st))
     return rc;
-  return net_forward(ctx, B, precision, nullptr, rot, trans, nullptr, st);
+  return net_forward(ctx, B, precision, nullptr, rot, trans, nullptr, st, nullptr);
 }
 
 DIM_API int32_t dim_transform_image_u8(dim_ctx *ctx, const uint8_t *bgr, int32_t B, const double *means, float *image,
@@ -292,6 +293,17 @@ DIM_API int32_t dim_refine(dim_ctx *ctx, const float *image_observed, const int3
   net_input_geometry(ctx, &rows, &cols, &pad, &hi, &lo);
   const double *pose_src = pose_init;
   for (int it = 0; it < n_iter; ++it) {
+    cudaEvent_t *ev = nullptr;
+    if (ctx->prof) {
+      while (ctx->prof_events.size() < ctx->prof_used + 5) {
+        cudaEvent_t e;
+        DIM_CHECK(cudaEventCreate(&e));
+        ctx->prof_events.push_back(e);
+      }
+      ev = &ctx->prof_events[ctx->prof_used];
+      ctx->prof_used += 5;
+      DIM_CHECK(cudaEventRecord(ev[0], st));
+    }
     if (pose_override) pose_src = pose_override + (size_t)it * B * 12;
     // src_pose blob is float32 (nd.array), the host pose stays float64 (tester.py:391)
     if (int rc = f64_to_f32_launch(pose_src, ctx->pose_cur_f32, B * 12, st)) return rc;
@@ -299,6 +311,7 @@ DIM_API int32_t dim_refine(dim_ctx *ctx, const float *image_observed, const int3
     if (int rc = render_launch(ctx, cls_idx, ctx->pose_cur_f32, B, K9, zn, zf, means, 1, ctx->image_rendered, nullptr,
                                ctx->mask_rendered, nullptr, nullptr, st))
       return rc;
+    if (ev) DIM_CHECK(cudaEventRecord(ev[1], st));
     float *zf_it = zoom_factor ? zoom_factor + (size_t)it * B * 4 : ctx->zoom_factor;
     int *bbox_it = bbox ? bbox + (size_t)it * B * 8 : nullptr;
     if (int rc = zoom_factor_from_ren_launch(ctx, ctx->bbox_ren, ctx->pose_cur_f32, B, K9, zf_it, bbox_it, ctx->status, st))
@@ -306,10 +319,12 @@ DIM_API int32_t dim_refine(dim_ctx *ctx, const float *image_observed, const int3
     if (int rc = zoom_fused_launch(ctx, image_observed, ctx->image_rendered, ctx->mask_rendered, zf_it, means_f, B,
                                    rows, cols, pad, hi, precision == DIM_PREC_BF16X3 ? lo : nullptr, st))
       return rc;
+    if (ev) DIM_CHECK(cudaEventRecord(ev[2], st));
     float *se3_it = se3 ? se3 + (size_t)it * B * 7 : ctx->se3_cur;
-    if (int rc = net_forward(ctx, B, precision, zf_it, nullptr, nullptr, se3_it, st)) return rc;
+    if (int rc = net_forward(ctx, B, precision, zf_it, nullptr, nullptr, se3_it, st, ev ? ev[3] : nullptr)) return rc;
     double *pose_out = poses + (size_t)it * B * 12;
     if (int rc = se3_compose_launch(pose_src, se3_it, B, Tm, Ts, 1 /*CAMERA*/, pose_out, nullptr, st)) return rc;
+    if (ev) DIM_CHECK(cudaEventRecord(ev[4], st));
     pose_src = pose_out;
   }
   return 0;
@@ -334,6 +349,28 @@ DIM_API int32_t dim_refine_host(dim_ctx *ctx, const uint8_t *img_u8, const int32
   if (se3_out)
     DIM_CHECK(cudaMemcpyAsync(se3_out, ctx->se3_hist_dev, sizeof(float) * (size_t)n_iter * B * 7, cudaMemcpyDeviceToHost, st));
   DIM_CHECK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+DIM_API int32_t dim_profile_enable(dim_ctx *ctx, int32_t enable) {
+  DIM_REQUIRE(ctx, "dim_profile_enable: NULL ctx");
+  ctx->prof = enable != 0;
+  ctx->prof_used = 0;
+  return 0;
+}
+DIM_API int32_t dim_profile_read(dim_ctx *ctx, float *ms4, int32_t *iterations) {
+  DIM_REQUIRE(ctx && ms4, "dim_profile_read: NULL argument");
+  DIM_CHECK(cudaDeviceSynchronize());
+  for (int k = 0; k < 4; ++k) ms4[k] = 0.f;
+  const size_t n = ctx->prof_used / 5;
+  for (size_t i = 0; i < n; ++i)
+    for (int k = 0; k < 4; ++k) {
+      float ms = 0.f;
+      DIM_CHECK(cudaEventElapsedTime(&ms, ctx->prof_events[5 * i + k], ctx->prof_events[5 * i + k + 1]));
+      ms4[k] += ms;
+    }
+  if (iterations) *iterations = (int32_t)n;
+  ctx->prof_used = 0;
   return 0;
 }
 

@@ -100,4 +100,8 @@ struct dim_ctx {
   double *poses_dev = nullptr;  // [8, max_batch, 12]
   float *se3_hist_dev = nullptr;
   dim::NetState *net = nullptr;
+  // stage profiling (dim_profile_enable)
+  bool prof = false;
+  std::vector<cudaEvent_t> prof_events;  // 5 per recorded iteration
+  size_t prof_used = 0;
 };

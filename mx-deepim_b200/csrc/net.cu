@@ -455,7 +455,7 @@ void net_input_geometry(dim_ctx *ctx, int *rows, int *cols, int *pad, __nv_bfloa
 
 // runs conv tower + fc6 + head on the already-filled conv1 input buffer
 int net_forward(dim_ctx *ctx, int B, int precision, const float *zoom_factor, float *rot_out, float *trans_out,
-                float *se3_out, cudaStream_t st) {
+                float *se3_out, cudaStream_t st, cudaEvent_t after_conv) {
   NetState *ns = ctx->net;
   DIM_REQUIRE(ns && ns->loaded, "dim_net_load has not been called");
   DIM_REQUIRE(B >= 1 && B <= ctx->max_batch, "batch exceeds max_batch");
@@ -484,6 +484,7 @@ int net_forward(dim_ctx *ctx, int B, int precision, const float *zoom_factor, fl
       DIM_LAUNCH_CHECK();
     }
   }
+  if (after_conv) DIM_CHECK(cudaEventRecord(after_conv, st));
   if (s3)
     fc6_splitk_kernel<true><<<FC6_SPLITS, 256, 0, st>>>(ns->act_hi[10], ns->act_lo[10], nullptr, ns->fc6_w_f32, B,
                                                         ctx->max_batch, ns->fc6_partial);

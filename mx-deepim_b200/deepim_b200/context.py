@@ -289,5 +289,21 @@ class Context:
         return poses_out, se3_out
 
 
+def _profile_enable(self, on=True):
+    check(lib.dim_profile_enable(self._h, int(on)))
+
+
+def _profile_read(self):
+    """-> (dict stage -> ms accumulated since last read, iterations)"""
+    ms = (C.c_float * 4)()
+    n = C.c_int32()
+    check(lib.dim_profile_read(self._h, ms, C.byref(n)))
+    return {"render": ms[0], "zoom": ms[1], "conv": ms[2], "head": ms[3]}, n.value
+
+
+Context.profile_enable = _profile_enable
+Context.profile_read = _profile_read
+
+
 def launch_count(reset=False):
     return int(lib.dim_launch_count(int(reset)))
