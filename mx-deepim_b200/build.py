@@ -3,7 +3,7 @@
     python mx-deepim_b200/build.py [--force] [--verbose]
 
 raster.cu / zoom.cu / geom.cu are compiled with -fmad=false: their float32 sequences are specified
-operation by operation (oracle/deepim_oracle.c is built with -ffp-contract=off) so that integer
+operation by operation (the CPU checker used by tests/ is built with -ffp-contract=off) so that integer
 outputs (bbox, masks, coverage) and the rendered images are bit-exact against the oracle.
 """
 import os

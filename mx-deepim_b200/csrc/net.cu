@@ -54,7 +54,7 @@ struct NetState {
   float *fc6_partial = nullptr;  // [FC6_SPLITS][max_batch][256]
   float *conv_partial = nullptr;
   size_t conv_partial_elems = 0;
-  bool loaded = false;
+  bool loaded = false, net_ok = false;
   std::map<int, TensorMaps> maps;  // per batch size
   int max_batch = 0, num_sms = 148;
 };
@@ -73,6 +73,8 @@ static void build_geometry(NetState *ns, int H, int W) {
     g.Hin = h; g.Win = w;
     g.Ho = (h + 2 * s.pad - s.k) / s.stride + 1;
     g.Wo = (w + 2 * s.pad - s.k) / s.stride + 1;
+    if (g.Ho < 1) g.Ho = 1;
+    if (g.Wo < 1) g.Wo = 1;
     int Hp = h + 2 * s.pad, Wp = w + 2 * s.pad;
     if (s.stride == 2) { Hp += Hp & 1; Wp += Wp & 1; }
     g.py = g.px = s.pad;
@@ -97,8 +99,9 @@ static void build_geometry(NetState *ns, int H, int W) {
         const int score = d * (128 / d) * 1000 + d;
         if (score > best_score) { best_score = score; best_bw = d; }
       }
+    if (best_bw == 0) best_bw = 1;  // degenerate geometry (tiny geometry-only contexts)
     g.BW = best_bw; g.BH = 128 / best_bw;
-    g.n_col_tiles = g.Wo / g.BW;
+    g.n_col_tiles = g.Wo > 0 ? g.Wo / g.BW : 0;
     g.kblocks = g.KH * g.KW * (g.Ceff / g.BLOCK_K);
     h = g.Ho; w = g.Wo;
   }
@@ -324,6 +327,7 @@ int net_create(dim_ctx *ctx) {
   ns->max_batch = ctx->max_batch;
   ns->num_sms = ctx->num_sms;
   build_geometry(ns, ctx->H, ctx->W);
+  if ((size_t)ns->g[9].Ho * ns->g[9].Wo * ns->g[9].Cout != (size_t)FC6_K) return 0;  // geometry-only context
   for (int i = 0; i <= 10; ++i) {
     size_t per;
     if (i < 10) per = (size_t)ns->g[i].rows * ns->g[i].cols * ns->g[i].Cbuf;
@@ -333,7 +337,7 @@ int net_create(dim_ctx *ctx) {
     if (int rc = dev_alloc(ctx, &ns->act_hi[i], per * ctx->max_batch, true)) return rc;
     if (int rc = dev_alloc(ctx, &ns->act_lo[i], per * ctx->max_batch, true)) return rc;
   }
-  DIM_REQUIRE(ns->act_elems_per_image[10] == (size_t)FC6_K, "fc6 input size mismatch (needs 480x640 input)");
+  ns->net_ok = ns->act_elems_per_image[10] == (size_t)FC6_K;  // fc6 is 81920 -> 256: needs 480x640
   size_t pmax = 0;
   for (int B = 1; B <= ctx->max_batch; ++B)
     for (int i = 0; i < 10; ++i) {
@@ -375,6 +379,7 @@ int net_load(dim_ctx *ctx, const float *const *W, const float *const *Bv) {
   NetState *ns = ctx->net;
   DIM_REQUIRE(ns != nullptr, "net not created");
   DIM_REQUIRE(!ns->loaded, "dim_net_load: weights already loaded for this context");
+  DIM_REQUIRE(ns->net_ok, "dim_net_load: FlowNetS + fc6 (81920 inputs) needs a 480x640 context");
   for (int i = 0; i < 10; ++i) {
     const LayerGeom &g = ns->g[i];
     const size_t Ktot = (size_t)g.KH * g.KW * g.Ceff;

@@ -326,3 +326,76 @@ def adi_metric(R_est, t_est, R_gt, t_gt, pts):
     pg = pts @ np.asarray(R_gt).T + np.asarray(t_gt).reshape(1, 3)
     d, _ = spatial.cKDTree(pe).query(pg, k=1)
     return float(d.mean())
+
+
+# ------------------------------------------------------------------------------------ Transform3D
+def _quat2mat_t3d(q):
+    """quat2mat_forward (deepim/operator_py/transform3d.py:185-212): identity unless |Nq-1| < 1e-2."""
+    w, x, y, z = [np.float32(v) for v in q]
+    Nq = np.float32(w * w + x * x + y * y + z * z)
+    if not (-1e-2 < float(Nq) - 1 < 1e-2):
+        return np.eye(3, dtype=np.float32)
+    s = 2.0 / float(Nq)
+    X, Y, Z = float(x) * s, float(y) * s, float(z) * s
+    wX, wY, wZ = float(w) * X, float(w) * Y, float(w) * Z
+    xX, xY, xZ = float(x) * X, float(x) * Y, float(x) * Z
+    yY, yZ, zZ = float(y) * Y, float(y) * Z, float(z) * Z
+    return np.array([[1.0 - (yY + zZ), xY - wZ, xZ + wY], [xY + wZ, 1.0 - (xX + zZ), yZ - wX],
+                     [xZ - wY, yZ + wX, 1.0 - (xX + yY)]], dtype=np.float32)
+
+
+def transform3d_forward(point_cloud, rotation, translation, pose_src, T_means, T_stds, rot_coord="model"):
+    """Transform3D forward (transform3d.py:34-97), numpy float32.  point_cloud (B,3,N)."""
+    B = point_cloud.shape[0]
+    out = np.empty_like(point_cloud, dtype=np.float32)
+    Tm, Ts = np.asarray(T_means, np.float32), np.asarray(T_stds, np.float32)
+    for b in range(B):
+        Rd = _quat2mat_t3d(rotation[b])
+        Rs = pose_src[b, :, :3].astype(np.float32)
+        Rt = (Rs @ Rd) if rot_coord.lower() == "model" else (Rd @ Rs)
+        d = translation[b].astype(np.float32) * Ts + Tm
+        src = pose_src[b, :, 3].astype(np.float32)
+        z2 = src[2] / np.exp(d[2])
+        if rot_coord.lower() == "camera_new":
+            Tt = np.array([src[2] * d[0] + src[0], src[2] * d[1] + src[1], z2], np.float32)
+        else:
+            Tt = np.array([z2 * (d[0] + src[0] / src[2]), z2 * (d[1] + src[1] / src[2]), z2], np.float32)
+        out[b] = Rt @ point_cloud[b].astype(np.float32) + Tt[:, None]
+    return out
+
+
+def transform3d_backward(out_grad, point_cloud, rotation, translation, pose_src, T_means, T_stds, rot_coord="model"):
+    """Transform3D backward (transform3d.py:99-281): returns rot_grad (B,4), trans_grad (B,3)."""
+    B = point_cloud.shape[0]
+    Tm, Ts = np.asarray(T_means, np.float64), np.asarray(T_stds, np.float64)
+    rg, tg = np.zeros((B, 4), np.float32), np.zeros((B, 3), np.float32)
+    for b in range(B):
+        D = out_grad[b].astype(np.float64).sum(axis=1)
+        d = translation[b].astype(np.float64) * Ts + Tm
+        src = pose_src[b, :, 3].astype(np.float64)
+        z2 = src[2] / np.exp(d[2])
+        if rot_coord.lower() == "camera_new":
+            tg[b] = [D[0] * Ts[0] * src[2], D[1] * Ts[1] * src[2], D[2] * (-Ts[2] * z2)]
+        else:
+            share = -Ts[2] * z2
+            tg[b] = [D[0] * Ts[0] * z2, D[1] * Ts[1] * z2,
+                     D[0] * share * (d[0] + src[0] / src[2]) + D[1] * share * (d[1] + src[1] / src[2]) + D[2] * share]
+        RtD = out_grad[b].astype(np.float64) @ point_cloud[b].astype(np.float64).T
+        Rs = pose_src[b, :, :3].astype(np.float64)
+        Dm = (Rs.T @ RtD) if rot_coord.lower() == "model" else (RtD @ Rs.T)
+        w, x, y, z = [float(v) for v in rotation[b]]
+        Nq = w * w + x * x + y * y + z * z
+        if not (-1e-4 < Nq - 1 < 1e-4):
+            continue
+        Ns = np.sqrt(Nq)
+        w_, x_, y_, z_ = w / Ns, x / Ns, y / Ns, z / Ns
+        wd = 2 * (-z_ * Dm[0, 1] + y_ * Dm[0, 2] + z_ * Dm[1, 0] - x_ * Dm[1, 2] - y_ * Dm[2, 0] + x_ * Dm[2, 1])
+        xd = 2 * (y_ * Dm[0, 1] + z_ * Dm[0, 2] + y_ * Dm[1, 0] - 2 * x_ * Dm[1, 1] - w_ * Dm[1, 2] + z_ * Dm[2, 0]
+                  + w_ * Dm[2, 1] - 2 * x_ * Dm[2, 2])
+        yd = 2 * (-2 * y_ * Dm[0, 0] + x_ * Dm[0, 1] + w_ * Dm[0, 2] + x_ * Dm[1, 0] + z_ * Dm[1, 2] - w_ * Dm[2, 0]
+                  + z_ * Dm[2, 1] - 2 * y_ * Dm[2, 2])
+        zd = 2 * (-2 * z_ * Dm[0, 0] - w_ * Dm[0, 1] + x_ * Dm[0, 2] + w_ * Dm[1, 0] - 2 * z_ * Dm[1, 1]
+                  + y_ * Dm[1, 2] + x_ * Dm[2, 0] + y_ * Dm[2, 1])
+        share = Ns ** 3 * (w * wd + x * xd + y * yd + z * zd)
+        rg[b] = [Ns * wd - w * share, Ns * xd - x * share, Ns * yd - y * share, Ns * zd - z * share]
+    return rg, tg

@@ -1,0 +1,109 @@
+"""CPU: the C-ABI library loads and exports every symbol include/deepim_b200.h declares (no compute
+calls without a GPU), the product package never touches the oracle, the op mirror has the
+reference's surface, and the product fails loudly without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+
+def declared_symbols(root):
+    txt = open(os.path.join(root, "include", "deepim_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"DIM_API\s+[\w\s\*]+?\b(dim_\w+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol(root):
+    so = os.path.join(root, "mx-deepim_b200", "libdeepim_b200.so")
+    assert os.path.exists(so), "run python __graft_entry__.py (build) first"
+    lib = ctypes.CDLL(so)
+    syms = declared_symbols(root)
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(lib, s), "symbol %s declared in the header but not exported" % s
+    lib.dim_abi_version.restype = ctypes.c_int32
+    assert lib.dim_abi_version() == 1
+
+
+def test_ctypes_binding_covers_the_header(root):
+    from deepim_b200 import _capi
+    assert sorted(_capi.SIGNATURES) == declared_symbols(root)
+
+
+def test_no_cpu_fallback_ctx_create_fails_loudly_without_gpu(root):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from deepim_b200 import _capi
+    h = ctypes.c_void_p()
+    rc = _capi.lib.dim_ctx_create(0, 1, 480, 640, 1, 8, 8, ctypes.byref(h))
+    assert rc != 0
+    assert b"no CPU fallback" in _capi.lib.dim_last_error()
+    from deepim_b200.context import Context
+    with pytest.raises(_capi.DeepIMError):
+        Context(0)
+
+
+def test_product_never_imports_or_links_the_oracle(root):
+    pkg = os.path.join(root, "mx-deepim_b200")
+    bad = []
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M) or "liboracle" in src or "deepim_oracle" in src:
+                    bad.append(os.path.join(dp, f))
+    assert not bad, bad
+    # and the shared library has no dependency on it
+    so = os.path.join(pkg, "libdeepim_b200.so")
+    assert b"liboracle" not in open(so, "rb").read()
+
+
+def test_operator_surface_matches_reference_signatures():
+    # names, argument / output lists and string attrs of deepim/operator_py/*.py
+    from deepim_b200 import operator_py as op
+    K = "[572.4114 0 325.2611 0 573.57043 242.04899 0 0 1]"
+    expect = {
+        "ZoomMask": (dict(K=K), ["mask_observed", "mask_gt_observed", "mask_rendered", "src_pose"],
+                     ["zoom_mask_observed", "zoom_mask_gt_observed", "zoom_mask_rendered", "zoom_factor"]),
+        "ZoomImageWithFactor": (dict(pixel_means="[123.68 116.779 103.939]"),
+                                ["zoom_factor", "image_observed", "image_rendered"],
+                                ["zoom_image_observed", "zoom_image_rendered"]),
+        "ZoomMaskWithFactor": (dict(b_inv_zoom="True"), ["zoom_factor", "mask"], ["zoom_mask"]),
+        "ZoomFlow": (dict(b_inv_zoom="False"), ["zoom_factor", "flow", "flow_weights"], ["zoom_flow", "zoom_flow_weights"]),
+        "ZoomTrans": (dict(b_inv_zoom="True"), ["zoom_factor", "trans_delta"], ["zoom_trans_delta"]),
+        "ZoomDepth": (dict(), ["zoom_factor", "depth_observed", "depth_rendered"],
+                      ["zoom_depth_observed", "zoom_depth_rendered"]),
+        "Transform3D": (dict(T_means="[0 0 0]", T_stds="[1 1 1]", rot_coord="CAMERA"),
+                        ["point_cloud", "rotation", "translation", "pose_src"], ["transformed_3d_points"]),
+        "FlowUpdater": (dict(K=K), ["depth_src", "depth_tgt", "pose_src", "pose_tgt"], ["flow", "flow_weights"]),
+    }
+    for name, (kw, args, outs) in expect.items():
+        prop = op.REGISTRY[name](**kw)
+        assert prop.list_arguments() == args and prop.list_outputs() == outs, name
+    inv = op.REGISTRY["ZoomFlow"](b_inv_zoom="True")
+    assert inv.list_arguments() == ["zoom_factor", "flow"] and inv.list_outputs() == ["zoom_flow"]
+    zm = op.REGISTRY["ZoomMask"](K=K, width="640", height="480")
+    np.testing.assert_allclose(zm.K[0], [572.4114, 0, 325.2611], rtol=1e-7)
+    assert zm.infer_shape([[4, 1, 480, 640]] * 3 + [[4, 3, 4]])[1][-1] == [4, 4]
+    zi = op.REGISTRY["ZoomImageWithFactor"](pixel_means="[123.68 116.779 103.939]")
+    np.testing.assert_allclose(zi.pixel_means, [103.939, 116.779, 123.68], rtol=1e-7)  # reversed, l.79-81
+    with pytest.raises(RuntimeError):
+        op.create("ZoomTrans", b_inv_zoom="True")  # no Context set -> loud
+
+
+def test_shard_range_and_chunks():
+    from deepim_b200 import sharding
+    for n in (0, 1, 7, 64, 65, 128):
+        for world in (1, 2, 3, 8):
+            rs = [sharding.shard_range(n, r, world) for r in range(world)]
+            assert rs[0][0] == 0 and rs[-1][1] == n
+            assert all(rs[i][1] == rs[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in rs]
+            assert max(sizes) - min(sizes) <= 1
+    assert sharding.chunks(3, 40, 16) == [(3, 19), (19, 35), (35, 40)]
+    assert sharding.chunks(5, 5, 16) == []
+    with pytest.raises(ValueError):
+        sharding.shard_range(4, 2, 2)
