@@ -306,6 +306,236 @@ __global__ void __launch_bounds__(192) conv_igemm_kernel(const __grid_constant__
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// v2: persistent, warp-specialised, double-buffered TMEM accumulators.
+//   grid = min(#tiles, SMs x CTAs/SM); CTA c walks tiles c, c+G, c+2G ... (tile id = ((m*Nn + n)*S + z),
+//   n fastest so CTAs that share an activation tile run side by side and hit it in L2 together).
+//   The smem ring runs across tile boundaries (the producer is already loading tile t+1 while the
+//   epilogue of tile t drains its accumulator); two TMEM accumulator stages of BLOCK_N columns let the
+//   MMA warp start tile t+1 while warps 2..5 read tile t.
+//   RESIDENT_B (conv1: whole 64 x 512 weight matrix = 64 KB): weights are loaded once per CTA and stay
+//   in shared memory; the ring then carries activation tiles only.
+template <int BLOCK_N, int BLOCK_K, int STAGES, bool SPLIT3, bool RESIDENT_B, int KBLOCKS_RES>
+struct ConvSmem2 {
+  static constexpr int A_BYTES = 128 * BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int NPREC = SPLIT3 ? 2 : 1;
+  static constexpr int STAGE_BYTES = (A_BYTES + (RESIDENT_B ? 0 : B_BYTES)) * NPREC;
+  static constexpr int RES_BYTES = RESIDENT_B ? KBLOCKS_RES * B_BYTES * NPREC : 0;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + RES_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ptx::smem_u32(bar)) : "memory");
+}
+
+template <int BLOCK_N, int BLOCK_K, int STAGES, bool SPLIT3, bool RESIDENT_B, int KBLOCKS_RES>
+__global__ void __launch_bounds__(192) conv_igemm_persistent_kernel(const __grid_constant__ ConvKParams p,
+                                                                    const int total_tiles, const int n_tiles) {
+  using S = ConvSmem2<BLOCK_N, BLOCK_K, STAGES, SPLIT3, RESIDENT_B, KBLOCKS_RES>;
+  constexpr uint32_t LAYOUT = (BLOCK_K == 64) ? 2u : 4u;
+  constexpr uint32_t SBO = 8u * BLOCK_K * 2u;
+  constexpr uint32_t ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t *res = smem + STAGES * S::STAGE_BYTES;  // resident weights (1024-aligned: stage sizes are multiples of 1 KB)
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(res + S::RES_BYTES);
+  uint64_t *empty_bar = full_bar + STAGES;
+  uint64_t *tmem_full_bar = empty_bar + STAGES;   // [2]
+  uint64_t *tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint64_t *res_bar = tmem_empty_bar + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(res_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kb_per = (p.kblocks + p.ksplit - 1) / p.ksplit;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full_bar[a], 1);
+      ptx::mbar_init(&tmem_empty_bar[a], 4);  // one arrive per epilogue warp
+    }
+    ptx::mbar_init(res_bar, 1);
+    ptx::fence_barrier_init();
+    ptx::prefetch_tmap(&p.b_map);
+    ptx::prefetch_tmap(&p.a_map[0]);
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      if (RESIDENT_B) {
+        ptx::mbar_expect_tx(res_bar, (uint32_t)S::RES_BYTES);
+        for (int kb = 0; kb < KBLOCKS_RES; ++kb) {
+          ptx::tma_load_2d(res + kb * S::B_BYTES, &p.b_map, res_bar, kb * BLOCK_K, 0);
+          if (SPLIT3) ptx::tma_load_2d(res + (KBLOCKS_RES + kb) * S::B_BYTES, &p.b_lo_map, res_bar, kb * BLOCK_K, 0);
+        }
+      }
+      const uint32_t tx = (uint32_t)(p.BW * p.BH * BLOCK_K * 2 + (RESIDENT_B ? 0 : BLOCK_N * BLOCK_K * 2)) * S::NPREC;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int z = tile % p.ksplit, mn = tile / p.ksplit;
+        const int nt = mn % n_tiles, mt = mn / n_tiles;
+        const int col_tile = mt % p.n_col_tiles, row_tile = mt / p.n_col_tiles;
+        const int g0 = row_tile * p.BH, ow0 = col_tile * p.BW, n0 = nt * BLOCK_N;
+        const int kb0 = z * kb_per, kb1 = min(p.kblocks, kb0 + kb_per);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
+          const int tap = kb / p.cchunks, cc = kb - tap * p.cchunks;
+          const int kh = tap / p.KW, kw = tap - kh * p.KW;
+          int view = 0, dr = kh, dc = kw;
+          if (p.stride == 2) {
+            view = ((kh & 1) << 1) | (kw & 1);
+            dr = kh >> 1;
+            dc = kw >> 1;
+          }
+          uint8_t *st = smem + s * S::STAGE_BYTES;
+          ptx::mbar_expect_tx(&full_bar[s], tx);
+          ptx::tma_load_3d(st, &p.a_map[view], &full_bar[s], cc * BLOCK_K, ow0 + dc, g0 + dr);
+          uint8_t *nxt = st + S::A_BYTES;
+          if (!RESIDENT_B) {
+            ptx::tma_load_2d(nxt, &p.b_map, &full_bar[s], kb * BLOCK_K, n0);
+            nxt += S::B_BYTES;
+          }
+          if (SPLIT3) {
+            ptx::tma_load_3d(nxt, &p.a_lo_map[view], &full_bar[s], cc * BLOCK_K, ow0 + dc, g0 + dr);
+            if (!RESIDENT_B) ptx::tma_load_2d(nxt + S::A_BYTES, &p.b_lo_map, &full_bar[s], kb * BLOCK_K, n0);
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      if (RESIDENT_B) {
+        ptx::mbar_wait(res_bar, 0);
+        ptx::tc_fence_after();
+      }
+      int s = 0, as = 0;
+      uint32_t ph = 0, aph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int z = tile % p.ksplit;
+        const int kb0 = z * kb_per, kb1 = min(p.kblocks, kb0 + kb_per);
+        ptx::mbar_wait(&tmem_empty_bar[as], aph ^ 1u);  // epilogue has drained this accumulator stage
+        ptx::tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + (uint32_t)as * ACC_COLS;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(&full_bar[s], ph);
+          ptx::tc_fence_after();
+          const uint32_t a_hi = ptx::smem_u32(smem + s * S::STAGE_BYTES);
+          uint32_t b_hi, a_lo, b_lo;
+          if (RESIDENT_B) {
+            b_hi = ptx::smem_u32(res + kb * S::B_BYTES);
+            b_lo = ptx::smem_u32(res + (KBLOCKS_RES + kb) * S::B_BYTES);
+            a_lo = a_hi + S::A_BYTES;
+          } else {
+            b_hi = a_hi + S::A_BYTES;
+            a_lo = b_hi + S::B_BYTES;
+            b_lo = a_lo + S::A_BYTES;
+          }
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
+            const uint64_t da = ptx::umma_desc(a_hi + k * 32, SBO, LAYOUT);
+            const uint64_t db = ptx::umma_desc(b_hi + k * 32, SBO, LAYOUT);
+            ptx::umma_f16(tmem_acc, da, db, p.idesc, acc);
+            if (SPLIT3) {
+              const uint64_t dal = ptx::umma_desc(a_lo + k * 32, SBO, LAYOUT);
+              const uint64_t dbl = ptx::umma_desc(b_lo + k * 32, SBO, LAYOUT);
+              ptx::umma_f16(tmem_acc, dal, db, p.idesc, 1u);
+              ptx::umma_f16(tmem_acc, da, dbl, p.idesc, 1u);
+            }
+          }
+          ptx::umma_commit(&empty_bar[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+        ptx::umma_commit(&tmem_full_bar[as]);
+        if (++as == 2) { as = 0; aph ^= 1u; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int quad = warp & 3;
+    const int m = quad * 32 + lane;
+    const int bh = m / p.BW, bw = m - bh * p.BW;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int z = tile % p.ksplit, mn = tile / p.ksplit;
+      const int nt = mn % n_tiles, mt = mn / n_tiles;
+      const int col_tile = mt % p.n_col_tiles, row_tile = mt / p.n_col_tiles;
+      const int g = row_tile * p.BH + bh, ow = col_tile * p.BW + bw, n0 = nt * BLOCK_N;
+      const int n_img = g / p.Hq, oh = g - n_img * p.Hq;
+      const bool valid = (m < p.BW * p.BH) && (n_img < p.Bn) && (oh < p.Ho) && (ow < p.Wo);
+      ptx::mbar_wait(&tmem_full_bar[as], aph);
+      ptx::tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)as * ACC_COLS;
+      if (p.ksplit > 1) {
+        const size_t opix = ((size_t)n_img * p.Ho + oh) * p.Wo + ow;
+        float *dst = p.partial + ((size_t)z * ((size_t)p.Bn * p.Ho * p.Wo) + opix) * p.Cout + n0;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(trow + c, r);
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<uint4 *>(dst + c + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+          }
+        }
+      } else {
+        const size_t pix = ((size_t)n_img * p.out_Hp + oh + p.out_py) * p.out_Wp + ow + p.out_px;
+        __nv_bfloat16 *dhi = p.out_hi + pix * p.Cout + n0;
+        __nv_bfloat16 *dlo = SPLIT3 ? (p.out_lo + pix * p.Cout + n0) : nullptr;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(trow + c, r);
+          if (valid) {
+            __align__(16) __nv_bfloat16 h[32];
+            __align__(16) __nv_bfloat16 l[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float v = __uint_as_float(r[j]) + __ldg(p.bias + n0 + c + j);
+              v = v > 0.f ? v : v * p.slope;
+              h[j] = __float2bfloat16_rn(v);
+              if (SPLIT3) l[j] = __float2bfloat16_rn(v - __bfloat162float(h[j]));
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              *reinterpret_cast<uint4 *>(dhi + c + j) = *reinterpret_cast<const uint4 *>(h + j);
+              if (SPLIT3) *reinterpret_cast<uint4 *>(dlo + c + j) = *reinterpret_cast<const uint4 *>(l + j);
+            }
+          }
+        }
+      }
+      // all tcgen05.ld of this warp have completed (wait::ld inside tmem_ld_32x32): release the stage
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+      if (++as == 2) { as = 0; aph ^= 1u; }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
 // split-K finalize: sum partials + bias + LeakyReLU -> bf16 (hi[, lo]) into the bordered NHWC buffer
 __global__ void __launch_bounds__(256) conv_splitk_finalize_kernel(const float *partial, int ksplit, int npix,
                                                                    int Cout, int Ho, int Wo, int out_Hp, int out_Wp,

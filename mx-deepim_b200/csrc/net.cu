@@ -3,8 +3,8 @@
 //
 //   conv tower : 10 x conv_igemm_kernel (tcgen05 + TMA, conv_igemm.cuh), split-K + finalize for the
 //                layers whose tile count cannot fill 148 SMs
-//   fc6        : 81920 -> 256, a pure weight stream (HBM-bound): split-K SIMT kernel, deterministic
-//                two-pass reduction (partials are reduced in fixed order by the head kernel)
+//   fc6        : 81920 -> 256, a pure weight stream (HBM-bound): split-K mma.sync kernel (batch = M = 16),
+//                deterministic two-pass reduction (partials reduced in fixed order by the head kernel)
 //   head       : fc6 reduce + bias + LeakyReLU -> fc7 -> LeakyReLU -> rot(4), trans(3) ->
 //                ZoomTrans^-1 (zoom_trans.py:30-31) -> se3 (B,7)
 #include <map>
@@ -33,6 +33,7 @@ struct LayerGeom {
   // implicit GEMM view
   int KH, KW, stride_eff, Ceff, Hq;
   int BLOCK_N, BLOCK_K, BW, BH, n_col_tiles, kblocks;
+  int occ;  // resident CTAs per SM of the persistent kernel variant used for this layer (bf16 mode)
 };
 
 struct TensorMaps {
@@ -47,8 +48,7 @@ struct NetState {
   __nv_bfloat16 *act_hi[11] = {}, *act_lo[11] = {};  // act[i] = input of layer i, act[10] = fc6 input
   size_t act_elems_per_image[11] = {};
   // fc
-  __nv_bfloat16 *fc6_w_bf16 = nullptr;  // [256][81920] in (h,w,c) order
-  float *fc6_w_f32 = nullptr;
+  __nv_bfloat16 *fc6_w_hi = nullptr, *fc6_w_lo = nullptr;  // [256][81920] in (h,w,c) order
   float *fc6_b = nullptr, *fc7_wT = nullptr, *fc7_b = nullptr, *rot_w = nullptr, *rot_b = nullptr,
         *trans_w = nullptr, *trans_b = nullptr;
   float *fc6_partial = nullptr;  // [FC6_SPLITS][max_batch][256]
@@ -60,8 +60,8 @@ struct NetState {
 };
 
 static constexpr int FC6_K = 1024 * 8 * 10;
-static constexpr int FC6_KC = 512;
-static constexpr int FC6_SPLITS = FC6_K / FC6_KC;  // 160
+static constexpr int FC6_KC = 256;
+static constexpr int FC6_SPLITS = FC6_K / FC6_KC;  // 320
 
 // --------------------------------------------------------------------------------- geometry
 static void build_geometry(NetState *ns, int H, int W) {
@@ -87,7 +87,7 @@ static void build_geometry(NetState *ns, int H, int W) {
       g.rows = Hp; g.cols = Wp; g.Cbuf = s.Cin;
       g.KH = g.KW = s.k; g.stride_eff = s.stride; g.Ceff = s.Cin;
       g.Hq = (s.stride == 2) ? Hp / 2 : Hp;
-      g.BLOCK_K = 64; g.BLOCK_N = 128;
+      g.BLOCK_K = 64; g.BLOCK_N = s.Cout >= 256 ? 256 : 128;
     }
     // M tile: BW x BH rectangle of output pixels with BW | Wo and BW*BH <= 128.  Maximise the rows
     // used; keep boxes at least 8 pixels wide (>= 1 KB contiguous per TMA row) when possible.
@@ -103,21 +103,28 @@ static void build_geometry(NetState *ns, int H, int W) {
     g.BW = best_bw; g.BH = 128 / best_bw;
     g.n_col_tiles = g.Wo > 0 ? g.Wo / g.BW : 0;
     g.kblocks = g.KH * g.KW * (g.Ceff / g.BLOCK_K);
+    g.occ = (g.BLOCK_N <= 128) ? 2 : 1;
     h = g.Ho; w = g.Wo;
   }
 }
 
+// split-K factor: maximise the fill of the last wave of the persistent grid (capacity = SMs x CTAs/SM)
+// with a small penalty per extra slice (fp32 partial traffic); every slice keeps >= 8 K-blocks.
 static int choose_ksplit(const NetState *ns, const LayerGeom &g, int B) {
-  const int row_tiles = cdiv(B * g.Hq, g.BH);
-  const int ctas = row_tiles * g.n_col_tiles * (g.Cout / g.BLOCK_N);
-  const int target = 2 * ns->num_sms;
-  if (ctas >= target || g.kblocks < 16) return 1;
-  int ks = cdiv(target, ctas);
-  if (ks > 8) ks = 8;
-  while (ks > 1 && g.kblocks / ks < 8) --ks;
-  // every K slice must be non-empty (an empty slice would publish an unwritten accumulator)
-  while (ks > 1 && (ks - 1) * cdiv(g.kblocks, ks) >= g.kblocks) --ks;
-  return ks;
+  const int tiles = cdiv(B * g.Hq, g.BH) * g.n_col_tiles * (g.Cout / g.BLOCK_N);
+  const int cap = ns->num_sms * g.occ;
+  if (tiles >= 2 * cap || g.kblocks < 16 || g.BLOCK_K == 32) return 1;  // conv1 keeps its weights resident: no split
+  int best = 1;
+  double best_score = -1.0;
+  for (int ks = 1; ks <= 8; ++ks) {
+    if (ks > 1 && g.kblocks / ks < 8) break;
+    if (ks > 1 && (ks - 1) * cdiv(g.kblocks, ks) >= g.kblocks) continue;  // no empty K slice
+    const int t = tiles * ks;
+    const double util = (double)t / (double)(cdiv(t, cap) * cap);
+    const double score = util - 0.03 * (ks - 1);
+    if (score > best_score + 1e-9) { best_score = score; best = ks; }
+  }
+  return best;
 }
 
 // --------------------------------------------------------------------------------- tensor maps
@@ -217,49 +224,86 @@ static int build_maps(NetState *ns, int B, TensorMaps &tm) {
 }
 
 // --------------------------------------------------------------------------------- fc6 + head
-// fc6 split-K: CTA s handles k in [s*KC, (s+1)*KC) for all 256 outputs and all B instances.
-// Weight stream (bf16: 42 MB, fp32: 84 MB) is read exactly once, coalesced along k.
-template <bool F32W>
-__global__ void __launch_bounds__(256) fc6_splitk_kernel(const __nv_bfloat16 *__restrict__ act_hi,
-                                                         const __nv_bfloat16 *__restrict__ act_lo,
-                                                         const __nv_bfloat16 *__restrict__ w_bf16,
-                                                         const float *__restrict__ w_f32, int B, int max_batch,
-                                                         float *__restrict__ partial) {
-  constexpr int MAXB = 16;
-  __shared__ float act_s[MAXB][FC6_KC + 4];
+// fc6 split-K on the legacy tensor path: the batch (<= 16 instances) is exactly the M = 16 of
+// mma.sync.m16n8k16, so each warp streams its weight rows once (16 B per lane, K-permuted so that the
+// 8 consecutive bf16 a lane loads feed two MMA steps) and multiplies them against the activation
+// chunk staged in shared memory.  HBM-bound by design: 42 MB of bf16 weights per call (84 MB with the
+// lo halves in bf16x3 mode).  CTA s owns k in [s*KC, (s+1)*KC) for all 256 outputs; partials are
+// reduced in fixed order by the head kernel (deterministic, no atomics).
+__device__ __forceinline__ void mma_bf16_16816(float *c, const uint32_t *a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <bool S3>
+__global__ void __launch_bounds__(256) fc6_mma_kernel(const __nv_bfloat16 *__restrict__ act_hi,
+                                                      const __nv_bfloat16 *__restrict__ act_lo,
+                                                      const __nv_bfloat16 *__restrict__ w_hi,
+                                                      const __nv_bfloat16 *__restrict__ w_lo, int B, int max_batch,
+                                                      float *__restrict__ partial) {
+  constexpr int PITCH = FC6_KC * 2 + 64;  // bytes; +64 keeps the 16-B fragment loads conflict-free
+  __shared__ __align__(16) uint8_t a_hi_s[16 * PITCH];
+  __shared__ __align__(16) uint8_t a_lo_s[S3 ? 16 * PITCH : 16];
   const int s = blockIdx.x, k0 = s * FC6_KC;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int b0 = 0; b0 < B; b0 += MAXB) {
-    const int nb = min(MAXB, B - b0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+  for (int b0 = 0; b0 < B; b0 += 16) {
+    const int nb = min(16, B - b0);
     __syncthreads();
-    for (int idx = threadIdx.x; idx < MAXB * FC6_KC; idx += blockDim.x) {
-      const int b = idx / FC6_KC, k = idx - b * FC6_KC;
-      float v = 0.f;
-      if (b < nb) {
-        const size_t o = (size_t)(b0 + b) * FC6_K + k0 + k;
-        v = __bfloat162float(act_hi[o]);
-        if (act_lo) v += __bfloat162float(act_lo[o]);
+    for (int idx = threadIdx.x; idx < 16 * (FC6_KC / 8); idx += blockDim.x) {
+      const int r = idx / (FC6_KC / 8), c8 = idx - r * (FC6_KC / 8);
+      uint4 vh = make_uint4(0, 0, 0, 0), vl = make_uint4(0, 0, 0, 0);
+      if (r < nb) {
+        const size_t o = (size_t)(b0 + r) * FC6_K + k0 + c8 * 8;
+        vh = *reinterpret_cast<const uint4 *>(act_hi + o);
+        if (S3) vl = *reinterpret_cast<const uint4 *>(act_lo + o);
       }
-      act_s[b][k] = v;
+      *reinterpret_cast<uint4 *>(a_hi_s + r * PITCH + c8 * 16) = vh;
+      if (S3) *reinterpret_cast<uint4 *>(a_lo_s + r * PITCH + c8 * 16) = vl;
     }
     __syncthreads();
-    for (int j = warp; j < 256; j += 8) {
-      float acc[MAXB];
+    float acc[4][4];
 #pragma unroll
-      for (int b = 0; b < MAXB; ++b) acc[b] = 0.f;
-#pragma unroll 4
-      for (int k = lane; k < FC6_KC; k += 32) {
-        const size_t wo = (size_t)j * FC6_K + k0 + k;
-        const float wv = F32W ? w_f32[wo] : __bfloat162float(w_bf16[wo]);
+    for (int t = 0; t < 4; ++t)
 #pragma unroll
-        for (int b = 0; b < MAXB; ++b) acc[b] = fmaf(wv, act_s[b][k], acc[b]);
+      for (int e = 0; e < 4; ++e) acc[t][e] = 0.f;
+#pragma unroll 2
+    for (int kc = 0; kc < FC6_KC; kc += 32) {
+      // activation fragments for both MMA steps of this 32-k chunk: rows g and g+8, 8 bf16 each
+      const uint4 ah0 = *reinterpret_cast<const uint4 *>(a_hi_s + g * PITCH + (kc + q * 8) * 2);
+      const uint4 ah1 = *reinterpret_cast<const uint4 *>(a_hi_s + (g + 8) * PITCH + (kc + q * 8) * 2);
+      const uint32_t A0[4] = {ah0.x, ah1.x, ah0.y, ah1.y}, A1[4] = {ah0.z, ah1.z, ah0.w, ah1.w};
+      uint32_t L0[4] = {0, 0, 0, 0}, L1[4] = {0, 0, 0, 0};
+      if (S3) {
+        const uint4 al0 = *reinterpret_cast<const uint4 *>(a_lo_s + g * PITCH + (kc + q * 8) * 2);
+        const uint4 al1 = *reinterpret_cast<const uint4 *>(a_lo_s + (g + 8) * PITCH + (kc + q * 8) * 2);
+        L0[0] = al0.x; L0[1] = al1.x; L0[2] = al0.y; L0[3] = al1.y;
+        L1[0] = al0.z; L1[1] = al1.z; L1[2] = al0.w; L1[3] = al1.w;
       }
 #pragma unroll
-      for (int b = 0; b < MAXB; ++b) {
-        float v = acc[b];
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0 && b < nb) partial[((size_t)s * max_batch + b0 + b) * 256 + j] = v;
+      for (int t = 0; t < 4; ++t) {
+        const int j = warp * 32 + t * 8 + g;  // output row whose weights this lane streams
+        const size_t wo = (size_t)j * FC6_K + k0 + kc + q * 8;
+        const uint4 wh = __ldg(reinterpret_cast<const uint4 *>(w_hi + wo));
+        mma_bf16_16816(acc[t], A0, wh.x, wh.y);
+        mma_bf16_16816(acc[t], A1, wh.z, wh.w);
+        if (S3) {
+          const uint4 wl = __ldg(reinterpret_cast<const uint4 *>(w_lo + wo));
+          mma_bf16_16816(acc[t], L0, wh.x, wh.y);
+          mma_bf16_16816(acc[t], L1, wh.z, wh.w);
+          mma_bf16_16816(acc[t], A0, wl.x, wl.y);
+          mma_bf16_16816(acc[t], A1, wl.z, wl.w);
+        }
       }
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int j = warp * 32 + t * 8 + q * 2;
+      if (g < nb)
+        *reinterpret_cast<float2 *>(partial + ((size_t)s * max_batch + b0 + g) * 256 + j) = make_float2(acc[t][0], acc[t][1]);
+      if (g + 8 < nb)
+        *reinterpret_cast<float2 *>(partial + ((size_t)s * max_batch + b0 + g + 8) * 256 + j) = make_float2(acc[t][2], acc[t][3]);
     }
   }
 }
@@ -418,10 +462,10 @@ int net_load(dim_ctx *ctx, const float *const *W, const float *const *Bv) {
     for (int o = 0; o < 256; ++o)
       for (int c = 0; c < 1024; ++c)
         for (int hw = 0; hw < 80; ++hw) p[(size_t)o * FC6_K + (size_t)hw * 1024 + c] = W[10][(size_t)o * FC6_K + (size_t)c * 80 + hw];
-    std::vector<__nv_bfloat16> hb(p.size());
-    for (size_t i = 0; i < p.size(); ++i) hb[i] = __float2bfloat16_rn(p[i]);
-    if (int rc = upload(ctx, &ns->fc6_w_bf16, hb)) return rc;
-    if (int rc = upload(ctx, &ns->fc6_w_f32, p)) return rc;
+    std::vector<__nv_bfloat16> hb, lb;
+    split_bf16(p.data(), p.size(), hb, lb);
+    if (int rc = upload(ctx, &ns->fc6_w_hi, hb)) return rc;
+    if (int rc = upload(ctx, &ns->fc6_w_lo, lb)) return rc;
     if (int rc = upload(ctx, &ns->fc6_b, std::vector<float>(Bv[10], Bv[10] + 256))) return rc;
     std::vector<float> t((size_t)256 * 256);
     for (int o = 0; o < 256; ++o)
@@ -437,16 +481,17 @@ int net_load(dim_ctx *ctx, const float *const *W, const float *const *Bv) {
   return 0;
 }
 
-template <int BN, int BK, int ST, bool S3>
-static int launch_conv(const ConvKParams &kp, dim3 grid, cudaStream_t st) {
-  using S = ConvSmem<BN, BK, ST, S3>;
+template <int BN, int BK, int ST, bool S3, bool RES, int KRES>
+static int launch_conv2(const ConvKParams &kp, int total_tiles, int n_tiles, int cap, cudaStream_t st) {
+  using S = ConvSmem2<BN, BK, ST, S3, RES, KRES>;
   static bool attr_set = false;
   if (!attr_set) {
-    DIM_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<BN, BK, ST, S3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   S::TOTAL));
+    DIM_CHECK(cudaFuncSetAttribute(conv_igemm_persistent_kernel<BN, BK, ST, S3, RES, KRES>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     attr_set = true;
   }
-  conv_igemm_kernel<BN, BK, ST, S3><<<grid, 192, S::TOTAL, st>>>(kp);
+  const int grid = total_tiles < cap ? total_tiles : cap;
+  conv_igemm_persistent_kernel<BN, BK, ST, S3, RES, KRES><<<grid, 192, S::TOTAL, st>>>(kp, total_tiles, n_tiles);
   DIM_LAUNCH_CHECK();
   return 0;
 }
@@ -475,10 +520,19 @@ int net_forward(dim_ctx *ctx, int B, int precision, const float *zoom_factor, fl
   for (int i = 0; i < 10; ++i) {
     const LayerGeom &g = ns->g[i];
     const ConvKParams &kp = tm.kp[i];
-    dim3 grid(cdiv(B * g.Hq, g.BH) * g.n_col_tiles, g.Cout / g.BLOCK_N, kp.ksplit);
+    const int n_tiles = g.Cout / g.BLOCK_N;
+    const int total_tiles = cdiv(B * g.Hq, g.BH) * g.n_col_tiles * n_tiles * kp.ksplit;
+    const int sms = ns->num_sms;
     int rc;
-    if (i == 0) rc = s3 ? launch_conv<64, 32, 6, true>(kp, grid, st) : launch_conv<64, 32, 6, false>(kp, grid, st);
-    else rc = s3 ? launch_conv<128, 64, 3, true>(kp, grid, st) : launch_conv<128, 64, 3, false>(kp, grid, st);
+    if (g.BLOCK_N == 64)  // conv1: resident 64 x 512 weight matrix, 64B-swizzled K = 32 blocks
+      rc = s3 ? launch_conv2<64, 32, 4, true, true, 16>(kp, total_tiles, n_tiles, sms, st)
+              : launch_conv2<64, 32, 5, false, true, 16>(kp, total_tiles, n_tiles, 2 * sms, st);
+    else if (g.BLOCK_N == 128)
+      rc = s3 ? launch_conv2<128, 64, 3, true, false, 0>(kp, total_tiles, n_tiles, sms, st)
+              : launch_conv2<128, 64, 3, false, false, 0>(kp, total_tiles, n_tiles, 2 * sms, st);
+    else
+      rc = s3 ? launch_conv2<256, 64, 2, true, false, 0>(kp, total_tiles, n_tiles, sms, st)
+              : launch_conv2<256, 64, 4, false, false, 0>(kp, total_tiles, n_tiles, sms, st);
     if (rc) return rc;
     if (kp.ksplit > 1) {
       const int npix = B * g.Ho * g.Wo;
@@ -491,11 +545,11 @@ int net_forward(dim_ctx *ctx, int B, int precision, const float *zoom_factor, fl
   }
   if (after_conv) DIM_CHECK(cudaEventRecord(after_conv, st));
   if (s3)
-    fc6_splitk_kernel<true><<<FC6_SPLITS, 256, 0, st>>>(ns->act_hi[10], ns->act_lo[10], nullptr, ns->fc6_w_f32, B,
-                                                        ctx->max_batch, ns->fc6_partial);
+    fc6_mma_kernel<true><<<FC6_SPLITS, 256, 0, st>>>(ns->act_hi[10], ns->act_lo[10], ns->fc6_w_hi, ns->fc6_w_lo, B,
+                                                     ctx->max_batch, ns->fc6_partial);
   else
-    fc6_splitk_kernel<false><<<FC6_SPLITS, 256, 0, st>>>(ns->act_hi[10], nullptr, ns->fc6_w_bf16, nullptr, B,
-                                                         ctx->max_batch, ns->fc6_partial);
+    fc6_mma_kernel<false><<<FC6_SPLITS, 256, 0, st>>>(ns->act_hi[10], nullptr, ns->fc6_w_hi, nullptr, B,
+                                                      ctx->max_batch, ns->fc6_partial);
   DIM_LAUNCH_CHECK();
   head_kernel<<<B, 256, 0, st>>>(ns->fc6_partial, ctx->max_batch, ns->fc6_b, ns->fc7_wT, ns->fc7_b, ns->rot_w,
                                  ns->rot_b, ns->trans_w, ns->trans_b, zoom_factor, rot_out, trans_out, se3_out);

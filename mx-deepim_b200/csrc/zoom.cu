@@ -298,12 +298,8 @@ struct FusedZoomParams {
   __nv_bfloat16 *hi, *lo;  // [B,Hp,Wp,8]
 };
 
-__global__ void __launch_bounds__(256) zoom_fused_nhwc8_kernel(FusedZoomParams p) {
-  const int b = blockIdx.y;
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= p.H * p.W) return;
-  const int i = q / p.W, j = q % p.W;
-  const float *zf = p.zoom_factor + 4 * b;
+__device__ __forceinline__ void zoom_fused_pixel(const FusedZoomParams &p, int b, int i, int j, const float *zf,
+                                                 __nv_bfloat16 *h, __nv_bfloat16 *l) {
   const Tap t = src_coord(i, j, zf[0], zf[1], zf[2], zf[3], p.H, p.W, p.stepx, p.stepy);
   const size_t P = (size_t)p.H * p.W;
   float v[8];
@@ -325,17 +321,39 @@ __global__ void __launch_bounds__(256) zoom_fused_nhwc8_kernel(FusedZoomParams p
                   br * (1.0f - wy1) * (1.0f - wx1));
   }
   v[7] = roundf(bilinear<1>(p.mask_rendered + (size_t)b * P, p.H, p.W, t, 0.f));
-  __align__(16) __nv_bfloat16 h[8];
-  __align__(16) __nv_bfloat16 l[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     h[c] = __float2bfloat16_rn(v[c]);
     l[c] = __float2bfloat16_rn(v[c] - __bfloat162float(h[c]));
   }
-  const int oi = i + p.pad, oj = j + p.pad;
-  const size_t o = ((((size_t)b * p.Hs + (oi >> 1)) * p.Ws + (oj >> 1)) * 4 + ((oi & 1) * 2 + (oj & 1))) * 8;
-  *reinterpret_cast<uint4 *>(p.hi + o) = *reinterpret_cast<const uint4 *>(h);
-  if (p.lo) *reinterpret_cast<uint4 *>(p.lo + o) = *reinterpret_cast<const uint4 *>(l);
+}
+
+// one thread per space-to-depth pixel = a 2x2 quad of output pixels = one full 64-B line of conv1's
+// input (a warp writes 2 KB contiguous); border slots are rewritten with zeros.
+__global__ void __launch_bounds__(128) zoom_fused_nhwc8_kernel(FusedZoomParams p) {
+  const int b = blockIdx.y;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= p.Hs * p.Ws) return;
+  const int sr = q / p.Ws, sc = q - sr * p.Ws;
+  const float *zf = p.zoom_factor + 4 * b;
+  __align__(16) __nv_bfloat16 h[4][8];
+  __align__(16) __nv_bfloat16 l[4][8];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const int i = 2 * sr + (s >> 1) - p.pad, j = 2 * sc + (s & 1) - p.pad;
+    if (i >= 0 && i < p.H && j >= 0 && j < p.W) {
+      zoom_fused_pixel(p, b, i, j, zf, h[s], l[s]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) { h[s][c] = __float2bfloat16_rn(0.f); l[s][c] = __float2bfloat16_rn(0.f); }
+    }
+  }
+  const size_t o = (((size_t)b * p.Hs + sr) * p.Ws + sc) * 32;
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    *reinterpret_cast<uint4 *>(p.hi + o + s * 8) = *reinterpret_cast<const uint4 *>(h[s]);
+    if (p.lo) *reinterpret_cast<uint4 *>(p.lo + o + s * 8) = *reinterpret_cast<const uint4 *>(l[s]);
+  }
 }
 
 int zoom_fused_launch(dim_ctx *ctx, const float *image_observed, const float *image_rendered,
@@ -349,7 +367,7 @@ int zoom_fused_launch(dim_ctx *ctx, const float *image_observed, const float *im
   p.stepx = (float)(2.0 / (double)(ctx->W - 1));
   p.stepy = (float)(2.0 / (double)(ctx->H - 1));
   p.hi = hi; p.lo = lo;
-  zoom_fused_nhwc8_kernel<<<dim3(cdiv(ctx->H * ctx->W, 256), B), 256, 0, st>>>(p);
+  zoom_fused_nhwc8_kernel<<<dim3(cdiv(Hs * Ws, 128), B), 128, 0, st>>>(p);
   DIM_LAUNCH_CHECK();
   return 0;
 }

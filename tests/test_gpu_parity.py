@@ -385,10 +385,13 @@ def test_refine_is_deterministic_and_batch_consistent(ctx, loop_case):
                    precision=capi.PREC_BF16)
     assert torch.equal(p["bbox"], a["bbox"][:, perm])
     assert (p["poses"] - a["poses"][:, perm]).abs().max().item() < 1e-5
-    # a single instance alone (different split-K schedule -> different fp32 summation order)
-    s = ctx.refine(dev(c["img"][1:2]), dev(c["cls"][1:2]), dev(c["ini"][1:2]), K, 4, pixel_means_rgb=MEANS,
-                   precision=capi.PREC_BF16)
-    assert (s["poses"][:, 0] - a["poses"][:, 1]).abs().max().item() < 1e-4
+    # a single instance alone (different tile / split-K schedule -> different fp32 summation order;
+    # the difference is then carried through 4 render-and-compare iterations)
+    for prec, tol in ((capi.PREC_BF16X3, 1e-4), (capi.PREC_BF16, 2e-3)):
+        full = ctx.refine(*args, pixel_means_rgb=MEANS, precision=prec)
+        s = ctx.refine(dev(c["img"][1:2]), dev(c["cls"][1:2]), dev(c["ini"][1:2]), K, 4, pixel_means_rgb=MEANS,
+                       precision=prec)
+        assert (s["poses"][:, 0] - full["poses"][:, 1]).abs().max().item() < tol
 
 
 def test_refine_host_matches_device_path(ctx, meshes, loop_case):
