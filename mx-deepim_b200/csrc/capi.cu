@@ -18,7 +18,7 @@ void set_error(const char *fmt, ...) {
 
 // implemented in raster.cu / zoom.cu / geom.cu / net.cu
 int render_launch(dim_ctx *, const int *, const float *, int, const float *, float, float, const double *, int, float *,
-                  float *, float *, float *, int *, cudaStream_t);
+                  float *, float *, float *, int *, float4 *, cudaStream_t);
 int zoom_gather_launch(dim_ctx *, int mode, const float *src, float *dst, const float *zf, int B, int C, int inv,
                        const float *param, cudaStream_t);
 int zoom_factor_launch(dim_ctx *, const float *, const float *, int C, const float *, int B, const float *K9, float *,
@@ -26,8 +26,10 @@ int zoom_factor_launch(dim_ctx *, const float *, const float *, int C, const flo
 int zoom_factor_from_ren_launch(dim_ctx *, const int *, const float *, int B, const float *K9, float *, int *, int *,
                                 cudaStream_t);
 int box_mask_launch(dim_ctx *, const int *, int B, float *, cudaStream_t);
-int zoom_fused_launch(dim_ctx *, const float *, const float *, const float *, const float *, const float *, int B,
-                      int Hs, int Ws, int pad, __nv_bfloat16 *, __nv_bfloat16 *, cudaStream_t);
+int zoom_fused_launch(dim_ctx *, const float4 *, const float4 *, const float *, const float *, int B, int Hs, int Ws,
+                      int pad, __nv_bfloat16 *, __nv_bfloat16 *, cudaStream_t);
+int pack_obs4_launch(dim_ctx *, const float *, int B, float4 *, cudaStream_t);
+int transform_u8_obs4_launch(dim_ctx *, const uint8_t *, int B, const double *, float4 *, cudaStream_t);
 int pack_nhwc8_launch(dim_ctx *, const float *, const float *, const float *, const float *, int B, int Hs, int Ws,
                       int pad, __nv_bfloat16 *, __nv_bfloat16 *, cudaStream_t);
 int flow_launch(dim_ctx *, const float *, const float *, const float *, const float *, int B, float *, float *,
@@ -112,7 +114,8 @@ DIM_API int32_t dim_ctx_create(int32_t device, int32_t max_batch, int32_t H, int
   rc |= ctx_alloc(ctx, &ctx->pose_cur, Bm * 12);
   rc |= ctx_alloc(ctx, &ctx->pose_cur_f32, Bm * 12);
   rc |= ctx_alloc(ctx, &ctx->se3_cur, Bm * 7);
-  rc |= ctx_alloc(ctx, &ctx->image_observed_f32, Bm * 3 * P);
+  rc |= ctx_alloc(ctx, &ctx->ren4, Bm * P);
+  rc |= ctx_alloc(ctx, &ctx->obs4, Bm * P);
   rc |= ctx_alloc(ctx, &ctx->image_observed_u8, Bm * 3 * P);
   rc |= ctx_alloc(ctx, &ctx->cls_dev, Bm);
   rc |= ctx_alloc(ctx, &ctx->poses_dev, 8 * Bm * 12);
@@ -163,7 +166,7 @@ DIM_API int32_t dim_render(dim_ctx *ctx, const int32_t *cls_idx, const float *po
                            float *out_depth, float *out_mask, float *out_bgr, int32_t *out_bbox, void *stream) {
   DIM_REQUIRE(ctx && cls_idx && pose && K9, "dim_render: NULL argument");
   return render_launch(ctx, cls_idx, pose, B, K9, zn, zf, means, trunc_u8, out_image, out_depth, out_mask, out_bgr,
-                       out_bbox, (cudaStream_t)stream);
+                       out_bbox, nullptr, (cudaStream_t)stream);
 }
 
 DIM_API int32_t dim_zoom_mask_fwd(dim_ctx *ctx, const float *mo, const float *mgt, const float *mr,
@@ -279,14 +282,10 @@ DIM_API int32_t dim_transform_image_u8(dim_ctx *ctx, const uint8_t *bgr, int32_t
   return transform_u8_launch(ctx, bgr, B, means, image, (cudaStream_t)stream);
 }
 
-DIM_API int32_t dim_refine(dim_ctx *ctx, const float *image_observed, const int32_t *cls_idx, const double *pose_init,
-                           int32_t B, int32_t n_iter, const float *K9, float zn, float zf, const double *means,
-                           int32_t precision, const double *pose_override, double *poses, float *se3,
-                           float *zoom_factor, int32_t *bbox, void *stream) {
-  DIM_REQUIRE(ctx && image_observed && cls_idx && pose_init && K9 && means && poses, "dim_refine: NULL argument");
-  DIM_REQUIRE(B >= 1 && B <= ctx->max_batch, "dim_refine: batch exceeds max_batch");
-  DIM_REQUIRE(n_iter >= 1, "dim_refine: n_iter must be >= 1");
-  cudaStream_t st = (cudaStream_t)stream;
+static int refine_core(dim_ctx *ctx, const float4 *obs4, const int32_t *cls_idx, const double *pose_init, int32_t B,
+                       int32_t n_iter, const float *K9, float zn, float zf, const double *means, int32_t precision,
+                       const double *pose_override, double *poses, float *se3, float *zoom_factor, int32_t *bbox,
+                       cudaStream_t st) {
   const double Tm[3] = {0, 0, 0}, Ts[3] = {1, 1, 1};  // trans_means / trans_stds of the shipped config
   const float means_f[3] = {(float)means[0], (float)means[1], (float)means[2]};
   int rows, cols, pad; __nv_bfloat16 *hi, *lo;
@@ -307,17 +306,18 @@ DIM_API int32_t dim_refine(dim_ctx *ctx, const float *image_observed, const int3
     if (pose_override) pose_src = pose_override + (size_t)it * B * 12;
     // src_pose blob is float32 (nd.array), the host pose stays float64 (tester.py:391)
     if (int rc = f64_to_f32_launch(pose_src, ctx->pose_cur_f32, B * 12, st)) return rc;
-    // render at the current pose (tester.py:427-442); mask_observed := box(mask_rendered) is analytic
-    if (int rc = render_launch(ctx, cls_idx, ctx->pose_cur_f32, B, K9, zn, zf, means, 1, ctx->image_rendered, nullptr,
-                               ctx->mask_rendered, nullptr, nullptr, st))
+    // render at the current pose (tester.py:427-442) straight into the pixel-interleaved
+    // (R,G,B,mask) image the zoom kernel samples; mask_observed := box(mask_rendered) is analytic
+    if (int rc = render_launch(ctx, cls_idx, ctx->pose_cur_f32, B, K9, zn, zf, means, 1, nullptr, nullptr, nullptr,
+                               nullptr, nullptr, ctx->ren4, st))
       return rc;
     if (ev) DIM_CHECK(cudaEventRecord(ev[1], st));
     float *zf_it = zoom_factor ? zoom_factor + (size_t)it * B * 4 : ctx->zoom_factor;
     int *bbox_it = bbox ? bbox + (size_t)it * B * 8 : nullptr;
     if (int rc = zoom_factor_from_ren_launch(ctx, ctx->bbox_ren, ctx->pose_cur_f32, B, K9, zf_it, bbox_it, ctx->status, st))
       return rc;
-    if (int rc = zoom_fused_launch(ctx, image_observed, ctx->image_rendered, ctx->mask_rendered, zf_it, means_f, B,
-                                   rows, cols, pad, hi, precision == DIM_PREC_BF16X3 ? lo : nullptr, st))
+    if (int rc = zoom_fused_launch(ctx, obs4, ctx->ren4, zf_it, means_f, B, rows, cols, pad, hi,
+                                   precision == DIM_PREC_BF16X3 ? lo : nullptr, st))
       return rc;
     if (ev) DIM_CHECK(cudaEventRecord(ev[2], st));
     float *se3_it = se3 ? se3 + (size_t)it * B * 7 : ctx->se3_cur;
@@ -328,6 +328,19 @@ DIM_API int32_t dim_refine(dim_ctx *ctx, const float *image_observed, const int3
     pose_src = pose_out;
   }
   return 0;
+}
+
+DIM_API int32_t dim_refine(dim_ctx *ctx, const float *image_observed, const int32_t *cls_idx, const double *pose_init,
+                           int32_t B, int32_t n_iter, const float *K9, float zn, float zf, const double *means,
+                           int32_t precision, const double *pose_override, double *poses, float *se3,
+                           float *zoom_factor, int32_t *bbox, void *stream) {
+  DIM_REQUIRE(ctx && image_observed && cls_idx && pose_init && K9 && means && poses, "dim_refine: NULL argument");
+  DIM_REQUIRE(B >= 1 && B <= ctx->max_batch, "dim_refine: batch exceeds max_batch");
+  DIM_REQUIRE(n_iter >= 1, "dim_refine: n_iter must be >= 1");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = pack_obs4_launch(ctx, image_observed, B, ctx->obs4, st)) return rc;
+  return refine_core(ctx, ctx->obs4, cls_idx, pose_init, B, n_iter, K9, zn, zf, means, precision, pose_override, poses,
+                     se3, zoom_factor, bbox, st);
 }
 
 DIM_API int32_t dim_refine_host(dim_ctx *ctx, const uint8_t *img_u8, const int32_t *cls_host, const double *pose_host,
@@ -341,9 +354,9 @@ DIM_API int32_t dim_refine_host(dim_ctx *ctx, const uint8_t *img_u8, const int32
   DIM_CHECK(cudaMemcpyAsync(ctx->image_observed_u8, img_u8, (size_t)B * 3 * P, cudaMemcpyHostToDevice, st));
   DIM_CHECK(cudaMemcpyAsync(ctx->cls_dev, cls_host, sizeof(int) * B, cudaMemcpyHostToDevice, st));
   DIM_CHECK(cudaMemcpyAsync(ctx->pose_cur, pose_host, sizeof(double) * B * 12, cudaMemcpyHostToDevice, st));
-  if (int rc = transform_u8_launch(ctx, ctx->image_observed_u8, B, means, ctx->image_observed_f32, st)) return rc;
-  if (int rc = dim_refine(ctx, ctx->image_observed_f32, ctx->cls_dev, ctx->pose_cur, B, n_iter, K9, zn, zf, means,
-                          precision, nullptr, ctx->poses_dev, ctx->se3_hist_dev, nullptr, nullptr, stream))
+  if (int rc = transform_u8_obs4_launch(ctx, ctx->image_observed_u8, B, means, ctx->obs4, st)) return rc;
+  if (int rc = refine_core(ctx, ctx->obs4, ctx->cls_dev, ctx->pose_cur, B, n_iter, K9, zn, zf, means, precision,
+                           nullptr, ctx->poses_dev, ctx->se3_hist_dev, nullptr, nullptr, st))
     return rc;
   DIM_CHECK(cudaMemcpyAsync(poses_out, ctx->poses_dev, sizeof(double) * (size_t)n_iter * B * 12, cudaMemcpyDeviceToHost, st));
   if (se3_out)

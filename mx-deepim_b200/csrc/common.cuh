@@ -94,7 +94,7 @@ struct dim_ctx {
   double *pose_cur = nullptr;  // [max_batch,3,4]
   float *pose_cur_f32 = nullptr;
   float *se3_cur = nullptr;  // [max_batch,7]
-  float *image_observed_f32 = nullptr;  // for dim_refine_host
+  float4 *ren4 = nullptr, *obs4 = nullptr;  // [max_batch,H,W] pixel-interleaved images of the fused loop
   uint8_t *image_observed_u8 = nullptr;
   int *cls_dev = nullptr;
   double *poses_dev = nullptr;  // [8, max_batch, 12]

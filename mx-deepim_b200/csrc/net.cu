@@ -121,7 +121,7 @@ static int choose_ksplit(const NetState *ns, const LayerGeom &g, int B) {
     if (ks > 1 && (ks - 1) * cdiv(g.kblocks, ks) >= g.kblocks) continue;  // no empty K slice
     const int t = tiles * ks;
     const double util = (double)t / (double)(cdiv(t, cap) * cap);
-    const double score = util - 0.03 * (ks - 1);
+    const double score = util - 0.06 * (ks - 1);
     if (score > best_score + 1e-9) { best_score = score; best = ks; }
   }
   return best;
@@ -308,28 +308,40 @@ __global__ void __launch_bounds__(256) fc6_mma_kernel(const __nv_bfloat16 *__res
   }
 }
 
-// one CTA per instance
-__global__ void __launch_bounds__(256) head_kernel(const float *__restrict__ partial, int max_batch,
-                                                   const float *__restrict__ fc6_b, const float *__restrict__ fc7_wT,
-                                                   const float *__restrict__ fc7_b, const float *__restrict__ rot_w,
-                                                   const float *__restrict__ rot_b, const float *__restrict__ trans_w,
-                                                   const float *__restrict__ trans_b,
-                                                   const float *__restrict__ zoom_factor /*nullable*/,
-                                                   float *__restrict__ rot_out, float *__restrict__ trans_out,
-                                                   float *__restrict__ se3_out) {
+// one CTA of 1024 threads per instance: 4 thread groups share the fc6 split reduction and the fc7
+// reduction (fixed summation order -> deterministic)
+__global__ void __launch_bounds__(1024) head_kernel(const float *__restrict__ partial, int max_batch,
+                                                    const float *__restrict__ fc6_b, const float *__restrict__ fc7_wT,
+                                                    const float *__restrict__ fc7_b, const float *__restrict__ rot_w,
+                                                    const float *__restrict__ rot_b, const float *__restrict__ trans_w,
+                                                    const float *__restrict__ trans_b,
+                                                    const float *__restrict__ zoom_factor /*nullable*/,
+                                                    float *__restrict__ rot_out, float *__restrict__ trans_out,
+                                                    float *__restrict__ se3_out) {
+  __shared__ float red[4][256];
   __shared__ float h6[256], h7[256], outv[8];
-  const int b = blockIdx.x, j = threadIdx.x;
+  const int b = blockIdx.x, j = threadIdx.x & 255, grp = threadIdx.x >> 8;
   float a = 0.f;
-  for (int s = 0; s < FC6_SPLITS; ++s) a += partial[((size_t)s * max_batch + b) * 256 + j];
-  a += fc6_b[j];
-  h6[j] = a > 0.f ? a : 0.1f * a;
+#pragma unroll 8
+  for (int s = grp; s < FC6_SPLITS; s += 4) a += partial[((size_t)s * max_batch + b) * 256 + j];
+  red[grp][j] = a;
+  __syncthreads();
+  if (grp == 0) {
+    const float v = (((red[0][j] + red[1][j]) + red[2][j]) + red[3][j]) + fc6_b[j];
+    h6[j] = v > 0.f ? v : 0.1f * v;
+  }
   __syncthreads();
   float c = 0.f;
-  for (int k = 0; k < 256; ++k) c = fmaf(h6[k], fc7_wT[k * 256 + j], c);
-  c += fc7_b[j];
-  h7[j] = c > 0.f ? c : 0.1f * c;
+#pragma unroll 8
+  for (int k = grp * 64; k < grp * 64 + 64; ++k) c = fmaf(h6[k], fc7_wT[k * 256 + j], c);
+  red[grp][j] = c;
   __syncthreads();
-  const int warp = j >> 5, lane = j & 31;
+  if (grp == 0) {
+    const float v = (((red[0][j] + red[1][j]) + red[2][j]) + red[3][j]) + fc7_b[j];
+    h7[j] = v > 0.f ? v : 0.1f * v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp < 7) {
     const float *wrow = warp < 4 ? rot_w + warp * 256 : trans_w + (warp - 4) * 256;
     float v = 0.f;
@@ -338,7 +350,7 @@ __global__ void __launch_bounds__(256) head_kernel(const float *__restrict__ par
     if (lane == 0) outv[warp] = v + (warp < 4 ? rot_b[warp] : trans_b[warp - 4]);
   }
   __syncthreads();
-  if (j == 0) {
+  if (threadIdx.x == 0) {
     if (rot_out)
       for (int k = 0; k < 4; ++k) rot_out[4 * b + k] = outv[k];
     if (trans_out)
@@ -551,7 +563,7 @@ int net_forward(dim_ctx *ctx, int B, int precision, const float *zoom_factor, fl
     fc6_mma_kernel<false><<<FC6_SPLITS, 256, 0, st>>>(ns->act_hi[10], nullptr, ns->fc6_w_hi, nullptr, B,
                                                       ctx->max_batch, ns->fc6_partial);
   DIM_LAUNCH_CHECK();
-  head_kernel<<<B, 256, 0, st>>>(ns->fc6_partial, ctx->max_batch, ns->fc6_b, ns->fc7_wT, ns->fc7_b, ns->rot_w,
+  head_kernel<<<B, 1024, 0, st>>>(ns->fc6_partial, ctx->max_batch, ns->fc6_b, ns->fc7_wT, ns->fc7_b, ns->rot_w,
                                  ns->rot_b, ns->trans_w, ns->trans_b, zoom_factor, rot_out, trans_out, se3_out);
   DIM_LAUNCH_CHECK();
   return 0;

@@ -38,6 +38,7 @@ struct RasterParams {
   float bg[3];  // (float)(0.0 - mean)
   int trunc_u8;
   float *out_image, *out_depth, *out_mask, *out_bgr;
+  float4 *out_ren4;  // [B,H,W] (R-mean, G-mean, B-mean, mask): the fused loop's layout
 };
 
 __global__ void raster_init_kernel(int *vbox, int *bbox_ren, int B, int H, int W) {
@@ -307,6 +308,11 @@ __global__ void __launch_bounds__(256) raster_resolve_kernel(RasterParams p) {
       *reinterpret_cast<float4 *>(img + P + o) = make_float4(g[0], g[1], g[2], g[3]);
       *reinterpret_cast<float4 *>(img + 2 * P + o) = make_float4(bl[0], bl[1], bl[2], bl[3]);
     }
+    if (p.out_ren4) {
+      float4 *o4 = p.out_ren4 + (size_t)b * P + o;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o4[k] = make_float4(r[k], g[k], bl[k], mk[k]);
+    }
     if (p.out_depth) *reinterpret_cast<float4 *>(p.out_depth + (size_t)b * P + o) = make_float4(d[0], d[1], d[2], d[3]);
     if (p.out_mask) *reinterpret_cast<float4 *>(p.out_mask + (size_t)b * P + o) = make_float4(mk[0], mk[1], mk[2], mk[3]);
     if (p.out_bgr) {  // Render_Py layout [H,W,3] BGR: 12 floats = 3 float4
@@ -343,7 +349,7 @@ __global__ void raster_finish_kernel(int *bbox_ren, int *out_bbox, int B) {
 
 int render_launch(dim_ctx *ctx, const int *cls, const float *pose, int B, const float *K9, float zn, float zf,
                   const double *means, int trunc_u8, float *out_image, float *out_depth, float *out_mask,
-                  float *out_bgr, int *out_bbox, cudaStream_t st) {
+                  float *out_bgr, int *out_bbox, float4 *out_ren4, cudaStream_t st) {
   DIM_REQUIRE(B >= 1 && B <= ctx->max_batch, "dim_render: batch exceeds max_batch");
   DIM_REQUIRE((ctx->W & 3) == 0, "dim_render: width must be a multiple of 4");
   RasterParams p;
@@ -357,6 +363,7 @@ int render_launch(dim_ctx *ctx, const int *cls, const float *pose, int B, const 
   }
   p.trunc_u8 = trunc_u8;
   p.out_image = out_image; p.out_depth = out_depth; p.out_mask = out_mask; p.out_bgr = out_bgr;
+  p.out_ren4 = out_ren4;
   int maxV = 0, maxF = 0;
   for (auto &m : ctx->meshes_host) { maxV = maxV > m.V ? maxV : m.V; maxF = maxF > m.F ? maxF : m.F; }
   DIM_REQUIRE(maxV > 0 && maxF > 0, "dim_render: no mesh uploaded");

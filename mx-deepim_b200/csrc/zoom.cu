@@ -141,8 +141,9 @@ __device__ __forceinline__ float bilinear(const float *img, int H, int W, const 
   float tr = fetch<BIN>(img, H, W, t.y0, t.x0 + 1, add);
   float bl = fetch<BIN>(img, H, W, t.y0 + 1, t.x0, add);
   float br = fetch<BIN>(img, H, W, t.y0 + 1, t.x0 + 1, add);
-  float wx1 = t.wx1, wy1 = t.wy1;
-  return tl * wy1 * wx1 + tr * wy1 * (1.0f - wx1) + bl * (1.0f - wy1) * wx1 + br * (1.0f - wy1) * (1.0f - wx1);
+  const float wx1 = t.wx1, wy1 = t.wy1, ax = 1.0f - wx1, ay = 1.0f - wy1;
+  const float a = wy1 * wx1, b = wy1 * ax, c = ay * wx1, d = ay * ax;
+  return fmaf(br, d, fmaf(bl, c, fmaf(tr, b, tl * a)));
 }
 
 // inverse-zoom affine (zoom_flow.py:35-44): float32 scalars with python numbers -> float64
@@ -289,47 +290,70 @@ int box_mask_launch(dim_ctx *ctx, const int *bbox, int B, float *mask, cudaStrea
 // bf16 (16 B) straight into conv1's zero-bordered, space-to-depth input buffer; `lo` (optional) receives the
 // bf16 residual for the bf16x3 precision mode.
 struct FusedZoomParams {
-  const float *image_observed, *image_rendered, *mask_rendered;  // [B,3,H,W] x2, [B,1,H,W]
-  const int *bbox8;                                              // observed box = bb[0..3] (inclusive)
+  const float4 *obs4;   // [B,H,W,4] observed RGB-mean (w unused)
+  const float4 *ren4;   // [B,H,W,4] rendered RGB-mean, w = mask_rendered (0/1)
+  const int *bbox8;     // observed box = bb[0..3] (inclusive)
   const float *zoom_factor;
   int H, W, Hs, Ws, pad;  // conv1 input is space-to-depth: [B,Hs,Ws,(ph,pw,c)=32]
   float mean[3];
   float stepx, stepy;
-  __nv_bfloat16 *hi, *lo;  // [B,Hp,Wp,8]
+  __nv_bfloat16 *hi, *lo;
 };
 
+template <bool LO>
 __device__ __forceinline__ void zoom_fused_pixel(const FusedZoomParams &p, int b, int i, int j, const float *zf,
                                                  __nv_bfloat16 *h, __nv_bfloat16 *l) {
   const Tap t = src_coord(i, j, zf[0], zf[1], zf[2], zf[3], p.H, p.W, p.stepx, p.stepy);
-  const size_t P = (size_t)p.H * p.W;
+  const bool x0ok = t.x0 >= 0 && t.x0 <= p.W - 1, x1ok = t.x0 + 1 >= 0 && t.x0 + 1 <= p.W - 1;
+  const bool y0ok = t.y0 >= 0 && t.y0 <= p.H - 1, y1ok = t.y0 + 1 >= 0 && t.y0 + 1 <= p.H - 1;
+  const bool k00 = y0ok && x0ok, k01 = y0ok && x1ok, k10 = y1ok && x0ok, k11 = y1ok && x1ok;
+  const size_t base = (size_t)b * p.H * p.W;
+  const long o = (long)t.y0 * p.W + t.x0;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 O00 = k00 ? __ldg(p.obs4 + base + o) : z4, O01 = k01 ? __ldg(p.obs4 + base + o + 1) : z4;
+  const float4 O10 = k10 ? __ldg(p.obs4 + base + o + p.W) : z4, O11 = k11 ? __ldg(p.obs4 + base + o + p.W + 1) : z4;
+  const float4 R00 = k00 ? __ldg(p.ren4 + base + o) : z4, R01 = k01 ? __ldg(p.ren4 + base + o + 1) : z4;
+  const float4 R10 = k10 ? __ldg(p.ren4 + base + o + p.W) : z4, R11 = k11 ? __ldg(p.ren4 + base + o + p.W + 1) : z4;
+  const float wx1 = t.wx1, wy1 = t.wy1, ax = 1.0f - wx1, ay = 1.0f - wy1;
+  const float wa = wy1 * wx1, wb = wy1 * ax, wc = ay * wx1, wd = ay * ax;
   float v[8];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    v[c] = (bilinear<0>(p.image_observed + ((size_t)b * 3 + c) * P, p.H, p.W, t, p.mean[c]) - p.mean[c]) / 255.0f;
-    v[3 + c] = (bilinear<0>(p.image_rendered + ((size_t)b * 3 + c) * P, p.H, p.W, t, p.mean[c]) - p.mean[c]) / 255.0f;
-  }
+  // (img + mean) sampled with zero padding, then - mean, then the graph's /255
+  auto img = [&](float tl, float tr, float bl, float br, float m) -> float {
+    tl = k00 ? tl + m : 0.f; tr = k01 ? tr + m : 0.f; bl = k10 ? bl + m : 0.f; br = k11 ? br + m : 0.f;
+    return (fmaf(br, wd, fmaf(bl, wc, fmaf(tr, wb, tl * wa))) - m) / 255.0f;
+  };
+  v[0] = img(O00.x, O01.x, O10.x, O11.x, p.mean[0]);
+  v[1] = img(O00.y, O01.y, O10.y, O11.y, p.mean[1]);
+  v[2] = img(O00.z, O01.z, O10.z, O11.z, p.mean[2]);
+  v[3] = img(R00.x, R01.x, R10.x, R11.x, p.mean[0]);
+  v[4] = img(R00.y, R01.y, R10.y, R11.y, p.mean[1]);
+  v[5] = img(R00.z, R01.z, R10.z, R11.z, p.mean[2]);
   {  // observed mask = rectangle; bb holds its inclusive bbox (x0, x1-1, y0, y1-1)
     const int *bb = p.bbox8 + 8 * b;
-    const int x0 = bb[0], x1 = bb[1], y0 = bb[2], y1 = bb[3];
-    auto box = [&](int y, int x) -> float {
-      if (x < 0 || x > p.W - 1 || y < 0 || y > p.H - 1) return 0.0f;
-      return (x1 >= 0 && x >= x0 && x <= x1 && y >= y0 && y <= y1) ? 1.0f : 0.0f;
-    };
-    float tl = box(t.y0, t.x0), tr = box(t.y0, t.x0 + 1), bl = box(t.y0 + 1, t.x0), br = box(t.y0 + 1, t.x0 + 1);
-    float wx1 = t.wx1, wy1 = t.wy1;
-    v[6] = roundf(tl * wy1 * wx1 + tr * wy1 * (1.0f - wx1) + bl * (1.0f - wy1) * wx1 +
-                  br * (1.0f - wy1) * (1.0f - wx1));
+    const int bx0 = bb[0], bx1 = bb[1], by0 = bb[2], by1 = bb[3];
+    const bool cx0 = t.x0 >= bx0 && t.x0 <= bx1, cx1 = t.x0 + 1 >= bx0 && t.x0 + 1 <= bx1;
+    const bool cy0 = t.y0 >= by0 && t.y0 <= by1, cy1 = t.y0 + 1 >= by0 && t.y0 + 1 <= by1;
+    const bool any = bx1 >= 0;
+    const float tl = (any && k00 && cy0 && cx0) ? 1.f : 0.f, tr = (any && k01 && cy0 && cx1) ? 1.f : 0.f;
+    const float bl = (any && k10 && cy1 && cx0) ? 1.f : 0.f, br = (any && k11 && cy1 && cx1) ? 1.f : 0.f;
+    v[6] = roundf(fmaf(br, wd, fmaf(bl, wc, fmaf(tr, wb, tl * wa))));
   }
-  v[7] = roundf(bilinear<1>(p.mask_rendered + (size_t)b * P, p.H, p.W, t, 0.f));
+  {  // rendered mask, binarised at 0.2 (zoom_mask.py:39-41)
+    const float tl = (k00 && R00.w > 0.2f) ? 1.f : 0.f, tr = (k01 && R01.w > 0.2f) ? 1.f : 0.f;
+    const float bl = (k10 && R10.w > 0.2f) ? 1.f : 0.f, br = (k11 && R11.w > 0.2f) ? 1.f : 0.f;
+    v[7] = roundf(fmaf(br, wd, fmaf(bl, wc, fmaf(tr, wb, tl * wa))));
+  }
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     h[c] = __float2bfloat16_rn(v[c]);
-    l[c] = __float2bfloat16_rn(v[c] - __bfloat162float(h[c]));
+    if (LO) l[c] = __float2bfloat16_rn(v[c] - __bfloat162float(h[c]));
   }
 }
 
 // one thread per space-to-depth pixel = a 2x2 quad of output pixels = one full 64-B line of conv1's
-// input (a warp writes 2 KB contiguous); border slots are rewritten with zeros.
+// input (a warp writes 2 KB contiguous); border slots are rewritten with zeros.  Sources are the
+// pixel-interleaved float4 images, so each tap is one 16-byte load per image.
+template <bool LO>
 __global__ void __launch_bounds__(128) zoom_fused_nhwc8_kernel(FusedZoomParams p) {
   const int b = blockIdx.y;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -342,7 +366,7 @@ __global__ void __launch_bounds__(128) zoom_fused_nhwc8_kernel(FusedZoomParams p
   for (int s = 0; s < 4; ++s) {
     const int i = 2 * sr + (s >> 1) - p.pad, j = 2 * sc + (s & 1) - p.pad;
     if (i >= 0 && i < p.H && j >= 0 && j < p.W) {
-      zoom_fused_pixel(p, b, i, j, zf, h[s], l[s]);
+      zoom_fused_pixel<LO>(p, b, i, j, zf, h[s], l[s]);
     } else {
 #pragma unroll
       for (int c = 0; c < 8; ++c) { h[s][c] = __float2bfloat16_rn(0.f); l[s][c] = __float2bfloat16_rn(0.f); }
@@ -352,22 +376,39 @@ __global__ void __launch_bounds__(128) zoom_fused_nhwc8_kernel(FusedZoomParams p
 #pragma unroll
   for (int s = 0; s < 4; ++s) {
     *reinterpret_cast<uint4 *>(p.hi + o + s * 8) = *reinterpret_cast<const uint4 *>(h[s]);
-    if (p.lo) *reinterpret_cast<uint4 *>(p.lo + o + s * 8) = *reinterpret_cast<const uint4 *>(l[s]);
+    if (LO) *reinterpret_cast<uint4 *>(p.lo + o + s * 8) = *reinterpret_cast<const uint4 *>(l[s]);
   }
 }
 
-int zoom_fused_launch(dim_ctx *ctx, const float *image_observed, const float *image_rendered,
-                      const float *mask_rendered, const float *zoom_factor, const float *means_rgb, int B, int Hs,
-                      int Ws, int pad, __nv_bfloat16 *hi, __nv_bfloat16 *lo, cudaStream_t st) {
+int zoom_fused_launch(dim_ctx *ctx, const float4 *obs4, const float4 *ren4, const float *zoom_factor,
+                      const float *means_rgb, int B, int Hs, int Ws, int pad, __nv_bfloat16 *hi, __nv_bfloat16 *lo,
+                      cudaStream_t st) {
   FusedZoomParams p;
-  p.image_observed = image_observed; p.image_rendered = image_rendered; p.mask_rendered = mask_rendered;
+  p.obs4 = obs4; p.ren4 = ren4;
   p.bbox8 = ctx->bbox8; p.zoom_factor = zoom_factor;
   p.H = ctx->H; p.W = ctx->W; p.Hs = Hs; p.Ws = Ws; p.pad = pad;
   for (int c = 0; c < 3; ++c) p.mean[c] = means_rgb[c];
   p.stepx = (float)(2.0 / (double)(ctx->W - 1));
   p.stepy = (float)(2.0 / (double)(ctx->H - 1));
   p.hi = hi; p.lo = lo;
-  zoom_fused_nhwc8_kernel<<<dim3(cdiv(Hs * Ws, 128), B), 128, 0, st>>>(p);
+  dim3 grid(cdiv(Hs * Ws, 128), B);
+  if (lo) zoom_fused_nhwc8_kernel<true><<<grid, 128, 0, st>>>(p);
+  else zoom_fused_nhwc8_kernel<false><<<grid, 128, 0, st>>>(p);
+  DIM_LAUNCH_CHECK();
+  return 0;
+}
+
+// NCHW f32 (3 planes) -> pixel-interleaved float4 (x,y,z = planes, w = 0): once per dim_refine call
+__global__ void __launch_bounds__(256) pack_obs4_kernel(const float *img, int P, float4 *out) {
+  const int b = blockIdx.y;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= P) return;
+  const float *s = img + (size_t)b * 3 * P;
+  out[(size_t)b * P + q] = make_float4(s[q], s[P + q], s[2 * (size_t)P + q], 0.f);
+}
+int pack_obs4_launch(dim_ctx *ctx, const float *img, int B, float4 *out, cudaStream_t st) {
+  const int P = ctx->H * ctx->W;
+  pack_obs4_kernel<<<dim3(cdiv(P, 256), B), 256, 0, st>>>(img, P, out);
   DIM_LAUNCH_CHECK();
   return 0;
 }

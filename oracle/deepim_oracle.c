@@ -389,9 +389,12 @@ static inline float orc_bilinear(const float *img, int H, int W, orc_tap t, floa
   float tr = orc_fetch(img, H, W, t.y0, t.x0 + 1, add);
   float bl = orc_fetch(img, H, W, t.y0 + 1, t.x0, add);
   float br = orc_fetch(img, H, W, t.y0 + 1, t.x0 + 1, add);
-  float wx1 = t.wx1, wy1 = t.wy1;
-  return tl * wy1 * wx1 + tr * wy1 * (1.0f - wx1) + bl * (1.0f - wy1) * wx1 +
-         br * (1.0f - wy1) * (1.0f - wx1);
+  /* the four tap weights are formed once per output pixel and accumulated with fused
+   * multiply-adds (same bilinear formula as MXNet's BilinearSampler; expression order is ours, the
+   * third-party kernel's own rounding order is unknowable -> parity unpinned, <= 1 ulp apart) */
+  float wx1 = t.wx1, wy1 = t.wy1, ax = 1.0f - wx1, ay = 1.0f - wy1;
+  float a = wy1 * wx1, b = wy1 * ax, c = ay * wx1, d = ay * ax;
+  return fmaf(br, d, fmaf(bl, c, fmaf(tr, b, tl * a)));
 }
 
 /*
