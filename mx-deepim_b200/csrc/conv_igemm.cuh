@@ -536,6 +536,200 @@ __global__ void __launch_bounds__(192) conv_igemm_persistent_kernel(const __grid
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// conv1 (flow_conv1: 8 -> 64, 7x7 s2, i.e. 16 taps x 32 space-to-depth channels).  The generic path
+// fetches every tap's operand tile from L2 separately (16x re-read of the input: the layer is then
+// bound by L2 -> SMEM traffic, not by the tensor pipe).  Here one TMA box per filter row dh brings the
+// (BW+3)-pixel input strip into shared memory ONCE, in the un-swizzled K-major "interleave" layout
+//     addr(pixel r, channel-chunk c) = base + c*LBO + 16*r          (8-channel chunks of 16 B)
+// in which the row index is linear in memory, so the four horizontal taps dw = 0..3 are the same
+// strip read through descriptors whose start address is shifted by dw*16 bytes: 4 TMA loads per
+// tile instead of 16, the input is read from L2 ~4x instead of 16x.
+// Input buffer layout (written by the zoom kernel): [B*Hs rows][4 chunks][Ws cols][8 ch] bf16.
+// Tile = one output row x BW output columns (BW <= 128; MMA rows >= BW are don't-care).
+// Weights: the whole 64 x 512 matrix stays resident in shared memory (64B-swizzled, 16 tap tiles).
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
+          "r"(ptx::smem_u32(dst)),
+      "l"((uint64_t)map), "r"(ptx::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t umma_desc_interleave(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;  // version 1, layout type 0 = SWIZZLE_NONE
+  return d;
+}
+
+template <int STAGES, bool SPLIT3>
+struct Conv1Smem {
+  static constexpr int MAXR = 128 + 3;                      // strip pixels incl. halo
+  static constexpr int A_BYTES = ((MAXR * 64 + 127) / 128) * 128;  // one strip (4 chunks x R x 16 B), 128-B aligned
+  static constexpr int NPREC = SPLIT3 ? 2 : 1;
+  static constexpr int STAGE_BYTES = A_BYTES * NPREC;
+  static constexpr int B_BYTES = 64 * 32 * 2;               // one tap tile of the weights
+  static constexpr int RES_BYTES = 16 * B_BYTES * NPREC;
+  static constexpr int TAIL = 4096;                         // don't-care rows of the last strip may be read past it
+  static constexpr int TOTAL = RES_BYTES + STAGES * STAGE_BYTES + TAIL + 1024 + 512;
+};
+
+template <int STAGES, bool SPLIT3>
+__global__ void __launch_bounds__(192) conv1_strip_kernel(const __grid_constant__ ConvKParams p, const int total_tiles) {
+  using S = Conv1Smem<STAGES, SPLIT3>;
+  constexpr uint32_t ACC_COLS = 64, TMEM_COLS = 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t *res = smem;                       // resident weights, SW64 tiles (512-B aligned)
+  uint8_t *ring = smem + S::RES_BYTES;       // strips
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(ring + STAGES * S::STAGE_BYTES + S::TAIL);
+  uint64_t *empty_bar = full_bar + STAGES;
+  uint64_t *tmem_full_bar = empty_bar + STAGES;
+  uint64_t *tmem_empty_bar = tmem_full_bar + 2;
+  uint64_t *res_bar = tmem_empty_bar + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(res_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int R = p.BW + 3;                    // strip width in pixels
+  const uint32_t LBO = (uint32_t)R * 16u;    // distance between 8-channel chunks
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full_bar[a], 1);
+      ptx::mbar_init(&tmem_empty_bar[a], 4);
+    }
+    ptx::mbar_init(res_bar, 1);
+    ptx::fence_barrier_init();
+    ptx::prefetch_tmap(&p.b_map);
+    ptx::prefetch_tmap(&p.a_map[0]);
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::mbar_expect_tx(res_bar, (uint32_t)S::RES_BYTES);
+      for (int kb = 0; kb < 16; ++kb) {
+        ptx::tma_load_2d(res + kb * S::B_BYTES, &p.b_map, res_bar, kb * 32, 0);
+        if (SPLIT3) ptx::tma_load_2d(res + (16 + kb) * S::B_BYTES, &p.b_lo_map, res_bar, kb * 32, 0);
+      }
+      const uint32_t tx = (uint32_t)(R * 64) * S::NPREC;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int ct = tile % p.n_col_tiles, g = tile / p.n_col_tiles;
+        const int ow0 = ct * p.BW;
+        for (int dh = 0; dh < 4; ++dh) {
+          ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
+          uint8_t *st = ring + s * S::STAGE_BYTES;
+          ptx::mbar_expect_tx(&full_bar[s], tx);
+          tma_load_4d(st, &p.a_map[0], &full_bar[s], 0, ow0, 0, g + dh);
+          if (SPLIT3) tma_load_4d(st + S::A_BYTES, &p.a_lo_map[0], &full_bar[s], 0, ow0, 0, g + dh);
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      ptx::mbar_wait(res_bar, 0);
+      ptx::tc_fence_after();
+      int s = 0, as = 0;
+      uint32_t ph = 0, aph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&tmem_empty_bar[as], aph ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + (uint32_t)as * ACC_COLS;
+        for (int dh = 0; dh < 4; ++dh) {
+          ptx::mbar_wait(&full_bar[s], ph);
+          ptx::tc_fence_after();
+          const uint32_t a_hi = ptx::smem_u32(ring + s * S::STAGE_BYTES);
+          const uint32_t a_lo = a_hi + S::A_BYTES;
+#pragma unroll
+          for (int dw = 0; dw < 4; ++dw) {
+            const uint32_t b_hi = ptx::smem_u32(res + (dh * 4 + dw) * S::B_BYTES);
+            const uint32_t b_lo = ptx::smem_u32(res + (16 + dh * 4 + dw) * S::B_BYTES);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {  // 16 channels = 2 chunks per UMMA
+              const uint32_t acc = (dh | dw | k) ? 1u : 0u;
+              const uint64_t da = umma_desc_interleave(a_hi + dw * 16 + k * 2 * LBO, LBO, 128);
+              const uint64_t db = ptx::umma_desc(b_hi + k * 32, 512, 4u);
+              ptx::umma_f16(tmem_acc, da, db, p.idesc, acc);
+              if (SPLIT3) {
+                const uint64_t dal = umma_desc_interleave(a_lo + dw * 16 + k * 2 * LBO, LBO, 128);
+                const uint64_t dbl = ptx::umma_desc(b_lo + k * 32, 512, 4u);
+                ptx::umma_f16(tmem_acc, dal, db, p.idesc, 1u);
+                ptx::umma_f16(tmem_acc, da, dbl, p.idesc, 1u);
+              }
+            }
+          }
+          ptx::umma_commit(&empty_bar[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+        ptx::umma_commit(&tmem_full_bar[as]);
+        if (++as == 2) { as = 0; aph ^= 1u; }
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int m = quad * 32 + lane;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int ct = tile % p.n_col_tiles, g = tile / p.n_col_tiles;
+      const int ow = ct * p.BW + m;
+      const int n_img = g / p.Hq, oh = g - n_img * p.Hq;
+      const bool valid = (m < p.BW) && (n_img < p.Bn) && (oh < p.Ho) && (ow < p.Wo);
+      ptx::mbar_wait(&tmem_full_bar[as], aph);
+      ptx::tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)as * ACC_COLS;
+      const size_t pix = ((size_t)n_img * p.out_Hp + oh + p.out_py) * p.out_Wp + ow + p.out_px;
+      __nv_bfloat16 *dhi = p.out_hi + pix * 64;
+      __nv_bfloat16 *dlo = SPLIT3 ? (p.out_lo + pix * 64) : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < 64; c += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(trow + c, r);
+        if (valid) {
+          __align__(16) __nv_bfloat16 h[32];
+          __align__(16) __nv_bfloat16 l[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float v = __uint_as_float(r[j]) + __ldg(p.bias + c + j);
+            v = v > 0.f ? v : v * p.slope;
+            h[j] = __float2bfloat16_rn(v);
+            if (SPLIT3) l[j] = __float2bfloat16_rn(v - __bfloat162float(h[j]));
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            *reinterpret_cast<uint4 *>(dhi + c + j) = *reinterpret_cast<const uint4 *>(h + j);
+            if (SPLIT3) *reinterpret_cast<uint4 *>(dlo + c + j) = *reinterpret_cast<const uint4 *>(l + j);
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+      if (++as == 2) { as = 0; aph ^= 1u; }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
 // split-K finalize: sum partials + bias + LeakyReLU -> bf16 (hi[, lo]) into the bordered NHWC buffer
 __global__ void __launch_bounds__(256) conv_splitk_finalize_kernel(const float *partial, int ksplit, int npix,
                                                                    int Cout, int Ho, int Wo, int out_Hp, int out_Wp,

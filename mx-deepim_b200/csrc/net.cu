@@ -102,6 +102,10 @@ static void build_geometry(NetState *ns, int H, int W) {
     if (best_bw == 0) best_bw = 1;  // degenerate geometry (tiny geometry-only contexts)
     g.BW = best_bw; g.BH = 128 / best_bw;
     g.n_col_tiles = g.Wo > 0 ? g.Wo / g.BW : 0;
+    if (i == 0) {  // conv1 strip kernel: one output row x BW columns per tile, BW = ceil(Wo / ceil(Wo/128))
+      const int nt = cdiv(g.Wo, 128);
+      g.BW = cdiv(g.Wo, nt); g.BH = 1; g.n_col_tiles = nt;
+    }
     g.kblocks = g.KH * g.KW * (g.Ceff / g.BLOCK_K);
     g.occ = (g.BLOCK_N <= 128) ? 2 : 1;
     h = g.Ho; w = g.Wo;
@@ -144,7 +148,7 @@ static EncodeTiledFn get_encode() {
 }
 
 static int encode_map(CUtensorMap *m, void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
-                      const uint32_t *box, int block_k) {
+                      const uint32_t *box, int block_k /*64: SW128, 32: SW64, 0: no swizzle*/) {
   EncodeTiledFn fn = get_encode();
   DIM_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available (driver too old?)");
   cuuint64_t gd[5]; cuuint64_t gs[5]; cuuint32_t bx[5]; cuuint32_t es[5];
@@ -152,7 +156,8 @@ static int encode_map(CUtensorMap *m, void *base, int rank, const uint64_t *dims
   for (int i = 0; i < rank - 1; ++i) gs[i] = strides_bytes[i];
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, gd, gs, bx, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : (block_k == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu %llu %llu box %u %u %u)", (int)r, rank,
@@ -178,7 +183,14 @@ static int build_maps(NetState *ns, int B, TensorMaps &tm) {
       __nv_bfloat16 *base = lo ? ns->act_lo[i] : ns->act_hi[i];
       CUtensorMap *maps = lo ? kp.a_lo_map : kp.a_map;
       const uint32_t box[3] = {(uint32_t)g.BLOCK_K, (uint32_t)g.BW, (uint32_t)g.BH};
-      if (g.stride_eff == 1) {
+      if (i == 0) {
+        // conv1 strip layout [B*rows][4 chunks][cols][8 ch]: box = 8 ch x (BW+3) cols x 4 chunks x 1 row
+        const uint64_t dims[4] = {8, (uint64_t)g.cols, 4, (uint64_t)B * g.rows};
+        const uint64_t str[3] = {16, (uint64_t)g.cols * 16, (uint64_t)g.cols * 64};
+        const uint32_t box4[4] = {8, (uint32_t)(g.BW + 3), 4, 1};
+        if (int rc = encode_map(&maps[0], base, 4, dims, str, box4, 0)) return rc;
+        maps[1] = maps[2] = maps[3] = maps[0];
+      } else if (g.stride_eff == 1) {
         const uint64_t dims[3] = {(uint64_t)g.Cbuf, (uint64_t)g.cols, (uint64_t)B * g.rows};
         const uint64_t str[2] = {(uint64_t)g.Cbuf * 2, (uint64_t)g.cols * g.Cbuf * 2};
         if (int rc = encode_map(&maps[0], base, 3, dims, str, box, g.BLOCK_K)) return rc;
@@ -536,10 +548,23 @@ int net_forward(dim_ctx *ctx, int B, int precision, const float *zoom_factor, fl
     const int total_tiles = cdiv(B * g.Hq, g.BH) * g.n_col_tiles * n_tiles * kp.ksplit;
     const int sms = ns->num_sms;
     int rc;
-    if (g.BLOCK_N == 64)  // conv1: resident 64 x 512 weight matrix, 64B-swizzled K = 32 blocks
-      rc = s3 ? launch_conv2<64, 32, 4, true, true, 16>(kp, total_tiles, n_tiles, sms, st)
-              : launch_conv2<64, 32, 5, false, true, 16>(kp, total_tiles, n_tiles, 2 * sms, st);
-    else if (g.BLOCK_N == 128)
+    if (i == 0) {  // conv1: strip kernel (one TMA strip per filter row, shifted un-swizzled descriptors)
+      const int tiles1 = B * g.Hq * g.n_col_tiles;
+      if (s3) {
+        using S1 = Conv1Smem<4, true>;
+        static bool set1 = false;
+        if (!set1) { DIM_CHECK(cudaFuncSetAttribute(conv1_strip_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S1::TOTAL)); set1 = true; }
+        conv1_strip_kernel<4, true><<<tiles1 < sms ? tiles1 : sms, 192, S1::TOTAL, st>>>(kp, tiles1);
+      } else {
+        using S1 = Conv1Smem<4, false>;
+        static bool set0 = false;
+        if (!set0) { DIM_CHECK(cudaFuncSetAttribute(conv1_strip_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S1::TOTAL)); set0 = true; }
+        conv1_strip_kernel<4, false><<<tiles1 < 2 * sms ? tiles1 : 2 * sms, 192, S1::TOTAL, st>>>(kp, tiles1);
+      }
+      DIM_LAUNCH_CHECK();
+      rc = 0;
+    }
+    else if (g.BLOCK_N <= 128)
       rc = s3 ? launch_conv2<128, 64, 3, true, false, 0>(kp, total_tiles, n_tiles, sms, st)
               : launch_conv2<128, 64, 3, false, false, 0>(kp, total_tiles, n_tiles, 2 * sms, st);
     else

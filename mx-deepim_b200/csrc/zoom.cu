@@ -350,8 +350,9 @@ __device__ __forceinline__ void zoom_fused_pixel(const FusedZoomParams &p, int b
   }
 }
 
-// one thread per space-to-depth pixel = a 2x2 quad of output pixels = one full 64-B line of conv1's
-// input (a warp writes 2 KB contiguous); border slots are rewritten with zeros.  Sources are the
+// one thread per space-to-depth pixel = a 2x2 quad of output pixels = the four 16-byte channel chunks
+// of conv1's strip layout (consecutive threads write consecutive 16 B of each chunk plane); border
+// slots are rewritten with zeros.  Sources are the
 // pixel-interleaved float4 images, so each tap is one 16-byte load per image.
 template <bool LO>
 __global__ void __launch_bounds__(128) zoom_fused_nhwc8_kernel(FusedZoomParams p) {
@@ -372,11 +373,12 @@ __global__ void __launch_bounds__(128) zoom_fused_nhwc8_kernel(FusedZoomParams p
       for (int c = 0; c < 8; ++c) { h[s][c] = __float2bfloat16_rn(0.f); l[s][c] = __float2bfloat16_rn(0.f); }
     }
   }
-  const size_t o = (((size_t)b * p.Hs + sr) * p.Ws + sc) * 32;
+  // conv1 strip layout: [B*Hs rows][4 chunks (= quad slot)][Ws cols][8 ch]
 #pragma unroll
   for (int s = 0; s < 4; ++s) {
-    *reinterpret_cast<uint4 *>(p.hi + o + s * 8) = *reinterpret_cast<const uint4 *>(h[s]);
-    if (LO) *reinterpret_cast<uint4 *>(p.lo + o + s * 8) = *reinterpret_cast<const uint4 *>(l[s]);
+    const size_t o = ((((size_t)b * p.Hs + sr) * 4 + s) * p.Ws + sc) * 8;
+    *reinterpret_cast<uint4 *>(p.hi + o) = *reinterpret_cast<const uint4 *>(h[s]);
+    if (LO) *reinterpret_cast<uint4 *>(p.lo + o) = *reinterpret_cast<const uint4 *>(l[s]);
   }
 }
 
@@ -437,7 +439,7 @@ __global__ void __launch_bounds__(256) pack_nhwc8_kernel(const float *io, const 
     l[c] = __float2bfloat16_rn(v[c] - __bfloat162float(h[c]));
   }
   const int oi = q / W + pad, oj = q % W + pad;
-  const size_t o = ((((size_t)b * Hs + (oi >> 1)) * Ws + (oj >> 1)) * 4 + ((oi & 1) * 2 + (oj & 1))) * 8;
+  const size_t o = ((((size_t)b * Hs + (oi >> 1)) * 4 + ((oi & 1) * 2 + (oj & 1))) * Ws + (oj >> 1)) * 8;
   *reinterpret_cast<uint4 *>(hi + o) = *reinterpret_cast<const uint4 *>(h);
   if (lo) *reinterpret_cast<uint4 *>(lo + o) = *reinterpret_cast<const uint4 *>(l);
 }
