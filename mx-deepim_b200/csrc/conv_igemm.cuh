@@ -143,166 +143,44 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo_bytes
 
 }  // namespace ptx
 
-template <int BLOCK_N, int BLOCK_K, int STAGES, bool SPLIT3>
-struct ConvSmem {
-  static constexpr int A_BYTES = 128 * BLOCK_K * 2;
-  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
-  static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (SPLIT3 ? 2 : 1);
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-};
-
-template <int BLOCK_N, int BLOCK_K, int STAGES, bool SPLIT3>
-__global__ void __launch_bounds__(192) conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
-  using S = ConvSmem<BLOCK_N, BLOCK_K, STAGES, SPLIT3>;
-  constexpr uint32_t LAYOUT = (BLOCK_K == 64) ? 2u : 4u;  // SWIZZLE_128B : SWIZZLE_64B
-  constexpr uint32_t SBO = 8u * BLOCK_K * 2u;
-  constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
-
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES * S::STAGE_BYTES);
-  uint64_t *empty_bar = full_bar + STAGES;
-  uint64_t *tmem_full_bar = empty_bar + STAGES;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full_bar + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int col_tile = blockIdx.x % p.n_col_tiles, row_tile = blockIdx.x / p.n_col_tiles;
-  const int g0 = row_tile * p.BH, ow0 = col_tile * p.BW;
-  const int n0 = blockIdx.y * BLOCK_N;
-  const int kb_per = (p.kblocks + p.ksplit - 1) / p.ksplit;
-  const int kb0 = blockIdx.z * kb_per;
-  const int kb1 = min(p.kblocks, kb0 + kb_per);
-
-  if (warp == 0 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], 1);
-    }
-    ptx::mbar_init(tmem_full_bar, 1);
-    ptx::fence_barrier_init();
-    ptx::prefetch_tmap(&p.b_map);
-    ptx::prefetch_tmap(&p.a_map[0]);
+// ---------------------------------------------------------------------------------------------
+// Epilogue helper: one warp owns 32 accumulator rows (its TMEM lane quadrant).  64 fp32 columns per
+// call are biased, LeakyReLU'd, converted to bf16 (hi[, lo]) and staged through a per-warp 4 KB
+// XOR-swizzled shared-memory tile so that the global stores are full 128-byte lines (lane l writes 16 B
+// of row i*4 + l/8): the "one thread = one output row" register layout would otherwise emit 16-byte
+// stores 128+ bytes apart (half-sector writes, 32 lines per instruction).
+template <bool SPLIT3>
+__device__ __forceinline__ void epilogue_store64(const uint32_t *r, const float *bias_s, float slope, uint8_t *stage,
+                                                 __nv_bfloat16 *out_hi, __nv_bfloat16 *out_lo, long long my_off,
+                                                 bool my_valid, int lane) {
+  __align__(16) __nv_bfloat16 h[64];
+  __align__(16) __nv_bfloat16 l[SPLIT3 ? 64 : 8];
+#pragma unroll
+  for (int j = 0; j < 64; ++j) {
+    float v = __uint_as_float(r[j]) + bias_s[j];
+    v = v > 0.f ? v : v * slope;
+    h[j] = __float2bfloat16_rn(v);
+    if (SPLIT3) l[j] = __float2bfloat16_rn(v - __bfloat162float(h[j]));
   }
-  if (warp == 1) ptx::tmem_alloc(tmem_slot, TMEM_COLS);
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      const uint32_t tx = (uint32_t)(p.BW * p.BH * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) * (SPLIT3 ? 2u : 1u);
-      int s = 0;
-      uint32_t ph = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
-        const int tap = kb / p.cchunks, cc = kb - tap * p.cchunks;
-        const int kh = tap / p.KW, kw = tap - kh * p.KW;
-        int view = 0, dr = kh, dc = kw;
-        if (p.stride == 2) {
-          view = ((kh & 1) << 1) | (kw & 1);
-          dr = kh >> 1;
-          dc = kw >> 1;
-        }
-        uint8_t *st = smem + s * S::STAGE_BYTES;
-        ptx::mbar_expect_tx(&full_bar[s], tx);
-        ptx::tma_load_3d(st, &p.a_map[view], &full_bar[s], cc * BLOCK_K, ow0 + dc, g0 + dr);
-        ptx::tma_load_2d(st + S::A_BYTES, &p.b_map, &full_bar[s], kb * BLOCK_K, n0);
-        if (SPLIT3) {
-          ptx::tma_load_3d(st + S::A_BYTES + S::B_BYTES, &p.a_lo_map[view], &full_bar[s], cc * BLOCK_K, ow0 + dc,
-                           g0 + dr);
-          ptx::tma_load_2d(st + 2 * S::A_BYTES + S::B_BYTES, &p.b_lo_map, &full_bar[s], kb * BLOCK_K, n0);
-        }
-        if (++s == STAGES) { s = 0; ph ^= 1u; }
-      }
+  const unsigned vmask = __ballot_sync(0xffffffffu, my_valid);
+  const int ch = lane & 7;
+#pragma unroll
+  for (int pass = 0; pass < (SPLIT3 ? 2 : 1); ++pass) {
+    const __nv_bfloat16 *src = pass ? l : h;
+    __nv_bfloat16 *out = pass ? out_lo : out_hi;
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      *reinterpret_cast<uint4 *>(stage + lane * 128 + ((c ^ (lane & 7)) << 4)) = *reinterpret_cast<const uint4 *>(src + c * 8);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = i * 4 + (lane >> 3);
+      const long long off = __shfl_sync(0xffffffffu, my_off, row);
+      if ((vmask >> row) & 1u)
+        *reinterpret_cast<uint4 *>(out + off + ch * 8) =
+            *reinterpret_cast<const uint4 *>(stage + row * 128 + ((ch ^ (row & 7)) << 4));
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        ptx::mbar_wait(&full_bar[s], ph);
-        ptx::tc_fence_after();
-        const uint32_t a_hi = ptx::smem_u32(smem + s * S::STAGE_BYTES);
-        const uint32_t b_hi = a_hi + S::A_BYTES;
-        const uint32_t a_lo = b_hi + S::B_BYTES;
-        const uint32_t b_lo = a_lo + S::A_BYTES;
-#pragma unroll
-        for (int k = 0; k < BLOCK_K / 16; ++k) {
-          const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
-          const uint64_t da = ptx::umma_desc(a_hi + k * 32, SBO, LAYOUT);
-          const uint64_t db = ptx::umma_desc(b_hi + k * 32, SBO, LAYOUT);
-          ptx::umma_f16(tmem_base, da, db, p.idesc, acc);
-          if (SPLIT3) {
-            const uint64_t dal = ptx::umma_desc(a_lo + k * 32, SBO, LAYOUT);
-            const uint64_t dbl = ptx::umma_desc(b_lo + k * 32, SBO, LAYOUT);
-            ptx::umma_f16(tmem_base, dal, db, p.idesc, 1u);
-            ptx::umma_f16(tmem_base, da, dbl, p.idesc, 1u);
-          }
-        }
-        ptx::umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
-        if (++s == STAGES) { s = 0; ph ^= 1u; }
-      }
-      ptx::umma_commit(tmem_full_bar);  // accumulator complete
-    }
-  } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
-    const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) are visible to this warp
-    const int m = quad * 32 + lane;
-    const int bh = m / p.BW, bw = m - bh * p.BW;
-    const int g = g0 + bh, ow = ow0 + bw;
-    const int n_img = g / p.Hq, oh = g - n_img * p.Hq;
-    const bool valid = (m < p.BW * p.BH) && (n_img < p.Bn) && (oh < p.Ho) && (ow < p.Wo);
-    ptx::mbar_wait(tmem_full_bar, 0);
-    ptx::tc_fence_after();
-    const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
-    if (p.ksplit > 1) {
-      const size_t opix = ((size_t)n_img * p.Ho + oh) * p.Wo + ow;
-      float *dst = p.partial + ((size_t)blockIdx.z * ((size_t)p.Bn * p.Ho * p.Wo) + opix) * p.Cout + n0;
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(trow + c, r);
-        if (valid) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<uint4 *>(dst + c + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-        }
-      }
-    } else {
-      const size_t pix = ((size_t)n_img * p.out_Hp + oh + p.out_py) * p.out_Wp + ow + p.out_px;
-      __nv_bfloat16 *dhi = p.out_hi + pix * p.Cout + n0;
-      __nv_bfloat16 *dlo = SPLIT3 ? (p.out_lo + pix * p.Cout + n0) : nullptr;
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(trow + c, r);
-        if (valid) {
-          __align__(16) __nv_bfloat16 h[32];
-          __align__(16) __nv_bfloat16 l[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float v = __uint_as_float(r[j]) + __ldg(p.bias + n0 + c + j);
-            v = v > 0.f ? v : v * p.slope;
-            h[j] = __float2bfloat16_rn(v);
-            if (SPLIT3) l[j] = __float2bfloat16_rn(v - __bfloat162float(h[j]));
-          }
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            *reinterpret_cast<uint4 *>(dhi + c + j) = *reinterpret_cast<const uint4 *>(h + j);
-            if (SPLIT3) *reinterpret_cast<uint4 *>(dlo + c + j) = *reinterpret_cast<const uint4 *>(l + j);
-          }
-        }
-      }
-    }
-    ptx::tc_fence_before();
-  }
-  __syncthreads();
-  if (warp == 1) {
-    ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+    __syncwarp();
   }
 }
 
@@ -322,7 +200,8 @@ struct ConvSmem2 {
   static constexpr int NPREC = SPLIT3 ? 2 : 1;
   static constexpr int STAGE_BYTES = (A_BYTES + (RESIDENT_B ? 0 : B_BYTES)) * NPREC;
   static constexpr int RES_BYTES = RESIDENT_B ? KBLOCKS_RES * B_BYTES * NPREC : 0;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + RES_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
+  static constexpr int EPI_BYTES = 4 * 4096 + 4096 /*bias, up to 1024 channels*/;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + RES_BYTES + EPI_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
@@ -341,7 +220,9 @@ __global__ void __launch_bounds__(192) conv_igemm_persistent_kernel(const __grid
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t *res = smem + STAGES * S::STAGE_BYTES;  // resident weights (1024-aligned: stage sizes are multiples of 1 KB)
-  uint64_t *full_bar = reinterpret_cast<uint64_t *>(res + S::RES_BYTES);
+  uint8_t *epi = res + S::RES_BYTES;               // per-warp staging tiles + bias
+  float *bias_s = reinterpret_cast<float *>(epi + 4 * 4096);
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(epi + S::EPI_BYTES);
   uint64_t *empty_bar = full_bar + STAGES;
   uint64_t *tmem_full_bar = empty_bar + STAGES;   // [2]
   uint64_t *tmem_empty_bar = tmem_full_bar + 2;   // [2]
@@ -365,6 +246,7 @@ __global__ void __launch_bounds__(192) conv_igemm_persistent_kernel(const __grid
     ptx::prefetch_tmap(&p.b_map);
     ptx::prefetch_tmap(&p.a_map[0]);
   }
+  for (int c = threadIdx.x; c < p.Cout; c += blockDim.x) bias_s[c] = p.bias[c];
   if (warp == 1) ptx::tmem_alloc(tmem_slot, TMEM_COLS);
   ptx::tc_fence_before();
   __syncthreads();
@@ -496,35 +378,27 @@ __global__ void __launch_bounds__(192) conv_igemm_persistent_kernel(const __grid
           }
         }
       } else {
-        const size_t pix = ((size_t)n_img * p.out_Hp + oh + p.out_py) * p.out_Wp + ow + p.out_px;
-        __nv_bfloat16 *dhi = p.out_hi + pix * p.Cout + n0;
-        __nv_bfloat16 *dlo = SPLIT3 ? (p.out_lo + pix * p.Cout + n0) : nullptr;
+        const long long my_off =
+            (((long long)n_img * p.out_Hp + oh + p.out_py) * p.out_Wp + ow + p.out_px) * p.Cout + n0;
+        uint8_t *stg = epi + (warp - 2) * 4096;
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N; c += 32) {
-          uint32_t r[32];
+        for (int c = 0; c < BLOCK_N; c += 64) {
+          uint32_t r[64];
           ptx::tmem_ld_32x32(trow + c, r);
-          if (valid) {
-            __align__(16) __nv_bfloat16 h[32];
-            __align__(16) __nv_bfloat16 l[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float v = __uint_as_float(r[j]) + __ldg(p.bias + n0 + c + j);
-              v = v > 0.f ? v : v * p.slope;
-              h[j] = __float2bfloat16_rn(v);
-              if (SPLIT3) l[j] = __float2bfloat16_rn(v - __bfloat162float(h[j]));
-            }
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              *reinterpret_cast<uint4 *>(dhi + c + j) = *reinterpret_cast<const uint4 *>(h + j);
-              if (SPLIT3) *reinterpret_cast<uint4 *>(dlo + c + j) = *reinterpret_cast<const uint4 *>(l + j);
-            }
+          ptx::tmem_ld_32x32(trow + c + 32, r + 32);
+          if (c + 64 >= BLOCK_N) {  // last TMEM read of this tile: hand the accumulator stage back early
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
           }
+          epilogue_store64<SPLIT3>(r, bias_s + n0 + c, p.slope, stg, p.out_hi, p.out_lo, my_off + c, valid, lane);
         }
       }
-      // all tcgen05.ld of this warp have completed (wait::ld inside tmem_ld_32x32): release the stage
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+      if (p.ksplit > 1) {
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+      }
       if (++as == 2) { as = 0; aph ^= 1u; }
     }
   }
@@ -573,8 +447,9 @@ struct Conv1Smem {
   static constexpr int STAGE_BYTES = A_BYTES * NPREC;
   static constexpr int B_BYTES = 64 * 32 * 2;               // one tap tile of the weights
   static constexpr int RES_BYTES = 16 * B_BYTES * NPREC;
-  static constexpr int TAIL = 4096;                         // don't-care rows of the last strip may be read past it
-  static constexpr int TOTAL = RES_BYTES + STAGES * STAGE_BYTES + TAIL + 1024 + 512;
+  static constexpr int TAIL = 0;  // don't-care rows of the last strip are read past it, into the staging tiles (harmless)
+  static constexpr int EPI_BYTES = 4 * 4096 + 256;  // per-warp staging tiles + 64 bias floats
+  static constexpr int TOTAL = RES_BYTES + STAGES * STAGE_BYTES + TAIL + EPI_BYTES + 1024 + 512;
 };
 
 template <int STAGES, bool SPLIT3>
@@ -585,7 +460,9 @@ __global__ void __launch_bounds__(192) conv1_strip_kernel(const __grid_constant_
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t *res = smem;                       // resident weights, SW64 tiles (512-B aligned)
   uint8_t *ring = smem + S::RES_BYTES;       // strips
-  uint64_t *full_bar = reinterpret_cast<uint64_t *>(ring + STAGES * S::STAGE_BYTES + S::TAIL);
+  uint8_t *epi = ring + STAGES * S::STAGE_BYTES + S::TAIL;
+  float *bias_s = reinterpret_cast<float *>(epi + 4 * 4096);
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(epi + S::EPI_BYTES);
   uint64_t *empty_bar = full_bar + STAGES;
   uint64_t *tmem_full_bar = empty_bar + STAGES;
   uint64_t *tmem_empty_bar = tmem_full_bar + 2;
@@ -610,6 +487,7 @@ __global__ void __launch_bounds__(192) conv1_strip_kernel(const __grid_constant_
     ptx::prefetch_tmap(&p.b_map);
     ptx::prefetch_tmap(&p.a_map[0]);
   }
+  if (threadIdx.x < 64) bias_s[threadIdx.x] = p.bias[threadIdx.x];
   if (warp == 1) ptx::tmem_alloc(tmem_slot, TMEM_COLS);
   ptx::tc_fence_before();
   __syncthreads();
@@ -692,33 +570,14 @@ __global__ void __launch_bounds__(192) conv1_strip_kernel(const __grid_constant_
       ptx::mbar_wait(&tmem_full_bar[as], aph);
       ptx::tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)as * ACC_COLS;
-      const size_t pix = ((size_t)n_img * p.out_Hp + oh + p.out_py) * p.out_Wp + ow + p.out_px;
-      __nv_bfloat16 *dhi = p.out_hi + pix * 64;
-      __nv_bfloat16 *dlo = SPLIT3 ? (p.out_lo + pix * 64) : nullptr;
-#pragma unroll 1
-      for (int c = 0; c < 64; c += 32) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(trow + c, r);
-        if (valid) {
-          __align__(16) __nv_bfloat16 h[32];
-          __align__(16) __nv_bfloat16 l[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float v = __uint_as_float(r[j]) + __ldg(p.bias + c + j);
-            v = v > 0.f ? v : v * p.slope;
-            h[j] = __float2bfloat16_rn(v);
-            if (SPLIT3) l[j] = __float2bfloat16_rn(v - __bfloat162float(h[j]));
-          }
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            *reinterpret_cast<uint4 *>(dhi + c + j) = *reinterpret_cast<const uint4 *>(h + j);
-            if (SPLIT3) *reinterpret_cast<uint4 *>(dlo + c + j) = *reinterpret_cast<const uint4 *>(l + j);
-          }
-        }
-      }
+      const long long my_off = (((long long)n_img * p.out_Hp + oh + p.out_py) * p.out_Wp + ow + p.out_px) * 64;
+      uint32_t r[64];
+      ptx::tmem_ld_32x32(trow, r);
+      ptx::tmem_ld_32x32(trow + 32, r + 32);
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);  // accumulator stage is free again
+      epilogue_store64<SPLIT3>(r, bias_s, p.slope, epi + (warp - 2) * 4096, p.out_hi, p.out_lo, my_off, valid, lane);
       if (++as == 2) { as = 0; aph ^= 1u; }
     }
   }

@@ -1,7 +1,7 @@
 // net.cu -- FlowNetS encoder + fc + heads on the device (deepim/symbols/deepIM_flownet.py:53-116 and
 // 716-726), weight repacking, tensor-map construction and layer scheduling.
 //
-//   conv tower : 10 x conv_igemm_kernel (tcgen05 + TMA, conv_igemm.cuh), split-K + finalize for the
+//   conv tower : conv1_strip_kernel + 9 x conv_igemm_persistent_kernel (tcgen05 + TMA, conv_igemm.cuh), split-K + finalize for the
 //                layers whose tile count cannot fill 148 SMs
 //   fc6        : 81920 -> 256, a pure weight stream (HBM-bound): split-K mma.sync kernel (batch = M = 16),
 //                deterministic two-pass reduction (partials reduced in fixed order by the head kernel)
@@ -107,7 +107,7 @@ static void build_geometry(NetState *ns, int H, int W) {
       g.BW = cdiv(g.Wo, nt); g.BH = 1; g.n_col_tiles = nt;
     }
     g.kblocks = g.KH * g.KW * (g.Ceff / g.BLOCK_K);
-    g.occ = (g.BLOCK_N <= 128) ? 2 : 1;
+    g.occ = (i == 0) ? 2 : 1;
     h = g.Ho; w = g.Wo;
   }
 }
@@ -556,17 +556,17 @@ int net_forward(dim_ctx *ctx, int B, int precision, const float *zoom_factor, fl
         if (!set1) { DIM_CHECK(cudaFuncSetAttribute(conv1_strip_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S1::TOTAL)); set1 = true; }
         conv1_strip_kernel<4, true><<<tiles1 < sms ? tiles1 : sms, 192, S1::TOTAL, st>>>(kp, tiles1);
       } else {
-        using S1 = Conv1Smem<4, false>;
+        using S1 = Conv1Smem<3, false>;
         static bool set0 = false;
-        if (!set0) { DIM_CHECK(cudaFuncSetAttribute(conv1_strip_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S1::TOTAL)); set0 = true; }
-        conv1_strip_kernel<4, false><<<tiles1 < 2 * sms ? tiles1 : 2 * sms, 192, S1::TOTAL, st>>>(kp, tiles1);
+        if (!set0) { DIM_CHECK(cudaFuncSetAttribute(conv1_strip_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S1::TOTAL)); set0 = true; }
+        conv1_strip_kernel<3, false><<<tiles1 < 2 * sms ? tiles1 : 2 * sms, 192, S1::TOTAL, st>>>(kp, tiles1);
       }
       DIM_LAUNCH_CHECK();
       rc = 0;
     }
     else if (g.BLOCK_N <= 128)
       rc = s3 ? launch_conv2<128, 64, 3, true, false, 0>(kp, total_tiles, n_tiles, sms, st)
-              : launch_conv2<128, 64, 3, false, false, 0>(kp, total_tiles, n_tiles, 2 * sms, st);
+              : launch_conv2<128, 64, 5, false, false, 0>(kp, total_tiles, n_tiles, sms, st);
     else
       rc = s3 ? launch_conv2<256, 64, 2, true, false, 0>(kp, total_tiles, n_tiles, sms, st)
               : launch_conv2<256, 64, 4, false, false, 0>(kp, total_tiles, n_tiles, sms, st);
