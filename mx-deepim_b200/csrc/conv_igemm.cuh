@@ -30,6 +30,8 @@ struct ConvKParams {
   CUtensorMap a_lo_map[4];  // activation views (lo), SPLIT3 only
   CUtensorMap b_map;        // weights hi
   CUtensorMap b_lo_map;     // weights lo
+  CUtensorMap b2_map;       // weights hi, box = BLOCK_N/2 rows (CTA-pair kernel: each CTA loads half of N)
+  CUtensorMap b2_lo_map;
   int KH, KW, stride, cchunks;  // taps and channel chunks (Cin_eff / BLOCK_K)
   int BW, BH, n_col_tiles;
   int Hq, Ho, Wo, Bn;           // virtual rows per image, valid output extent, batch
@@ -586,6 +588,268 @@ __global__ void __launch_bounds__(192) conv1_strip_kernel(const __grid_constant_
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// v3: CTA-pair kernel (tcgen05.mma.cta_group::2).  Two CTAs of a cluster (same TPC) compute a
+// 256 x BLOCK_N tile: each CTA stages its own 128 activation rows and HALF of the weight tile; the
+// leader CTA issues the MMAs for both, the hardware reads the operand halves from both shared
+// memories and writes each CTA's 128 accumulator rows into its own TMEM.  Per CTA and K-block this
+// moves 16 KB (A) + BLOCK_N/2*128 B (B half) through shared memory for 128 x BLOCK_N x 64 MACs, i.e.
+// half the weight traffic of the 1-CTA kernel: the 1-CTA kernel is bound by shared-memory bandwidth
+// (operand reads + TMA fills), not by the tensor pipe.
+//   full[s]   : leader's barrier, completed by the TMA bytes of BOTH CTAs (peer-bit-masked address)
+//   empty[s]  : per CTA, released by the leader's tcgen05.commit multicast to both CTAs
+//   tmem_full : per CTA, multicast commit;  tmem_empty: leader's, 8 arrivals (4 epilogue warps x 2 CTAs)
+namespace ptx2 {
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // cute::Sm100MmaPeerBitMask: address of CTA 0's copy
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+          "r"(ptx::smem_u32(dst)),
+      "l"((uint64_t)map), "r"(ptx::smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+          "r"(ptx::smem_u32(dst)),
+      "l"((uint64_t)map), "r"(ptx::smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t *slot_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ptx::smem_u32(slot_smem)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8, %9, %10, %11, %12}, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u), "r"(0u), "r"(0u),
+      "r"(0u), "r"(0u)
+      : "memory");
+}
+// arrive on the barrier at this smem offset in BOTH CTAs when the issued MMAs have completed
+__device__ __forceinline__ void umma_commit_mc(uint64_t *bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          ptx::smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+// arrive on the leader CTA's copy of a barrier
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, 0;\n\tmbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(
+          ptx::smem_u32(bar))
+      : "memory");
+}
+}  // namespace ptx2
+
+template <int BLOCK_N, int STAGES, bool SPLIT3>
+struct ConvSmemPair {
+  static constexpr int A_BYTES = 128 * 64 * 2;
+  static constexpr int B_BYTES = (BLOCK_N / 2) * 64 * 2;  // this CTA's half of the weight tile
+  static constexpr int NPREC = SPLIT3 ? 2 : 1;
+  static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * NPREC;
+  static constexpr int EPI_BYTES = 4 * 4096 + 4096;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 512;
+};
+
+template <int BLOCK_N, int STAGES, bool SPLIT3>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192)
+    conv_igemm_pair_kernel(const __grid_constant__ ConvKParams p, const int total_pair_tiles, const int n_tiles) {
+  using S = ConvSmemPair<BLOCK_N, STAGES, SPLIT3>;
+  constexpr uint32_t LAYOUT = 2u, SBO = 1024u;
+  constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t *epi = smem + STAGES * S::STAGE_BYTES;
+  float *bias_s = reinterpret_cast<float *>(epi + 4 * 4096);
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(epi + S::EPI_BYTES);
+  uint64_t *empty_bar = full_bar + STAGES;
+  uint64_t *tmem_full_bar = empty_bar + STAGES;
+  uint64_t *tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx2::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int kb_per = (p.kblocks + p.ksplit - 1) / p.ksplit;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full_bar[a], 1);
+      ptx::mbar_init(&tmem_empty_bar[a], 8);  // 4 epilogue warps x 2 CTAs (leader's copy is the one used)
+    }
+    ptx::fence_barrier_init();
+    ptx::prefetch_tmap(&p.b2_map);
+    ptx::prefetch_tmap(&p.a_map[0]);
+  }
+  for (int c = threadIdx.x; c < p.Cout; c += blockDim.x) bias_s[c] = p.bias[c];
+  if (warp == 1) ptx2::tmem_alloc(tmem_slot, TMEM_COLS);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx2::cluster_sync();  // both CTAs' barriers are initialised before any remote arrive / multicast commit
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      const uint32_t tx_cta = (uint32_t)(p.BW * p.BH * 64 * 2 + (BLOCK_N / 2) * 64 * 2) * S::NPREC;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = pair; tile < total_pair_tiles; tile += npairs) {
+        const int z = tile % p.ksplit, mn = tile / p.ksplit;
+        const int nt = mn % n_tiles, mt = 2 * (mn / n_tiles) + (int)rank;
+        const int col_tile = mt % p.n_col_tiles, row_tile = mt / p.n_col_tiles;
+        const int g0 = row_tile * p.BH, ow0 = col_tile * p.BW;
+        const int n0 = nt * BLOCK_N + (int)rank * (BLOCK_N / 2);
+        const int kb0 = z * kb_per, kb1 = min(p.kblocks, kb0 + kb_per);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
+          const int tap = kb / p.cchunks, cc = kb - tap * p.cchunks;
+          const int kh = tap / p.KW, kw = tap - kh * p.KW;
+          int view = 0, dr = kh, dc = kw;
+          if (p.stride == 2) {
+            view = ((kh & 1) << 1) | (kw & 1);
+            dr = kh >> 1;
+            dc = kw >> 1;
+          }
+          uint8_t *st = smem + s * S::STAGE_BYTES;
+          if (leader) ptx::mbar_expect_tx(&full_bar[s], 2u * tx_cta);  // bytes landing in both CTAs
+          ptx2::tma_load_3d(st, &p.a_map[view], &full_bar[s], cc * 64, ow0 + dc, g0 + dr);
+          ptx2::tma_load_2d(st + S::A_BYTES, &p.b2_map, &full_bar[s], kb * 64, n0);
+          if (SPLIT3) {
+            ptx2::tma_load_3d(st + S::A_BYTES + S::B_BYTES, &p.a_lo_map[view], &full_bar[s], cc * 64, ow0 + dc, g0 + dr);
+            ptx2::tma_load_2d(st + 2 * S::A_BYTES + S::B_BYTES, &p.b2_lo_map, &full_bar[s], kb * 64, n0);
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader && lane == 0) {
+      int s = 0, as = 0;
+      uint32_t ph = 0, aph = 0;
+      for (int tile = pair; tile < total_pair_tiles; tile += npairs) {
+        const int z = tile % p.ksplit;
+        const int kb0 = z * kb_per, kb1 = min(p.kblocks, kb0 + kb_per);
+        ptx::mbar_wait(&tmem_empty_bar[as], aph ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + (uint32_t)as * BLOCK_N;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(&full_bar[s], ph);
+          ptx::tc_fence_after();
+          const uint32_t a_hi = ptx::smem_u32(smem + s * S::STAGE_BYTES);
+          const uint32_t b_hi = a_hi + S::A_BYTES;
+          const uint32_t a_lo = b_hi + S::B_BYTES;
+          const uint32_t b_lo = a_lo + S::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
+            const uint64_t da = ptx::umma_desc(a_hi + k * 32, SBO, LAYOUT);
+            const uint64_t db = ptx::umma_desc(b_hi + k * 32, SBO, LAYOUT);
+            ptx2::umma_f16(tmem_acc, da, db, p.idesc, acc);
+            if (SPLIT3) {
+              const uint64_t dal = ptx::umma_desc(a_lo + k * 32, SBO, LAYOUT);
+              const uint64_t dbl = ptx::umma_desc(b_lo + k * 32, SBO, LAYOUT);
+              ptx2::umma_f16(tmem_acc, dal, db, p.idesc, 1u);
+              ptx2::umma_f16(tmem_acc, da, dbl, p.idesc, 1u);
+            }
+          }
+          ptx2::umma_commit_mc(&empty_bar[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+        ptx2::umma_commit_mc(&tmem_full_bar[as]);
+        if (++as == 2) { as = 0; aph ^= 1u; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5, both CTAs)
+    const int quad = warp & 3;
+    const int m = quad * 32 + lane;
+    const int bh = m / p.BW, bw = m - bh * p.BW;
+    uint8_t *stg = epi + (warp - 2) * 4096;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int tile = pair; tile < total_pair_tiles; tile += npairs) {
+      const int z = tile % p.ksplit, mn = tile / p.ksplit;
+      const int nt = mn % n_tiles, mt = 2 * (mn / n_tiles) + (int)rank;
+      const int col_tile = mt % p.n_col_tiles, row_tile = mt / p.n_col_tiles;
+      const int g = row_tile * p.BH + bh, ow = col_tile * p.BW + bw, n0 = nt * BLOCK_N;
+      const int n_img = g / p.Hq, oh = g - n_img * p.Hq;
+      const bool valid = (m < p.BW * p.BH) && (n_img < p.Bn) && (oh < p.Ho) && (ow < p.Wo);
+      ptx::mbar_wait(&tmem_full_bar[as], aph);
+      ptx::tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)as * BLOCK_N;
+      if (p.ksplit > 1) {
+        const size_t opix = ((size_t)n_img * p.Ho + oh) * p.Wo + ow;
+        float *dst = p.partial + ((size_t)z * ((size_t)p.Bn * p.Ho * p.Wo) + opix) * p.Cout + n0;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(trow + c, r);
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<uint4 *>(dst + c + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx2::mbar_arrive_leader(&tmem_empty_bar[as]);
+      } else {
+        const long long my_off =
+            (((long long)n_img * p.out_Hp + oh + p.out_py) * p.out_Wp + ow + p.out_px) * p.Cout + n0;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 64) {
+          uint32_t r[64];
+          ptx::tmem_ld_32x32(trow + c, r);
+          ptx::tmem_ld_32x32(trow + c + 32, r + 32);
+          if (c + 64 >= BLOCK_N) {
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx2::mbar_arrive_leader(&tmem_empty_bar[as]);
+          }
+          epilogue_store64<SPLIT3>(r, bias_s + n0 + c, p.slope, stg, p.out_hi, p.out_lo, my_off + c, valid, lane);
+        }
+      }
+      if (++as == 2) { as = 0; aph ^= 1u; }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx2::cluster_sync();  // the peer may still be signalling our barriers / reading our shared memory
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx2::tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 

@@ -33,6 +33,7 @@ struct LayerGeom {
   // implicit GEMM view
   int KH, KW, stride_eff, Ceff, Hq;
   int BLOCK_N, BLOCK_K, BW, BH, n_col_tiles, kblocks;
+  int pair;  // 1: CTA-pair kernel (cta_group::2, 256 x BLOCK_N tiles)
   int occ;  // resident CTAs per SM of the persistent kernel variant used for this layer (bf16 mode)
 };
 
@@ -64,6 +65,15 @@ static constexpr int FC6_KC = 256;
 static constexpr int FC6_SPLITS = FC6_K / FC6_KC;  // 320
 
 // --------------------------------------------------------------------------------- geometry
+static bool use_pair_kernel() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("DIM_CONV_PAIR");  // 1 enables the cta_group::2 kernel (A/B testing)
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v != 0;
+}
+
 static void build_geometry(NetState *ns, int H, int W) {
   int h = H, w = W;
   for (int i = 0; i < 10; ++i) {
@@ -108,6 +118,7 @@ static void build_geometry(NetState *ns, int H, int W) {
     }
     g.kblocks = g.KH * g.KW * (g.Ceff / g.BLOCK_K);
     g.occ = (i == 0) ? 2 : 1;
+    g.pair = (i >= 1 && use_pair_kernel()) ? 1 : 0;
     h = g.Ho; w = g.Wo;
   }
 }
@@ -115,8 +126,9 @@ static void build_geometry(NetState *ns, int H, int W) {
 // split-K factor: maximise the fill of the last wave of the persistent grid (capacity = SMs x CTAs/SM)
 // with a small penalty per extra slice (fp32 partial traffic); every slice keeps >= 8 K-blocks.
 static int choose_ksplit(const NetState *ns, const LayerGeom &g, int B) {
-  const int tiles = cdiv(B * g.Hq, g.BH) * g.n_col_tiles * (g.Cout / g.BLOCK_N);
-  const int cap = ns->num_sms * g.occ;
+  int tiles = cdiv(B * g.Hq, g.BH) * g.n_col_tiles * (g.Cout / g.BLOCK_N);
+  int cap = ns->num_sms * g.occ;
+  if (g.pair) { tiles = cdiv(cdiv(B * g.Hq, g.BH) * g.n_col_tiles, 2) * (g.Cout / g.BLOCK_N); cap = ns->num_sms / 2; }
   if (tiles >= 2 * cap || g.kblocks < 16 || g.BLOCK_K == 32) return 1;  // conv1 keeps its weights resident: no split
   int best = 1;
   double best_score = -1.0;
@@ -212,6 +224,9 @@ static int build_maps(NetState *ns, int B, TensorMaps &tm) {
       const uint32_t box[2] = {(uint32_t)g.BLOCK_K, (uint32_t)g.BLOCK_N};
       if (int rc = encode_map(&kp.b_map, ns->w_hi[i], 2, dims, str, box, g.BLOCK_K)) return rc;
       if (int rc = encode_map(&kp.b_lo_map, ns->w_lo[i], 2, dims, str, box, g.BLOCK_K)) return rc;
+      const uint32_t box2[2] = {(uint32_t)g.BLOCK_K, (uint32_t)(g.BLOCK_N / 2)};
+      if (int rc = encode_map(&kp.b2_map, ns->w_hi[i], 2, dims, str, box2, g.BLOCK_K)) return rc;
+      if (int rc = encode_map(&kp.b2_lo_map, ns->w_lo[i], 2, dims, str, box2, g.BLOCK_K)) return rc;
     }
     kp.KH = g.KH; kp.KW = g.KW; kp.stride = g.stride_eff; kp.cchunks = g.Ceff / g.BLOCK_K;
     kp.BW = g.BW; kp.BH = g.BH; kp.n_col_tiles = g.n_col_tiles;
@@ -225,7 +240,7 @@ static int build_maps(NetState *ns, int B, TensorMaps &tm) {
     kp.Cout = g.Cout;
     kp.kblocks = g.kblocks;
     kp.ksplit = tm.ksplit[i] = choose_ksplit(ns, g, B);
-    kp.idesc = make_idesc(128, g.BLOCK_N);
+    kp.idesc = make_idesc(g.pair ? 256 : 128, g.BLOCK_N);
     kp.slope = 0.1f;
     kp.bias = ns->bias[i];
     kp.out_hi = ns->act_hi[i + 1];
@@ -520,6 +535,21 @@ static int launch_conv2(const ConvKParams &kp, int total_tiles, int n_tiles, int
   return 0;
 }
 
+template <int BN, int ST, bool S3>
+static int launch_pair(const ConvKParams &kp, int pair_tiles, int n_tiles, int sms, cudaStream_t st) {
+  using S = ConvSmemPair<BN, ST, S3>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DIM_CHECK(cudaFuncSetAttribute(conv_igemm_pair_kernel<BN, ST, S3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   S::TOTAL));
+    attr_set = true;
+  }
+  const int pairs = pair_tiles < sms / 2 ? pair_tiles : sms / 2;
+  conv_igemm_pair_kernel<BN, ST, S3><<<2 * pairs, 192, S::TOTAL, st>>>(kp, pair_tiles, n_tiles);  // __cluster_dims__(2,1,1)
+  DIM_LAUNCH_CHECK();
+  return 0;
+}
+
 // where conv1's input buffer expects pixel (i,j) of the 8-channel blob (space-to-depth, pad 3)
 void net_input_geometry(dim_ctx *ctx, int *rows, int *cols, int *pad, __nv_bfloat16 **hi, __nv_bfloat16 **lo) {
   NetState *ns = ctx->net;
@@ -564,9 +594,19 @@ int net_forward(dim_ctx *ctx, int B, int precision, const float *zoom_factor, fl
       DIM_LAUNCH_CHECK();
       rc = 0;
     }
-    else if (g.BLOCK_N <= 128)
+    else if (g.pair) {
+      const int m_tiles = cdiv(B * g.Hq, g.BH) * g.n_col_tiles;
+      const int pair_tiles = cdiv(m_tiles, 2) * n_tiles * kp.ksplit;
+      if (g.BLOCK_N == 128)
+        rc = s3 ? launch_pair<128, 4, true>(kp, pair_tiles, n_tiles, sms, st) : launch_pair<128, 8, false>(kp, pair_tiles, n_tiles, sms, st);
+      else
+        rc = s3 ? launch_pair<256, 3, true>(kp, pair_tiles, n_tiles, sms, st) : launch_pair<256, 6, false>(kp, pair_tiles, n_tiles, sms, st);
+    } else if (g.BLOCK_N <= 128) {
+      static const bool occ2 = [] { const char *e = getenv("DIM_CONV2_OCC2"); return e && e[0] == '1'; }();
       rc = s3 ? launch_conv2<128, 64, 3, true, false, 0>(kp, total_tiles, n_tiles, sms, st)
-              : launch_conv2<128, 64, 5, false, false, 0>(kp, total_tiles, n_tiles, sms, st);
+              : (occ2 ? launch_conv2<128, 64, 2, false, false, 0>(kp, total_tiles, n_tiles, 2 * sms, st)
+                      : launch_conv2<128, 64, 5, false, false, 0>(kp, total_tiles, n_tiles, sms, st));
+    }
     else
       rc = s3 ? launch_conv2<256, 64, 2, true, false, 0>(kp, total_tiles, n_tiles, sms, st)
               : launch_conv2<256, 64, 4, false, false, 0>(kp, total_tiles, n_tiles, sms, st);
