@@ -188,6 +188,16 @@ DIM_API int32_t dim_refine_host(dim_ctx *ctx, const uint8_t *image_observed_u8_h
                                 float zfar, const double *pixel_means_rgb_host, int32_t precision,
                                 double *poses_out_host, float *se3_out_host, void *stream);
 
+/* Same as dim_refine_host but returns right after enqueueing the copies and kernels on `stream`
+ * (no synchronisation): the host output buffers are valid once the stream has been synchronised.
+ * Lets a caller overlap the H2D copy of batch k+1 (second context / stream) with the compute of k. */
+DIM_API int32_t dim_refine_host_async(dim_ctx *ctx, const uint8_t *image_observed_u8_host,
+                                      const int32_t *cls_idx_host, const double *pose_init_host,
+                                      int32_t B, int32_t n_iter, const float *K9_host, float znear,
+                                      float zfar, const double *pixel_means_rgb_host,
+                                      int32_t precision, double *poses_out_host, float *se3_out_host,
+                                      void *stream);
+
 /* BGR u8 HWC -> RGB-mean f32 CHW on device (lib/utils/image.py:583-594 transform). */
 DIM_API int32_t dim_transform_image_u8(dim_ctx *ctx, const uint8_t *bgr_u8, int32_t B,
                                        const double *pixel_means_rgb_host, float *image,

@@ -343,9 +343,10 @@ DIM_API int32_t dim_refine(dim_ctx *ctx, const float *image_observed, const int3
                      se3, zoom_factor, bbox, st);
 }
 
-DIM_API int32_t dim_refine_host(dim_ctx *ctx, const uint8_t *img_u8, const int32_t *cls_host, const double *pose_host,
-                                int32_t B, int32_t n_iter, const float *K9, float zn, float zf, const double *means,
-                                int32_t precision, double *poses_out, float *se3_out, void *stream) {
+DIM_API int32_t dim_refine_host_async(dim_ctx *ctx, const uint8_t *img_u8, const int32_t *cls_host,
+                                      const double *pose_host, int32_t B, int32_t n_iter, const float *K9, float zn,
+                                      float zf, const double *means, int32_t precision, double *poses_out,
+                                      float *se3_out, void *stream) {
   DIM_REQUIRE(ctx && img_u8 && cls_host && pose_host && K9 && means && poses_out, "dim_refine_host: NULL argument");
   DIM_REQUIRE(B >= 1 && B <= ctx->max_batch, "dim_refine_host: batch exceeds max_batch");
   DIM_REQUIRE(n_iter >= 1 && n_iter <= 8, "dim_refine_host: n_iter must be in [1,8]");
@@ -361,7 +362,16 @@ DIM_API int32_t dim_refine_host(dim_ctx *ctx, const uint8_t *img_u8, const int32
   DIM_CHECK(cudaMemcpyAsync(poses_out, ctx->poses_dev, sizeof(double) * (size_t)n_iter * B * 12, cudaMemcpyDeviceToHost, st));
   if (se3_out)
     DIM_CHECK(cudaMemcpyAsync(se3_out, ctx->se3_hist_dev, sizeof(float) * (size_t)n_iter * B * 7, cudaMemcpyDeviceToHost, st));
-  DIM_CHECK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+DIM_API int32_t dim_refine_host(dim_ctx *ctx, const uint8_t *img_u8, const int32_t *cls_host, const double *pose_host,
+                                int32_t B, int32_t n_iter, const float *K9, float zn, float zf, const double *means,
+                                int32_t precision, double *poses_out, float *se3_out, void *stream) {
+  if (int rc = dim_refine_host_async(ctx, img_u8, cls_host, pose_host, B, n_iter, K9, zn, zf, means, precision, poses_out,
+                                     se3_out, stream))
+    return rc;
+  DIM_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
   return 0;
 }
 

@@ -40,6 +40,7 @@ struct LayerGeom {
 struct TensorMaps {
   ConvKParams kp[10];
   int ksplit[10];
+  LayerGeom g[10];  // per-batch-size effective geometry (tile width may depend on the batch)
 };
 
 struct NetState {
@@ -123,6 +124,19 @@ static void build_geometry(NetState *ns, int H, int W) {
   }
 }
 
+// Layers whose 128 x 256 tile count cannot fill the machine at this batch size run 128 x 128 tiles with
+// two CTAs per SM instead (twice the tiles, no or less split-K).
+static LayerGeom effective_geom(const NetState *ns, int i, int B) {
+  LayerGeom g = ns->g[i];
+  static const bool small_n = [] { const char *e = getenv("DIM_CONV_SMALL_BN128"); return e && e[0] == '1'; }();  // measured slower: opt-in
+  if (i >= 1 && g.BLOCK_N == 256 && !g.pair && small_n) {
+    const int tiles256 = cdiv(B * g.Hq, g.BH) * g.n_col_tiles * (g.Cout / 256);
+    if (tiles256 < ns->num_sms) { g.BLOCK_N = 128; g.occ = 2; }
+  }
+  if (i >= 1 && g.BLOCK_N == 128 && ns->g[i].BLOCK_N == 128) g.occ = 2;  // conv2
+  return g;
+}
+
 // split-K factor: maximise the fill of the last wave of the persistent grid (capacity = SMs x CTAs/SM)
 // with a small penalty per extra slice (fp32 partial traffic); every slice keeps >= 8 K-blocks.
 static int choose_ksplit(const NetState *ns, const LayerGeom &g, int B) {
@@ -188,7 +202,8 @@ static uint32_t make_idesc(int M, int N) {
 
 static int build_maps(NetState *ns, int B, TensorMaps &tm) {
   for (int i = 0; i < 10; ++i) {
-    const LayerGeom &g = ns->g[i];
+    tm.g[i] = effective_geom(ns, i, B);
+    const LayerGeom &g = tm.g[i];
     ConvKParams &kp = tm.kp[i];
     memset(&kp, 0, sizeof(kp));
     for (int lo = 0; lo < 2; ++lo) {
@@ -424,7 +439,7 @@ int net_create(dim_ctx *ctx) {
   size_t pmax = 0;
   for (int B = 1; B <= ctx->max_batch; ++B)
     for (int i = 0; i < 10; ++i) {
-      int ks = choose_ksplit(ns, ns->g[i], B);
+      int ks = choose_ksplit(ns, effective_geom(ns, i, B), B);
       if (ks > 1) {
         size_t e = (size_t)ks * B * ns->g[i].Ho * ns->g[i].Wo * ns->g[i].Cout;
         pmax = e > pmax ? e : pmax;
@@ -572,7 +587,7 @@ int net_forward(dim_ctx *ctx, int B, int precision, const float *zoom_factor, fl
   const TensorMaps &tm = it->second;
   const bool s3 = precision == DIM_PREC_BF16X3;
   for (int i = 0; i < 10; ++i) {
-    const LayerGeom &g = ns->g[i];
+    const LayerGeom &g = tm.g[i];
     const ConvKParams &kp = tm.kp[i];
     const int n_tiles = g.Cout / g.BLOCK_N;
     const int total_tiles = cdiv(B * g.Hq, g.BH) * g.n_col_tiles * n_tiles * kp.ksplit;
@@ -602,10 +617,9 @@ int net_forward(dim_ctx *ctx, int B, int precision, const float *zoom_factor, fl
       else
         rc = s3 ? launch_pair<256, 3, true>(kp, pair_tiles, n_tiles, sms, st) : launch_pair<256, 6, false>(kp, pair_tiles, n_tiles, sms, st);
     } else if (g.BLOCK_N <= 128) {
-      static const bool occ2 = [] { const char *e = getenv("DIM_CONV2_OCC2"); return e && e[0] == '1'; }();
       rc = s3 ? launch_conv2<128, 64, 3, true, false, 0>(kp, total_tiles, n_tiles, sms, st)
-              : (occ2 ? launch_conv2<128, 64, 2, false, false, 0>(kp, total_tiles, n_tiles, 2 * sms, st)
-                      : launch_conv2<128, 64, 5, false, false, 0>(kp, total_tiles, n_tiles, sms, st));
+              : (g.occ == 2 ? launch_conv2<128, 64, 2, false, false, 0>(kp, total_tiles, n_tiles, 2 * sms, st)
+                            : launch_conv2<128, 64, 5, false, false, 0>(kp, total_tiles, n_tiles, sms, st));
     }
     else
       rc = s3 ? launch_conv2<256, 64, 2, true, false, 0>(kp, total_tiles, n_tiles, sms, st)

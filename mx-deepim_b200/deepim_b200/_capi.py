@@ -43,6 +43,7 @@ SIGNATURES = {
     "dim_net_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, vp, vp, vp]),
     "dim_refine": (i32, [vp, vp, vp, vp, i32, i32, pf32, f32, f32, pf64, i32, vp, vp, vp, vp, vp, vp]),
     "dim_refine_host": (i32, [vp, vp, vp, vp, i32, i32, pf32, f32, f32, pf64, i32, vp, vp, vp]),
+    "dim_refine_host_async": (i32, [vp, vp, vp, vp, i32, i32, pf32, f32, f32, pf64, i32, vp, vp, vp]),
     "dim_transform_image_u8": (i32, [vp, vp, i32, pf64, vp, vp]),
     "dim_debug_activation": (i32, [vp, i32, i32, vp, u64]),
     "dim_debug_layer_geometry": (i32, [vp, i32, C.POINTER(i32)]),

@@ -272,9 +272,10 @@ class Context:
 
     def refine_host(self, image_observed_u8, cls_idx, pose_init, K, n_iter=4, znear=0.25, zfar=6.0,
                     pixel_means_rgb=(103.939, 116.779, 123.68), precision=capi.PREC_BF16, poses_out=None,
-                    se3_out=None):
+                    se3_out=None, sync=True):
         """Host-buffer entry (what a tester loop calls): uint8 BGR HWC images (pinned torch tensors or
-        numpy), host poses in / out.  Synchronous."""
+        numpy), host poses in / out.  sync=False only enqueues on the current torch stream (outputs must
+        then be pinned and are valid after the stream is synchronised)."""
         def hptr(a):
             return C.c_void_p(a.data_ptr()) if isinstance(a, torch.Tensor) else C.c_void_p(a.ctypes.data)
         B = image_observed_u8.shape[0]
@@ -282,10 +283,10 @@ class Context:
             poses_out = np.empty((n_iter, B, 3, 4), np.float64)
         if se3_out is None:
             se3_out = np.empty((n_iter, B, 7), np.float32)
-        check(lib.dim_refine_host(self._h, hptr(image_observed_u8), hptr(cls_idx), hptr(pose_init), B, n_iter,
+        fn = lib.dim_refine_host if sync else lib.dim_refine_host_async
+        check(fn(self._h, hptr(image_observed_u8), hptr(cls_idx), hptr(pose_init), B, n_iter,
                                   farr(np.asarray(K, np.float32).reshape(9), 9), znear, zfar,
-                                  farr(pixel_means_rgb, 3, C.c_double), precision, hptr(poses_out), hptr(se3_out),
-                                  _stream()))
+                 farr(pixel_means_rgb, 3, C.c_double), precision, hptr(poses_out), hptr(se3_out), _stream()))
         return poses_out, se3_out
 
 
