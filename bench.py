@@ -145,7 +145,7 @@ def run_b200(args):
     mesh = synth.make_blob()  # C2
     weights = synth.make_weights(0)
     refiner = PoseRefiner([mesh], weights, K, device=local_rank, max_batch=B, n_iter=N_ITER, pixel_means_rgb=means,
-                          precision=args.precision, n_slots=2)
+                          precision=args.precision, n_slots=args.slots)
     ctx = refiner.ctx
     sets = make_inputs(ctx, synth, mesh, B, 3, 1000 + rank, dev, torch)
 
@@ -163,7 +163,7 @@ def run_b200(args):
         pending, last = [], None
         for k in range(n_steps):
             s = sets[k % len(sets)]
-            if len(pending) == 2:
+            if len(pending) == len(refiner.slots):
                 last = refiner.result(pending.pop(0))
             pending.append(refiner.submit(s["u8_host"], s["cls_host"], s["pose_host"]))
         for t in pending:
@@ -176,7 +176,7 @@ def run_b200(args):
     ctxs = [s_["ctx"] for s_ in refiner.slots]
 
     def step_dev2(k):
-        i = k % 2
+        i = k % len(streams)
         with torch.cuda.stream(streams[i]):
             s = sets[k % len(sets)]
             return ctxs[i].refine(s["img_dev"], s["cls_dev"], s["pose_dev"], K, N_ITER, pixel_means_rgb=means,
@@ -184,7 +184,10 @@ def run_b200(args):
 
     for k in range(max(W_steps, 3)):
         step_dev(k)
+    torch.cuda.synchronize()  # a context must only ever be driven from one stream at a time
+    for k in range(2 * len(streams)):
         step_dev2(k)
+    torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.3)
@@ -258,7 +261,7 @@ def run_b200(args):
             "warmup": max(W_steps, 3), "ms_per_step": round(ms_total / K_steps, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if prec == capi.PREC_BF16 else "bf16x3",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "n_iter": N_ITER, "precision": args.precision, "batches_in_flight": 2,
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "n_iter": N_ITER, "precision": args.precision, "batches_in_flight": args.slots,
                        "l2": "per-step working set (~1.6 GB of activations + 90 MB weights + 59 MB inputs) exceeds the "
                              "126 MB L2; 3 rotating input sets"},
             "clocks": clocks,
@@ -368,6 +371,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="instances per GPU")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--slots", type=int, default=2, help="independent batches in flight per GPU (streams)")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = 5 if args.steps is None else args.steps

@@ -210,9 +210,38 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ptx::smem_u32(bar)) : "memory");
 }
 
+// Work items of one CTA of the persistent kernel.  Phase 1: whole tiles round*G + c for the R = T/G full
+// waves (all CTAs walk the K range in lock-step, so the weight tile of a K-block is requested by every SM
+// at about the same time).  Phase 2: the T - R*G tiles of the partial last wave are each cut into `ks`
+// K slices (ks = G / tail tiles) so the tail occupies the whole machine for 1/ks of a tile time instead of
+// a fraction of it for a full tile time; slices leave fp32 partials that conv_tail_finalize_kernel reduces
+// in fixed order (deterministic; layers with fewer tiles than SMs are "all tail" = classic split-K).
+struct WorkIter {
+  int round, R, G, c, KB, base_tile, tail_items, ks, kb_per;
+  bool tail_done;
+  // returns false when done; slice < 0 for a whole tile
+  __device__ __forceinline__ bool next(int &tile, int &kb0, int &kb1, int &slice) {
+    if (round < R) {
+      tile = round * G + c;
+      kb0 = 0; kb1 = KB; slice = -1;
+      ++round;
+      return true;
+    }
+    if (tail_done || c >= tail_items) return false;
+    tail_done = true;
+    const int t = c / ks, z = c - t * ks;
+    tile = base_tile + t;
+    kb0 = z * kb_per;
+    kb1 = min(KB, kb0 + kb_per);
+    slice = (ks > 1) ? z : -1;
+    return true;
+  }
+};
+
 template <int BLOCK_N, int BLOCK_K, int STAGES, bool SPLIT3, bool RESIDENT_B, int KBLOCKS_RES>
 __global__ void __launch_bounds__(192) conv_igemm_persistent_kernel(const __grid_constant__ ConvKParams p,
-                                                                    const int total_tiles, const int n_tiles) {
+                                                                    const int total_tiles, const int n_tiles,
+                                                                    const int ks_tail, float *__restrict__ ws) {
   using S = ConvSmem2<BLOCK_N, BLOCK_K, STAGES, SPLIT3, RESIDENT_B, KBLOCKS_RES>;
   constexpr uint32_t LAYOUT = (BLOCK_K == 64) ? 2u : 4u;
   constexpr uint32_t SBO = 8u * BLOCK_K * 2u;
@@ -221,8 +250,8 @@ __global__ void __launch_bounds__(192) conv_igemm_persistent_kernel(const __grid
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t *res = smem + STAGES * S::STAGE_BYTES;  // resident weights (1024-aligned: stage sizes are multiples of 1 KB)
-  uint8_t *epi = res + S::RES_BYTES;               // per-warp staging tiles + bias
+  uint8_t *res = smem + STAGES * S::STAGE_BYTES;
+  uint8_t *epi = res + S::RES_BYTES;
   float *bias_s = reinterpret_cast<float *>(epi + 4 * 4096);
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(epi + S::EPI_BYTES);
   uint64_t *empty_bar = full_bar + STAGES;
@@ -232,7 +261,13 @@ __global__ void __launch_bounds__(192) conv_igemm_persistent_kernel(const __grid
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(res_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kb_per = (p.kblocks + p.ksplit - 1) / p.ksplit;
+  WorkIter it;
+  it.KB = p.kblocks; it.G = gridDim.x; it.c = blockIdx.x; it.round = 0; it.tail_done = false;
+  it.R = total_tiles / (int)gridDim.x;
+  it.base_tile = it.R * (int)gridDim.x;
+  it.ks = ks_tail;
+  it.tail_items = (total_tiles - it.base_tile) * ks_tail;
+  it.kb_per = (p.kblocks + ks_tail - 1) / ks_tail;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -268,12 +303,11 @@ __global__ void __launch_bounds__(192) conv_igemm_persistent_kernel(const __grid
       const uint32_t tx = (uint32_t)(p.BW * p.BH * BLOCK_K * 2 + (RESIDENT_B ? 0 : BLOCK_N * BLOCK_K * 2)) * S::NPREC;
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int z = tile % p.ksplit, mn = tile / p.ksplit;
-        const int nt = mn % n_tiles, mt = mn / n_tiles;
+      int tile, kb0, kb1, slice;
+      while (it.next(tile, kb0, kb1, slice)) {
+        const int nt = tile % n_tiles, mt = tile / n_tiles;
         const int col_tile = mt % p.n_col_tiles, row_tile = mt / p.n_col_tiles;
         const int g0 = row_tile * p.BH, ow0 = col_tile * p.BW, n0 = nt * BLOCK_N;
-        const int kb0 = z * kb_per, kb1 = min(p.kblocks, kb0 + kb_per);
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
           const int tap = kb / p.cchunks, cc = kb - tap * p.cchunks;
@@ -309,9 +343,8 @@ __global__ void __launch_bounds__(192) conv_igemm_persistent_kernel(const __grid
       }
       int s = 0, as = 0;
       uint32_t ph = 0, aph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int z = tile % p.ksplit;
-        const int kb0 = z * kb_per, kb1 = min(p.kblocks, kb0 + kb_per);
+      int tile, kb0, kb1, slice;
+      while (it.next(tile, kb0, kb1, slice)) {
         ptx::mbar_wait(&tmem_empty_bar[as], aph ^ 1u);  // epilogue has drained this accumulator stage
         ptx::tc_fence_after();
         const uint32_t tmem_acc = tmem_base + (uint32_t)as * ACC_COLS;
@@ -354,35 +387,36 @@ __global__ void __launch_bounds__(192) conv_igemm_persistent_kernel(const __grid
     const int quad = warp & 3;
     const int m = quad * 32 + lane;
     const int bh = m / p.BW, bw = m - bh * p.BW;
+    uint8_t *stg = epi + (warp - 2) * 4096;
     int as = 0;
     uint32_t aph = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int z = tile % p.ksplit, mn = tile / p.ksplit;
-      const int nt = mn % n_tiles, mt = mn / n_tiles;
-      const int col_tile = mt % p.n_col_tiles, row_tile = mt / p.n_col_tiles;
-      const int g = row_tile * p.BH + bh, ow = col_tile * p.BW + bw, n0 = nt * BLOCK_N;
-      const int n_img = g / p.Hq, oh = g - n_img * p.Hq;
-      const bool valid = (m < p.BW * p.BH) && (n_img < p.Bn) && (oh < p.Ho) && (ow < p.Wo);
+    int tile, kb0, kb1, slice;
+    while (it.next(tile, kb0, kb1, slice)) {
       ptx::mbar_wait(&tmem_full_bar[as], aph);
       ptx::tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)as * ACC_COLS;
-      if (p.ksplit > 1) {
-        const size_t opix = ((size_t)n_img * p.Ho + oh) * p.Wo + ow;
-        float *dst = p.partial + ((size_t)z * ((size_t)p.Bn * p.Ho * p.Wo) + opix) * p.Cout + n0;
+      if (slice >= 0) {
+        // K slice of a tail tile: fp32 partial [tail tile][slice][row][BLOCK_N] for conv_tail_finalize_kernel
+        float *dst = ws + ((size_t)((tile - it.base_tile) * it.ks + slice) * 128 + m) * BLOCK_N;
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N; c += 32) {
           uint32_t r[32];
           ptx::tmem_ld_32x32(trow + c, r);
-          if (valid) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<uint4 *>(dst + c + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-          }
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<uint4 *>(dst + c + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
         }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
       } else {
+        const int nt = tile % n_tiles, mt = tile / n_tiles;
+        const int col_tile = mt % p.n_col_tiles, row_tile = mt / p.n_col_tiles;
+        const int g = row_tile * p.BH + bh, ow = col_tile * p.BW + bw, n0 = nt * BLOCK_N;
+        const int n_img = g / p.Hq, oh = g - n_img * p.Hq;
+        const bool valid = (m < p.BW * p.BH) && (n_img < p.Bn) && (oh < p.Ho) && (ow < p.Wo);
         const long long my_off =
             (((long long)n_img * p.out_Hp + oh + p.out_py) * p.out_Wp + ow + p.out_px) * p.Cout + n0;
-        uint8_t *stg = epi + (warp - 2) * 4096;
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N; c += 64) {
           uint32_t r[64];
@@ -396,11 +430,6 @@ __global__ void __launch_bounds__(192) conv_igemm_persistent_kernel(const __grid
           epilogue_store64<SPLIT3>(r, bias_s + n0 + c, p.slope, stg, p.out_hi, p.out_lo, my_off + c, valid, lane);
         }
       }
-      if (p.ksplit > 1) {
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
-      }
       if (++as == 2) { as = 0; aph ^= 1u; }
     }
   }
@@ -410,6 +439,43 @@ __global__ void __launch_bounds__(192) conv_igemm_persistent_kernel(const __grid
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, TMEM_COLS);
   }
+}
+
+// reduces the K slices of the tail tiles: one thread per (tail tile, row, 4 channels)
+__global__ void __launch_bounds__(256) conv_tail_finalize_kernel(const __grid_constant__ ConvKParams p, const float *ws,
+                                                                 int base_tile, int tail_tiles, int ks, int n_tiles,
+                                                                 int BN, int split3) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cq = BN / 4;
+  if (idx >= (size_t)tail_tiles * 128 * cq) return;
+  const int c4 = (int)(idx % cq) * 4;
+  const int m = (int)((idx / cq) % 128);
+  const int t = (int)(idx / ((size_t)cq * 128));
+  const int tile = base_tile + t;
+  const int nt = tile % n_tiles, mt = tile / n_tiles;
+  const int col_tile = mt % p.n_col_tiles, row_tile = mt / p.n_col_tiles;
+  const int bh = m / p.BW, bw = m - bh * p.BW;
+  const int g = row_tile * p.BH + bh, ow = col_tile * p.BW + bw, n0 = nt * BN;
+  const int n_img = g / p.Hq, oh = g - n_img * p.Hq;
+  if (!((m < p.BW * p.BH) && (n_img < p.Bn) && (oh < p.Ho) && (ow < p.Wo))) return;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int z = 0; z < ks; ++z) {
+    const float4 v = *reinterpret_cast<const float4 *>(ws + ((size_t)(t * ks + z) * 128 + m) * BN + c4);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  const int c = n0 + c4;
+  float v[4] = {acc.x + p.bias[c], acc.y + p.bias[c + 1], acc.z + p.bias[c + 2], acc.w + p.bias[c + 3]};
+  const size_t pix = ((size_t)n_img * p.out_Hp + oh + p.out_py) * p.out_Wp + ow + p.out_px;
+  __align__(8) __nv_bfloat16 h[4];
+  __align__(8) __nv_bfloat16 l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float x = v[j] > 0.f ? v[j] : v[j] * p.slope;
+    h[j] = __float2bfloat16_rn(x);
+    l[j] = __float2bfloat16_rn(x - __bfloat162float(h[j]));
+  }
+  *reinterpret_cast<uint2 *>(p.out_hi + pix * p.Cout + c) = *reinterpret_cast<const uint2 *>(h);
+  if (split3) *reinterpret_cast<uint2 *>(p.out_lo + pix * p.Cout + c) = *reinterpret_cast<const uint2 *>(l);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -56,6 +56,7 @@ struct NetState {
   float *fc6_partial = nullptr;  // [FC6_SPLITS][max_batch][256]
   float *conv_partial = nullptr;
   size_t conv_partial_elems = 0;
+  float *tail_ws = nullptr;  // K-slice partials of the tail tiles: [<= 2*SMs slots][128][256] fp32
   bool loaded = false, net_ok = false;
   std::map<int, TensorMaps> maps;  // per batch size
   int max_batch = 0, num_sms = 148;
@@ -139,7 +140,15 @@ static LayerGeom effective_geom(const NetState *ns, int i, int B) {
 
 // split-K factor: maximise the fill of the last wave of the persistent grid (capacity = SMs x CTAs/SM)
 // with a small penalty per extra slice (fp32 partial traffic); every slice keeps >= 8 K-blocks.
+static bool use_tail_split() {
+  // opt-in: helps a single batch in flight by ~1%, costs ~5% when two batches overlap (the other stream
+  // already fills the tail-wave bubbles and the extra finalize launches / fp32 partials only add traffic)
+  static const bool v = [] { const char *e = getenv("DIM_CONV_TAILSPLIT"); return e && e[0] == '1'; }();
+  return v;
+}
+
 static int choose_ksplit(const NetState *ns, const LayerGeom &g, int B) {
+  if (!g.pair) return 1;  // the persistent kernel splits only its tail tiles (see launch_conv2)
   int tiles = cdiv(B * g.Hq, g.BH) * g.n_col_tiles * (g.Cout / g.BLOCK_N);
   int cap = ns->num_sms * g.occ;
   if (g.pair) { tiles = cdiv(cdiv(B * g.Hq, g.BH) * g.n_col_tiles, 2) * (g.Cout / g.BLOCK_N); cap = ns->num_sms / 2; }
@@ -449,6 +458,7 @@ int net_create(dim_ctx *ctx) {
   if (pmax)
     if (int rc = dev_alloc(ctx, &ns->conv_partial, pmax, false)) return rc;
   if (int rc = dev_alloc(ctx, &ns->fc6_partial, (size_t)FC6_SPLITS * ctx->max_batch * 256, true)) return rc;
+  if (int rc = dev_alloc(ctx, &ns->tail_ws, (size_t)2 * ns->num_sms * 128 * 256, false)) return rc;
   return 0;
 }
 
@@ -536,7 +546,7 @@ int net_load(dim_ctx *ctx, const float *const *W, const float *const *Bv) {
 }
 
 template <int BN, int BK, int ST, bool S3, bool RES, int KRES>
-static int launch_conv2(const ConvKParams &kp, int total_tiles, int n_tiles, int cap, cudaStream_t st) {
+static int launch_conv2(NetState *ns, const ConvKParams &kp, int total_tiles, int n_tiles, int cap, cudaStream_t st) {
   using S = ConvSmem2<BN, BK, ST, S3, RES, KRES>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -545,8 +555,27 @@ static int launch_conv2(const ConvKParams &kp, int total_tiles, int n_tiles, int
     attr_set = true;
   }
   const int grid = total_tiles < cap ? total_tiles : cap;
-  conv_igemm_persistent_kernel<BN, BK, ST, S3, RES, KRES><<<grid, 192, S::TOTAL, st>>>(kp, total_tiles, n_tiles);
+  // tail tiles (partial last wave, or the whole layer when it has fewer tiles than CTAs) are cut into
+  // ks K slices so that they fill the machine; every slice keeps >= 4 K-blocks
+  const int tail = (total_tiles < cap) ? total_tiles : total_tiles % cap;
+  int ks = 1;
+  if (use_tail_split() && tail > 0) {
+    ks = cap / tail;
+    if (ks > 8) ks = 8;
+    while (ks > 1 && kp.kblocks / ks < 4) --ks;
+    while (ks > 1 && (ks - 1) * cdiv(kp.kblocks, ks) >= kp.kblocks) --ks;
+  }
+  const int launch_grid = (ks > 1 && total_tiles < cap) ? tail * ks : grid;  // all-tail layers: one CTA per slice
+  conv_igemm_persistent_kernel<BN, BK, ST, S3, RES, KRES><<<launch_grid, 192, S::TOTAL, st>>>(kp, total_tiles, n_tiles, ks,
+                                                                                                ns->tail_ws);
   DIM_LAUNCH_CHECK();
+  if (ks > 1) {
+    const int base_tile = (total_tiles / launch_grid) * launch_grid;
+    const size_t n = (size_t)tail * 128 * (BN / 4);
+    conv_tail_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(kp, ns->tail_ws, base_tile, tail, ks, n_tiles, BN,
+                                                                           S3 ? 1 : 0);
+    DIM_LAUNCH_CHECK();
+  }
   return 0;
 }
 
@@ -617,13 +646,13 @@ int net_forward(dim_ctx *ctx, int B, int precision, const float *zoom_factor, fl
       else
         rc = s3 ? launch_pair<256, 3, true>(kp, pair_tiles, n_tiles, sms, st) : launch_pair<256, 6, false>(kp, pair_tiles, n_tiles, sms, st);
     } else if (g.BLOCK_N <= 128) {
-      rc = s3 ? launch_conv2<128, 64, 3, true, false, 0>(kp, total_tiles, n_tiles, sms, st)
-              : (g.occ == 2 ? launch_conv2<128, 64, 2, false, false, 0>(kp, total_tiles, n_tiles, 2 * sms, st)
-                            : launch_conv2<128, 64, 5, false, false, 0>(kp, total_tiles, n_tiles, sms, st));
+      rc = s3 ? launch_conv2<128, 64, 3, true, false, 0>(ns, kp, total_tiles, n_tiles, sms, st)
+              : (g.occ == 2 ? launch_conv2<128, 64, 2, false, false, 0>(ns, kp, total_tiles, n_tiles, 2 * sms, st)
+                            : launch_conv2<128, 64, 5, false, false, 0>(ns, kp, total_tiles, n_tiles, sms, st));
     }
     else
-      rc = s3 ? launch_conv2<256, 64, 2, true, false, 0>(kp, total_tiles, n_tiles, sms, st)
-              : launch_conv2<256, 64, 4, false, false, 0>(kp, total_tiles, n_tiles, sms, st);
+      rc = s3 ? launch_conv2<256, 64, 2, true, false, 0>(ns, kp, total_tiles, n_tiles, sms, st)
+              : launch_conv2<256, 64, 4, false, false, 0>(ns, kp, total_tiles, n_tiles, sms, st);
     if (rc) return rc;
     if (kp.ksplit > 1) {
       const int npix = B * g.Ho * g.Wo;
