@@ -371,14 +371,14 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="instances per GPU")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--slots", type=int, default=2, help="independent batches in flight per GPU (streams)")
+    ap.add_argument("--slots", type=int, default=4, help="independent batches in flight per GPU (streams)")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = 5 if args.steps is None else args.steps
         args.warmup = 1 if args.warmup is None else args.warmup
         run_reference(args)
     else:
-        args.steps = 100 if args.steps is None else args.steps
+        args.steps = 200 if args.steps is None else args.steps
         args.warmup = 3 if args.warmup is None else args.warmup
         run_b200(args)
 

@@ -144,6 +144,26 @@ DIM_API int32_t dim_transform3d_bwd(dim_ctx *ctx, const float *out_grad, const f
                                     int32_t rot_coord, float *rot_grad, float *trans_grad,
                                     void *stream);
 
+/* Train-time inter-iteration update (lib/pair_matching/batch_updater_py_multi.py:91-328,
+ * batchUpdaterPyMulti.forward): compose the predicted delta onto src_pose, re-render WITHOUT uint8
+ * truncation (float32 image - float32 means, l.184,234), recompute the labels rot (quaternion of
+ * calc_RT_delta(..., "QUAT")), trans, the reprojection flow against depth_gt_observed and its weights
+ * (valid tiled to 2 channels).  mask_observed / image_observed / tgt_pose stay fixed (not touched).
+ *   in : cls_idx i32[B], src_pose/tgt_pose f32[B,3,4], rot_est f32[B,4], trans_est f32[B,3],
+ *        depth_gt_observed f32[B,1,H,W] (may be NULL when flow == NULL); K9 / T_means / T_stds /
+ *        pixel_means_rgb host f64
+ *   out: image_rendered f32[B,3,H,W], depth_rendered/mask_rendered f32[B,1,H,W], src_pose_new f32[B,3,4],
+ *        rot_label f32[B,4], trans_label f32[B,3], flow f32[B,2,H,W], flow_weights f32[B,2,H,W]
+ *        (flow, flow_weights may be NULL together). */
+DIM_API int32_t dim_train_update(dim_ctx *ctx, const int32_t *cls_idx, const float *src_pose,
+                                 const float *rot_est, const float *trans_est, const float *tgt_pose,
+                                 const float *depth_gt_observed, int32_t B, const double *K9_host,
+                                 float znear, float zfar, const double *pixel_means_rgb_host,
+                                 const double *T_means_host, const double *T_stds_host,
+                                 int32_t rot_coord, float *image_rendered, float *depth_rendered,
+                                 float *mask_rendered, float *src_pose_new, float *rot_label,
+                                 float *trans_label, float *flow, float *flow_weights, void *stream);
+
 /* FlowNetS weights (deepim/symbols/deepIM_flownet.py:63-116,716-717; MXNet layouts: Convolution
  * (Cout,Cin,kh,kw), FullyConnected (out,in)).  Host float32 pointers, 14 (weight,bias) pairs in the
  * order flow_conv1, conv2, conv3, conv3_1, conv4, conv4_1, conv5, conv5_1, conv6, conv6_1, fc6,

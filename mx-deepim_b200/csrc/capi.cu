@@ -33,7 +33,9 @@ int transform_u8_obs4_launch(dim_ctx *, const uint8_t *, int B, const double *, 
 int pack_nhwc8_launch(dim_ctx *, const float *, const float *, const float *, const float *, int B, int Hs, int Ws,
                       int pad, __nv_bfloat16 *, __nv_bfloat16 *, cudaStream_t);
 int flow_launch(dim_ctx *, const float *, const float *, const float *, const float *, int B, float *, float *,
-                cudaStream_t);
+                float *, cudaStream_t);
+int train_pose_launch(const float *, const float *, const float *, const float *, int B, const double *,
+                      const double *, int, const double *, float *, float *, float *, float *, cudaStream_t);
 int se3_compose_launch(const double *, const float *, int B, const double *, const double *, int, double *, float *,
                        cudaStream_t);
 int f64_to_f32_launch(const double *, float *, int n, cudaStream_t);
@@ -242,7 +244,7 @@ DIM_API int32_t dim_se3_compose(dim_ctx *ctx, const double *pose_src, const floa
 DIM_API int32_t dim_flow_fwd(dim_ctx *ctx, const float *ds, const float *dt, const float *KT, const float *Kinv,
                              int32_t B, float *flow, float *valid, void *stream) {
   DIM_REQUIRE(ctx && ds && dt && KT && Kinv && flow && valid, "dim_flow_fwd: NULL argument");
-  return flow_launch(ctx, ds, dt, KT, Kinv, B, flow, valid, (cudaStream_t)stream);
+  return flow_launch(ctx, ds, dt, KT, Kinv, B, flow, valid, nullptr, (cudaStream_t)stream);
 }
 
 DIM_API int32_t dim_transform3d_fwd(dim_ctx *ctx, const float *pc, const float *rot, const float *tr,
@@ -372,6 +374,50 @@ DIM_API int32_t dim_refine_host(dim_ctx *ctx, const uint8_t *img_u8, const int32
                                      se3_out, stream))
     return rc;
   DIM_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+
+DIM_API int32_t dim_train_update(dim_ctx *ctx, const int32_t *cls_idx, const float *src_pose, const float *rot_est,
+                                 const float *trans_est, const float *tgt_pose, const float *depth_gt_observed,
+                                 int32_t B, const double *K9, float zn, float zf, const double *means,
+                                 const double *Tm, const double *Ts, int32_t rot_coord, float *image_rendered,
+                                 float *depth_rendered, float *mask_rendered, float *src_pose_new, float *rot_label,
+                                 float *trans_label, float *flow, float *flow_weights, void *stream) {
+  DIM_REQUIRE(ctx && cls_idx && src_pose && rot_est && trans_est && tgt_pose && K9 && means && Tm && Ts,
+              "dim_train_update: NULL argument");
+  DIM_REQUIRE(image_rendered && depth_rendered && mask_rendered && src_pose_new && rot_label && trans_label,
+              "dim_train_update: NULL output");
+  DIM_REQUIRE(B >= 1 && B <= ctx->max_batch, "dim_train_update: batch exceeds max_batch");
+  DIM_REQUIRE(rot_coord >= 0 && rot_coord <= 2, "dim_train_update: unknown rot_coord");
+  cudaStream_t st = (cudaStream_t)stream;
+  float *KT = ctx->pose_cur_f32;  // [B,12] scratch
+  if (int rc = train_pose_launch(src_pose, rot_est, trans_est, tgt_pose, B, Tm, Ts, rot_coord, K9, src_pose_new,
+                                 rot_label, trans_label, KT, st))
+    return rc;
+  const float K9f[9] = {(float)K9[0], (float)K9[1], (float)K9[2], (float)K9[3], (float)K9[4],
+                        (float)K9[5], (float)K9[6], (float)K9[7], (float)K9[8]};
+  // no uint8 truncation on the train path (batch_updater_py_multi.py:184,234)
+  if (int rc = render_launch(ctx, cls_idx, src_pose_new, B, K9f, zn, zf, means, 0, image_rendered, depth_rendered,
+                             mask_rendered, nullptr, nullptr, nullptr, st))
+    return rc;
+  if (flow && flow_weights) {
+    DIM_REQUIRE(depth_gt_observed != nullptr, "dim_train_update: flow labels need depth_gt_observed");
+    // Kinv = inverse of K (np.linalg.inv, l.60) in float64, cast to float32 (l.292)
+    const double a = K9[0], b_ = K9[1], c = K9[2], d = K9[3], e = K9[4], f = K9[5], g = K9[6], h = K9[7], i = K9[8];
+    const double det = a * (e * i - f * h) - b_ * (d * i - f * g) + c * (d * h - e * g);
+    const float Kinv[9] = {(float)((e * i - f * h) / det), (float)((c * h - b_ * i) / det), (float)((b_ * f - c * e) / det),
+                           (float)((f * g - d * i) / det), (float)((a * i - c * g) / det), (float)((c * d - a * f) / det),
+                           (float)((d * h - e * g) / det), (float)((b_ * g - a * h) / det), (float)((a * e - b_ * d) / det)};
+    const size_t P = (size_t)ctx->H * ctx->W;
+    // flow_weights = tile(valid, [1,2,1,1]) (l.296): the kernel writes both copies
+    if (int rc = flow_launch(ctx, depth_rendered, depth_gt_observed, KT, Kinv, B, flow, ctx->mask_rendered,
+                             nullptr, st))
+      return rc;
+    // interleave valid into the two weight planes per instance
+    for (int pl = 0; pl < 2; ++pl)
+      DIM_CHECK(cudaMemcpy2DAsync(flow_weights + pl * P, 2 * P * sizeof(float), ctx->mask_rendered, P * sizeof(float),
+                                  P * sizeof(float), B, cudaMemcpyDeviceToDevice, st));
+  }
   return 0;
 }
 

@@ -17,7 +17,8 @@ __global__ void __launch_bounds__(256) flow_kernel(const float *__restrict__ dep
                                                    const float *__restrict__ depth_tgt,
                                                    const float *__restrict__ KT, float i0, float i1, float i2,
                                                    float i3, float i4, float i5, int H, int W,
-                                                   float *__restrict__ flow, float *__restrict__ valid) {
+                                                   float *__restrict__ flow, float *__restrict__ valid,
+                                                   float *__restrict__ valid2 /*nullable: second copy*/) {
   const int b = blockIdx.y;
   const int q4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (q4 >= H * W) return;
@@ -56,14 +57,15 @@ __global__ void __launch_bounds__(256) flow_kernel(const float *__restrict__ dep
   *reinterpret_cast<float4 *>(flow + ((size_t)b * 2 + 0) * P + q4) = make_float4(fh[0], fh[1], fh[2], fh[3]);
   *reinterpret_cast<float4 *>(flow + ((size_t)b * 2 + 1) * P + q4) = make_float4(fw[0], fw[1], fw[2], fw[3]);
   *reinterpret_cast<float4 *>(valid + (size_t)b * P + q4) = make_float4(ok[0], ok[1], ok[2], ok[3]);
+  if (valid2) *reinterpret_cast<float4 *>(valid2 + (size_t)b * P + q4) = make_float4(ok[0], ok[1], ok[2], ok[3]);
 }
 
 int flow_launch(dim_ctx *ctx, const float *depth_src, const float *depth_tgt, const float *KT, const float *Kinv,
-                int B, float *flow, float *valid, cudaStream_t st) {
+                int B, float *flow, float *valid, float *valid2, cudaStream_t st) {
   DIM_REQUIRE((ctx->W & 3) == 0, "width must be a multiple of 4");
   flow_kernel<<<dim3(cdiv(ctx->H * ctx->W / 4, 256), B), 256, 0, st>>>(depth_src, depth_tgt, KT, Kinv[0], Kinv[1],
                                                                         Kinv[2], Kinv[3], Kinv[4], Kinv[5], ctx->H,
-                                                                        ctx->W, flow, valid);
+                                                                        ctx->W, flow, valid, valid2);
   DIM_LAUNCH_CHECK();
   return 0;
 }
@@ -133,6 +135,132 @@ int se3_compose_launch(const double *pose_src, const float *se3, int B, const do
                        int rot_coord, double *pose_out, float *pose_out_f32, cudaStream_t st) {
   se3_compose_kernel<<<cdiv(B, 64), 64, 0, st>>>(pose_src, se3, B, Tm[0], Tm[1], Tm[2], Ts[0], Ts[1], Ts[2],
                                                   rot_coord, pose_out, pose_out_f32);
+  DIM_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------- train-time pose / label update
+// lib/pair_matching/batch_updater_py_multi.py:174-259 per instance: refined pose = RT_transform(src,
+// rot_est, trans_est); new labels (rot as quaternion via mat2quat, trans) = calc_RT_delta(refined, tgt,
+// "QUAT"); KT = K . calc_se3(refined, tgt) for the reprojection-flow kernel.
+// mat2quat (RT_transform.py:432-509) takes the eigenvector of the largest eigenvalue of a symmetric 4x4
+// matrix (numpy eigh); here a cyclic Jacobi iteration in float64.
+__device__ void jacobi_eig4(double A[4][4], double V[4][4]) {
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 24; ++sweep) {
+    double off = 0.0;
+    for (int p_ = 0; p_ < 3; ++p_)
+      for (int q = p_ + 1; q < 4; ++q) off += A[p_][q] * A[p_][q];
+    if (off < 1e-32) break;
+    for (int p_ = 0; p_ < 3; ++p_)
+      for (int q = p_ + 1; q < 4; ++q) {
+        if (fabs(A[p_][q]) < 1e-300) continue;
+        const double theta = (A[q][q] - A[p_][p_]) / (2.0 * A[p_][q]);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+        for (int k = 0; k < 4; ++k) {
+          const double akp = A[k][p_], akq = A[k][q];
+          A[k][p_] = c * akp - sn * akq;
+          A[k][q] = sn * akp + c * akq;
+        }
+        for (int k = 0; k < 4; ++k) {
+          const double apk = A[p_][k], aqk = A[q][k];
+          A[p_][k] = c * apk - sn * aqk;
+          A[q][k] = sn * apk + c * aqk;
+        }
+        for (int k = 0; k < 4; ++k) {
+          const double vkp = V[k][p_], vkq = V[k][q];
+          V[k][p_] = c * vkp - sn * vkq;
+          V[k][q] = sn * vkp + c * vkq;
+        }
+      }
+  }
+}
+
+__device__ void mat2quat_f64(const double *M, double *q) {
+  const double Qxx = M[0], Qyx = M[1], Qzx = M[2], Qxy = M[3], Qyy = M[4], Qzy = M[5], Qxz = M[6], Qyz = M[7],
+               Qzz = M[8];
+  double A[4][4] = {{Qxx - Qyy - Qzz, Qyx + Qxy, Qzx + Qxz, Qyz - Qzy},
+                    {Qyx + Qxy, Qyy - Qxx - Qzz, Qzy + Qyz, Qzx - Qxz},
+                    {Qzx + Qxz, Qzy + Qyz, Qzz - Qxx - Qyy, Qxy - Qyx},
+                    {Qyz - Qzy, Qzx - Qxz, Qxy - Qyx, Qxx + Qyy + Qzz}};
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) A[i][j] /= 3.0;
+  double V[4][4];
+  jacobi_eig4(A, V);
+  int best = 0;
+  for (int k = 1; k < 4; ++k)
+    if (A[k][k] > A[best][best]) best = k;
+  q[0] = V[3][best]; q[1] = V[0][best]; q[2] = V[1][best]; q[3] = V[2][best];
+  if (q[0] < 0)
+    for (int k = 0; k < 4; ++k) q[k] = -q[k];
+}
+
+__global__ void train_pose_kernel(const float *src_pose, const float *rot_est, const float *trans_est,
+                                  const float *tgt_pose, int B, double m0, double m1, double m2, double s0, double s1,
+                                  double s2, int rot_coord, double k0, double k1, double k2, double k3, double k4,
+                                  double k5, double k6, double k7, double k8, float *pose_new_f32, float *rot_label,
+                                  float *trans_label, float *KT) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double ps[12], pt[12], po[12];
+  for (int k = 0; k < 12; ++k) { ps[k] = (double)src_pose[12 * b + k]; pt[k] = (double)tgt_pose[12 * b + k]; }
+  const double quat[4] = {(double)rot_est[4 * b], (double)rot_est[4 * b + 1], (double)rot_est[4 * b + 2],
+                          (double)rot_est[4 * b + 3]};
+  const double td[3] = {(double)trans_est[3 * b], (double)trans_est[3 * b + 1], (double)trans_est[3 * b + 2]};
+  const double Tm[3] = {m0, m1, m2}, Ts[3] = {s0, s1, s2};
+  rt_transform_f64(ps, quat, td, Tm, Ts, rot_coord, po);
+  for (int k = 0; k < 12; ++k) pose_new_f32[12 * b + k] = (float)po[k];
+  // calc_RT_delta(refined, tgt, QUAT)  (RT_transform.py:16-44)
+  double Rd[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double acc = 0.0;
+      for (int k = 0; k < 3; ++k) acc += (rot_coord == 0) ? po[k * 4 + i] * pt[k * 4 + j] : pt[i * 4 + k] * po[j * 4 + k];
+      Rd[i * 3 + j] = acc;
+    }
+  double q[4];
+  mat2quat_f64(Rd, q);
+  for (int k = 0; k < 4; ++k) rot_label[4 * b + k] = (float)q[k];
+  double d[3];
+  if (rot_coord == 2) {
+    d[0] = (pt[3] - po[3]) / po[11];
+    d[1] = (pt[7] - po[7]) / po[11];
+  } else {
+    // tgt_pose is a float32 array in the train loop: T_tgt[0]/T_tgt[2] is a float32 division
+    const float *tg32 = tgt_pose + 12 * b;
+    d[0] = (double)(tg32[3] / tg32[11]) - po[3] / po[11];
+    d[1] = (double)(tg32[7] / tg32[11]) - po[7] / po[11];
+  }
+  d[2] = log(po[11] / pt[11]);
+  for (int k = 0; k < 3; ++k) trans_label[3 * b + k] = (float)((d[k] - Tm[k]) / Ts[k]);
+  // calc_se3 (RT_transform.py:176-187 over lib/utils/projection.py: float32 storage) then K . se3
+  float Ri[9], Ti[3];
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) Ri[i * 3 + j] = (float)po[j * 4 + i];
+    Ti[i] = (float)(-1.0 * ((po[0 * 4 + i] * po[3] + po[1 * 4 + i] * po[7]) + po[2 * 4 + i] * po[11]));
+  }
+  const float *tg = tgt_pose + 12 * b;
+  float se3[12];
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j)
+      se3[i * 4 + j] = (tg[i * 4 + 0] * Ri[0 * 3 + j] + tg[i * 4 + 1] * Ri[1 * 3 + j]) + tg[i * 4 + 2] * Ri[2 * 3 + j];
+    se3[i * 4 + 3] = ((tg[i * 4 + 0] * Ti[0] + tg[i * 4 + 1] * Ti[1]) + tg[i * 4 + 2] * Ti[2]) + tg[i * 4 + 3];
+  }
+  const double Kd[9] = {k0, k1, k2, k3, k4, k5, k6, k7, k8};
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 4; ++j)
+      KT[12 * b + i * 4 + j] = (float)((Kd[i * 3 + 0] * (double)se3[0 * 4 + j] + Kd[i * 3 + 1] * (double)se3[1 * 4 + j]) +
+                                        Kd[i * 3 + 2] * (double)se3[2 * 4 + j]);
+}
+
+int train_pose_launch(const float *src_pose, const float *rot_est, const float *trans_est, const float *tgt_pose, int B,
+                      const double *Tm, const double *Ts, int rot_coord, const double *K9, float *pose_new_f32,
+                      float *rot_label, float *trans_label, float *KT, cudaStream_t st) {
+  train_pose_kernel<<<cdiv(B, 32), 32, 0, st>>>(src_pose, rot_est, trans_est, tgt_pose, B, Tm[0], Tm[1], Tm[2], Ts[0],
+                                                 Ts[1], Ts[2], rot_coord, K9[0], K9[1], K9[2], K9[3], K9[4], K9[5], K9[6],
+                                                 K9[7], K9[8], pose_new_f32, rot_label, trans_label, KT);
   DIM_LAUNCH_CHECK();
   return 0;
 }

@@ -283,9 +283,15 @@ __global__ void __launch_bounds__(256) raster_resolve_kernel(RasterParams p) {
       float c0 = colour_of(tp[0], p.trunc_u8), c1 = colour_of(tp[1], p.trunc_u8), c2 = colour_of(tp[2], p.trunc_u8);
       raw[k][0] = c0; raw[k][1] = c1; raw[k][2] = c2;
       // image.transform works in float64 and nd.array casts to float32 (lib/utils/image.py:583-594)
-      r[k] = (float)((double)c0 - p.mean[0]);
-      g[k] = (float)((double)c1 - p.mean[1]);
-      bl[k] = (float)((double)c2 - p.mean[2]);
+      if (p.trunc_u8) {
+        r[k] = (float)((double)c0 - p.mean[0]);
+        g[k] = (float)((double)c1 - p.mean[1]);
+        bl[k] = (float)((double)c2 - p.mean[2]);
+      } else {  // train path (batch_updater_py_multi.py:234-235): float32 image -= float32 pixel_means
+        r[k] = c0 - (float)p.mean[0];
+        g[k] = c1 - (float)p.mean[1];
+        bl[k] = c2 - (float)p.mean[2];
+      }
       d[k] = z;
       if (z > 0.2f) {  // mask = depth > 0.2 (deepim/core/tester.py:440)
         mk[k] = 1.f;
@@ -359,7 +365,7 @@ int render_launch(dim_ctx *ctx, const int *cls, const float *pose, int B, const 
   p.fx = K9[0]; p.fy = K9[4]; p.cx = K9[2]; p.cy = K9[5]; p.zn = zn; p.zf = zf;
   for (int c = 0; c < 3; ++c) {
     p.mean[c] = means ? means[c] : 0.0;
-    p.bg[c] = (float)(0.0 - p.mean[c]);
+    p.bg[c] = trunc_u8 ? (float)(0.0 - p.mean[c]) : 0.0f - (float)p.mean[c];
   }
   p.trunc_u8 = trunc_u8;
   p.out_image = out_image; p.out_depth = out_depth; p.out_mask = out_mask; p.out_bgr = out_bgr;

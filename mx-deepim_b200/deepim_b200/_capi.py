@@ -39,6 +39,8 @@ SIGNATURES = {
     "dim_flow_fwd": (i32, [vp, vp, vp, vp, pf32, i32, vp, vp, vp]),
     "dim_transform3d_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, pf32, pf32, i32, vp, vp]),
     "dim_transform3d_bwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, pf32, pf32, i32, vp, vp, vp]),
+    "dim_train_update": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, pf64, f32, f32, pf64, pf64, pf64, i32, vp, vp, vp, vp, vp,
+                               vp, vp, vp, vp]),
     "dim_net_load": (i32, [vp, C.POINTER(vp), C.POINTER(vp)]),
     "dim_net_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, vp, vp, vp]),
     "dim_refine": (i32, [vp, vp, vp, vp, i32, i32, pf32, f32, f32, pf64, i32, vp, vp, vp, vp, vp, vp]),

@@ -221,6 +221,34 @@ class Context:
                                       capi.ROT_COORD[rot_coord.lower()], _p(rg), _p(tg), _stream()))
         return rg, tg
 
+    def train_update(self, cls_idx, src_pose, rot_est, trans_est, tgt_pose, depth_gt_observed, K,
+                     pixel_means_rgb=(103.939, 116.779, 123.68), T_means=(0, 0, 0), T_stds=(1, 1, 1),
+                     rot_coord="camera", znear=0.25, zfar=6.0, want_flow=True):
+        """batchUpdaterPyMulti.forward on the device (lib/pair_matching/batch_updater_py_multi.py:91-328)."""
+        B = src_pose.shape[0]
+        for n, t, shp in (("src_pose", src_pose, (B, 3, 4)), ("tgt_pose", tgt_pose, (B, 3, 4)), ("rot_est", rot_est, (B, 4)),
+                          ("trans_est", trans_est, (B, 3))):
+            _chk(t, torch.float32, shp, n)
+        _chk(cls_idx, torch.int32, (B,), "cls_idx")
+        out = {
+            "image_rendered": self._new((B, 3, self.H, self.W)), "depth_rendered": self._new((B, 1, self.H, self.W)),
+            "mask_rendered": self._new((B, 1, self.H, self.W)), "src_pose": self._new((B, 3, 4)),
+            "rot": self._new((B, 4)), "trans": self._new((B, 3)),
+            "flow": self._new((B, 2, self.H, self.W)) if want_flow else None,
+            "flow_weights": self._new((B, 2, self.H, self.W)) if want_flow else None,
+        }
+        if want_flow:
+            _chk(depth_gt_observed, torch.float32, (B, 1, self.H, self.W), "depth_gt_observed")
+        check(lib.dim_train_update(self._h, _p(cls_idx), _p(src_pose), _p(rot_est), _p(trans_est), _p(tgt_pose),
+                                   _p(depth_gt_observed) if want_flow else None, B,
+                                   farr(np.asarray(K, np.float64).reshape(9), 9, C.c_double), znear, zfar,
+                                   farr(pixel_means_rgb, 3, C.c_double), farr(T_means, 3, C.c_double),
+                                   farr(T_stds, 3, C.c_double), capi.ROT_COORD[rot_coord.lower()],
+                                   _p(out["image_rendered"]), _p(out["depth_rendered"]), _p(out["mask_rendered"]),
+                                   _p(out["src_pose"]), _p(out["rot"]), _p(out["trans"]), _p(out["flow"]),
+                                   _p(out["flow_weights"]), _stream()))
+        return out
+
     def transform_image_u8(self, bgr_u8, pixel_means_rgb):
         B = bgr_u8.shape[0]
         _chk(bgr_u8, torch.uint8, (B, self.H, self.W, 3), "bgr_u8")

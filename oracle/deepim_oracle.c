@@ -245,10 +245,17 @@ ORC_API void orc_render(const float *verts, const float *uvs, int32_t V, const i
       if (out_depth) out_depth[p] = depth;
       if (out_image) {
         size_t P = (size_t)H * W;
-        /* image.transform works in float64 (np.zeros tensor) and nd.array casts to float32 */
-        out_image[p] = (float)((double)rgb[0] - means_rgb[0]);
-        out_image[P + p] = (float)((double)rgb[1] - means_rgb[1]);
-        out_image[2 * P + p] = (float)((double)rgb[2] - means_rgb[2]);
+        if (trunc_u8) {
+          /* test path: image.transform works in float64 (np.zeros tensor), nd.array casts to float32 */
+          out_image[p] = (float)((double)rgb[0] - means_rgb[0]);
+          out_image[P + p] = (float)((double)rgb[1] - means_rgb[1]);
+          out_image[2 * P + p] = (float)((double)rgb[2] - means_rgb[2]);
+        } else {
+          /* train path (batch_updater_py_multi.py:234-235): float32 image -= float32 pixel_means */
+          out_image[p] = rgb[0] - (float)means_rgb[0];
+          out_image[P + p] = rgb[1] - (float)means_rgb[1];
+          out_image[2 * P + p] = rgb[2] - (float)means_rgb[2];
+        }
       }
       if (out_mask) out_mask[p] = m;
     }

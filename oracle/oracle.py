@@ -399,3 +399,71 @@ def transform3d_backward(out_grad, point_cloud, rotation, translation, pose_src,
         share = Ns ** 3 * (w * wd + x * xd + y * yd + z * zd)
         rg[b] = [Ns * wd - w * share, Ns * xd - x * share, Ns * yd - y * share, Ns * zd - z * share]
     return rg, tg
+
+
+# ----------------------------------------------------------------------- train-time batch update
+def mat2quat(M):
+    """RT_transform.py:432-509 (Bar-Itzhack): eigenvector of the largest eigenvalue of a symmetric 4x4."""
+    Qxx, Qyx, Qzx, Qxy, Qyy, Qzy, Qxz, Qyz, Qzz = np.asarray(M, np.float64).flat
+    Kq = np.array([[Qxx - Qyy - Qzz, 0, 0, 0], [Qyx + Qxy, Qyy - Qxx - Qzz, 0, 0],
+                   [Qzx + Qxz, Qzy + Qyz, Qzz - Qxx - Qyy, 0],
+                   [Qyz - Qzy, Qzx - Qxz, Qxy - Qyx, Qxx + Qyy + Qzz]]) / 3.0
+    vals, vecs = np.linalg.eigh(Kq)
+    q = vecs[[3, 0, 1, 2], np.argmax(vals)]
+    if q[0] < 0:
+        q = -q
+    return q
+
+
+def rt_delta_f32tgt(pose_src, pose_tgt32, T_means, T_stds, rot_coord):
+    """calc_RT_delta as the train loop calls it: pose_src float64 (refined pose), pose_tgt a float32 array
+    (it comes out of an NDArray), so T_tgt[0]/T_tgt[2] is a float32 division (RT_transform.py:120-121)."""
+    tgt32 = np.asarray(pose_tgt32, np.float32)
+    Rd, Td = rt_delta(pose_src, tgt32.astype(np.float64), T_means, T_stds, rot_coord)
+    if rot_coord.lower() != "camera_new":
+        src = np.asarray(pose_src, np.float64)
+        d0 = np.float64(tgt32[0, 3] / tgt32[2, 3]) - src[0, 3] / src[2, 3]
+        d1 = np.float64(tgt32[1, 3] / tgt32[2, 3]) - src[1, 3] / src[2, 3]
+        Td = Td.copy()
+        Td[0] = (d0 - T_means[0]) / T_stds[0]
+        Td[1] = (d1 - T_means[1]) / T_stds[1]
+    return Rd, Td
+
+
+def calc_se3_f32(pose_src, pose_tgt):
+    """calc_se3 (RT_transform.py:176-187) over lib/utils/projection.py se3_inverse / se3_mul, which store
+    their results in float32 arrays.  pose_src float64 (refined pose), pose_tgt float32."""
+    R, T = np.asarray(pose_src)[:, :3], np.asarray(pose_src)[:, 3].reshape(3, 1)
+    inv = np.zeros((3, 4), np.float32)
+    inv[:, :3] = R.T
+    inv[:, 3] = (-1 * (R.T @ T)).reshape(3)
+    R1, T1 = np.asarray(pose_tgt, np.float32)[:, :3], np.asarray(pose_tgt, np.float32)[:, 3].reshape(3, 1)
+    out = np.zeros((3, 4), np.float32)
+    out[:, :3] = R1 @ inv[:, :3]
+    out[:, 3] = (R1 @ inv[:, 3].reshape(3, 1) + T1).reshape(3)
+    return out
+
+
+def train_update(meshes, cls_idx, src_pose, rot_est, trans_est, tgt_pose, depth_gt_observed, K, means_rgb,
+                 T_means=(0, 0, 0), T_stds=(1, 1, 1), rot_coord="camera", zn=0.25, zf=6.0):
+    """batchUpdaterPyMulti.forward (lib/pair_matching/batch_updater_py_multi.py:91-328) for one context.
+    src_pose / tgt_pose / rot_est / trans_est are float32 (they come out of NDArrays)."""
+    B = len(cls_idx)
+    H, W = depth_gt_observed.shape[-2:]
+    out = {"image_rendered": np.zeros((B, 3, H, W), np.float32), "depth_rendered": np.zeros((B, 1, H, W), np.float32),
+           "mask_rendered": np.zeros((B, 1, H, W), np.float32), "src_pose": np.zeros((B, 3, 4), np.float32),
+           "rot": np.zeros((B, 4), np.float32), "trans": np.zeros((B, 3), np.float32)}
+    KT = np.zeros((B, 3, 4), np.float32)
+    for b in range(B):
+        refined = rt_transform(src_pose[b].astype(np.float64), rot_est[b], trans_est[b], T_means, T_stds, rot_coord)
+        r = render(meshes[int(cls_idx[b])], refined, K, zn, zf, H, W, means_rgb, trunc_u8=False,
+                   want=("image", "depth", "mask"))
+        out["image_rendered"][b], out["depth_rendered"][b, 0], out["mask_rendered"][b, 0] = r["image"], r["depth"], r["mask"]
+        Rd, Td = rt_delta_f32tgt(refined, tgt_pose[b], T_means, T_stds, rot_coord)
+        out["rot"][b], out["trans"][b] = mat2quat(Rd), Td
+        out["src_pose"][b] = refined
+        KT[b] = (np.asarray(K, np.float64) @ calc_se3_f32(refined, tgt_pose[b]).astype(np.float64)).astype(np.float32)
+    Kinv = np.linalg.inv(np.asarray(K, np.float64)).astype(np.float32)
+    fl, va = flow(out["depth_rendered"], depth_gt_observed, KT, Kinv)
+    out["flow"], out["flow_weights"], out["KT"] = fl, np.tile(va, [1, 2, 1, 1]), KT
+    return out

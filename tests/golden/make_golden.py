@@ -76,6 +76,17 @@ def main():
         out["pose_out_norm_" + coord] = po_norm
         out["R_delta_" + coord] = Rd
         out["T_delta_" + coord] = Td
+    # train-time labels: calc_RT_delta(..., "QUAT") (mat2quat, eigh) and K . calc_se3 (batch_updater_py_multi.py:239-259)
+    Kmat = np.array([[572.4114, 0, 325.2611], [0, 573.57043, 242.04899], [0, 0, 1.0]])
+    pose_tgt32 = out["pose_out_CAMERA"].astype(np.float32)
+    quat_lbl, trans_lbl, KT = np.zeros((N, 4)), np.zeros((N, 3)), np.zeros((N, 3, 4))
+    for k in range(N):
+        q, t = RT.calc_RT_delta(pose_src[k], pose_tgt32[k], np.zeros(3), np.ones(3), "CAMERA", "QUAT")
+        quat_lbl[k], trans_lbl[k] = q, t
+        rm, tt = RT.calc_se3(pose_src[k], pose_tgt32[k])
+        se3_m = np.zeros([3, 4]); se3_m[:, :3] = rm; se3_m[:, 3] = tt
+        KT[k] = np.dot(Kmat, se3_m)
+    out["label_quat"], out["label_trans"], out["label_KT"], out["label_K"] = quat_lbl, trans_lbl, KT, Kmat
     # quat2mat known answers from the docstring examples (RT_transform.py:397-404)
     out["quat2mat_in"] = np.array([[1.0, 0, 0, 0], [0, 1.0, 0, 0]])
     out["quat2mat_out"] = np.stack([RT.quat2mat(q) for q in out["quat2mat_in"]])

@@ -414,3 +414,93 @@ def test_errors_are_loud(ctx):
                    torch.zeros(5, 3, 4, dtype=torch.float64, device=DEV), K, 4)  # batch > max_batch
     with pytest.raises((TypeError, ValueError)):
         ctx.zoom_trans(torch.zeros(2, 4, device=DEV), torch.zeros(2, 3, dtype=torch.float64, device=DEV), True)
+
+
+# ------------------------------------------------------------------- BASELINE.json configs C3 / C5
+def test_config_c3_thirteen_meshes_sharded_batch(weights):
+    """C3: 13 LINEMOD-scale meshes, instances round-robin over classes, batch split into device batches
+    (the 8-GPU sharding itself is covered by tests/test_sharding_gloo.py; instances are independent, so a
+    rank's slice is just such a batch).  Integer bboxes bit-exact, poses within tolerance."""
+    from deepim_b200.refiner import PoseRefiner
+    meshes13 = synth.make_linemod_like_set(13, seed=2)
+    n = 13
+    obs, ini = synth.sample_pose_pairs(n, 61)
+    cls = np.arange(n, dtype=np.int32) % 13
+    u8 = []
+    for b in range(n):
+        r = O.render(meshes13[cls[b]], obs[b], K)
+        u8.append(synth.composite_observed(r["bgr"], r["mask"], b))
+    u8 = np.stack(u8)
+    ref = PoseRefiner(meshes13, weights, K, device=0, max_batch=8, n_iter=2, precision="bf16x3", n_slots=2)
+    poses = ref.refine(u8, cls, ini)                       # 2 device batches (8 + 5), pipelined
+    ref.close()
+    img = np.stack([synth.transform_image(u8[b]) for b in range(n)])
+    oref = O.refine(weights, meshes13, cls, img, ini, K, 2, MEANS32)
+    assert poses.shape == (2, n, 3, 4)
+    assert np.abs(poses - oref["poses"]).max() < 1e-3
+    # first-iteration poses depend only on exact integer/bbox work + the net: tight tolerance
+    assert np.abs(poses[0] - oref["poses"][0]).max() < 1e-4
+
+
+def test_config_c5_50k_vertex_mesh_render_and_refine(weights):
+    """C5 stress mesh (~50k verts / 100k tris, diameter 0.25 m at 0.6 m): rasteriser bit-exact on
+    sub-pixel triangles, one refinement iteration within tolerance."""
+    big = synth.make_blob(158, 316, diameter=0.25, tex_size=512, seed=4, name="stress")
+    assert len(big.verts) > 50000 and len(big.faces) > 99000
+    c5 = Context(0, max_batch=2, max_classes=1, max_verts=len(big.verts), max_faces=len(big.faces))
+    c5.upload_mesh(0, big)
+    c5.load_weights(weights)
+    obs, ini = synth.sample_pose_pairs(2, 71, z_mean=0.6)
+    cls = np.zeros(2, np.int32)
+    out = c5.render(dev(cls), dev(ini.astype(np.float32)), K, pixel_means_rgb=MEANS, want=("image", "depth", "mask"))
+    for b in range(2):
+        r = O.render(big, ini[b], K, means_rgb=MEANS)
+        assert r["mask"].sum() > 20000
+        assert np.array_equal(out["bbox"][b].cpu().numpy(), r["bbox"])
+        assert np.array_equal(out["mask"][b, 0].cpu().numpy(), r["mask"])
+        assert np.array_equal(out["depth"][b, 0].cpu().numpy(), r["depth"])
+        assert np.array_equal(out["image"][b].cpu().numpy(), r["image"])
+    img = observed_images([big], cls, obs)
+    res = c5.refine(dev(img), dev(cls), dev(ini), K, 1, pixel_means_rgb=MEANS, precision=capi.PREC_BF16X3)
+    oref = O.refine(weights, [big], cls, img, ini, K, 1, MEANS32)
+    assert np.array_equal(res["bbox"].cpu().numpy(), oref["bbox"])
+    assert np.abs(res["se3"].cpu().numpy()[..., :4] - oref["se3"][..., :4]).max() < 1e-4
+    assert np.abs(res["se3"].cpu().numpy()[..., 4:] - oref["se3"][..., 4:]).max() < 1e-3
+    c5.close()
+
+
+# ------------------------------------------------------------------------- train-time update (a14)
+def test_train_update_matches_oracle(ctx, meshes, golden_dir):
+    """batchUpdaterPyMulti.forward on the device: refined pose, train-path render (no uint8 truncation,
+    float32 mean subtraction), labels rot (mat2quat) / trans, reprojection flow + tiled weights."""
+    B = 3
+    obs, ini = synth.sample_pose_pairs(B, 81)
+    cls = np.array([1, 0, 1], np.int32)
+    rng = np.random.default_rng(7)
+    rot_est = (np.array([1.0, 0, 0, 0]) + rng.normal(size=(B, 4)) * 0.03).astype(np.float32)
+    trans_est = (rng.normal(size=(B, 3)) * 0.01).astype(np.float32)
+    src32, tgt32 = ini.astype(np.float32), obs.astype(np.float32)
+    depth_gt = np.stack([O.render(meshes[cls[b]], obs[b], K)["depth"] for b in range(B)])[:, None]
+    out = ctx.train_update(dev(cls), dev(src32), dev(rot_est), dev(trans_est), dev(tgt32), dev(depth_gt), K,
+                           pixel_means_rgb=MEANS)
+    ref = O.train_update(meshes, cls, src32, rot_est, trans_est, tgt32, depth_gt, K, MEANS)
+    assert np.abs(out["src_pose"].cpu().numpy() - ref["src_pose"]).max() < 1e-6
+    assert np.abs(out["rot"].cpu().numpy() - ref["rot"]).max() < 1e-6     # Jacobi vs LAPACK eigh, float32 store
+    assert np.abs(out["trans"].cpu().numpy() - ref["trans"]).max() < 1e-6
+    # the refined pose is float64 on both sides and rounds to the same float32 -> renders are bit-exact
+    if np.array_equal(out["src_pose"].cpu().numpy(), ref["src_pose"]):
+        assert np.array_equal(out["mask_rendered"].cpu().numpy(), ref["mask_rendered"])
+        assert np.array_equal(out["depth_rendered"].cpu().numpy(), ref["depth_rendered"])
+        assert np.array_equal(out["image_rendered"].cpu().numpy(), ref["image_rendered"])
+    else:
+        assert (out["mask_rendered"].cpu().numpy() != ref["mask_rendered"]).mean() < 1e-4
+    fw, ofw = out["flow_weights"].cpu().numpy(), ref["flow_weights"]
+    assert np.array_equal(fw[:, 0], fw[:, 1]) and ofw.sum() > 1000
+    assert (fw != ofw).mean() < 2e-4       # KT differs at float32 rounding level -> a few threshold pixels
+    both = (fw[:, :1] == 1) & (ofw[:, :1] == 1)
+    assert np.abs(out["flow"].cpu().numpy() - ref["flow"])[np.repeat(both, 2, 1)].max() < 2e-3
+    # labels are consistent: composing the label delta onto the refined pose gives the target pose
+    for b in range(B):
+        back = O.rt_transform(ref["src_pose"][b].astype(np.float64), out["rot"][b].cpu().numpy(),
+                              out["trans"][b].cpu().numpy(), (0, 0, 0), (1, 1, 1), "camera")
+        assert np.abs(back - tgt32[b]).max() < 1e-5

@@ -78,3 +78,15 @@ def test_image_transform_matches_reference(golden_dir):
     t = np.load(os.path.join(golden_dir, "ref_transform.npz"))
     out = synth.transform_image(t["im"])
     assert np.array_equal(out, t["out"][0])
+
+
+def test_train_labels_match_reference(golden_dir):
+    # calc_RT_delta(..., "QUAT") (mat2quat / eigh) and K . calc_se3 as used by batch_updater_py_multi.py:239-259
+    g = np.load(os.path.join(golden_dir, "ref_se3.npz"))
+    tgt32 = g["pose_out_CAMERA"].astype(np.float32)
+    for k in range(len(g["pose_src"])):
+        Rd, Td = O.rt_delta_f32tgt(g["pose_src"][k], tgt32[k], (0, 0, 0), (1, 1, 1), "camera")
+        np.testing.assert_allclose(O.mat2quat(Rd), g["label_quat"][k], atol=1e-12)
+        np.testing.assert_allclose(Td, g["label_trans"][k], atol=1e-12)
+        KT = g["label_K"] @ O.calc_se3_f32(g["pose_src"][k], tgt32[k]).astype(np.float64)
+        np.testing.assert_allclose(KT, g["label_KT"][k], rtol=0, atol=2e-4)  # float32 se3 storage, BLAS order
