@@ -223,6 +223,40 @@ def make_weights(seed: int = 0):
     return w
 
 
+DECODER_SPECS = [  # name, kind, weight shape (MXNet layouts: conv (Cout,Cin,k,k); deconv (Cin,Cout,k,k)), bias length
+    ("Convolution1", "conv", (2, 1024, 3, 3), 2), ("deconv5", "deconv", (1024, 512, 4, 4), 512),
+    ("upsample_flow6to5", "deconv", (2, 2, 4, 4), 2), ("Convolution2", "conv", (2, 1026, 3, 3), 2),
+    ("deconv4", "deconv", (1026, 256, 4, 4), 256), ("upsample_flow5to4", "deconv", (2, 2, 4, 4), 2),
+    ("Convolution3", "conv", (2, 770, 3, 3), 2), ("mask_conv3", "conv", (1, 770, 3, 3), 1),
+]
+
+
+def bilinear_upsampling_kernel(k: int = 32) -> np.ndarray:
+    """mx.init.Initializer._init_bilinear as called by init_weights (deepIM_flownet.py:806-820)."""
+    f = np.ceil(k / 2.0)
+    c = (2 * f - 1 - f % 2) / (2.0 * f)
+    v = 1 - np.abs(np.arange(k) / f - c)
+    return np.outer(v, v).astype(np.float32)
+
+
+def make_train_weights(seed: int = 0):
+    """make_weights + the train-only decoder / flow / mask heads (deepIM_flownet.py:121-167,176-193,317-338):
+    He-normal decoder convs/deconvs (a k4 s2 deconv sums Cin*4 taps per output), N(0, 0.01) mask_conv3
+    (init_weights l.811-813), frozen bilinear `upsampling` (2 groups) / `mask_upsampling` kernels."""
+    w = make_weights(seed)
+    rng = np.random.default_rng(seed + 1000003)
+    gain = np.sqrt(2.0 / (1.0 + 0.1 ** 2))
+    for name, kind, shp, nb in DECODER_SPECS:
+        fan = shp[1] * shp[2] * shp[3] if kind == "conv" else shp[0] * (shp[2] // 2) * (shp[3] // 2)
+        std = 0.01 if name == "mask_conv3" else (gain if name.startswith("deconv") else 1.0) / np.sqrt(fan)
+        w[name + "_weight"] = rng.standard_normal(shp, dtype=np.float32) * np.float32(std)
+        w[name + "_bias"] = rng.standard_normal((nb,), dtype=np.float32) * np.float32(0.02)
+    bk = bilinear_upsampling_kernel(32)
+    w["upsampling_weight"] = np.ascontiguousarray(np.broadcast_to(bk, (2, 1, 32, 32))).copy()
+    w["mask_upsampling_weight"] = bk.reshape(1, 1, 32, 32).copy()
+    return w
+
+
 def composite_observed(bgr_render: np.ndarray, mask: np.ndarray, seed: int) -> np.ndarray:
     """observed image = render composited over uniform-noise background, uint8 BGR [H,W,3]
     (what cv2.imread hands the reference's loader)."""
