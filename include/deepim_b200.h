@@ -237,6 +237,51 @@ DIM_API int32_t dim_debug_layer_geometry(dim_ctx *ctx, int32_t idx, int32_t *out
 DIM_API int32_t dim_profile_enable(dim_ctx *ctx, int32_t enable);
 DIM_API int32_t dim_profile_read(dim_ctx *ctx, float *ms4, int32_t *iterations);
 
+/* ---------------------------------------------------------------------------------------------
+ * Training step of the refiner network (train graph: deepim/symbols/deepIM_flownet.py:121-365 decoder,
+ * flow / mask / point-matching losses; optimiser: deepim/train.py:296-304 SGD-momentum, one update per inner
+ * iteration as deepim/core/module.py:1131-1137).  Replaces Module.forward_backward + Module.update for this
+ * network; the zoom front of the train symbol (ZoomMask / ZoomImageWithFactor / ZoomFlow, symbol:391-489) is
+ * the dim_zoom_* calls above, the inter-iteration batch update is dim_train_update.
+ *
+ * Parameters live in ONE flat fp32 vector in MXNet layouts: for each of the 22 trainable tensors in the order
+ * returned by dim_train_param_info (flow_conv1 ... conv6_1, fc6, fc7, rot, trans, Convolution1, deconv5,
+ * upsample_flow6to5, Convolution2, deconv4, upsample_flow5to4, Convolution3, mask_conv3) weight then bias,
+ * followed by the frozen bilinear upsampling_weight (2,1,32,32) and mask_upsampling_weight (1,1,32,32):
+ * 57 749 164 floats.  Gradients use the same layout (that is the buffer a data-parallel caller all-reduces
+ * with NCCL between dim_train_forward_backward and dim_train_sgd_update; kvstore replacement,
+ * deepim/core/module.py:616-635). */
+DIM_API int32_t dim_train_create(dim_ctx *ctx, int32_t max_points);
+DIM_API int64_t dim_train_param_count(dim_ctx *ctx);
+DIM_API int32_t dim_train_param_info(int32_t idx, const char **name, int64_t *weight_numel,
+                                     int64_t *bias_numel);
+/* flat_host: host pointer.  Also (re)loads the inference network of this context. */
+DIM_API int32_t dim_train_load_params(dim_ctx *ctx, const float *flat_host, int64_t n, void *stream);
+/* which = 0: parameters, 1: momentum.  Synchronises the stream. */
+DIM_API int32_t dim_train_get_params(dim_ctx *ctx, float *flat_host, int64_t n, int32_t which,
+                                     void *stream);
+/* Device pointers, fp32 NCHW: zoomed images (B,3,H,W), zoomed masks (B,1,H,W), zoom_factor (B,4), zoomed flow
+ * label (B,2,H,W) and weights (B,2,H,W), zoomed GT mask (B,1,H,W), src_pose (B,3,4), point clouds (B,3,N).
+ * Outputs: rot_est_norm (B,4) = L2Normalization(rot), trans_est (B,3) = invZoomTrans, flow_est (B,2,H,W)
+ * (= flow_est_crop * NORMALIZE_FLOW, nullable), mask_prob (B,1,H,W) (nullable), losses4 = [sum flow_loss,
+ * sum point_matching_loss, sum mask BCE, weighted objective], grads (flat, see above; NULL = forward only:
+ * the non-FAST_TEST outputs of the test graph, symbol:624-713). */
+DIM_API int32_t dim_train_forward_backward(
+    dim_ctx *ctx, const float *zoom_image_observed, const float *zoom_image_rendered,
+    const float *zoom_mask_observed, const float *zoom_mask_rendered, const float *zoom_factor,
+    const float *zoom_flow, const float *zoom_flow_weights, const float *zoom_mask_gt_observed,
+    const float *src_pose, const float *point_cloud_model, const float *point_cloud_weights,
+    const float *point_cloud_observed, int32_t B, int32_t N, float *rot_est_norm, float *trans_est,
+    float *flow_est, float *mask_prob, float *losses4, float *grads, void *stream);
+/* mom = momentum*mom - lr*(rescale_grad*grad + wd*w); w += mom  (wd on *_weight only; the two bilinear kernels
+ * are frozen), then refreshes every bf16 operand pack of the context from the new master weights. */
+DIM_API int32_t dim_train_sgd_update(dim_ctx *ctx, const float *grads, float lr, float momentum, float wd,
+                                     float rescale_grad, void *stream);
+/* Test hooks: intermediates of the training step (ids in train.cu) and their geometry
+ * out7 = Hp, Wp, py, px, C, H, W. */
+DIM_API int32_t dim_train_debug_tensor(dim_ctx *ctx, int32_t id, void *host_dst, uint64_t bytes);
+DIM_API int32_t dim_train_debug_geometry(dim_ctx *ctx, int32_t id, int32_t *out7);
+
 /* number of kernel launches issued by this library since the counter was last reset */
 DIM_API int64_t dim_launch_count(int32_t reset);
 

@@ -21,6 +21,7 @@ UNITS = {
     "zoom.cu": ["-fmad=false"],
     "geom.cu": ["-fmad=false"],
     "net.cu": [],
+    "train.cu": [],
     "capi.cu": [],
 }
 

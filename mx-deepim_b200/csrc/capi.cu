@@ -53,6 +53,22 @@ int net_forward(dim_ctx *, int B, int precision, const float *zoom_factor, float
                 cudaStream_t, cudaEvent_t after_conv);
 int net_debug_activation(dim_ctx *, int idx, int lo, void *host_dst, size_t bytes);
 void net_layer_geometry(dim_ctx *, int idx, int *out);
+// train.cu
+struct TrainIO {
+  const float *zio, *zir, *zmo, *zmr, *zoom_factor, *zflow, *zfw, *zmask_gt, *src_pose, *pc_model, *pc_weights, *pc_observed;
+  int B, N;
+  float *rot_est_norm, *trans_est, *flow_est, *mask_prob, *losses, *grads;
+};
+int train_create(dim_ctx *, int max_points);
+void train_destroy(dim_ctx *);
+int train_load_params(dim_ctx *, const float *flat_host, size_t n, cudaStream_t);
+int train_get_params(dim_ctx *, float *flat_host, size_t n, int which, cudaStream_t);
+size_t train_param_count(dim_ctx *);
+int train_param_info(int idx, const char **name, long long *w_numel, long long *b_numel);
+int train_forward_backward(dim_ctx *, const TrainIO &, cudaStream_t);
+int train_sgd_update(dim_ctx *, const float *grads, float lr, float momentum, float wd, float rescale, cudaStream_t);
+int train_debug_tensor(dim_ctx *, int id, void *host, size_t bytes);
+void train_debug_geometry(dim_ctx *, int id, int *out);
 
 template <typename T>
 static int ctx_alloc(dim_ctx *ctx, T **p, size_t n) {
@@ -137,6 +153,7 @@ DIM_API void dim_ctx_destroy(dim_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
+  train_destroy(ctx);
   net_destroy(ctx);
   for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
   for (void *p : ctx->owned) cudaFree(p);
@@ -453,4 +470,52 @@ DIM_API int32_t dim_debug_layer_geometry(dim_ctx *ctx, int32_t idx, int32_t *out
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------ training step
+DIM_API int32_t dim_train_create(dim_ctx *ctx, int32_t max_points) {
+  DIM_REQUIRE(ctx && max_points >= 1, "dim_train_create: bad argument");
+  return train_create(ctx, max_points);
+}
+DIM_API int64_t dim_train_param_count(dim_ctx *ctx) { return ctx ? (int64_t)train_param_count(ctx) : 0; }
+DIM_API int32_t dim_train_param_info(int32_t idx, const char **name, int64_t *w_numel, int64_t *b_numel) {
+  long long w = 0, b = 0;
+  DIM_REQUIRE(name && w_numel && b_numel, "dim_train_param_info: NULL argument");
+  if (train_param_info(idx, name, &w, &b)) return 2;
+  *w_numel = w; *b_numel = b;
+  return 0;
+}
+DIM_API int32_t dim_train_load_params(dim_ctx *ctx, const float *flat_host, int64_t n, void *stream) {
+  DIM_REQUIRE(ctx && flat_host && n > 0, "dim_train_load_params: bad argument");
+  return train_load_params(ctx, flat_host, (size_t)n, (cudaStream_t)stream);
+}
+DIM_API int32_t dim_train_get_params(dim_ctx *ctx, float *flat_host, int64_t n, int32_t which, void *stream) {
+  DIM_REQUIRE(ctx && flat_host && n > 0, "dim_train_get_params: bad argument");
+  return train_get_params(ctx, flat_host, (size_t)n, which, (cudaStream_t)stream);
+}
+DIM_API int32_t dim_train_forward_backward(dim_ctx *ctx, const float *zio, const float *zir, const float *zmo, const float *zmr,
+                                           const float *zoom_factor, const float *zflow, const float *zfw, const float *zmask_gt,
+                                           const float *src_pose, const float *pc_model, const float *pc_weights,
+                                           const float *pc_observed, int32_t B, int32_t N, float *rot_est_norm, float *trans_est,
+                                           float *flow_est, float *mask_prob, float *losses4, float *grads, void *stream) {
+  DIM_REQUIRE(ctx && zio && zir && zmo && zmr && zoom_factor && zflow && zfw && zmask_gt && src_pose && pc_model && pc_weights &&
+                  pc_observed && losses4,
+              "dim_train_forward_backward: NULL argument");
+  TrainIO io{zio, zir, zmo, zmr, zoom_factor, zflow, zfw, zmask_gt, src_pose, pc_model, pc_weights, pc_observed, B, N,
+             rot_est_norm, trans_est, flow_est, mask_prob, losses4, grads};
+  return train_forward_backward(ctx, io, (cudaStream_t)stream);
+}
+DIM_API int32_t dim_train_sgd_update(dim_ctx *ctx, const float *grads, float lr, float momentum, float wd, float rescale_grad,
+                                     void *stream) {
+  DIM_REQUIRE(ctx && grads, "dim_train_sgd_update: NULL argument");
+  return train_sgd_update(ctx, grads, lr, momentum, wd, rescale_grad, (cudaStream_t)stream);
+}
+DIM_API int32_t dim_train_debug_tensor(dim_ctx *ctx, int32_t id, void *host_dst, uint64_t bytes) {
+  DIM_REQUIRE(ctx && host_dst, "dim_train_debug_tensor: NULL argument");
+  return train_debug_tensor(ctx, id, host_dst, (size_t)bytes);
+}
+DIM_API int32_t dim_train_debug_geometry(dim_ctx *ctx, int32_t id, int32_t *out7) {
+  DIM_REQUIRE(ctx && out7, "dim_train_debug_geometry: NULL argument");
+  train_debug_geometry(ctx, id, out7);
+  return 0;
+}
 }  // extern "C"

@@ -42,6 +42,16 @@ struct ConvKParams {
   const float *bias;
   __nv_bfloat16 *out_hi, *out_lo;
   float *partial;  // [ksplit][Bn*Ho*Wo][Cout] when ksplit > 1
+  // ---- generic epilogue (EPI = 1: decoder deconvolutions as parity sub-convolutions, data gradients)
+  //   TMA coordinates get (in_off_c, in_off_r) added; virtual output pixel (oh, ow) of image n lands at
+  //   interior pixel (oh*out_sy + out_oy, ow*out_sx + out_ox) of the output buffer when that is inside
+  //   [0,out_H) x [0,out_W);  value = (acc + bias + addend) then LeakyReLU (mask.p == nullptr, slope 1 = none)
+  //   or * (mask > 0 ? 1 : slope) for channels < mask_climit (LeakyReLU backward through the stored
+  //   activation).  All side buffers are bf16 NHWC with their own border / channel stride.
+  int in_off_r, in_off_c;
+  int out_sy, out_sx, out_oy, out_ox, out_H, out_W, out_cs, out_coff;
+  struct PixBuf { const __nv_bfloat16 *p; int Hp, Wp, py, px, cs, coff; } addend, mask;
+  int mask_climit;
 };
 
 namespace ptx {
@@ -186,6 +196,51 @@ __device__ __forceinline__ void epilogue_store64(const uint32_t *r, const float 
   }
 }
 
+// generic epilogue of the training-step kernels (see ConvKParams): 64 channels of one output pixel per thread
+__device__ __forceinline__ void epilogue_generic64(const uint32_t *r, const ConvKParams &p, const float *bias_s, uint8_t *stage,
+                                                   long long my_off, long long add_off, long long mask_off, bool my_valid,
+                                                   bool use_mask, bool chan_ok, int lane) {
+  __align__(16) __nv_bfloat16 h[64];
+  const bool has_bias = p.bias != nullptr;
+  const bool has_add = p.addend.p != nullptr && my_valid && chan_ok;
+  const bool has_mask = p.mask.p != nullptr && my_valid && use_mask && chan_ok;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    __align__(16) __nv_bfloat16 a8[8];
+    __align__(16) __nv_bfloat16 m8[8];
+    if (has_add) *reinterpret_cast<uint4 *>(a8) = *reinterpret_cast<const uint4 *>(p.addend.p + add_off + q * 8);
+    if (has_mask) *reinterpret_cast<uint4 *>(m8) = *reinterpret_cast<const uint4 *>(p.mask.p + mask_off + q * 8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int j = q * 8 + e;
+      float v = __uint_as_float(r[j]);
+      if (has_bias) v += bias_s[j];
+      if (has_add) v += __bfloat162float(a8[e]);
+      if (p.mask.p != nullptr) {
+        if (has_mask && !(__bfloat162float(m8[e]) > 0.f)) v *= p.slope;
+      } else {
+        v = v > 0.f ? v : v * p.slope;
+      }
+      h[j] = __float2bfloat16_rn(v);
+    }
+  }
+  const unsigned vmask = __ballot_sync(0xffffffffu, my_valid && chan_ok);
+  const int ch = lane & 7;
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    *reinterpret_cast<uint4 *>(stage + lane * 128 + ((c ^ (lane & 7)) << 4)) = *reinterpret_cast<const uint4 *>(h + c * 8);
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = i * 4 + (lane >> 3);
+    const long long off = __shfl_sync(0xffffffffu, my_off, row);
+    if ((vmask >> row) & 1u)
+      *reinterpret_cast<uint4 *>(p.out_hi + off + ch * 8) =
+          *reinterpret_cast<const uint4 *>(stage + row * 128 + ((ch ^ (row & 7)) << 4));
+  }
+  __syncwarp();
+}
+
 // ---------------------------------------------------------------------------------------------
 // v2: persistent, warp-specialised, double-buffered TMEM accumulators.
 //   grid = min(#tiles, SMs x CTAs/SM); CTA c walks tiles c, c+G, c+2G ... (tile id = ((m*Nn + n)*S + z),
@@ -238,7 +293,7 @@ struct WorkIter {
   }
 };
 
-template <int BLOCK_N, int BLOCK_K, int STAGES, bool SPLIT3, bool RESIDENT_B, int KBLOCKS_RES>
+template <int BLOCK_N, int BLOCK_K, int STAGES, bool SPLIT3, bool RESIDENT_B, int KBLOCKS_RES, int EPI = 0>
 __global__ void __launch_bounds__(192) conv_igemm_persistent_kernel(const __grid_constant__ ConvKParams p,
                                                                     const int total_tiles, const int n_tiles,
                                                                     const int ks_tail, float *__restrict__ ws) {
@@ -283,7 +338,7 @@ __global__ void __launch_bounds__(192) conv_igemm_persistent_kernel(const __grid
     ptx::prefetch_tmap(&p.b_map);
     ptx::prefetch_tmap(&p.a_map[0]);
   }
-  for (int c = threadIdx.x; c < p.Cout; c += blockDim.x) bias_s[c] = p.bias[c];
+  for (int c = threadIdx.x; c < p.Cout && c < 1024; c += blockDim.x) bias_s[c] = p.bias ? p.bias[c] : 0.f;
   if (warp == 1) ptx::tmem_alloc(tmem_slot, TMEM_COLS);
   ptx::tc_fence_before();
   __syncthreads();
@@ -320,6 +375,7 @@ __global__ void __launch_bounds__(192) conv_igemm_persistent_kernel(const __grid
           }
           uint8_t *st = smem + s * S::STAGE_BYTES;
           ptx::mbar_expect_tx(&full_bar[s], tx);
+          if (EPI) { dr += p.in_off_r; dc += p.in_off_c; }
           ptx::tma_load_3d(st, &p.a_map[view], &full_bar[s], cc * BLOCK_K, ow0 + dc, g0 + dr);
           uint8_t *nxt = st + S::A_BYTES;
           if (!RESIDENT_B) {
@@ -409,6 +465,33 @@ __global__ void __launch_bounds__(192) conv_igemm_persistent_kernel(const __grid
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+      } else if (EPI == 1) {
+        const int nt = tile % n_tiles, mt = tile / n_tiles;
+        const int col_tile = mt % p.n_col_tiles, row_tile = mt / p.n_col_tiles;
+        const int g = row_tile * p.BH + bh, ow = col_tile * p.BW + bw, n0 = nt * BLOCK_N;
+        const int n_img = g / p.Hq, oh = g - n_img * p.Hq;
+        const int y = oh * p.out_sy + p.out_oy, x = ow * p.out_sx + p.out_ox;
+        const bool valid = (m < p.BW * p.BH) && (n_img < p.Bn) && (oh < p.Ho) && (ow < p.Wo) && y >= 0 && y < p.out_H &&
+                           x >= 0 && x < p.out_W;
+        const long long my_off =
+            (((long long)n_img * p.out_Hp + y + p.out_py) * p.out_Wp + x + p.out_px) * p.out_cs + p.out_coff + n0;
+        const long long add_off =
+            (((long long)n_img * p.addend.Hp + y + p.addend.py) * p.addend.Wp + x + p.addend.px) * p.addend.cs + p.addend.coff + n0;
+        const long long mask_off =
+            (((long long)n_img * p.mask.Hp + y + p.mask.py) * p.mask.Wp + x + p.mask.px) * p.mask.cs + p.mask.coff + n0;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 64) {
+          uint32_t r[64];
+          ptx::tmem_ld_32x32(trow + c, r);
+          ptx::tmem_ld_32x32(trow + c + 32, r + 32);
+          if (c + 64 >= BLOCK_N) {
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+          }
+          epilogue_generic64(r, p, bias_s + ((n0 + c) & 1023), stg, my_off + c, add_off + c, mask_off + c, valid,
+                             n0 + c < p.mask_climit, n0 + c < p.Cout, lane);
+        }
       } else {
         const int nt = tile % n_tiles, mt = tile / n_tiles;
         const int col_tile = mt % p.n_col_tiles, row_tile = mt / p.n_col_tiles;
@@ -442,7 +525,7 @@ __global__ void __launch_bounds__(192) conv_igemm_persistent_kernel(const __grid
 }
 
 // reduces the K slices of the tail tiles: one thread per (tail tile, row, 4 channels)
-__global__ void __launch_bounds__(256) conv_tail_finalize_kernel(const __grid_constant__ ConvKParams p, const float *ws,
+static __global__ void __launch_bounds__(256) conv_tail_finalize_kernel(const __grid_constant__ ConvKParams p, const float *ws,
                                                                  int base_tile, int tail_tiles, int ks, int n_tiles,
                                                                  int BN, int split3) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -920,7 +1003,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192)
 }
 
 // split-K finalize: sum partials + bias + LeakyReLU -> bf16 (hi[, lo]) into the bordered NHWC buffer
-__global__ void __launch_bounds__(256) conv_splitk_finalize_kernel(const float *partial, int ksplit, int npix,
+static __global__ void __launch_bounds__(256) conv_splitk_finalize_kernel(const float *partial, int ksplit, int npix,
                                                                    int Cout, int Ho, int Wo, int out_Hp, int out_Wp,
                                                                    int out_py, int out_px, const float *bias,
                                                                    float slope, __nv_bfloat16 *out_hi,

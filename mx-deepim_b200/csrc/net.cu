@@ -7,64 +7,11 @@
 //                deterministic two-pass reduction (partials reduced in fixed order by the head kernel)
 //   head       : fc6 reduce + bias + LeakyReLU -> fc7 -> LeakyReLU -> rot(4), trans(3) ->
 //                ZoomTrans^-1 (zoom_trans.py:30-31) -> se3 (B,7)
-#include <map>
 #include <mutex>
 
-#include "conv_igemm.cuh"
+#include "net_state.cuh"
 
 namespace dim {
-
-// FlowNetS tower: name, Cout, Cin, k, stride, pad (deepIM_flownet.py:63-107)
-struct LayerSpec {
-  const char *name;
-  int Cout, Cin, k, stride, pad;
-};
-static const LayerSpec kLayers[10] = {
-    {"flow_conv1", 64, 8, 7, 2, 3},  {"conv2", 128, 64, 5, 2, 2},   {"conv3", 256, 128, 5, 2, 2},
-    {"conv3_1", 256, 256, 3, 1, 1},  {"conv4", 512, 256, 3, 2, 1},  {"conv4_1", 512, 512, 3, 1, 1},
-    {"conv5", 512, 512, 3, 2, 1},    {"conv5_1", 512, 512, 3, 1, 1}, {"conv6", 1024, 512, 3, 2, 1},
-    {"conv6_1", 1024, 1024, 3, 1, 1}};
-
-struct LayerGeom {
-  // logical
-  int Cin, Cout, k, stride, pad, Hin, Win, Ho, Wo;
-  // input buffer: [B, rows, cols, Cbuf] bf16 (conv1: space-to-depth, Cbuf = 32)
-  int rows, cols, Cbuf, py, px;  // py/px: where the producer writes pixel (0,0) (pre-s2d for conv1)
-  // implicit GEMM view
-  int KH, KW, stride_eff, Ceff, Hq;
-  int BLOCK_N, BLOCK_K, BW, BH, n_col_tiles, kblocks;
-  int pair;  // 1: CTA-pair kernel (cta_group::2, 256 x BLOCK_N tiles)
-  int occ;  // resident CTAs per SM of the persistent kernel variant used for this layer (bf16 mode)
-};
-
-struct TensorMaps {
-  ConvKParams kp[10];
-  int ksplit[10];
-  LayerGeom g[10];  // per-batch-size effective geometry (tile width may depend on the batch)
-};
-
-struct NetState {
-  LayerGeom g[10];
-  __nv_bfloat16 *w_hi[10] = {}, *w_lo[10] = {};
-  float *bias[10] = {};
-  __nv_bfloat16 *act_hi[11] = {}, *act_lo[11] = {};  // act[i] = input of layer i, act[10] = fc6 input
-  size_t act_elems_per_image[11] = {};
-  // fc
-  __nv_bfloat16 *fc6_w_hi = nullptr, *fc6_w_lo = nullptr;  // [256][81920] in (h,w,c) order
-  float *fc6_b = nullptr, *fc7_wT = nullptr, *fc7_b = nullptr, *rot_w = nullptr, *rot_b = nullptr,
-        *trans_w = nullptr, *trans_b = nullptr;
-  float *fc6_partial = nullptr;  // [FC6_SPLITS][max_batch][256]
-  float *conv_partial = nullptr;
-  size_t conv_partial_elems = 0;
-  float *tail_ws = nullptr;  // K-slice partials of the tail tiles: [<= 2*SMs slots][128][256] fp32
-  bool loaded = false, net_ok = false;
-  std::map<int, TensorMaps> maps;  // per batch size
-  int max_batch = 0, num_sms = 148;
-};
-
-static constexpr int FC6_K = 1024 * 8 * 10;
-static constexpr int FC6_KC = 256;
-static constexpr int FC6_SPLITS = FC6_K / FC6_KC;  // 320
 
 // --------------------------------------------------------------------------------- geometry
 static bool use_pair_kernel() {
@@ -182,7 +129,7 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-static int encode_map(CUtensorMap *m, void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
+int encode_map(CUtensorMap *m, void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
                       const uint32_t *box, int block_k /*64: SW128, 32: SW64, 0: no swizzle*/) {
   EncodeTiledFn fn = get_encode();
   DIM_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available (driver too old?)");
@@ -203,7 +150,7 @@ static int encode_map(CUtensorMap *m, void *base, int rank, const uint64_t *dims
   return 0;
 }
 
-static uint32_t make_idesc(int M, int N) {
+uint32_t make_idesc(int M, int N) {
   // cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b_format BF16 (1) @7/@10, K-major both,
   // n_dim = N>>3 @17, m_dim = M>>4 @24
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -368,7 +315,8 @@ __global__ void __launch_bounds__(1024) head_kernel(const float *__restrict__ pa
                                                     const float *__restrict__ trans_b,
                                                     const float *__restrict__ zoom_factor /*nullable*/,
                                                     float *__restrict__ rot_out, float *__restrict__ trans_out,
-                                                    float *__restrict__ se3_out) {
+                                                    float *__restrict__ se3_out, float *__restrict__ h6_out,
+                                                    float *__restrict__ h7_out) {
   __shared__ float red[4][256];
   __shared__ float h6[256], h7[256], outv[8];
   const int b = blockIdx.x, j = threadIdx.x & 255, grp = threadIdx.x >> 8;
@@ -390,6 +338,7 @@ __global__ void __launch_bounds__(1024) head_kernel(const float *__restrict__ pa
   if (grp == 0) {
     const float v = (((red[0][j] + red[1][j]) + red[2][j]) + red[3][j]) + fc7_b[j];
     h7[j] = v > 0.f ? v : 0.1f * v;
+    if (h6_out) { h6_out[b * 256 + j] = h6[j]; h7_out[b * 256 + j] = h7[j]; }
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -418,16 +367,6 @@ __global__ void __launch_bounds__(1024) head_kernel(const float *__restrict__ pa
 }
 
 // --------------------------------------------------------------------------------- host API
-template <typename T>
-static int dev_alloc(dim_ctx *ctx, T **p, size_t n, bool zero) {
-  void *q = nullptr;
-  DIM_CHECK(cudaMalloc(&q, n * sizeof(T)));
-  if (zero) DIM_CHECK(cudaMemset(q, 0, n * sizeof(T)));
-  ctx->owned.push_back(q);
-  *p = reinterpret_cast<T *>(q);
-  return 0;
-}
-
 int net_create(dim_ctx *ctx) {
   NetState *ns = new NetState();
   ctx->net = ns;
@@ -672,7 +611,8 @@ int net_forward(dim_ctx *ctx, int B, int precision, const float *zoom_factor, fl
                                                       ctx->max_batch, ns->fc6_partial);
   DIM_LAUNCH_CHECK();
   head_kernel<<<B, 1024, 0, st>>>(ns->fc6_partial, ctx->max_batch, ns->fc6_b, ns->fc7_wT, ns->fc7_b, ns->rot_w,
-                                 ns->rot_b, ns->trans_w, ns->trans_b, zoom_factor, rot_out, trans_out, se3_out);
+                                 ns->rot_b, ns->trans_w, ns->trans_b, zoom_factor, rot_out, trans_out, se3_out, ns->save_h6,
+                                 ns->save_h7);
   DIM_LAUNCH_CHECK();
   return 0;
 }

@@ -1,0 +1,80 @@
+// net_state.cuh -- state of the FlowNetS network shared by net.cu (inference) and train.cu (training step).
+#pragma once
+#include <map>
+
+#include "conv_igemm.cuh"
+
+namespace dim {
+
+// FlowNetS tower: name, Cout, Cin, k, stride, pad (deepIM_flownet.py:63-107)
+struct LayerSpec {
+  const char *name;
+  int Cout, Cin, k, stride, pad;
+};
+static const LayerSpec kLayers[10] = {
+    {"flow_conv1", 64, 8, 7, 2, 3},  {"conv2", 128, 64, 5, 2, 2},   {"conv3", 256, 128, 5, 2, 2},
+    {"conv3_1", 256, 256, 3, 1, 1},  {"conv4", 512, 256, 3, 2, 1},  {"conv4_1", 512, 512, 3, 1, 1},
+    {"conv5", 512, 512, 3, 2, 1},    {"conv5_1", 512, 512, 3, 1, 1}, {"conv6", 1024, 512, 3, 2, 1},
+    {"conv6_1", 1024, 1024, 3, 1, 1}};
+
+struct LayerGeom {
+  // logical
+  int Cin, Cout, k, stride, pad, Hin, Win, Ho, Wo;
+  // input buffer: [B, rows, cols, Cbuf] bf16 (conv1: space-to-depth, Cbuf = 32)
+  int rows, cols, Cbuf, py, px;  // py/px: where the producer writes pixel (0,0) (pre-s2d for conv1)
+  // implicit GEMM view
+  int KH, KW, stride_eff, Ceff, Hq;
+  int BLOCK_N, BLOCK_K, BW, BH, n_col_tiles, kblocks;
+  int pair;  // 1: CTA-pair kernel (cta_group::2, 256 x BLOCK_N tiles)
+  int occ;  // resident CTAs per SM of the persistent kernel variant used for this layer (bf16 mode)
+};
+
+struct TensorMaps {
+  ConvKParams kp[10];
+  int ksplit[10];
+  LayerGeom g[10];  // per-batch-size effective geometry (tile width may depend on the batch)
+};
+
+struct NetState {
+  LayerGeom g[10];
+  __nv_bfloat16 *w_hi[10] = {}, *w_lo[10] = {};
+  float *bias[10] = {};
+  __nv_bfloat16 *act_hi[11] = {}, *act_lo[11] = {};  // act[i] = input of layer i, act[10] = fc6 input
+  size_t act_elems_per_image[11] = {};
+  // fc
+  __nv_bfloat16 *fc6_w_hi = nullptr, *fc6_w_lo = nullptr;  // [256][81920] in (h,w,c) order
+  float *fc6_b = nullptr, *fc7_wT = nullptr, *fc7_b = nullptr, *rot_w = nullptr, *rot_b = nullptr,
+        *trans_w = nullptr, *trans_b = nullptr;
+  float *fc6_partial = nullptr;  // [FC6_SPLITS][max_batch][256]
+  float *conv_partial = nullptr;
+  size_t conv_partial_elems = 0;
+  float *tail_ws = nullptr;  // K-slice partials of the tail tiles: [<= 2*SMs slots][128][256] fp32
+  bool loaded = false, net_ok = false;
+  float *save_h6 = nullptr, *save_h7 = nullptr;  // training: fc6 / fc7 activations kept for the backward pass ([B][256])
+  std::map<int, TensorMaps> maps;  // per batch size
+  int max_batch = 0, num_sms = 148;
+};
+
+static constexpr int FC6_K = 1024 * 8 * 10;
+static constexpr int FC6_KC = 256;
+static constexpr int FC6_SPLITS = FC6_K / FC6_KC;  // 320
+
+
+// helpers implemented in net.cu
+int encode_map(CUtensorMap *m, void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
+               const uint32_t *box, int block_k /*64: SW128, 32: SW64, 0: no swizzle*/);
+uint32_t make_idesc(int M, int N);
+int net_forward(dim_ctx *ctx, int B, int precision, const float *zoom_factor, float *rot_out, float *trans_out,
+                float *se3_out, cudaStream_t st, cudaEvent_t after_conv);
+
+template <typename T>
+static int dev_alloc(dim_ctx *ctx, T **p, size_t n, bool zero) {
+  void *q = nullptr;
+  DIM_CHECK(cudaMalloc(&q, n * sizeof(T)));
+  if (zero) DIM_CHECK(cudaMemset(q, 0, n * sizeof(T)));
+  ctx->owned.push_back(q);
+  *p = reinterpret_cast<T *>(q);
+  return 0;
+}
+
+}  // namespace dim

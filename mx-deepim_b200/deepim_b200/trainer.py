@@ -1,0 +1,160 @@
+"""Trainer: the device replacement of Module.forward_backward + Module.update for the refiner network
+(deepim/core/module.py:1131-1137: one SGD update after each of the TRAIN_ITER_SIZE = 4 inner iterations, with
+the batch re-rendered in between by batchUpdaterPyMulti -> Context.train_update).
+
+Data parallel (training row): one process per GPU, every rank runs forward_backward on its slice
+of the batch, the flat fp32 gradient vector is sum-all-reduced with NCCL in buckets (rescale_grad = 1.0, so a
+plain sum like kvstore's), then every rank applies the identical SGD update."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _capi as capi
+from ._capi import check, lib
+
+NORMALIZE_FLOW = 20.0
+
+
+def param_table():
+    """[(tensor name, numel)] in flat order, as the library reports it (dim_train_param_info)."""
+    out = []
+    for i in range(64):
+        name, wn, bn = C.c_char_p(), C.c_int64(), C.c_int64()
+        if lib.dim_train_param_info(i, C.byref(name), C.byref(wn), C.byref(bn)) != 0:
+            break
+        out.append((name.value.decode() + "_weight", wn.value))
+        if bn.value:
+            out.append((name.value.decode() + "_bias", bn.value))
+    return out
+
+
+def flatten_params(weights: dict) -> np.ndarray:
+    parts = []
+    for name, n in param_table():
+        a = np.ascontiguousarray(weights[name], dtype=np.float32).reshape(-1)
+        if a.size != n:
+            raise ValueError("%s: expected %d values, got %d" % (name, n, a.size))
+        parts.append(a)
+    return np.concatenate(parts)
+
+
+def unflatten_params(flat: np.ndarray, like: dict) -> dict:
+    out, off = {}, 0
+    for name, n in param_table():
+        out[name] = np.asarray(flat[off:off + n], np.float32).reshape(like[name].shape).copy()
+        off += n
+    return out
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class Trainer:
+    def __init__(self, ctx, weights: dict, max_points=3000, lr=1e-4, momentum=0.975, wd=5e-4, bucket_mb=32.0):
+        self.ctx, self.lr, self.momentum, self.wd = ctx, lr, momentum, wd
+        check(lib.dim_train_create(ctx._h, max_points))
+        self.n = int(lib.dim_train_param_count(ctx._h))
+        self.table = param_table()
+        flat = flatten_params(weights)
+        assert flat.size == self.n
+        self._shapes = {k: np.asarray(v).shape for k, v in weights.items()}
+        check(lib.dim_train_load_params(ctx._h, flat.ctypes.data_as(C.c_void_p), self.n, self._stream()))
+        torch.cuda.current_stream(ctx.device).synchronize()
+        self.grads = torch.zeros(self.n, dtype=torch.float32, device=ctx.device)
+        limit = int(bucket_mb * (1 << 20) / 4)
+        self.buckets, hi, lo = [], self.n, self.n
+        for _, n in reversed(self.table):  # reverse order = the order the backward pass produces the gradients
+            lo -= n
+            if hi - lo >= limit:
+                self.buckets.append((lo, hi))
+                hi = lo
+        if hi > 0:
+            self.buckets.append((0, hi))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.ctx.device).cuda_stream)
+
+    def offsets(self):
+        out, off = {}, 0
+        for name, n in self.table:
+            out[name] = (off, n)
+            off += n
+        return out
+
+    def forward_backward(self, z, want_maps=True, backward=True):
+        """z: dict of device float32 tensors (the outputs of the zoom front of the train symbol + labels):
+        zoom_image_observed/rendered (B,3,H,W), zoom_mask_observed/rendered (B,1,H,W), zoom_factor (B,4),
+        zoom_flow, zoom_flow_weights (B,2,H,W), zoom_mask_gt_observed (B,1,H,W), src_pose (B,3,4),
+        point_cloud_model/weights/observed (B,3,N)."""
+        ctx = self.ctx
+        B, N = z["zoom_image_observed"].shape[0], z["point_cloud_model"].shape[2]
+        for k, t in z.items():
+            if t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda:
+                raise TypeError("%s must be a contiguous float32 CUDA tensor" % k)
+        out = {"rot_est_norm": ctx._new((B, 4)), "trans_est": ctx._new((B, 3)), "losses": ctx._new((4,)),
+               "flow_est": ctx._new((B, 2, ctx.H, ctx.W)) if want_maps else None,
+               "mask_prob": ctx._new((B, 1, ctx.H, ctx.W)) if want_maps else None}
+        check(lib.dim_train_forward_backward(
+            ctx._h, _p(z["zoom_image_observed"]), _p(z["zoom_image_rendered"]), _p(z["zoom_mask_observed"]),
+            _p(z["zoom_mask_rendered"]), _p(z["zoom_factor"]), _p(z["zoom_flow"]), _p(z["zoom_flow_weights"]),
+            _p(z["zoom_mask_gt_observed"]), _p(z["src_pose"]), _p(z["point_cloud_model"]), _p(z["point_cloud_weights"]),
+            _p(z["point_cloud_observed"]), B, N, _p(out["rot_est_norm"]), _p(out["trans_est"]), _p(out["flow_est"]),
+            _p(out["mask_prob"]), _p(out["losses"]), _p(self.grads) if backward else None, self._stream()))
+        return out
+
+    def allreduce(self, dist):
+        if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+            for lo, hi in self.buckets:
+                dist.all_reduce(self.grads[lo:hi], op=dist.ReduceOp.SUM)
+
+    def update(self, lr=None):
+        check(lib.dim_train_sgd_update(self.ctx._h, _p(self.grads), self.lr if lr is None else lr, self.momentum, self.wd,
+                                       1.0, self._stream()))
+
+    def step(self, z, dist=None, want_maps=False):
+        out = self.forward_backward(z, want_maps=want_maps)
+        self.allreduce(dist)
+        self.update()
+        return out
+
+    def zoom_front(self, batch, K):
+        """ZoomMask / ZoomImageWithFactor / ZoomFlow of get_train_symbol (deepIM_flownet.py:391-489) on device tensors."""
+        ctx = self.ctx
+        zo, zg, zr, zf, _ = ctx.zoom_mask(batch["mask_observed"], batch["mask_gt_observed"], batch["mask_rendered"],
+                                          batch["src_pose"], K)
+        zio, zir = ctx.zoom_image_with_factor(zf, batch["image_observed"], batch["image_rendered"], batch["pixel_means_rgb"])
+        zfl, zfw = ctx.zoom_flow(zf, batch["flow"], batch["flow_weights"], False)
+        return {"zoom_image_observed": zio, "zoom_image_rendered": zir, "zoom_mask_observed": zo, "zoom_mask_rendered": zr,
+                "zoom_factor": zf, "zoom_flow": zfl, "zoom_flow_weights": zfw, "zoom_mask_gt_observed": zg,
+                "src_pose": batch["src_pose"], "point_cloud_model": batch["point_cloud_model"],
+                "point_cloud_weights": batch["point_cloud_weights"], "point_cloud_observed": batch["point_cloud_observed"]}
+
+    def get_params(self, momentum=False) -> dict:
+        flat = np.empty(self.n, np.float32)
+        check(lib.dim_train_get_params(self.ctx._h, flat.ctypes.data_as(C.c_void_p), self.n, 1 if momentum else 0, self._stream()))
+        return unflatten_params(flat, {k: np.empty(s, np.float32) for k, s in self._shapes.items()})
+
+    def grads_dict(self) -> dict:
+        flat = self.grads.cpu().numpy()
+        return unflatten_params(flat, {k: np.empty(s, np.float32) for k, s in self._shapes.items()})
+
+    def debug_tensor(self, tid):
+        """fp32 maps (id < 10) as [B,h,w,c]; bf16 buffers (id >= 10) as float32 [B,Hp,Wp,C] incl. border."""
+        ctx = self.ctx
+        B = ctx.max_batch
+        if tid < 10:
+            hw = {0: (8, 10, 2), 1: (15, 20, 2), 2: (30, 40, 2), 3: (30, 40, 1), 4: (30, 40, 2), 5: (30, 40, 1), 6: (15, 20, 2),
+                  7: (8, 10, 2)}[tid]
+            a = np.empty((B,) + hw, np.float32)
+            check(lib.dim_train_debug_tensor(ctx._h, tid, a.ctypes.data_as(C.c_void_p), a.nbytes))
+            return a
+        geo = (C.c_int32 * 7)()
+        check(lib.dim_train_debug_geometry(ctx._h, tid, geo))
+        Hp, Wp, py, px, Cc, H, W = list(geo)
+        raw = np.empty((B, Hp, Wp, Cc), np.uint16)
+        check(lib.dim_train_debug_tensor(ctx._h, tid, raw.ctypes.data_as(C.c_void_p), raw.nbytes))
+        return (raw.astype(np.uint32) << 16).view(np.float32), (py, px, H, W)

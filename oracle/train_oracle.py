@@ -68,9 +68,13 @@ def graph(weights, zin, labels, requires_grad=True, num_threads=None):
     lrelu = lambda x: F.leaky_relu(x, 0.1)
     x = torch.cat([_t(zin["zoom_image_observed"]) / 255.0, _t(zin["zoom_image_rendered"]) / 255.0,
                    _t(zin["zoom_mask_observed"]), _t(zin["zoom_mask_rendered"])], dim=1)
-    feat = {}
+    feat, pre = {}, {}
     for name, s, p in ENC:
-        x = lrelu(F.conv2d(x, P[name + "_weight"], P[name + "_bias"], stride=s, padding=p))
+        z = F.conv2d(x, P[name + "_weight"], P[name + "_bias"], stride=s, padding=p)
+        if requires_grad:
+            z.retain_grad()
+        pre[name] = z
+        x = lrelu(z)
         feat[name] = x
     r10, r8, r6 = feat["conv6_1"], feat["conv5_1"], feat["conv4_1"]
     h = lrelu(F.linear(r10.flatten(1), P["fc6_weight"], P["fc6_bias"]))
@@ -135,6 +139,8 @@ def graph(weights, zin, labels, requires_grad=True, num_threads=None):
     if requires_grad:
         objective.backward()
         grads = {k: (v.grad.numpy().copy() if v.grad is not None else np.zeros(v.shape, np.float32)) for k, v in P.items()}
+        for name, z in pre.items():  # gradients wrt the pre-activation conv outputs (debugging aid for the device backward)
+            grads["dz_" + name] = z.grad.numpy().copy()
     out = {
         "rot_est_norm": rot_n.detach().numpy(), "rot_raw": rot.detach().numpy(), "zoom_trans_est": ztrans.detach().numpy(),
         "trans_est": trans_est.detach().numpy(),
