@@ -735,12 +735,16 @@ int train_param_info(int idx, const char **name, long long *w_numel, long long *
 
 // ------------------------------------------------------------------------ generic conv launches
 static void pick_tile(int W, int rows_total, int cap, int &BW, int &BH, int max_bw = 1 << 30, int max_bh = 1 << 30) {
-  long best = -1;
-  for (int bw = 1; bw <= cap; bw <<= 1) {
-    const int bh = cap / bw;
-    if ((bw > max_bw || bh > max_bh) && !(bw == 1 && best < 0)) continue;  // keep TMA boxes inside the tensor extents
-    const long cost = (long)cdiv(W, bw) * bw * cdiv(rows_total, bh) * bh;
-    if (best < 0 || cost < best || (cost == best && bw > BW)) { best = cost; BW = bw; BH = bh; }
+  // power-of-two BW x BH = cap rectangle with the least padding; prefer TMA boxes inside the tensor extents
+  for (int pass = 0; pass < 2; ++pass) {
+    long best = -1;
+    for (int bw = 1; bw <= cap; bw <<= 1) {
+      const int bh = cap / bw;
+      if (pass == 0 && (bw > max_bw || bh > max_bh)) continue;
+      const long cost = (long)cdiv(W, bw) * bw * cdiv(rows_total, bh) * bh;
+      if (best < 0 || cost < best || (cost == best && bw > BW)) { best = cost; BW = bw; BH = bh; }
+    }
+    if (best >= 0) return;
   }
 }
 

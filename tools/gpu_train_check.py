@@ -31,11 +31,12 @@ def make_batch(meshes, B, seed):
                          tgt32, depth_gt, K, MEANS)
     img_obs = np.stack([synth.transform_image(synth.composite_observed(r_obs[b]["bgr"], r_obs[b]["mask"], b)) for b in range(B)])
     rng = np.random.default_rng(seed)
-    pts = np.stack([meshes[cls[b]].verts[rng.permutation(len(meshes[cls[b]].verts))[:3000]].T for b in range(B)])
-    if pts.shape[2] < 3000:
-        pts = np.concatenate([pts, np.zeros((B, 3, 3000 - pts.shape[2]), np.float32)], axis=2)
-    pw = (np.abs(pts).sum(axis=1, keepdims=True) > 0).astype(np.float32).repeat(3, axis=1)
-    pts = pts.astype(np.float32)
+    pts, pw = np.zeros((B, 3, 3000), np.float32), np.zeros((B, 3, 3000), np.float32)
+    for b in range(B):  # get_point_cloud_model (lib/utils/image.py:452-478): up to 3000 shuffled model points, weight 1
+        v = meshes[cls[b]].verts
+        keep = rng.permutation(len(v))[:3000]
+        pts[b, :, :len(keep)] = v[keep].T
+        pw[b, :, :len(keep)] = 1
     pobs = np.stack([tgt32[b, :, :3] @ pts[b] + tgt32[b, :, 3:4] for b in range(B)]).astype(np.float32)
     box = np.stack([O.box_mask(O.mask_bbox(mask_gt[b, 0], 0.0), 480, 640) for b in range(B)])[:, None]
     return dict(image_observed=img_obs, image_rendered=upd["image_rendered"], mask_observed=box, mask_gt_observed=mask_gt,
@@ -51,7 +52,7 @@ def cmp(a, b):
 
 
 def main():
-    B = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+    B = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 2
     meshes = [synth.make_cube(), synth.make_blob()]
     w = synth.make_train_weights(0)
     batch = make_batch(meshes, B, 11)
