@@ -1,0 +1,168 @@
+"""GPU: the training step through the C-ABI against the CPU training oracle
+(oracle/train_oracle.py: torch-CPU fp32 autograd restatement of get_convs/get_loss, deepIM_flownet.py:32-365).
+
+Tolerances: the device step is bf16 mixed precision (bf16 activations and activation gradients, fp32 accumulation,
+fp32 master weights), the oracle is fp32.  Forward maps agree to ~1e-2 of their range; parameter gradients are
+compared by direction and scale (cosine >= 0.995, |g - g_ref|_max <= 0.15 |g_ref|_max): besides bf16 rounding, a
+LeakyReLU whose pre-activation is within rounding distance of zero takes the other slope in the two precisions.
+The oracle itself is PARITY UNPINNED for MXNet's Convolution/Deconvolution/SGD arithmetic (its header lists the
+assumed semantics); Transform3D forward/backward is pinned by the reference self-test (test_gpu_operator_surface)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+from oracle import oracle as O, train_oracle as T  # noqa: E402
+from deepim_b200 import synth  # noqa: E402
+from deepim_b200.context import Context  # noqa: E402
+from deepim_b200.trainer import Trainer, param_table  # noqa: E402
+import gpu_train_check as G  # noqa: E402  (batch builder shared with the diagnostic tool)
+
+K, MEANS = synth.K_LINEMOD, synth.PIXEL_MEANS_RGB
+dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, np.float32)).cuda()
+
+
+@pytest.fixture(scope="module")
+def setup():
+    B = 2
+    meshes = [synth.make_cube(), synth.make_blob()]
+    w = synth.make_train_weights(0)
+    batch = G.make_batch(meshes, B, 11)
+    ctx = Context(0, max_batch=B, max_classes=2, max_verts=6000, max_faces=11000)
+    for i, m in enumerate(meshes):
+        ctx.upload_mesh(i, m)
+    tr = Trainer(ctx, w)
+    yield B, meshes, w, batch, ctx, tr
+    ctx.close()
+
+
+def test_param_table_matches_the_reference_parameter_count(setup):
+    B, meshes, w, batch, ctx, tr = setup
+    tab = param_table()
+    assert sum(n for _, n in tab) == 57749164 == tr.n          # 230 996 656 B of fp32 gradients
+    assert [k for k, _ in tab][:2] == ["flow_conv1_weight", "flow_conv1_bias"]
+    assert set(k for k, _ in tab) == set(w.keys())
+    p = tr.get_params()
+    for k in w:
+        assert np.array_equal(p[k], w[k]), k                   # flat layout round trip
+
+
+def test_zoom_front_on_device_matches_oracle(setup):
+    B, meshes, w, batch, ctx, tr = setup
+    zin, lab = T.zoom_inputs(batch, K, MEANS)
+    b = {k: dev(v) for k, v in batch.items()}
+    b["pixel_means_rgb"] = MEANS.astype(np.float32)
+    z = tr.zoom_front(b, K)
+    for k in ("zoom_image_observed", "zoom_image_rendered", "zoom_mask_observed", "zoom_mask_rendered"):
+        assert np.array_equal(z[k].cpu().numpy(), zin[k]), k
+    for k in ("zoom_factor", "zoom_flow", "zoom_flow_weights", "zoom_mask_gt_observed"):
+        assert np.array_equal(z[k].cpu().numpy(), lab[k]), k
+
+
+def test_training_step_matches_oracle(setup):
+    B, meshes, w, batch, ctx, tr = setup
+    out, g, zin, lab = T.forward_backward(w, batch, K, MEANS)
+    b = {k: dev(v) for k, v in batch.items()}
+    b["pixel_means_rgb"] = MEANS.astype(np.float32)
+    z = tr.zoom_front(b, K)
+    res = tr.forward_backward(z)
+    torch.cuda.synchronize()
+    losses = res["losses"].cpu().numpy()
+    assert abs(losses[0] - out["flow_loss"].sum()) < 2e-3 * out["flow_loss"].sum()
+    assert abs(losses[1] - out["point_matching_loss"].sum()) < 2e-3 * out["point_matching_loss"].sum()
+    assert abs(losses[3] - out["objective"]) < 2e-3 * out["objective"]
+    assert np.abs(res["rot_est_norm"].cpu().numpy() - out["rot_est_norm"]).max() < 5e-4
+    assert np.abs(res["trans_est"].cpu().numpy() - out["trans_est"]).max() < 1e-4
+    assert np.abs(res["flow_est"].cpu().numpy() - out["flow_est"]).max() < 2e-2 * np.abs(out["flow_est"]).max()
+    assert np.abs(res["mask_prob"].cpu().numpy() - out["mask_prob"]).max() < 1e-2
+    nhwc = lambda a: np.transpose(a, (0, 2, 3, 1))
+    for tid, name in ((0, "flow6"), (1, "flow5"), (2, "flow4"), (3, "mask4")):
+        assert G.cmp(tr.debug_tensor(tid), nhwc(out[name]))["rel"] < 3e-2, name
+    for tid, name, C in ((10, "concat2", 1026), (11, "concat3", 770)):
+        buf, (py, px, H, W) = tr.debug_tensor(tid)
+        assert G.cmp(buf[:, py:py + H, px:px + W, :C], nhwc(out[name]))["rel"] < 3e-2, name
+        assert np.abs(buf[:, py:py + H, px:px + W, C:]).max() == 0.0            # padding channels stay zero
+        assert np.abs(buf[:, 0]).max() == 0.0 and np.abs(buf[:, :, 0]).max() == 0.0   # and so does the border
+    gd = tr.grads_dict()
+    worst = {}
+    for k in sorted(gd):
+        if k in T.FROZEN:
+            assert np.abs(gd[k]).max() == 0.0
+            continue
+        c = G.cmp(gd[k], g[k])
+        worst[k] = (c["cos"], c["rel"])
+        assert c["cos"] > 0.995 and c["rel"] < 0.15, (k, c)
+    # the data gradient that reaches every encoder layer (bf16, zero border intact)
+    for i, (name, _, _) in enumerate(T.ENC):
+        buf, (py, px, H, W) = tr.debug_tensor(20 + i)
+        assert G.cmp(buf[:, py:py + H, px:px + W, :], nhwc(g["dz_" + name]))["cos"] > 0.98, name
+        assert max(np.abs(buf[:, 0]).max(), np.abs(buf[:, -1]).max(), np.abs(buf[:, :, 0]).max(), np.abs(buf[:, :, -1]).max()) == 0.0
+
+
+def test_sgd_update_and_repack(setup):
+    """mom = m*mom - lr*(g + wd*w), w += mom on the flat vector (wd on weights only, bilinear kernels frozen);
+    the bf16 operand packs follow the master weights: the next forward pass uses the updated network."""
+    B, meshes, w, batch, ctx, tr = setup
+    b = {k: dev(v) for k, v in batch.items()}
+    b["pixel_means_rgb"] = MEANS.astype(np.float32)
+    z = tr.zoom_front(b, K)
+    p0 = tr.get_params()
+    m0 = tr.get_params(momentum=True)
+    res0 = tr.forward_backward(z)
+    gd = tr.grads_dict()
+    tr.update(lr=1e-4)
+    p1, m1 = tr.get_params(), tr.get_params(momentum=True)
+    for k in p0:
+        if k in T.FROZEN:
+            assert np.array_equal(p1[k], p0[k])
+            continue
+        wd = 5e-4 if k.endswith("_weight") else 0.0
+        mom = (np.float32(0.975) * m0[k] - np.float32(1e-4) * (gd[k] + np.float32(wd) * p0[k])).astype(np.float32)
+        assert np.abs(m1[k] - mom).max() <= 1e-6 * max(np.abs(mom).max(), 1e-12) + 1e-12, k
+        assert np.abs(p1[k] - (p0[k] + mom)).max() <= 2e-7 * max(np.abs(p0[k]).max(), 1e-12), k
+    # a few large-lr steps on the same batch must reduce the objective (the packs were refreshed)
+    first = float(res0["losses"][3])
+    for _ in range(6):
+        tr.forward_backward(z, want_maps=False)
+        tr.update(lr=2e-3)
+    last = float(tr.forward_backward(z, want_maps=False, backward=False)["losses"][3])
+    assert last < first, (first, last)
+    # and the inference path of the same context now runs the updated weights (bf16 packs refreshed)
+    rot, trans = ctx.net_forward(z["zoom_image_observed"], z["zoom_image_rendered"], z["zoom_mask_observed"], z["zoom_mask_rendered"],
+                                 precision=0)
+    pnow = tr.get_params()
+    orot, otrans = O.net_forward(pnow, z["zoom_image_observed"].cpu().numpy(), z["zoom_image_rendered"].cpu().numpy(),
+                                 z["zoom_mask_observed"].cpu().numpy(), z["zoom_mask_rendered"].cpu().numpy())
+    assert np.abs(rot.cpu().numpy() - orot).max() < 2e-2 and np.abs(trans.cpu().numpy() - otrans).max() < 2e-2
+
+
+def test_inner_iteration_loop_like_module_fit(setup):
+    """module.py:1131-1137: forward_backward, update, then batchUpdaterPyMulti.forward re-renders at the predicted
+    pose and recomputes the labels -- 4 inner iterations on the device."""
+    B, meshes, w, batch, ctx, tr = setup
+    b = {k: dev(v) for k, v in batch.items()}
+    b["pixel_means_rgb"] = MEANS.astype(np.float32)
+    cls = torch.tensor([0, 1], dtype=torch.int32, device="cuda")
+    obs, ini = synth.sample_pose_pairs(B, 11)
+    tgt = dev(obs.astype(np.float32))
+    depth_gt = dev(np.stack([O.render(meshes[i % 2], obs[i], K, trunc_u8=False)["depth"] for i in range(B)])[:, None])
+    objs = []
+    for it in range(4):
+        z = tr.zoom_front(b, K)
+        res = tr.step(z)
+        objs.append(float(res["losses"][3]))
+        if it < 3:
+            upd = ctx.train_update(cls, b["src_pose"], res["rot_est_norm"], res["trans_est"], tgt, depth_gt, K, pixel_means_rgb=MEANS)
+            for k in ("image_rendered", "mask_rendered", "src_pose", "flow", "flow_weights"):
+                b[k] = upd[k]
+    assert all(np.isfinite(objs)) and len(objs) == 4
