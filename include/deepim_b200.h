@@ -33,7 +33,7 @@ extern "C" {
 
 typedef struct dim_ctx dim_ctx;
 
-#define DIM_ABI_VERSION 1
+#define DIM_ABI_VERSION 2
 DIM_API int32_t dim_abi_version(void);
 DIM_API const char *dim_last_error(void);
 
@@ -93,10 +93,12 @@ DIM_API int32_t dim_zoom_mask_with_factor_fwd(dim_ctx *ctx, const float *zoom_fa
                                               float *zoom_mask, void *stream);
 
 /* ZoomFlow forward (zoom_flow.py:28-71): flow f32[B,2,H,W]; flow_weights/zoom_flow_weights
- * f32[B,1,H,W] used only when b_inv_zoom == 0 (may be NULL). */
+ * f32[B,fw_channels,H,W] (1, or 2 as tiled by batch_updater_py_multi.py:293-296) used only when
+ * b_inv_zoom == 0 (may be NULL). */
 DIM_API int32_t dim_zoom_flow_fwd(dim_ctx *ctx, const float *zoom_factor, const float *flow,
-                                  const float *flow_weights, int32_t B, int32_t b_inv_zoom,
-                                  float *zoom_flow, float *zoom_flow_weights, void *stream);
+                                  const float *flow_weights, int32_t fw_channels, int32_t B,
+                                  int32_t b_inv_zoom, float *zoom_flow, float *zoom_flow_weights,
+                                  void *stream);
 
 /* ZoomDepth forward (zoom_depth.py:24-44): depth f32[B,1,H,W] x2. */
 DIM_API int32_t dim_zoom_depth_fwd(dim_ctx *ctx, const float *zoom_factor,

@@ -219,11 +219,14 @@ DIM_API int32_t dim_zoom_mask_with_factor_fwd(dim_ctx *ctx, const float *zoom_fa
 }
 
 DIM_API int32_t dim_zoom_flow_fwd(dim_ctx *ctx, const float *zoom_factor, const float *flow, const float *fw,
-                                  int32_t B, int32_t inv, float *zflow, float *zfw, void *stream) {
+                                  int32_t fw_channels, int32_t B, int32_t inv, float *zflow, float *zfw, void *stream) {
   DIM_REQUIRE(ctx && zoom_factor && flow && zflow, "dim_zoom_flow_fwd: NULL argument");
   cudaStream_t st = (cudaStream_t)stream;
   if (int rc = zoom_gather_launch(ctx, inv ? 4 : 6, flow, zflow, zoom_factor, B, 2, inv, nullptr, st)) return rc;
-  if (!inv && fw && zfw) return zoom_gather_launch(ctx, 5, fw, zfw, zoom_factor, B, 1, 0, nullptr, st);
+  if (!inv && fw && zfw) {
+    DIM_REQUIRE(fw_channels == 1 || fw_channels == 2, "dim_zoom_flow_fwd: flow_weights has 1 or 2 channels");
+    return zoom_gather_launch(ctx, 5, fw, zfw, zoom_factor, B, fw_channels, 0, nullptr, st);
+  }
   return 0;
 }
 

@@ -30,7 +30,7 @@ SIGNATURES = {
     "dim_zoom_mask_fwd": (i32, [vp, vp, vp, vp, vp, i32, pf32, vp, vp, vp, vp, vp, vp, vp]),
     "dim_zoom_image_with_factor_fwd": (i32, [vp, vp, vp, vp, i32, pf32, vp, vp, vp]),
     "dim_zoom_mask_with_factor_fwd": (i32, [vp, vp, vp, i32, i32, vp, vp]),
-    "dim_zoom_flow_fwd": (i32, [vp, vp, vp, vp, i32, i32, vp, vp, vp]),
+    "dim_zoom_flow_fwd": (i32, [vp, vp, vp, vp, i32, i32, i32, vp, vp, vp]),
     "dim_zoom_depth_fwd": (i32, [vp, vp, vp, vp, i32, vp, vp, vp]),
     "dim_zoom_trans_fwd": (i32, [vp, vp, vp, i32, i32, vp, vp]),
     "dim_zoom_trans_bwd": (i32, [vp, vp, vp, i32, i32, i32, vp, vp]),

@@ -148,10 +148,12 @@ class Context:
         _chk(flow, torch.float32, (B, 2, self.H, self.W), "flow")
         out = self._new(flow.shape)
         outw = None
+        fwc = 1
         if not b_inv_zoom and flow_weights is not None:
-            _chk(flow_weights, torch.float32, (B, 1, self.H, self.W), "flow_weights")
+            fwc = flow_weights.shape[1]  # 1, or 2 when tiled like batch_updater_py_multi.py:293-296
+            _chk(flow_weights, torch.float32, (B, fwc, self.H, self.W), "flow_weights")
             outw = self._new(flow_weights.shape)
-        check(lib.dim_zoom_flow_fwd(self._h, _p(zoom_factor), _p(flow), _p(flow_weights), B, int(b_inv_zoom), _p(out),
+        check(lib.dim_zoom_flow_fwd(self._h, _p(zoom_factor), _p(flow), _p(flow_weights), fwc, B, int(b_inv_zoom), _p(out),
                                     _p(outw), _stream()))
         return out, outw
 

@@ -124,7 +124,7 @@ class Trainer:
     def zoom_front(self, batch, K):
         """ZoomMask / ZoomImageWithFactor / ZoomFlow of get_train_symbol (deepIM_flownet.py:391-489) on device tensors."""
         ctx = self.ctx
-        zo, zg, zr, zf, _ = ctx.zoom_mask(batch["mask_observed"], batch["mask_gt_observed"], batch["mask_rendered"],
+        zo, zg, zr, zf, _, _ = ctx.zoom_mask(batch["mask_observed"], batch["mask_gt_observed"], batch["mask_rendered"],
                                           batch["src_pose"], K)
         zio, zir = ctx.zoom_image_with_factor(zf, batch["image_observed"], batch["image_rendered"], batch["pixel_means_rgb"])
         zfl, zfw = ctx.zoom_flow(zf, batch["flow"], batch["flow_weights"], False)

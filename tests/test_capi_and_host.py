@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(root):
     for s in syms:
         assert hasattr(lib, s), "symbol %s declared in the header but not exported" % s
     lib.dim_abi_version.restype = ctypes.c_int32
-    assert lib.dim_abi_version() == 1
+    assert lib.dim_abi_version() == 2
 
 
 def test_ctypes_binding_covers_the_header(root):
