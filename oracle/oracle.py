@@ -172,7 +172,8 @@ def zoom_flow(zoom_factor, flow, flow_weights=None, b_inv_zoom=False):
             s = zoom_plane(flow[b, c], aff, 0)
             out[b, c] = s * wx if b_inv_zoom else s / wx
         if outw is not None:
-            outw[b, 0] = zoom_plane(flow_weights[b, 0], aff, 5)
+            for c in range(flow_weights.shape[1]):  # 1 channel, or 2 when tiled (batch_updater_py_multi.py:293-296)
+                outw[b, c] = zoom_plane(flow_weights[b, c], aff, 5)
     return out, outw
 
 
