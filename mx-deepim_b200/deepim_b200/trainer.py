@@ -158,3 +158,52 @@ class Trainer:
         raw = np.empty((B, Hp, Wp, Cc), np.uint16)
         check(lib.dim_train_debug_tensor(ctx._h, tid, raw.ctypes.data_as(C.c_void_p), raw.nbytes))
         return (raw.astype(np.uint32) << 16).view(np.float32), (py, px, H, W)
+
+
+def make_device_batch(ctx, meshes, B, seed, K, pixel_means_rgb, num_points=3000):
+    """Synthetic training batch built with the device kernels only (config C4: rendered pairs, labels from
+    dim_train_update, INIT_MASK box_gt without dilation, 3000 sampled model points as get_point_cloud_model,
+    lib/utils/image.py:452-478).  Returns (batch dict of CUDA tensors, cls int32[B], tgt_pose f32[B,3,4], depth_gt)."""
+    from . import synth
+    obs, ini = synth.sample_pose_pairs(B, seed)
+    dev = ctx.device
+    cls_np = (np.arange(B) % len(meshes)).astype(np.int32)
+    cls = torch.from_numpy(cls_np).to(dev)
+    tgt = torch.from_numpy(obs.astype(np.float32)).to(dev)
+    src = torch.from_numpy(ini.astype(np.float32)).to(dev)
+    r = ctx.render(cls, tgt, K, pixel_means_rgb=pixel_means_rgb, trunc_u8=True)
+    ident = torch.tensor([[1.0, 0, 0, 0]] * B, dtype=torch.float32, device=dev)
+    upd = ctx.train_update(cls, src, ident, torch.zeros(B, 3, device=dev), tgt, r["depth"], K, pixel_means_rgb=pixel_means_rgb)
+    rng = np.random.default_rng(seed)
+    pts, pw = np.zeros((B, 3, num_points), np.float32), np.zeros((B, 3, num_points), np.float32)
+    for b in range(B):
+        v = meshes[cls_np[b]].verts
+        keep = rng.permutation(len(v))[:num_points]
+        pts[b, :, :len(keep)] = v[keep].T
+        pw[b, :, :len(keep)] = 1
+    pobs = np.stack([obs[b, :, :3].astype(np.float32) @ pts[b] + obs[b, :, 3:4].astype(np.float32) for b in range(B)]).astype(np.float32)
+    batch = {"image_observed": r["image"], "image_rendered": upd["image_rendered"], "mask_observed": ctx.update_mask_box(r["bbox"]),
+             "mask_gt_observed": r["mask"], "mask_rendered": upd["mask_rendered"], "src_pose": upd["src_pose"], "flow": upd["flow"],
+             "flow_weights": upd["flow_weights"], "point_cloud_model": torch.from_numpy(pts).to(dev),
+             "point_cloud_weights": torch.from_numpy(pw).to(dev), "point_cloud_observed": torch.from_numpy(pobs).to(dev),
+             "pixel_means_rgb": np.asarray(pixel_means_rgb, np.float32)}
+    return batch, cls, tgt, r["depth"]
+
+
+def fit_batch(trainer, batch, cls, tgt_pose, depth_gt, K, n_inner=4, dist=None):
+    """One data batch of Module.fit (deepim/core/module.py:1131-1137): n_inner x (forward_backward, update), the
+    batch re-rendered at the predicted pose in between (batchUpdaterPyMulti.forward -> Context.train_update).
+    Returns the objective of every inner iteration (device tensor [n_inner])."""
+    ctx = trainer.ctx
+    b = dict(batch)
+    objs = []
+    for it in range(n_inner):
+        z = trainer.zoom_front(b, K)
+        res = trainer.step(z, dist=dist)
+        objs.append(res["losses"][3])
+        if it != n_inner - 1:
+            upd = ctx.train_update(cls, b["src_pose"], res["rot_est_norm"], res["trans_est"], tgt_pose, depth_gt, K,
+                                   pixel_means_rgb=batch["pixel_means_rgb"])
+            for k in ("image_rendered", "mask_rendered", "src_pose", "flow", "flow_weights"):
+                b[k] = upd[k]
+    return torch.stack(objs)
