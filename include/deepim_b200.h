@@ -250,7 +250,9 @@ DIM_API int32_t dim_profile_read(dim_ctx *ctx, float *ms4, int32_t *iterations);
  * returned by dim_train_param_info (flow_conv1 ... conv6_1, fc6, fc7, rot, trans, Convolution1, deconv5,
  * upsample_flow6to5, Convolution2, deconv4, upsample_flow5to4, Convolution3, mask_conv3) weight then bias,
  * followed by the frozen bilinear upsampling_weight (2,1,32,32) and mask_upsampling_weight (1,1,32,32):
- * 57 749 164 floats.  Gradients use the same layout (that is the buffer a data-parallel caller all-reduces
+ * 57 749 164 floats.  One tensor is permuted: fc6_weight is stored (256, h*10+w, c) -- the NHWC order of the
+ * conv6_1 activation it multiplies -- instead of MXNet's (256, c*80 + h*10 + w) (the Python host permutes on
+ * load / get; element-wise consumers such as the all-reduce and SGD do not care).  Gradients use the same layout (that is the buffer a data-parallel caller all-reduces
  * with NCCL between dim_train_forward_backward and dim_train_sgd_update; kvstore replacement,
  * deepim/core/module.py:616-635). */
 DIM_API int32_t dim_train_create(dim_ctx *ctx, int32_t max_points);

@@ -83,7 +83,8 @@ struct TrainState {
   float *loss_part = nullptr;    // [3][LOSS_BLOCKS]
   float *h6 = nullptr, *h7 = nullptr, *rot_raw = nullptr, *ztrans = nullptr, *rot_n = nullptr, *trans_est = nullptr;
   float *pts_est = nullptr, *dpts = nullptr, *drot_n = nullptr, *dtrans = nullptr, *drot = nullptr, *dh7 = nullptr, *dh6 = nullptr;
-  float *bias_part = nullptr;    // [64][1088]
+  float *bias_part = nullptr;    // [<= BIAS_CHUNKS][1088]
+  float *thin_part = nullptr;    // [THIN_CHUNKS][2][1026*9]
   float *wg_partial = nullptr;
   size_t wg_partial_elems = 0;
   // bf16 operand packs
@@ -94,7 +95,8 @@ struct TrainState {
 };
 
 static constexpr int LOSS_BLOCKS = 1024;
-static constexpr int BIAS_CHUNKS = 64;
+static constexpr int THIN_CHUNKS = 64;
+static constexpr int BIAS_CHUNKS = 1024;  // upper bound; the launch uses min(1024, npix / 64) chunks
 
 // ---------------------------------------------------------------------------------- small kernels
 __global__ void __launch_bounds__(256) strip_to_nhwc32_kernel(const __nv_bfloat16 *src, __nv_bfloat16 *dst, size_t n_chunks,
@@ -168,31 +170,54 @@ __global__ void __launch_bounds__(256) thin_conv_fwd_kernel(const __nv_bfloat16 
   }
 }
 
-// weight gradient: one thread per (ci, tap), loops over the pixels; bias gradient by block 0
+// weight gradient, stage 1: thread (ci, tap) x pixel chunk blockIdx.y -> part[chunk][co][ci*9 + tap]
 template <int CO>
 __global__ void __launch_bounds__(256) thin_conv_wgrad_kernel(const __nv_bfloat16 *x, int Hp, int Wp, int cs, int Cin, int B, int H,
-                                                              int W, const float *dy, float *dw, float *db) {
+                                                              int W, const float *dy, float *part) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < Cin * 9) {
-    const int ci = i % Cin, tap = i / Cin, ky = tap / 3, kx = tap % 3;
-    float acc[CO];
+  if (i >= Cin * 9) return;
+  const int ci = i % Cin, tap = i / Cin, ky = tap / 3, kx = tap % 3;
+  const int npix = B * H * W, per = (npix + gridDim.y - 1) / gridDim.y;
+  const int p0 = blockIdx.y * per, p1 = min(npix, p0 + per);
+  float acc[CO];
 #pragma unroll
-    for (int co = 0; co < CO; ++co) acc[co] = 0.f;
-    for (int b = 0; b < B; ++b)
-      for (int yy = 0; yy < H; ++yy)
-        for (int xx = 0; xx < W; ++xx) {
-          const float v = __bfloat162float(x[(((size_t)b * Hp + yy + ky) * Wp + xx + kx) * cs + ci]);
-          const float *d = dy + ((size_t)(b * H + yy) * W + xx) * CO;
+  for (int co = 0; co < CO; ++co) acc[co] = 0.f;
+  int xx = p0 % W, yy = (p0 / W) % H, b = p0 / (W * H);
+  for (int p = p0; p < p1; ++p) {
+    const float v = __bfloat162float(x[(((size_t)b * Hp + yy + ky) * Wp + xx + kx) * cs + ci]);
+    const float *d = dy + (size_t)p * CO;
 #pragma unroll
-          for (int co = 0; co < CO; ++co) acc[co] = fmaf(v, d[co], acc[co]);
-        }
-#pragma unroll
-    for (int co = 0; co < CO; ++co) dw[((size_t)(co * Cin + ci) * 3 + ky) * 3 + kx] = acc[co];
+    for (int co = 0; co < CO; ++co) acc[co] = fmaf(v, d[co], acc[co]);
+    if (++xx == W) { xx = 0; if (++yy == H) { yy = 0; ++b; } }
   }
-  if (blockIdx.x == 0 && threadIdx.x < CO) {
+#pragma unroll
+  for (int co = 0; co < CO; ++co) part[((size_t)blockIdx.y * CO + co) * Cin * 9 + i] = acc[co];
+}
+// stage 2: fixed-order sum over the chunks, MXNet layout (co, ci, ky, kx); bias gradient by the last block
+template <int CO>
+__global__ void __launch_bounds__(256) thin_conv_wgrad_final_kernel(const float *part, int chunks, int Cin, const float *dy, int npix,
+                                                                    float *dw, float *db) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < CO * Cin * 9) {
+    const int co = i / (Cin * 9), r = i % (Cin * 9), ci = r % Cin, tap = r / Cin;
     float a = 0.f;
-    for (int p = 0; p < B * H * W; ++p) a += dy[(size_t)p * CO + threadIdx.x];
-    db[threadIdx.x] = a;
+    for (int c = 0; c < chunks; ++c) a += part[((size_t)c * CO + co) * Cin * 9 + r];
+    dw[(size_t)(co * Cin + ci) * 9 + tap] = a;
+  }
+  if (blockIdx.x == gridDim.x - 1) {
+    __shared__ float red[256];
+    for (int co = 0; co < CO; ++co) {
+      float a = 0.f;
+      for (int p = threadIdx.x; p < npix; p += 256) a += dy[(size_t)p * CO + co];
+      red[threadIdx.x] = a;
+      __syncthreads();
+      for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) db[co] = red[0];
+      __syncthreads();
+    }
   }
 }
 
@@ -245,42 +270,48 @@ __global__ void __launch_bounds__(256) thin_deconv_fwd_kernel(const float *in, i
   out[(((size_t)b * Hp + oy + py) * Wp + ox + px) * cs + coff + co] = __float2bfloat16_rn(acc);
 }
 
-// backward of the thin deconvolution: din (one thread per input pixel x ci), dw (32 threads), db (2 threads)
+// backward of the thin deconvolution: din (one thread per input pixel x ci)
+__device__ __forceinline__ float thin_dY(const __nv_bfloat16 *dout, int Hp, int Wp, int py, int px, int cs, int coff, int Ho, int Wo,
+                                         int b, int oy, int ox, int co) {
+  if (oy < 0 || oy >= Ho || ox < 0 || ox >= Wo) return 0.f;
+  return __bfloat162float(dout[(((size_t)b * Hp + oy + py) * Wp + ox + px) * cs + coff + co]);
+}
 __global__ void __launch_bounds__(256) thin_deconv_bwd_kernel(const float *in, int B, int Hi, int Wi, const float *w,
                                                               const __nv_bfloat16 *dout, int Hp, int Wp, int py, int px, int cs,
-                                                              int coff, int Ho, int Wo, float *din, float *dw, float *db) {
+                                                              int coff, int Ho, int Wo, float *din) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  auto dY = [&](int b, int oy, int ox, int co) -> float {
-    if (oy < 0 || oy >= Ho || ox < 0 || ox >= Wo) return 0.f;
-    return __bfloat162float(dout[(((size_t)b * Hp + oy + py) * Wp + ox + px) * cs + coff + co]);
-  };
-  if (i < B * Hi * Wi * 2) {
-    const int ci = i & 1, ix = (i >> 1) % Wi, iy = ((i >> 1) / Wi) % Hi, b = (i >> 1) / (Wi * Hi);
-    float acc = 0.f;
-    for (int ky = 0; ky < 4; ++ky)
-      for (int kx = 0; kx < 4; ++kx)
-        for (int co = 0; co < 2; ++co)
-          acc = fmaf(dY(b, 2 * iy + ky - 1, 2 * ix + kx - 1, co), w[((ci * 2 + co) * 4 + ky) * 4 + kx], acc);
-    din[i] = acc;
-  }
-  if (blockIdx.x == 0 && threadIdx.x < 64) {
-    const int t = threadIdx.x;
+  if (i >= B * Hi * Wi * 2) return;
+  const int ci = i & 1, ix = (i >> 1) % Wi, iy = ((i >> 1) / Wi) % Hi, b = (i >> 1) / (Wi * Hi);
+  float acc = 0.f;
+  for (int ky = 0; ky < 4; ++ky)
+    for (int kx = 0; kx < 4; ++kx)
+      for (int co = 0; co < 2; ++co)
+        acc = fmaf(thin_dY(dout, Hp, Wp, py, px, cs, coff, Ho, Wo, b, 2 * iy + ky - 1, 2 * ix + kx - 1, co),
+                   w[((ci * 2 + co) * 4 + ky) * 4 + kx], acc);
+  din[i] = acc;
+}
+// dw (64 values) and db (2 values): one warp per output, lanes stride over the pixels (fixed order -> deterministic)
+__global__ void __launch_bounds__(256) thin_deconv_wgrad_kernel(const float *in, int B, int Hi, int Wi, const __nv_bfloat16 *dout, int Hp,
+                                                                int Wp, int py, int px, int cs, int coff, int Ho, int Wo, float *dw,
+                                                                float *db) {
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (t >= 66) return;
+  float acc = 0.f;
+  if (t < 64) {
     const int kx = t & 3, ky = (t >> 2) & 3, co = (t >> 4) & 1, ci = t >> 5;
-    float acc = 0.f;
-    for (int b = 0; b < B; ++b)
-      for (int iy = 0; iy < Hi; ++iy)
-        for (int ix = 0; ix < Wi; ++ix)
-          acc = fmaf(in[((size_t)(b * Hi + iy) * Wi + ix) * 2 + ci], dY(b, 2 * iy + ky - 1, 2 * ix + kx - 1, co), acc);
-    dw[t] = acc;  // ((ci*2+co)*4+ky)*4+kx == t
+    for (int p = lane; p < B * Hi * Wi; p += 32) {
+      const int ix = p % Wi, iy = (p / Wi) % Hi, b = p / (Wi * Hi);
+      acc = fmaf(in[(size_t)p * 2 + ci], thin_dY(dout, Hp, Wp, py, px, cs, coff, Ho, Wo, b, 2 * iy + ky - 1, 2 * ix + kx - 1, co), acc);
+    }
+  } else {
+    const int co = t - 64;
+    for (int p = lane; p < B * Ho * Wo; p += 32) {
+      const int ox = p % Wo, oy = (p / Wo) % Ho, b = p / (Wo * Ho);
+      acc += thin_dY(dout, Hp, Wp, py, px, cs, coff, Ho, Wo, b, oy, ox, co);
+    }
   }
-  if (blockIdx.x == 0 && threadIdx.x >= 64 && threadIdx.x < 66) {
-    const int co = threadIdx.x - 64;
-    float acc = 0.f;
-    for (int b = 0; b < B; ++b)
-      for (int oy = 0; oy < Ho; ++oy)
-        for (int ox = 0; ox < Wo; ++ox) acc += dY(b, oy, ox, co);
-    db[co] = acc;
-  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) { if (t < 64) dw[t] = acc; else db[t - 64] = acc; }
 }
 
 // ---- full-resolution heads: fixed bilinear Deconvolution k32 s16 (+ Crop offset 8), flow loss, mask loss
@@ -451,14 +482,22 @@ __global__ void __launch_bounds__(256) fc_wgrad_kernel(const float *dy, const fl
   }
 }
 
-// fc6 weight gradient in the reference layout (256, c*80 + hw) from the NHWC activation (hw*1024 + c)
+// fc6 weight gradient; the flat vector keeps fc6_weight as (256, h*10+w, c) -- the NHWC order of ReLU10 -- so both the
+// activation reads and the gradient writes are coalesced (the host API permutes to MXNet's (256, c*80+hw) on load / get)
 __global__ void __launch_bounds__(256) fc6_wgrad_kernel(const float *dh6, const __nv_bfloat16 *a10, int B, float *dw) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)256 * 81920) return;
-  const int o = (int)(i / 81920), kr = (int)(i % 81920), c = kr / 80, hw = kr % 80;
-  float a = 0.f;
-  for (int b = 0; b < B; ++b) a = fmaf(dh6[b * 256 + o], __bfloat162float(a10[(size_t)b * 81920 + hw * 1024 + c]), a);
-  dw[i] = a;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over 81920 / 2 pairs of k
+  if (i >= 81920 / 2) return;
+  float2 a[16];
+#pragma unroll
+  for (int b = 0; b < 16; ++b)
+    if (b < B) a[b] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(a10 + (size_t)b * 81920 + 2 * i));
+  for (int o = blockIdx.y * 32; o < blockIdx.y * 32 + 32; ++o) {
+    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int b = 0; b < 16; ++b)
+      if (b < B) { const float d = dh6[b * 256 + o]; acc.x = fmaf(d, a[b].x, acc.x); acc.y = fmaf(d, a[b].y, acc.y); }
+    *reinterpret_cast<float2 *>(dw + (size_t)o * 81920 + 2 * i) = acc;
+  }
 }
 // fc6 data gradient, added to the bf16 partial gradient of ReLU10 ([B][80][1024])
 __global__ void __launch_bounds__(256) fc6_dgrad_kernel(const float *dh6, const __nv_bfloat16 *w_hi /*[256][81920] packed*/, int B,
@@ -468,6 +507,7 @@ __global__ void __launch_bounds__(256) fc6_dgrad_kernel(const float *dh6, const 
   float acc[16];
 #pragma unroll
   for (int b = 0; b < 16; ++b) acc[b] = 0.f;
+#pragma unroll 8
   for (int o = 0; o < 256; ++o) {
     const float w = __bfloat162float(w_hi[(size_t)o * 81920 + k]);
 #pragma unroll
@@ -484,7 +524,7 @@ __global__ void __launch_bounds__(256) fc6_dgrad_kernel(const float *dh6, const 
 __global__ void __launch_bounds__(256) bias_partial_kernel(const __nv_bfloat16 *g, size_t npix, int cs, int coff, int C, float *part) {
   const int c = blockIdx.x * 64 + (threadIdx.x & 63), lanep = threadIdx.x >> 6, chunk = blockIdx.y;
   __shared__ float red[4][64];
-  const size_t per = (npix + BIAS_CHUNKS - 1) / BIAS_CHUNKS;
+  const size_t per = (npix + gridDim.y - 1) / gridDim.y;
   const size_t p0 = (size_t)chunk * per, p1 = p0 + per < npix ? p0 + per : npix;
   float a = 0.f;
   if (c < C)
@@ -494,20 +534,29 @@ __global__ void __launch_bounds__(256) bias_partial_kernel(const __nv_bfloat16 *
   if (threadIdx.x < 64 && c < C)
     part[(size_t)chunk * 1088 + c] = (red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]);
 }
-__global__ void bias_final_kernel(const float *part, int C, float *db) {
+__global__ void bias_final_kernel(const float *part, int chunks, int C, float *db) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float a = 0.f;
-  for (int k = 0; k < BIAS_CHUNKS; ++k) a += part[(size_t)k * 1088 + c];
+  for (int k = 0; k < chunks; ++k) a += part[(size_t)k * 1088 + c];
   db[c] = a;
 }
 
 // MXNet SGD with momentum (train.py:296-304): mom = m*mom - lr*(rescale*g + wd*w); w += mom
-__global__ void __launch_bounds__(256) sgd_kernel(float *w, float *mom, const float *g, size_t n, float lr, float momentum, float wd,
-                                                  float rescale) {
+// One launch over the flat vector: seg_end[s] = end offset of segment s (weight, bias, weight, bias, ...; 44 segments
+// cover the 22 trainable tensors), even segments are weights (weight decay applies), odd ones biases (wd_mult = 0).
+struct SgdSegs { unsigned long long end[44]; };
+__global__ void __launch_bounds__(256) sgd_kernel(float *w, float *mom, const float *g, size_t n, const __grid_constant__ SgdSegs segs,
+                                                  float lr, float momentum, float wd, float rescale) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float m = momentum * mom[i] - lr * (rescale * g[i] + wd * w[i]);
+  int lo = 0, hi = 43;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (i < segs.end[mid]) hi = mid; else lo = mid + 1;
+  }
+  const float wdv = (lo & 1) ? 0.f : wd;
+  const float m = momentum * mom[i] - lr * (rescale * g[i] + wdv * w[i]);
   mom[i] = m;
   w[i] += m;
 }
@@ -558,12 +607,11 @@ __global__ void __launch_bounds__(256) pack_deconv_dgrad_kernel(const float *w, 
   const int co = (int)(i % Cout), tap = (int)((i / Cout) % 16), ci = (int)(i / ((size_t)Cout * 16));
   dst[i] = __float2bfloat16_rn(ci < Cin ? w[((size_t)(ci * Cout + co) * 4 + tap / 4) * 4 + tap % 4] : 0.f);
 }
-// fc6 (out, c*80+hw) -> (out, hw*1024+c) hi/lo
+// fc6 master (out, hw, c) fp32 -> bf16 hi/lo operand (same order)
 __global__ void __launch_bounds__(256) pack_fc6_kernel(const float *w, __nv_bfloat16 *hi, __nv_bfloat16 *lo) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)256 * 81920) return;
-  const int o = (int)(i / 81920), kp = (int)(i % 81920), hw = kp / 1024, c = kp % 1024;
-  store_split(hi, lo, i, w[(size_t)o * 81920 + c * 80 + hw]);
+  store_split(hi, lo, i, w[i]);
 }
 __global__ void transpose256_kernel(const float *w, float *wT) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -634,6 +682,7 @@ int train_create(dim_ctx *ctx, int max_points) {
   rc |= dev_alloc(ctx, &ts->pts_est, (size_t)B * 3 * max_points, true);
   rc |= dev_alloc(ctx, &ts->dpts, (size_t)B * 3 * max_points, true);
   rc |= dev_alloc(ctx, &ts->bias_part, (size_t)BIAS_CHUNKS * 1088, true);
+  rc |= dev_alloc(ctx, &ts->thin_part, (size_t)THIN_CHUNKS * 2 * 1026 * 9, true);
   // operand packs
   for (int i = 1; i < 10; ++i) {
     const LayerSpec &s = kLayers[i];
@@ -908,9 +957,34 @@ static int run_wgrad(const WgradParams &p, int BN, int kind, int D0, int D1, int
 
 static int bias_grad(TrainState *ts, const Buf &g, int B, int coff, int C, float *db, cudaStream_t st) {
   const size_t npix = (size_t)B * g.Hp * g.Wp;
-  bias_partial_kernel<<<dim3(cdiv(C, 64), BIAS_CHUNKS), 256, 0, st>>>(g.p, npix, g.C, coff, C, ts->bias_part);
+  int chunks = (int)(npix / 64);
+  chunks = chunks < 1 ? 1 : (chunks > BIAS_CHUNKS ? BIAS_CHUNKS : chunks);
+  bias_partial_kernel<<<dim3(cdiv(C, 64), chunks), 256, 0, st>>>(g.p, npix, g.C, coff, C, ts->bias_part);
   DIM_LAUNCH_CHECK();
-  bias_final_kernel<<<cdiv(C, 256), 256, 0, st>>>(ts->bias_part, C, db);
+  bias_final_kernel<<<cdiv(C, 256), 256, 0, st>>>(ts->bias_part, chunks, C, db);
+  DIM_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int CO>
+static int thin_wgrad(TrainState *ts, const Buf &x, int Cin, int B, int H, int W, const float *dy, float *dw, float *db, cudaStream_t st) {
+  const int npix = B * H * W;
+  int chunks = npix / 32;
+  chunks = chunks < 1 ? 1 : (chunks > THIN_CHUNKS ? THIN_CHUNKS : chunks);
+  thin_conv_wgrad_kernel<CO><<<dim3(cdiv(Cin * 9, 256), chunks), 256, 0, st>>>(x.p, x.Hp, x.Wp, x.C, Cin, B, H, W, dy, ts->thin_part);
+  DIM_LAUNCH_CHECK();
+  thin_conv_wgrad_final_kernel<CO><<<cdiv(CO * Cin * 9, 256) + 1, 256, 0, st>>>(ts->thin_part, chunks, Cin, dy, npix, dw, db);
+  DIM_LAUNCH_CHECK();
+  return 0;
+}
+
+static int thin_deconv_bwd(const float *in, int B, int Hi, int Wi, const float *w, const Buf &dout, int coff, int Ho, int Wo, float *din,
+                           float *dw, float *db, cudaStream_t st) {
+  thin_deconv_bwd_kernel<<<cdiv(B * Hi * Wi * 2, 256), 256, 0, st>>>(in, B, Hi, Wi, w, dout.p, dout.Hp, dout.Wp, dout.py, dout.px, dout.C,
+                                                                      coff, Ho, Wo, din);
+  DIM_LAUNCH_CHECK();
+  thin_deconv_wgrad_kernel<<<cdiv(66 * 32, 256), 256, 0, st>>>(in, B, Hi, Wi, dout.p, dout.Hp, dout.Wp, dout.py, dout.px, dout.C, coff, Ho,
+                                                                Wo, dw, db);
   DIM_LAUNCH_CHECK();
   return 0;
 }
@@ -1086,24 +1160,23 @@ int train_forward_backward(dim_ctx *ctx, const TrainIO &io, cudaStream_t st) {
   LAUNCH1D(fc_wgrad_kernel, 4 * 256, st, ts->drot, ts->h7, B, 4, 256, G + ts->off[P_ROT].w, G + ts->off[P_ROT].b);
   LAUNCH1D(fc_wgrad_kernel, 3 * 256, st, ts->dtrans, ts->h7, B, 3, 256, G + ts->off[P_TRANS].w, G + ts->off[P_TRANS].b);
   LAUNCH1D(fc_wgrad_kernel, 256 * 256, st, ts->dh7, ts->h6, B, 256, 256, G + ts->off[P_FC7].w, G + ts->off[P_FC7].b);
-  LAUNCH1D(fc6_wgrad_kernel, (size_t)256 * 81920, st, ts->dh6, ns->act_hi[10], B, G + ts->off[P_FC6].w);
+  fc6_wgrad_kernel<<<dim3(81920 / 2 / 256, 8), 256, 0, st>>>(ts->dh6, ns->act_hi[10], B, G + ts->off[P_FC6].w);
+  DIM_LAUNCH_CHECK();
   LAUNCH1D(fc_wgrad_kernel, 256, st, ts->dh6, ts->h6 /*unused for K=0*/, B, 256, 0, G + ts->off[P_FC6].w /*no write*/, G + ts->off[P_FC6].b);
   // full-resolution heads -> 1/16 maps
   LAUNCH1D(upsample_bwd_kernel, (size_t)B * h4 * w4 * 3 * 32, st, ts->dfull, M + ts->off[P_UPS].w, M + ts->off[P_MUPS].w, B, H, W, h4, w4,
            ts->dflow4, ts->dmask4);
   // Convolution3 / mask_conv3
-  LAUNCH1D(thin_conv_wgrad_kernel<2>, 770 * 9, st, ts->cat3.p, ts->cat3.Hp, ts->cat3.Wp, 832, 770, B, h4, w4, ts->dflow4,
-           G + ts->off[P_CONV3D].w, G + ts->off[P_CONV3D].b);
-  LAUNCH1D(thin_conv_wgrad_kernel<1>, 770 * 9, st, ts->cat3.p, ts->cat3.Hp, ts->cat3.Wp, 832, 770, B, h4, w4, ts->dmask4,
-           G + ts->off[P_MASK3].w, G + ts->off[P_MASK3].b);
+  if (int rc = thin_wgrad<2>(ts, ts->cat3, 770, B, h4, w4, ts->dflow4, G + ts->off[P_CONV3D].w, G + ts->off[P_CONV3D].b, st)) return rc;
+  if (int rc = thin_wgrad<1>(ts, ts->cat3, 770, B, h4, w4, ts->dmask4, G + ts->off[P_MASK3].w, G + ts->off[P_MASK3].b, st)) return rc;
   LAUNCH1D(thin_conv_dgrad_kernel<2>, (size_t)B * h4 * w4 * 832, st, ts->dflow4, M + ts->off[P_CONV3D].w, 770, B, h4, w4, ts->dcat3.p,
            ts->dcat3.Hp, ts->dcat3.Wp, 1, 1, 832, 832, 0);
   LAUNCH1D(thin_conv_dgrad_kernel<1>, (size_t)B * h4 * w4 * 832, st, ts->dmask4, M + ts->off[P_MASK3].w, 770, B, h4, w4, ts->dcat3.p,
            ts->dcat3.Hp, ts->dcat3.Wp, 1, 1, 832, 832, 1);
   // upsample_flow5to4
-  LAUNCH1D(thin_deconv_bwd_kernel, (size_t)B * h5 * w5 * 2 > 256 ? (size_t)B * h5 * w5 * 2 : 256, st, ts->flow5, B, h5, w5,
-           M + ts->off[P_UP54].w, ts->dcat3.p, ts->dcat3.Hp, ts->dcat3.Wp, 1, 1, 832, 768, h4, w4, ts->dflow5, G + ts->off[P_UP54].w,
-           G + ts->off[P_UP54].b);
+  if (int rc = thin_deconv_bwd(ts->flow5, B, h5, w5, M + ts->off[P_UP54].w, ts->dcat3, 768, h4, w4, ts->dflow5, G + ts->off[P_UP54].w,
+                               G + ts->off[P_UP54].b, st))
+    return rc;
   // deconv4: LeakyReLU backward on its slice, bias, weight and data gradients
   LAUNCH1D(lrelu_mask_inplace_kernel, (size_t)B * h4 * w4 * 32, st, ts->dcat3.p, ts->cat3.p, ts->cat3.Hp, ts->cat3.Wp, 1, 1, 832, 512, B, h4,
            w4, 256, 0.1f);
@@ -1111,21 +1184,19 @@ int train_forward_backward(dim_ctx *ctx, const TrainIO &io, cudaStream_t st) {
   if (int rc = run_wgrad(tm.wg_deconv4, tm.wg_bn_d4, WG_DECONV, 1026, 256, 4, G + ts->off[P_DECONV4].w, st)) return rc;
   if (int rc = run_generic(ctx, tm.deconv4_dgrad, tm.g_deconv4_dgrad, B, st)) return rc;
   // Convolution2 (adds to dcat2), upsample_flow6to5
-  LAUNCH1D(thin_conv_wgrad_kernel<2>, 1026 * 9, st, ts->cat2.p, ts->cat2.Hp, ts->cat2.Wp, 1088, 1026, B, h5, w5, ts->dflow5,
-           G + ts->off[P_CONV2D].w, G + ts->off[P_CONV2D].b);
+  if (int rc = thin_wgrad<2>(ts, ts->cat2, 1026, B, h5, w5, ts->dflow5, G + ts->off[P_CONV2D].w, G + ts->off[P_CONV2D].b, st)) return rc;
   LAUNCH1D(thin_conv_dgrad_kernel<2>, (size_t)B * h5 * w5 * 1088, st, ts->dflow5, M + ts->off[P_CONV2D].w, 1026, B, h5, w5, ts->dcat2.p,
            ts->dcat2.Hp, ts->dcat2.Wp, 1, 1, 1088, 1088, 1);
-  LAUNCH1D(thin_deconv_bwd_kernel, (size_t)B * h6 * w6 * 2 > 256 ? (size_t)B * h6 * w6 * 2 : 256, st, ts->flow6, B, h6, w6,
-           M + ts->off[P_UP65].w, ts->dcat2.p, ts->dcat2.Hp, ts->dcat2.Wp, 1, 1, 1088, 1024, h5, w5, ts->dflow6, G + ts->off[P_UP65].w,
-           G + ts->off[P_UP65].b);
+  if (int rc = thin_deconv_bwd(ts->flow6, B, h6, w6, M + ts->off[P_UP65].w, ts->dcat2, 1024, h5, w5, ts->dflow6, G + ts->off[P_UP65].w,
+                               G + ts->off[P_UP65].b, st))
+    return rc;
   // deconv5
   LAUNCH1D(lrelu_mask_inplace_kernel, (size_t)B * h5 * w5 * 64, st, ts->dcat2.p, ts->cat2.p, ts->cat2.Hp, ts->cat2.Wp, 1, 1, 1088, 512, B, h5,
            w5, 512, 0.1f);
   if (int rc = bias_grad(ts, ts->dcat2, B, 512, 512, G + ts->off[P_DECONV5].b, st)) return rc;
   if (int rc = run_wgrad(tm.wg_deconv5, tm.wg_bn_d5, WG_DECONV, 1024, 512, 4, G + ts->off[P_DECONV5].w, st)) return rc;
   // Convolution1 -> partial gradient of ReLU10, + fc6 data gradient, then deconv5's data gradient closes dZ of conv6_1
-  LAUNCH1D(thin_conv_wgrad_kernel<2>, 1024 * 9, st, ts->act10b.p, ts->act10b.Hp, ts->act10b.Wp, 1024, 1024, B, h6, w6, ts->dflow6,
-           G + ts->off[P_CONV1D].w, G + ts->off[P_CONV1D].b);
+  if (int rc = thin_wgrad<2>(ts, ts->act10b, 1024, B, h6, w6, ts->dflow6, G + ts->off[P_CONV1D].w, G + ts->off[P_CONV1D].b, st)) return rc;
   LAUNCH1D(thin_conv_dgrad_kernel<2>, (size_t)B * h6 * w6 * 1024, st, ts->dflow6, M + ts->off[P_CONV1D].w, 1024, B, h6, w6, ts->dA10p.p,
            ts->dA10p.Hp, ts->dA10p.Wp, 0, 0, 1024, 1024, 0);
   LAUNCH1D(fc6_dgrad_kernel, 81920, st, ts->dh6, ns->fc6_w_hi, B, ts->dA10p.p);
@@ -1147,12 +1218,13 @@ int train_forward_backward(dim_ctx *ctx, const TrainIO &io, cudaStream_t st) {
 int train_sgd_update(dim_ctx *ctx, const float *grads, float lr, float momentum, float wd, float rescale, cudaStream_t st) {
   TrainState *ts = train_of(ctx);
   DIM_REQUIRE(ts != nullptr && grads != nullptr, "dim_train_sgd_update: bad state");
-  for (int i = 0; i < 22; ++i) {  // the two bilinear upsampling kernels are frozen (lr_mult 0, deepIM_flownet.py:193,333)
-    LAUNCH1D(sgd_kernel, ts->off[i].wn, st, ts->master + ts->off[i].w, ts->mom + ts->off[i].w, grads + ts->off[i].w, ts->off[i].wn, lr,
-             momentum, wd, rescale);
-    LAUNCH1D(sgd_kernel, ts->off[i].bn, st, ts->master + ts->off[i].b, ts->mom + ts->off[i].b, grads + ts->off[i].b, ts->off[i].bn, lr,
-             momentum, 0.f, rescale);  // wd_mult = 0 for biases
+  SgdSegs segs;
+  for (int i = 0; i < 22; ++i) {
+    segs.end[2 * i] = ts->off[i].w + ts->off[i].wn;
+    segs.end[2 * i + 1] = ts->off[i].b + ts->off[i].bn;
   }
+  const size_t n = ts->off[21].b + ts->off[21].bn;  // the two bilinear upsampling kernels behind it are frozen (lr_mult 0)
+  LAUNCH1D(sgd_kernel, n, st, ts->master, ts->mom, grads, n, segs, lr, momentum, wd, rescale);
   return repack_all(ctx, st);
 }
 

@@ -34,7 +34,10 @@ def param_table():
 def flatten_params(weights: dict) -> np.ndarray:
     parts = []
     for name, n in param_table():
-        a = np.ascontiguousarray(weights[name], dtype=np.float32).reshape(-1)
+        a = np.asarray(weights[name], dtype=np.float32)
+        if name == "fc6_weight":  # the flat vector keeps fc6 as (out, h*10+w, c): NHWC order of the conv6_1 activation
+            a = a.reshape(256, 1024, 80).transpose(0, 2, 1)
+        a = np.ascontiguousarray(a).reshape(-1)
         if a.size != n:
             raise ValueError("%s: expected %d values, got %d" % (name, n, a.size))
         parts.append(a)
@@ -44,7 +47,10 @@ def flatten_params(weights: dict) -> np.ndarray:
 def unflatten_params(flat: np.ndarray, like: dict) -> dict:
     out, off = {}, 0
     for name, n in param_table():
-        out[name] = np.asarray(flat[off:off + n], np.float32).reshape(like[name].shape).copy()
+        a = np.asarray(flat[off:off + n], np.float32)
+        if name == "fc6_weight":  # back to MXNet's (out, c*80 + h*10 + w) (deepIM_flownet.py:110-112)
+            a = a.reshape(256, 80, 1024).transpose(0, 2, 1)
+        out[name] = np.ascontiguousarray(a).reshape(like[name].shape).copy()
         off += n
     return out
 
