@@ -92,11 +92,15 @@ struct TrainState {
   __nv_bfloat16 *d5_fwd[4] = {}, *d4_fwd[4] = {}, *d5_dg = nullptr, *d4_dg = nullptr;
   std::map<int, TrainMaps> maps;
   int max_points = 0;
+  // internal streams: [0..2] run parity classes 1..3 next to class 0 on the caller's stream; [3] runs the weight / bias
+  // gradients next to the data-gradient chain (both only read the dZ buffers)
+  cudaStream_t side[4] = {};
+  cudaEvent_t ev_fork = nullptr, ev_cls[3] = {}, ev_side = nullptr;
 };
 
 static constexpr int LOSS_BLOCKS = 1024;
 static constexpr int THIN_CHUNKS = 64;
-static constexpr int BIAS_CHUNKS = 1024;  // upper bound; the launch uses min(1024, npix / 64) chunks
+static constexpr int BIAS_CHUNKS = 256;  // upper bound; the launch uses min(256, npix / 64) chunks
 
 // ---------------------------------------------------------------------------------- small kernels
 __global__ void __launch_bounds__(256) strip_to_nhwc32_kernel(const __nv_bfloat16 *src, __nv_bfloat16 *dst, size_t n_chunks,
@@ -699,11 +703,21 @@ int train_create(dim_ctx *ctx, int max_points) {
   rc |= dev_alloc(ctx, &ts->wg_partial, ts->wg_partial_elems, false);
   ns->save_h6 = ts->h6;
   ns->save_h7 = ts->h7;
+  for (int i = 0; i < 4; ++i) DIM_CHECK(cudaStreamCreateWithFlags(&ts->side[i], cudaStreamNonBlocking));
+  DIM_CHECK(cudaEventCreateWithFlags(&ts->ev_fork, cudaEventDisableTiming));
+  DIM_CHECK(cudaEventCreateWithFlags(&ts->ev_side, cudaEventDisableTiming));
+  for (int i = 0; i < 3; ++i) DIM_CHECK(cudaEventCreateWithFlags(&ts->ev_cls[i], cudaEventDisableTiming));
   return rc;
 }
 
 void train_destroy(dim_ctx *ctx) {
   TrainState *&ts = train_of(ctx);
+  if (ts) {
+    for (int i = 0; i < 4; ++i) if (ts->side[i]) cudaStreamDestroy(ts->side[i]);
+    if (ts->ev_fork) cudaEventDestroy(ts->ev_fork);
+    if (ts->ev_side) cudaEventDestroy(ts->ev_side);
+    for (int i = 0; i < 3; ++i) if (ts->ev_cls[i]) cudaEventDestroy(ts->ev_cls[i]);
+  }
   delete ts;
   ts = nullptr;
 }
@@ -1082,6 +1096,26 @@ static int copy_interior(const Buf &src, Buf &dst, int dcoff, int B, int C, cuda
   return 0;
 }
 
+// the parity classes of one layer write disjoint pixels: class 0 on the caller's stream, 1..3 on internal streams
+static int run_classes(dim_ctx *ctx, TrainState *ts, const ConvKParams *kp, const LayerGeom *g, int n, int B, cudaStream_t st) {
+  if (n == 1) return run_generic(ctx, kp[0], g[0], B, st);
+  DIM_CHECK(cudaEventRecord(ts->ev_fork, st));
+  for (int c = 1; c < n; ++c) {
+    DIM_CHECK(cudaStreamWaitEvent(ts->side[c - 1], ts->ev_fork, 0));
+    if (int rc = run_generic(ctx, kp[c], g[c], B, ts->side[c - 1])) return rc;
+    DIM_CHECK(cudaEventRecord(ts->ev_cls[c - 1], ts->side[c - 1]));
+  }
+  if (int rc = run_generic(ctx, kp[0], g[0], B, st)) return rc;
+  for (int c = 1; c < n; ++c) DIM_CHECK(cudaStreamWaitEvent(st, ts->ev_cls[c - 1], 0));
+  return 0;
+}
+// everything enqueued on `st` so far becomes visible to the weight-gradient stream
+static int fork_side(TrainState *ts, cudaStream_t st) {
+  DIM_CHECK(cudaEventRecord(ts->ev_fork, st));
+  DIM_CHECK(cudaStreamWaitEvent(ts->side[3], ts->ev_fork, 0));
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------ the step
 struct TrainIO {
   const float *zio, *zir, *zmo, *zmr, *zoom_factor, *zflow, *zfw, *zmask_gt, *src_pose, *pc_model, *pc_weights, *pc_observed;
@@ -1116,15 +1150,13 @@ int train_forward_backward(dim_ctx *ctx, const TrainIO &io, cudaStream_t st) {
   if (int rc = copy_interior(a10, ts->act10b, 0, B, 1024, st)) return rc;
   LAUNCH1D(thin_conv_fwd_kernel<2>, (size_t)B * h6 * w6 * 32, st, ts->act10b.p, ts->act10b.Hp, ts->act10b.Wp, 1024, 1024, B, h6, w6,
            M + ts->off[P_CONV1D].w, M + ts->off[P_CONV1D].b, ts->flow6);
-  for (int c = 0; c < 4; ++c)
-    if (int rc = run_generic(ctx, tm.deconv5_fwd[c], tm.g_deconv5_fwd[c], B, st)) return rc;
+  if (int rc = run_classes(ctx, ts, tm.deconv5_fwd, tm.g_deconv5_fwd, 4, B, st)) return rc;
   if (int rc = copy_interior(a8, ts->cat2, 0, B, 512, st)) return rc;
   LAUNCH1D(thin_deconv_fwd_kernel, (size_t)B * h5 * w5 * 2, st, ts->flow6, B, h6, w6, M + ts->off[P_UP65].w, M + ts->off[P_UP65].b,
            ts->cat2.p, ts->cat2.Hp, ts->cat2.Wp, 1, 1, 1088, 1024, h5, w5);
   LAUNCH1D(thin_conv_fwd_kernel<2>, (size_t)B * h5 * w5 * 32, st, ts->cat2.p, ts->cat2.Hp, ts->cat2.Wp, 1088, 1026, B, h5, w5,
            M + ts->off[P_CONV2D].w, M + ts->off[P_CONV2D].b, ts->flow5);
-  for (int c = 0; c < 4; ++c)
-    if (int rc = run_generic(ctx, tm.deconv4_fwd[c], tm.g_deconv4_fwd[c], B, st)) return rc;
+  if (int rc = run_classes(ctx, ts, tm.deconv4_fwd, tm.g_deconv4_fwd, 4, B, st)) return rc;
   if (int rc = copy_interior(a6, ts->cat3, 0, B, 512, st)) return rc;
   LAUNCH1D(thin_deconv_fwd_kernel, (size_t)B * h4 * w4 * 2, st, ts->flow5, B, h5, w5, M + ts->off[P_UP54].w, M + ts->off[P_UP54].b,
            ts->cat3.p, ts->cat3.Hp, ts->cat3.Wp, 1, 1, 832, 768, h4, w4);
@@ -1180,8 +1212,10 @@ int train_forward_backward(dim_ctx *ctx, const TrainIO &io, cudaStream_t st) {
   // deconv4: LeakyReLU backward on its slice, bias, weight and data gradients
   LAUNCH1D(lrelu_mask_inplace_kernel, (size_t)B * h4 * w4 * 32, st, ts->dcat3.p, ts->cat3.p, ts->cat3.Hp, ts->cat3.Wp, 1, 1, 832, 512, B, h4,
            w4, 256, 0.1f);
-  if (int rc = bias_grad(ts, ts->dcat3, B, 512, 256, G + ts->off[P_DECONV4].b, st)) return rc;
-  if (int rc = run_wgrad(tm.wg_deconv4, tm.wg_bn_d4, WG_DECONV, 1026, 256, 4, G + ts->off[P_DECONV4].w, st)) return rc;
+  cudaStream_t sw = ts->side[3];
+  if (int rc = fork_side(ts, st)) return rc;
+  if (int rc = bias_grad(ts, ts->dcat3, B, 512, 256, G + ts->off[P_DECONV4].b, sw)) return rc;
+  if (int rc = run_wgrad(tm.wg_deconv4, tm.wg_bn_d4, WG_DECONV, 1026, 256, 4, G + ts->off[P_DECONV4].w, sw)) return rc;
   if (int rc = run_generic(ctx, tm.deconv4_dgrad, tm.g_deconv4_dgrad, B, st)) return rc;
   // Convolution2 (adds to dcat2), upsample_flow6to5
   if (int rc = thin_wgrad<2>(ts, ts->cat2, 1026, B, h5, w5, ts->dflow5, G + ts->off[P_CONV2D].w, G + ts->off[P_CONV2D].b, st)) return rc;
@@ -1193,8 +1227,9 @@ int train_forward_backward(dim_ctx *ctx, const TrainIO &io, cudaStream_t st) {
   // deconv5
   LAUNCH1D(lrelu_mask_inplace_kernel, (size_t)B * h5 * w5 * 64, st, ts->dcat2.p, ts->cat2.p, ts->cat2.Hp, ts->cat2.Wp, 1, 1, 1088, 512, B, h5,
            w5, 512, 0.1f);
-  if (int rc = bias_grad(ts, ts->dcat2, B, 512, 512, G + ts->off[P_DECONV5].b, st)) return rc;
-  if (int rc = run_wgrad(tm.wg_deconv5, tm.wg_bn_d5, WG_DECONV, 1024, 512, 4, G + ts->off[P_DECONV5].w, st)) return rc;
+  if (int rc = fork_side(ts, st)) return rc;
+  if (int rc = bias_grad(ts, ts->dcat2, B, 512, 512, G + ts->off[P_DECONV5].b, sw)) return rc;
+  if (int rc = run_wgrad(tm.wg_deconv5, tm.wg_bn_d5, WG_DECONV, 1024, 512, 4, G + ts->off[P_DECONV5].w, sw)) return rc;
   // Convolution1 -> partial gradient of ReLU10, + fc6 data gradient, then deconv5's data gradient closes dZ of conv6_1
   if (int rc = thin_wgrad<2>(ts, ts->act10b, 1024, B, h6, w6, ts->dflow6, G + ts->off[P_CONV1D].w, G + ts->off[P_CONV1D].b, st)) return rc;
   LAUNCH1D(thin_conv_dgrad_kernel<2>, (size_t)B * h6 * w6 * 1024, st, ts->dflow6, M + ts->off[P_CONV1D].w, 1024, B, h6, w6, ts->dA10p.p,
@@ -1206,12 +1241,14 @@ int train_forward_backward(dim_ctx *ctx, const TrainIO &io, cudaStream_t st) {
            g[0].cols);
   for (int i = 9; i >= 0; --i) {
     const LayerSpec &s = kLayers[i];
-    if (int rc = bias_grad(ts, ts->gz[i], B, 0, s.Cout, G + ts->off[i].b, st)) return rc;
-    if (int rc = run_wgrad(tm.wg[i], tm.wg_bn[i], i == 0 ? WG_CONV1_S2D : WG_CONV, s.Cout, s.Cin, s.k, G + ts->off[i].w, st)) return rc;
+    if (int rc = fork_side(ts, st)) return rc;  // gz[i] is complete on st
+    if (int rc = bias_grad(ts, ts->gz[i], B, 0, s.Cout, G + ts->off[i].b, sw)) return rc;
+    if (int rc = run_wgrad(tm.wg[i], tm.wg_bn[i], i == 0 ? WG_CONV1_S2D : WG_CONV, s.Cout, s.Cin, s.k, G + ts->off[i].w, sw)) return rc;
     if (i >= 1)
-      for (int c = 0; c < tm.n_dgrad[i]; ++c)
-        if (int rc = run_generic(ctx, tm.dgrad[i][c], tm.g_dgrad[i][c], B, st)) return rc;
+      if (int rc = run_classes(ctx, ts, tm.dgrad[i], tm.g_dgrad[i], tm.n_dgrad[i], B, st)) return rc;
   }
+  DIM_CHECK(cudaEventRecord(ts->ev_side, sw));
+  DIM_CHECK(cudaStreamWaitEvent(st, ts->ev_side, 0));
   return 0;
 }
 
