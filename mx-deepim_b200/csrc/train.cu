@@ -1121,7 +1121,19 @@ struct TrainIO {
   const float *zio, *zir, *zmo, *zmr, *zoom_factor, *zflow, *zfw, *zmask_gt, *src_pose, *pc_model, *pc_weights, *pc_observed;
   int B, N;
   float *rot_est_norm, *trans_est, *flow_est, *mask_prob, *losses, *grads;
+  // gradient-bucket readiness (overlap of the NCCL all-reduce with the rest of the backward pass): event k is recorded as
+  // soon as every gradient of the tensors with table index >= bucket_first_tensor[k] has been produced
+  void *const *bucket_events;
+  const int *bucket_first_tensor;
+  int n_buckets;
 };
+
+static int record_buckets(const TrainIO &io, int lo_inclusive, int hi_exclusive, cudaStream_t s) {
+  for (int k = 0; k < io.n_buckets; ++k)
+    if (io.bucket_first_tensor[k] >= lo_inclusive && io.bucket_first_tensor[k] < hi_exclusive)
+      DIM_CHECK(cudaEventRecord((cudaEvent_t)io.bucket_events[k], s));
+  return 0;
+}
 
 int train_forward_backward(dim_ctx *ctx, const TrainIO &io, cudaStream_t st) {
   NetState *ns = ctx->net;
@@ -1242,8 +1254,11 @@ int train_forward_backward(dim_ctx *ctx, const TrainIO &io, cudaStream_t st) {
   for (int i = 9; i >= 0; --i) {
     const LayerSpec &s = kLayers[i];
     if (int rc = fork_side(ts, st)) return rc;  // gz[i] is complete on st
+    if (i == 9)  // heads, decoder (thin kernels on st, deconvolution wgrads on sw): tensors 10..23 are done
+      if (int rc = record_buckets(io, 10, 1 << 30, sw)) return rc;
     if (int rc = bias_grad(ts, ts->gz[i], B, 0, s.Cout, G + ts->off[i].b, sw)) return rc;
     if (int rc = run_wgrad(tm.wg[i], tm.wg_bn[i], i == 0 ? WG_CONV1_S2D : WG_CONV, s.Cout, s.Cin, s.k, G + ts->off[i].w, sw)) return rc;
+    if (int rc = record_buckets(io, i, i + 1, sw)) return rc;
     if (i >= 1)
       if (int rc = run_classes(ctx, ts, tm.dgrad[i], tm.g_dgrad[i], tm.n_dgrad[i], B, st)) return rc;
   }

@@ -72,14 +72,26 @@ class Trainer:
         torch.cuda.current_stream(ctx.device).synchronize()
         self.grads = torch.zeros(self.n, dtype=torch.float32, device=ctx.device)
         limit = int(bucket_mb * (1 << 20) / 4)
-        self.buckets, hi, lo = [], self.n, self.n
-        for _, n in reversed(self.table):  # reverse order = the order the backward pass produces the gradients
+        # buckets along tensor boundaries, walking the table backwards (= the order the backward pass produces the
+        # gradients); each bucket remembers the table index of its first tensor for the readiness events
+        names = []
+        for i in range(64):
+            nm, wn, bn = C.c_char_p(), C.c_int64(), C.c_int64()
+            if lib.dim_train_param_info(i, C.byref(nm), C.byref(wn), C.byref(bn)) != 0:
+                break
+            names.append((i, wn.value + bn.value))
+        self.buckets, self.bucket_first, hi, lo = [], [], self.n, self.n
+        for idx, n in reversed(names):
             lo -= n
             if hi - lo >= limit:
                 self.buckets.append((lo, hi))
+                self.bucket_first.append(idx)
                 hi = lo
         if hi > 0:
             self.buckets.append((0, hi))
+            self.bucket_first.append(0)
+        self._events = None
+        self._comm_stream = None
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.ctx.device).cuda_stream)
@@ -91,7 +103,17 @@ class Trainer:
             off += n
         return out
 
-    def forward_backward(self, z, want_maps=True, backward=True):
+    def _bucket_events(self):
+        if self._events is None:
+            self._events = [torch.cuda.Event() for _ in self.buckets]
+            for e in self._events:
+                e.record()  # forces creation of the underlying cudaEvent_t
+            self._ev_handles = (C.c_void_p * len(self._events))(*[e.cuda_event for e in self._events])
+            self._ev_first = (C.c_int32 * len(self._events))(*self.bucket_first)
+            self._comm_stream = torch.cuda.Stream(device=self.ctx.device)
+        return self._ev_handles, self._ev_first
+
+    def forward_backward(self, z, want_maps=True, backward=True, overlap=False):
         """z: dict of device float32 tensors (the outputs of the zoom front of the train symbol + labels):
         zoom_image_observed/rendered (B,3,H,W), zoom_mask_observed/rendered (B,1,H,W), zoom_factor (B,4),
         zoom_flow, zoom_flow_weights (B,2,H,W), zoom_mask_gt_observed (B,1,H,W), src_pose (B,3,4),
@@ -109,7 +131,8 @@ class Trainer:
             _p(z["zoom_mask_rendered"]), _p(z["zoom_factor"]), _p(z["zoom_flow"]), _p(z["zoom_flow_weights"]),
             _p(z["zoom_mask_gt_observed"]), _p(z["src_pose"]), _p(z["point_cloud_model"]), _p(z["point_cloud_weights"]),
             _p(z["point_cloud_observed"]), B, N, _p(out["rot_est_norm"]), _p(out["trans_est"]), _p(out["flow_est"]),
-            _p(out["mask_prob"]), _p(out["losses"]), _p(self.grads) if backward else None, self._stream()))
+            _p(out["mask_prob"]), _p(out["losses"]), _p(self.grads) if backward else None,
+            *((self._bucket_events() + (len(self.buckets),)) if (backward and overlap) else (None, None, 0)), self._stream()))
         return out
 
     def allreduce(self, dist):
@@ -121,9 +144,26 @@ class Trainer:
         check(lib.dim_train_sgd_update(self.ctx._h, _p(self.grads), self.lr if lr is None else lr, self.momentum, self.wd,
                                        1.0, self._stream()))
 
-    def step(self, z, dist=None, want_maps=False):
-        out = self.forward_backward(z, want_maps=want_maps)
-        self.allreduce(dist)
+    def allreduce_overlapped(self, dist):
+        """Bucket k is all-reduced as soon as its readiness event (recorded inside dim_train_forward_backward) fires,
+        i.e. while the backward pass of the lower layers is still running; the update waits for all of them."""
+        cur = torch.cuda.current_stream(self.ctx.device)
+        works = []
+        with torch.cuda.stream(self._comm_stream):
+            for k, (lo, hi) in enumerate(self.buckets):
+                self._comm_stream.wait_event(self._events[k])
+                works.append(dist.all_reduce(self.grads[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+            for w in works:
+                w.wait()
+        cur.wait_stream(self._comm_stream)
+
+    def step(self, z, dist=None, want_maps=False, overlap=True):
+        multi = dist is not None and dist.is_initialized() and dist.get_world_size() > 1
+        out = self.forward_backward(z, want_maps=want_maps, overlap=multi and overlap)
+        if multi and overlap:
+            self.allreduce_overlapped(dist)
+        else:
+            self.allreduce(dist)
         self.update()
         return out
 

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--out", default="")
+    ap.add_argument("--no-overlap", action="store_true", help="all-reduce after the backward pass instead of bucket by bucket during it")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank, local = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
@@ -44,6 +45,9 @@ def main():
         ctx.upload_mesh(i, m)
     tr = Trainer(ctx, synth.make_train_weights(0))
     batch, cls, tgt, depth = make_device_batch(ctx, meshes, a.batch, 3 + rank, K, MEANS)
+    if a.no_overlap:
+        step0 = tr.step
+        tr.step = lambda z, dist=None, want_maps=False: step0(z, dist=dist, want_maps=want_maps, overlap=False)
     for _ in range(a.warmup):
         fit_batch(tr, batch, cls, tgt, depth, K, dist=dist)
     torch.cuda.synchronize()
@@ -69,7 +73,7 @@ def main():
             "ms_per_inner_iteration": float(ms) / 4, "split_ms": {"forward_backward": ev[0].elapsed_time(ev[1]),
                                                                    "allreduce": ev[1].elapsed_time(ev[2]), "sgd_update_repack": ev[2].elapsed_time(ev[3])},
             "dtype": "bf16 activations/gradients, fp32 master", "data": "synthetic", "scaling": "weak",
-            "config": {"workload": "C4 training step", "per_gpu_batch": a.batch, "inner_iterations": 4, "grad_bytes": tr.n * 4},
+            "config": {"workload": "C4 training step", "allreduce_overlap": (not a.no_overlap) and world > 1, "per_gpu_batch": a.batch, "inner_iterations": 4, "grad_bytes": tr.n * 4},
             "objective_last_batch": [float(v) for v in objs.cpu()]}
     if rank == 0:
         print(json.dumps(line))
