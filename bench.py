@@ -372,7 +372,15 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--slots", type=int, default=4, help="independent batches in flight per GPU (streams)")
+    ap.add_argument("--workload", default="refine", choices=["refine", "train"],
+                    help="refine = the headline metric (default); train = config C4 training step (tools/train_bench.py)")
     args = ap.parse_args()
+    if args.workload == "train":  # secondary workload: BASELINE.json configs[3]; same launch contract (torchrun for N > 1)
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools"))
+        import train_bench
+        sys.argv = [sys.argv[0], "--batch", str(4 if args.batch == 16 else args.batch), "--steps", str(args.steps or 10),
+                    "--warmup", str(args.warmup or 3)]
+        return train_bench.main()
     if args.impl == "reference":
         args.steps = 5 if args.steps is None else args.steps
         args.warmup = 1 if args.warmup is None else args.warmup
