@@ -87,6 +87,22 @@ DIM_API int32_t dim_zoom_image_with_factor_fwd(dim_ctx *ctx, const float *zoom_f
                                                float *zoom_image_observed,
                                                float *zoom_image_rendered, void *stream);
 
+/* ZoomImage forward (zoom_image.py:26-107, the INPUT_MASK: False front end): the two boxes come from the
+ * images themselves, valid = sum_c(image + pixel_mean_c) > 0.01; centre / crop / sampling as ZoomMask +
+ * ZoomImageWithFactor.  pixel_means_rgb_host = the op's (already reversed) pixel_means attr.
+ * bbox i32[B,8] / status i32[B] as dim_zoom_mask_fwd (may be NULL). */
+DIM_API int32_t dim_zoom_image_fwd(dim_ctx *ctx, const float *image_observed, const float *image_rendered,
+                                   const float *src_pose, int32_t B, const float *K9_host,
+                                   const float *pixel_means_rgb_host, float *zoom_image_observed,
+                                   float *zoom_image_rendered, float *zoom_factor, int32_t *bbox,
+                                   int32_t *status, void *stream);
+
+/* GroupPicker (group_picker.py:22-60): forward out[b] = in[b, g*cg:(g+1)*cg] (g = group_idx[b], a float like the
+ * NDArray the reference reads); backward = 1 scatters out_grad (in) into a zero [B,channels,...] gradient. */
+DIM_API int32_t dim_group_picker(dim_ctx *ctx, const float *in, const float *group_idx, int32_t B,
+                                 int32_t channels, int32_t group_num, int64_t elems_per_channel,
+                                 int32_t backward, float *out, void *stream);
+
 /* ZoomMaskWithFactor forward (zoom_mask_with_factor.py:29-64): mask f32[B,1,H,W]. */
 DIM_API int32_t dim_zoom_mask_with_factor_fwd(dim_ctx *ctx, const float *zoom_factor,
                                               const float *mask, int32_t B, int32_t b_inv_zoom,

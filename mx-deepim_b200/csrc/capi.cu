@@ -22,7 +22,8 @@ int render_launch(dim_ctx *, const int *, const float *, int, const float *, flo
 int zoom_gather_launch(dim_ctx *, int mode, const float *src, float *dst, const float *zf, int B, int C, int inv,
                        const float *param, cudaStream_t);
 int zoom_factor_launch(dim_ctx *, const float *, const float *, int C, const float *, int B, const float *K9, float *,
-                       int *, int *, cudaStream_t);
+                       int *, int *, cudaStream_t, const float *img_means = nullptr);
+int group_pick_launch(const float *, const float *, int B, int Ctot, int groups, size_t n, float *, int backward, cudaStream_t);
 int zoom_factor_from_ren_launch(dim_ctx *, const int *, const float *, int B, const float *K9, float *, int *, int *,
                                 cudaStream_t);
 int box_mask_launch(dim_ctx *, const int *, int B, float *, cudaStream_t);
@@ -213,6 +214,25 @@ DIM_API int32_t dim_zoom_image_with_factor_fwd(dim_ctx *ctx, const float *zoom_f
   cudaStream_t st = (cudaStream_t)stream;
   if (int rc = zoom_gather_launch(ctx, 3, io, zio, zoom_factor, B, 3, 0, means, st)) return rc;
   return zoom_gather_launch(ctx, 3, ir, zir, zoom_factor, B, 3, 0, means, st);
+}
+
+// ZoomImage (zoom_image.py:26-107): bbox from the images themselves (INPUT_MASK: False graphs)
+DIM_API int32_t dim_zoom_image_fwd(dim_ctx *ctx, const float *io, const float *ir, const float *src_pose, int32_t B,
+                                   const float *K9, const float *means, float *zio, float *zir, float *zoom_factor,
+                                   int32_t *bbox, int32_t *status, void *stream) {
+  DIM_REQUIRE(ctx && io && ir && src_pose && K9 && means && zio && zir && zoom_factor, "dim_zoom_image_fwd: NULL argument");
+  DIM_REQUIRE(B >= 1 && B <= ctx->max_batch, "dim_zoom_image_fwd: batch exceeds max_batch");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = zoom_factor_launch(ctx, io, ir, 3, src_pose, B, K9, zoom_factor, bbox, status, st, means)) return rc;
+  if (int rc = zoom_gather_launch(ctx, 3, io, zio, zoom_factor, B, 3, 0, means, st)) return rc;
+  return zoom_gather_launch(ctx, 3, ir, zir, zoom_factor, B, 3, 0, means, st);
+}
+
+DIM_API int32_t dim_group_picker(dim_ctx *ctx, const float *in, const float *group_idx, int32_t B, int32_t channels,
+                                 int32_t group_num, int64_t elems_per_channel, int32_t backward, float *out, void *stream) {
+  DIM_REQUIRE(ctx && in && group_idx && out, "dim_group_picker: NULL argument");
+  DIM_REQUIRE(group_num >= 1 && channels % group_num == 0 && elems_per_channel >= 1, "dim_group_picker: channels must divide into groups");
+  return group_pick_launch(in, group_idx, B, channels, group_num, (size_t)elems_per_channel, out, backward, (cudaStream_t)stream);
 }
 
 DIM_API int32_t dim_zoom_mask_with_factor_fwd(dim_ctx *ctx, const float *zoom_factor, const float *mask, int32_t B,

@@ -23,8 +23,10 @@ __global__ void bbox_init_kernel(int *bbox8, int B, int H, int W) {
 
 // one block per (row, instance, which-mask).  valid = sum_c(mask) > 0.3 (zoom_mask.py:36-37), with
 // each channel binarised at 0.2 first for the rendered mask (l.39-43).
+// img_mode (ZoomImage, zoom_image.py:33-37): valid = sum_c(img + pixel_mean_c) > 0.01 for both images.
 __global__ void __launch_bounds__(160) mask_bbox_kernel(const float *mask_real, const float *mask_ren, int C,
-                                                        int H, int W, int *bbox8) {
+                                                        int H, int W, int *bbox8, int img_mode, float m0, float m1,
+                                                        float m2) {
   const int i = blockIdx.x, b = blockIdx.y, which = blockIdx.z;
   const float *src = (which == 0 ? mask_real : mask_ren) + (size_t)b * C * H * W + (size_t)i * W;
   int x0 = 0x7fffffff, x1 = -1;
@@ -33,12 +35,13 @@ __global__ void __launch_bounds__(160) mask_bbox_kernel(const float *mask_real, 
     for (int c = 0; c < C; ++c) {
       float4 v = *reinterpret_cast<const float4 *>(src + (size_t)c * H * W + j4);
       float e[4] = {v.x, v.y, v.z, v.w};
+      const float mc = c == 0 ? m0 : (c == 1 ? m1 : m2);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) s[k] += which ? (e[k] > 0.2f ? 1.f : 0.f) : e[k];
+      for (int k = 0; k < 4; ++k) s[k] += img_mode ? (e[k] + mc) : (which ? (e[k] > 0.2f ? 1.f : 0.f) : e[k]);
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      if (s[k] > 0.3f) {
+      if (s[k] > (img_mode ? 0.01f : 0.3f)) {
         x0 = min(x0, j4 + k);
         x1 = max(x1, j4 + k);
       }
@@ -226,11 +229,14 @@ int zoom_gather_launch(dim_ctx *ctx, int mode, const float *src, float *dst, con
 }
 
 int zoom_factor_launch(dim_ctx *ctx, const float *mask_real, const float *mask_ren, int C, const float *src_pose,
-                       int B, const float *K9, float *zoom_factor, int *bbox_out, int *status, cudaStream_t st) {
+                       int B, const float *K9, float *zoom_factor, int *bbox_out, int *status, cudaStream_t st,
+                       const float *img_means) {
   DIM_REQUIRE((ctx->W & 3) == 0, "width must be a multiple of 4");
   bbox_init_kernel<<<cdiv(2 * B, 128), 128, 0, st>>>(ctx->bbox8, B, ctx->H, ctx->W);
   DIM_LAUNCH_CHECK();
-  mask_bbox_kernel<<<dim3(ctx->H, B, 2), 160, 0, st>>>(mask_real, mask_ren, C, ctx->H, ctx->W, ctx->bbox8);
+  mask_bbox_kernel<<<dim3(ctx->H, B, 2), 160, 0, st>>>(mask_real, mask_ren, C, ctx->H, ctx->W, ctx->bbox8,
+                                                       img_means ? 1 : 0, img_means ? img_means[0] : 0.f,
+                                                       img_means ? img_means[1] : 0.f, img_means ? img_means[2] : 0.f);
   DIM_LAUNCH_CHECK();
   zoom_factor_kernel<<<cdiv(B, 64), 64, 0, st>>>(ctx->bbox8, src_pose, B, ctx->H, ctx->W, K9[0], K9[1], K9[2], K9[3],
                                                   K9[4], K9[5], K9[6], K9[7], K9[8], zoom_factor, bbox_out, status);
@@ -448,6 +454,34 @@ int pack_nhwc8_launch(dim_ctx *ctx, const float *io, const float *ir, const floa
                       int Hs, int Ws, int pad, __nv_bfloat16 *hi, __nv_bfloat16 *lo, cudaStream_t st) {
   pack_nhwc8_kernel<<<dim3(cdiv(ctx->H * ctx->W, 256), B), 256, 0, st>>>(io, ir, mo, mr, ctx->H, ctx->W, Hs, Ws, pad,
                                                                          hi, lo);
+  DIM_LAUNCH_CHECK();
+  return 0;
+}
+
+// GroupPicker (deepim/operator_py/group_picker.py:22-60): out[b] = in[b, g*cg:(g+1)*cg] with g = group_idx[b];
+// backward scatters the gradient into the picked group and zero elsewhere.  n = elements per channel (H*W).
+__global__ void __launch_bounds__(256) group_pick_kernel(const float *in, const float *group_idx, int B, int Ctot, int groups,
+                                                         size_t n, float *out, int backward) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cg = Ctot / groups;
+  if (!backward) {
+    if (i >= (size_t)B * cg * n) return;
+    const int b = (int)(i / ((size_t)cg * n));
+    const size_t r = i - (size_t)b * cg * n;
+    const int g = (int)group_idx[b];
+    out[i] = in[((size_t)b * Ctot + (size_t)g * cg) * n + r];
+  } else {
+    if (i >= (size_t)B * Ctot * n) return;
+    const int b = (int)(i / ((size_t)Ctot * n));
+    const size_t r = i - (size_t)b * Ctot * n;
+    const int c = (int)(r / n), g = (int)group_idx[b];
+    out[i] = (c / cg == g) ? in[((size_t)b * cg + (c - g * cg)) * n + (r - (size_t)c * n)] : 0.f;
+  }
+}
+int group_pick_launch(const float *in, const float *group_idx, int B, int Ctot, int groups, size_t n, float *out, int backward,
+                      cudaStream_t st) {
+  const size_t total = (size_t)B * (backward ? Ctot : Ctot / groups) * n;
+  group_pick_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, group_idx, B, Ctot, groups, n, out, backward);
   DIM_LAUNCH_CHECK();
   return 0;
 }

@@ -135,6 +135,32 @@ class Context:
                                                  farr(pixel_means_rgb, 3), _p(zo), _p(zr), _stream()))
         return zo, zr
 
+    def zoom_image(self, image_observed, image_rendered, src_pose, K, pixel_means_rgb):
+        """ZoomImage (zoom_image.py:26-107): boxes from sum_c(image + mean) > 0.01."""
+        B = image_observed.shape[0]
+        shp = (B, 3, self.H, self.W)
+        _chk(image_observed, torch.float32, shp, "image_observed")
+        _chk(image_rendered, torch.float32, shp, "image_rendered")
+        _chk(src_pose, torch.float32, (B, 3, 4), "src_pose")
+        zo, zr, zf = self._new(shp), self._new(shp), self._new((B, 4))
+        bbox, status = self._new((B, 8), torch.int32), self._new((B,), torch.int32)
+        check(lib.dim_zoom_image_fwd(self._h, _p(image_observed), _p(image_rendered), _p(src_pose), B,
+                                     farr(np.asarray(K, np.float32).reshape(9), 9), farr(pixel_means_rgb, 3), _p(zo), _p(zr),
+                                     _p(zf), _p(bbox), _p(status), _stream()))
+        return zo, zr, zf, bbox, status
+
+    def group_picker(self, data, group_idx, group_num, backward=False, channels=None):
+        """GroupPicker (group_picker.py:22-56).  forward: data [B,C,...] -> [B,C/group_num,...];
+        backward: data = out_grad [B,C/group_num,...] -> [B,channels,...] (zero outside the picked group)."""
+        B = data.shape[0]
+        Ctot = channels if backward else data.shape[1]
+        n = int(np.prod(data.shape[2:])) if data.dim() > 2 else 1
+        gi = group_idx.reshape(-1).to(torch.float32).contiguous()
+        _chk(data, torch.float32, tuple(data.shape), "data")
+        out = self._new((B, Ctot if backward else Ctot // group_num) + tuple(data.shape[2:]))
+        check(lib.dim_group_picker(self._h, _p(data), _p(gi), B, Ctot, group_num, n, int(backward), _p(out), _stream()))
+        return out
+
     def zoom_mask_with_factor(self, zoom_factor, mask, b_inv_zoom):
         B = mask.shape[0]
         _chk(mask, torch.float32, (B, 1, self.H, self.W), "mask")

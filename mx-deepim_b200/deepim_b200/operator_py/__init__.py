@@ -11,4 +11,4 @@ An MXNet adapter only needs to wrap NDArrays as torch tensors via DLPack (INTEGR
 """
 from .base import CustomOp, CustomOpProp, REGISTRY, create, register, set_default_context  # noqa: F401
 from . import zoom_mask, zoom_image_with_factor, zoom_mask_with_factor, zoom_flow, zoom_trans  # noqa: F401
-from . import zoom_depth, transform3d, flow_updater  # noqa: F401
+from . import zoom_depth, transform3d, flow_updater, zoom_image, group_picker  # noqa: F401

@@ -132,6 +132,28 @@ def zoom_mask(mask_observed, mask_gt_observed, mask_rendered, src_pose, K):
     return outs[0], outs[1], outs[2], zf, bboxes
 
 
+def zoom_image(image_observed, image_rendered, src_pose, K, means_rgb):
+    """ZoomImage forward (deepim/operator_py/zoom_image.py:26-107): boxes from sum_c(image + mean) > 0.01 (float32 adds
+    in channel order, as np.sum over 3 non-contiguous elements), then the ZoomMask centre/crop rule and the
+    ZoomImageWithFactor sampling.  Returns zoom_image_observed, zoom_image_rendered, zoom_factor, bbox(B,8)."""
+    B, _, H, W = image_observed.shape
+    K9 = np.ascontiguousarray(K, dtype=np.float32).reshape(9)
+    m = np.asarray(means_rgb, np.float32)
+    zf = np.zeros((B, 4), np.float32)
+    bboxes = np.zeros((B, 8), np.int32)
+    for b in range(B):
+        so = ((image_observed[b, 0] + m[0]) + (image_observed[b, 1] + m[1])) + (image_observed[b, 2] + m[2])
+        sr = ((image_rendered[b, 0] + m[0]) + (image_rendered[b, 1] + m[1])) + (image_rendered[b, 2] + m[2])
+        bb_real, bb_ren = mask_bbox(so.astype(np.float32), 0.01), mask_bbox(sr.astype(np.float32), 0.01)
+        z = np.zeros(4, np.float32)
+        if lib().orc_zoom_factor(bb_real, bb_ren, np.ascontiguousarray(src_pose[b], dtype=np.float32), K9, H, W, z) != 0:
+            raise ValueError("zoom_image: observed image empty (the reference raises here as well)")
+        zf[b] = z
+        bboxes[b, :4], bboxes[b, 4:] = bb_real, bb_ren
+    o, r = zoom_image_with_factor(zf, image_observed, image_rendered, m)
+    return o, r, zf, bboxes
+
+
 def zoom_image_with_factor(zoom_factor, image_observed, image_rendered, means_rgb):
     """ZoomImageWithFactor forward (zoom_image_with_factor.py:31-65); means_rgb = reversed pixel_means."""
     B = image_observed.shape[0]

@@ -79,6 +79,9 @@ def test_operator_surface_matches_reference_signatures():
         "Transform3D": (dict(T_means="[0 0 0]", T_stds="[1 1 1]", rot_coord="CAMERA"),
                         ["point_cloud", "rotation", "translation", "pose_src"], ["transformed_3d_points"]),
         "FlowUpdater": (dict(K=K), ["depth_src", "depth_tgt", "pose_src", "pose_tgt"], ["flow", "flow_weights"]),
+        "ZoomImage": (dict(K=K, pixel_means="[123.68 116.779 103.939]"), ["image_observed", "image_rendered", "src_pose"],
+                      ["zoom_image_observed", "zoom_image_rendered", "zoom_factor"]),
+        "GroupPicker": (dict(group_num="13"), ["input_data", "group_idx"], ["picked_data"]),
     }
     for name, (kw, args, outs) in expect.items():
         prop = op.REGISTRY[name](**kw)
@@ -90,6 +93,7 @@ def test_operator_surface_matches_reference_signatures():
     assert zm.infer_shape([[4, 1, 480, 640]] * 3 + [[4, 3, 4]])[1][-1] == [4, 4]
     zi = op.REGISTRY["ZoomImageWithFactor"](pixel_means="[123.68 116.779 103.939]")
     np.testing.assert_allclose(zi.pixel_means, [103.939, 116.779, 123.68], rtol=1e-7)  # reversed, l.79-81
+    assert op.REGISTRY["GroupPicker"](group_num="13").infer_shape([[4, 52], [4, 1]])[1] == [[4, 4]]  # group_picker.py:73-79
     with pytest.raises(RuntimeError):
         op.create("ZoomTrans", b_inv_zoom="True")  # no Context set -> loud
 

@@ -198,3 +198,44 @@ def test_flow_updater_and_shims(env):
     bgr, depth = rm.render(1, obs[0][:, :3], obs[0][:, 3], r_type="mat", K=K)
     r = O.render(meshes[1], obs[0], K, trunc_u8=False)
     assert bgr.shape == (480, 640, 3) and np.array_equal(bgr, r["bgr"]) and np.array_equal(depth, r["depth"])
+
+
+def test_zoom_image_and_group_picker(env):
+    """ZoomImage (zoom_image.py:26-107, the INPUT_MASK: False front end) and GroupPicker (group_picker.py:22-56,
+    whose reference self-test checks forward against slicing and backward against scatter)."""
+    ctx, meshes = env
+    B = 2
+    obs, ini = synth.sample_pose_pairs(B, 97)
+    img_o = np.stack([O.render(meshes[b % 2], obs[b], K, means_rgb=synth.PIXEL_MEANS_RGB)["image"] for b in range(B)])
+    img_r = np.stack([O.render(meshes[b % 2], ini[b], K, means_rgb=synth.PIXEL_MEANS_RGB)["image"] for b in range(B)])
+    pose32 = ini.astype(np.float32)
+    zi = ops.create("ZoomImage", K=KSTR, height="480", width="640", pixel_means=MEANS_ATTR)
+    zo, zr, zf = _run(zi, [dev(img_o), dev(img_r), dev(pose32)], [(B, 3, H, W)] * 2 + [(B, 4)])
+    eo, er, ezf, ebb = O.zoom_image(img_o, img_r, pose32, K, synth.PIXEL_MEANS_RGB.astype(np.float32))
+    assert np.array_equal(zi.bbox.cpu().numpy(), ebb) and (ebb[:, 1] > ebb[:, 0]).all()
+    assert np.array_equal(zf.cpu().numpy(), ezf)
+    assert np.array_equal(zo.cpu().numpy(), eo) and np.array_equal(zr.cpu().numpy(), er)
+    # the image-derived boxes coincide with the mask-derived ones of ZoomMask on clean renders
+    mo = np.stack([O.render(meshes[b % 2], obs[b], K)["mask"] for b in range(B)])[:, None]
+    mr = np.stack([O.render(meshes[b % 2], ini[b], K)["mask"] for b in range(B)])[:, None]
+    assert np.array_equal(O.zoom_mask(mo, mo, mr, pose32, K)[4], ebb)
+
+    rng = np.random.default_rng(3)
+    G, cg = 13, 4
+    x = rng.normal(size=(B, G * cg)).astype(np.float32)
+    gi = np.array([[5.0], [12.0]], np.float32)
+    gp = ops.create("GroupPicker", group_num=str(G))
+    (picked,) = _run(gp, [dev(x), dev(gi)], [(B, cg)])
+    want = np.stack([x[b, int(gi[b, 0]) * cg:(int(gi[b, 0]) + 1) * cg] for b in range(B)])
+    assert np.array_equal(picked.cpu().numpy(), want)
+    og = rng.normal(size=(B, cg)).astype(np.float32)
+    gr = [torch.full((B, G * cg), 3.0, device=DEV), torch.full((B, 1), 3.0, device=DEV)]
+    gp.backward(["write", "write"], [dev(og)], [dev(x), dev(gi)], [picked], gr, [])
+    wantg = np.zeros((B, G * cg), np.float32)
+    for b in range(B):
+        wantg[b, int(gi[b, 0]) * cg:(int(gi[b, 0]) + 1) * cg] = og[b]
+    assert np.array_equal(gr[0].cpu().numpy(), wantg) and float(gr[1].abs().max()) == 0.0
+    # 4-D input (feature maps), as the per-class regressor graphs use it
+    x4 = rng.normal(size=(B, 2 * 3, 5, 7)).astype(np.float32)
+    (p4,) = _run(ops.create("GroupPicker", group_num="2"), [dev(x4), dev(np.array([1.0, 0.0], np.float32))], [(B, 3, 5, 7)])
+    assert np.array_equal(p4.cpu().numpy(), np.stack([x4[0, 3:6], x4[1, 0:3]]))
