@@ -286,6 +286,8 @@ DIM_API int32_t dim_train_get_params(dim_ctx *ctx, float *flat_host, int64_t n, 
  * (= flow_est_crop * NORMALIZE_FLOW, nullable), mask_prob (B,1,H,W) (nullable), losses4 = [sum flow_loss,
  * sum point_matching_loss, sum mask BCE, weighted objective], grads (flat, see above; NULL = forward only:
  * the non-FAST_TEST outputs of the test graph, symbol:624-713).
+ * With grads == NULL the labels (zoom_flow ... point clouds, losses4) may all be NULL: pure test-time forward of
+ * the full graph; rot_raw (B,4, nullable) is the un-normalised quaternion the test graph concatenates into se3.
  * bucket_events (nullable): n_buckets cudaEvent_t handles; event k is recorded (on an internal stream) as soon as
  * the gradients of every tensor with table index >= bucket_first_tensor[k] are complete, so a data-parallel
  * caller can start the NCCL all-reduce of that slice of `grads` while the rest of the backward pass still runs.
@@ -296,7 +298,8 @@ DIM_API int32_t dim_train_forward_backward(
     const float *zoom_flow, const float *zoom_flow_weights, const float *zoom_mask_gt_observed,
     const float *src_pose, const float *point_cloud_model, const float *point_cloud_weights,
     const float *point_cloud_observed, int32_t B, int32_t N, float *rot_est_norm, float *trans_est,
-    float *flow_est, float *mask_prob, float *losses4, float *grads, void *const *bucket_events,
+    float *flow_est, float *mask_prob, float *losses4, float *grads, float *rot_raw,
+    void *const *bucket_events,
     const int32_t *bucket_first_tensor, int32_t n_buckets, void *stream);
 /* mom = momentum*mom - lr*(rescale_grad*grad + wd*w); w += mom  (wd on *_weight only; the two bilinear kernels
  * are frozen), then refreshes every bf16 operand pack of the context from the new master weights. */

@@ -59,6 +59,7 @@ struct TrainIO {
   const float *zio, *zir, *zmo, *zmr, *zoom_factor, *zflow, *zfw, *zmask_gt, *src_pose, *pc_model, *pc_weights, *pc_observed;
   int B, N;
   float *rot_est_norm, *trans_est, *flow_est, *mask_prob, *losses, *grads;
+  float *rot_raw;
   void *const *bucket_events;
   const int *bucket_first_tensor;
   int n_buckets;
@@ -522,14 +523,12 @@ DIM_API int32_t dim_train_forward_backward(dim_ctx *ctx, const float *zio, const
                                            const float *zoom_factor, const float *zflow, const float *zfw, const float *zmask_gt,
                                            const float *src_pose, const float *pc_model, const float *pc_weights,
                                            const float *pc_observed, int32_t B, int32_t N, float *rot_est_norm, float *trans_est,
-                                           float *flow_est, float *mask_prob, float *losses4, float *grads,
+                                           float *flow_est, float *mask_prob, float *losses4, float *grads, float *rot_raw,
                                            void *const *bucket_events, const int32_t *bucket_first_tensor, int32_t n_buckets,
                                            void *stream) {
-  DIM_REQUIRE(ctx && zio && zir && zmo && zmr && zoom_factor && zflow && zfw && zmask_gt && src_pose && pc_model && pc_weights &&
-                  pc_observed && losses4,
-              "dim_train_forward_backward: NULL argument");
+  DIM_REQUIRE(ctx && zio && zir && zmo && zmr && zoom_factor, "dim_train_forward_backward: NULL argument");
   TrainIO io{zio, zir, zmo, zmr, zoom_factor, zflow, zfw, zmask_gt, src_pose, pc_model, pc_weights, pc_observed, B, N,
-             rot_est_norm, trans_est, flow_est, mask_prob, losses4, grads, bucket_events, bucket_first_tensor,
+             rot_est_norm, trans_est, flow_est, mask_prob, losses4, grads, rot_raw, bucket_events, bucket_first_tensor,
              (bucket_events && bucket_first_tensor) ? n_buckets : 0};
   return train_forward_backward(ctx, io, (cudaStream_t)stream);
 }

@@ -348,17 +348,21 @@ __global__ void __launch_bounds__(256) fullres_loss_kernel(const float *flow4, c
     const size_t q = (size_t)y * W + x;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
-      const float wgt = zfw[((size_t)b * 2 + c) * P + q];
-      const float d = v[c] - zflow[((size_t)b * 2 + c) * P + q] / norm_flow;
-      lf += wgt * d * d;
-      dfull[((size_t)b * 3 + c) * P + q] = gs_flow * 2.f * wgt * d;
+      if (zflow) {
+        const float wgt = zfw[((size_t)b * 2 + c) * P + q];
+        const float d = v[c] - zflow[((size_t)b * 2 + c) * P + q] / norm_flow;
+        lf += wgt * d * d;
+        dfull[((size_t)b * 3 + c) * P + q] = gs_flow * 2.f * wgt * d;
+      }
       if (flow_est) flow_est[((size_t)b * 2 + c) * P + q] = v[c] * norm_flow;
     }
-    const float lab = mask_gt[(size_t)b * P + q];
     const float pr = 1.f / (1.f + __expf(-v[2]));
-    // BCE with logits: max(x,0) - x*y + log(1 + exp(-|x|))
-    lm += fmaxf(v[2], 0.f) - v[2] * lab + log1pf(__expf(-fabsf(v[2])));
-    dfull[((size_t)b * 3 + 2) * P + q] = gs_mask * (pr - lab);
+    if (mask_gt) {
+      const float lab = mask_gt[(size_t)b * P + q];
+      // BCE with logits: max(x,0) - x*y + log(1 + exp(-|x|))
+      lm += fmaxf(v[2], 0.f) - v[2] * lab + log1pf(__expf(-fabsf(v[2])));
+      dfull[((size_t)b * 3 + 2) * P + q] = gs_mask * (pr - lab);
+    }
     if (mask_prob) mask_prob[(size_t)b * P + q] = pr;
   }
   red[0][threadIdx.x] = lf;
@@ -1121,6 +1125,7 @@ struct TrainIO {
   const float *zio, *zir, *zmo, *zmr, *zoom_factor, *zflow, *zfw, *zmask_gt, *src_pose, *pc_model, *pc_weights, *pc_observed;
   int B, N;
   float *rot_est_norm, *trans_est, *flow_est, *mask_prob, *losses, *grads;
+  float *rot_raw;  // nullable: the un-normalised quaternion of the test graph (se3 = [rot_raw, trans_est], symbol:716-725)
   // gradient-bucket readiness (overlap of the NCCL all-reduce with the rest of the backward pass): event k is recorded as
   // soon as every gradient of the tensors with table index >= bucket_first_tensor[k] has been produced
   void *const *bucket_events;
@@ -1140,7 +1145,10 @@ int train_forward_backward(dim_ctx *ctx, const TrainIO &io, cudaStream_t st) {
   TrainState *ts = train_of(ctx);
   DIM_REQUIRE(ts != nullptr && ns->loaded, "dim_train_forward_backward: call dim_train_create / dim_train_load_params first");
   const int B = io.B, H = ctx->H, W = ctx->W;
-  DIM_REQUIRE(B >= 1 && B <= ctx->max_batch && io.N >= 1 && io.N <= ts->max_points, "dim_train_forward_backward: bad batch / point count");
+  DIM_REQUIRE(B >= 1 && B <= ctx->max_batch && io.N >= 0 && io.N <= ts->max_points, "dim_train_forward_backward: bad batch / point count");
+  const bool labels = io.zflow && io.zfw && io.zmask_gt && io.src_pose && io.pc_model && io.pc_weights && io.pc_observed && io.N >= 1;
+  DIM_REQUIRE(labels || io.grads == nullptr, "dim_train_forward_backward: the backward pass needs every label");
+  DIM_REQUIRE(labels || (!io.zflow && !io.zfw && !io.zmask_gt && !io.pc_model), "dim_train_forward_backward: pass all labels or none");
   auto it = ts->maps.find(B);
   if (it == ts->maps.end()) {
     TrainMaps tm;
@@ -1182,12 +1190,17 @@ int train_forward_backward(dim_ctx *ctx, const TrainIO &io, cudaStream_t st) {
   DIM_LAUNCH_CHECK();
   pose_head_fwd_kernel<<<1, 32, 0, st>>>(ts->rot_raw, ts->ztrans, io.zoom_factor, B, ts->rot_n, ts->trans_est);
   DIM_LAUNCH_CHECK();
-  if (int rc = transform3d_fwd_launch(io.pc_model, ts->rot_n, ts->trans_est, io.src_pose, B, io.N, Tm, Tsd, 1, ts->pts_est, st)) return rc;
   const int pm_blocks = 64;
-  pm_loss_kernel<<<pm_blocks, 256, 0, st>>>(ts->pts_est, io.pc_observed, io.pc_weights, (size_t)B * 3 * io.N, 0.1f, gs_pm, ts->dpts, ts->loss_part);
-  DIM_LAUNCH_CHECK();
-  loss_final_kernel<<<1, 32, 0, st>>>(ts->loss_part, LOSS_BLOCKS, pm_blocks, gs_flow, gs_pm, gs_mask, io.losses);
-  DIM_LAUNCH_CHECK();
+  if (io.pc_model) {
+    if (int rc = transform3d_fwd_launch(io.pc_model, ts->rot_n, ts->trans_est, io.src_pose, B, io.N, Tm, Tsd, 1, ts->pts_est, st)) return rc;
+    pm_loss_kernel<<<pm_blocks, 256, 0, st>>>(ts->pts_est, io.pc_observed, io.pc_weights, (size_t)B * 3 * io.N, 0.1f, gs_pm, ts->dpts, ts->loss_part);
+    DIM_LAUNCH_CHECK();
+  }
+  if (io.losses) {
+    loss_final_kernel<<<1, 32, 0, st>>>(ts->loss_part, LOSS_BLOCKS, io.pc_model ? pm_blocks : 0, gs_flow, gs_pm, gs_mask, io.losses);
+    DIM_LAUNCH_CHECK();
+  }
+  if (io.rot_raw) DIM_CHECK(cudaMemcpyAsync(io.rot_raw, ts->rot_raw, (size_t)B * 16, cudaMemcpyDeviceToDevice, st));
   if (io.rot_est_norm) DIM_CHECK(cudaMemcpyAsync(io.rot_est_norm, ts->rot_n, (size_t)B * 16, cudaMemcpyDeviceToDevice, st));
   if (io.trans_est) DIM_CHECK(cudaMemcpyAsync(io.trans_est, ts->trans_est, (size_t)B * 12, cudaMemcpyDeviceToDevice, st));
   if (G == nullptr) return 0;  // forward only (non-FAST_TEST outputs)

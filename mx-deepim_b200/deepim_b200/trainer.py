@@ -131,9 +131,30 @@ class Trainer:
             _p(z["zoom_mask_rendered"]), _p(z["zoom_factor"]), _p(z["zoom_flow"]), _p(z["zoom_flow_weights"]),
             _p(z["zoom_mask_gt_observed"]), _p(z["src_pose"]), _p(z["point_cloud_model"]), _p(z["point_cloud_weights"]),
             _p(z["point_cloud_observed"]), B, N, _p(out["rot_est_norm"]), _p(out["trans_est"]), _p(out["flow_est"]),
-            _p(out["mask_prob"]), _p(out["losses"]), _p(self.grads) if backward else None,
+            _p(out["mask_prob"]), _p(out["losses"]), _p(self.grads) if backward else None, None,
             *((self._bucket_events() + (len(self.buckets),)) if (backward and overlap) else (None, None, 0)), self._stream()))
         return out
+
+    def test_forward_full(self, batch, K):
+        """The non-FAST_TEST test graph (get_test_symbol_share, deepIM_flownet.py:548-735 with FAST_TEST: False):
+        se3 = [rot_raw, invZoomTrans(trans)], mask_observed_pred = round(invZoomMask(sigmoid(mask logits))),
+        flow_est = invZoomFlow(upsampled flow x NORMALIZE_FLOW), plus the zoomed intermediates the graph also returns.
+        batch: image_observed/rendered (B,3,H,W), mask_observed/rendered (B,1,H,W), src_pose (B,3,4), pixel_means_rgb."""
+        ctx = self.ctx
+        zo, zg, zr, zf, bbox, status = ctx.zoom_mask(batch["mask_observed"], batch["mask_observed"], batch["mask_rendered"],
+                                                     batch["src_pose"], K)
+        zio, zir = ctx.zoom_image_with_factor(zf, batch["image_observed"], batch["image_rendered"], batch["pixel_means_rgb"])
+        B = zio.shape[0]
+        rot, trans = ctx._new((B, 4)), ctx._new((B, 3))
+        zflow, zprob = ctx._new((B, 2, ctx.H, ctx.W)), ctx._new((B, 1, ctx.H, ctx.W))
+        check(lib.dim_train_forward_backward(ctx._h, _p(zio), _p(zir), _p(zo), _p(zr), _p(zf), None, None, None, None, None, None,
+                                             None, B, 0, None, _p(trans), _p(zflow), _p(zprob), None, None, _p(rot), None, None, 0,
+                                             self._stream()))
+        mask_pred = torch.round(ctx.zoom_mask_with_factor(zf, zprob, True))
+        flow_est, _ = ctx.zoom_flow(zf, zflow, None, True)
+        return {"se3": torch.cat([rot, trans], dim=1), "zoom_factor": zf, "mask_observed_pred": mask_pred, "flow_est": flow_est,
+                "zoom_mask_observed_pred": zprob, "zoom_flow_est": zflow, "zoom_mask_observed": zo, "zoom_image_observed": zio,
+                "zoom_image_rendered": zir, "bbox": bbox}
 
     def allreduce(self, dist):
         if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:

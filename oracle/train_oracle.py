@@ -187,3 +187,21 @@ def sgd_update(weights, mom, grads, lr=1e-4, momentum=0.975, wd=5e-4, rescale_gr
         g = rescale_grad * grads[k] + (wd * w if k.endswith("_weight") else 0.0)
         mom[k] = (np.float32(momentum) * mom[k] - np.float32(lr) * g).astype(np.float32)
         w += mom[k]
+
+
+def test_forward_full(weights, image_observed, image_rendered, mask_observed, mask_rendered, src_pose, K, means_rgb):
+    """Non-FAST_TEST test graph (get_test_symbol_share, deepIM_flownet.py:548-735): se3, mask_observed_pred (invZoomMask of
+    the sigmoid mask, rounded), flow_est (invZoomFlow of the upsampled flow x NORMALIZE_FLOW) and the zoomed intermediates."""
+    zo, _, zr, zf, bbox = O.zoom_mask(mask_observed, mask_observed, mask_rendered, src_pose.astype(np.float32), K)
+    zio, zir = O.zoom_image_with_factor(zf, image_observed, image_rendered, np.asarray(means_rgb, np.float32))
+    B, _, H, W = zio.shape
+    zin = {"zoom_image_observed": zio, "zoom_image_rendered": zir, "zoom_mask_observed": zo, "zoom_mask_rendered": zr}
+    z1 = np.zeros((B, 3, 1), np.float32)
+    labels = {"zoom_factor": zf, "zoom_flow": np.zeros((B, 2, H, W), np.float32), "zoom_flow_weights": np.zeros((B, 2, H, W), np.float32),
+              "zoom_mask_gt_observed": np.zeros((B, 1, H, W), np.float32), "src_pose": src_pose.astype(np.float32),
+              "point_cloud_model": z1, "point_cloud_weights": z1, "point_cloud_observed": z1}
+    out, _ = graph(weights, zin, labels, requires_grad=False)
+    mask_pred = np.round(O.zoom_mask_with_factor(zf, out["mask_prob"], True))
+    flow_est, _ = O.zoom_flow(zf, out["flow_est"], None, True)
+    return {"se3": np.concatenate([out["rot_raw"], out["trans_est"]], axis=1), "zoom_factor": zf, "mask_observed_pred": mask_pred,
+            "flow_est": flow_est, "zoom_mask_observed_pred": out["mask_prob"], "zoom_flow_est": out["flow_est"], "bbox": bbox}

@@ -166,3 +166,24 @@ def test_inner_iteration_loop_like_module_fit(setup):
             for k in ("image_rendered", "mask_rendered", "src_pose", "flow", "flow_weights"):
                 b[k] = upd[k]
     assert all(np.isfinite(objs)) and len(objs) == 4
+
+
+def test_full_test_graph_outputs(setup):
+    """FAST_TEST: False outputs of the test symbol (deepIM_flownet.py:622-713): unzoomed flow estimate and mask
+    prediction next to se3, through the forward-only mode of the training entry point."""
+    B, meshes, w, batch, ctx, tr = setup
+    tr2_w = tr.get_params()   # whatever the earlier tests left in the context
+    b = {k: dev(batch[k]) for k in ("image_observed", "image_rendered", "mask_observed", "mask_rendered", "src_pose")}
+    b["pixel_means_rgb"] = MEANS.astype(np.float32)
+    got = tr.test_forward_full(b, K)
+    ref = T.test_forward_full(tr2_w, batch["image_observed"], batch["image_rendered"], batch["mask_observed"], batch["mask_rendered"],
+                              batch["src_pose"], K, MEANS)
+    assert np.array_equal(got["zoom_factor"].cpu().numpy(), ref["zoom_factor"])
+    assert np.array_equal(got["bbox"].cpu().numpy(), ref["bbox"])
+    se3 = got["se3"].cpu().numpy()
+    assert np.abs(se3[:, :4] - ref["se3"][:, :4]).max() < 2e-2 and np.abs(se3[:, 4:] - ref["se3"][:, 4:]).max() < 2e-3   # bf16 mode
+    assert np.abs(got["zoom_mask_observed_pred"].cpu().numpy() - ref["zoom_mask_observed_pred"]).max() < 2e-2
+    fe, rfe = got["flow_est"].cpu().numpy(), ref["flow_est"]
+    assert np.abs(fe - rfe).max() < 3e-2 * max(np.abs(rfe).max(), 1.0)
+    mp, rmp = got["mask_observed_pred"].cpu().numpy(), ref["mask_observed_pred"]
+    assert set(np.unique(mp)) <= {0.0, 1.0} and (mp != rmp).mean() < 5e-3   # probabilities near the 0.2 threshold may flip
