@@ -514,4 +514,74 @@ int transform_u8_obs4_launch(dim_ctx *ctx, const uint8_t *bgr, int B, const doub
   return 0;
 }
 
+// ------------------------------------------------------------------------------- ADD / ADI
+// lib/utils/pose_error.py:72-108 in float64: ADD = mean_p |(R^ p + t^) - (R p + t)|, ADI = mean over the GT-transformed
+// points of the distance to the nearest ESTIMATE-transformed point (cKDTree(pts_est).query(pts_gt)): brute force, one block
+// per pose pair, the estimate cloud staged through shared memory in tiles.  Fixed-order block reduction (deterministic).
+__global__ void __launch_bounds__(256) pose_error_kernel(const double *pose_est, const double *pose_gt, const float *pts, int N,
+                                                         int symmetric, double *out) {
+  __shared__ double Pe[12], Pg[12];
+  __shared__ double tile[256 * 3];
+  __shared__ double red[256];
+  const int m = blockIdx.x;
+  if (threadIdx.x < 12) { Pe[threadIdx.x] = pose_est[12 * m + threadIdx.x]; Pg[threadIdx.x] = pose_gt[12 * m + threadIdx.x]; }
+  __syncthreads();
+  double acc = 0.0;
+  if (!symmetric) {
+    for (int n = threadIdx.x; n < N; n += 256) {
+      const double x = pts[3 * n], y = pts[3 * n + 1], z = pts[3 * n + 2];
+      double d2 = 0.0;
+      for (int r = 0; r < 3; ++r) {
+        const double e = ((Pe[4 * r] * x + Pe[4 * r + 1] * y) + Pe[4 * r + 2] * z) + Pe[4 * r + 3];
+        const double g = ((Pg[4 * r] * x + Pg[4 * r + 1] * y) + Pg[4 * r + 2] * z) + Pg[4 * r + 3];
+        d2 += (e - g) * (e - g);
+      }
+      acc += sqrt(d2);
+    }
+  } else {
+    for (int n0 = 0; n0 < N; n0 += 256) {  // every thread owns GT point n0 + tid; loop over all estimate points by tiles
+      const int n = n0 + threadIdx.x;
+      double gx = 0, gy = 0, gz = 0;
+      if (n < N) {
+        const double x = pts[3 * n], y = pts[3 * n + 1], z = pts[3 * n + 2];
+        gx = ((Pg[0] * x + Pg[1] * y) + Pg[2] * z) + Pg[3];
+        gy = ((Pg[4] * x + Pg[5] * y) + Pg[6] * z) + Pg[7];
+        gz = ((Pg[8] * x + Pg[9] * y) + Pg[10] * z) + Pg[11];
+      }
+      double best = 1e300;
+      for (int k0 = 0; k0 < N; k0 += 256) {
+        __syncthreads();
+        const int k = k0 + threadIdx.x;
+        if (k < N) {
+          const double x = pts[3 * k], y = pts[3 * k + 1], z = pts[3 * k + 2];
+          tile[3 * threadIdx.x] = ((Pe[0] * x + Pe[1] * y) + Pe[2] * z) + Pe[3];
+          tile[3 * threadIdx.x + 1] = ((Pe[4] * x + Pe[5] * y) + Pe[6] * z) + Pe[7];
+          tile[3 * threadIdx.x + 2] = ((Pe[8] * x + Pe[9] * y) + Pe[10] * z) + Pe[11];
+        }
+        __syncthreads();
+        const int cnt = min(256, N - k0);
+        for (int j = 0; j < cnt; ++j) {
+          const double dx = tile[3 * j] - gx, dy = tile[3 * j + 1] - gy, dz = tile[3 * j + 2] - gz;
+          const double d2 = (dx * dx + dy * dy) + dz * dz;
+          best = d2 < best ? d2 : best;
+        }
+      }
+      if (n < N) acc += sqrt(best);
+    }
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[m] = red[0] / (double)N;
+}
+int pose_error_launch(const double *pose_est, const double *pose_gt, int M, const float *pts, int N, int symmetric, double *out,
+                      cudaStream_t st) {
+  pose_error_kernel<<<M, 256, 0, st>>>(pose_est, pose_gt, pts, N, symmetric, out);
+  DIM_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace dim

@@ -1,0 +1,94 @@
+"""ADD / ADI evaluation on the device -- the error metric of the headline benchmark.
+
+Mirrors lib/utils/pose_error.py:72-108 (`add`, `adi`) and the counting / Simpson-AUC part of
+LM6D_REFINE.evaluate_pose_add (lib/dataset/LM6D_REFINE.py:372-512): accuracy at 0.02 / 0.05 / 0.10 x diameter and the
+area under the accuracy-vs-threshold curve over [0, 0.1 d] with step 1e-4 (scipy.integrate.simps, dx = 1e-4, / 0.1)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from ._capi import check, lib
+
+SYMMETRIC_CLASSES = ("eggbox", "glue", "bowl", "cup")  # LM6D_REFINE.py:418-420
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def pose_errors(ctx, poses_est, poses_gt, points, symmetric=False):
+    """poses_est / poses_gt: [M,3,4] float64 (CUDA tensors or numpy), points [N,3] float32.  Returns float64 CUDA [M]."""
+    dev = ctx.device
+    pe = torch.as_tensor(poses_est, dtype=torch.float64, device=dev).contiguous()
+    pg = torch.as_tensor(poses_gt, dtype=torch.float64, device=dev).contiguous()
+    pts = torch.as_tensor(points, dtype=torch.float32, device=dev).contiguous()
+    out = torch.empty(pe.shape[0], dtype=torch.float64, device=dev)
+    check(lib.dim_pose_error(ctx._h, _p(pe), _p(pg), pe.shape[0], _p(pts), pts.shape[0], int(symmetric), _p(out),
+                             C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return out
+
+
+def add(ctx, R_est, t_est, R_gt, t_gt, pts):
+    """Call-compatible with lib/utils/pose_error.py:add (single pose pair)."""
+    pe = np.hstack([np.asarray(R_est, np.float64), np.asarray(t_est, np.float64).reshape(3, 1)])[None]
+    pg = np.hstack([np.asarray(R_gt, np.float64), np.asarray(t_gt, np.float64).reshape(3, 1)])[None]
+    return float(pose_errors(ctx, pe, pg, pts, False)[0])
+
+
+def adi(ctx, R_est, t_est, R_gt, t_gt, pts):
+    """Call-compatible with lib/utils/pose_error.py:adi."""
+    pe = np.hstack([np.asarray(R_est, np.float64), np.asarray(t_est, np.float64).reshape(3, 1)])[None]
+    pg = np.hstack([np.asarray(R_gt, np.float64), np.asarray(t_gt, np.float64).reshape(3, 1)])[None]
+    return float(pose_errors(ctx, pe, pg, pts, True)[0])
+
+
+def simpson(y, dx):
+    """Composite Simpson rule as scipy.integrate.simps(y, dx=dx) with the default even='avg' handling for an even
+    number of samples (average of 'first N-2 intervals + trapezoid on the last' and 'trapezoid on the first + last N-2')."""
+    y = np.asarray(y, np.float64)
+    n = len(y)
+    if n % 2 == 1:
+        return dx / 3.0 * (y[0] + y[-1] + 4 * y[1:-1:2].sum() + 2 * y[2:-1:2].sum())
+    first = simpson(y[:-1], dx) + 0.5 * dx * (y[-1] + y[-2])
+    last = simpson(y[1:], dx) + 0.5 * dx * (y[0] + y[1])
+    return 0.5 * (first + last)
+
+
+def evaluate_pose_add(ctx, poses_est, poses_gt, cls_idx, points_per_class, diameters, symmetric_flags):
+    """poses_est [n_iter,M,3,4], poses_gt [M,3,4], cls_idx [M]; per class: points [N,3], diameter, symmetric flag.
+    Returns dict with per-class and mean accuracies (percent) at 0.02/0.05/0.10 d and the AUC ('mean'), per iteration,
+    computed exactly like LM6D_REFINE.evaluate_pose_add (errors come from the device kernel)."""
+    poses_est = np.asarray(poses_est, np.float64)
+    poses_gt = np.asarray(poses_gt, np.float64)
+    cls_idx = np.asarray(cls_idx)
+    n_iter = poses_est.shape[0]
+    dx = 0.0001
+    th = np.arange(0, 0.1, dx).astype(np.float32)
+    res = {"classes": {}, "mean": {}}
+    sums = {k: np.zeros(n_iter) for k in ("auc", "0.02", "0.05", "0.10")}
+    nvalid = 0
+    for c, pts in enumerate(points_per_class):
+        sel = np.nonzero(cls_idx == c)[0]
+        if len(sel) == 0:
+            continue
+        nvalid += 1
+        d = float(diameters[c])
+        per = {k: [] for k in ("auc", "0.02", "0.05", "0.10")}
+        errs = []
+        for it in range(n_iter):
+            e = pose_errors(ctx, poses_est[it, sel], poses_gt[sel], pts, bool(symmetric_flags[c])).cpu().numpy()
+            errs.append(e)
+            n = float(len(sel))
+            for k, f in (("0.02", 0.02), ("0.05", 0.05), ("0.10", 0.10)):
+                per[k].append(100.0 * float((e < np.float32(f * d)).sum()) / n)
+            curve = np.array([(e < t).sum() for t in (th * np.float32(d))], np.float32) / n
+            per["auc"].append(simpson(curve, dx) / 0.1 * 100.0)
+        for k in per:
+            sums[k] += np.array(per[k])
+        res["classes"][c] = dict(per, errors=np.stack(errs))
+    for k in sums:
+        res["mean"][k] = (sums[k] / max(nvalid, 1)).tolist()
+    return res

@@ -239,3 +239,45 @@ def test_zoom_image_and_group_picker(env):
     x4 = rng.normal(size=(B, 2 * 3, 5, 7)).astype(np.float32)
     (p4,) = _run(ops.create("GroupPicker", group_num="2"), [dev(x4), dev(np.array([1.0, 0.0], np.float32))], [(B, 3, 5, 7)])
     assert np.array_equal(p4.cpu().numpy(), np.stack([x4[0, 3:6], x4[1, 0:3]]))
+
+
+def test_pose_error_add_adi_against_reference_goldens(env):
+    """Device ADD / ADI (dim_pose_error) against the fixtures generated from the live lib/utils/pose_error.py
+    (tests/golden/ref_pose_error.npz), and the evaluate_pose_add bookkeeping (LM6D_REFINE.py:372-512)."""
+    import os
+    from deepim_b200 import pose_eval
+    ctx, meshes = env
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_pose_error.npz"))
+    n = d["R_est"].shape[0]
+    pe = np.concatenate([d["R_est"], d["t_est"][:, :, None]], axis=2)
+    pg = np.concatenate([d["R_gt"], d["t_gt"][:, :, None]], axis=2)
+    add = pose_eval.pose_errors(ctx, pe, pg, d["pts"], False).cpu().numpy()
+    adi = pose_eval.pose_errors(ctx, pe, pg, d["pts"], True).cpu().numpy()
+    np.testing.assert_allclose(add, d["add"], rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(adi, d["adi"], rtol=1e-12, atol=1e-15)
+    assert abs(pose_eval.add(ctx, d["R_est"][0], d["t_est"][0], d["R_gt"][0], d["t_gt"][0], d["pts"]) - d["add"][0]) < 1e-14
+    assert abs(pose_eval.adi(ctx, d["R_est"][1], d["t_est"][1], d["R_gt"][1], d["t_gt"][1], d["pts"]) - d["adi"][1]) < 1e-14
+    # a larger cloud than one tile, ADI vs the oracle's cKDTree restatement
+    pts = meshes[1].verts.astype(np.float32)
+    obs, ini = synth.sample_pose_pairs(6, 5)
+    e = pose_eval.pose_errors(ctx, ini, obs, pts, True).cpu().numpy()
+    for i in range(6):
+        assert abs(e[i] - O.adi_metric(ini[i][:, :3], ini[i][:, 3], obs[i][:, :3], obs[i][:, 3], pts)) < 1e-12
+    # evaluator: two classes (second one scored with ADI), two "iterations"
+    cls = np.array([0, 1, 0, 1, 1, 0])
+    est = np.stack([ini, 0.5 * (ini + obs)])          # iteration 2 = closer to the target (not a rotation; irrelevant here)
+    ptsc = [meshes[0].verts.astype(np.float32), pts]
+    diam = [0.17, 0.10]
+    res = pose_eval.evaluate_pose_add(ctx, est, obs, cls, ptsc, diam, [False, True])
+    for c in (0, 1):
+        sel = cls == c
+        for it in range(2):
+            f = O.adi_metric if c == 1 else O.add_metric
+            err = np.array([f(est[it, i][:, :3], est[it, i][:, 3], obs[i][:, :3], obs[i][:, 3], ptsc[c]) for i in np.nonzero(sel)[0]])
+            np.testing.assert_allclose(res["classes"][c]["errors"][it], err, rtol=1e-10)
+            assert res["classes"][c]["0.10"][it] == 100.0 * (err < np.float32(0.10 * diam[c])).sum() / sel.sum()
+    assert res["mean"]["auc"][1] >= res["mean"]["auc"][0]
+    # Simpson rule of the AUC = scipy.integrate.simps(even='avg') of the reference's era: exact for odd sample counts,
+    # first/last-trapezoid average for the 1000-sample threshold grid
+    y = np.linspace(0, 1, 1001) ** 2
+    assert abs(pose_eval.simpson(y, 1e-3) - 1.0 / 3.0) < 1e-12
