@@ -256,11 +256,11 @@ DIM_API int32_t dim_profile_enable(dim_ctx *ctx, int32_t enable);
 DIM_API int32_t dim_profile_read(dim_ctx *ctx, float *ms4, int32_t *iterations);
 
 /* ADD / ADI pose error (lib/utils/pose_error.py:72-108; LM6D_REFINE.evaluate_pose_add l.418-424 picks ADI for the
- * symmetric classes): poses f64[M,3,4] (device), points f32[N,3] model points (device), err f64[M].
+ * symmetric classes): poses f64[M,3,4] (device), points f64[N,3] model points (device), err f64[M].
  * symmetric = 0: mean point distance; 1: mean distance from every GT-transformed point to the nearest
  * estimate-transformed point (brute force, float64). */
 DIM_API int32_t dim_pose_error(dim_ctx *ctx, const double *poses_est, const double *poses_gt, int32_t M,
-                               const float *points, int32_t N, int32_t symmetric, double *err,
+                               const double *points, int32_t N, int32_t symmetric, double *err,
                                void *stream);
 
 /* ---------------------------------------------------------------------------------------------

@@ -23,7 +23,7 @@ int zoom_gather_launch(dim_ctx *, int mode, const float *src, float *dst, const 
                        const float *param, cudaStream_t);
 int zoom_factor_launch(dim_ctx *, const float *, const float *, int C, const float *, int B, const float *K9, float *,
                        int *, int *, cudaStream_t, const float *img_means = nullptr);
-int pose_error_launch(const double *, const double *, int M, const float *, int N, int symmetric, double *, cudaStream_t);
+int pose_error_launch(const double *, const double *, int M, const double *, int N, int symmetric, double *, cudaStream_t);
 int group_pick_launch(const float *, const float *, int B, int Ctot, int groups, size_t n, float *, int backward, cudaStream_t);
 int zoom_factor_from_ren_launch(dim_ctx *, const int *, const float *, int B, const float *K9, float *, int *, int *,
                                 cudaStream_t);
@@ -500,7 +500,7 @@ DIM_API int32_t dim_debug_layer_geometry(dim_ctx *ctx, int32_t idx, int32_t *out
 
 
 // ADD / ADI (lib/utils/pose_error.py:72-108)
-DIM_API int32_t dim_pose_error(dim_ctx *ctx, const double *poses_est, const double *poses_gt, int32_t M, const float *points,
+DIM_API int32_t dim_pose_error(dim_ctx *ctx, const double *poses_est, const double *poses_gt, int32_t M, const double *points,
                                int32_t N, int32_t symmetric, double *err, void *stream) {
   DIM_REQUIRE(ctx && poses_est && poses_gt && points && err && M >= 1 && N >= 1, "dim_pose_error: bad argument");
   return pose_error_launch(poses_est, poses_gt, M, points, N, symmetric, err, (cudaStream_t)stream);

@@ -518,7 +518,7 @@ int transform_u8_obs4_launch(dim_ctx *ctx, const uint8_t *bgr, int B, const doub
 // lib/utils/pose_error.py:72-108 in float64: ADD = mean_p |(R^ p + t^) - (R p + t)|, ADI = mean over the GT-transformed
 // points of the distance to the nearest ESTIMATE-transformed point (cKDTree(pts_est).query(pts_gt)): brute force, one block
 // per pose pair, the estimate cloud staged through shared memory in tiles.  Fixed-order block reduction (deterministic).
-__global__ void __launch_bounds__(256) pose_error_kernel(const double *pose_est, const double *pose_gt, const float *pts, int N,
+__global__ void __launch_bounds__(256) pose_error_kernel(const double *pose_est, const double *pose_gt, const double *pts, int N,
                                                          int symmetric, double *out) {
   __shared__ double Pe[12], Pg[12];
   __shared__ double tile[256 * 3];
@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(256) pose_error_kernel(const double *pose_est,
   }
   if (threadIdx.x == 0) out[m] = red[0] / (double)N;
 }
-int pose_error_launch(const double *pose_est, const double *pose_gt, int M, const float *pts, int N, int symmetric, double *out,
+int pose_error_launch(const double *pose_est, const double *pose_gt, int M, const double *pts, int N, int symmetric, double *out,
                       cudaStream_t st) {
   pose_error_kernel<<<M, 256, 0, st>>>(pose_est, pose_gt, pts, N, symmetric, out);
   DIM_LAUNCH_CHECK();

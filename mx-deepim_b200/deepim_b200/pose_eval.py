@@ -20,11 +20,11 @@ def _p(t):
 
 
 def pose_errors(ctx, poses_est, poses_gt, points, symmetric=False):
-    """poses_est / poses_gt: [M,3,4] float64 (CUDA tensors or numpy), points [N,3] float32.  Returns float64 CUDA [M]."""
+    """poses_est / poses_gt: [M,3,4] float64 (CUDA tensors or numpy), points [N,3] (float64 on the device).  Returns float64 CUDA [M]."""
     dev = ctx.device
     pe = torch.as_tensor(poses_est, dtype=torch.float64, device=dev).contiguous()
     pg = torch.as_tensor(poses_gt, dtype=torch.float64, device=dev).contiguous()
-    pts = torch.as_tensor(points, dtype=torch.float32, device=dev).contiguous()
+    pts = torch.as_tensor(np.asarray(points, np.float64), dtype=torch.float64, device=dev).contiguous()
     out = torch.empty(pe.shape[0], dtype=torch.float64, device=dev)
     check(lib.dim_pose_error(ctx._h, _p(pe), _p(pg), pe.shape[0], _p(pts), pts.shape[0], int(symmetric), _p(out),
                              C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
