@@ -111,3 +111,31 @@ def test_shard_range_and_chunks():
     assert sharding.chunks(5, 5, 16) == []
     with pytest.raises(ValueError):
         sharding.shard_range(4, 2, 2)
+
+
+def test_mxnet_params_reader_writer(tmp_path):
+    """MXNet .params container (mx.nd.save dict; lib/utils/load_model.py:10-30): writer/reader round trip, the legacy
+    and V1 record layouts, and a byte string assembled by hand from the documented layout.  Format parity is unpinned
+    (no sample checkpoint in the reference, MXNet not installable): see the module docstring."""
+    import struct
+    from deepim_b200 import mx_params, synth
+    w = synth.make_weights(0)
+    small = {k: w[k] for k in ("flow_conv1_weight", "flow_conv1_bias", "rot_weight", "trans_bias")}
+    mx_params.save_checkpoint(str(tmp_path / "net"), 8, small, {"bn_moving_mean": np.arange(4, dtype=np.float32)})
+    arg, aux = mx_params.load_checkpoint(str(tmp_path / "net"), 8)
+    assert set(arg) == set(small) and list(aux) == ["bn_moving_mean"]
+    for k in small:
+        assert arg[k].dtype == np.float32 and np.array_equal(arg[k], small[k])
+    # hand-assembled: one V2 float32 (2,3), one V1 int32 (2,), one legacy float64 (1,2)
+    a0, a1, a2 = np.arange(6, dtype=np.float32).reshape(2, 3), np.array([7, -9], np.int32), np.array([[0.5, 1.5]])
+    rec0 = struct.pack("<IiI2qiii", 0xF993FAC9, 0, 2, 2, 3, 1, 0, 0) + a0.tobytes()
+    rec1 = struct.pack("<II1qiii", 0xF993FAC8, 1, 2, 2, 0, 4) + a1.tobytes()
+    rec2 = struct.pack("<I2Iiii", 2, 1, 2, 1, 0, 1) + a2.tobytes()
+    names = [b"arg:a0", b"arg:a1", b"aux:a2"]
+    blob = struct.pack("<QQQ", 0x112, 0, 3) + rec0 + rec1 + rec2 + struct.pack("<Q", 3) + b"".join(struct.pack("<Q", len(n)) + n for n in names)
+    d = mx_params.load(blob)
+    assert np.array_equal(d["arg:a0"], a0) and np.array_equal(d["arg:a1"], a1) and np.array_equal(d["aux:a2"], a2)
+    with pytest.raises(ValueError):
+        mx_params.load(b"\x00" * 32)
+    with pytest.raises(ValueError):
+        mx_params.load(blob[:-40])
