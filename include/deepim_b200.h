@@ -87,6 +87,19 @@ DIM_API int32_t dim_zoom_image_with_factor_fwd(dim_ctx *ctx, const float *zoom_f
                                                float *zoom_image_observed,
                                                float *zoom_image_rendered, void *stream);
 
+/* Lit renderer (lib/render_glumpy/render_py_light_modelnet_multi.py:36-79 shader, 131-175 render): Lambert shading
+ * colour = texel * ((1 - brightness_ratio) + brightness_ratio * clamp(cos(normal, light - position), 0, 1)) *
+ * light_intensity, quantised to 8 bits like the framebuffer the reference reads back.  normals f32[V,3] (host) per
+ * class; light_position / light_intensity f32[B,3] (device), position in the GL camera frame (x, -y, -z of the
+ * OpenCV frame).  Outputs as dim_render (out_bgr holds the quantised colours as floats). */
+DIM_API int32_t dim_mesh_upload_normals(dim_ctx *ctx, int32_t cls_idx, const float *normals_host, int32_t V);
+DIM_API int32_t dim_render_lit(dim_ctx *ctx, const int32_t *cls_idx, const float *pose, int32_t B,
+                               const float *K9_host, float znear, float zfar,
+                               const double *pixel_means_rgb_host, const float *light_position,
+                               const float *light_intensity, float brightness_ratio, float *out_image,
+                               float *out_depth, float *out_mask, float *out_bgr, int32_t *out_bbox,
+                               void *stream);
+
 /* ZoomImage forward (zoom_image.py:26-107, the INPUT_MASK: False front end): the two boxes come from the
  * images themselves, valid = sum_c(image + pixel_mean_c) > 0.01; centre / crop / sampling as ZoomMask +
  * ZoomImageWithFactor.  pixel_means_rgb_host = the op's (already reversed) pixel_means attr.

@@ -17,8 +17,9 @@ void set_error(const char *fmt, ...) {
 }
 
 // implemented in raster.cu / zoom.cu / geom.cu / net.cu
+struct LitParams { const float *light_pos, *light_int; float a0, a1; };  // device [B,3] each; a0 = 1 - ratio, a1 = ratio
 int render_launch(dim_ctx *, const int *, const float *, int, const float *, float, float, const double *, int, float *,
-                  float *, float *, float *, int *, float4 *, cudaStream_t);
+                  float *, float *, float *, int *, float4 *, cudaStream_t, const LitParams *lit = nullptr);
 int zoom_gather_launch(dim_ctx *, int mode, const float *src, float *dst, const float *zf, int B, int C, int inv,
                        const float *param, cudaStream_t);
 int zoom_factor_launch(dim_ctx *, const float *, const float *, int C, const float *, int B, const float *K9, float *,
@@ -145,7 +146,7 @@ DIM_API int32_t dim_ctx_create(int32_t device, int32_t max_batch, int32_t H, int
   rc |= ctx_alloc(ctx, &ctx->poses_dev, 8 * Bm * 12);
   rc |= ctx_alloc(ctx, &ctx->se3_hist_dev, 8 * Bm * 7);
   if (rc) { dim_ctx_destroy(ctx); return 12; }
-  ctx->meshes_host.assign(max_classes, MeshDev{nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0});
+  ctx->meshes_host.assign(max_classes, MeshDev{nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, nullptr});
   DIM_CHECK(cudaMemset(ctx->meshes, 0, sizeof(MeshDev) * max_classes));
   DIM_CHECK(cudaMemset(ctx->vis, 0xFF, sizeof(unsigned long long) * Bm * P));  // all pixels empty
   DIM_CHECK(cudaMemset(ctx->pverts, 0, sizeof(PVert) * Bm * max_verts));
@@ -180,7 +181,7 @@ DIM_API int32_t dim_mesh_upload(dim_ctx *ctx, int32_t cls, const float *verts, c
   DIM_CHECK(cudaMemcpy(du, uvs, sizeof(float) * 2 * V, cudaMemcpyHostToDevice));
   DIM_CHECK(cudaMemcpy(df, faces, sizeof(int) * 3 * F, cudaMemcpyHostToDevice));
   DIM_CHECK(cudaMemcpy(dt, tex, (size_t)3 * Th * Tw, cudaMemcpyHostToDevice));
-  m.verts = dv; m.uvs = du; m.faces = df; m.tex = dt; m.V = V; m.F = F; m.Th = Th; m.Tw = Tw;
+  m.verts = dv; m.uvs = du; m.faces = df; m.tex = dt; m.V = V; m.F = F; m.Th = Th; m.Tw = Tw; m.normals = nullptr;
   ctx->meshes_host[cls] = m;
   DIM_CHECK(cudaMemcpy(ctx->meshes + cls, &m, sizeof(MeshDev), cudaMemcpyHostToDevice));
   return 0;
@@ -192,6 +193,29 @@ DIM_API int32_t dim_render(dim_ctx *ctx, const int32_t *cls_idx, const float *po
   DIM_REQUIRE(ctx && cls_idx && pose && K9, "dim_render: NULL argument");
   return render_launch(ctx, cls_idx, pose, B, K9, zn, zf, means, trunc_u8, out_image, out_depth, out_mask, out_bgr,
                        out_bbox, nullptr, (cudaStream_t)stream);
+}
+
+// lit renderer (lib/render_glumpy/render_py_light_modelnet_multi.py)
+DIM_API int32_t dim_mesh_upload_normals(dim_ctx *ctx, int32_t cls, const float *normals, int32_t V) {
+  DIM_REQUIRE(ctx && normals && cls >= 0 && cls < ctx->max_classes, "dim_mesh_upload_normals: bad argument");
+  MeshDev &m = ctx->meshes_host[cls];
+  DIM_REQUIRE(m.V > 0 && m.V == V, "dim_mesh_upload_normals: upload the mesh first; V must match");
+  float *dn;
+  if (ctx_alloc(ctx, &dn, (size_t)3 * V)) return 12;
+  DIM_CHECK(cudaMemcpy(dn, normals, sizeof(float) * 3 * V, cudaMemcpyHostToDevice));
+  m.normals = dn;
+  DIM_CHECK(cudaMemcpy(ctx->meshes + cls, &m, sizeof(MeshDev), cudaMemcpyHostToDevice));
+  return 0;
+}
+DIM_API int32_t dim_render_lit(dim_ctx *ctx, const int32_t *cls_idx, const float *pose, int32_t B, const float *K9, float zn,
+                               float zf, const double *means, const float *light_pos, const float *light_int,
+                               float brightness_ratio, float *out_image, float *out_depth, float *out_mask, float *out_bgr,
+                               int32_t *out_bbox, void *stream) {
+  DIM_REQUIRE(ctx && cls_idx && pose && K9 && light_pos && light_int, "dim_render_lit: NULL argument");
+  for (auto &m : ctx->meshes_host) DIM_REQUIRE(m.V == 0 || m.normals != nullptr, "dim_render_lit: a mesh has no normals (dim_mesh_upload_normals)");
+  LitParams lit{light_pos, light_int, (float)(1.0 - (double)brightness_ratio), brightness_ratio};
+  return render_launch(ctx, cls_idx, pose, B, K9, zn, zf, means, 1, out_image, out_depth, out_mask, out_bgr, out_bbox, nullptr,
+                       (cudaStream_t)stream, &lit);
 }
 
 DIM_API int32_t dim_zoom_mask_fwd(dim_ctx *ctx, const float *mo, const float *mgt, const float *mr,

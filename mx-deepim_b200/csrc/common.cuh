@@ -57,6 +57,7 @@ struct MeshDev {
   const int *faces;     // [F,3]
   const uint8_t *tex;   // [Th,Tw,3]
   int V, F, Th, Tw;
+  const float *normals; // [V,3] per-vertex normals (lit renderer only; nullptr otherwise)
 };
 
 // ------------------------------------------------------------------------------------ network

@@ -24,6 +24,8 @@ namespace dim {
 
 static constexpr unsigned long long VIS_EMPTY = ~0ull;
 
+struct LitParams { const float *light_pos, *light_int; float a0, a1; };
+
 struct RasterParams {
   const MeshDev *meshes;
   const int *cls;
@@ -39,6 +41,10 @@ struct RasterParams {
   int trunc_u8;
   float *out_image, *out_depth, *out_mask, *out_bgr;
   float4 *out_ren4;  // [B,H,W] (R-mean, G-mean, B-mean, mask): the fused loop's layout
+  // lit renderer (render_py_light_modelnet_multi.py): per-instance light position / intensity, a0 + a1 * brightness
+  int lit;
+  const float *light_pos, *light_int;
+  float a0, a1;
 };
 
 __global__ void raster_init_kernel(int *vbox, int *bbox_ren, int B, int H, int W) {
@@ -280,7 +286,48 @@ __global__ void __launch_bounds__(256) raster_resolve_kernel(RasterParams p) {
       tx = min(max(tx, 0), m.Tw - 1);
       ty = min(max(ty, 0), m.Th - 1);
       const unsigned char *tp = m.tex + ((size_t)ty * m.Tw + tx) * 3;
-      float c0 = colour_of(tp[0], p.trunc_u8), c1 = colour_of(tp[1], p.trunc_u8), c2 = colour_of(tp[2], p.trunc_u8);
+      float c0, c1, c2;
+      if (p.lit) {
+        // Lambert shading, same float32 sequence as the CPU checker (see DESIGN.md "lit renderer")
+        const int iA = m.faces[3 * f];
+        int iB = m.faces[3 * f + 1], iC = m.faces[3 * f + 2];
+        if (edge_fn(pv[iA].X, pv[iA].Y, pv[iB].X, pv[iB].Y, pv[iC].X, pv[iC].Y) < 0) { const int tmp = iB; iB = iC; iC = tmp; }
+        const float w0 = b0 * A.iz, w1 = b1 * Bv.iz, w2 = b2 * Cv.iz;
+        const float *ps = p.pose + 12 * b;
+        float pm[3], nm[3], pc[3], nc[3];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+          pm[e] = ((w0 * m.verts[3 * iA + e] + w1 * m.verts[3 * iB + e]) + w2 * m.verts[3 * iC + e]) / iz;
+          nm[e] = ((w0 * m.normals[3 * iA + e] + w1 * m.normals[3 * iB + e]) + w2 * m.normals[3 * iC + e]) / iz;
+        }
+#pragma unroll
+        for (int rr = 0; rr < 3; ++rr) {
+          pc[rr] = ((ps[4 * rr] * pm[0] + ps[4 * rr + 1] * pm[1]) + ps[4 * rr + 2] * pm[2]) + ps[4 * rr + 3];
+          nc[rr] = (ps[4 * rr] * nm[0] + ps[4 * rr + 1] * nm[1]) + ps[4 * rr + 2] * nm[2];
+        }
+        const float *lp = p.light_pos + 3 * b, *li = p.light_int + 3 * b;
+        const float s0 = lp[0] - pc[0], s1 = lp[1] - (0.f - pc[1]), s2 = lp[2] - (0.f - pc[2]);
+        const float g0 = nc[0], g1 = 0.f - nc[1], g2 = 0.f - nc[2];
+        const float dot = (g0 * s0 + g1 * s1) + g2 * s2;
+        const float ls = sqrtf((s0 * s0 + s1 * s1) + s2 * s2), ln = sqrtf((g0 * g0 + g1 * g1) + g2 * g2);
+        const float den = ls * ln;
+        float br = 0.f;
+        if (den > 0.f) br = dot / den;
+        br = br < 1.f ? br : 1.f;
+        br = br > 0.f ? br : 0.f;
+        const float scale = p.a0 + p.a1 * br;
+        float q[3];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+          float col = ((float)tp[e] / 255.0f) * (scale * li[e]);
+          col = col < 1.f ? col : 1.f;
+          col = col > 0.f ? col : 0.f;
+          q[e] = rintf(col * 255.0f);
+        }
+        c0 = q[0]; c1 = q[1]; c2 = q[2];
+      } else {
+        c0 = colour_of(tp[0], p.trunc_u8); c1 = colour_of(tp[1], p.trunc_u8); c2 = colour_of(tp[2], p.trunc_u8);
+      }
       raw[k][0] = c0; raw[k][1] = c1; raw[k][2] = c2;
       // image.transform works in float64 and nd.array casts to float32 (lib/utils/image.py:583-594)
       if (p.trunc_u8) {
@@ -355,7 +402,7 @@ __global__ void raster_finish_kernel(int *bbox_ren, int *out_bbox, int B) {
 
 int render_launch(dim_ctx *ctx, const int *cls, const float *pose, int B, const float *K9, float zn, float zf,
                   const double *means, int trunc_u8, float *out_image, float *out_depth, float *out_mask,
-                  float *out_bgr, int *out_bbox, float4 *out_ren4, cudaStream_t st) {
+                  float *out_bgr, int *out_bbox, float4 *out_ren4, cudaStream_t st, const LitParams *lit) {
   DIM_REQUIRE(B >= 1 && B <= ctx->max_batch, "dim_render: batch exceeds max_batch");
   DIM_REQUIRE((ctx->W & 3) == 0, "dim_render: width must be a multiple of 4");
   RasterParams p;
@@ -370,6 +417,9 @@ int render_launch(dim_ctx *ctx, const int *cls, const float *pose, int B, const 
   p.trunc_u8 = trunc_u8;
   p.out_image = out_image; p.out_depth = out_depth; p.out_mask = out_mask; p.out_bgr = out_bgr;
   p.out_ren4 = out_ren4;
+  p.lit = lit ? 1 : 0;
+  p.light_pos = lit ? lit->light_pos : nullptr; p.light_int = lit ? lit->light_int : nullptr;
+  p.a0 = lit ? lit->a0 : 0.f; p.a1 = lit ? lit->a1 : 0.f;
   int maxV = 0, maxF = 0;
   for (auto &m : ctx->meshes_host) { maxV = maxV > m.V ? maxV : m.V; maxF = maxF > m.F ? maxF : m.F; }
   DIM_REQUIRE(maxV > 0 && maxF > 0, "dim_render: no mesh uploaded");

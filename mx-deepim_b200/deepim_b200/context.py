@@ -70,6 +70,12 @@ class Context:
         check(lib.dim_mesh_upload(self._h, cls_idx, v.ctypes.data, uv.ctypes.data, len(v), f.ctypes.data, len(f),
                                   tex.ctypes.data, tex.shape[0], tex.shape[1]))
         self.num_classes = max(self.num_classes, cls_idx + 1)
+        if getattr(mesh, "normals", None) is not None:
+            self.upload_normals(cls_idx, mesh.normals)
+
+    def upload_normals(self, cls_idx, normals):
+        n = np.ascontiguousarray(normals, np.float32)
+        check(lib.dim_mesh_upload_normals(self._h, cls_idx, n.ctypes.data, len(n)))
 
     def load_weights(self, weights: dict):
         """weights: name_weight / name_bias float32 arrays with MXNet layouts
@@ -105,6 +111,28 @@ class Context:
         means = farr(pixel_means_rgb, 3, C.c_double)
         check(lib.dim_render(self._h, _p(cls_idx), _p(pose), B, K9, znear, zfar, means, int(trunc_u8), _p(out["image"]),
                              _p(out["depth"]), _p(out["mask"]), _p(out["bgr"]), _p(out["bbox"]), _stream()))
+        return out
+
+    def render_lit(self, cls_idx, pose, K, light_position, light_intensity, brightness_ratio=0.7, znear=0.25, zfar=6.0,
+                   pixel_means_rgb=(0, 0, 0), want=("bgr", "depth")):
+        """Lambert-lit render (render_py_light_modelnet_multi.py:131-175).  light_position / light_intensity float32[B,3]
+        CUDA tensors (position in the GL camera frame)."""
+        B = pose.shape[0]
+        _chk(pose, torch.float32, (B, 3, 4), "pose")
+        _chk(cls_idx, torch.int32, (B,), "cls_idx")
+        _chk(light_position, torch.float32, (B, 3), "light_position")
+        _chk(light_intensity, torch.float32, (B, 3), "light_intensity")
+        out = {
+            "image": self._new((B, 3, self.H, self.W)) if "image" in want else None,
+            "depth": self._new((B, 1, self.H, self.W)) if "depth" in want else None,
+            "mask": self._new((B, 1, self.H, self.W)) if "mask" in want else None,
+            "bgr": self._new((B, self.H, self.W, 3)) if "bgr" in want else None,
+            "bbox": self._new((B, 4), torch.int32),
+        }
+        check(lib.dim_render_lit(self._h, _p(cls_idx), _p(pose), B, farr(np.asarray(K, np.float32).reshape(9), 9), znear, zfar,
+                                 farr(pixel_means_rgb, 3, C.c_double), _p(light_position), _p(light_intensity),
+                                 float(np.float32(brightness_ratio)), _p(out["image"]), _p(out["depth"]), _p(out["mask"]),
+                                 _p(out["bgr"]), _p(out["bbox"]), _stream()))
         return out
 
     # -------------------------------------------------------------------------------- zoom

@@ -129,6 +129,18 @@ def make_linemod_like_set(n: int = 13, seed: int = 2):
     return meshes
 
 
+def vertex_normals(mesh) -> np.ndarray:
+    """Area-weighted per-vertex normals [V,3] float32 (what an OBJ exporter writes as `vn`; the lit renderer reads them
+    through glumpy's objload, render_py_light_modelnet_multi.py:99-101)."""
+    v, f = mesh.verts.astype(np.float64), mesh.faces
+    fn = np.cross(v[f[:, 1]] - v[f[:, 0]], v[f[:, 2]] - v[f[:, 0]])
+    n = np.zeros_like(v)
+    for k in range(3):
+        np.add.at(n, f[:, k], fn)
+    ln = np.linalg.norm(n, axis=1, keepdims=True)
+    return (n / np.maximum(ln, 1e-20)).astype(np.float32)
+
+
 def euler_to_mat(ax, ay, az):
     cx, sx, cy, sy, cz, sz = np.cos(ax), np.sin(ax), np.cos(ay), np.sin(ay), np.cos(az), np.sin(az)
     Rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])

@@ -103,6 +103,7 @@ typedef struct {
   orc_pvert a, b, c;
   int64_t area;
   int valid;
+  int swapped; /* b and c exchanged to make the area positive */
 } orc_tri;
 
 static void orc_setup_tri(const orc_pvert *pv, const int32_t *face, orc_tri *t) {
@@ -110,6 +111,7 @@ static void orc_setup_tri(const orc_pvert *pv, const int32_t *face, orc_tri *t) 
   t->b = pv[face[1]];
   t->c = pv[face[2]];
   t->valid = t->a.ok && t->b.ok && t->c.ok;
+  t->swapped = 0;
   if (!t->valid) return;
   int64_t area = orc_edge(t->a.X, t->a.Y, t->b.X, t->b.Y, t->c.X, t->c.Y);
   if (area == 0) {
@@ -121,6 +123,7 @@ static void orc_setup_tri(const orc_pvert *pv, const int32_t *face, orc_tri *t) 
     t->b = t->c;
     t->c = tmp;
     area = -area;
+    t->swapped = 1;
   }
   t->area = area;
 }
@@ -167,11 +170,48 @@ static inline float orc_colour(uint8_t c, int trunc_u8) {
  *  bbox_ren  : 4 ints  x0,x1,y0,y1 of out_mask (min/max nonzero col/row), or -1 if empty
  *  any output pointer may be NULL.
  */
-ORC_API void orc_render(const float *verts, const float *uvs, int32_t V, const int32_t *faces,
+/* Lambert shading of the lit renderer (lib/render_glumpy/render_py_light_modelnet_multi.py:36-79 fragment shader):
+ * position / normal interpolated perspective-correctly in model space, moved to the GL camera frame (x, -y, -z of
+ * the OpenCV frame, _get_view_mtx), brightness = clamp(cos(normal, light - position), 0, 1),
+ * colour = texel * ((1 - ratio) + ratio * brightness) * light_intensity, quantised like the 8-bit framebuffer the
+ * reference reads back (np.round(rgb * 255), l.160).  float32, one operation per line (no contraction). */
+static void orc_shade_lit(float b0, float b1, float b2, float iz, float izA, float izB, float izC, const float *vA,
+                          const float *vB, const float *vC, const float *nA, const float *nB, const float *nC,
+                          const float *pose, const float *light_pos, const float *light_int, float a0, float a1,
+                          const uint8_t *tp, float *rgb) {
+  float w0 = b0 * izA, w1 = b1 * izB, w2 = b2 * izC;
+  float pm[3], nm[3], pc[3], nc[3];
+  for (int k = 0; k < 3; ++k) {
+    pm[k] = ((w0 * vA[k] + w1 * vB[k]) + w2 * vC[k]) / iz;
+    nm[k] = ((w0 * nA[k] + w1 * nB[k]) + w2 * nC[k]) / iz;
+  }
+  for (int r = 0; r < 3; ++r) {
+    pc[r] = ((pose[4 * r] * pm[0] + pose[4 * r + 1] * pm[1]) + pose[4 * r + 2] * pm[2]) + pose[4 * r + 3];
+    nc[r] = (pose[4 * r] * nm[0] + pose[4 * r + 1] * nm[1]) + pose[4 * r + 2] * nm[2];
+  }
+  float s0 = light_pos[0] - pc[0], s1 = light_pos[1] - (0.f - pc[1]), s2 = light_pos[2] - (0.f - pc[2]);
+  float g0 = nc[0], g1 = 0.f - nc[1], g2 = 0.f - nc[2];
+  float dot = (g0 * s0 + g1 * s1) + g2 * s2;
+  float ls = sqrtf((s0 * s0 + s1 * s1) + s2 * s2), ln = sqrtf((g0 * g0 + g1 * g1) + g2 * g2);
+  float den = ls * ln, br = 0.f;
+  if (den > 0.f) br = dot / den;
+  br = br < 1.f ? br : 1.f;
+  br = br > 0.f ? br : 0.f;
+  float scale = a0 + a1 * br;
+  for (int c = 0; c < 3; ++c) {
+    float col = ((float)tp[c] / 255.0f) * (scale * light_int[c]);
+    col = col < 1.f ? col : 1.f;
+    col = col > 0.f ? col : 0.f;
+    rgb[c] = rintf(col * 255.0f);
+  }
+}
+
+static void orc_render_impl(const float *verts, const float *uvs, int32_t V, const int32_t *faces,
                         int32_t F, const uint8_t *tex, int32_t Th, int32_t Tw, const float *pose,
                         const float *K4 /*fx,fy,cx,cy*/, float zn, float zf, int32_t H, int32_t W,
                         const double *means_rgb, int32_t trunc_u8, float *out_bgr,
-                        float *out_depth, float *out_image, float *out_mask, int32_t *bbox_ren) {
+                        float *out_depth, float *out_image, float *out_mask, int32_t *bbox_ren,
+                        const float *normals, const float *light_pos, const float *light_int, float a0, float a1) {
   orc_pvert *pv = (orc_pvert *)malloc(sizeof(orc_pvert) * (size_t)V);
   uint64_t *zb = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)H * W);
   for (size_t k = 0; k < (size_t)H * W; ++k) zb[k] = ~(uint64_t)0;
@@ -225,9 +265,16 @@ ORC_API void orc_render(const float *verts, const float *uvs, int32_t V, const i
         if (ty < 0) ty = 0;
         if (ty > Th - 1) ty = Th - 1;
         const uint8_t *tp = tex + ((size_t)ty * Tw + tx) * 3;
-        rgb[0] = orc_colour(tp[0], trunc_u8);
-        rgb[1] = orc_colour(tp[1], trunc_u8);
-        rgb[2] = orc_colour(tp[2], trunc_u8);
+        if (normals) {
+          const int32_t *fi = faces + 3 * f;
+          const int32_t iA = fi[0], iB = t.swapped ? fi[2] : fi[1], iC = t.swapped ? fi[1] : fi[2];
+          orc_shade_lit(b0, b1, b2, iz, t.a.iz, t.b.iz, t.c.iz, verts + 3 * iA, verts + 3 * iB, verts + 3 * iC,
+                        normals + 3 * iA, normals + 3 * iB, normals + 3 * iC, pose, light_pos, light_int, a0, a1, tp, rgb);
+        } else {
+          rgb[0] = orc_colour(tp[0], trunc_u8);
+          rgb[1] = orc_colour(tp[1], trunc_u8);
+          rgb[2] = orc_colour(tp[2], trunc_u8);
+        }
         depth = z;
       }
       float m = depth > 0.2f ? 1.f : 0.f;
@@ -278,6 +325,27 @@ ORC_API void orc_render(const float *verts, const float *uvs, int32_t V, const i
  * ---------------------------------------------------------------------------------------- */
 
 /* min/max nonzero column/row of (mask > thresh); x0,x1,y0,y1 or -1 (zoom_mask.py:51-58,62-66) */
+
+ORC_API void orc_render(const float *verts, const float *uvs, int32_t V, const int32_t *faces,
+                        int32_t F, const uint8_t *tex, int32_t Th, int32_t Tw, const float *pose,
+                        const float *K4 /*fx,fy,cx,cy*/, float zn, float zf, int32_t H, int32_t W,
+                        const double *means_rgb, int32_t trunc_u8, float *out_bgr,
+                        float *out_depth, float *out_image, float *out_mask, int32_t *bbox_ren) {
+  orc_render_impl(verts, uvs, V, faces, F, tex, Th, Tw, pose, K4, zn, zf, H, W, means_rgb, trunc_u8, out_bgr, out_depth,
+                  out_image, out_mask, bbox_ren, NULL, NULL, NULL, 0.f, 0.f);
+}
+
+/* Render_Py_Light_ModelNet_Multi.render (render_py_light_modelnet_multi.py:131-175): per-vertex normals,
+ * light_pos / light_int (3 floats each, GL camera frame), a0 = 1 - brightness_ratio, a1 = brightness_ratio. */
+ORC_API void orc_render_lit(const float *verts, const float *uvs, const float *normals, int32_t V, const int32_t *faces,
+                            int32_t F, const uint8_t *tex, int32_t Th, int32_t Tw, const float *pose, const float *K4,
+                            float zn, float zf, int32_t H, int32_t W, const double *means_rgb, const float *light_pos,
+                            const float *light_int, float a0, float a1, float *out_bgr, float *out_depth,
+                            float *out_image, float *out_mask, int32_t *bbox_ren) {
+  orc_render_impl(verts, uvs, V, faces, F, tex, Th, Tw, pose, K4, zn, zf, H, W, means_rgb, 1, out_bgr, out_depth, out_image,
+                  out_mask, bbox_ren, normals, light_pos, light_int, a0, a1);
+}
+
 ORC_API void orc_mask_bbox(const float *mask, int32_t H, int32_t W, float thresh, int32_t *bbox) {
   int32_t bx0 = W, bx1 = -1, by0 = H, by1 = -1;
   for (int32_t i = 0; i < H; ++i)

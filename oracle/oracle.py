@@ -44,6 +44,10 @@ def lib():
         L.orc_render.argtypes = [f32p, f32p, C.c_int32, i32p, C.c_int32, u8p, C.c_int32, C.c_int32, f32p, f32p,
                                  C.c_float, C.c_float, C.c_int32, C.c_int32, f64p, C.c_int32, vp, vp, vp, vp, vp]
         L.orc_render.restype = None
+        L.orc_render_lit.argtypes = [f32p, f32p, f32p, C.c_int32, i32p, C.c_int32, u8p, C.c_int32, C.c_int32, f32p, f32p,
+                                     C.c_float, C.c_float, C.c_int32, C.c_int32, f64p, f32p, f32p, C.c_float, C.c_float,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_render_lit.restype = None
         L.orc_mask_bbox.argtypes = [f32p, C.c_int32, C.c_int32, C.c_float, i32p]
         L.orc_zoom_factor.argtypes = [i32p, i32p, f32p, f32p, C.c_int32, C.c_int32, f32p]
         L.orc_zoom_factor.restype = C.c_int32
@@ -86,6 +90,28 @@ def render(mesh, pose, K, zn=0.25, zf=6.0, H=480, W=640, means_rgb=None, trunc_u
     lib().orc_render(mesh.verts, mesh.uvs, len(mesh.verts), mesh.faces, len(mesh.faces), mesh.tex,
                      mesh.tex.shape[0], mesh.tex.shape[1], pose32, k4(K), zn, zf, H, W, means, int(trunc_u8),
                      _ptr(out["bgr"]), _ptr(out["depth"]), _ptr(out["image"]), _ptr(out["mask"]), _ptr(bbox))
+    out["bbox"] = bbox
+    return out
+
+
+def render_lit(mesh, normals, pose, K, light_position, light_intensity, brightness_ratio=0.7, zn=0.25, zf=6.0, H=480, W=640,
+               means_rgb=None, want=("bgr", "depth", "image", "mask")):
+    """Render_Py_Light_ModelNet_Multi.render (lib/render_glumpy/render_py_light_modelnet_multi.py:131-175): Lambert-lit
+    textured render; light position in the GL camera frame, bgr holds the 8-bit quantised colours as floats."""
+    pose32 = np.ascontiguousarray(pose, dtype=np.float32)
+    means = np.zeros(3, np.float64) if means_rgb is None else np.ascontiguousarray(means_rgb, dtype=np.float64)
+    out = {
+        "bgr": np.empty((H, W, 3), np.float32) if "bgr" in want else None,
+        "depth": np.empty((H, W), np.float32) if "depth" in want else None,
+        "image": np.empty((3, H, W), np.float32) if "image" in want else None,
+        "mask": np.empty((H, W), np.float32) if "mask" in want else None,
+    }
+    bbox = np.zeros(4, np.int32)
+    lib().orc_render_lit(mesh.verts, mesh.uvs, np.ascontiguousarray(normals, np.float32), len(mesh.verts), mesh.faces,
+                         len(mesh.faces), mesh.tex, mesh.tex.shape[0], mesh.tex.shape[1], pose32, k4(K), zn, zf, H, W, means,
+                         np.ascontiguousarray(light_position, np.float32), np.ascontiguousarray(light_intensity, np.float32),
+                         float(np.float32(1.0 - float(np.float32(brightness_ratio)))), float(np.float32(brightness_ratio)),
+                         _ptr(out["bgr"]), _ptr(out["depth"]), _ptr(out["image"]), _ptr(out["mask"]), _ptr(bbox))
     out["bbox"] = bbox
     return out
 
