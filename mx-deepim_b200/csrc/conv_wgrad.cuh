@@ -176,33 +176,143 @@ __global__ void __launch_bounds__(192) conv_wgrad_kernel(const __grid_constant__
 }
 
 // kinds of parameter tensors the reduction writes (MXNet layouts)
-enum { WG_CONV = 0, WG_CONV1_S2D = 1, WG_DECONV = 2 };
+enum { WG_CONV = 0, WG_CONV1_S2D = 1, WG_DECONV = 2, WG_CONV1_ROW = 3 };
 
-// grad[dst] = sum_slices partial[slice][tap][m][n]; one thread per destination element (gather).
+// grad[dst] = sum_slices partial[slice][tap][m][n]; one thread per SOURCE element (tap, m, n) with n fastest, so the
+// partial tiles are read coalesced; the (Cout,Cin,kh,kw) destination is written with a k*k-element stride.
 //   WG_CONV      : m = co, n = ci            -> (Cout, Cin, k, k)
-//   WG_CONV1_S2D : m = co, n = ph*16+pw*8+c  -> (64, 8, 7, 7), kh = 2dh+ph, kw = 2dw+pw
+//   WG_CONV1_S2D : m = co, n = ph*16+pw*8+c  -> (64, 8, 7, 7), kh = 2dh+ph, kw = 2dw+pw      (taps = 16)
+//   WG_CONV1_ROW : m = dw*32+ph*16+pw*8+c, n = co, tap = dh -> (64, 8, 7, 7)                  (conv1_wgrad_kernel, taps = 4)
 //   WG_DECONV    : m = ci, n = co            -> (Cin, Cout, k, k)
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float *__restrict__ partial, int kslices, int taps,
                                                            int Mp, int Np, int kind, int D0, int D1, int k,
                                                            float *__restrict__ grad) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t total = (size_t)D0 * D1 * k * k;
-  if (idx >= total) return;
-  const int kw = (int)(idx % k), kh = (int)((idx / k) % k);
-  const int d1 = (int)((idx / ((size_t)k * k)) % D1), d0 = (int)(idx / ((size_t)k * k * D1));
-  int tap, m, n;
+  if (idx >= (size_t)taps * Mp * Np) return;
+  const int n = (int)(idx % Np), m = (int)((idx / Np) % Mp), tap = (int)(idx / ((size_t)Np * Mp));
+  int d0, d1, kh, kw;
   if (kind == WG_CONV1_S2D) {
-    tap = (kh >> 1) * 4 + (kw >> 1);
-    m = d0;
-    n = (kh & 1) * 16 + (kw & 1) * 8 + d1;
+    d0 = m; d1 = n & 7;
+    kh = 2 * (tap >> 2) + ((n >> 4) & 1); kw = 2 * (tap & 3) + ((n >> 3) & 1);
+    if (n >= 32) return;
+  } else if (kind == WG_CONV1_ROW) {
+    d0 = n; d1 = m & 7;
+    kh = 2 * tap + ((m >> 4) & 1); kw = 2 * (m >> 5) + ((m >> 3) & 1);
   } else {
-    tap = kh * k + kw;
-    m = d0;
-    n = d1;
+    d0 = m; d1 = n; kh = tap / k; kw = tap - kh * k;
   }
+  if (d0 >= D0 || d1 >= D1 || kh >= k || kw >= k) return;
   float acc = 0.f;
-  for (int s = 0; s < kslices; ++s) acc += partial[(((size_t)s * taps + tap) * Mp + m) * Np + n];
-  grad[idx] = acc;
+  for (int s = 0; s < kslices; ++s) acc += partial[(size_t)s * taps * Mp * Np + idx];
+  grad[(((size_t)d0 * D1 + d1) * k + kh) * k + kw] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// conv1 weight gradient (64 x 8 x 7 x 7 from 240 x 320 output pixels): the generic kernel would run 16 taps of
+// 128(64 used) x 32 tiles and fetch dZ 16 times.  Here one GEMM per filter ROW dh: M = (dw, 32 space-to-depth channels) =
+// 128 rows assembled from FOUR column-shifted TMA boxes of the NHWC-32 input copy (64-byte rows, SWIZZLE_64B, MN-major
+// groups LBO = 4 KB apart), N = 64 output channels of dZ (one SWIZZLE_128B box), K = 64 pixels: dZ is fetched 4x instead of
+// 16x and no MMA row is padding.
+template <int STAGES>
+struct Conv1WgradSmem {
+  static constexpr int A_BYTES = 4 * 4096, B_BYTES = 8192, STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int STAGES>
+__global__ void __launch_bounds__(192) conv1_wgrad_kernel(const __grid_constant__ WgradParams p) {
+  using S = Conv1WgradSmem<STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES * S::STAGE_BYTES);
+  uint64_t *empty_bar = full_bar + STAGES;
+  uint64_t *done_bar = empty_bar + STAGES;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int dh = blockIdx.x % 4, slice = blockIdx.x / 4;
+  const int kb0 = slice * p.kb_per_slice;
+  const int kb1 = min(p.kb_total, kb0 + p.kb_per_slice);
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    ptx::mbar_init(done_bar, 1);
+    ptx::fence_barrier_init();
+    ptx::prefetch_tmap(&p.z_map);
+    ptx::prefetch_tmap(&p.a_map[0]);
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, 64);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
+        const int rx = kb % p.rects_x;
+        const int t = kb / p.rects_x;
+        const int ry = t % p.rects_y, b = t / p.rects_y;
+        const int oy0 = ry * p.BH, ox0 = rx * p.BW;
+        uint8_t *st = smem + s * S::STAGE_BYTES;
+        ptx::mbar_expect_tx(&full_bar[s], (uint32_t)S::STAGE_BYTES);
+#pragma unroll
+        for (int dw = 0; dw < 4; ++dw) tma_load_4d(st + dw * 4096, &p.a_map[0], &full_bar[s], 0, ox0 + dw, oy0 + dh, b);
+        tma_load_4d(st + S::A_BYTES, &p.z_map, &full_bar[s], 0, ox0 + p.z_off_c, oy0 + p.z_off_r, b);
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        ptx::mbar_wait(&full_bar[s], ph);
+        ptx::tc_fence_after();
+        const uint32_t a0 = ptx::smem_u32(smem + s * S::STAGE_BYTES);
+        const uint32_t b0 = a0 + S::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t da = ptx::umma_desc_mn(a0 + k * 1024, 4096, 512, 4u);
+          const uint64_t db = ptx::umma_desc_mn(b0 + k * 2048, 8192, 1024, 2u);
+          ptx::umma_f16(tmem_base, da, db, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+        }
+        ptx::umma_commit(&empty_bar[s]);
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
+      }
+      ptx::umma_commit(done_bar);
+    }
+  } else {
+    const int quad = warp & 3;
+    const int m = quad * 32 + lane;
+    if (kb1 > kb0) {
+      ptx::mbar_wait(done_bar, 0);
+      ptx::tc_fence_after();
+    }
+    float *dst = p.partial + (((size_t)slice * 4 + dh) * 128 + m) * 64;
+    const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < 64; c += 32) {
+      uint32_t r[32];
+      if (kb1 > kb0) {
+        ptx::tmem_ld_32x32(trow + c, r);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
+      }
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4 *>(dst + c + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 64);
+  }
 }
 
 }  // namespace dim

@@ -966,9 +966,33 @@ static int run_wgrad(const WgradParams &p, int BN, int kind, int D0, int D1, int
   else if (BN == 64) rc = launch_wgrad<64, 8>(p, st);
   else rc = launch_wgrad<32, 8>(p, st);
   if (rc) return rc;
-  const size_t total = (size_t)D0 * D1 * k * k;
+  const size_t total = (size_t)p.KH * p.KW * p.m_tiles * 128 * p.n_tiles * BN;
   wgrad_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p.partial, p.kslices, p.KH * p.KW, p.m_tiles * 128,
                                                                         p.n_tiles * BN, kind, D0, D1, k, grad);
+  DIM_LAUNCH_CHECK();
+  return 0;
+}
+
+// conv1: one GEMM per filter row (conv1_wgrad_kernel); p was built by make_wgrad for the 16-tap form, only the slicing differs
+static int run_wgrad_conv1(TrainState *ts, const WgradParams &p16, int sms, float *grad, cudaStream_t st) {
+  using S = Conv1WgradSmem<8>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DIM_CHECK(cudaFuncSetAttribute(conv1_wgrad_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    attr_set = true;
+  }
+  WgradParams p = p16;
+  int ks = cdiv(2 * sms, 4);
+  if (ks > p.kb_total / 2) ks = p.kb_total / 2;
+  if (ks < 1) ks = 1;
+  p.kb_per_slice = cdiv(p.kb_total, ks);
+  p.kslices = cdiv(p.kb_total, p.kb_per_slice);
+  p.idesc = make_idesc_mn(128, 64);
+  DIM_REQUIRE((size_t)p.kslices * 4 * 128 * 64 <= ts->wg_partial_elems, "wgrad workspace too small");
+  conv1_wgrad_kernel<8><<<4 * p.kslices, 192, S::TOTAL, st>>>(p);
+  DIM_LAUNCH_CHECK();
+  const size_t total = (size_t)4 * 128 * 64;
+  wgrad_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p.partial, p.kslices, 4, 128, 64, WG_CONV1_ROW, 64, 8, 7, grad);
   DIM_LAUNCH_CHECK();
   return 0;
 }
@@ -1270,7 +1294,9 @@ int train_forward_backward(dim_ctx *ctx, const TrainIO &io, cudaStream_t st) {
     if (i == 9)  // heads, decoder (thin kernels on st, deconvolution wgrads on sw): tensors 10..23 are done
       if (int rc = record_buckets(io, 10, 1 << 30, sw)) return rc;
     if (int rc = bias_grad(ts, ts->gz[i], B, 0, s.Cout, G + ts->off[i].b, sw)) return rc;
-    if (int rc = run_wgrad(tm.wg[i], tm.wg_bn[i], i == 0 ? WG_CONV1_S2D : WG_CONV, s.Cout, s.Cin, s.k, G + ts->off[i].w, sw)) return rc;
+    if (i == 0) {
+      if (int rc = run_wgrad_conv1(ts, tm.wg[0], ctx->num_sms, G + ts->off[0].w, sw)) return rc;
+    } else if (int rc = run_wgrad(tm.wg[i], tm.wg_bn[i], WG_CONV, s.Cout, s.Cin, s.k, G + ts->off[i].w, sw)) return rc;
     if (int rc = record_buckets(io, i, i + 1, sw)) return rc;
     if (i >= 1)
       if (int rc = run_classes(ctx, ts, tm.dgrad[i], tm.g_dgrad[i], tm.n_dgrad[i], B, st)) return rc;
