@@ -66,12 +66,18 @@ def main():
     z = tr.zoom_front(batch, K)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     torch.cuda.synchronize()
-    ev[0].record(); tr.forward_backward(z, want_maps=False); ev[1].record(); tr.allreduce(dist); ev[2].record(); tr.update(); ev[3].record()
+    import time
+    c0 = time.perf_counter()
+    ev[0].record(); tr.forward_backward(z, want_maps=False); ev[1].record()
+    c1 = time.perf_counter()   # host time to ENQUEUE the step (no sync): if it is close to the device time the step is launch-bound
+    tr.allreduce(dist); ev[2].record(); tr.update(); ev[3].record()
+    c2 = time.perf_counter()
     torch.cuda.synchronize()
     line = {"metric": "training instances/s (4 inner updates per instance)", "value": a.batch * world / (float(ms) / 1e3),
             "unit": "instances/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": float(ms),
             "ms_per_inner_iteration": float(ms) / 4, "split_ms": {"forward_backward": ev[0].elapsed_time(ev[1]),
-                                                                   "allreduce": ev[1].elapsed_time(ev[2]), "sgd_update_repack": ev[2].elapsed_time(ev[3])},
+                                                                   "allreduce": ev[1].elapsed_time(ev[2]), "sgd_update_repack": ev[2].elapsed_time(ev[3]),
+                                                                   "host_enqueue_forward_backward": (c1 - c0) * 1e3, "host_enqueue_update": (c2 - c1) * 1e3},
             "dtype": "bf16 activations/gradients, fp32 master", "data": "synthetic", "scaling": "weak",
             "config": {"workload": "C4 training step", "allreduce_overlap": (not a.no_overlap) and world > 1, "per_gpu_batch": a.batch, "inner_iterations": 4, "grad_bytes": tr.n * 4},
             "objective_last_batch": [float(v) for v in objs.cpu()]}
