@@ -434,14 +434,25 @@ __global__ void __launch_bounds__(256) pm_loss_kernel(const float *pts_est, cons
   if (threadIdx.x == 0) loss_part[2 * LOSS_BLOCKS + blockIdx.x] = red[0];
 }
 
-__global__ void loss_final_kernel(const float *loss_part, int nb_full, int nb_pm, float gs_flow, float gs_pm, float gs_mask,
-                                  float *losses /*flow_sum, pm_sum, mask_bce_sum, objective*/) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// one block of 256 threads: fixed-order tree reduction of the per-block partial sums (float64)
+__global__ void __launch_bounds__(256) loss_final_kernel(const float *loss_part, int nb_full, int nb_pm, float gs_flow, float gs_pm,
+                                                         float gs_mask, float *losses /*flow_sum, pm_sum, mask_bce_sum, objective*/) {
+  __shared__ double red[3][256];
   double f = 0, m = 0, p = 0;
-  for (int i = 0; i < nb_full; ++i) { f += loss_part[i]; m += loss_part[LOSS_BLOCKS + i]; }
-  for (int i = 0; i < nb_pm; ++i) p += loss_part[2 * LOSS_BLOCKS + i];
-  losses[0] = (float)f; losses[1] = (float)p; losses[2] = (float)m;
-  losses[3] = (float)(gs_flow * f + gs_pm * p + gs_mask * m);
+  for (int i = threadIdx.x; i < nb_full; i += 256) { f += loss_part[i]; m += loss_part[LOSS_BLOCKS + i]; }
+  for (int i = threadIdx.x; i < nb_pm; i += 256) p += loss_part[2 * LOSS_BLOCKS + i];
+  red[0][threadIdx.x] = f; red[1][threadIdx.x] = m; red[2][threadIdx.x] = p;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s)
+      for (int k = 0; k < 3; ++k) red[k][threadIdx.x] += red[k][threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    f = red[0][0]; m = red[1][0]; p = red[2][0];
+    losses[0] = (float)f; losses[1] = (float)p; losses[2] = (float)m;
+    losses[3] = (float)(gs_flow * f + gs_pm * p + gs_mask * m);
+  }
 }
 
 // backward of L2Normalization (d rot_raw) ; ZoomTrans backward with b_zoom_grad=False is the identity
@@ -1126,7 +1137,13 @@ static int copy_interior(const Buf &src, Buf &dst, int dcoff, int B, int C, cuda
 
 // the parity classes of one layer write disjoint pixels: class 0 on the caller's stream, 1..3 on internal streams
 static int run_classes(dim_ctx *ctx, TrainState *ts, const ConvKParams *kp, const LayerGeom *g, int n, int B, cudaStream_t st) {
-  if (n == 1) return run_generic(ctx, kp[0], g[0], B, st);
+  // classes that fill the machine on their own gain nothing from running side by side: keep them on one stream
+  const int tiles0 = cdiv(B * g[0].Hq, g[0].BH) * g[0].n_col_tiles * cdiv(g[0].Cout, g[0].BLOCK_N);
+  if (n == 1 || tiles0 >= ctx->num_sms) {
+    for (int c = 0; c < n; ++c)
+      if (int rc = run_generic(ctx, kp[c], g[c], B, st)) return rc;
+    return 0;
+  }
   DIM_CHECK(cudaEventRecord(ts->ev_fork, st));
   for (int c = 1; c < n; ++c) {
     DIM_CHECK(cudaStreamWaitEvent(ts->side[c - 1], ts->ev_fork, 0));
@@ -1221,7 +1238,7 @@ int train_forward_backward(dim_ctx *ctx, const TrainIO &io, cudaStream_t st) {
     DIM_LAUNCH_CHECK();
   }
   if (io.losses) {
-    loss_final_kernel<<<1, 32, 0, st>>>(ts->loss_part, LOSS_BLOCKS, io.pc_model ? pm_blocks : 0, gs_flow, gs_pm, gs_mask, io.losses);
+    loss_final_kernel<<<1, 256, 0, st>>>(ts->loss_part, LOSS_BLOCKS, io.pc_model ? pm_blocks : 0, gs_flow, gs_pm, gs_mask, io.losses);
     DIM_LAUNCH_CHECK();
   }
   if (io.rot_raw) DIM_CHECK(cudaMemcpyAsync(io.rot_raw, ts->rot_raw, (size_t)B * 16, cudaMemcpyDeviceToDevice, st));
