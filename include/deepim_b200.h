@@ -330,6 +330,10 @@ DIM_API int32_t dim_train_sgd_update(dim_ctx *ctx, const float *grads, float lr,
  * out7 = Hp, Wp, py, px, C, H, W. */
 DIM_API int32_t dim_train_debug_tensor(dim_ctx *ctx, int32_t id, void *host_dst, uint64_t bytes);
 DIM_API int32_t dim_train_debug_geometry(dim_ctx *ctx, int32_t id, int32_t *out7);
+/* ms7 = device time of the phases of the last dim_train_forward_backward (with gradients) on the caller's stream:
+ * encoder fwd, decoder fwd, losses + pose heads, fc/head backward, decoder backward, encoder data-gradient chain,
+ * wait for the weight-gradient stream.  Synchronises the device. */
+DIM_API int32_t dim_train_debug_phases(dim_ctx *ctx, float *ms7);
 
 /* number of kernel launches issued by this library since the counter was last reset */
 DIM_API int64_t dim_launch_count(int32_t reset);

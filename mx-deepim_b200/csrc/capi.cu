@@ -76,6 +76,7 @@ int train_forward_backward(dim_ctx *, const TrainIO &, cudaStream_t);
 int train_sgd_update(dim_ctx *, const float *grads, float lr, float momentum, float wd, float rescale, cudaStream_t);
 int train_debug_tensor(dim_ctx *, int id, void *host, size_t bytes);
 void train_debug_geometry(dim_ctx *, int id, int *out);
+int train_debug_phases(dim_ctx *, float *ms7);
 
 template <typename T>
 static int ctx_alloc(dim_ctx *ctx, T **p, size_t n) {
@@ -572,6 +573,10 @@ DIM_API int32_t dim_train_sgd_update(dim_ctx *ctx, const float *grads, float lr,
 DIM_API int32_t dim_train_debug_tensor(dim_ctx *ctx, int32_t id, void *host_dst, uint64_t bytes) {
   DIM_REQUIRE(ctx && host_dst, "dim_train_debug_tensor: NULL argument");
   return train_debug_tensor(ctx, id, host_dst, (size_t)bytes);
+}
+DIM_API int32_t dim_train_debug_phases(dim_ctx *ctx, float *ms7) {
+  DIM_REQUIRE(ctx && ms7, "dim_train_debug_phases: NULL argument");
+  return train_debug_phases(ctx, ms7);
 }
 DIM_API int32_t dim_train_debug_geometry(dim_ctx *ctx, int32_t id, int32_t *out7) {
   DIM_REQUIRE(ctx && out7, "dim_train_debug_geometry: NULL argument");

@@ -95,6 +95,7 @@ struct TrainState {
   // internal streams: [0..2] run parity classes 1..3 next to class 0 on the caller's stream; [3] runs the weight / bias
   // gradients next to the data-gradient chain (both only read the dZ buffers)
   cudaStream_t side[4] = {};
+  cudaEvent_t ev_phase[9] = {};  // phase boundaries of the last step on the caller's stream (dim_train_debug_phases)
   cudaEvent_t ev_fork = nullptr, ev_cls[3] = {}, ev_side = nullptr;
 };
 
@@ -722,6 +723,7 @@ int train_create(dim_ctx *ctx, int max_points) {
   DIM_CHECK(cudaEventCreateWithFlags(&ts->ev_fork, cudaEventDisableTiming));
   DIM_CHECK(cudaEventCreateWithFlags(&ts->ev_side, cudaEventDisableTiming));
   for (int i = 0; i < 3; ++i) DIM_CHECK(cudaEventCreateWithFlags(&ts->ev_cls[i], cudaEventDisableTiming));
+  for (int i = 0; i < 9; ++i) DIM_CHECK(cudaEventCreate(&ts->ev_phase[i]));
   return rc;
 }
 
@@ -732,6 +734,7 @@ void train_destroy(dim_ctx *ctx) {
     if (ts->ev_fork) cudaEventDestroy(ts->ev_fork);
     if (ts->ev_side) cudaEventDestroy(ts->ev_side);
     for (int i = 0; i < 3; ++i) if (ts->ev_cls[i]) cudaEventDestroy(ts->ev_cls[i]);
+    for (int i = 0; i < 9; ++i) if (ts->ev_phase[i]) cudaEventDestroy(ts->ev_phase[i]);
   }
   delete ts;
   ts = nullptr;
@@ -1205,8 +1208,10 @@ int train_forward_backward(dim_ctx *ctx, const TrainIO &io, cudaStream_t st) {
   const float Tm[3] = {0, 0, 0}, Tsd[3] = {1, 1, 1};
 
   // ---------------- forward
+  DIM_CHECK(cudaEventRecord(ts->ev_phase[0], st));
   if (int rc = pack_nhwc8_launch(ctx, io.zio, io.zir, io.zmo, io.zmr, B, g[0].rows, g[0].cols, g[0].py, ns->act_hi[0], nullptr, st)) return rc;
   if (int rc = net_forward(ctx, B, DIM_PREC_BF16, nullptr, ts->rot_raw, ts->ztrans, nullptr, st, nullptr)) return rc;
+  DIM_CHECK(cudaEventRecord(ts->ev_phase[1], st));
   const Buf a10 = act_buf(ns, 10), a8 = act_buf(ns, 8), a6 = act_buf(ns, 6);
   if (int rc = copy_interior(a10, ts->act10b, 0, B, 1024, st)) return rc;
   LAUNCH1D(thin_conv_fwd_kernel<2>, (size_t)B * h6 * w6 * 32, st, ts->act10b.p, ts->act10b.Hp, ts->act10b.Wp, 1024, 1024, B, h6, w6,
@@ -1225,6 +1230,7 @@ int train_forward_backward(dim_ctx *ctx, const TrainIO &io, cudaStream_t st) {
            M + ts->off[P_CONV3D].w, M + ts->off[P_CONV3D].b, ts->flow4);
   LAUNCH1D(thin_conv_fwd_kernel<1>, (size_t)B * h4 * w4 * 32, st, ts->cat3.p, ts->cat3.Hp, ts->cat3.Wp, 832, 770, B, h4, w4,
            M + ts->off[P_MASK3].w, M + ts->off[P_MASK3].b, ts->mask4);
+  DIM_CHECK(cudaEventRecord(ts->ev_phase[2], st));
   fullres_loss_kernel<<<LOSS_BLOCKS, 256, 0, st>>>(ts->flow4, ts->mask4, h4, w4, M + ts->off[P_UPS].w, M + ts->off[P_MUPS].w, io.zflow,
                                                    io.zfw, io.zmask_gt, B, H, W, 20.0f, gs_flow, gs_mask, io.flow_est, io.mask_prob,
                                                    ts->dfull, ts->loss_part);
@@ -1244,6 +1250,7 @@ int train_forward_backward(dim_ctx *ctx, const TrainIO &io, cudaStream_t st) {
   if (io.rot_raw) DIM_CHECK(cudaMemcpyAsync(io.rot_raw, ts->rot_raw, (size_t)B * 16, cudaMemcpyDeviceToDevice, st));
   if (io.rot_est_norm) DIM_CHECK(cudaMemcpyAsync(io.rot_est_norm, ts->rot_n, (size_t)B * 16, cudaMemcpyDeviceToDevice, st));
   if (io.trans_est) DIM_CHECK(cudaMemcpyAsync(io.trans_est, ts->trans_est, (size_t)B * 12, cudaMemcpyDeviceToDevice, st));
+  DIM_CHECK(cudaEventRecord(ts->ev_phase[3], st));
   if (G == nullptr) return 0;  // forward only (non-FAST_TEST outputs)
 
   // ---------------- backward
@@ -1261,6 +1268,7 @@ int train_forward_backward(dim_ctx *ctx, const TrainIO &io, cudaStream_t st) {
   fc6_wgrad_kernel<<<dim3(81920 / 2 / 256, 8), 256, 0, st>>>(ts->dh6, ns->act_hi[10], B, G + ts->off[P_FC6].w);
   DIM_LAUNCH_CHECK();
   LAUNCH1D(fc_wgrad_kernel, 256, st, ts->dh6, ts->h6 /*unused for K=0*/, B, 256, 0, G + ts->off[P_FC6].w /*no write*/, G + ts->off[P_FC6].b);
+  DIM_CHECK(cudaEventRecord(ts->ev_phase[4], st));
   // full-resolution heads -> 1/16 maps
   LAUNCH1D(upsample_bwd_kernel, (size_t)B * h4 * w4 * 3 * 32, st, ts->dfull, M + ts->off[P_UPS].w, M + ts->off[P_MUPS].w, B, H, W, h4, w4,
            ts->dflow4, ts->dmask4);
@@ -1302,6 +1310,7 @@ int train_forward_backward(dim_ctx *ctx, const TrainIO &io, cudaStream_t st) {
            ts->dA10p.Hp, ts->dA10p.Wp, 0, 0, 1024, 1024, 0);
   LAUNCH1D(fc6_dgrad_kernel, 81920, st, ts->dh6, ns->fc6_w_hi, B, ts->dA10p.p);
   if (int rc = run_generic(ctx, tm.deconv5_dgrad, tm.g_deconv5_dgrad, B, st)) return rc;
+  DIM_CHECK(cudaEventRecord(ts->ev_phase[5], st));
   // encoder
   LAUNCH1D(strip_to_nhwc32_kernel, (size_t)B * g[0].rows * 4 * g[0].cols, st, ns->act_hi[0], ts->s2d32.p, (size_t)B * g[0].rows * 4 * g[0].cols,
            g[0].cols);
@@ -1318,8 +1327,10 @@ int train_forward_backward(dim_ctx *ctx, const TrainIO &io, cudaStream_t st) {
     if (i >= 1)
       if (int rc = run_classes(ctx, ts, tm.dgrad[i], tm.g_dgrad[i], tm.n_dgrad[i], B, st)) return rc;
   }
+  DIM_CHECK(cudaEventRecord(ts->ev_phase[6], st));
   DIM_CHECK(cudaEventRecord(ts->ev_side, sw));
   DIM_CHECK(cudaStreamWaitEvent(st, ts->ev_side, 0));
+  DIM_CHECK(cudaEventRecord(ts->ev_phase[7], st));
   return 0;
 }
 
@@ -1367,6 +1378,16 @@ int train_debug_tensor(dim_ctx *ctx, int id, void *host, size_t bytes) {
   DIM_REQUIRE(src != nullptr && bytes <= have, "bad debug tensor id or size");
   DIM_CHECK(cudaDeviceSynchronize());
   DIM_CHECK(cudaMemcpy(host, src, bytes, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// milliseconds of the phases of the last forward_backward on the caller's stream: encoder fwd, decoder fwd, losses + pose heads,
+// fc / head backward, decoder backward, encoder backward (data-gradient chain), wait for the weight-gradient stream
+int train_debug_phases(dim_ctx *ctx, float *ms7) {
+  TrainState *ts = train_of(ctx);
+  DIM_REQUIRE(ts != nullptr, "no training state");
+  DIM_CHECK(cudaDeviceSynchronize());
+  for (int i = 0; i < 7; ++i) DIM_CHECK(cudaEventElapsedTime(&ms7[i], ts->ev_phase[i], ts->ev_phase[i + 1]));
   return 0;
 }
 

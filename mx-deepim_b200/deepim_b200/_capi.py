@@ -65,6 +65,7 @@ SIGNATURES = {
     "dim_train_forward_backward": (i32, [vp] + [vp] * 12 + [i32, i32] + [vp] * 7 + [vp, vp, i32] + [vp]),
     "dim_train_sgd_update": (i32, [vp, vp, f32, f32, f32, f32, vp]),
     "dim_train_debug_tensor": (i32, [vp, i32, vp, C.c_uint64]),
+    "dim_train_debug_phases": (i32, [vp, pf32]),
     "dim_train_debug_geometry": (i32, [vp, i32, C.POINTER(i32)]),
 }
 

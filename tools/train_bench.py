@@ -73,6 +73,10 @@ def main():
     tr.allreduce(dist); ev[2].record(); tr.update(); ev[3].record()
     c2 = time.perf_counter()
     torch.cuda.synchronize()
+    import ctypes
+    from deepim_b200._capi import lib as _lib
+    ph = (ctypes.c_float * 7)()
+    _lib.dim_train_debug_phases(ctx._h, ph)
     line = {"metric": "training instances/s (4 inner updates per instance)", "value": a.batch * world / (float(ms) / 1e3),
             "unit": "instances/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": float(ms),
             "ms_per_inner_iteration": float(ms) / 4, "split_ms": {"forward_backward": ev[0].elapsed_time(ev[1]),
@@ -80,6 +84,7 @@ def main():
                                                                    "host_enqueue_forward_backward": (c1 - c0) * 1e3, "host_enqueue_update": (c2 - c1) * 1e3},
             "dtype": "bf16 activations/gradients, fp32 master", "data": "synthetic", "scaling": "weak",
             "config": {"workload": "C4 training step", "allreduce_overlap": (not a.no_overlap) and world > 1, "per_gpu_batch": a.batch, "inner_iterations": 4, "grad_bytes": tr.n * 4},
+            "phases_ms": dict(zip(["encoder_fwd", "decoder_fwd", "losses_heads", "fc_bwd", "decoder_bwd", "encoder_dgrad_chain", "wait_wgrad_stream"], [round(float(x), 4) for x in ph])),
             "objective_last_batch": [float(v) for v in objs.cpu()]}
     if rank == 0:
         print(json.dumps(line))
