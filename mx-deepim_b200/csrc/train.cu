@@ -85,6 +85,7 @@ struct TrainState {
   float *pts_est = nullptr, *dpts = nullptr, *drot_n = nullptr, *dtrans = nullptr, *drot = nullptr, *dh7 = nullptr, *dh6 = nullptr;
   float *bias_part = nullptr;    // [<= BIAS_CHUNKS][1088]
   float *thin_part = nullptr;    // [THIN_CHUNKS][2][1026*9]
+  float *thin_w[4] = {};         // Convolution1/2/3, mask_conv3 as [tap][co][ci]
   float *wg_partial = nullptr;
   size_t wg_partial_elems = 0;
   // bf16 operand packs
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(256) thin_conv_fwd_kernel(const __nv_bfloat16 
       for (int ci = lane; ci < Cin; ci += 32) {
         const float v = __bfloat162float(px[ci]);
 #pragma unroll
-        for (int co = 0; co < CO; ++co) acc[co] = fmaf(v, w[((size_t)(co * Cin + ci) * 3 + ky) * 3 + kx], acc[co]);
+        for (int co = 0; co < CO; ++co) acc[co] = fmaf(v, w[((ky * 3 + kx) * CO + co) * Cin + ci], acc[co]);  // w = [tap][co][ci]
       }
     }
 #pragma unroll
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(256) thin_conv_dgrad_kernel(const float *dy, c
         if (ox < 0 || ox >= W) continue;
         const float *d = dy + ((size_t)(b * H + oy) * W + ox) * CO;
 #pragma unroll
-        for (int co = 0; co < CO; ++co) acc = fmaf(d[co], w[((size_t)(co * Cin + ci) * 3 + ky) * 3 + kx], acc);
+        for (int co = 0; co < CO; ++co) acc = fmaf(d[co], w[((ky * 3 + kx) * CO + co) * Cin + ci], acc);  // w = [tap][co][ci]
       }
     }
   __nv_bfloat16 *o = dx + (((size_t)b * Hp + yy + py) * Wp + xx + px) * cs + ci;
@@ -519,24 +520,43 @@ __global__ void __launch_bounds__(256) fc6_wgrad_kernel(const float *dh6, const 
     *reinterpret_cast<float2 *>(dw + (size_t)o * 81920 + 2 * i) = acc;
   }
 }
-// fc6 data gradient, added to the bf16 partial gradient of ReLU10 ([B][80][1024])
+// fc6 data gradient, added to the bf16 partial gradient of ReLU10 ([B][80][1024]).  Block = 64 consecutive k (2 per lane),
+// warp w streams output rows o in [32w, 32w+32) of the packed bf16 weight matrix; the 8 partial sums per (b, k) are
+// combined through shared memory in fixed order.
 __global__ void __launch_bounds__(256) fc6_dgrad_kernel(const float *dh6, const __nv_bfloat16 *w_hi /*[256][81920] packed*/, int B,
                                                         __nv_bfloat16 *dA) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= 81920) return;
-  float acc[16];
+  __shared__ float red[8][16][64];
+  __shared__ float dh[16][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k0 = blockIdx.x * 64 + 2 * lane;
+  for (int i = threadIdx.x; i < 16 * 256; i += 256) dh[i >> 8][i & 255] = (i >> 8) < B ? dh6[i] : 0.f;
+  __syncthreads();
+  float2 acc[16];
 #pragma unroll
-  for (int b = 0; b < 16; ++b) acc[b] = 0.f;
-#pragma unroll 8
-  for (int o = 0; o < 256; ++o) {
-    const float w = __bfloat162float(w_hi[(size_t)o * 81920 + k]);
+  for (int b = 0; b < 16; ++b) acc[b] = make_float2(0.f, 0.f);
+#pragma unroll 4
+  for (int o = warp * 32; o < warp * 32 + 32; ++o) {
+    const float2 w = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(w_hi + (size_t)o * 81920 + k0));
 #pragma unroll
-    for (int b = 0; b < 16; ++b)
-      if (b < B) acc[b] = fmaf(dh6[b * 256 + o], w, acc[b]);
+    for (int b = 0; b < 16; ++b) {
+      const float d = dh[b][o];
+      acc[b].x = fmaf(d, w.x, acc[b].x);
+      acc[b].y = fmaf(d, w.y, acc[b].y);
+    }
   }
-  for (int b = 0; b < B && b < 16; ++b) {
-    __nv_bfloat16 *o = dA + (size_t)b * 81920 + k;
-    *o = __float2bfloat16_rn(__bfloat162float(*o) + acc[b]);
+#pragma unroll
+  for (int b = 0; b < 16; ++b) {
+    red[warp][b][2 * lane] = acc[b].x;
+    red[warp][b][2 * lane + 1] = acc[b].y;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < B * 64; i += 256) {
+    const int b = i >> 6, kk = i & 63;
+    float s = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) s += red[w8][b][kk];
+    __nv_bfloat16 *o = dA + (size_t)b * 81920 + blockIdx.x * 64 + kk;
+    *o = __float2bfloat16_rn(__bfloat162float(*o) + s);
   }
 }
 
@@ -633,6 +653,13 @@ __global__ void __launch_bounds__(256) pack_fc6_kernel(const float *w, __nv_bflo
   if (i >= (size_t)256 * 81920) return;
   store_split(hi, lo, i, w[i]);
 }
+// thin-conv weights (CO, Cin, 3, 3) -> [tap][co][ci] fp32 so that lanes striding over ci read consecutive words
+__global__ void __launch_bounds__(256) pack_thin_kernel(const float *w, int CO, int Cin, float *wt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= CO * Cin * 9) return;
+  const int ci = i % Cin, co = (i / Cin) % CO, tap = i / (Cin * CO);
+  wt[i] = w[((size_t)(co * Cin + ci)) * 9 + tap];
+}
 __global__ void transpose256_kernel(const float *w, float *wT) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < 65536) wT[(i & 255) * 256 + (i >> 8)] = w[i];
@@ -703,6 +730,7 @@ int train_create(dim_ctx *ctx, int max_points) {
   rc |= dev_alloc(ctx, &ts->dpts, (size_t)B * 3 * max_points, true);
   rc |= dev_alloc(ctx, &ts->bias_part, (size_t)BIAS_CHUNKS * 1088, true);
   rc |= dev_alloc(ctx, &ts->thin_part, (size_t)THIN_CHUNKS * 2 * 1026 * 9, true);
+  for (int i = 0; i < 4; ++i) rc |= dev_alloc(ctx, &ts->thin_w[i], (size_t)2 * 1026 * 9, true);
   // operand packs
   for (int i = 1; i < 10; ++i) {
     const LayerSpec &s = kLayers[i];
@@ -779,6 +807,10 @@ static int repack_all(dim_ctx *ctx, cudaStream_t st) {
     LAUNCH1D(pack_deconv_fwd_kernel, (size_t)512 * 4 * 1024, st, M + ts->off[P_DECONV5].w, 1024, 512, 1024, c >> 1, c & 1, ts->d5_fwd[c]);
     LAUNCH1D(pack_deconv_fwd_kernel, (size_t)256 * 4 * 1088, st, M + ts->off[P_DECONV4].w, 1026, 256, 1088, c >> 1, c & 1, ts->d4_fwd[c]);
   }
+  LAUNCH1D(pack_thin_kernel, 2 * 1024 * 9, st, M + ts->off[P_CONV1D].w, 2, 1024, ts->thin_w[0]);
+  LAUNCH1D(pack_thin_kernel, 2 * 1026 * 9, st, M + ts->off[P_CONV2D].w, 2, 1026, ts->thin_w[1]);
+  LAUNCH1D(pack_thin_kernel, 2 * 770 * 9, st, M + ts->off[P_CONV3D].w, 2, 770, ts->thin_w[2]);
+  LAUNCH1D(pack_thin_kernel, 1 * 770 * 9, st, M + ts->off[P_MASK3].w, 1, 770, ts->thin_w[3]);
   LAUNCH1D(pack_deconv_dgrad_kernel, (size_t)1024 * 16 * 512, st, M + ts->off[P_DECONV5].w, 1024, 512, 1024, ts->d5_dg);
   LAUNCH1D(pack_deconv_dgrad_kernel, (size_t)1088 * 16 * 256, st, M + ts->off[P_DECONV4].w, 1026, 256, 1088, ts->d4_dg);
   return 0;
@@ -1035,11 +1067,13 @@ static int thin_wgrad(TrainState *ts, const Buf &x, int Cin, int B, int H, int W
 }
 
 static int thin_deconv_bwd(const float *in, int B, int Hi, int Wi, const float *w, const Buf &dout, int coff, int Ho, int Wo, float *din,
-                           float *dw, float *db, cudaStream_t st) {
+                           float *dw, float *db, cudaStream_t st, cudaStream_t sw, TrainState *ts) {
   thin_deconv_bwd_kernel<<<cdiv(B * Hi * Wi * 2, 256), 256, 0, st>>>(in, B, Hi, Wi, w, dout.p, dout.Hp, dout.Wp, dout.py, dout.px, dout.C,
                                                                       coff, Ho, Wo, din);
   DIM_LAUNCH_CHECK();
-  thin_deconv_wgrad_kernel<<<cdiv(66 * 32, 256), 256, 0, st>>>(in, B, Hi, Wi, dout.p, dout.Hp, dout.Wp, dout.py, dout.px, dout.C, coff, Ho,
+  DIM_CHECK(cudaEventRecord(ts->ev_fork, st));  // dout is final on st; the weight gradient is off the critical path
+  DIM_CHECK(cudaStreamWaitEvent(sw, ts->ev_fork, 0));
+  thin_deconv_wgrad_kernel<<<cdiv(66 * 32, 256), 256, 0, sw>>>(in, B, Hi, Wi, dout.p, dout.Hp, dout.Wp, dout.py, dout.px, dout.C, coff, Ho,
                                                                 Wo, dw, db);
   DIM_LAUNCH_CHECK();
   return 0;
@@ -1215,21 +1249,21 @@ int train_forward_backward(dim_ctx *ctx, const TrainIO &io, cudaStream_t st) {
   const Buf a10 = act_buf(ns, 10), a8 = act_buf(ns, 8), a6 = act_buf(ns, 6);
   if (int rc = copy_interior(a10, ts->act10b, 0, B, 1024, st)) return rc;
   LAUNCH1D(thin_conv_fwd_kernel<2>, (size_t)B * h6 * w6 * 32, st, ts->act10b.p, ts->act10b.Hp, ts->act10b.Wp, 1024, 1024, B, h6, w6,
-           M + ts->off[P_CONV1D].w, M + ts->off[P_CONV1D].b, ts->flow6);
+           ts->thin_w[0], M + ts->off[P_CONV1D].b, ts->flow6);
   if (int rc = run_classes(ctx, ts, tm.deconv5_fwd, tm.g_deconv5_fwd, 4, B, st)) return rc;
   if (int rc = copy_interior(a8, ts->cat2, 0, B, 512, st)) return rc;
   LAUNCH1D(thin_deconv_fwd_kernel, (size_t)B * h5 * w5 * 2, st, ts->flow6, B, h6, w6, M + ts->off[P_UP65].w, M + ts->off[P_UP65].b,
            ts->cat2.p, ts->cat2.Hp, ts->cat2.Wp, 1, 1, 1088, 1024, h5, w5);
   LAUNCH1D(thin_conv_fwd_kernel<2>, (size_t)B * h5 * w5 * 32, st, ts->cat2.p, ts->cat2.Hp, ts->cat2.Wp, 1088, 1026, B, h5, w5,
-           M + ts->off[P_CONV2D].w, M + ts->off[P_CONV2D].b, ts->flow5);
+           ts->thin_w[1], M + ts->off[P_CONV2D].b, ts->flow5);
   if (int rc = run_classes(ctx, ts, tm.deconv4_fwd, tm.g_deconv4_fwd, 4, B, st)) return rc;
   if (int rc = copy_interior(a6, ts->cat3, 0, B, 512, st)) return rc;
   LAUNCH1D(thin_deconv_fwd_kernel, (size_t)B * h4 * w4 * 2, st, ts->flow5, B, h5, w5, M + ts->off[P_UP54].w, M + ts->off[P_UP54].b,
            ts->cat3.p, ts->cat3.Hp, ts->cat3.Wp, 1, 1, 832, 768, h4, w4);
   LAUNCH1D(thin_conv_fwd_kernel<2>, (size_t)B * h4 * w4 * 32, st, ts->cat3.p, ts->cat3.Hp, ts->cat3.Wp, 832, 770, B, h4, w4,
-           M + ts->off[P_CONV3D].w, M + ts->off[P_CONV3D].b, ts->flow4);
+           ts->thin_w[2], M + ts->off[P_CONV3D].b, ts->flow4);
   LAUNCH1D(thin_conv_fwd_kernel<1>, (size_t)B * h4 * w4 * 32, st, ts->cat3.p, ts->cat3.Hp, ts->cat3.Wp, 832, 770, B, h4, w4,
-           M + ts->off[P_MASK3].w, M + ts->off[P_MASK3].b, ts->mask4);
+           ts->thin_w[3], M + ts->off[P_MASK3].b, ts->mask4);
   DIM_CHECK(cudaEventRecord(ts->ev_phase[2], st));
   fullres_loss_kernel<<<LOSS_BLOCKS, 256, 0, st>>>(ts->flow4, ts->mask4, h4, w4, M + ts->off[P_UPS].w, M + ts->off[P_MUPS].w, io.zflow,
                                                    io.zfw, io.zmask_gt, B, H, W, 20.0f, gs_flow, gs_mask, io.flow_est, io.mask_prob,
@@ -1262,41 +1296,44 @@ int train_forward_backward(dim_ctx *ctx, const TrainIO &io, cudaStream_t st) {
   fc_heads_bwd_kernel<<<B, 256, 0, st>>>(ts->drot, ts->dtrans, M + ts->off[P_ROT].w, M + ts->off[P_TRANS].w, M + ts->off[P_FC7].w, ts->h6,
                                          ts->h7, ts->dh7, ts->dh6);
   DIM_LAUNCH_CHECK();
-  LAUNCH1D(fc_wgrad_kernel, 4 * 256, st, ts->drot, ts->h7, B, 4, 256, G + ts->off[P_ROT].w, G + ts->off[P_ROT].b);
-  LAUNCH1D(fc_wgrad_kernel, 3 * 256, st, ts->dtrans, ts->h7, B, 3, 256, G + ts->off[P_TRANS].w, G + ts->off[P_TRANS].b);
-  LAUNCH1D(fc_wgrad_kernel, 256 * 256, st, ts->dh7, ts->h6, B, 256, 256, G + ts->off[P_FC7].w, G + ts->off[P_FC7].b);
-  fc6_wgrad_kernel<<<dim3(81920 / 2 / 256, 8), 256, 0, st>>>(ts->dh6, ns->act_hi[10], B, G + ts->off[P_FC6].w);
+  // every weight gradient runs on the internal stream sw, next to the data-gradient chain on st
+  cudaStream_t sw = ts->side[3];
+  if (int rc = fork_side(ts, st)) return rc;
+  LAUNCH1D(fc_wgrad_kernel, 4 * 256, sw, ts->drot, ts->h7, B, 4, 256, G + ts->off[P_ROT].w, G + ts->off[P_ROT].b);
+  LAUNCH1D(fc_wgrad_kernel, 3 * 256, sw, ts->dtrans, ts->h7, B, 3, 256, G + ts->off[P_TRANS].w, G + ts->off[P_TRANS].b);
+  LAUNCH1D(fc_wgrad_kernel, 256 * 256, sw, ts->dh7, ts->h6, B, 256, 256, G + ts->off[P_FC7].w, G + ts->off[P_FC7].b);
+  fc6_wgrad_kernel<<<dim3(81920 / 2 / 256, 8), 256, 0, sw>>>(ts->dh6, ns->act_hi[10], B, G + ts->off[P_FC6].w);
   DIM_LAUNCH_CHECK();
-  LAUNCH1D(fc_wgrad_kernel, 256, st, ts->dh6, ts->h6 /*unused for K=0*/, B, 256, 0, G + ts->off[P_FC6].w /*no write*/, G + ts->off[P_FC6].b);
+  LAUNCH1D(fc_wgrad_kernel, 256, sw, ts->dh6, ts->h6 /*unused for K=0*/, B, 256, 0, G + ts->off[P_FC6].w /*no write*/, G + ts->off[P_FC6].b);
   DIM_CHECK(cudaEventRecord(ts->ev_phase[4], st));
   // full-resolution heads -> 1/16 maps
   LAUNCH1D(upsample_bwd_kernel, (size_t)B * h4 * w4 * 3 * 32, st, ts->dfull, M + ts->off[P_UPS].w, M + ts->off[P_MUPS].w, B, H, W, h4, w4,
            ts->dflow4, ts->dmask4);
   // Convolution3 / mask_conv3
-  if (int rc = thin_wgrad<2>(ts, ts->cat3, 770, B, h4, w4, ts->dflow4, G + ts->off[P_CONV3D].w, G + ts->off[P_CONV3D].b, st)) return rc;
-  if (int rc = thin_wgrad<1>(ts, ts->cat3, 770, B, h4, w4, ts->dmask4, G + ts->off[P_MASK3].w, G + ts->off[P_MASK3].b, st)) return rc;
-  LAUNCH1D(thin_conv_dgrad_kernel<2>, (size_t)B * h4 * w4 * 832, st, ts->dflow4, M + ts->off[P_CONV3D].w, 770, B, h4, w4, ts->dcat3.p,
+  if (int rc = fork_side(ts, st)) return rc;
+  if (int rc = thin_wgrad<2>(ts, ts->cat3, 770, B, h4, w4, ts->dflow4, G + ts->off[P_CONV3D].w, G + ts->off[P_CONV3D].b, sw)) return rc;
+  if (int rc = thin_wgrad<1>(ts, ts->cat3, 770, B, h4, w4, ts->dmask4, G + ts->off[P_MASK3].w, G + ts->off[P_MASK3].b, sw)) return rc;
+  LAUNCH1D(thin_conv_dgrad_kernel<2>, (size_t)B * h4 * w4 * 832, st, ts->dflow4, ts->thin_w[2], 770, B, h4, w4, ts->dcat3.p,
            ts->dcat3.Hp, ts->dcat3.Wp, 1, 1, 832, 832, 0);
-  LAUNCH1D(thin_conv_dgrad_kernel<1>, (size_t)B * h4 * w4 * 832, st, ts->dmask4, M + ts->off[P_MASK3].w, 770, B, h4, w4, ts->dcat3.p,
+  LAUNCH1D(thin_conv_dgrad_kernel<1>, (size_t)B * h4 * w4 * 832, st, ts->dmask4, ts->thin_w[3], 770, B, h4, w4, ts->dcat3.p,
            ts->dcat3.Hp, ts->dcat3.Wp, 1, 1, 832, 832, 1);
   // upsample_flow5to4
   if (int rc = thin_deconv_bwd(ts->flow5, B, h5, w5, M + ts->off[P_UP54].w, ts->dcat3, 768, h4, w4, ts->dflow5, G + ts->off[P_UP54].w,
-                               G + ts->off[P_UP54].b, st))
+                               G + ts->off[P_UP54].b, st, sw, ts))
     return rc;
   // deconv4: LeakyReLU backward on its slice, bias, weight and data gradients
   LAUNCH1D(lrelu_mask_inplace_kernel, (size_t)B * h4 * w4 * 32, st, ts->dcat3.p, ts->cat3.p, ts->cat3.Hp, ts->cat3.Wp, 1, 1, 832, 512, B, h4,
            w4, 256, 0.1f);
-  cudaStream_t sw = ts->side[3];
   if (int rc = fork_side(ts, st)) return rc;
   if (int rc = bias_grad(ts, ts->dcat3, B, 512, 256, G + ts->off[P_DECONV4].b, sw)) return rc;
   if (int rc = run_wgrad(tm.wg_deconv4, tm.wg_bn_d4, WG_DECONV, 1026, 256, 4, G + ts->off[P_DECONV4].w, sw)) return rc;
   if (int rc = run_generic(ctx, tm.deconv4_dgrad, tm.g_deconv4_dgrad, B, st)) return rc;
   // Convolution2 (adds to dcat2), upsample_flow6to5
-  if (int rc = thin_wgrad<2>(ts, ts->cat2, 1026, B, h5, w5, ts->dflow5, G + ts->off[P_CONV2D].w, G + ts->off[P_CONV2D].b, st)) return rc;
-  LAUNCH1D(thin_conv_dgrad_kernel<2>, (size_t)B * h5 * w5 * 1088, st, ts->dflow5, M + ts->off[P_CONV2D].w, 1026, B, h5, w5, ts->dcat2.p,
+  if (int rc = thin_wgrad<2>(ts, ts->cat2, 1026, B, h5, w5, ts->dflow5, G + ts->off[P_CONV2D].w, G + ts->off[P_CONV2D].b, sw)) return rc;  // dflow5 was final before the last fork
+  LAUNCH1D(thin_conv_dgrad_kernel<2>, (size_t)B * h5 * w5 * 1088, st, ts->dflow5, ts->thin_w[1], 1026, B, h5, w5, ts->dcat2.p,
            ts->dcat2.Hp, ts->dcat2.Wp, 1, 1, 1088, 1088, 1);
   if (int rc = thin_deconv_bwd(ts->flow6, B, h6, w6, M + ts->off[P_UP65].w, ts->dcat2, 1024, h5, w5, ts->dflow6, G + ts->off[P_UP65].w,
-                               G + ts->off[P_UP65].b, st))
+                               G + ts->off[P_UP65].b, st, sw, ts))
     return rc;
   // deconv5
   LAUNCH1D(lrelu_mask_inplace_kernel, (size_t)B * h5 * w5 * 64, st, ts->dcat2.p, ts->cat2.p, ts->cat2.Hp, ts->cat2.Wp, 1, 1, 1088, 512, B, h5,
@@ -1305,10 +1342,11 @@ int train_forward_backward(dim_ctx *ctx, const TrainIO &io, cudaStream_t st) {
   if (int rc = bias_grad(ts, ts->dcat2, B, 512, 512, G + ts->off[P_DECONV5].b, sw)) return rc;
   if (int rc = run_wgrad(tm.wg_deconv5, tm.wg_bn_d5, WG_DECONV, 1024, 512, 4, G + ts->off[P_DECONV5].w, sw)) return rc;
   // Convolution1 -> partial gradient of ReLU10, + fc6 data gradient, then deconv5's data gradient closes dZ of conv6_1
-  if (int rc = thin_wgrad<2>(ts, ts->act10b, 1024, B, h6, w6, ts->dflow6, G + ts->off[P_CONV1D].w, G + ts->off[P_CONV1D].b, st)) return rc;
-  LAUNCH1D(thin_conv_dgrad_kernel<2>, (size_t)B * h6 * w6 * 1024, st, ts->dflow6, M + ts->off[P_CONV1D].w, 1024, B, h6, w6, ts->dA10p.p,
+  if (int rc = thin_wgrad<2>(ts, ts->act10b, 1024, B, h6, w6, ts->dflow6, G + ts->off[P_CONV1D].w, G + ts->off[P_CONV1D].b, sw)) return rc;  // dflow6: before the last fork
+  LAUNCH1D(thin_conv_dgrad_kernel<2>, (size_t)B * h6 * w6 * 1024, st, ts->dflow6, ts->thin_w[0], 1024, B, h6, w6, ts->dA10p.p,
            ts->dA10p.Hp, ts->dA10p.Wp, 0, 0, 1024, 1024, 0);
-  LAUNCH1D(fc6_dgrad_kernel, 81920, st, ts->dh6, ns->fc6_w_hi, B, ts->dA10p.p);
+  fc6_dgrad_kernel<<<81920 / 64, 256, 0, st>>>(ts->dh6, ns->fc6_w_hi, B, ts->dA10p.p);
+  DIM_LAUNCH_CHECK();
   if (int rc = run_generic(ctx, tm.deconv5_dgrad, tm.g_deconv5_dgrad, B, st)) return rc;
   DIM_CHECK(cudaEventRecord(ts->ev_phase[5], st));
   // encoder
