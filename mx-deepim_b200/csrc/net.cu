@@ -554,6 +554,8 @@ int net_forward(dim_ctx *ctx, int B, int precision, const float *zoom_factor, fl
   }
   const TensorMaps &tm = it->second;
   const bool s3 = precision == DIM_PREC_BF16X3;
+  if (s3 && ns->lo_stale)
+    if (int rc = train_refresh_lo(ctx, st)) return rc;
   for (int i = 0; i < 10; ++i) {
     const LayerGeom &g = tm.g[i];
     const ConvKParams &kp = tm.kp[i];

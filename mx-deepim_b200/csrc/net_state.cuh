@@ -50,7 +50,8 @@ struct NetState {
   size_t conv_partial_elems = 0;
   float *tail_ws = nullptr;  // K-slice partials of the tail tiles: [<= 2*SMs slots][128][256] fp32
   bool loaded = false, net_ok = false;
-  float *save_h6 = nullptr, *save_h7 = nullptr;  // training: fc6 / fc7 activations kept for the backward pass ([B][256])
+  float *save_h6 = nullptr, *save_h7 = nullptr;
+  bool lo_stale = false;  // training updated the weights without refreshing the bf16 'lo' halves (bf16x3 mode refreshes lazily)  // training: fc6 / fc7 activations kept for the backward pass ([B][256])
   std::map<int, TensorMaps> maps;  // per batch size
   int max_batch = 0, num_sms = 148;
 };
@@ -64,6 +65,7 @@ static constexpr int FC6_SPLITS = FC6_K / FC6_KC;  // 320
 int encode_map(CUtensorMap *m, void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
                const uint32_t *box, int block_k /*64: SW128, 32: SW64, 0: no swizzle*/);
 uint32_t make_idesc(int M, int N);
+int train_refresh_lo(dim_ctx *ctx, cudaStream_t st);  // train.cu
 int net_forward(dim_ctx *ctx, int B, int precision, const float *zoom_factor, float *rot_out, float *trans_out,
                 float *se3_out, cudaStream_t st, cudaEvent_t after_conv);
 

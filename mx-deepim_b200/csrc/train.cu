@@ -776,14 +776,16 @@ void train_destroy(dim_ctx *ctx) {
   } while (0)
 
 // refresh every bf16 operand pack (and the fp32 head parameters of the inference net) from the master weights
-static int repack_all(dim_ctx *ctx, cudaStream_t st) {
+// with_lo = false skips the bf16 'lo' halves (only the bf16x3 inference mode reads them); they are then marked stale and
+// refreshed lazily by train_refresh_lo() the next time that mode runs
+static int repack_all(dim_ctx *ctx, cudaStream_t st, bool with_lo) {
   NetState *ns = ctx->net;
   TrainState *ts = train_of(ctx);
   const float *M = ts->master;
-  LAUNCH1D(pack_conv1_kernel, 64 * 512, st, M + ts->off[0].w, ns->w_hi[0], ns->w_lo[0]);
+  LAUNCH1D(pack_conv1_kernel, 64 * 512, st, M + ts->off[0].w, ns->w_hi[0], with_lo ? ns->w_lo[0] : nullptr);
   for (int i = 0; i < 10; ++i) {
     const LayerSpec &s = kLayers[i];
-    if (i >= 1) LAUNCH1D(pack_conv_fwd_kernel, ts->off[i].wn, st, M + ts->off[i].w, s.Cout, s.Cin, s.k, ns->w_hi[i], ns->w_lo[i]);
+    if (i >= 1) LAUNCH1D(pack_conv_fwd_kernel, ts->off[i].wn, st, M + ts->off[i].w, s.Cout, s.Cin, s.k, ns->w_hi[i], with_lo ? ns->w_lo[i] : nullptr);
     DIM_CHECK(cudaMemcpyAsync(ns->bias[i], M + ts->off[i].b, s.Cout * 4, cudaMemcpyDeviceToDevice, st));
     if (i >= 1) {
       const int ncls = s.stride == 2 ? 4 : 1;
@@ -795,7 +797,8 @@ static int repack_all(dim_ctx *ctx, cudaStream_t st) {
       }
     }
   }
-  LAUNCH1D(pack_fc6_kernel, (size_t)256 * 81920, st, M + ts->off[P_FC6].w, ns->fc6_w_hi, ns->fc6_w_lo);
+  LAUNCH1D(pack_fc6_kernel, (size_t)256 * 81920, st, M + ts->off[P_FC6].w, ns->fc6_w_hi, with_lo ? ns->fc6_w_lo : nullptr);
+  ns->lo_stale = !with_lo;
   LAUNCH1D(transpose256_kernel, 65536, st, M + ts->off[P_FC7].w, ns->fc7_wT);
   DIM_CHECK(cudaMemcpyAsync(ns->fc6_b, M + ts->off[P_FC6].b, 256 * 4, cudaMemcpyDeviceToDevice, st));
   DIM_CHECK(cudaMemcpyAsync(ns->fc7_b, M + ts->off[P_FC7].b, 256 * 4, cudaMemcpyDeviceToDevice, st));
@@ -828,7 +831,13 @@ int train_load_params(dim_ctx *ctx, const float *flat_host, size_t n, cudaStream
   }
   DIM_CHECK(cudaMemcpyAsync(ts->master, flat_host, n * sizeof(float), cudaMemcpyHostToDevice, st));
   DIM_CHECK(cudaMemsetAsync(ts->mom, 0, n * sizeof(float), st));
-  return repack_all(ctx, st);
+  return repack_all(ctx, st, true);
+}
+
+// called by net_forward before a bf16x3 pass when the training step left the lo halves stale
+int train_refresh_lo(dim_ctx *ctx, cudaStream_t st) {
+  if (train_of(ctx) == nullptr) return 0;
+  return repack_all(ctx, st, true);
 }
 
 int train_get_params(dim_ctx *ctx, float *flat_host, size_t n, int which, cudaStream_t st) {
@@ -1382,7 +1391,7 @@ int train_sgd_update(dim_ctx *ctx, const float *grads, float lr, float momentum,
   }
   const size_t n = ts->off[21].b + ts->off[21].bn;  // the two bilinear upsampling kernels behind it are frozen (lr_mult 0)
   LAUNCH1D(sgd_kernel, n, st, ts->master, ts->mom, grads, n, segs, lr, momentum, wd, rescale);
-  return repack_all(ctx, st);
+  return repack_all(ctx, st, false);
 }
 
 // test / debugging hook: copy an intermediate to the host.  id: 0 flow6, 1 flow5, 2 flow4, 3 mask4 (fp32);

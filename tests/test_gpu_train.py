@@ -144,6 +144,10 @@ def test_sgd_update_and_repack(setup):
     orot, otrans = O.net_forward(pnow, z["zoom_image_observed"].cpu().numpy(), z["zoom_image_rendered"].cpu().numpy(),
                                  z["zoom_mask_observed"].cpu().numpy(), z["zoom_mask_rendered"].cpu().numpy())
     assert np.abs(rot.cpu().numpy() - orot).max() < 2e-2 and np.abs(trans.cpu().numpy() - otrans).max() < 2e-2
+    # the update skips the bf16 'lo' halves; the near-fp32 (bf16x3) inference mode refreshes them lazily
+    rot3, trans3 = ctx.net_forward(z["zoom_image_observed"], z["zoom_image_rendered"], z["zoom_mask_observed"], z["zoom_mask_rendered"],
+                                   precision=1)
+    assert np.abs(rot3.cpu().numpy() - orot).max() < 1e-4 and np.abs(trans3.cpu().numpy() - otrans).max() < 1e-3
 
 
 def test_inner_iteration_loop_like_module_fit(setup):
