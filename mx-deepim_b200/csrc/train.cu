@@ -607,12 +607,22 @@ __device__ __forceinline__ void store_split(__nv_bfloat16 *hi, __nv_bfloat16 *lo
   hi[i] = h;
   if (lo) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
-// forward pack [Cout][kh][kw][Cin] (net.cu net_load)
+// The packs are permutations of (Cout, Cin, k, k); a thread-per-destination gather reads the master with a k*k-float
+// stride (every 4-byte read in its own sector).  The tiled kernels below read k*k-float rows (contiguous) into shared
+// memory and write 64 consecutive bf16 per (tap, class): both sides coalesced.
+//
+// forward pack [Cout][kh][kw][Cin] (net.cu net_load): block = (co, 64 input channels)
 __global__ void __launch_bounds__(256) pack_conv_fwd_kernel(const float *w, int Cout, int Cin, int k, __nv_bfloat16 *hi, __nv_bfloat16 *lo) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)Cout * k * k * Cin) return;
-  const int c = (int)(i % Cin), tap = (int)((i / Cin) % (k * k)), co = (int)(i / ((size_t)Cin * k * k));
-  store_split(hi, lo, i, w[((size_t)(co * Cin + c) * k + tap / k) * k + tap % k]);
+  __shared__ float tile[64 * 25];
+  const int co = blockIdx.x, c0 = blockIdx.y * 64, kk = k * k;
+  const int nc = min(64, Cin - c0);
+  const float *src = w + ((size_t)co * Cin + c0) * kk;
+  for (int i = threadIdx.x; i < nc * kk; i += 256) tile[i] = src[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < nc * kk; i += 256) {
+    const int tap = i / nc, cl = i - tap * nc;
+    store_split(hi, lo, ((size_t)co * kk + tap) * Cin + c0 + cl, tile[cl * kk + tap]);
+  }
 }
 // conv1 space-to-depth pack [64][4][4][32]
 __global__ void __launch_bounds__(256) pack_conv1_kernel(const float *w, __nv_bfloat16 *hi, __nv_bfloat16 *lo) {
@@ -622,30 +632,54 @@ __global__ void __launch_bounds__(256) pack_conv1_kernel(const float *w, __nv_bf
   const int kh = 2 * dh + ph, kw = 2 * dw + pw;
   store_split(hi, lo, i, (kh < 7 && kw < 7) ? w[((co * 8 + c) * 7 + kh) * 7 + kw] : 0.f);
 }
-// data-gradient pack of one parity class: [Cin][Ty][Tx][Cout], ky = ry + s*(Ty-1-ty)
-__global__ void __launch_bounds__(256) pack_dgrad_kernel(const float *w, int Cout, int Cin, int k, int s, int ry, int rx, int Ty, int Tx,
-                                                         __nv_bfloat16 *dst) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)Cin * Ty * Tx * Cout) return;
-  const int co = (int)(i % Cout), t = (int)((i / Cout) % (Ty * Tx)), ci = (int)(i / ((size_t)Cout * Ty * Tx));
-  const int ky = ry + s * (Ty - 1 - t / Tx), kx = rx + s * (Tx - 1 - t % Tx);
-  dst[i] = __float2bfloat16_rn(w[((size_t)(co * Cin + ci) * k + ky) * k + kx]);
+// data-gradient packs of ALL parity classes of one layer: class (ry, rx) is [Cin][Ty][Tx][Cout] with ky = ry + s*(Ty-1-ty).
+// block = (ci, 64 output channels): reads 64 rows of k*k floats, writes 64 consecutive bf16 per (class, tap)
+struct DgradPackDst { __nv_bfloat16 *p[4]; };
+__global__ void __launch_bounds__(256) pack_dgrad_kernel(const float *w, int Cout, int Cin, int k, int s, DgradPackDst dst) {
+  __shared__ float tile[64 * 25];
+  const int ci = blockIdx.x, co0 = blockIdx.y * 64, kk = k * k;
+  for (int i = threadIdx.x; i < 64 * kk; i += 256) {
+    const int col = i / kk, e = i - col * kk;
+    tile[i] = w[((size_t)(co0 + col) * Cin + ci) * kk + e];
+  }
+  __syncthreads();
+  const int ncls = s == 2 ? 4 : 1;
+  for (int c = 0; c < ncls; ++c) {
+    const int ry = c >> 1, rx = c & 1;
+    const int Ty = s == 2 ? (k - ry + 1) / 2 : k, Tx = s == 2 ? (k - rx + 1) / 2 : k;
+    for (int i = threadIdx.x; i < Ty * Tx * 64; i += 256) {
+      const int tt = i >> 6, col = i & 63;
+      const int ky = ry + s * (Ty - 1 - tt / Tx), kx = rx + s * (Tx - 1 - tt % Tx);
+      dst.p[c][((size_t)ci * Ty * Tx + tt) * Cout + co0 + col] = __float2bfloat16_rn(tile[col * kk + ky * k + kx]);
+    }
+  }
 }
-// deconvolution forward, parity class (ry, rx): [Cout][2][2][Cin_eff], ky = ry + 2*(1 - ty); W (Cin,Cout,4,4)
-__global__ void __launch_bounds__(256) pack_deconv_fwd_kernel(const float *w, int Cin, int Cout, int Cin_eff, int ry, int rx,
-                                                              __nv_bfloat16 *dst) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)Cout * 4 * Cin_eff) return;
-  const int ci = (int)(i % Cin_eff), t = (int)((i / Cin_eff) % 4), co = (int)(i / ((size_t)Cin_eff * 4));
-  const int ky = ry + 2 * (1 - t / 2), kx = rx + 2 * (1 - t % 2);
-  dst[i] = __float2bfloat16_rn(ci < Cin ? w[((size_t)(ci * Cout + co) * 4 + ky) * 4 + kx] : 0.f);
+// deconvolution forward, all 4 parity classes: class (ry, rx) is [Cout][2][2][Cin_eff], ky = ry + 2*(1 - ty); W (Cin,Cout,4,4).
+// block = (co, 64 input channels)
+__global__ void __launch_bounds__(256) pack_deconv_fwd_kernel(const float *w, int Cin, int Cout, int Cin_eff, DgradPackDst dst) {
+  __shared__ float tile[64 * 16];
+  const int co = blockIdx.x, c0 = blockIdx.y * 64;
+  for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+    const int cl = i >> 4, e = i & 15;
+    tile[i] = (c0 + cl < Cin) ? w[((size_t)(c0 + cl) * Cout + co) * 16 + e] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 4 * 4 * 64; i += 256) {
+    const int cl = i & 63, t = (i >> 6) & 3, c = i >> 8;
+    const int ky = (c >> 1) + 2 * (1 - t / 2), kx = (c & 1) + 2 * (1 - t % 2);
+    if (c0 + cl < Cin_eff) dst.p[c][((size_t)co * 4 + t) * Cin_eff + c0 + cl] = __float2bfloat16_rn(tile[cl * 16 + ky * 4 + kx]);
+  }
 }
-// deconvolution data gradient = stride-2 4x4 convolution: [Cin_eff][4][4][Cout]
+// deconvolution data gradient = stride-2 4x4 convolution: [Cin_eff][4][4][Cout]; block = one ci: Cout*16 contiguous floats in
 __global__ void __launch_bounds__(256) pack_deconv_dgrad_kernel(const float *w, int Cin, int Cout, int Cin_eff, __nv_bfloat16 *dst) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)Cin_eff * 16 * Cout) return;
-  const int co = (int)(i % Cout), tap = (int)((i / Cout) % 16), ci = (int)(i / ((size_t)Cout * 16));
-  dst[i] = __float2bfloat16_rn(ci < Cin ? w[((size_t)(ci * Cout + co) * 4 + tap / 4) * 4 + tap % 4] : 0.f);
+  extern __shared__ float dtile[];  // [Cout][17] (padded: the transposed read below would otherwise hit 2 banks)
+  const int ci = blockIdx.x;
+  for (int i = threadIdx.x; i < Cout * 16; i += 256) dtile[(i >> 4) * 17 + (i & 15)] = ci < Cin ? w[(size_t)ci * Cout * 16 + i] : 0.f;
+  __syncthreads();
+  for (int i = threadIdx.x; i < Cout * 16; i += 256) {
+    const int co = i % Cout, tap = i / Cout;
+    dst[((size_t)ci * 16 + tap) * Cout + co] = __float2bfloat16_rn(dtile[co * 17 + tap]);
+  }
 }
 // fc6 master (out, hw, c) fp32 -> bf16 hi/lo operand (same order)
 __global__ void __launch_bounds__(256) pack_fc6_kernel(const float *w, __nv_bfloat16 *hi, __nv_bfloat16 *lo) {
@@ -783,39 +817,33 @@ static int repack_all(dim_ctx *ctx, cudaStream_t st, bool with_lo) {
   TrainState *ts = train_of(ctx);
   const float *M = ts->master;
   LAUNCH1D(pack_conv1_kernel, 64 * 512, st, M + ts->off[0].w, ns->w_hi[0], with_lo ? ns->w_lo[0] : nullptr);
-  for (int i = 0; i < 10; ++i) {
+  for (int i = 1; i < 10; ++i) {
     const LayerSpec &s = kLayers[i];
-    if (i >= 1) LAUNCH1D(pack_conv_fwd_kernel, ts->off[i].wn, st, M + ts->off[i].w, s.Cout, s.Cin, s.k, ns->w_hi[i], with_lo ? ns->w_lo[i] : nullptr);
-    DIM_CHECK(cudaMemcpyAsync(ns->bias[i], M + ts->off[i].b, s.Cout * 4, cudaMemcpyDeviceToDevice, st));
-    if (i >= 1) {
-      const int ncls = s.stride == 2 ? 4 : 1;
-      for (int c = 0; c < ncls; ++c) {
-        const int ry = c >> 1, rx = c & 1;
-        const int Ty = s.stride == 2 ? (s.k - ry + 1) / 2 : s.k, Tx = s.stride == 2 ? (s.k - rx + 1) / 2 : s.k;
-        LAUNCH1D(pack_dgrad_kernel, (size_t)s.Cin * Ty * Tx * s.Cout, st, M + ts->off[i].w, s.Cout, s.Cin, s.k, s.stride, ry, rx, Ty,
-                 Tx, ts->dg_pack[i][c]);
-      }
-    }
+    pack_conv_fwd_kernel<<<dim3(s.Cout, cdiv(s.Cin, 64)), 256, 0, st>>>(M + ts->off[i].w, s.Cout, s.Cin, s.k, ns->w_hi[i],
+                                                                          with_lo ? ns->w_lo[i] : nullptr);
+    DIM_LAUNCH_CHECK();
+    DgradPackDst d{{ts->dg_pack[i][0], ts->dg_pack[i][1], ts->dg_pack[i][2], ts->dg_pack[i][3]}};
+    pack_dgrad_kernel<<<dim3(s.Cin, s.Cout / 64), 256, 0, st>>>(M + ts->off[i].w, s.Cout, s.Cin, s.k, s.stride, d);
+    DIM_LAUNCH_CHECK();
   }
   LAUNCH1D(pack_fc6_kernel, (size_t)256 * 81920, st, M + ts->off[P_FC6].w, ns->fc6_w_hi, with_lo ? ns->fc6_w_lo : nullptr);
   ns->lo_stale = !with_lo;
   LAUNCH1D(transpose256_kernel, 65536, st, M + ts->off[P_FC7].w, ns->fc7_wT);
-  DIM_CHECK(cudaMemcpyAsync(ns->fc6_b, M + ts->off[P_FC6].b, 256 * 4, cudaMemcpyDeviceToDevice, st));
-  DIM_CHECK(cudaMemcpyAsync(ns->fc7_b, M + ts->off[P_FC7].b, 256 * 4, cudaMemcpyDeviceToDevice, st));
-  DIM_CHECK(cudaMemcpyAsync(ns->rot_w, M + ts->off[P_ROT].w, 1024 * 4, cudaMemcpyDeviceToDevice, st));
-  DIM_CHECK(cudaMemcpyAsync(ns->rot_b, M + ts->off[P_ROT].b, 4 * 4, cudaMemcpyDeviceToDevice, st));
-  DIM_CHECK(cudaMemcpyAsync(ns->trans_w, M + ts->off[P_TRANS].w, 768 * 4, cudaMemcpyDeviceToDevice, st));
-  DIM_CHECK(cudaMemcpyAsync(ns->trans_b, M + ts->off[P_TRANS].b, 3 * 4, cudaMemcpyDeviceToDevice, st));
-  for (int c = 0; c < 4; ++c) {
-    LAUNCH1D(pack_deconv_fwd_kernel, (size_t)512 * 4 * 1024, st, M + ts->off[P_DECONV5].w, 1024, 512, 1024, c >> 1, c & 1, ts->d5_fwd[c]);
-    LAUNCH1D(pack_deconv_fwd_kernel, (size_t)256 * 4 * 1088, st, M + ts->off[P_DECONV4].w, 1026, 256, 1088, c >> 1, c & 1, ts->d4_fwd[c]);
+  {
+    DgradPackDst d5{{ts->d5_fwd[0], ts->d5_fwd[1], ts->d5_fwd[2], ts->d5_fwd[3]}}, d4{{ts->d4_fwd[0], ts->d4_fwd[1], ts->d4_fwd[2], ts->d4_fwd[3]}};
+    pack_deconv_fwd_kernel<<<dim3(512, 1024 / 64), 256, 0, st>>>(M + ts->off[P_DECONV5].w, 1024, 512, 1024, d5);
+    DIM_LAUNCH_CHECK();
+    pack_deconv_fwd_kernel<<<dim3(256, 1088 / 64), 256, 0, st>>>(M + ts->off[P_DECONV4].w, 1026, 256, 1088, d4);
+    DIM_LAUNCH_CHECK();
   }
   LAUNCH1D(pack_thin_kernel, 2 * 1024 * 9, st, M + ts->off[P_CONV1D].w, 2, 1024, ts->thin_w[0]);
   LAUNCH1D(pack_thin_kernel, 2 * 1026 * 9, st, M + ts->off[P_CONV2D].w, 2, 1026, ts->thin_w[1]);
   LAUNCH1D(pack_thin_kernel, 2 * 770 * 9, st, M + ts->off[P_CONV3D].w, 2, 770, ts->thin_w[2]);
   LAUNCH1D(pack_thin_kernel, 1 * 770 * 9, st, M + ts->off[P_MASK3].w, 1, 770, ts->thin_w[3]);
-  LAUNCH1D(pack_deconv_dgrad_kernel, (size_t)1024 * 16 * 512, st, M + ts->off[P_DECONV5].w, 1024, 512, 1024, ts->d5_dg);
-  LAUNCH1D(pack_deconv_dgrad_kernel, (size_t)1088 * 16 * 256, st, M + ts->off[P_DECONV4].w, 1026, 256, 1088, ts->d4_dg);
+  pack_deconv_dgrad_kernel<<<1024, 256, 512 * 17 * 4, st>>>(M + ts->off[P_DECONV5].w, 1024, 512, 1024, ts->d5_dg);
+  DIM_LAUNCH_CHECK();
+  pack_deconv_dgrad_kernel<<<1088, 256, 256 * 17 * 4, st>>>(M + ts->off[P_DECONV4].w, 1026, 256, 1088, ts->d4_dg);
+  DIM_LAUNCH_CHECK();
   return 0;
 }
 
@@ -831,6 +859,13 @@ int train_load_params(dim_ctx *ctx, const float *flat_host, size_t n, cudaStream
   }
   DIM_CHECK(cudaMemcpyAsync(ts->master, flat_host, n * sizeof(float), cudaMemcpyHostToDevice, st));
   DIM_CHECK(cudaMemsetAsync(ts->mom, 0, n * sizeof(float), st));
+  // fp32 parameters that the kernels read as they are (biases, rot / trans heads) now alias the master vector, so an
+  // update needs no copy for them; cached launch descriptors hold the old pointers -> rebuild them lazily
+  for (int i = 0; i < 10; ++i) ns->bias[i] = ts->master + ts->off[i].b;
+  ns->fc6_b = ts->master + ts->off[P_FC6].b; ns->fc7_b = ts->master + ts->off[P_FC7].b;
+  ns->rot_w = ts->master + ts->off[P_ROT].w; ns->rot_b = ts->master + ts->off[P_ROT].b;
+  ns->trans_w = ts->master + ts->off[P_TRANS].w; ns->trans_b = ts->master + ts->off[P_TRANS].b;
+  ns->maps.clear();
   return repack_all(ctx, st, true);
 }
 
