@@ -268,7 +268,7 @@ def run_b200(args):
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT,
                     "h2d_bytes_per_step": int(B * 480 * 640 * 3 + B * 4 + B * 96),
                     "d2h_bytes_per_step": int(N_ITER * B * (96 + 28)), "ms_per_step": round(ms_e2e / K_steps, 4),
-                    "api": "PoseRefiner.submit/result -> dim_refine_host_async (uint8 BGR HWC pinned host images in, float64 poses out; 2 batches in flight)", "timer": "host wall clock around K steps, bracketed by barrier + cuda synchronize"},
+                    "api": "PoseRefiner.submit/result -> dim_refine_host_async (uint8 BGR HWC pinned host images in, float64 poses out; %d batches in flight)" % args.slots, "timer": "host wall clock around K steps, bracketed by barrier + cuda synchronize"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (10 launches / iteration)",
                          "achieved": round(conv_tflops, 2), "peak": peaks["tflops"], "unit": "TFLOP/s",
