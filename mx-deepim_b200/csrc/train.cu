@@ -906,7 +906,7 @@ static void pick_tile(int W, int rows_total, int cap, int &BW, int &BH, int max_
 }
 
 template <int BN, int ST>
-static int launch_generic(const ConvKParams &kp, int total_tiles, int n_tiles, int sms, cudaStream_t st) {
+static int launch_generic(const ConvKParams &kp, int total_tiles, int n_tiles, int cap, cudaStream_t st) {
   using S = ConvSmem2<BN, 64, ST, false, false, 0>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -914,18 +914,28 @@ static int launch_generic(const ConvKParams &kp, int total_tiles, int n_tiles, i
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     attr_set = true;
   }
-  const int grid = total_tiles < sms ? total_tiles : sms;
+  const int grid = total_tiles < cap ? total_tiles : cap;
   conv_igemm_persistent_kernel<BN, 64, ST, false, false, 0, 1><<<grid, 192, S::TOTAL, st>>>(kp, total_tiles, n_tiles, 1, nullptr);
   DIM_LAUNCH_CHECK();
   return 0;
 }
 
+// N <= 128 tiles are bound by L2 -> shared-memory operand traffic, not by the tensor pipe: two resident CTAs per SM with a
+// shallow ring hide more fill latency than one CTA with a deep ring (same finding as conv2 of the forward tower).
+// DIM_TRAIN_OCC2=0 restores one CTA per SM (A/B switch).
+static bool train_occ2() {
+  static const bool v = [] { const char *e = getenv("DIM_TRAIN_OCC2"); return !(e && e[0] == '0'); }();
+  return v;
+}
+
 static int run_generic(dim_ctx *ctx, const ConvKParams &kp, const LayerGeom &g, int B, cudaStream_t st) {
   const int n_tiles = cdiv(g.Cout, g.BLOCK_N);
   const int total = cdiv(B * g.Hq, g.BH) * g.n_col_tiles * n_tiles;
-  if (g.BLOCK_N == 256) return launch_generic<256, 4>(kp, total, n_tiles, ctx->num_sms, st);
-  if (g.BLOCK_N == 128) return launch_generic<128, 5>(kp, total, n_tiles, ctx->num_sms, st);
-  return launch_generic<64, 6>(kp, total, n_tiles, ctx->num_sms, st);
+  const int sms = ctx->num_sms;
+  if (g.BLOCK_N == 256) return launch_generic<256, 4>(kp, total, n_tiles, sms, st);
+  if (g.BLOCK_N == 128)
+    return train_occ2() ? launch_generic<128, 2>(kp, total, n_tiles, 2 * sms, st) : launch_generic<128, 5>(kp, total, n_tiles, sms, st);
+  return train_occ2() ? launch_generic<64, 3>(kp, total, n_tiles, 2 * sms, st) : launch_generic<64, 6>(kp, total, n_tiles, sms, st);
 }
 
 // Describe one launch of the generic kernel.
