@@ -162,3 +162,25 @@ def test_lm6d_disk_formats_round_trip(tmp_path):
     assert np.abs(rec["pose_observed"] - np.loadtxt(os.path.join(str(tmp_path), "data", "gt_observed", "cube", "000000-pose.txt"),
                                                     skiprows=1)).max() == 0
     assert ds.points("glue").shape[1] == 3
+
+
+def test_trainer_flat_parameter_layout():
+    """The flat fp32 parameter vector of the training step (dim_train_param_info; no GPU needed for the table):
+    57 749 164 values = SURVEY 8(d)'s 230 996 656-byte gradient all-reduce, reference tensor order, fc6 kept in NHWC order."""
+    from deepim_b200 import synth, trainer
+    from deepim_b200.grad_allreduce import param_table as ref_table
+    tab = trainer.param_table()
+    assert sum(n for _, n in tab) == 57749164 and 4 * 57749164 == 230996656
+    # same trainable tensors, same order, as the gloo-tested bucket module (which restates deepIM_flownet.py's shapes)
+    assert tab[:len(ref_table())] == ref_table()
+    assert [k for k, _ in tab[-2:]] == ["upsampling_weight", "mask_upsampling_weight"]
+    w = synth.make_train_weights(3)
+    flat = trainer.flatten_params(w)
+    back = trainer.unflatten_params(flat, w)
+    assert all(np.array_equal(back[k], w[k]) for k in w)
+    off = 0
+    for name, n in tab:
+        if name == "fc6_weight":   # stored (out, h*10+w, c): element (o, c*80+hw) of MXNet's layout sits at (o, hw, c)
+            f6 = flat[off:off + n].reshape(256, 80, 1024)
+            assert f6[5, 17, 300] == w["fc6_weight"][5, 300 * 80 + 17]
+        off += n
