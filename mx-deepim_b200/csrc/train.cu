@@ -101,7 +101,7 @@ struct TrainState {
 };
 
 static constexpr int LOSS_BLOCKS = 1024;
-static constexpr int THIN_CHUNKS = 64;
+static constexpr int THIN_CHUNKS = 256;
 static constexpr int BIAS_CHUNKS = 256;  // upper bound; the launch uses min(256, npix / 64) chunks
 
 // ---------------------------------------------------------------------------------- small kernels
@@ -296,28 +296,33 @@ __global__ void __launch_bounds__(256) thin_deconv_bwd_kernel(const float *in, i
                    w[((ci * 2 + co) * 4 + ky) * 4 + kx], acc);
   din[i] = acc;
 }
-// dw (64 values) and db (2 values): one warp per output, lanes stride over the pixels (fixed order -> deterministic)
+// dw (64 values) and db (2 values): one block per output, threads stride over the pixels, fixed-order tree reduction
 __global__ void __launch_bounds__(256) thin_deconv_wgrad_kernel(const float *in, int B, int Hi, int Wi, const __nv_bfloat16 *dout, int Hp,
                                                                 int Wp, int py, int px, int cs, int coff, int Ho, int Wo, float *dw,
                                                                 float *db) {
-  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (t >= 66) return;
+  __shared__ float red[256];
+  const int t = blockIdx.x;  // 0..63: dw[((ci*2+co)*4+ky)*4+kx], 64..65: db[co]
   float acc = 0.f;
   if (t < 64) {
     const int kx = t & 3, ky = (t >> 2) & 3, co = (t >> 4) & 1, ci = t >> 5;
-    for (int p = lane; p < B * Hi * Wi; p += 32) {
+    for (int p = threadIdx.x; p < B * Hi * Wi; p += 256) {
       const int ix = p % Wi, iy = (p / Wi) % Hi, b = p / (Wi * Hi);
       acc = fmaf(in[(size_t)p * 2 + ci], thin_dY(dout, Hp, Wp, py, px, cs, coff, Ho, Wo, b, 2 * iy + ky - 1, 2 * ix + kx - 1, co), acc);
     }
   } else {
     const int co = t - 64;
-    for (int p = lane; p < B * Ho * Wo; p += 32) {
+    for (int p = threadIdx.x; p < B * Ho * Wo; p += 256) {
       const int ox = p % Wo, oy = (p / Wo) % Ho, b = p / (Wo * Ho);
       acc += thin_dY(dout, Hp, Wp, py, px, cs, coff, Ho, Wo, b, oy, ox, co);
     }
   }
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) { if (t < 64) dw[t] = acc; else db[t - 64] = acc; }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { if (t < 64) dw[t] = red[0]; else db[t - 64] = red[0]; }
 }
 
 // ---- full-resolution heads: fixed bilinear Deconvolution k32 s16 (+ Crop offset 8), flow loss, mask loss
@@ -1031,11 +1036,17 @@ static int make_wgrad(TrainState *ts, WgradParams &p, int &BN, int B, const Buf 
   p.m_tiles = cdiv(M, 128); p.n_tiles = cdiv(N, BN);
   p.kb_total = B * p.rects_x * p.rects_y;
   const int tiles = KH * KW * p.m_tiles * p.n_tiles;
-  int ks = cdiv(2 * sms, tiles);
-  if (ks > p.kb_total / 2) ks = p.kb_total / 2;
-  if (ks < 1) ks = 1;
+  // K slices: one CTA per SM is resident (190 KB ring), so pick the slice count whose CTA total fills whole waves of `sms`
+  // best (e.g. 25 tiles: 11 slices = 275 CTAs = 2 waves at 93 %, where 12 slices = 300 CTAs would need a third wave)
   const size_t per_slice = (size_t)KH * KW * p.m_tiles * 128 * p.n_tiles * BN;
-  while (ks > 1 && per_slice * ks > ts->wg_partial_elems) --ks;
+  int ks = 1;
+  double best = -1.0;
+  for (int c = 1; c <= 24 && c <= (p.kb_total + 1) / 2 && per_slice * c <= ts->wg_partial_elems; ++c) {
+    const int ctas = tiles * c;
+    if (c > 1 && ctas > 2 * sms) break;  // at most two waves: more slices only add fp32 partial traffic
+    const double eff = (double)ctas / ((double)cdiv(ctas, sms) * sms) - 0.004 * c + (ctas >= sms ? 0.0 : -0.5);
+    if (eff > best + 1e-12) { best = eff; ks = c; }
+  }
   DIM_REQUIRE(per_slice * ks <= ts->wg_partial_elems, "wgrad workspace too small");
   p.kb_per_slice = cdiv(p.kb_total, ks);
   p.kslices = cdiv(p.kb_total, p.kb_per_slice);
@@ -1127,7 +1138,7 @@ static int thin_deconv_bwd(const float *in, int B, int Hi, int Wi, const float *
   DIM_LAUNCH_CHECK();
   DIM_CHECK(cudaEventRecord(ts->ev_fork, st));  // dout is final on st; the weight gradient is off the critical path
   DIM_CHECK(cudaStreamWaitEvent(sw, ts->ev_fork, 0));
-  thin_deconv_wgrad_kernel<<<cdiv(66 * 32, 256), 256, 0, sw>>>(in, B, Hi, Wi, dout.p, dout.Hp, dout.Wp, dout.py, dout.px, dout.C, coff, Ho,
+  thin_deconv_wgrad_kernel<<<66, 256, 0, sw>>>(in, B, Hi, Wi, dout.p, dout.Hp, dout.Wp, dout.py, dout.px, dout.C, coff, Ho,
                                                                 Wo, dw, db);
   DIM_LAUNCH_CHECK();
   return 0;
