@@ -718,12 +718,12 @@ static int alloc_buf(dim_ctx *ctx, Buf &b, int B, int H, int W, int C, int borde
   return dev_alloc(ctx, &b.p, b.per_image() * B, true);
 }
 
-struct TrainCtx;  // forward
-
 static TrainState *&train_of(dim_ctx *ctx) {
   static std::map<dim_ctx *, TrainState *> table;  // contexts are created/destroyed from one host thread at a time
   return table[ctx];
 }
+
+void train_destroy(dim_ctx *ctx);
 
 int train_create(dim_ctx *ctx, int max_points) {
   NetState *ns = ctx->net;
@@ -791,7 +791,12 @@ int train_create(dim_ctx *ctx, int max_points) {
   DIM_CHECK(cudaEventCreateWithFlags(&ts->ev_side, cudaEventDisableTiming));
   for (int i = 0; i < 3; ++i) DIM_CHECK(cudaEventCreateWithFlags(&ts->ev_cls[i], cudaEventDisableTiming));
   for (int i = 0; i < 9; ++i) DIM_CHECK(cudaEventCreate(&ts->ev_phase[i]));
-  return rc;
+  if (rc) {  // an allocation failed: leave no half-built state behind (the buffers themselves are owned by ctx)
+    set_error("dim_train_create: device allocation failed (%d)", rc);
+    train_destroy(ctx);
+    return 12;
+  }
+  return 0;
 }
 
 void train_destroy(dim_ctx *ctx) {
