@@ -316,9 +316,39 @@ def cpu_baseline_leg(sample, weights=None, mesh=None, warm=True):
     for b in range(sample):  # the reference runs one instance at a time (deepim/core/tester.py:83)
         O.refine(weights, [mesh], cls[b:b + 1], imgs[b:b + 1], ini[b:b + 1], K, N_ITER, means.astype(np.float32))
     dt = time.time() - t
-    return {"value": round(sample / dt, 4), "unit": UNIT, "cores": cores, "kind": "port",
+    return {"value": round(sample / dt, 4), "unit": UNIT, "cores": cores, "kind": "port", "cpu_model": cpu_model(),
+            "stages_ms_per_iteration": cpu_stage_split(O, synth, mesh, weights, imgs[:1], ini[:1], K, means),
             "sample": "%d instances x %d iters of the C2 workload, batch 1 (restated reference CPU path: C rasteriser "
                       "+ C zoom + torch-CPU fp32 FlowNetS + float64 se3)" % (sample, N_ITER)}
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def cpu_stage_split(O, synth, mesh, weights, img, pose, K, means):
+    """One iteration of the restated CPU path, stage by stage (the reference logs data / net / calc_gt,
+    deepim/core/tester.py:300-308): render, bbox + zoom, network, SE(3) compose; milliseconds."""
+    t0 = time.time()
+    r = O.render(mesh, pose[0], K, means_rgb=means)
+    t1 = time.time()
+    mr = r["mask"][None, None]
+    mo = O.box_mask(r["bbox"], 480, 640)[None, None]
+    zo, _, zr, zf, _ = O.zoom_mask(mo, mo, mr, pose.astype(np.float32), K)
+    zio, zir = O.zoom_image_with_factor(zf, img, r["image"][None], np.asarray(means, np.float32))
+    t2 = time.time()
+    rot, trans = O.net_forward(weights, zio, zir, zo, zr)
+    t3 = time.time()
+    O.rt_transform(pose[0], rot[0], O.zoom_trans(zf, trans, True)[0])
+    t4 = time.time()
+    return {"render": round((t1 - t0) * 1e3, 2), "zoom": round((t2 - t1) * 1e3, 2), "net": round((t3 - t2) * 1e3, 2),
+            "compose": round((t4 - t3) * 1e3, 3)}
 
 
 def run_reference(args):
@@ -357,7 +387,10 @@ def run_reference(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch_per_step": 1, "n_iter": N_ITER,
                    "note": "MXNet/glumpy cannot be installed offline (BASELINE.md 2): the reference arm is the oracle port"},
-        "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "cpu_model": cpu_model(),
+                         "stages_ms_per_iteration": cpu_stage_split(O, synth, mesh, weights, synth.transform_image(
+                             synth.composite_observed(O.render(mesh, obs[0], K)["bgr"], O.render(mesh, obs[0], K)["mask"], 0))[None],
+                             ini[:1], K, means)},
         "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
