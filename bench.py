@@ -368,19 +368,29 @@ def run_reference(args):
     obs, ini = synth.sample_pose_pairs(max(n, 1), 4242)
     cls = np.zeros(1, np.int32)
 
-    def step(k):
+    def step(k, n_it):
         r = O.render(mesh, obs[k], K)
         img = synth.transform_image(synth.composite_observed(r["bgr"], r["mask"], k))[None]
-        O.refine(weights, [mesh], cls, img, ini[k:k + 1], K, N_ITER, means)
+        O.refine(weights, [mesh], cls, img, ini[k:k + 1], K, n_it, means)
 
+    # bounded sample per step: one instance; if K full 4-iteration refinements would not fit ~3 minutes of CPU time the
+    # step is cut to 2 or 1 iteration(s) of the same instance and counted as that fraction of a refinement
+    step(0, 1)  # page in the libraries / oneDNN primitives (not a timed or counted step)
+    t = time.time()
+    step(0, 1)
+    t_iter = time.time() - t
+    n_it = N_ITER
+    while n_it > 1 and (K_steps + W_steps) * n_it * t_iter > 180.0:
+        n_it //= 2
     for k in range(W_steps):
-        step(k)
+        step(k, n_it)
     t = time.time()
     for k in range(W_steps, n):
-        step(k)
+        step(k, n_it)
     dt = time.time() - t
-    v = K_steps / dt
-    sample = "each step = 1 instance x %d iters of the C2 workload through the restated reference CPU path" % N_ITER
+    v = K_steps * (n_it / float(N_ITER)) / dt
+    sample = ("each step = 1 instance x %d of the %d iterations of the C2 workload through the restated reference CPU path "
+              "(counted as %g refinement)" % (n_it, N_ITER, n_it / float(N_ITER)))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT, "n_gpus": int(args.gpus),
         "steps": K_steps, "warmup": W_steps, "ms_per_step": round(dt / K_steps * 1e3, 2), "higher_is_better": True,
