@@ -55,6 +55,38 @@ def unflatten_params(flat: np.ndarray, like: dict) -> dict:
     return out
 
 
+def tensor_sizes():
+    """[(table index, weight + bias numel)] of the tensors of the flat vector (dim_train_param_info order)."""
+    out = []
+    for i in range(64):
+        nm, wn, bn = C.c_char_p(), C.c_int64(), C.c_int64()
+        if lib.dim_train_param_info(i, C.byref(nm), C.byref(wn), C.byref(bn)) != 0:
+            break
+        out.append((i, wn.value + bn.value))
+    return out
+
+
+def make_buckets(bucket_mb=32.0, sizes=None):
+    """Gradient buckets for the overlapped all-reduce: contiguous [lo, hi) slices of the flat vector cut along tensor
+    boundaries, formed walking the tensors BACKWARDS (the order the backward pass completes them), each at least
+    bucket_mb MB (the last one takes the remainder).  Returns (buckets, first) where first[k] = table index of the
+    lowest tensor in bucket k: the library records event k once every tensor with index >= first[k] is complete."""
+    sizes = tensor_sizes() if sizes is None else sizes
+    n = sum(m for _, m in sizes)
+    limit = int(bucket_mb * (1 << 20) / 4)
+    buckets, first, hi, lo = [], [], n, n
+    for idx, m in reversed(sizes):
+        lo -= m
+        if hi - lo >= limit:
+            buckets.append((lo, hi))
+            first.append(idx)
+            hi = lo
+    if hi > 0:
+        buckets.append((0, hi))
+        first.append(0)
+    return buckets, first
+
+
 def _p(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -71,25 +103,7 @@ class Trainer:
         check(lib.dim_train_load_params(ctx._h, flat.ctypes.data_as(C.c_void_p), self.n, self._stream()))
         torch.cuda.current_stream(ctx.device).synchronize()
         self.grads = torch.zeros(self.n, dtype=torch.float32, device=ctx.device)
-        limit = int(bucket_mb * (1 << 20) / 4)
-        # buckets along tensor boundaries, walking the table backwards (= the order the backward pass produces the
-        # gradients); each bucket remembers the table index of its first tensor for the readiness events
-        names = []
-        for i in range(64):
-            nm, wn, bn = C.c_char_p(), C.c_int64(), C.c_int64()
-            if lib.dim_train_param_info(i, C.byref(nm), C.byref(wn), C.byref(bn)) != 0:
-                break
-            names.append((i, wn.value + bn.value))
-        self.buckets, self.bucket_first, hi, lo = [], [], self.n, self.n
-        for idx, n in reversed(names):
-            lo -= n
-            if hi - lo >= limit:
-                self.buckets.append((lo, hi))
-                self.bucket_first.append(idx)
-                hi = lo
-        if hi > 0:
-            self.buckets.append((0, hi))
-            self.bucket_first.append(0)
+        self.buckets, self.bucket_first = make_buckets(bucket_mb)
         self._events = None
         self._comm_stream = None
 
