@@ -242,6 +242,8 @@ __device__ __forceinline__ float colour_of(unsigned char c, int trunc_u8) {
   return f;
 }
 
+// LIT is a compile-time switch: the unlit instantiation (the refinement loop's renderer) carries none of the shading code
+template <bool LIT>
 __global__ void __launch_bounds__(256) raster_resolve_kernel(RasterParams p) {
   const int b = blockIdx.y;
   const int W4 = p.W >> 2;
@@ -287,7 +289,7 @@ __global__ void __launch_bounds__(256) raster_resolve_kernel(RasterParams p) {
       ty = min(max(ty, 0), m.Th - 1);
       const unsigned char *tp = m.tex + ((size_t)ty * m.Tw + tx) * 3;
       float c0, c1, c2;
-      if (p.lit) {
+      if (LIT) {
         // Lambert shading, same float32 sequence as the CPU checker (see DESIGN.md "lit renderer")
         const int iA = m.faces[3 * f];
         int iB = m.faces[3 * f + 1], iC = m.faces[3 * f + 2];
@@ -429,7 +431,8 @@ int render_launch(dim_ctx *ctx, const int *cls, const float *pose, int B, const 
   DIM_LAUNCH_CHECK();
   raster_coverage_kernel<<<dim3(cdiv(maxF, 128), B), 128, 0, st>>>(p);
   DIM_LAUNCH_CHECK();
-  raster_resolve_kernel<<<dim3(cdiv((ctx->W / 4) * ctx->H, 256), B), 256, 0, st>>>(p);
+  if (p.lit) raster_resolve_kernel<true><<<dim3(cdiv((ctx->W / 4) * ctx->H, 256), B), 256, 0, st>>>(p);
+  else raster_resolve_kernel<false><<<dim3(cdiv((ctx->W / 4) * ctx->H, 256), B), 256, 0, st>>>(p);
   DIM_LAUNCH_CHECK();
   raster_finish_kernel<<<cdiv(B, 128), 128, 0, st>>>(ctx->bbox_ren, out_bbox, B);
   DIM_LAUNCH_CHECK();
