@@ -298,10 +298,9 @@ def cpu_baseline_leg(sample, weights=None, mesh=None, warm=True):
     from deepim_b200 import synth
     from oracle import oracle as O
 
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     mesh = mesh or synth.make_blob()
     weights = weights or synth.make_weights(0)
+    cores = pick_cpu_threads(O, weights)
     K, means = synth.K_LINEMOD, synth.PIXEL_MEANS_RGB
     obs, ini = synth.sample_pose_pairs(sample, 4242)
     imgs = []
@@ -316,10 +315,30 @@ def cpu_baseline_leg(sample, weights=None, mesh=None, warm=True):
     for b in range(sample):  # the reference runs one instance at a time (deepim/core/tester.py:83)
         O.refine(weights, [mesh], cls[b:b + 1], imgs[b:b + 1], ini[b:b + 1], K, N_ITER, means.astype(np.float32))
     dt = time.time() - t
-    return {"value": round(sample / dt, 4), "unit": UNIT, "cores": cores, "kind": "port", "cpu_model": cpu_model(),
+    return {"value": round(sample / dt, 4), "unit": UNIT, "cores": cores, "kind": "port", "cpu_model": cpu_model(), "host_cores": os.cpu_count(),
             "stages_ms_per_iteration": cpu_stage_split(O, synth, mesh, weights, imgs[:1], ini[:1], K, means),
             "sample": "%d instances x %d iters of the C2 workload, batch 1 (restated reference CPU path: C rasteriser "
                       "+ C zoom + torch-CPU fp32 FlowNetS + float64 se3)" % (sample, N_ITER)}
+
+
+def pick_cpu_threads(O, weights):
+    """The restated CPU path is timed with the thread count that serves it best: at batch 1 torch's oneDNN convolutions get
+    SLOWER beyond a few dozen threads on many-core hosts (measured 3.4 s / forward with 128 threads on the GPU box), and the
+    reference arm must not be handicapped.  Tries a few counts on one forward pass and keeps the fastest."""
+    import torch
+    cores = os.cpu_count() or 1
+    z3, z1 = np.zeros((1, 3, 480, 640), np.float32), np.zeros((1, 1, 480, 640), np.float32)
+    best, best_t = cores, None
+    for n in sorted({c for c in (8, 16, 32, 64, cores) if c <= cores}):
+        torch.set_num_threads(n)
+        O.net_forward(weights, z3, z3, z1, z1)  # warm
+        t = time.time()
+        O.net_forward(weights, z3, z3, z1, z1)
+        dt = time.time() - t
+        if best_t is None or dt < best_t:
+            best, best_t = n, dt
+    torch.set_num_threads(best)
+    return best
 
 
 def cpu_model():
@@ -360,9 +379,8 @@ def run_reference(args):
     from deepim_b200 import synth
     from oracle import oracle as O
 
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     mesh, weights = synth.make_blob(), synth.make_weights(0)
+    cores = pick_cpu_threads(O, weights)
     K, means = synth.K_LINEMOD, synth.PIXEL_MEANS_RGB.astype(np.float32)
     n = K_steps + W_steps
     obs, ini = synth.sample_pose_pairs(max(n, 1), 4242)
@@ -397,7 +415,7 @@ def run_reference(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch_per_step": 1, "n_iter": N_ITER,
                    "note": "MXNet/glumpy cannot be installed offline (BASELINE.md 2): the reference arm is the oracle port"},
-        "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "cpu_model": cpu_model(),
+        "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "cpu_model": cpu_model(), "host_cores": os.cpu_count(),
                          "stages_ms_per_iteration": cpu_stage_split(O, synth, mesh, weights, synth.transform_image(
                              synth.composite_observed(O.render(mesh, obs[0], K)["bgr"], O.render(mesh, obs[0], K)["mask"], 0))[None],
                              ini[:1], K, means)},
