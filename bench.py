@@ -170,8 +170,8 @@ def run_b200(args):
             last = refiner.result(t)
         return last
 
-    # ---------------- device-resident arm (`value`): inputs already in HBM, two independent batches in
-    # flight on two streams (instances are independent, so consecutive steps overlap their tails)
+    # ---------------- device-resident arm (`value`): inputs already in HBM, `--slots` independent batches in
+    # flight on as many streams (instances are independent, so consecutive steps overlap their tails)
     streams = [s_["stream"] for s_ in refiner.slots]
     ctxs = [s_["ctx"] for s_ in refiner.slots]
 
@@ -278,7 +278,7 @@ def run_b200(args):
             "single_stream": {"ms_per_step": round(ms_single / K_steps, 4),
                               "value": round(B * K_steps / (ms_single / 1e3), 2),
                               "note": "roofline / stage times come from this pass (one batch at a time, CUDA events "
-                                      "between stages); `value` runs two independent batches on two streams"},
+                                      "between stages); `value` runs %d independent batches on %d streams" % (args.slots, args.slots)},
             "e2e_roofline_frac": round(value / world / (peaks["tflops"] * 1e12 / (conv_flops_per_instance_iter() * N_ITER)), 4),
             "add_m": {"init": round(add_init, 5), "final": round(add_final, 5), "note": "random-init weights: not expected to improve"},
         }
