@@ -149,20 +149,21 @@ __global__ void __launch_bounds__(256) lrelu_mask_inplace_kernel(__nv_bfloat16 *
 }
 
 // ---- thin 3x3 / pad 1 convolutions with <= 2 output channels (Convolution1/2/3, mask_conv3): CUDA cores
-// forward: one warp per output pixel, lanes stride over input channels
+// forward: one 128-thread block per output pixel; the 4 warps split the input channels (warp w takes ci = w*32 + lane,
+// + 128, ...) so the dependent-FMA chain per lane is 4x shorter than with one warp per pixel; fixed-order combine
 template <int CO>
-__global__ void __launch_bounds__(256) thin_conv_fwd_kernel(const __nv_bfloat16 *x, int Hp, int Wp, int cs, int Cin, int B, int H,
+__global__ void __launch_bounds__(128) thin_conv_fwd_kernel(const __nv_bfloat16 *x, int Hp, int Wp, int cs, int Cin, int B, int H,
                                                             int W, const float *w, const float *bias, float *out) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= B * H * W) return;
-  const int xx = warp % W, yy = (warp / W) % H, b = warp / (W * H);
+  __shared__ float red[4][CO];
+  const int pix = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int xx = pix % W, yy = (pix / W) % H, b = pix / (W * H);
   float acc[CO];
 #pragma unroll
   for (int co = 0; co < CO; ++co) acc[co] = 0.f;
   for (int ky = 0; ky < 3; ++ky)
     for (int kx = 0; kx < 3; ++kx) {
       const __nv_bfloat16 *px = x + (((size_t)b * Hp + yy + ky) * Wp + xx + kx) * cs;  // border 1 == pad 1
-      for (int ci = lane; ci < Cin; ci += 32) {
+      for (int ci = threadIdx.x; ci < Cin; ci += 128) {
         const float v = __bfloat162float(px[ci]);
 #pragma unroll
         for (int co = 0; co < CO; ++co) acc[co] = fmaf(v, w[((ky * 3 + kx) * CO + co) * Cin + ci], acc[co]);  // w = [tap][co][ci]
@@ -172,8 +173,10 @@ __global__ void __launch_bounds__(256) thin_conv_fwd_kernel(const __nv_bfloat16 
   for (int co = 0; co < CO; ++co) {
     float v = acc[co];
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) out[(size_t)warp * CO + co] = v + bias[co];
+    if (lane == 0) red[warp][co] = v;
   }
+  __syncthreads();
+  if (threadIdx.x < CO) out[(size_t)pix * CO + threadIdx.x] = (((red[0][threadIdx.x] + red[1][threadIdx.x]) + red[2][threadIdx.x]) + red[3][threadIdx.x]) + bias[threadIdx.x];
 }
 
 // weight gradient, stage 1: thread (ci, tap) x pixel chunk blockIdx.y -> part[chunk][co][ci*9 + tap]
@@ -1318,22 +1321,26 @@ int train_forward_backward(dim_ctx *ctx, const TrainIO &io, cudaStream_t st) {
   DIM_CHECK(cudaEventRecord(ts->ev_phase[1], st));
   const Buf a10 = act_buf(ns, 10), a8 = act_buf(ns, 8), a6 = act_buf(ns, 6);
   if (int rc = copy_interior(a10, ts->act10b, 0, B, 1024, st)) return rc;
-  LAUNCH1D(thin_conv_fwd_kernel<2>, (size_t)B * h6 * w6 * 32, st, ts->act10b.p, ts->act10b.Hp, ts->act10b.Wp, 1024, 1024, B, h6, w6,
+  thin_conv_fwd_kernel<2><<<B * h6 * w6, 128, 0, st>>>(ts->act10b.p, ts->act10b.Hp, ts->act10b.Wp, 1024, 1024, B, h6, w6,
            ts->thin_w[0], M + ts->off[P_CONV1D].b, ts->flow6);
+  DIM_LAUNCH_CHECK();
   if (int rc = run_classes(ctx, ts, tm.deconv5_fwd, tm.g_deconv5_fwd, 4, B, st)) return rc;
   if (int rc = copy_interior(a8, ts->cat2, 0, B, 512, st)) return rc;
   LAUNCH1D(thin_deconv_fwd_kernel, (size_t)B * h5 * w5 * 2, st, ts->flow6, B, h6, w6, M + ts->off[P_UP65].w, M + ts->off[P_UP65].b,
            ts->cat2.p, ts->cat2.Hp, ts->cat2.Wp, 1, 1, 1088, 1024, h5, w5);
-  LAUNCH1D(thin_conv_fwd_kernel<2>, (size_t)B * h5 * w5 * 32, st, ts->cat2.p, ts->cat2.Hp, ts->cat2.Wp, 1088, 1026, B, h5, w5,
+  thin_conv_fwd_kernel<2><<<B * h5 * w5, 128, 0, st>>>(ts->cat2.p, ts->cat2.Hp, ts->cat2.Wp, 1088, 1026, B, h5, w5,
            ts->thin_w[1], M + ts->off[P_CONV2D].b, ts->flow5);
+  DIM_LAUNCH_CHECK();
   if (int rc = run_classes(ctx, ts, tm.deconv4_fwd, tm.g_deconv4_fwd, 4, B, st)) return rc;
   if (int rc = copy_interior(a6, ts->cat3, 0, B, 512, st)) return rc;
   LAUNCH1D(thin_deconv_fwd_kernel, (size_t)B * h4 * w4 * 2, st, ts->flow5, B, h5, w5, M + ts->off[P_UP54].w, M + ts->off[P_UP54].b,
            ts->cat3.p, ts->cat3.Hp, ts->cat3.Wp, 1, 1, 832, 768, h4, w4);
-  LAUNCH1D(thin_conv_fwd_kernel<2>, (size_t)B * h4 * w4 * 32, st, ts->cat3.p, ts->cat3.Hp, ts->cat3.Wp, 832, 770, B, h4, w4,
+  thin_conv_fwd_kernel<2><<<B * h4 * w4, 128, 0, st>>>(ts->cat3.p, ts->cat3.Hp, ts->cat3.Wp, 832, 770, B, h4, w4,
            ts->thin_w[2], M + ts->off[P_CONV3D].b, ts->flow4);
-  LAUNCH1D(thin_conv_fwd_kernel<1>, (size_t)B * h4 * w4 * 32, st, ts->cat3.p, ts->cat3.Hp, ts->cat3.Wp, 832, 770, B, h4, w4,
+  DIM_LAUNCH_CHECK();
+  thin_conv_fwd_kernel<1><<<B * h4 * w4, 128, 0, st>>>(ts->cat3.p, ts->cat3.Hp, ts->cat3.Wp, 832, 770, B, h4, w4,
            ts->thin_w[3], M + ts->off[P_MASK3].b, ts->mask4);
+  DIM_LAUNCH_CHECK();
   DIM_CHECK(cudaEventRecord(ts->ev_phase[2], st));
   fullres_loss_kernel<<<LOSS_BLOCKS, 256, 0, st>>>(ts->flow4, ts->mask4, h4, w4, M + ts->off[P_UPS].w, M + ts->off[P_MUPS].w, io.zflow,
                                                    io.zfw, io.zmask_gt, B, H, W, 20.0f, gs_flow, gs_mask, io.flow_est, io.mask_prob,
