@@ -553,6 +553,7 @@ int net_forward(dim_ctx *ctx, int B, int precision, const float *zoom_factor, fl
     it = ns->maps.emplace(B, tm).first;
   }
   const TensorMaps &tm = it->second;
+  if (ns->repack_done) DIM_CHECK(cudaStreamWaitEvent(st, ns->repack_done, 0));
   const bool s3 = precision == DIM_PREC_BF16X3;
   if (s3 && ns->lo_stale)
     if (int rc = train_refresh_lo(ctx, st)) return rc;

@@ -51,6 +51,8 @@ struct NetState {
   float *tail_ws = nullptr;  // K-slice partials of the tail tiles: [<= 2*SMs slots][128][256] fp32
   bool loaded = false, net_ok = false;
   float *save_h6 = nullptr, *save_h7 = nullptr;
+  cudaEvent_t repack_done = nullptr;  // training: the operand packs are refreshed on an internal stream after an update;
+                                      // every consumer (net_forward) orders itself behind this event
   bool lo_stale = false;  // training updated the weights without refreshing the bf16 'lo' halves (bf16x3 mode refreshes lazily)  // training: fc6 / fc7 activations kept for the backward pass ([B][256])
   std::map<int, TensorMaps> maps;  // per batch size
   int max_batch = 0, num_sms = 148;

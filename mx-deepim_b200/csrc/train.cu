@@ -97,7 +97,7 @@ struct TrainState {
   // gradients next to the data-gradient chain (both only read the dZ buffers)
   cudaStream_t side[4] = {};
   cudaEvent_t ev_phase[9] = {};  // phase boundaries of the last step on the caller's stream (dim_train_debug_phases)
-  cudaEvent_t ev_fork = nullptr, ev_cls[3] = {}, ev_side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_cls[3] = {}, ev_side = nullptr, ev_repack = nullptr;
 };
 
 static constexpr int LOSS_BLOCKS = 1024;
@@ -792,6 +792,7 @@ int train_create(dim_ctx *ctx, int max_points) {
   for (int i = 0; i < 4; ++i) DIM_CHECK(cudaStreamCreateWithFlags(&ts->side[i], cudaStreamNonBlocking));
   DIM_CHECK(cudaEventCreateWithFlags(&ts->ev_fork, cudaEventDisableTiming));
   DIM_CHECK(cudaEventCreateWithFlags(&ts->ev_side, cudaEventDisableTiming));
+  DIM_CHECK(cudaEventCreateWithFlags(&ts->ev_repack, cudaEventDisableTiming));
   for (int i = 0; i < 3; ++i) DIM_CHECK(cudaEventCreateWithFlags(&ts->ev_cls[i], cudaEventDisableTiming));
   for (int i = 0; i < 9; ++i) DIM_CHECK(cudaEventCreate(&ts->ev_phase[i]));
   if (rc) {  // an allocation failed: leave no half-built state behind (the buffers themselves are owned by ctx)
@@ -808,6 +809,7 @@ void train_destroy(dim_ctx *ctx) {
     for (int i = 0; i < 4; ++i) if (ts->side[i]) cudaStreamDestroy(ts->side[i]);
     if (ts->ev_fork) cudaEventDestroy(ts->ev_fork);
     if (ts->ev_side) cudaEventDestroy(ts->ev_side);
+    if (ts->ev_repack) { ctx->net->repack_done = nullptr; cudaEventDestroy(ts->ev_repack); }
     for (int i = 0; i < 3; ++i) if (ts->ev_cls[i]) cudaEventDestroy(ts->ev_cls[i]);
     for (int i = 0; i < 9; ++i) if (ts->ev_phase[i]) cudaEventDestroy(ts->ev_phase[i]);
   }
@@ -1458,8 +1460,17 @@ int train_sgd_update(dim_ctx *ctx, const float *grads, float lr, float momentum,
     segs.end[2 * i + 1] = ts->off[i].b + ts->off[i].bn;
   }
   const size_t n = ts->off[21].b + ts->off[21].bn;  // the two bilinear upsampling kernels behind it are frozen (lr_mult 0)
+  if (ctx->net->repack_done) DIM_CHECK(cudaStreamWaitEvent(st, ctx->net->repack_done, 0));  // a previous refresh still reads the master
   LAUNCH1D(sgd_kernel, n, st, ts->master, ts->mom, grads, n, segs, lr, momentum, wd, rescale);
-  return repack_all(ctx, st, false);
+  // The bf16 operand packs are refreshed on the internal stream, so the caller's stream is free for the work that does
+  // not need them (re-render + labels of the next inner iteration, the zoom front); net_forward waits for `repack_done`.
+  cudaStream_t sw = ts->side[3];
+  DIM_CHECK(cudaEventRecord(ts->ev_fork, st));
+  DIM_CHECK(cudaStreamWaitEvent(sw, ts->ev_fork, 0));
+  if (int rc = repack_all(ctx, sw, false)) return rc;
+  DIM_CHECK(cudaEventRecord(ts->ev_repack, sw));
+  ctx->net->repack_done = ts->ev_repack;
+  return 0;
 }
 
 // test / debugging hook: copy an intermediate to the host.  id: 0 flow6, 1 flow5, 2 flow4, 3 mask4 (fp32);
