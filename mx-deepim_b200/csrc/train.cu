@@ -1082,10 +1082,20 @@ static int make_wgrad(TrainState *ts, WgradParams &p, int &BN, int B, const Buf 
 
 static int run_wgrad(const WgradParams &p, int BN, int kind, int D0, int D1, int k, float *grad, cudaStream_t st) {
   int rc;
-  if (BN == 256) rc = launch_wgrad<256, 4>(p, st);
-  else if (BN == 128) rc = launch_wgrad<128, 6>(p, st);
-  else if (BN == 64) rc = launch_wgrad<64, 8>(p, st);
-  else rc = launch_wgrad<32, 8>(p, st);
+  // Two resident CTAs per SM with half-depth rings (the same bytes in flight per SM): the barrier-init / TMEM-alloc
+  // prologue and the fp32 epilogue of one CTA overlap the K loop of the other.  DIM_WGRAD_OCC2=0: one CTA, deep ring.
+  static const bool occ2 = [] { const char *e = getenv("DIM_WGRAD_OCC2"); return !(e && e[0] == '0'); }();
+  if (occ2) {
+    if (BN == 256) rc = launch_wgrad<256, 2>(p, st);
+    else if (BN == 128) rc = launch_wgrad<128, 3>(p, st);
+    else if (BN == 64) rc = launch_wgrad<64, 4>(p, st);
+    else rc = launch_wgrad<32, 4>(p, st);
+  } else {
+    if (BN == 256) rc = launch_wgrad<256, 4>(p, st);
+    else if (BN == 128) rc = launch_wgrad<128, 6>(p, st);
+    else if (BN == 64) rc = launch_wgrad<64, 8>(p, st);
+    else rc = launch_wgrad<32, 8>(p, st);
+  }
   if (rc) return rc;
   const size_t total = (size_t)p.KH * p.KW * p.m_tiles * 128 * p.n_tiles * BN;
   wgrad_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p.partial, p.kslices, p.KH * p.KW, p.m_tiles * 128,
