@@ -97,12 +97,12 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_inputs(ctx, synth, mesh, B, n_sets, seed, dev, torch):
+def make_inputs(ctx, synth, mesh, B, n_sets, seed, dev, torch, z_mean=0.8):
     """n_sets rotating input sets so consecutive steps never reuse L2-resident inputs."""
     K, means = synth.K_LINEMOD, synth.PIXEL_MEANS_RGB
     sets = []
     for s in range(n_sets):
-        obs, ini = synth.sample_pose_pairs(B, seed * 100 + s)
+        obs, ini = synth.sample_pose_pairs(B, seed * 100 + s, z_mean=z_mean)
         cls = torch.zeros(B, dtype=torch.int32, device=dev)
         r = ctx.render(cls, torch.from_numpy(obs.astype(np.float32)).to(dev), K, want=("bgr", "mask"))
         g = torch.Generator(device=dev); g.manual_seed(seed * 100 + s)
@@ -142,12 +142,18 @@ def run_b200(args):
     means = synth.PIXEL_MEANS_RGB
 
     from deepim_b200.refiner import PoseRefiner
-    mesh = synth.make_blob()  # C2
+    workload = WORKLOAD
+    if args.config == "c5":  # BASELINE.json configs[4]: rasteriser stress (secondary line; the headline stays C2)
+        mesh = synth.make_blob(158, 316, diameter=0.25, tex_size=512, seed=4, name="stress")
+        workload = ("C5: synthetic %d-vert / %d-tri mesh, diameter 0.25 m at 0.6 m (large on-screen footprint), 4 iters, batch=%d "
+                    "per GPU, FlowNetS random-init" % (len(mesh.verts), len(mesh.faces), B))
+    else:
+        mesh = synth.make_blob()  # C2
     weights = synth.make_weights(0)
     refiner = PoseRefiner([mesh], weights, K, device=local_rank, max_batch=B, n_iter=N_ITER, pixel_means_rgb=means,
                           precision=args.precision, n_slots=args.slots)
     ctx = refiner.ctx
-    sets = make_inputs(ctx, synth, mesh, B, 3, 1000 + rank, dev, torch)
+    sets = make_inputs(ctx, synth, mesh, B, 3, 1000 + rank, dev, torch, z_mean=0.6 if args.config == "c5" else 0.8)
 
     def barrier():
         if dist is not None:
@@ -261,7 +267,7 @@ def run_b200(args):
             "warmup": max(W_steps, 3), "ms_per_step": round(ms_total / K_steps, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if prec == capi.PREC_BF16 else "bf16x3",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "n_iter": N_ITER, "precision": args.precision, "batches_in_flight": args.slots,
+            "config": {"workload": workload, "batch_per_gpu": B, "n_iter": N_ITER, "precision": args.precision, "batches_in_flight": args.slots,
                        "l2": "per-step working set (~1.6 GB of activations + 90 MB weights + 59 MB inputs) exceeds the "
                              "126 MB L2; 3 rotating input sets"},
             "clocks": clocks,
@@ -433,6 +439,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--slots", type=int, default=4, help="independent batches in flight per GPU (streams)")
+    ap.add_argument("--config", default="c2", choices=["c2", "c5"], help="c2 = headline config (default); c5 = 50k-vert rasteriser stress mesh")
     ap.add_argument("--workload", default="refine", choices=["refine", "train"],
                     help="refine = the headline metric (default); train = config C4 training step (tools/train_bench.py)")
     args = ap.parse_args()
