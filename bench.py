@@ -97,13 +97,13 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_inputs(ctx, synth, mesh, B, n_sets, seed, dev, torch, z_mean=0.8):
+def make_inputs(ctx, synth, mesh, B, n_sets, seed, dev, torch, z_mean=0.8, n_classes=1):
     """n_sets rotating input sets so consecutive steps never reuse L2-resident inputs."""
     K, means = synth.K_LINEMOD, synth.PIXEL_MEANS_RGB
     sets = []
     for s in range(n_sets):
         obs, ini = synth.sample_pose_pairs(B, seed * 100 + s, z_mean=z_mean)
-        cls = torch.zeros(B, dtype=torch.int32, device=dev)
+        cls = (torch.arange(B, dtype=torch.int32, device=dev) % n_classes).contiguous()  # round-robin over the classes
         r = ctx.render(cls, torch.from_numpy(obs.astype(np.float32)).to(dev), K, want=("bgr", "mask"))
         g = torch.Generator(device=dev); g.manual_seed(seed * 100 + s)
         bg = torch.randint(0, 256, r["bgr"].shape, generator=g, device=dev, dtype=torch.int32).to(torch.uint8)
@@ -112,7 +112,7 @@ def make_inputs(ctx, synth, mesh, B, n_sets, seed, dev, torch, z_mean=0.8):
         sets.append({
             "img_dev": ctx.transform_image_u8(u8, means),                     # resident f32 blob for `value`
             "cls_dev": cls, "pose_dev": torch.from_numpy(ini).to(dev),
-            "u8_host": u8.cpu().pin_memory(), "cls_host": torch.zeros(B, dtype=torch.int32).pin_memory(),
+            "u8_host": u8.cpu().pin_memory(), "cls_host": cls.cpu().pin_memory(),
             "pose_host": torch.from_numpy(ini).pin_memory(), "obs": obs, "ini": ini,
         })
     torch.cuda.synchronize()
@@ -147,13 +147,21 @@ def run_b200(args):
         mesh = synth.make_blob(158, 316, diameter=0.25, tex_size=512, seed=4, name="stress")
         workload = ("C5: synthetic %d-vert / %d-tri mesh, diameter 0.25 m at 0.6 m (large on-screen footprint), 4 iters, batch=%d "
                     "per GPU, FlowNetS random-init" % (len(mesh.verts), len(mesh.faces), B))
+    elif args.config == "c3":  # BASELINE.json configs[2]: 13 LINEMOD-scale meshes, instances round-robin over the classes
+        meshes = synth.make_linemod_like_set(13)
+        mesh = meshes[0]
+        workload = ("C3: 13 synthetic LINEMOD-scale meshes (%d-%d verts), instances round-robin over classes, 4 iters, batch=%d per "
+                    "GPU, FlowNetS random-init" % (min(len(m.verts) for m in meshes), max(len(m.verts) for m in meshes), B))
     else:
         mesh = synth.make_blob()  # C2
+    if args.config != "c3":
+        meshes = [mesh]
     weights = synth.make_weights(0)
-    refiner = PoseRefiner([mesh], weights, K, device=local_rank, max_batch=B, n_iter=N_ITER, pixel_means_rgb=means,
+    refiner = PoseRefiner(meshes, weights, K, device=local_rank, max_batch=B, n_iter=N_ITER, pixel_means_rgb=means,
                           precision=args.precision, n_slots=args.slots)
     ctx = refiner.ctx
-    sets = make_inputs(ctx, synth, mesh, B, 3, 1000 + rank, dev, torch, z_mean=0.6 if args.config == "c5" else 0.8)
+    sets = make_inputs(ctx, synth, mesh, B, 3, 1000 + rank, dev, torch, z_mean=0.6 if args.config == "c5" else 0.8,
+                       n_classes=len(meshes))
 
     def barrier():
         if dist is not None:
@@ -257,11 +265,11 @@ def run_b200(args):
             traffic = json.load(open(tpath)).get("conv_igemm_bytes_per_launch")
         # ADD(-S) sanity of the last step against the observed pose (blob is asymmetric -> ADD)
         s_last = sets[(K_steps - 1) % len(sets)]
-        pts = mesh.verts.astype(np.float64)
-        def add(p, q):
+        def add(p, q, b):
+            pts = meshes[b % len(meshes)].verts.astype(np.float64)
             return float(np.linalg.norm((pts @ p[:, :3].T + p[:, 3]) - (pts @ q[:, :3].T + q[:, 3]), axis=1).mean())
-        add_init = float(np.mean([add(s_last["ini"][b], s_last["obs"][b]) for b in range(B)]))
-        add_final = float(np.mean([add(poses_last[b], s_last["obs"][b]) for b in range(B)]))
+        add_init = float(np.mean([add(s_last["ini"][b], s_last["obs"][b], b) for b in range(B)]))
+        add_final = float(np.mean([add(poses_last[b], s_last["obs"][b], b) for b in range(B)]))
         result = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K_steps,
             "warmup": max(W_steps, 3), "ms_per_step": round(ms_total / K_steps, 4), "higher_is_better": True,
@@ -439,7 +447,8 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--slots", type=int, default=4, help="independent batches in flight per GPU (streams)")
-    ap.add_argument("--config", default="c2", choices=["c2", "c5"], help="c2 = headline config (default); c5 = 50k-vert rasteriser stress mesh")
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c5"],
+                    help="c2 = headline config (default); c3 = 13 meshes round-robin; c5 = 50k-vert rasteriser stress mesh")
     ap.add_argument("--workload", default="refine", choices=["refine", "train"],
                     help="refine = the headline metric (default); train = config C4 training step (tools/train_bench.py)")
     args = ap.parse_args()
