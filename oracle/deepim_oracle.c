@@ -16,8 +16,10 @@
  *   - zoom bbox / zoom factor : restated from deepim/operator_py/zoom_mask.py (numpy part is
  *                               pinned by replaying the reference's numpy expressions in
  *                               tests/golden/make_golden.py)
- *   - GridGenerator/BilinearSampler, OpenGL rasterisation: third-party (MXNet, glumpy/GL,
+ *   - GridGenerator/BilinearSampler, OpenGL rasterisation (unlit orc_render and Lambert-lit
+ *     orc_render_lit, render_py_light_modelnet_multi.py:36-79): third-party (MXNet, glumpy/GL,
  *     not vendored) -> PARITY UNPINNED; the formulas below define the contract.
+ *   - training graph / gradients / SGD: oracle/train_oracle.py (torch-CPU fp32; unpinned, see its header)
  *
  * Build: gcc -O2 -ffp-contract=off -fno-fast-math -shared -fPIC (oracle/Makefile).
  * -ffp-contract=off matters: the CUDA kernels are compiled with -fmad=false so that the
