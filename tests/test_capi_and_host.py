@@ -184,3 +184,24 @@ def test_trainer_flat_parameter_layout():
             f6 = flat[off:off + n].reshape(256, 80, 1024)
             assert f6[5, 17, 300] == w["fc6_weight"][5, 300 * 80 + 17]
         off += n
+
+
+def test_simpson_rule_and_obj_parser(tmp_path):
+    """pose_eval.simpson = scipy.integrate.simps(even='avg') of the reference's era (LM6D_REFINE.py:462-466 integrates 1000
+    samples); the OBJ reader handles vn records, negative indices and polygon fans (glumpy.objload conventions)."""
+    from deepim_b200 import lm6d_io
+    from deepim_b200.pose_eval import simpson
+    x = np.linspace(0.0, 1.0, 1001)
+    assert abs(simpson(x ** 3, x[1] - x[0]) - 0.25) < 1e-12          # odd sample count: exact for cubics
+    y = np.linspace(0.0, 0.0999, 1000) ** 2                          # the evaluator's grid: 1000 samples, dx = 1e-4
+    first = simpson(y[:-1], 1e-4) + 0.5e-4 * (y[-1] + y[-2])
+    last = simpson(y[1:], 1e-4) + 0.5e-4 * (y[0] + y[1])
+    assert abs(simpson(y, 1e-4) - 0.5 * (first + last)) < 1e-18 and abs(simpson(y, 1e-4) - 0.0999 ** 3 / 3) < 1e-9
+    obj = tmp_path / "m.obj"
+    obj.write_text("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvt 0 0\nvt 1 0\nvt 1 1\nvt 0 1\nvn 0 0 1\n"
+                   "f 1/1/1 2/2/1 3/3/1 4/4/1\nf -4/-4/-1 -3/-3/-1 -2/-2/-1\n")
+    m = lm6d_io.load_textured_obj(str(obj))
+    assert m.faces.shape == (3, 3) and m.verts.shape == (9, 3)       # quad -> 2 triangles (fan) + 1 triangle, un-rolled
+    assert np.array_equal(m.verts[3:6], np.array([[0, 0, 0], [1, 1, 0], [0, 1, 0]], np.float32))
+    assert np.array_equal(m.verts[6:9], m.verts[[0, 1, 2]]) and np.array_equal(m.normals, np.tile([[0, 0, 1]], (9, 1)))
+    assert np.array_equal(m.uvs[2], [1, 1])
