@@ -68,6 +68,10 @@ static void build_geometry(NetState *ns, int H, int W) {
     g.kblocks = g.KH * g.KW * (g.Ceff / g.BLOCK_K);
     g.occ = (i == 0) ? 2 : 1;
     g.pair = (i >= 1 && use_pair_kernel()) ? 1 : 0;
+    // opt-in experiment for the next round (not yet measured): conv2 only on the CTA-pair kernel with a 3-stage ring so that
+    // two pairs are resident per SM pair (conv2 is bound by L2 -> SM operand traffic; a pair fetches each weight tile once)
+    static const bool conv2_pair = [] { const char *e = getenv("DIM_CONV2_PAIR"); return e && e[0] == '1'; }();
+    if (i == 1 && conv2_pair) g.pair = 2;
     h = g.Ho; w = g.Wo;
   }
 }
@@ -583,7 +587,9 @@ int net_forward(dim_ctx *ctx, int B, int precision, const float *zoom_factor, fl
     else if (g.pair) {
       const int m_tiles = cdiv(B * g.Hq, g.BH) * g.n_col_tiles;
       const int pair_tiles = cdiv(m_tiles, 2) * n_tiles * kp.ksplit;
-      if (g.BLOCK_N == 128)
+      if (g.BLOCK_N == 128 && g.pair == 2 && !s3)
+        rc = launch_pair<128, 3, false>(kp, pair_tiles, n_tiles, 2 * sms, st);
+      else if (g.BLOCK_N == 128)
         rc = s3 ? launch_pair<128, 4, true>(kp, pair_tiles, n_tiles, sms, st) : launch_pair<128, 8, false>(kp, pair_tiles, n_tiles, sms, st);
       else
         rc = s3 ? launch_pair<256, 3, true>(kp, pair_tiles, n_tiles, sms, st) : launch_pair<256, 6, false>(kp, pair_tiles, n_tiles, sms, st);
