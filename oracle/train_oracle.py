@@ -53,21 +53,40 @@ def _t(a):
     return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
 
 
-def graph(weights, zin, labels, requires_grad=True, num_threads=None):
+def graph(weights, zin, labels, requires_grad=True, num_threads=None, emulate_bf16=False):
     """The network part of the train symbol on already-zoomed inputs.
     zin: zoom_image_observed, zoom_image_rendered (B,3,H,W), zoom_mask_observed, zoom_mask_rendered (B,1,H,W)
     labels: zoom_factor (B,4), zoom_flow (B,2,H,W), zoom_flow_weights (B,2,H,W), zoom_mask_gt_observed (B,1,H,W),
             src_pose (B,3,4), point_cloud_model / point_cloud_weights / point_cloud_observed (B,3,N)
-    Returns (outputs dict of numpy arrays, grads dict name -> numpy) ; grads is {} when requires_grad=False."""
+    Returns (outputs dict of numpy arrays, grads dict name -> numpy) ; grads is {} when requires_grad=False.
+    emulate_bf16=True rounds what the device step keeps in bf16 -- conv / deconv operand weights, every stored activation
+    and every activation gradient -- to bf16 (fp32 accumulation everywhere, fp32 master weights): the resulting deviation
+    from the fp32 run is the intrinsic cost of that storage format and calibrates the tolerances of tests/test_gpu_train.py."""
     import torch
     import torch.nn.functional as F
 
     if num_threads:
         torch.set_num_threads(num_threads)
     P = {k: _t(v).requires_grad_(requires_grad and k not in FROZEN) for k, v in weights.items()}
-    lrelu = lambda x: F.leaky_relu(x, 0.1)
-    x = torch.cat([_t(zin["zoom_image_observed"]) / 255.0, _t(zin["zoom_image_rendered"]) / 255.0,
-                   _t(zin["zoom_mask_observed"]), _t(zin["zoom_mask_rendered"])], dim=1)
+    rb = (lambda t: t.bfloat16().float()) if emulate_bf16 else (lambda t: t)
+
+    def store(t):  # an activation as the device stores it (+ its gradient on the way back)
+        if not emulate_bf16:
+            return t
+        t = rb(t)
+        if t.requires_grad:
+            t.register_hook(lambda g: g.bfloat16().float())
+        return t
+
+    tc = ("flow_conv1", "conv2", "conv3", "conv3_1", "conv4", "conv4_1", "conv5", "conv5_1", "conv6", "conv6_1", "fc6", "deconv5", "deconv4")
+    if emulate_bf16:  # tensor-core operands are bf16; the thin 2-channel heads, fc7, rot, trans read the fp32 master
+        P = {k: (rb(v) if k.endswith("_weight") and k[:-7] in tc else v) for k, v in P.items()}
+        for k, v in P.items():
+            if k.endswith("_weight") and k[:-7] in tc and requires_grad:
+                v.retain_grad()
+    lrelu = lambda x: store(F.leaky_relu(x, 0.1))
+    x = rb(torch.cat([_t(zin["zoom_image_observed"]) / 255.0, _t(zin["zoom_image_rendered"]) / 255.0,
+                      _t(zin["zoom_mask_observed"]), _t(zin["zoom_mask_rendered"])], dim=1))
     feat, pre = {}, {}
     for name, s, p in ENC:
         z = F.conv2d(x, P[name + "_weight"], P[name + "_bias"], stride=s, padding=p)
@@ -77,20 +96,20 @@ def graph(weights, zin, labels, requires_grad=True, num_threads=None):
         x = lrelu(z)
         feat[name] = x
     r10, r8, r6 = feat["conv6_1"], feat["conv5_1"], feat["conv4_1"]
-    h = lrelu(F.linear(r10.flatten(1), P["fc6_weight"], P["fc6_bias"]))
-    h = lrelu(F.linear(h, P["fc7_weight"], P["fc7_bias"]))
+    h = F.leaky_relu(F.linear(r10.flatten(1), P["fc6_weight"], P["fc6_bias"]), 0.1)   # fc activations stay fp32 on the device
+    h = F.leaky_relu(F.linear(h, P["fc7_weight"], P["fc7_bias"]), 0.1)
     rot = F.linear(h, P["rot_weight"], P["rot_bias"])
     ztrans = F.linear(h, P["trans_weight"], P["trans_bias"])
     # decoder (symbol:121-165)
     flow6 = F.conv2d(r10, P["Convolution1_weight"], P["Convolution1_bias"], padding=1)
     d5 = F.conv_transpose2d(r10, P["deconv5_weight"], P["deconv5_bias"], stride=2)[:, :, 1:1 + r8.shape[2], 1:1 + r8.shape[3]]
     up65 = F.conv_transpose2d(flow6, P["upsample_flow6to5_weight"], P["upsample_flow6to5_bias"], stride=2)
-    up65 = up65[:, :, 1:1 + r8.shape[2], 1:1 + r8.shape[3]]
+    up65 = store(up65[:, :, 1:1 + r8.shape[2], 1:1 + r8.shape[3]])
     cat2 = torch.cat([r8, lrelu(d5), up65], dim=1)
     flow5 = F.conv2d(cat2, P["Convolution2_weight"], P["Convolution2_bias"], padding=1)
     d4 = F.conv_transpose2d(cat2, P["deconv4_weight"], P["deconv4_bias"], stride=2)[:, :, 1:1 + r6.shape[2], 1:1 + r6.shape[3]]
     up54 = F.conv_transpose2d(flow5, P["upsample_flow5to4_weight"], P["upsample_flow5to4_bias"], stride=2)
-    up54 = up54[:, :, 1:1 + r6.shape[2], 1:1 + r6.shape[3]]
+    up54 = store(up54[:, :, 1:1 + r6.shape[2], 1:1 + r6.shape[3]])
     cat3 = torch.cat([r6, lrelu(d4), up54], dim=1)
     # losses (symbol:171-365)
     Himg, Wimg = zin["zoom_image_observed"].shape[-2:]
