@@ -280,9 +280,11 @@ def flow(depth_src, depth_tgt, KT, Kinv):
 
 # --------------------------------------------------------------------------------------------- net
 def net_forward(weights, zoom_image_observed, zoom_image_rendered, zoom_mask_observed, zoom_mask_rendered,
-                num_threads=None, return_features=False):
+                num_threads=None, return_features=False, emulate_bf16=False):
     """FlowNetS encoder + fc + heads, torch-CPU fp32 (deepIM_flownet.py:53-116, 716-717).
-    Returns rot (B,4) raw quaternion, trans (B,3) zoomed translation."""
+    Returns rot (B,4) raw quaternion, trans (B,3) zoomed translation.
+    emulate_bf16=True rounds what the device's throughput mode (DIM_PREC_BF16) stores in bf16 -- the conv / fc6 operand
+    weights and every conv activation -- keeping fp32 accumulation: calibrates that mode's tolerance (tests)."""
     import torch
     import torch.nn.functional as F
 
@@ -290,18 +292,19 @@ def net_forward(weights, zoom_image_observed, zoom_image_rendered, zoom_mask_obs
         torch.set_num_threads(num_threads)
     from_np = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
     with torch.no_grad():
-        x = torch.cat([from_np(zoom_image_observed) / 255.0, from_np(zoom_image_rendered) / 255.0,
-                       from_np(zoom_mask_observed), from_np(zoom_mask_rendered)], dim=1)
+        rb = (lambda t: t.bfloat16().float()) if emulate_bf16 else (lambda t: t)
+        x = rb(torch.cat([from_np(zoom_image_observed) / 255.0, from_np(zoom_image_rendered) / 255.0,
+                          from_np(zoom_mask_observed), from_np(zoom_mask_rendered)], dim=1))
         feats = {}
         specs = [("flow_conv1", 2, 3), ("conv2", 2, 2), ("conv3", 2, 2), ("conv3_1", 1, 1), ("conv4", 2, 1),
                  ("conv4_1", 1, 1), ("conv5", 2, 1), ("conv5_1", 1, 1), ("conv6", 2, 1), ("conv6_1", 1, 1)]
         for name, s, p in specs:
-            x = F.conv2d(x, from_np(weights[name + "_weight"]), from_np(weights[name + "_bias"]), stride=s, padding=p)
-            x = F.leaky_relu(x, 0.1)
+            x = F.conv2d(x, rb(from_np(weights[name + "_weight"])), from_np(weights[name + "_bias"]), stride=s, padding=p)
+            x = rb(F.leaky_relu(x, 0.1))
             if return_features:
                 feats[name] = x.numpy().copy()
         x = x.flatten(1)  # NCHW flatten: c*80 + h*10 + w (deepIM_flownet.py:110)
-        x = F.leaky_relu(F.linear(x, from_np(weights["fc6_weight"]), from_np(weights["fc6_bias"])), 0.1)
+        x = F.leaky_relu(F.linear(x, rb(from_np(weights["fc6_weight"])), from_np(weights["fc6_bias"])), 0.1)
         if return_features:
             feats["fc6"] = x.numpy().copy()
         x = F.leaky_relu(F.linear(x, from_np(weights["fc7_weight"]), from_np(weights["fc7_bias"])), 0.1)

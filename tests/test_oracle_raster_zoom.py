@@ -186,3 +186,28 @@ def test_net_forward_shapes_and_refine_runs():
     R = res["poses"][0, 0, :, :3]
     np.testing.assert_allclose(R @ R.T, np.eye(3), atol=1e-9)
     assert res["bbox"][0, 0, 1] >= res["bbox"][0, 0, 0] >= 0
+
+
+def test_bf16_storage_emulation_calibrates_the_throughput_mode_tolerance():
+    """DIM_PREC_BF16 (what bench.py reports) stores conv activations and operand weights in bf16 with fp32 accumulation.
+    The oracle network with exactly that storage emulated differs from the fp32 oracle by ~1e-4 on the regressed se3 delta
+    -- the size of the deviation the GPU tests allow that mode (2e-3) and that profiles/r01_parity_report.json records
+    for the device (1.5e-4 on the first-iteration pose over 64 instances).  The parity mode (bf16x3) does not have it."""
+    from deepim_b200 import synth
+    w = synth.make_weights(0)
+    mesh = synth.make_blob(nlat=24, nlon=48, tex_size=128)
+    K, means = synth.K_LINEMOD, synth.PIXEL_MEANS_RGB
+    obs, ini = synth.sample_pose_pairs(2, 33)
+    zs = []
+    for b in range(2):
+        ro, rr = O.render(mesh, obs[b], K, means_rgb=means), O.render(mesh, ini[b], K, means_rgb=means)
+        mo = O.box_mask(rr["bbox"], 480, 640)[None, None]
+        mr = rr["mask"][None, None]
+        zo, _, zr, zf, _ = O.zoom_mask(mo, mo, mr, ini[b:b + 1].astype(np.float32), K)
+        zio, zir = O.zoom_image_with_factor(zf, ro["image"][None], rr["image"][None], means.astype(np.float32))
+        zs.append((zio, zir, zo, zr))
+    zio, zir, zo, zr = [np.concatenate([z[k] for z in zs]) for k in range(4)]
+    rot, trans = O.net_forward(w, zio, zir, zo, zr)
+    rot16, trans16 = O.net_forward(w, zio, zir, zo, zr, emulate_bf16=True)
+    dr, dt = np.abs(rot16 - rot).max(), np.abs(trans16 - trans).max()
+    assert 1e-6 < dr < 2e-3 and dt < 2e-3, (dr, dt)
