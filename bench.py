@@ -6,10 +6,14 @@
            --master-port P bench.py --gpus N --steps K --warmup W
     python bench.py --impl reference --steps 5 --warmup 1      # restated reference CPU path (oracle)
 
-One "step" = one pass of the fused hot path (dim_refine: 4 x render -> bbox+zoom -> FlowNetS ->
-se3 compose) over one batch of synthetic instances; workload = BASELINE.json configs[1]
-(C2: ~5k-vert mesh, 4 iters, batch 16 per GPU, random-init FlowNetS).  Instances are independent:
-N GPUs = N replicas of the per-GPU batch, no data-path collective ("scaling": "weak").
+One "step" = STEP_BATCHES (32) passes of the fused hot path (dim_refine: 4 x render -> bbox+zoom -> FlowNetS ->
+se3 compose), each over one batch of 16 synthetic instances = 512 refinements; workload = BASELINE.json configs[1]
+(C2: ~5k-vert mesh, 4 iters, batch 16 per GPU, random-init FlowNetS).  32 batches per step make the default
+20-step timed region ~1.5-2 s long, so the clocks settle under the power cap, the clock sampler sees >= 15 samples and
+the SUSTAINED tensor peak of MEASURED_PEAKS.json is the right roofline denominator.  Instances are independent:
+N GPUs = N replicas of the per-GPU work, no data-path collective ("scaling": "weak").
+The headline precision is DIM_PREC_FP16 (one fp16 tcgen05 pass; the mode whose -m gpu tests assert the north-star
+1e-4 rot / 1e-3 trans tolerance at batch 16); the bf16 fast mode is reported as the labelled secondary `fast_mode`.
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -30,6 +34,7 @@ import numpy as np  # noqa: E402
 METRIC = "480x640 4-iter pose refinements/sec"
 UNIT = "refinements/s"
 N_ITER = 4
+STEP_BATCHES = 32  # device batches per bench step
 WORKLOAD = "C2: synthetic 5k-vert mesh (5151 verts / 10000 tris), 4 iters, batch=16 per GPU, FlowNetS random-init"
 
 
@@ -44,11 +49,14 @@ def conv_flops_per_instance_iter():
 
 
 def measured_peaks():
+    """MEASURED_PEAKS.json (driver-written): fp16 and bf16 share the tcgen05 kind::f16 rate, so the cuBLAS bf16 figures are the
+    denominators.  `burst` for a region shorter than ~1 s (boost clocks), `sustained` for a long one (power-capped clocks)."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         d = json.load(open(path))
-        return {"tflops": d.get("bf16_tflops_sustained", d.get("bf16_tflops")), "hbm": d.get("hbm_gbs"), "src": "measured"}
-    return {"tflops": 1400.0, "hbm": 6650.0, "src": "fallback"}
+        burst = d.get("bf16_tflops")
+        return {"burst": burst, "sustained": d.get("bf16_tflops_sustained", burst), "hbm": d.get("hbm_gbs"), "src": "measured"}
+    return {"burst": 1590.0, "sustained": 1400.0, "hbm": 6650.0, "src": "fallback"}
 
 
 class ClockSampler:
@@ -136,8 +144,8 @@ def run_b200(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    B, K_steps, W_steps = args.batch, args.steps, args.warmup
-    prec = capi.PREC_BF16X3 if args.precision == "bf16x3" else capi.PREC_BF16
+    B, K_steps, W_steps, SB = args.batch, args.steps, max(args.warmup, 3), args.step_batches
+    prec = capi.precision_id(args.precision)
     K = synth.K_LINEMOD
     means = synth.PIXEL_MEANS_RGB
 
@@ -156,6 +164,7 @@ def run_b200(args):
         mesh = synth.make_blob()  # C2
     if args.config != "c3":
         meshes = [mesh]
+    workload += "; one bench step = %d device batches of %d = %d refinements" % (SB, B, SB * B)
     weights = synth.make_weights(0)
     refiner = PoseRefiner(meshes, weights, K, device=local_rank, max_batch=B, n_iter=N_ITER, pixel_means_rgb=means,
                           precision=args.precision, n_slots=args.slots)
@@ -168,14 +177,14 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_dev(k):
+    def batch_single(k, p):
         s = sets[k % len(sets)]
-        return ctx.refine(s["img_dev"], s["cls_dev"], s["pose_dev"], K, N_ITER, pixel_means_rgb=means, precision=prec)
+        return ctx.refine(s["img_dev"], s["cls_dev"], s["pose_dev"], K, N_ITER, pixel_means_rgb=means, precision=p)
 
-    def run_host(n_steps):
-        """public host API, two batches in flight: H2D of step k+1 overlaps the kernels of step k"""
+    def run_host(n_batches):
+        """public host API, `slots` batches in flight: the H2D of batch k+1 overlaps the kernels of batch k"""
         pending, last = [], None
-        for k in range(n_steps):
+        for k in range(n_batches):
             s = sets[k % len(sets)]
             if len(pending) == len(refiner.slots):
                 last = refiner.result(pending.pop(0))
@@ -185,53 +194,67 @@ def run_b200(args):
         return last
 
     # ---------------- device-resident arm (`value`): inputs already in HBM, `--slots` independent batches in
-    # flight on as many streams (instances are independent, so consecutive steps overlap their tails)
+    # flight on as many streams / contexts (instances are independent, so consecutive batches overlap their tails)
     streams = [s_["stream"] for s_ in refiner.slots]
     ctxs = [s_["ctx"] for s_ in refiner.slots]
 
-    def step_dev2(k):
+    def batch_multi(k, p):
         i = k % len(streams)
         with torch.cuda.stream(streams[i]):
             s = sets[k % len(sets)]
-            return ctxs[i].refine(s["img_dev"], s["cls_dev"], s["pose_dev"], K, N_ITER, pixel_means_rgb=means,
-                                  precision=prec)
+            return ctxs[i].refine(s["img_dev"], s["cls_dev"], s["pose_dev"], K, N_ITER, pixel_means_rgb=means, precision=p)
 
-    for k in range(max(W_steps, 3)):
-        step_dev(k)
+    def device_pass(p, n_steps, with_clocks):
+        """n_steps x SB batches round-robin over the streams; CUDA events on torch's current stream bracket the region,
+        every slot stream waits for the start event and is joined before the stop event."""
+        sampler = None
+        if with_clocks:
+            sampler = ClockSampler(local_rank)
+            sampler.start()
+            time.sleep(0.3)
+        barrier()
+        launch_count(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record()
+        for st_ in streams:
+            st_.wait_event(e0)
+        out = None
+        for k in range(n_steps * SB):
+            out = batch_multi(k, p)
+        for st_ in streams:
+            torch.cuda.current_stream().wait_stream(st_)
+        e1.record()
+        barrier()
+        t1 = time.time()
+        n_launch = launch_count()
+        clocks = sampler.stop(t0, t1) if sampler else None
+        return e0.elapsed_time(e1), n_launch, clocks, out
+
+    for k in range(3):
+        batch_single(k, prec)
     torch.cuda.synchronize()  # a context must only ever be driven from one stream at a time
-    for k in range(2 * len(streams)):
-        step_dev2(k)
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    time.sleep(0.3)
-    barrier()
-    launch_count(True)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.time()
-    e0.record()
-    for st_ in streams:
-        st_.wait_event(e0)
-    for k in range(K_steps):
-        out = step_dev2(k)
-    for st_ in streams:
-        torch.cuda.current_stream().wait_stream(st_)
-    e1.record()
-    barrier()
-    t1 = time.time()
-    launches = launch_count()
-    ms_total = e0.elapsed_time(e1)
-    clocks = sampler.stop(t0, t1)
+    device_pass(prec, W_steps, False)                               # W warm-up steps of the timed configuration
+    ms_total, launches, clocks, out = device_pass(prec, K_steps, True)
     poses_last = out["poses"][-1].cpu().numpy()
 
-    # ---------------- roofline pass: the same K steps on ONE stream with CUDA events between the stages
-    # (stage times are only meaningful without a second batch interleaved on the SMs)
+    # ---------------- secondary: the bf16 fast mode (fails the 1e-4 rot tolerance -- NOT the headline), same pass shape
+    fast = None
+    if prec != capi.PREC_BF16 and not args.no_fast_mode:
+        kf = max(3, K_steps // 4)
+        device_pass(capi.PREC_BF16, 1, False)
+        ms_f, _, _, _ = device_pass(capi.PREC_BF16, kf, False)
+        fast = (ms_f, kf)
+
+    # ---------------- stage pass: a few steps on ONE stream with CUDA events between the stages (stage times are only
+    # meaningful without a second batch interleaved on the SMs); explains the headline, does not produce it
     barrier()
+    k_single = max(1, min(K_steps, 2))
     ctx.profile_enable(True)
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     p0.record()
-    for k in range(K_steps):
-        step_dev(k)
+    for k in range(k_single * SB):
+        batch_single(k, prec)
     p1.record()
     barrier()
     ms_single = p0.elapsed_time(p1)
@@ -239,63 +262,82 @@ def run_b200(args):
     ctx.profile_enable(False)
 
     # ---------------- end-to-end arm (host buffers, H2D + D2H inside the timed region)
-    run_host(3)
+    run_host(2 * len(refiner.slots))
     barrier()
     tw0 = time.perf_counter()
-    poses_host_last = run_host(K_steps)   # every step: pinned H2D of its inputs + D2H of its poses, results consumed
+    poses_host_last = run_host(K_steps * SB)   # every batch: pinned H2D of its inputs + D2H of its poses, results consumed
     barrier()
     ms_e2e = (time.perf_counter() - tw0) * 1e3
     assert np.isfinite(poses_host_last).all()
 
-    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, ms_e2e, fast[0] if fast else 0.0], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e = float(t[0]), float(t[1])
-    value = world * B * K_steps / (ms_total / 1e3)
-    e2e_value = world * B * K_steps / (ms_e2e / 1e3)
+    ms_total, ms_e2e, ms_fast = float(t[0]), float(t[1]), float(t[2])
+    n_ref = world * B * SB * K_steps                                      # refinements in the timed region, all ranks
+    value = n_ref / (ms_total / 1e3)
+    e2e_value = n_ref / (ms_e2e / 1e3)
 
     result = None
     if rank == 0:
         peaks = measured_peaks()
-        conv_flops = conv_flops_per_instance_iter() * B * n_rec          # algorithmic flops in the recorded region
-        conv_tflops = conv_flops / (stages["conv"] / 1e3) / 1e12 if stages["conv"] > 0 else 0.0
+        flops_ii = conv_flops_per_instance_iter()
+        # roofline of the conv tower IN THE SAME multi-stream pass that produced `value`: every tcgen05 FLOP of the timed
+        # region over the whole region (the other kernels of the step run inside it: this is a lower bound of the conv
+        # kernels' own rate).  Denominator: sustained bf16/fp16 peak when the region is >= 1 s, else the burst peak.
+        long_run = ms_total >= 1000.0
+        peak = peaks["sustained"] if long_run else peaks["burst"]
+        step_tflops = flops_ii * N_ITER * B * SB * K_steps / (ms_total / 1e3) / 1e12
+        conv_single = flops_ii * B * n_rec / (stages["conv"] / 1e3) / 1e12 if stages["conv"] > 0 else 0.0
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get("conv_igemm_bytes_per_launch")
-        # ADD(-S) sanity of the last step against the observed pose (blob is asymmetric -> ADD)
-        s_last = sets[(K_steps - 1) % len(sets)]
+        # ADD(-S) sanity of the last batch against the observed pose (blob is asymmetric -> ADD)
+        s_last = sets[(K_steps * SB - 1) % len(sets)]
         def add(p, q, b):
             pts = meshes[b % len(meshes)].verts.astype(np.float64)
             return float(np.linalg.norm((pts @ p[:, :3].T + p[:, 3]) - (pts @ q[:, :3].T + q[:, 3]), axis=1).mean())
         add_init = float(np.mean([add(s_last["ini"][b], s_last["obs"][b], b) for b in range(B)]))
         add_final = float(np.mean([add(poses_last[b], s_last["obs"][b], b) for b in range(B)]))
+        n_launch_kernels = 10  # conv1 + 9 implicit-GEMM launches per instance-batch iteration
         result = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K_steps,
-            "warmup": max(W_steps, 3), "ms_per_step": round(ms_total / K_steps, 4), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if prec == capi.PREC_BF16 else "bf16x3",
+            "warmup": W_steps, "ms_per_step": round(ms_total / K_steps, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.precision,
             "data": "synthetic",
-            "config": {"workload": workload, "batch_per_gpu": B, "n_iter": N_ITER, "precision": args.precision, "batches_in_flight": args.slots,
-                       "l2": "per-step working set (~1.6 GB of activations + 90 MB weights + 59 MB inputs) exceeds the "
+            "config": {"workload": workload, "batch_per_gpu": B, "batches_per_step": SB, "n_iter": N_ITER,
+                       "precision": args.precision, "batches_in_flight": args.slots,
+                       "parity": "DIM_PREC_FP16: tests/test_gpu_headline_b16.py asserts 1e-4 rot / 1e-3 trans per iteration at batch 16"
+                                 if args.precision == "fp16" else "see tests/test_gpu_parity.py for this mode's bounds",
+                       "l2": "per-batch working set (~1.6 GB of activations + 90 MB weights + 59 MB inputs) exceeds the "
                              "126 MB L2; 3 rotating input sets"},
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT,
-                    "h2d_bytes_per_step": int(B * 480 * 640 * 3 + B * 4 + B * 96),
-                    "d2h_bytes_per_step": int(N_ITER * B * (96 + 28)), "ms_per_step": round(ms_e2e / K_steps, 4),
+                    "h2d_bytes_per_step": int(SB * (B * 480 * 640 * 3 + B * 4 + B * 96)),
+                    "d2h_bytes_per_step": int(SB * N_ITER * B * (96 + 28)), "ms_per_step": round(ms_e2e / K_steps, 4),
                     "api": "PoseRefiner.submit/result -> dim_refine_host_async (uint8 BGR HWC pinned host images in, float64 poses out; %d batches in flight)" % args.slots, "timer": "host wall clock around K steps, bracketed by barrier + cuda synchronize"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (10 launches / iteration)",
-                         "achieved": round(conv_tflops, 2), "peak": peaks["tflops"], "unit": "TFLOP/s",
-                         "frac": round(conv_tflops / peaks["tflops"], 4), "traffic": traffic,
-                         "peak_source": peaks["src"] + " bf16 sustained (MEASURED_PEAKS.json)"},
-            "stages_ms_per_step": {k: round(v / K_steps, 4) for k, v in stages.items()},
-            "single_stream": {"ms_per_step": round(ms_single / K_steps, 4),
-                              "value": round(B * K_steps / (ms_single / 1e3), 2),
-                              "note": "roofline / stage times come from this pass (one batch at a time, CUDA events "
-                                      "between stages); `value` runs %d independent batches on %d streams" % (args.slots, args.slots)},
-            "e2e_roofline_frac": round(value / world / (peaks["tflops"] * 1e12 / (conv_flops_per_instance_iter() * N_ITER)), 4),
+            "roofline": {"bound": "tensor", "kernel": "conv1_strip_kernel + conv_igemm_persistent_kernel (10 launches per batch-iteration)",
+                         "achieved": round(step_tflops, 2), "peak": peak, "unit": "TFLOP/s",
+                         "frac": round(step_tflops / peak, 4), "traffic": traffic,
+                         "how": "algorithmic conv FLOPs of the timed region (38.79 GFLOP x %d instances x %d iterations x %d batches x %d steps) / "
+                                "the CUDA-event duration of the same multi-stream region that produced `value`" % (B, N_ITER, SB, K_steps),
+                         "peak_source": "%s bf16 %s (MEASURED_PEAKS.json; timed region %.2f s)" % (peaks["src"], "sustained" if long_run else "burst", ms_total / 1e3),
+                         "frac_of_burst": round(step_tflops / peaks["burst"], 4), "frac_of_sustained": round(step_tflops / peaks["sustained"], 4),
+                         "conv_tower_single_stream_tflops": round(conv_single, 2),
+                         "launches_per_batch_iteration": n_launch_kernels},
+            "stages_ms_per_batch_single_stream": {k: round(v / (k_single * SB), 4) for k, v in stages.items()},
+            "single_stream": {"ms_per_batch": round(ms_single / (k_single * SB), 4),
+                              "value": round(B * k_single * SB / (ms_single / 1e3), 2),
+                              "note": "stage times come from this pass (one batch at a time, CUDA events between stages); "
+                                      "`value` and `roofline` come from the pass with %d independent batches on %d streams" % (args.slots, args.slots)},
             "add_m": {"init": round(add_init, 5), "final": round(add_final, 5), "note": "random-init weights: not expected to improve"},
         }
+        if fast:
+            result["fast_mode"] = {"dtype": "bf16", "value": round(world * B * SB * fast[1] / (ms_fast / 1e3), 2), "unit": UNIT,
+                                   "steps": fast[1], "ms_per_step": round(ms_fast / fast[1], 4),
+                                   "note": "secondary: single bf16 pass, bounded at 2e-3 rot by its tests (fails the north-star 1e-4); not the headline"}
         if world == 1 and not args.no_cpu_baseline:
             result["cpu_baseline"] = cpu_baseline_leg(sample=2, weights=weights, mesh=mesh)
     if dist is not None:
@@ -338,7 +380,7 @@ def cpu_baseline_leg(sample, weights=None, mesh=None, warm=True):
 def pick_cpu_threads(O, weights):
     """The restated CPU path is timed with the thread count that serves it best: at batch 1 torch's oneDNN convolutions get
     SLOWER beyond a few dozen threads on many-core hosts (measured 3.4 s / forward with 128 threads on the GPU box), and the
-    reference arm must not be handicapped.  Tries a few counts on one forward pass and keeps the fastest."""
+    reference arm must not be handicapped.  Best of 3 forwards per candidate (a single shot swung the pick 1.7x run to run)."""
     import torch
     cores = os.cpu_count() or 1
     z3, z1 = np.zeros((1, 3, 480, 640), np.float32), np.zeros((1, 1, 480, 640), np.float32)
@@ -346,9 +388,12 @@ def pick_cpu_threads(O, weights):
     for n in sorted({c for c in (8, 16, 32, 64, cores) if c <= cores}):
         torch.set_num_threads(n)
         O.net_forward(weights, z3, z3, z1, z1)  # warm
-        t = time.time()
-        O.net_forward(weights, z3, z3, z1, z1)
-        dt = time.time() - t
+        dt = None
+        for _ in range(3):
+            t = time.time()
+            O.net_forward(weights, z3, z3, z1, z1)
+            d = time.time() - t
+            dt = d if dt is None else min(dt, d)
         if best_t is None or dt < best_t:
             best, best_t = n, dt
     torch.set_num_threads(best)
@@ -444,7 +489,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="instances per GPU")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16x3", "bf16"],
+                    help="fp16 = headline (single tcgen05 pass, meets 1e-4 rot / 1e-3 trans); bf16x3 = 3-pass; bf16 = fast mode")
+    ap.add_argument("--step-batches", type=int, default=STEP_BATCHES, help="device batches per bench step")
+    ap.add_argument("--no-fast-mode", action="store_true", help="skip the secondary bf16 fast-mode pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--slots", type=int, default=4, help="independent batches in flight per GPU (streams)")
     ap.add_argument("--config", default="c2", choices=["c2", "c3", "c5"],
@@ -463,7 +511,7 @@ def main():
         args.warmup = 1 if args.warmup is None else args.warmup
         run_reference(args)
     else:
-        args.steps = 200 if args.steps is None else args.steps
+        args.steps = 20 if args.steps is None else args.steps
         args.warmup = 3 if args.warmup is None else args.warmup
         run_b200(args)
 

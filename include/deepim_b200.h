@@ -205,6 +205,8 @@ DIM_API int32_t dim_net_load(dim_ctx *ctx, const float *const *weights_host,
 /* precision of the conv stack */
 #define DIM_PREC_BF16 0   /* one bf16 tcgen05 pass, fp32 accumulate (throughput mode)          */
 #define DIM_PREC_BF16X3 1 /* hi/lo split, 3 tcgen05 passes, ~fp32 accuracy (parity mode)       */
+#define DIM_PREC_FP16 2   /* one fp16 tcgen05 pass (11 significant bits), fp32 accumulate, saturating stores:
+                             the single-pass mode that meets the 1e-4 rot / 1e-3 trans se3 tolerance (headline mode) */
 
 /* Encoder + fc + heads on already-zoomed blobs (get_convs, deepIM_flownet.py:53-116; heads
  * l.716-717): inputs f32 NCHW as the op surface produces them; rot f32[B,4] raw quaternion,

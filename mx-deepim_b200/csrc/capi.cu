@@ -30,11 +30,11 @@ int zoom_factor_from_ren_launch(dim_ctx *, const int *, const float *, int B, co
                                 cudaStream_t);
 int box_mask_launch(dim_ctx *, const int *, int B, float *, cudaStream_t);
 int zoom_fused_launch(dim_ctx *, const float4 *, const float4 *, const float *, const float *, int B, int Hs, int Ws,
-                      int pad, __nv_bfloat16 *, __nv_bfloat16 *, cudaStream_t);
+                      int pad, __nv_bfloat16 *, __nv_bfloat16 *, cudaStream_t, int f16);
 int pack_obs4_launch(dim_ctx *, const float *, int B, float4 *, cudaStream_t);
 int transform_u8_obs4_launch(dim_ctx *, const uint8_t *, int B, const double *, float4 *, cudaStream_t);
 int pack_nhwc8_launch(dim_ctx *, const float *, const float *, const float *, const float *, int B, int Hs, int Ws,
-                      int pad, __nv_bfloat16 *, __nv_bfloat16 *, cudaStream_t);
+                      int pad, __nv_bfloat16 *, __nv_bfloat16 *, cudaStream_t, int f16);
 int flow_launch(dim_ctx *, const float *, const float *, const float *, const float *, int B, float *, float *,
                 float *, cudaStream_t);
 int train_pose_launch(const float *, const float *, const float *, const float *, int B, const double *,
@@ -343,7 +343,7 @@ DIM_API int32_t dim_net_fwd(dim_ctx *ctx, const float *zio, const float *zir, co
   int rows, cols, pad; __nv_bfloat16 *hi, *lo;
   net_input_geometry(ctx, &rows, &cols, &pad, &hi, &lo);
   if (int rc = pack_nhwc8_launch(ctx, zio, zir, zmo, zmr, B, rows, cols, pad, hi,
-                                 precision == DIM_PREC_BF16X3 ? lo : nullptr, st))
+                                 precision == DIM_PREC_BF16X3 ? lo : nullptr, st, precision == DIM_PREC_FP16))
     return rc;
   return net_forward(ctx, B, precision, nullptr, rot, trans, nullptr, st, nullptr);
 }
@@ -389,7 +389,7 @@ static int refine_core(dim_ctx *ctx, const float4 *obs4, const int32_t *cls_idx,
     if (int rc = zoom_factor_from_ren_launch(ctx, ctx->bbox_ren, ctx->pose_cur_f32, B, K9, zf_it, bbox_it, ctx->status, st))
       return rc;
     if (int rc = zoom_fused_launch(ctx, obs4, ctx->ren4, zf_it, means_f, B, rows, cols, pad, hi,
-                                   precision == DIM_PREC_BF16X3 ? lo : nullptr, st))
+                                   precision == DIM_PREC_BF16X3 ? lo : nullptr, st, precision == DIM_PREC_FP16))
       return rc;
     if (ev) DIM_CHECK(cudaEventRecord(ev[2], st));
     float *se3_it = se3 ? se3 + (size_t)it * B * 7 : ctx->se3_cur;

@@ -19,8 +19,13 @@
 //
 // SPLIT3 = bf16x3 precision mode: operands are hi/lo bf16 pairs (x = hi + lo); each K step issues
 // hi*hi + lo*hi + hi*lo into the same fp32 accumulator (error ~2^-16 relative, near-fp32).
+// ConvKParams::f16 = fp16 precision mode (DIM_PREC_FP16): the same one-pass kernels with IEEE half
+// operands (instruction-descriptor a/b format F16; 11 significant bits instead of bf16's 8) and
+// epilogues that store saturating fp16; the 16-bit activation / weight buffers are shared with the
+// bf16 modes (typed __nv_bfloat16* in the signatures, the bits are whatever the mode stores).
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace dim {
@@ -37,6 +42,7 @@ struct ConvKParams {
   int Hq, Ho, Wo, Bn;           // virtual rows per image, valid output extent, batch
   int out_Hp, out_Wp, out_py, out_px, Cout;
   int kblocks, ksplit;
+  int f16;  // 1: outputs are stored as fp16 (operands are fp16 as well: see idesc)
   uint32_t idesc;
   float slope;
   const float *bias;
@@ -155,6 +161,19 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo_bytes
 
 }  // namespace ptx
 
+// two fp32 -> packed 16-bit pair (element 0 in the low half).  fp16 saturates to +-65504 instead of
+// overflowing to inf (the reference computes in fp32: a finite value must stay finite).
+__device__ __forceinline__ uint32_t pack2_f16(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Epilogue helper: one warp owns 32 accumulator rows (its TMEM lane quadrant).  64 fp32 columns per
 // call are biased, LeakyReLU'd, converted to bf16 (hi[, lo]) and staged through a per-warp 4 KB
@@ -164,25 +183,37 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo_bytes
 template <bool SPLIT3>
 __device__ __forceinline__ void epilogue_store64(const uint32_t *r, const float *bias_s, float slope, uint8_t *stage,
                                                  __nv_bfloat16 *out_hi, __nv_bfloat16 *out_lo, long long my_off,
-                                                 bool my_valid, int lane) {
-  __align__(16) __nv_bfloat16 h[64];
-  __align__(16) __nv_bfloat16 l[SPLIT3 ? 64 : 8];
+                                                 bool my_valid, int lane, bool f16 = false) {
+  __align__(16) uint32_t h[32];
+  __align__(16) uint32_t l[SPLIT3 ? 32 : 4];
+  if (!SPLIT3 && f16) {
 #pragma unroll
-  for (int j = 0; j < 64; ++j) {
-    float v = __uint_as_float(r[j]) + bias_s[j];
-    v = v > 0.f ? v : v * slope;
-    h[j] = __float2bfloat16_rn(v);
-    if (SPLIT3) l[j] = __float2bfloat16_rn(v - __bfloat162float(h[j]));
+    for (int j = 0; j < 64; j += 2) {
+      float v0 = __uint_as_float(r[j]) + bias_s[j], v1 = __uint_as_float(r[j + 1]) + bias_s[j + 1];
+      v0 = v0 > 0.f ? v0 : v0 * slope;
+      v1 = v1 > 0.f ? v1 : v1 * slope;
+      h[j >> 1] = pack2_f16(v0, v1);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 64; j += 2) {
+      float v0 = __uint_as_float(r[j]) + bias_s[j], v1 = __uint_as_float(r[j + 1]) + bias_s[j + 1];
+      v0 = v0 > 0.f ? v0 : v0 * slope;
+      v1 = v1 > 0.f ? v1 : v1 * slope;
+      const uint32_t hh = pack2_bf16(v0, v1);
+      h[j >> 1] = hh;
+      if (SPLIT3) l[j >> 1] = pack2_bf16(v0 - __uint_as_float(hh << 16), v1 - __uint_as_float(hh & 0xFFFF0000u));
+    }
   }
   const unsigned vmask = __ballot_sync(0xffffffffu, my_valid);
   const int ch = lane & 7;
 #pragma unroll
   for (int pass = 0; pass < (SPLIT3 ? 2 : 1); ++pass) {
-    const __nv_bfloat16 *src = pass ? l : h;
+    const uint32_t *src = pass ? l : h;
     __nv_bfloat16 *out = pass ? out_lo : out_hi;
 #pragma unroll
     for (int c = 0; c < 8; ++c)
-      *reinterpret_cast<uint4 *>(stage + lane * 128 + ((c ^ (lane & 7)) << 4)) = *reinterpret_cast<const uint4 *>(src + c * 8);
+      *reinterpret_cast<uint4 *>(stage + lane * 128 + ((c ^ (lane & 7)) << 4)) = *reinterpret_cast<const uint4 *>(src + c * 4);
     __syncwarp();
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -510,7 +541,7 @@ __global__ void __launch_bounds__(192) conv_igemm_persistent_kernel(const __grid
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
           }
-          epilogue_store64<SPLIT3>(r, bias_s + n0 + c, p.slope, stg, p.out_hi, p.out_lo, my_off + c, valid, lane);
+          epilogue_store64<SPLIT3>(r, bias_s + n0 + c, p.slope, stg, p.out_hi, p.out_lo, my_off + c, valid, lane, p.f16 != 0);
         }
       }
       if (++as == 2) { as = 0; aph ^= 1u; }
@@ -549,16 +580,18 @@ static __global__ void __launch_bounds__(256) conv_tail_finalize_kernel(const __
   const int c = n0 + c4;
   float v[4] = {acc.x + p.bias[c], acc.y + p.bias[c + 1], acc.z + p.bias[c + 2], acc.w + p.bias[c + 3]};
   const size_t pix = ((size_t)n_img * p.out_Hp + oh + p.out_py) * p.out_Wp + ow + p.out_px;
-  __align__(8) __nv_bfloat16 h[4];
-  __align__(8) __nv_bfloat16 l[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float x = v[j] > 0.f ? v[j] : v[j] * p.slope;
-    h[j] = __float2bfloat16_rn(x);
-    l[j] = __float2bfloat16_rn(x - __bfloat162float(h[j]));
+  for (int j = 0; j < 4; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
+  if (p.f16) {
+    *reinterpret_cast<uint2 *>(p.out_hi + pix * p.Cout + c) = make_uint2(pack2_f16(v[0], v[1]), pack2_f16(v[2], v[3]));
+    return;
   }
-  *reinterpret_cast<uint2 *>(p.out_hi + pix * p.Cout + c) = *reinterpret_cast<const uint2 *>(h);
-  if (split3) *reinterpret_cast<uint2 *>(p.out_lo + pix * p.Cout + c) = *reinterpret_cast<const uint2 *>(l);
+  const uint32_t h0 = pack2_bf16(v[0], v[1]), h1 = pack2_bf16(v[2], v[3]);
+  *reinterpret_cast<uint2 *>(p.out_hi + pix * p.Cout + c) = make_uint2(h0, h1);
+  if (split3)
+    *reinterpret_cast<uint2 *>(p.out_lo + pix * p.Cout + c) =
+        make_uint2(pack2_bf16(v[0] - __uint_as_float(h0 << 16), v[1] - __uint_as_float(h0 & 0xFFFF0000u)),
+                   pack2_bf16(v[2] - __uint_as_float(h1 << 16), v[3] - __uint_as_float(h1 & 0xFFFF0000u)));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -728,7 +761,7 @@ __global__ void __launch_bounds__(192) conv1_strip_kernel(const __grid_constant_
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);  // accumulator stage is free again
-      epilogue_store64<SPLIT3>(r, bias_s, p.slope, epi + (warp - 2) * 4096, p.out_hi, p.out_lo, my_off, valid, lane);
+      epilogue_store64<SPLIT3>(r, bias_s, p.slope, epi + (warp - 2) * 4096, p.out_hi, p.out_lo, my_off, valid, lane, p.f16 != 0);
       if (++as == 2) { as = 0; aph ^= 1u; }
     }
   }
@@ -987,7 +1020,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192)
             __syncwarp();
             if (lane == 0) ptx2::mbar_arrive_leader(&tmem_empty_bar[as]);
           }
-          epilogue_store64<SPLIT3>(r, bias_s + n0 + c, p.slope, stg, p.out_hi, p.out_lo, my_off + c, valid, lane);
+          epilogue_store64<SPLIT3>(r, bias_s + n0 + c, p.slope, stg, p.out_hi, p.out_lo, my_off + c, valid, lane, p.f16 != 0);
         }
       }
       if (++as == 2) { as = 0; aph ^= 1u; }
@@ -1007,7 +1040,7 @@ static __global__ void __launch_bounds__(256) conv_splitk_finalize_kernel(const 
                                                                    int Cout, int Ho, int Wo, int out_Hp, int out_Wp,
                                                                    int out_py, int out_px, const float *bias,
                                                                    float slope, __nv_bfloat16 *out_hi,
-                                                                   __nv_bfloat16 *out_lo) {
+                                                                   __nv_bfloat16 *out_lo, int f16) {
   const size_t idx4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (idx4 >= (size_t)npix * Cout) return;
   const size_t opix = idx4 / Cout;
@@ -1022,16 +1055,18 @@ static __global__ void __launch_bounds__(256) conv_splitk_finalize_kernel(const 
   const int rem = (int)(opix - (size_t)n_img * Ho * Wo);
   const int oh = rem / Wo, ow = rem - oh * Wo;
   const size_t pix = ((size_t)n_img * out_Hp + oh + out_py) * out_Wp + ow + out_px;
-  __align__(8) __nv_bfloat16 h[4];
-  __align__(8) __nv_bfloat16 l[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float x = v[j] > 0.f ? v[j] : v[j] * slope;
-    h[j] = __float2bfloat16_rn(x);
-    l[j] = __float2bfloat16_rn(x - __bfloat162float(h[j]));
+  for (int j = 0; j < 4; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * slope;
+  if (f16) {
+    *reinterpret_cast<uint2 *>(out_hi + pix * Cout + c) = make_uint2(pack2_f16(v[0], v[1]), pack2_f16(v[2], v[3]));
+    return;
   }
-  *reinterpret_cast<uint2 *>(out_hi + pix * Cout + c) = *reinterpret_cast<const uint2 *>(h);
-  if (out_lo) *reinterpret_cast<uint2 *>(out_lo + pix * Cout + c) = *reinterpret_cast<const uint2 *>(l);
+  const uint32_t h0 = pack2_bf16(v[0], v[1]), h1 = pack2_bf16(v[2], v[3]);
+  *reinterpret_cast<uint2 *>(out_hi + pix * Cout + c) = make_uint2(h0, h1);
+  if (out_lo)
+    *reinterpret_cast<uint2 *>(out_lo + pix * Cout + c) =
+        make_uint2(pack2_bf16(v[0] - __uint_as_float(h0 << 16), v[1] - __uint_as_float(h0 & 0xFFFF0000u)),
+                   pack2_bf16(v[2] - __uint_as_float(h1 << 16), v[3] - __uint_as_float(h1 & 0xFFFF0000u)));
 }
 
 }  // namespace dim

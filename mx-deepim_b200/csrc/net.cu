@@ -7,6 +7,9 @@
 //                deterministic two-pass reduction (partials reduced in fixed order by the head kernel)
 //   head       : fc6 reduce + bias + LeakyReLU -> fc7 -> LeakyReLU -> rot(4), trans(3) ->
 //                ZoomTrans^-1 (zoom_trans.py:30-31) -> se3 (B,7)
+#include <cuda_fp16.h>
+#include <string.h>
+
 #include <mutex>
 
 #include "net_state.cuh"
@@ -154,13 +157,14 @@ int encode_map(CUtensorMap *m, void *base, int rank, const uint64_t *dims, const
   return 0;
 }
 
-uint32_t make_idesc(int M, int N) {
-  // cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b_format BF16 (1) @7/@10, K-major both,
+uint32_t make_idesc(int M, int N, bool f16) {
+  // cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b_format @7/@10 (0 = F16, 1 = BF16), K-major both,
   // n_dim = N>>3 @17, m_dim = M>>4 @24
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+  const uint32_t fmt = f16 ? 0u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-static int build_maps(NetState *ns, int B, TensorMaps &tm) {
+static int build_maps(NetState *ns, int B, bool f16, TensorMaps &tm) {
   for (int i = 0; i < 10; ++i) {
     tm.g[i] = effective_geom(ns, i, B);
     const LayerGeom &g = tm.g[i];
@@ -197,10 +201,11 @@ static int build_maps(NetState *ns, int B, TensorMaps &tm) {
       const uint64_t dims[2] = {Ktot, (uint64_t)g.Cout};
       const uint64_t str[1] = {Ktot * 2};
       const uint32_t box[2] = {(uint32_t)g.BLOCK_K, (uint32_t)g.BLOCK_N};
-      if (int rc = encode_map(&kp.b_map, ns->w_hi[i], 2, dims, str, box, g.BLOCK_K)) return rc;
+      __nv_bfloat16 *wop = f16 ? ns->w_f16[i] : ns->w_hi[i];
+      if (int rc = encode_map(&kp.b_map, wop, 2, dims, str, box, g.BLOCK_K)) return rc;
       if (int rc = encode_map(&kp.b_lo_map, ns->w_lo[i], 2, dims, str, box, g.BLOCK_K)) return rc;
       const uint32_t box2[2] = {(uint32_t)g.BLOCK_K, (uint32_t)(g.BLOCK_N / 2)};
-      if (int rc = encode_map(&kp.b2_map, ns->w_hi[i], 2, dims, str, box2, g.BLOCK_K)) return rc;
+      if (int rc = encode_map(&kp.b2_map, wop, 2, dims, str, box2, g.BLOCK_K)) return rc;
       if (int rc = encode_map(&kp.b2_lo_map, ns->w_lo[i], 2, dims, str, box2, g.BLOCK_K)) return rc;
     }
     kp.KH = g.KH; kp.KW = g.KW; kp.stride = g.stride_eff; kp.cchunks = g.Ceff / g.BLOCK_K;
@@ -215,7 +220,8 @@ static int build_maps(NetState *ns, int B, TensorMaps &tm) {
     kp.Cout = g.Cout;
     kp.kblocks = g.kblocks;
     kp.ksplit = tm.ksplit[i] = choose_ksplit(ns, g, B);
-    kp.idesc = make_idesc(g.pair ? 256 : 128, g.BLOCK_N);
+    kp.idesc = make_idesc(g.pair ? 256 : 128, g.BLOCK_N, f16);
+    kp.f16 = f16 ? 1 : 0;
     kp.slope = 0.1f;
     kp.bias = ns->bias[i];
     kp.out_hi = ns->act_hi[i + 1];
@@ -232,14 +238,22 @@ static int build_maps(NetState *ns, int B, TensorMaps &tm) {
 // chunk staged in shared memory.  HBM-bound by design: 42 MB of bf16 weights per call (84 MB with the
 // lo halves in bf16x3 mode).  CTA s owns k in [s*KC, (s+1)*KC) for all 256 outputs; partials are
 // reduced in fixed order by the head kernel (deterministic, no atomics).
+template <bool F16>
 __device__ __forceinline__ void mma_bf16_16816(float *c, const uint32_t *a, uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  if (F16)
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  else
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-template <bool S3>
+// S3: bf16 hi/lo operands (3 MMAs per step); F16: IEEE half operands (one MMA per step, like plain bf16)
+template <bool S3, bool F16 = false>
 __global__ void __launch_bounds__(256) fc6_mma_kernel(const __nv_bfloat16 *__restrict__ act_hi,
                                                       const __nv_bfloat16 *__restrict__ act_lo,
                                                       const __nv_bfloat16 *__restrict__ w_hi,
@@ -288,14 +302,14 @@ __global__ void __launch_bounds__(256) fc6_mma_kernel(const __nv_bfloat16 *__res
         const int j = warp * 32 + t * 8 + g;  // output row whose weights this lane streams
         const size_t wo = (size_t)j * FC6_K + k0 + kc + q * 8;
         const uint4 wh = __ldg(reinterpret_cast<const uint4 *>(w_hi + wo));
-        mma_bf16_16816(acc[t], A0, wh.x, wh.y);
-        mma_bf16_16816(acc[t], A1, wh.z, wh.w);
+        mma_bf16_16816<F16>(acc[t], A0, wh.x, wh.y);
+        mma_bf16_16816<F16>(acc[t], A1, wh.z, wh.w);
         if (S3) {
           const uint4 wl = __ldg(reinterpret_cast<const uint4 *>(w_lo + wo));
-          mma_bf16_16816(acc[t], L0, wh.x, wh.y);
-          mma_bf16_16816(acc[t], L1, wh.z, wh.w);
-          mma_bf16_16816(acc[t], A0, wl.x, wl.y);
-          mma_bf16_16816(acc[t], A1, wl.z, wl.w);
+          mma_bf16_16816<false>(acc[t], L0, wh.x, wh.y);
+          mma_bf16_16816<false>(acc[t], L1, wh.z, wh.w);
+          mma_bf16_16816<false>(acc[t], A0, wl.x, wl.y);
+          mma_bf16_16816<false>(acc[t], A1, wl.z, wl.w);
         }
       }
     }
@@ -410,27 +424,62 @@ void net_destroy(dim_ctx *ctx) {
   ctx->net = nullptr;
 }
 
-static void split_bf16(const float *src, size_t n, std::vector<__nv_bfloat16> &hi, std::vector<__nv_bfloat16> &lo) {
+static void split_bf16(const float *src, size_t n, std::vector<__nv_bfloat16> &hi, std::vector<__nv_bfloat16> &lo,
+                       std::vector<__nv_bfloat16> &f16) {
   hi.resize(n);
   lo.resize(n);
+  f16.resize(n);
   for (size_t i = 0; i < n; ++i) {
     hi[i] = __float2bfloat16_rn(src[i]);
     lo[i] = __float2bfloat16_rn(src[i] - __bfloat162float(hi[i]));
+    const __half h = __float2half_rn(src[i]);  // He-scale weights are far inside the fp16 range; inf only for |w| > 65504
+    memcpy(&f16[i], &h, 2);
   }
 }
 
+// first call allocates, later calls (dim_net_load on a loaded context) overwrite in place: the tensor maps
+// cached in NetState::maps keep pointing at valid storage
 template <typename T>
 static int upload(dim_ctx *ctx, T **dst, const std::vector<T> &v) {
-  if (int rc = dev_alloc(ctx, dst, v.size(), false)) return rc;
+  if (*dst == nullptr)
+    if (int rc = dev_alloc(ctx, dst, v.size(), false)) return rc;
   DIM_CHECK(cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// fp16 operand packs re-derived on the device from the bf16 hi/lo pair (hi + lo carries 16 significant bits): used
+// after a training update refreshed hi/lo from the fp32 master weights (train.cu repack_all)
+__global__ void __launch_bounds__(256) f16_from_hilo_kernel(const __nv_bfloat16 *hi, const __nv_bfloat16 *lo, size_t n,
+                                                            __nv_bfloat16 *out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const __half h = __float2half_rn(__bfloat162float(hi[i]) + __bfloat162float(lo[i]));
+  reinterpret_cast<__half *>(out)[i] = h;
+}
+
+static int net_refresh_f16(dim_ctx *ctx, cudaStream_t st) {
+  NetState *ns = ctx->net;
+  if (ns->lo_stale)
+    if (int rc = train_refresh_lo(ctx, st)) return rc;
+  for (int i = 0; i < 10; ++i) {
+    const LayerGeom &g = ns->g[i];
+    const size_t n = (size_t)g.Cout * g.KH * g.KW * g.Ceff;
+    f16_from_hilo_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ns->w_hi[i], ns->w_lo[i], n, ns->w_f16[i]);
+    DIM_LAUNCH_CHECK();
+  }
+  const size_t n6 = (size_t)256 * FC6_K;
+  f16_from_hilo_kernel<<<(unsigned)((n6 + 255) / 256), 256, 0, st>>>(ns->fc6_w_hi, ns->fc6_w_lo, n6, ns->fc6_w_f16);
+  DIM_LAUNCH_CHECK();
+  ns->f16_stale = false;
   return 0;
 }
 
 int net_load(dim_ctx *ctx, const float *const *W, const float *const *Bv) {
   NetState *ns = ctx->net;
   DIM_REQUIRE(ns != nullptr, "net not created");
-  DIM_REQUIRE(!ns->loaded, "dim_net_load: weights already loaded for this context");
   DIM_REQUIRE(ns->net_ok, "dim_net_load: FlowNetS + fc6 (81920 inputs) needs a 480x640 context");
+  DIM_REQUIRE(!ns->train_aliased, "dim_net_load: this context trains; use dim_train_load_params (it owns the weights)");
+  if (ns->loaded) DIM_CHECK(cudaDeviceSynchronize());  // a reload must not race kernels still reading the old weights
   for (int i = 0; i < 10; ++i) {
     const LayerGeom &g = ns->g[i];
     const size_t Ktot = (size_t)g.KH * g.KW * g.Ceff;
@@ -457,10 +506,11 @@ int net_load(dim_ctx *ctx, const float *const *W, const float *const *Bv) {
               packed[(size_t)co * Ktot + (size_t)(kh * g.k + kw) * g.Cin + c] =
                   w[(((size_t)co * g.Cin + c) * g.k + kh) * g.k + kw];
     }
-    std::vector<__nv_bfloat16> hi, lo;
-    split_bf16(packed.data(), packed.size(), hi, lo);
+    std::vector<__nv_bfloat16> hi, lo, hf;
+    split_bf16(packed.data(), packed.size(), hi, lo, hf);
     if (int rc = upload(ctx, &ns->w_hi[i], hi)) return rc;
     if (int rc = upload(ctx, &ns->w_lo[i], lo)) return rc;
+    if (int rc = upload(ctx, &ns->w_f16[i], hf)) return rc;
     std::vector<float> bv(Bv[i], Bv[i] + g.Cout);
     if (int rc = upload(ctx, &ns->bias[i], bv)) return rc;
   }
@@ -469,10 +519,11 @@ int net_load(dim_ctx *ctx, const float *const *W, const float *const *Bv) {
     for (int o = 0; o < 256; ++o)
       for (int c = 0; c < 1024; ++c)
         for (int hw = 0; hw < 80; ++hw) p[(size_t)o * FC6_K + (size_t)hw * 1024 + c] = W[10][(size_t)o * FC6_K + (size_t)c * 80 + hw];
-    std::vector<__nv_bfloat16> hb, lb;
-    split_bf16(p.data(), p.size(), hb, lb);
+    std::vector<__nv_bfloat16> hb, lb, fb;
+    split_bf16(p.data(), p.size(), hb, lb, fb);
     if (int rc = upload(ctx, &ns->fc6_w_hi, hb)) return rc;
     if (int rc = upload(ctx, &ns->fc6_w_lo, lb)) return rc;
+    if (int rc = upload(ctx, &ns->fc6_w_f16, fb)) return rc;
     if (int rc = upload(ctx, &ns->fc6_b, std::vector<float>(Bv[10], Bv[10] + 256))) return rc;
     std::vector<float> t((size_t)256 * 256);
     for (int o = 0; o < 256; ++o)
@@ -550,17 +601,22 @@ int net_forward(dim_ctx *ctx, int B, int precision, const float *zoom_factor, fl
   NetState *ns = ctx->net;
   DIM_REQUIRE(ns && ns->loaded, "dim_net_load has not been called");
   DIM_REQUIRE(B >= 1 && B <= ctx->max_batch, "batch exceeds max_batch");
-  auto it = ns->maps.find(B);
+  DIM_REQUIRE(precision == DIM_PREC_BF16 || precision == DIM_PREC_BF16X3 || precision == DIM_PREC_FP16,
+              "unknown precision (DIM_PREC_BF16 / DIM_PREC_BF16X3 / DIM_PREC_FP16)");
+  const bool s3 = precision == DIM_PREC_BF16X3, f16 = precision == DIM_PREC_FP16;
+  const int key = B + (f16 ? kF16MapKey : 0);
+  auto it = ns->maps.find(key);
   if (it == ns->maps.end()) {
     TensorMaps tm;
-    if (int rc = build_maps(ns, B, tm)) return rc;
-    it = ns->maps.emplace(B, tm).first;
+    if (int rc = build_maps(ns, B, f16, tm)) return rc;
+    it = ns->maps.emplace(key, tm).first;
   }
   const TensorMaps &tm = it->second;
   if (ns->repack_done) DIM_CHECK(cudaStreamWaitEvent(st, ns->repack_done, 0));
-  const bool s3 = precision == DIM_PREC_BF16X3;
   if (s3 && ns->lo_stale)
     if (int rc = train_refresh_lo(ctx, st)) return rc;
+  if (f16 && ns->f16_stale)
+    if (int rc = net_refresh_f16(ctx, st)) return rc;
   for (int i = 0; i < 10; ++i) {
     const LayerGeom &g = tm.g[i];
     const ConvKParams &kp = tm.kp[i];
@@ -607,7 +663,7 @@ int net_forward(dim_ctx *ctx, int B, int precision, const float *zoom_factor, fl
       const size_t n4 = (size_t)npix * g.Cout / 4;
       conv_splitk_finalize_kernel<<<(unsigned)cdiv((int)n4, 256), 256, 0, st>>>(
           ns->conv_partial, kp.ksplit, npix, g.Cout, g.Ho, g.Wo, kp.out_Hp, kp.out_Wp, kp.out_py, kp.out_px,
-          ns->bias[i], 0.1f, ns->act_hi[i + 1], s3 ? ns->act_lo[i + 1] : nullptr);
+          ns->bias[i], 0.1f, ns->act_hi[i + 1], s3 ? ns->act_lo[i + 1] : nullptr, f16 ? 1 : 0);
       DIM_LAUNCH_CHECK();
     }
   }
@@ -615,6 +671,9 @@ int net_forward(dim_ctx *ctx, int B, int precision, const float *zoom_factor, fl
   if (s3)
     fc6_mma_kernel<true><<<FC6_SPLITS, 256, 0, st>>>(ns->act_hi[10], ns->act_lo[10], ns->fc6_w_hi, ns->fc6_w_lo, B,
                                                      ctx->max_batch, ns->fc6_partial);
+  else if (f16)
+    fc6_mma_kernel<false, true><<<FC6_SPLITS, 256, 0, st>>>(ns->act_hi[10], nullptr, ns->fc6_w_f16, nullptr, B,
+                                                            ctx->max_batch, ns->fc6_partial);
   else
     fc6_mma_kernel<false><<<FC6_SPLITS, 256, 0, st>>>(ns->act_hi[10], nullptr, ns->fc6_w_hi, nullptr, B,
                                                       ctx->max_batch, ns->fc6_partial);

@@ -38,11 +38,15 @@ struct TensorMaps {
 struct NetState {
   LayerGeom g[10];
   __nv_bfloat16 *w_hi[10] = {}, *w_lo[10] = {};
+  __nv_bfloat16 *w_f16[10] = {};  // the same packs as IEEE half (DIM_PREC_FP16; 16-bit payload, typed like the others)
   float *bias[10] = {};
   __nv_bfloat16 *act_hi[11] = {}, *act_lo[11] = {};  // act[i] = input of layer i, act[10] = fc6 input
   size_t act_elems_per_image[11] = {};
   // fc
   __nv_bfloat16 *fc6_w_hi = nullptr, *fc6_w_lo = nullptr;  // [256][81920] in (h,w,c) order
+  __nv_bfloat16 *fc6_w_f16 = nullptr;
+  bool train_aliased = false;  // dim_train_load_params made biases / head parameters alias the fp32 master vector
+  bool f16_stale = false;  // training updated the weights: the fp16 packs are re-derived lazily (net_refresh_f16)
   float *fc6_b = nullptr, *fc7_wT = nullptr, *fc7_b = nullptr, *rot_w = nullptr, *rot_b = nullptr,
         *trans_w = nullptr, *trans_b = nullptr;
   float *fc6_partial = nullptr;  // [FC6_SPLITS][max_batch][256]
@@ -54,7 +58,7 @@ struct NetState {
   cudaEvent_t repack_done = nullptr;  // training: the operand packs are refreshed on an internal stream after an update;
                                       // every consumer (net_forward) orders itself behind this event
   bool lo_stale = false;  // training updated the weights without refreshing the bf16 'lo' halves (bf16x3 mode refreshes lazily)  // training: fc6 / fc7 activations kept for the backward pass ([B][256])
-  std::map<int, TensorMaps> maps;  // per batch size
+  std::map<int, TensorMaps> maps;  // per batch size (+ kF16MapKey for the fp16 operand maps)
   int max_batch = 0, num_sms = 148;
 };
 
@@ -66,7 +70,8 @@ static constexpr int FC6_SPLITS = FC6_K / FC6_KC;  // 320
 // helpers implemented in net.cu
 int encode_map(CUtensorMap *m, void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
                const uint32_t *box, int block_k /*64: SW128, 32: SW64, 0: no swizzle*/);
-uint32_t make_idesc(int M, int N);
+uint32_t make_idesc(int M, int N, bool f16 = false);
+static constexpr int kF16MapKey = 1 << 20;
 int train_refresh_lo(dim_ctx *ctx, cudaStream_t st);  // train.cu
 int net_forward(dim_ctx *ctx, int B, int precision, const float *zoom_factor, float *rot_out, float *trans_out,
                 float *se3_out, cudaStream_t st, cudaEvent_t after_conv);

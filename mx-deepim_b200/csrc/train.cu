@@ -26,7 +26,7 @@
 namespace dim {
 
 int pack_nhwc8_launch(dim_ctx *, const float *, const float *, const float *, const float *, int B, int Hs, int Ws,
-                      int pad, __nv_bfloat16 *, __nv_bfloat16 *, cudaStream_t);
+                      int pad, __nv_bfloat16 *, __nv_bfloat16 *, cudaStream_t, int f16);
 int transform3d_fwd_launch(const float *, const float *, const float *, const float *, int, int, const float *,
                            const float *, int, float *, cudaStream_t);
 int transform3d_bwd_launch(const float *, const float *, const float *, const float *, const float *, int, int,
@@ -843,6 +843,7 @@ static int repack_all(dim_ctx *ctx, cudaStream_t st, bool with_lo) {
   }
   LAUNCH1D(pack_fc6_kernel, (size_t)256 * 81920, st, M + ts->off[P_FC6].w, ns->fc6_w_hi, with_lo ? ns->fc6_w_lo : nullptr);
   ns->lo_stale = !with_lo;
+  ns->f16_stale = true;  // the fp16 packs of DIM_PREC_FP16 are re-derived from hi/lo when that mode next runs
   LAUNCH1D(transpose256_kernel, 65536, st, M + ts->off[P_FC7].w, ns->fc7_wT);
   {
     DgradPackDst d5{{ts->d5_fwd[0], ts->d5_fwd[1], ts->d5_fwd[2], ts->d5_fwd[3]}}, d4{{ts->d4_fwd[0], ts->d4_fwd[1], ts->d4_fwd[2], ts->d4_fwd[3]}};
@@ -876,6 +877,7 @@ int train_load_params(dim_ctx *ctx, const float *flat_host, size_t n, cudaStream
   DIM_CHECK(cudaMemsetAsync(ts->mom, 0, n * sizeof(float), st));
   // fp32 parameters that the kernels read as they are (biases, rot / trans heads) now alias the master vector, so an
   // update needs no copy for them; cached launch descriptors hold the old pointers -> rebuild them lazily
+  ns->train_aliased = true;
   for (int i = 0; i < 10; ++i) ns->bias[i] = ts->master + ts->off[i].b;
   ns->fc6_b = ts->master + ts->off[P_FC6].b; ns->fc7_b = ts->master + ts->off[P_FC7].b;
   ns->rot_w = ts->master + ts->off[P_ROT].w; ns->rot_b = ts->master + ts->off[P_ROT].b;
@@ -1328,7 +1330,7 @@ int train_forward_backward(dim_ctx *ctx, const TrainIO &io, cudaStream_t st) {
 
   // ---------------- forward
   DIM_CHECK(cudaEventRecord(ts->ev_phase[0], st));
-  if (int rc = pack_nhwc8_launch(ctx, io.zio, io.zir, io.zmo, io.zmr, B, g[0].rows, g[0].cols, g[0].py, ns->act_hi[0], nullptr, st)) return rc;
+  if (int rc = pack_nhwc8_launch(ctx, io.zio, io.zir, io.zmo, io.zmr, B, g[0].rows, g[0].cols, g[0].py, ns->act_hi[0], nullptr, st, 0)) return rc;
   if (int rc = net_forward(ctx, B, DIM_PREC_BF16, nullptr, ts->rot_raw, ts->ztrans, nullptr, st, nullptr)) return rc;
   DIM_CHECK(cudaEventRecord(ts->ev_phase[1], st));
   const Buf a10 = act_buf(ns, 10), a8 = act_buf(ns, 8), a6 = act_buf(ns, 6);

@@ -7,6 +7,8 @@
 //     x_t = -1 + j*(2/(W-1)),  x_s = wx*x_t + tx,  x = (x_s+1)*(W-1)/2,  4 taps, zero padding.
 // The reference does the bbox on the host after three full-mask asnumpy() syncs and one
 // GridGenerator launch per sample; here everything stays on the device.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace dim {
@@ -306,7 +308,7 @@ struct FusedZoomParams {
   __nv_bfloat16 *hi, *lo;
 };
 
-template <bool LO>
+template <bool LO, bool F16>
 __device__ __forceinline__ void zoom_fused_pixel(const FusedZoomParams &p, int b, int i, int j, const float *zf,
                                                  __nv_bfloat16 *h, __nv_bfloat16 *l) {
   const Tap t = src_coord(i, j, zf[0], zf[1], zf[2], zf[3], p.H, p.W, p.stepx, p.stepy);
@@ -351,8 +353,12 @@ __device__ __forceinline__ void zoom_fused_pixel(const FusedZoomParams &p, int b
   }
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
-    h[c] = __float2bfloat16_rn(v[c]);
-    if (LO) l[c] = __float2bfloat16_rn(v[c] - __bfloat162float(h[c]));
+    if (F16) {
+      reinterpret_cast<__half *>(h)[c] = __float2half_rn(v[c]);  // |v| <= 1: always in range
+    } else {
+      h[c] = __float2bfloat16_rn(v[c]);
+      if (LO) l[c] = __float2bfloat16_rn(v[c] - __bfloat162float(h[c]));
+    }
   }
 }
 
@@ -360,7 +366,7 @@ __device__ __forceinline__ void zoom_fused_pixel(const FusedZoomParams &p, int b
 // of conv1's strip layout (consecutive threads write consecutive 16 B of each chunk plane); border
 // slots are rewritten with zeros.  Sources are the
 // pixel-interleaved float4 images, so each tap is one 16-byte load per image.
-template <bool LO>
+template <bool LO, bool F16>
 __global__ void __launch_bounds__(128) zoom_fused_nhwc8_kernel(FusedZoomParams p) {
   const int b = blockIdx.y;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -373,7 +379,7 @@ __global__ void __launch_bounds__(128) zoom_fused_nhwc8_kernel(FusedZoomParams p
   for (int s = 0; s < 4; ++s) {
     const int i = 2 * sr + (s >> 1) - p.pad, j = 2 * sc + (s & 1) - p.pad;
     if (i >= 0 && i < p.H && j >= 0 && j < p.W) {
-      zoom_fused_pixel<LO>(p, b, i, j, zf, h[s], l[s]);
+      zoom_fused_pixel<LO, F16>(p, b, i, j, zf, h[s], l[s]);
     } else {
 #pragma unroll
       for (int c = 0; c < 8; ++c) { h[s][c] = __float2bfloat16_rn(0.f); l[s][c] = __float2bfloat16_rn(0.f); }
@@ -390,7 +396,7 @@ __global__ void __launch_bounds__(128) zoom_fused_nhwc8_kernel(FusedZoomParams p
 
 int zoom_fused_launch(dim_ctx *ctx, const float4 *obs4, const float4 *ren4, const float *zoom_factor,
                       const float *means_rgb, int B, int Hs, int Ws, int pad, __nv_bfloat16 *hi, __nv_bfloat16 *lo,
-                      cudaStream_t st) {
+                      cudaStream_t st, int f16) {
   FusedZoomParams p;
   p.obs4 = obs4; p.ren4 = ren4;
   p.bbox8 = ctx->bbox8; p.zoom_factor = zoom_factor;
@@ -400,8 +406,9 @@ int zoom_fused_launch(dim_ctx *ctx, const float4 *obs4, const float4 *ren4, cons
   p.stepy = (float)(2.0 / (double)(ctx->H - 1));
   p.hi = hi; p.lo = lo;
   dim3 grid(cdiv(Hs * Ws, 128), B);
-  if (lo) zoom_fused_nhwc8_kernel<true><<<grid, 128, 0, st>>>(p);
-  else zoom_fused_nhwc8_kernel<false><<<grid, 128, 0, st>>>(p);
+  if (f16) zoom_fused_nhwc8_kernel<false, true><<<grid, 128, 0, st>>>(p);  // zero bits are the same in both formats
+  else if (lo) zoom_fused_nhwc8_kernel<true, false><<<grid, 128, 0, st>>>(p);
+  else zoom_fused_nhwc8_kernel<false, false><<<grid, 128, 0, st>>>(p);
   DIM_LAUNCH_CHECK();
   return 0;
 }
@@ -424,7 +431,7 @@ int pack_obs4_launch(dim_ctx *ctx, const float *img, int B, float4 *out, cudaStr
 // NCHW float32 zoomed blobs -> conv1 NHWC8 bf16 input (used by dim_net_fwd on the op surface)
 __global__ void __launch_bounds__(256) pack_nhwc8_kernel(const float *io, const float *ir, const float *mo,
                                                          const float *mr, int H, int W, int Hs, int Ws, int pad,
-                                                         __nv_bfloat16 *hi, __nv_bfloat16 *lo) {
+                                                         __nv_bfloat16 *hi, __nv_bfloat16 *lo, int f16) {
   const int b = blockIdx.y;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= H * W) return;
@@ -441,8 +448,12 @@ __global__ void __launch_bounds__(256) pack_nhwc8_kernel(const float *io, const 
   __align__(16) __nv_bfloat16 l[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
-    h[c] = __float2bfloat16_rn(v[c]);
-    l[c] = __float2bfloat16_rn(v[c] - __bfloat162float(h[c]));
+    if (f16) {
+      reinterpret_cast<__half *>(h)[c] = __float2half_rn(v[c]);
+    } else {
+      h[c] = __float2bfloat16_rn(v[c]);
+      l[c] = __float2bfloat16_rn(v[c] - __bfloat162float(h[c]));
+    }
   }
   const int oi = q / W + pad, oj = q % W + pad;
   const size_t o = ((((size_t)b * Hs + (oi >> 1)) * 4 + ((oi & 1) * 2 + (oj & 1))) * Ws + (oj >> 1)) * 8;
@@ -451,9 +462,9 @@ __global__ void __launch_bounds__(256) pack_nhwc8_kernel(const float *io, const 
 }
 
 int pack_nhwc8_launch(dim_ctx *ctx, const float *io, const float *ir, const float *mo, const float *mr, int B,
-                      int Hs, int Ws, int pad, __nv_bfloat16 *hi, __nv_bfloat16 *lo, cudaStream_t st) {
+                      int Hs, int Ws, int pad, __nv_bfloat16 *hi, __nv_bfloat16 *lo, cudaStream_t st, int f16) {
   pack_nhwc8_kernel<<<dim3(cdiv(ctx->H * ctx->W, 256), B), 256, 0, st>>>(io, ir, mo, mr, ctx->H, ctx->W, Hs, Ws, pad,
-                                                                         hi, lo);
+                                                                         hi, f16 ? nullptr : lo, f16);
   DIM_LAUNCH_CHECK();
   return 0;
 }

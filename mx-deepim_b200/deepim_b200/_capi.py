@@ -74,8 +74,22 @@ for _name, (_res, _args) in SIGNATURES.items():
     _fn.restype = _res
     _fn.argtypes = _args
 
-PREC_BF16 = 0
-PREC_BF16X3 = 1
+PREC_BF16 = 0    # one bf16 pass: fast mode, se3 only within ~2e-3 of the fp32 reference
+PREC_BF16X3 = 1  # bf16 hi/lo split, 3 passes: near-fp32
+PREC_FP16 = 2    # one fp16 pass: meets the 1e-4 rot / 1e-3 trans se3 tolerance at the bf16 MMA rate (default)
+PRECISIONS = {"bf16": PREC_BF16, "bf16x3": PREC_BF16X3, "fp16": PREC_FP16}
+
+
+def precision_id(p):
+    """'fp16' | 'bf16x3' | 'bf16' (or an already numeric id) -> DIM_PREC_* value"""
+    if isinstance(p, str):
+        if p not in PRECISIONS:
+            raise ValueError("unknown precision %r (one of %s)" % (p, sorted(PRECISIONS)))
+        return PRECISIONS[p]
+    if int(p) not in PRECISIONS.values():
+        raise ValueError("unknown precision id %r" % (p,))
+    return int(p)
+
 ROT_COORD = {"model": 0, "camera": 1, "camera_new": 2}
 
 

@@ -17,8 +17,6 @@ WEIGHT_ORDER = ["flow_conv1", "conv2", "conv3", "conv3_1", "conv4", "conv4_1", "
                 "conv6_1", "fc6", "fc7", "rot", "trans"]
 
 
-def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
 def _p(t):
@@ -49,6 +47,10 @@ class Context:
         check(lib.dim_ctx_create(device, max_batch, height, width, max_classes, max_verts, max_faces, C.byref(h)))
         self._h = h
         self.num_classes = 0
+
+    def _stream(self):
+        """torch's current stream OF THIS CONTEXT'S DEVICE (a process may hold contexts on several GPUs)"""
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -110,7 +112,7 @@ class Context:
         K9 = farr(np.asarray(K, np.float32).reshape(9), 9)
         means = farr(pixel_means_rgb, 3, C.c_double)
         check(lib.dim_render(self._h, _p(cls_idx), _p(pose), B, K9, znear, zfar, means, int(trunc_u8), _p(out["image"]),
-                             _p(out["depth"]), _p(out["mask"]), _p(out["bgr"]), _p(out["bbox"]), _stream()))
+                             _p(out["depth"]), _p(out["mask"]), _p(out["bgr"]), _p(out["bbox"]), self._stream()))
         return out
 
     def render_lit(self, cls_idx, pose, K, light_position, light_intensity, brightness_ratio=0.7, znear=0.25, zfar=6.0,
@@ -132,7 +134,7 @@ class Context:
         check(lib.dim_render_lit(self._h, _p(cls_idx), _p(pose), B, farr(np.asarray(K, np.float32).reshape(9), 9), znear, zfar,
                                  farr(pixel_means_rgb, 3, C.c_double), _p(light_position), _p(light_intensity),
                                  float(np.float32(brightness_ratio)), _p(out["image"]), _p(out["depth"]), _p(out["mask"]),
-                                 _p(out["bgr"]), _p(out["bbox"]), _stream()))
+                                 _p(out["bgr"]), _p(out["bbox"]), self._stream()))
         return out
 
     # -------------------------------------------------------------------------------- zoom
@@ -149,7 +151,7 @@ class Context:
         status = self._new((B,), torch.int32)
         K9 = farr(np.asarray(K, np.float32).reshape(9), 9)
         check(lib.dim_zoom_mask_fwd(self._h, _p(mask_observed), _p(mask_gt_observed), _p(mask_rendered), _p(src_pose), B,
-                                    K9, _p(zo), _p(zg), _p(zr), _p(zf), _p(bbox), _p(status), _stream()))
+                                    K9, _p(zo), _p(zg), _p(zr), _p(zf), _p(bbox), _p(status), self._stream()))
         return zo, zg, zr, zf, bbox, status
 
     def zoom_image_with_factor(self, zoom_factor, image_observed, image_rendered, pixel_means_rgb):
@@ -160,7 +162,7 @@ class Context:
         _chk(zoom_factor, torch.float32, (B, 4), "zoom_factor")
         zo, zr = self._new(shp), self._new(shp)
         check(lib.dim_zoom_image_with_factor_fwd(self._h, _p(zoom_factor), _p(image_observed), _p(image_rendered), B,
-                                                 farr(pixel_means_rgb, 3), _p(zo), _p(zr), _stream()))
+                                                 farr(pixel_means_rgb, 3), _p(zo), _p(zr), self._stream()))
         return zo, zr
 
     def zoom_image(self, image_observed, image_rendered, src_pose, K, pixel_means_rgb):
@@ -174,7 +176,7 @@ class Context:
         bbox, status = self._new((B, 8), torch.int32), self._new((B,), torch.int32)
         check(lib.dim_zoom_image_fwd(self._h, _p(image_observed), _p(image_rendered), _p(src_pose), B,
                                      farr(np.asarray(K, np.float32).reshape(9), 9), farr(pixel_means_rgb, 3), _p(zo), _p(zr),
-                                     _p(zf), _p(bbox), _p(status), _stream()))
+                                     _p(zf), _p(bbox), _p(status), self._stream()))
         return zo, zr, zf, bbox, status
 
     def group_picker(self, data, group_idx, group_num, backward=False, channels=None):
@@ -186,7 +188,7 @@ class Context:
         gi = group_idx.reshape(-1).to(torch.float32).contiguous()
         _chk(data, torch.float32, tuple(data.shape), "data")
         out = self._new((B, Ctot if backward else Ctot // group_num) + tuple(data.shape[2:]))
-        check(lib.dim_group_picker(self._h, _p(data), _p(gi), B, Ctot, group_num, n, int(backward), _p(out), _stream()))
+        check(lib.dim_group_picker(self._h, _p(data), _p(gi), B, Ctot, group_num, n, int(backward), _p(out), self._stream()))
         return out
 
     def zoom_mask_with_factor(self, zoom_factor, mask, b_inv_zoom):
@@ -194,7 +196,7 @@ class Context:
         _chk(mask, torch.float32, (B, 1, self.H, self.W), "mask")
         out = self._new(mask.shape)
         check(lib.dim_zoom_mask_with_factor_fwd(self._h, _p(zoom_factor), _p(mask), B, int(b_inv_zoom), _p(out),
-                                                _stream()))
+                                                self._stream()))
         return out
 
     def zoom_flow(self, zoom_factor, flow, flow_weights=None, b_inv_zoom=False):
@@ -208,35 +210,35 @@ class Context:
             _chk(flow_weights, torch.float32, (B, fwc, self.H, self.W), "flow_weights")
             outw = self._new(flow_weights.shape)
         check(lib.dim_zoom_flow_fwd(self._h, _p(zoom_factor), _p(flow), _p(flow_weights), fwc, B, int(b_inv_zoom), _p(out),
-                                    _p(outw), _stream()))
+                                    _p(outw), self._stream()))
         return out, outw
 
     def zoom_depth(self, zoom_factor, depth_observed, depth_rendered):
         B = depth_observed.shape[0]
         zo, zr = self._new(depth_observed.shape), self._new(depth_rendered.shape)
         check(lib.dim_zoom_depth_fwd(self._h, _p(zoom_factor), _p(depth_observed), _p(depth_rendered), B, _p(zo), _p(zr),
-                                     _stream()))
+                                     self._stream()))
         return zo, zr
 
     def zoom_trans(self, zoom_factor, trans, b_inv_zoom):
         B = trans.shape[0]
         _chk(trans, torch.float32, (B, 3), "trans_delta")
         out = self._new((B, 3))
-        check(lib.dim_zoom_trans_fwd(self._h, _p(zoom_factor), _p(trans), B, int(b_inv_zoom), _p(out), _stream()))
+        check(lib.dim_zoom_trans_fwd(self._h, _p(zoom_factor), _p(trans), B, int(b_inv_zoom), _p(out), self._stream()))
         return out
 
     def zoom_trans_backward(self, zoom_factor, out_grad, b_inv_zoom, b_zoom_grad):
         B = out_grad.shape[0]
         out = self._new((B, 3))
         check(lib.dim_zoom_trans_bwd(self._h, _p(zoom_factor), _p(out_grad), B, int(b_inv_zoom), int(b_zoom_grad),
-                                     _p(out), _stream()))
+                                     _p(out), self._stream()))
         return out
 
     def update_mask_box(self, bbox4):
         B = bbox4.shape[0]
         _chk(bbox4, torch.int32, (B, 4), "bbox")
         out = self._new((B, 1, self.H, self.W))
-        check(lib.dim_update_mask_box(self._h, _p(bbox4), B, _p(out), _stream()))
+        check(lib.dim_update_mask_box(self._h, _p(bbox4), B, _p(out), self._stream()))
         return out
 
     # ---------------------------------------------------------------------------- geometry
@@ -246,7 +248,7 @@ class Context:
         _chk(se3, torch.float32, (B, 7), "se3")
         out = self._new((B, 3, 4), torch.float64)
         check(lib.dim_se3_compose(self._h, _p(pose_src), _p(se3), B, farr(T_means, 3, C.c_double),
-                                  farr(T_stds, 3, C.c_double), capi.ROT_COORD[rot_coord.lower()], _p(out), _stream()))
+                                  farr(T_stds, 3, C.c_double), capi.ROT_COORD[rot_coord.lower()], _p(out), self._stream()))
         return out
 
     def flow(self, depth_src, depth_tgt, KT, Kinv):
@@ -257,7 +259,7 @@ class Context:
         _chk(KT, torch.float32, (B, 3, 4), "KT")
         fl, va = self._new((B, 2, self.H, self.W)), self._new(shp)
         check(lib.dim_flow_fwd(self._h, _p(depth_src), _p(depth_tgt), _p(KT), farr(np.asarray(Kinv, np.float32).reshape(9), 9),
-                               B, _p(fl), _p(va), _stream()))
+                               B, _p(fl), _p(va), self._stream()))
         return fl, va
 
     def transform3d(self, point_cloud, rotation, translation, pose_src, T_means, T_stds, rot_coord="model"):
@@ -265,7 +267,7 @@ class Context:
         out = self._new(point_cloud.shape)
         check(lib.dim_transform3d_fwd(self._h, _p(point_cloud), _p(rotation), _p(translation), _p(pose_src), B, N,
                                       farr(T_means, 3), farr(T_stds, 3), capi.ROT_COORD[rot_coord.lower()], _p(out),
-                                      _stream()))
+                                      self._stream()))
         return out
 
     def transform3d_backward(self, out_grad, point_cloud, rotation, translation, pose_src, T_means, T_stds,
@@ -274,7 +276,7 @@ class Context:
         rg, tg = self._new((B, 4)), self._new((B, 3))
         check(lib.dim_transform3d_bwd(self._h, _p(out_grad), _p(point_cloud), _p(rotation), _p(translation),
                                       _p(pose_src), B, N, farr(T_means, 3), farr(T_stds, 3),
-                                      capi.ROT_COORD[rot_coord.lower()], _p(rg), _p(tg), _stream()))
+                                      capi.ROT_COORD[rot_coord.lower()], _p(rg), _p(tg), self._stream()))
         return rg, tg
 
     def train_update(self, cls_idx, src_pose, rot_est, trans_est, tgt_pose, depth_gt_observed, K,
@@ -302,14 +304,14 @@ class Context:
                                    farr(T_stds, 3, C.c_double), capi.ROT_COORD[rot_coord.lower()],
                                    _p(out["image_rendered"]), _p(out["depth_rendered"]), _p(out["mask_rendered"]),
                                    _p(out["src_pose"]), _p(out["rot"]), _p(out["trans"]), _p(out["flow"]),
-                                   _p(out["flow_weights"]), _stream()))
+                                   _p(out["flow_weights"]), self._stream()))
         return out
 
     def transform_image_u8(self, bgr_u8, pixel_means_rgb):
         B = bgr_u8.shape[0]
         _chk(bgr_u8, torch.uint8, (B, self.H, self.W, 3), "bgr_u8")
         out = self._new((B, 3, self.H, self.W))
-        check(lib.dim_transform_image_u8(self._h, _p(bgr_u8), B, farr(pixel_means_rgb, 3, C.c_double), _p(out), _stream()))
+        check(lib.dim_transform_image_u8(self._h, _p(bgr_u8), B, farr(pixel_means_rgb, 3, C.c_double), _p(out), self._stream()))
         return out
 
     # --------------------------------------------------------------------------------- net
@@ -318,12 +320,12 @@ class Context:
         B = zoom_image_observed.shape[0]
         rot, trans = self._new((B, 4)), self._new((B, 3))
         check(lib.dim_net_fwd(self._h, _p(zoom_image_observed), _p(zoom_image_rendered), _p(zoom_mask_observed),
-                              _p(zoom_mask_rendered), B, precision, _p(rot), _p(trans), _stream()))
+                              _p(zoom_mask_rendered), B, precision, _p(rot), _p(trans), self._stream()))
         return rot, trans
 
-    def debug_activation(self, idx, B, lo=False):
-        """bf16 NHWC activation buffer feeding conv layer idx (10 = fc6 input) as float32 numpy
-        [B, rows, cols, C] including the zero border."""
+    def debug_activation(self, idx, B, lo=False, fp16=False):
+        """16-bit NHWC activation buffer feeding conv layer idx (10 = fc6 input) as float32 numpy
+        [B, rows, cols, C] including the zero border (fp16=True: the last pass ran in DIM_PREC_FP16)."""
         g = (C.c_int32 * 8)()
         check(lib.dim_debug_layer_geometry(self._h, idx, g))
         rows, cols, ch = g[0], g[1], g[2]
@@ -331,12 +333,12 @@ class Context:
         buf = np.empty(n, np.uint16)
         torch.cuda.synchronize()
         check(lib.dim_debug_activation(self._h, idx, int(lo), buf.ctypes.data, n * 2))
-        f = (buf.astype(np.uint32) << 16).view(np.float32)
+        f = buf.view(np.float16).astype(np.float32) if fp16 else (buf.astype(np.uint32) << 16).view(np.float32)
         return f.reshape(B, rows, cols, ch), tuple(g)
 
     # ------------------------------------------------------------------------------ refine
     def refine(self, image_observed, cls_idx, pose_init, K, n_iter=4, znear=0.25, zfar=6.0,
-               pixel_means_rgb=(103.939, 116.779, 123.68), precision=capi.PREC_BF16, pose_override=None):
+               pixel_means_rgb=(103.939, 116.779, 123.68), precision=capi.PREC_FP16, pose_override=None):
         """Device-resident fused loop.  image_observed f32[B,3,H,W], cls_idx i32[B], pose_init f64[B,3,4]."""
         B = image_observed.shape[0]
         _chk(image_observed, torch.float32, (B, 3, self.H, self.W), "image_observed")
@@ -351,11 +353,11 @@ class Context:
         check(lib.dim_refine(self._h, _p(image_observed), _p(cls_idx), _p(pose_init), B, n_iter,
                              farr(np.asarray(K, np.float32).reshape(9), 9), znear, zfar,
                              farr(pixel_means_rgb, 3, C.c_double), precision, _p(pose_override), _p(poses), _p(se3),
-                             _p(zf), _p(bbox), _stream()))
+                             _p(zf), _p(bbox), self._stream()))
         return {"poses": poses, "se3": se3, "zoom_factor": zf, "bbox": bbox}
 
     def refine_host(self, image_observed_u8, cls_idx, pose_init, K, n_iter=4, znear=0.25, zfar=6.0,
-                    pixel_means_rgb=(103.939, 116.779, 123.68), precision=capi.PREC_BF16, poses_out=None,
+                    pixel_means_rgb=(103.939, 116.779, 123.68), precision=capi.PREC_FP16, poses_out=None,
                     se3_out=None, sync=True):
         """Host-buffer entry (what a tester loop calls): uint8 BGR HWC images (pinned torch tensors or
         numpy), host poses in / out.  sync=False only enqueues on the current torch stream (outputs must
@@ -370,7 +372,7 @@ class Context:
         fn = lib.dim_refine_host if sync else lib.dim_refine_host_async
         check(fn(self._h, hptr(image_observed_u8), hptr(cls_idx), hptr(pose_init), B, n_iter,
                                   farr(np.asarray(K, np.float32).reshape(9), 9), znear, zfar,
-                 farr(pixel_means_rgb, 3, C.c_double), precision, hptr(poses_out), hptr(se3_out), _stream()))
+                 farr(pixel_means_rgb, 3, C.c_double), precision, hptr(poses_out), hptr(se3_out), self._stream()))
         return poses_out, se3_out
 
 

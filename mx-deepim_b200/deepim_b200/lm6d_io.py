@@ -165,7 +165,7 @@ class LM6DRefine:
 
 
 def evaluate(dataset: LM6DRefine, weights, K, symmetric=("eggbox", "glue", "bowl", "cup"), n_iter=4, max_batch=16, device=0,
-             precision="bf16"):
+             precision="fp16"):
     """Batched pred_eval (deepim/core/tester.py:50-527 without its batch = 1 limit): refine every pair of the image set
     and score ADD (ADI for the symmetric classes).  Returns (evaluate_pose_add result, poses_est [n_iter,M,3,4], poses_gt)."""
     from . import pose_eval

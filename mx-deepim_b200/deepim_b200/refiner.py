@@ -17,11 +17,11 @@ from .context import Context
 
 class PoseRefiner:
     def __init__(self, meshes, weights, K=synth.K_LINEMOD, device=0, max_batch=16, n_iter=4,
-                 pixel_means_rgb=synth.PIXEL_MEANS_RGB, znear=synth.ZNEAR, zfar=synth.ZFAR, precision="bf16",
+                 pixel_means_rgb=synth.PIXEL_MEANS_RGB, znear=synth.ZNEAR, zfar=synth.ZFAR, precision="fp16",
                  n_slots=2):
         self.K = np.asarray(K, np.float32)
         self.n_iter, self.means, self.zn, self.zf = n_iter, np.asarray(pixel_means_rgb, np.float64), znear, zfar
-        self.precision = capi.PREC_BF16X3 if precision == "bf16x3" else capi.PREC_BF16
+        self.precision = capi.precision_id(precision)
         mv = max(len(m.verts) for m in meshes)
         mf = max(len(m.faces) for m in meshes)
         self.max_batch = max_batch

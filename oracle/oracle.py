@@ -280,11 +280,12 @@ def flow(depth_src, depth_tgt, KT, Kinv):
 
 # --------------------------------------------------------------------------------------------- net
 def net_forward(weights, zoom_image_observed, zoom_image_rendered, zoom_mask_observed, zoom_mask_rendered,
-                num_threads=None, return_features=False, emulate_bf16=False):
+                num_threads=None, return_features=False, emulate_bf16=False, emulate_fp16=False):
     """FlowNetS encoder + fc + heads, torch-CPU fp32 (deepIM_flownet.py:53-116, 716-717).
     Returns rot (B,4) raw quaternion, trans (B,3) zoomed translation.
     emulate_bf16=True rounds what the device's throughput mode (DIM_PREC_BF16) stores in bf16 -- the conv / fc6 operand
-    weights and every conv activation -- keeping fp32 accumulation: calibrates that mode's tolerance (tests)."""
+    weights and every conv activation -- keeping fp32 accumulation: calibrates that mode's tolerance (tests).
+    emulate_fp16=True does the same for DIM_PREC_FP16 (IEEE half storage, 11 significant bits)."""
     import torch
     import torch.nn.functional as F
 
@@ -292,7 +293,7 @@ def net_forward(weights, zoom_image_observed, zoom_image_rendered, zoom_mask_obs
         torch.set_num_threads(num_threads)
     from_np = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
     with torch.no_grad():
-        rb = (lambda t: t.bfloat16().float()) if emulate_bf16 else (lambda t: t)
+        rb = (lambda t: t.bfloat16().float()) if emulate_bf16 else ((lambda t: t.half().float()) if emulate_fp16 else (lambda t: t))
         x = rb(torch.cat([from_np(zoom_image_observed) / 255.0, from_np(zoom_image_rendered) / 255.0,
                           from_np(zoom_mask_observed), from_np(zoom_mask_rendered)], dim=1))
         feats = {}
