@@ -177,9 +177,13 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    outs = {}  # persistent result tensors per context: same device addresses every call -> the library replays its CUDA graph
+
     def batch_single(k, p):
         s = sets[k % len(sets)]
-        return ctx.refine(s["img_dev"], s["cls_dev"], s["pose_dev"], K, N_ITER, pixel_means_rgb=means, precision=p)
+        outs[0] = ctx.refine(s["img_dev"], s["cls_dev"], s["pose_dev"], K, N_ITER, pixel_means_rgb=means, precision=p,
+                             out=outs.get(0))
+        return outs[0]
 
     def run_host(n_batches):
         """public host API, `slots` batches in flight: the H2D of batch k+1 overlaps the kernels of batch k"""
@@ -202,7 +206,9 @@ def run_b200(args):
         i = k % len(streams)
         with torch.cuda.stream(streams[i]):
             s = sets[k % len(sets)]
-            return ctxs[i].refine(s["img_dev"], s["cls_dev"], s["pose_dev"], K, N_ITER, pixel_means_rgb=means, precision=p)
+            outs[i] = ctxs[i].refine(s["img_dev"], s["cls_dev"], s["pose_dev"], K, N_ITER, pixel_means_rgb=means, precision=p,
+                                     out=outs.get(i))
+            return outs[i]
 
     def device_pass(p, n_steps, with_clocks):
         """n_steps x SB batches round-robin over the streams; CUDA events on torch's current stream bracket the region,
@@ -237,6 +243,7 @@ def run_b200(args):
     device_pass(prec, W_steps, False)                               # W warm-up steps of the timed configuration
     ms_total, launches, clocks, out = device_pass(prec, K_steps, True)
     poses_last = out["poses"][-1].cpu().numpy()
+    idx_last = (K_steps * SB - 1) % len(sets)
 
     # ---------------- secondary: the bf16 fast mode (fails the 1e-4 rot tolerance -- NOT the headline), same pass shape
     fast = None
@@ -294,7 +301,7 @@ def run_b200(args):
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get("conv_igemm_bytes_per_launch")
         # ADD(-S) sanity of the last batch against the observed pose (blob is asymmetric -> ADD)
-        s_last = sets[(K_steps * SB - 1) % len(sets)]
+        s_last = sets[idx_last]
         def add(p, q, b):
             pts = meshes[b % len(meshes)].verts.astype(np.float64)
             return float(np.linalg.norm((pts @ p[:, :3].T + p[:, 3]) - (pts @ q[:, :3].T + q[:, 3]), axis=1).mean())

@@ -262,6 +262,13 @@ DIM_API int32_t dim_transform_image_u8(dim_ctx *ctx, const uint8_t *bgr_u8, int3
 DIM_API int32_t dim_debug_activation(dim_ctx *ctx, int32_t idx, int32_t lo, void *host_dst,
                                      uint64_t bytes);
 DIM_API int32_t dim_debug_layer_geometry(dim_ctx *ctx, int32_t idx, int32_t *out8);
+/* tuning hooks (tools/conv_lab.py; not part of the drop-in surface).
+ * dim_debug_set_option: run-time kernel-variant switch; key "pair_mask": bit i puts conv layer i (1..9) on the
+ *   cta_group::2 kernel.  Synchronises the device and drops the cached launch descriptors.
+ * dim_debug_layer_profile: enable = 1 records CUDA events around each conv layer of every dim_net_fwd / dim_refine
+ *   iteration; ms10 (nullable) receives the 10 layer times of the LAST forward pass; enable = 0 stops. */
+DIM_API int32_t dim_debug_set_option(dim_ctx *ctx, const char *key, int32_t value);
+DIM_API int32_t dim_debug_layer_profile(dim_ctx *ctx, int32_t enable, float *ms10);
 
 /* Stage profiling of dim_refine with CUDA events on the launching stream (used by bench.py for the
  * live roofline numbers).  enable=1 starts recording; dim_profile_read synchronises the device and

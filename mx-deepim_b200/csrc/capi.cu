@@ -30,7 +30,7 @@ int zoom_factor_from_ren_launch(dim_ctx *, const int *, const float *, int B, co
                                 cudaStream_t);
 int box_mask_launch(dim_ctx *, const int *, int B, float *, cudaStream_t);
 int zoom_fused_launch(dim_ctx *, const float4 *, const float4 *, const float *, const float *, int B, int Hs, int Ws,
-                      int pad, __nv_bfloat16 *, __nv_bfloat16 *, cudaStream_t, int f16);
+                      int pad, __nv_bfloat16 *, __nv_bfloat16 *, cudaStream_t, int f16, const double *means_d);
 int pack_obs4_launch(dim_ctx *, const float *, int B, float4 *, cudaStream_t);
 int transform_u8_obs4_launch(dim_ctx *, const uint8_t *, int B, const double *, float4 *, cudaStream_t);
 int pack_nhwc8_launch(dim_ctx *, const float *, const float *, const float *, const float *, int B, int Hs, int Ws,
@@ -56,6 +56,9 @@ int net_forward(dim_ctx *, int B, int precision, const float *zoom_factor, float
                 cudaStream_t, cudaEvent_t after_conv);
 int net_debug_activation(dim_ctx *, int idx, int lo, void *host_dst, size_t bytes);
 void net_layer_geometry(dim_ctx *, int idx, int *out);
+bool net_graph_safe(dim_ctx *);
+int net_set_option(dim_ctx *, const char *key, int value);
+int net_layer_profile(dim_ctx *, int enable, float *ms10);
 // train.cu
 struct TrainIO {
   const float *zio, *zir, *zmo, *zmr, *zoom_factor, *zflow, *zfw, *zmask_gt, *src_pose, *pc_model, *pc_weights, *pc_observed;
@@ -90,6 +93,14 @@ static int ctx_alloc(dim_ctx *ctx, T **p, size_t n) {
 }  // namespace dim
 
 using namespace dim;
+
+// captured refinement graphs bake in launch dimensions and kernel choices: anything that changes them drops the graphs
+static void drop_graphs(dim_ctx *ctx) {
+  if (ctx->graphs.empty()) return;
+  cudaDeviceSynchronize();
+  for (auto &g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  ctx->graphs.clear();
+}
 
 extern "C" {
 
@@ -163,6 +174,7 @@ DIM_API void dim_ctx_destroy(dim_ctx *ctx) {
   cudaDeviceSynchronize();
   train_destroy(ctx);
   net_destroy(ctx);
+  for (auto &g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
   for (void *p : ctx->owned) cudaFree(p);
   delete ctx;
@@ -172,6 +184,7 @@ DIM_API int32_t dim_mesh_upload(dim_ctx *ctx, int32_t cls, const float *verts, c
                                 const int32_t *faces, int32_t F, const uint8_t *tex, int32_t Th, int32_t Tw) {
   DIM_REQUIRE(ctx && cls >= 0 && cls < ctx->max_classes, "dim_mesh_upload: bad class index");
   DIM_REQUIRE(V > 0 && V <= ctx->max_verts && F > 0 && F <= ctx->max_faces, "dim_mesh_upload: mesh exceeds ctx limits");
+  drop_graphs(ctx);  // the render launch grid follows the largest uploaded mesh
   for (int32_t i = 0; i < 3 * F; ++i) DIM_REQUIRE(faces[i] >= 0 && faces[i] < V, "dim_mesh_upload: face index out of range");
   MeshDev m;
   float *dv, *du; int *df; uint8_t *dt;
@@ -332,6 +345,7 @@ DIM_API int32_t dim_transform3d_bwd(dim_ctx *ctx, const float *og, const float *
 
 DIM_API int32_t dim_net_load(dim_ctx *ctx, const float *const *W, const float *const *Bv) {
   DIM_REQUIRE(ctx && W && Bv, "dim_net_load: NULL argument");
+  drop_graphs(ctx);
   return net_load(ctx, W, Bv);
 }
 
@@ -389,7 +403,7 @@ static int refine_core(dim_ctx *ctx, const float4 *obs4, const int32_t *cls_idx,
     if (int rc = zoom_factor_from_ren_launch(ctx, ctx->bbox_ren, ctx->pose_cur_f32, B, K9, zf_it, bbox_it, ctx->status, st))
       return rc;
     if (int rc = zoom_fused_launch(ctx, obs4, ctx->ren4, zf_it, means_f, B, rows, cols, pad, hi,
-                                   precision == DIM_PREC_BF16X3 ? lo : nullptr, st, precision == DIM_PREC_FP16))
+                                   precision == DIM_PREC_BF16X3 ? lo : nullptr, st, precision == DIM_PREC_FP16, means))
       return rc;
     if (ev) DIM_CHECK(cudaEventRecord(ev[2], st));
     float *se3_it = se3 ? se3 + (size_t)it * B * 7 : ctx->se3_cur;
@@ -402,6 +416,62 @@ static int refine_core(dim_ctx *ctx, const float4 *obs4, const int32_t *cls_idx,
   return 0;
 }
 
+// The 4-iteration chain is ~90 kernel launches whose arguments do not change from call to call when the caller reuses
+// its buffers (PoseRefiner does; so does bench.py).  After one eager run of an argument set the chain is captured into a
+// CUDA graph (stream capture, thread-local mode) and replayed with one cudaGraphLaunch: the data-dependent parts of the
+// loop are already branch-free on the device.  Disabled while stage / layer profiling is on or the context trains.
+static int refine_graphed(dim_ctx *ctx, const float4 *obs4, const int32_t *cls_idx, const double *pose_init, int32_t B,
+                          int32_t n_iter, const float *K9, float zn, float zf, const double *means, int32_t precision,
+                          const double *pose_override, double *poses, float *se3, float *zoom_factor, int32_t *bbox,
+                          cudaStream_t st) {
+  if (!ctx->use_graph || ctx->prof || !net_graph_safe(ctx))
+    return refine_core(ctx, obs4, cls_idx, pose_init, B, n_iter, K9, zn, zf, means, precision, pose_override, poses, se3,
+                       zoom_factor, bbox, st);
+  std::vector<unsigned char> key;
+  auto put = [&key](const void *p, size_t n) { key.insert(key.end(), (const unsigned char *)p, (const unsigned char *)p + n); };
+  const void *ptrs[8] = {obs4, cls_idx, pose_init, pose_override, poses, se3, zoom_factor, bbox};
+  const int32_t ints[3] = {B, n_iter, precision};
+  put(ptrs, sizeof(ptrs)); put(ints, sizeof(ints)); put(K9, 9 * sizeof(float)); put(&zn, sizeof(zn)); put(&zf, sizeof(zf));
+  put(means, 3 * sizeof(double));
+  dim_ctx::RefineGraph *g = nullptr;
+  for (auto &e : ctx->graphs)
+    if (e.key == key) { g = &e; break; }
+  if (g && g->exec) {
+    DIM_CHECK(cudaGraphLaunch(g->exec, st));
+    g_launches += g->kernels;
+    return 0;
+  }
+  if (!g) {  // first sight of this argument set: eager run (also builds tensor maps, sets function attributes)
+    if (ctx->graphs.size() >= 32) ctx->graphs.erase(ctx->graphs.begin());
+    ctx->graphs.push_back(dim_ctx::RefineGraph{key, nullptr, 0});
+    return refine_core(ctx, obs4, cls_idx, pose_init, B, n_iter, K9, zn, zf, means, precision, pose_override, poses, se3,
+                       zoom_factor, bbox, st);
+  }
+  const long long before = g_launches;
+  DIM_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  const int rc = refine_core(ctx, obs4, cls_idx, pose_init, B, n_iter, K9, zn, zf, means, precision, pose_override, poses,
+                             se3, zoom_factor, bbox, st);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+  if (rc != 0 || ce != cudaSuccess || graph == nullptr) {
+    if (graph) cudaGraphDestroy(graph);
+    if (rc == 0) set_error("dim_refine: stream capture failed: %s", cudaGetErrorString(ce));
+    cudaGetLastError();
+    return rc ? rc : 1;
+  }
+  const long long kernels = g_launches - before;
+  g_launches = before;
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess) { set_error("dim_refine: cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); return 1; }
+  g->exec = exec;
+  g->kernels = kernels;
+  DIM_CHECK(cudaGraphLaunch(exec, st));
+  g_launches += kernels;
+  return 0;
+}
+
 DIM_API int32_t dim_refine(dim_ctx *ctx, const float *image_observed, const int32_t *cls_idx, const double *pose_init,
                            int32_t B, int32_t n_iter, const float *K9, float zn, float zf, const double *means,
                            int32_t precision, const double *pose_override, double *poses, float *se3,
@@ -411,8 +481,8 @@ DIM_API int32_t dim_refine(dim_ctx *ctx, const float *image_observed, const int3
   DIM_REQUIRE(n_iter >= 1, "dim_refine: n_iter must be >= 1");
   cudaStream_t st = (cudaStream_t)stream;
   if (int rc = pack_obs4_launch(ctx, image_observed, B, ctx->obs4, st)) return rc;
-  return refine_core(ctx, ctx->obs4, cls_idx, pose_init, B, n_iter, K9, zn, zf, means, precision, pose_override, poses,
-                     se3, zoom_factor, bbox, st);
+  return refine_graphed(ctx, ctx->obs4, cls_idx, pose_init, B, n_iter, K9, zn, zf, means, precision, pose_override, poses,
+                        se3, zoom_factor, bbox, st);
 }
 
 DIM_API int32_t dim_refine_host_async(dim_ctx *ctx, const uint8_t *img_u8, const int32_t *cls_host,
@@ -428,8 +498,8 @@ DIM_API int32_t dim_refine_host_async(dim_ctx *ctx, const uint8_t *img_u8, const
   DIM_CHECK(cudaMemcpyAsync(ctx->cls_dev, cls_host, sizeof(int) * B, cudaMemcpyHostToDevice, st));
   DIM_CHECK(cudaMemcpyAsync(ctx->pose_cur, pose_host, sizeof(double) * B * 12, cudaMemcpyHostToDevice, st));
   if (int rc = transform_u8_obs4_launch(ctx, ctx->image_observed_u8, B, means, ctx->obs4, st)) return rc;
-  if (int rc = refine_core(ctx, ctx->obs4, ctx->cls_dev, ctx->pose_cur, B, n_iter, K9, zn, zf, means, precision,
-                           nullptr, ctx->poses_dev, ctx->se3_hist_dev, nullptr, nullptr, st))
+  if (int rc = refine_graphed(ctx, ctx->obs4, ctx->cls_dev, ctx->pose_cur, B, n_iter, K9, zn, zf, means, precision,
+                              nullptr, ctx->poses_dev, ctx->se3_hist_dev, nullptr, nullptr, st))
     return rc;
   DIM_CHECK(cudaMemcpyAsync(poses_out, ctx->poses_dev, sizeof(double) * (size_t)n_iter * B * 12, cudaMemcpyDeviceToHost, st));
   if (se3_out)
@@ -493,6 +563,7 @@ DIM_API int32_t dim_train_update(dim_ctx *ctx, const int32_t *cls_idx, const flo
 
 DIM_API int32_t dim_profile_enable(dim_ctx *ctx, int32_t enable) {
   DIM_REQUIRE(ctx, "dim_profile_enable: NULL ctx");
+  DIM_CHECK(cudaDeviceSynchronize());
   ctx->prof = enable != 0;
   ctx->prof_used = 0;
   return 0;
@@ -523,6 +594,17 @@ DIM_API int32_t dim_debug_layer_geometry(dim_ctx *ctx, int32_t idx, int32_t *out
   return 0;
 }
 
+
+DIM_API int32_t dim_debug_set_option(dim_ctx *ctx, const char *key, int32_t value) {
+  DIM_REQUIRE(ctx && key, "dim_debug_set_option: NULL argument");
+  drop_graphs(ctx);  // captured graphs hold the old kernel choice
+  if (!strcmp(key, "graph")) { ctx->use_graph = value != 0; return 0; }
+  return net_set_option(ctx, key, value);
+}
+DIM_API int32_t dim_debug_layer_profile(dim_ctx *ctx, int32_t enable, float *ms10) {
+  DIM_REQUIRE(ctx, "dim_debug_layer_profile: NULL ctx");
+  return net_layer_profile(ctx, enable, ms10);
+}
 
 // ADD / ADI (lib/utils/pose_error.py:72-108)
 DIM_API int32_t dim_pose_error(dim_ctx *ctx, const double *poses_est, const double *poses_gt, int32_t M, const double *points,

@@ -101,6 +101,14 @@ struct dim_ctx {
   double *poses_dev = nullptr;  // [8, max_batch, 12]
   float *se3_hist_dev = nullptr;
   dim::NetState *net = nullptr;
+  // CUDA graphs of the fused refinement chain (capi.cu refine_graphed): one executable graph per distinct argument set
+  struct RefineGraph {
+    std::vector<unsigned char> key;  // every launch argument of refine_core, byte for byte
+    cudaGraphExec_t exec = nullptr;  // nullptr: seen once (eager warm-up run), captured on the next call
+    long long kernels = 0;           // kernel nodes (dim_launch_count bookkeeping)
+  };
+  std::vector<RefineGraph> graphs;
+  bool use_graph = true;
   // stage profiling (dim_profile_enable)
   bool prof = false;
   std::vector<cudaEvent_t> prof_events;  // 5 per recorded iteration

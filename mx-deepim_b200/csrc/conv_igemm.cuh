@@ -274,8 +274,10 @@ __device__ __forceinline__ void epilogue_generic64(const uint32_t *r, const Conv
 
 // ---------------------------------------------------------------------------------------------
 // v2: persistent, warp-specialised, double-buffered TMEM accumulators.
-//   grid = min(#tiles, SMs x CTAs/SM); CTA c walks tiles c, c+G, c+2G ... (tile id = ((m*Nn + n)*S + z),
+//   grid = min(#tiles, SMs x CTAs/SM); CTA c walks tiles c, c+G, c+2G ... (tile id = m*Nn + n,
 //   n fastest so CTAs that share an activation tile run side by side and hit it in L2 together).
+//   No split-K / tail splitting: measured slower than leaving the last partial wave to the batches in flight on the
+//   other streams (round-1 experiments: stream-K, tail K-slices + finalize kernel).
 //   The smem ring runs across tile boundaries (the producer is already loading tile t+1 while the
 //   epilogue of tile t drains its accumulator); two TMEM accumulator stages of BLOCK_N columns let the
 //   MMA warp start tile t+1 while warps 2..5 read tile t.
@@ -296,38 +298,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ptx::smem_u32(bar)) : "memory");
 }
 
-// Work items of one CTA of the persistent kernel.  Phase 1: whole tiles round*G + c for the R = T/G full
-// waves (all CTAs walk the K range in lock-step, so the weight tile of a K-block is requested by every SM
-// at about the same time).  Phase 2: the T - R*G tiles of the partial last wave are each cut into `ks`
-// K slices (ks = G / tail tiles) so the tail occupies the whole machine for 1/ks of a tile time instead of
-// a fraction of it for a full tile time; slices leave fp32 partials that conv_tail_finalize_kernel reduces
-// in fixed order (deterministic; layers with fewer tiles than SMs are "all tail" = classic split-K).
-struct WorkIter {
-  int round, R, G, c, KB, base_tile, tail_items, ks, kb_per;
-  bool tail_done;
-  // returns false when done; slice < 0 for a whole tile
-  __device__ __forceinline__ bool next(int &tile, int &kb0, int &kb1, int &slice) {
-    if (round < R) {
-      tile = round * G + c;
-      kb0 = 0; kb1 = KB; slice = -1;
-      ++round;
-      return true;
-    }
-    if (tail_done || c >= tail_items) return false;
-    tail_done = true;
-    const int t = c / ks, z = c - t * ks;
-    tile = base_tile + t;
-    kb0 = z * kb_per;
-    kb1 = min(KB, kb0 + kb_per);
-    slice = (ks > 1) ? z : -1;
-    return true;
-  }
-};
-
 template <int BLOCK_N, int BLOCK_K, int STAGES, bool SPLIT3, bool RESIDENT_B, int KBLOCKS_RES, int EPI = 0>
 __global__ void __launch_bounds__(192) conv_igemm_persistent_kernel(const __grid_constant__ ConvKParams p,
-                                                                    const int total_tiles, const int n_tiles,
-                                                                    const int ks_tail, float *__restrict__ ws) {
+                                                                    const int total_tiles, const int n_tiles) {
   using S = ConvSmem2<BLOCK_N, BLOCK_K, STAGES, SPLIT3, RESIDENT_B, KBLOCKS_RES>;
   constexpr uint32_t LAYOUT = (BLOCK_K == 64) ? 2u : 4u;
   constexpr uint32_t SBO = 8u * BLOCK_K * 2u;
@@ -347,13 +320,7 @@ __global__ void __launch_bounds__(192) conv_igemm_persistent_kernel(const __grid
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(res_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  WorkIter it;
-  it.KB = p.kblocks; it.G = gridDim.x; it.c = blockIdx.x; it.round = 0; it.tail_done = false;
-  it.R = total_tiles / (int)gridDim.x;
-  it.base_tile = it.R * (int)gridDim.x;
-  it.ks = ks_tail;
-  it.tail_items = (total_tiles - it.base_tile) * ks_tail;
-  it.kb_per = (p.kblocks + ks_tail - 1) / ks_tail;
+  const int kb0 = 0, kb1 = p.kblocks;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -389,8 +356,7 @@ __global__ void __launch_bounds__(192) conv_igemm_persistent_kernel(const __grid
       const uint32_t tx = (uint32_t)(p.BW * p.BH * BLOCK_K * 2 + (RESIDENT_B ? 0 : BLOCK_N * BLOCK_K * 2)) * S::NPREC;
       int s = 0;
       uint32_t ph = 0;
-      int tile, kb0, kb1, slice;
-      while (it.next(tile, kb0, kb1, slice)) {
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nt = tile % n_tiles, mt = tile / n_tiles;
         const int col_tile = mt % p.n_col_tiles, row_tile = mt / p.n_col_tiles;
         const int g0 = row_tile * p.BH, ow0 = col_tile * p.BW, n0 = nt * BLOCK_N;
@@ -430,8 +396,7 @@ __global__ void __launch_bounds__(192) conv_igemm_persistent_kernel(const __grid
       }
       int s = 0, as = 0;
       uint32_t ph = 0, aph = 0;
-      int tile, kb0, kb1, slice;
-      while (it.next(tile, kb0, kb1, slice)) {
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         ptx::mbar_wait(&tmem_empty_bar[as], aph ^ 1u);  // epilogue has drained this accumulator stage
         ptx::tc_fence_after();
         const uint32_t tmem_acc = tmem_base + (uint32_t)as * ACC_COLS;
@@ -477,26 +442,11 @@ __global__ void __launch_bounds__(192) conv_igemm_persistent_kernel(const __grid
     uint8_t *stg = epi + (warp - 2) * 4096;
     int as = 0;
     uint32_t aph = 0;
-    int tile, kb0, kb1, slice;
-    while (it.next(tile, kb0, kb1, slice)) {
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       ptx::mbar_wait(&tmem_full_bar[as], aph);
       ptx::tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)as * ACC_COLS;
-      if (slice >= 0) {
-        // K slice of a tail tile: fp32 partial [tail tile][slice][row][BLOCK_N] for conv_tail_finalize_kernel
-        float *dst = ws + ((size_t)((tile - it.base_tile) * it.ks + slice) * 128 + m) * BLOCK_N;
-#pragma unroll 1
-        for (int c = 0; c < BLOCK_N; c += 32) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32(trow + c, r);
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<uint4 *>(dst + c + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-        }
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
-      } else if (EPI == 1) {
+      if (EPI == 1) {
         const int nt = tile % n_tiles, mt = tile / n_tiles;
         const int col_tile = mt % p.n_col_tiles, row_tile = mt / p.n_col_tiles;
         const int g = row_tile * p.BH + bh, ow = col_tile * p.BW + bw, n0 = nt * BLOCK_N;
@@ -553,45 +503,6 @@ __global__ void __launch_bounds__(192) conv_igemm_persistent_kernel(const __grid
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, TMEM_COLS);
   }
-}
-
-// reduces the K slices of the tail tiles: one thread per (tail tile, row, 4 channels)
-static __global__ void __launch_bounds__(256) conv_tail_finalize_kernel(const __grid_constant__ ConvKParams p, const float *ws,
-                                                                 int base_tile, int tail_tiles, int ks, int n_tiles,
-                                                                 int BN, int split3) {
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int cq = BN / 4;
-  if (idx >= (size_t)tail_tiles * 128 * cq) return;
-  const int c4 = (int)(idx % cq) * 4;
-  const int m = (int)((idx / cq) % 128);
-  const int t = (int)(idx / ((size_t)cq * 128));
-  const int tile = base_tile + t;
-  const int nt = tile % n_tiles, mt = tile / n_tiles;
-  const int col_tile = mt % p.n_col_tiles, row_tile = mt / p.n_col_tiles;
-  const int bh = m / p.BW, bw = m - bh * p.BW;
-  const int g = row_tile * p.BH + bh, ow = col_tile * p.BW + bw, n0 = nt * BN;
-  const int n_img = g / p.Hq, oh = g - n_img * p.Hq;
-  if (!((m < p.BW * p.BH) && (n_img < p.Bn) && (oh < p.Ho) && (ow < p.Wo))) return;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int z = 0; z < ks; ++z) {
-    const float4 v = *reinterpret_cast<const float4 *>(ws + ((size_t)(t * ks + z) * 128 + m) * BN + c4);
-    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-  }
-  const int c = n0 + c4;
-  float v[4] = {acc.x + p.bias[c], acc.y + p.bias[c + 1], acc.z + p.bias[c + 2], acc.w + p.bias[c + 3]};
-  const size_t pix = ((size_t)n_img * p.out_Hp + oh + p.out_py) * p.out_Wp + ow + p.out_px;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
-  if (p.f16) {
-    *reinterpret_cast<uint2 *>(p.out_hi + pix * p.Cout + c) = make_uint2(pack2_f16(v[0], v[1]), pack2_f16(v[2], v[3]));
-    return;
-  }
-  const uint32_t h0 = pack2_bf16(v[0], v[1]), h1 = pack2_bf16(v[2], v[3]);
-  *reinterpret_cast<uint2 *>(p.out_hi + pix * p.Cout + c) = make_uint2(h0, h1);
-  if (split3)
-    *reinterpret_cast<uint2 *>(p.out_lo + pix * p.Cout + c) =
-        make_uint2(pack2_bf16(v[0] - __uint_as_float(h0 << 16), v[1] - __uint_as_float(h0 & 0xFFFF0000u)),
-                   pack2_bf16(v[2] - __uint_as_float(h1 << 16), v[3] - __uint_as_float(h1 & 0xFFFF0000u)));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -721,7 +632,8 @@ __global__ void __launch_bounds__(192) conv1_strip_kernel(const __grid_constant_
             const uint32_t b_hi = ptx::smem_u32(res + (dh * 4 + dw) * S::B_BYTES);
             const uint32_t b_lo = ptx::smem_u32(res + (16 + dh * 4 + dw) * S::B_BYTES);
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {  // 16 channels = 2 chunks per UMMA
+            for (int k = 0; k < 2; ++k) {  // 16 channels = 2 chunks per UMMA: k = 0 -> row parity 0, k = 1 -> row parity 1
+              if (dh == 3 && k == 1) continue;  // kh = 2*3 + 1 = 7 lies outside the 7x7 filter: all-zero weights, skip the MMA
               const uint32_t acc = (dh | dw | k) ? 1u : 0u;
               const uint64_t da = umma_desc_interleave(a_hi + dw * 16 + k * 2 * LBO, LBO, 128);
               const uint64_t db = ptx::umma_desc(b_hi + k * 32, 512, 4u);
@@ -761,6 +673,160 @@ __global__ void __launch_bounds__(192) conv1_strip_kernel(const __grid_constant_
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);  // accumulator stage is free again
+      epilogue_store64<SPLIT3>(r, bias_s, p.slope, epi + (warp - 2) * 4096, p.out_hi, p.out_lo, my_off, valid, lane, p.f16 != 0);
+      if (++as == 2) { as = 0; aph ^= 1u; }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// conv1, rolling-strip variant.  The strip kernel above gives every output row its own four input strips, so each
+// strip travels L2 -> shared memory four times (once per filter row dh) -- 0.68 GB per launch against 0.16 GB of
+// input.  Here a CTA owns one column tile and a CONTIGUOUS run of output rows [g_lo, g_hi) and walks down it: output
+// row g uses strips g .. g+3, so moving to row g+1 needs ONE new strip; the other three are still in the ring.
+// Strip s of the chunk (input row g_lo + s) lives in ring slot s % STAGES from its TMA fill until the MMAs of output
+// row s (its last user) have completed (tcgen05.commit -> empty barrier).  L2 -> SM traffic and the TMA writes into
+// shared memory drop 4x (plus a 3-row halo per chunk); MMA sequence, accumulators, epilogue are those of the strip
+// kernel.  One CTA per SM (64 KB resident weights + an 8-deep ring), grid = column tiles x chunks.
+template <int STAGES, bool SPLIT3>
+__global__ void __launch_bounds__(192) conv1_roll_kernel(const __grid_constant__ ConvKParams p, const int rows_total,
+                                                         const int rows_per_chunk, const int chunks_per_col,
+                                                         const int strip_bytes /*per precision, multiple of 128*/) {
+  constexpr uint32_t ACC_COLS = 64, TMEM_COLS = 128;
+  constexpr int NPREC = SPLIT3 ? 2 : 1;
+  constexpr int B_BYTES = 64 * 32 * 2, RES_BYTES = 16 * B_BYTES * NPREC, EPI_BYTES = 4 * 4096 + 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t *res = smem;
+  uint8_t *ring = smem + RES_BYTES;
+  const int stage_bytes = strip_bytes * NPREC;
+  uint8_t *epi = ring + STAGES * stage_bytes;
+  float *bias_s = reinterpret_cast<float *>(epi + 4 * 4096);
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(epi + EPI_BYTES);
+  uint64_t *empty_bar = full_bar + STAGES;
+  uint64_t *tmem_full_bar = empty_bar + STAGES;
+  uint64_t *tmem_empty_bar = tmem_full_bar + 2;
+  uint64_t *res_bar = tmem_empty_bar + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(res_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int R = p.BW + 3;
+  const uint32_t LBO = (uint32_t)R * 16u;
+  const int ct = blockIdx.x / chunks_per_col, ck = blockIdx.x - ct * chunks_per_col;
+  const int g_lo = ck * rows_per_chunk;
+  const int g_hi = min(rows_total, g_lo + rows_per_chunk);
+  const int n_rows = max(0, g_hi - g_lo);          // output rows (tiles) of this CTA
+  const int n_strips = n_rows > 0 ? n_rows + 3 : 0;
+  const int ow0 = ct * p.BW;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full_bar[a], 1);
+      ptx::mbar_init(&tmem_empty_bar[a], 4);
+    }
+    ptx::mbar_init(res_bar, 1);
+    ptx::fence_barrier_init();
+    ptx::prefetch_tmap(&p.b_map);
+    ptx::prefetch_tmap(&p.a_map[0]);
+  }
+  if (threadIdx.x < 64) bias_s[threadIdx.x] = p.bias[threadIdx.x];
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0 && n_rows > 0) {
+      ptx::mbar_expect_tx(res_bar, (uint32_t)RES_BYTES);
+      for (int kb = 0; kb < 16; ++kb) {
+        ptx::tma_load_2d(res + kb * B_BYTES, &p.b_map, res_bar, kb * 32, 0);
+        if (SPLIT3) ptx::tma_load_2d(res + (16 + kb) * B_BYTES, &p.b_lo_map, res_bar, kb * 32, 0);
+      }
+      const uint32_t tx = (uint32_t)(R * 64) * NPREC;
+      for (int s = 0; s < n_strips; ++s) {
+        const int slot = s % STAGES;
+        ptx::mbar_wait(&empty_bar[slot], (((uint32_t)(s / STAGES)) & 1u) ^ 1u);
+        uint8_t *st = ring + slot * stage_bytes;
+        ptx::mbar_expect_tx(&full_bar[slot], tx);
+        tma_load_4d(st, &p.a_map[0], &full_bar[slot], 0, ow0, 0, g_lo + s);
+        if (SPLIT3) tma_load_4d(st + strip_bytes, &p.a_lo_map[0], &full_bar[slot], 0, ow0, 0, g_lo + s);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_rows > 0) {
+      ptx::mbar_wait(res_bar, 0);
+      ptx::tc_fence_after();
+      int as = 0, waited = 0;
+      uint32_t aph = 0;
+      for (int t = 0; t < n_rows; ++t) {
+        ptx::mbar_wait(&tmem_empty_bar[as], aph ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + (uint32_t)as * ACC_COLS;
+        for (int dh = 0; dh < 4; ++dh) {
+          const int s = t + dh, slot = s % STAGES;
+          if (s >= waited) {  // first use of this strip
+            ptx::mbar_wait(&full_bar[slot], ((uint32_t)(s / STAGES)) & 1u);
+            ptx::tc_fence_after();
+            waited = s + 1;
+          }
+          const uint32_t a_hi = ptx::smem_u32(ring + slot * stage_bytes);
+          const uint32_t a_lo = a_hi + (uint32_t)strip_bytes;
+#pragma unroll
+          for (int dw = 0; dw < 4; ++dw) {
+            const uint32_t b_hi = ptx::smem_u32(res + (dh * 4 + dw) * B_BYTES);
+            const uint32_t b_lo = ptx::smem_u32(res + (16 + dh * 4 + dw) * B_BYTES);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              if (dh == 3 && k == 1) continue;  // kh = 7: outside the 7x7 filter, all-zero weights
+              const uint32_t acc = (dh | dw | k) ? 1u : 0u;
+              const uint64_t da = umma_desc_interleave(a_hi + dw * 16 + k * 2 * LBO, LBO, 128);
+              const uint64_t db = ptx::umma_desc(b_hi + k * 32, 512, 4u);
+              ptx::umma_f16(tmem_acc, da, db, p.idesc, acc);
+              if (SPLIT3) {
+                const uint64_t dal = umma_desc_interleave(a_lo + dw * 16 + k * 2 * LBO, LBO, 128);
+                const uint64_t dbl = ptx::umma_desc(b_lo + k * 32, 512, 4u);
+                ptx::umma_f16(tmem_acc, dal, db, p.idesc, 1u);
+                ptx::umma_f16(tmem_acc, da, dbl, p.idesc, 1u);
+              }
+            }
+          }
+        }
+        ptx::umma_commit(&empty_bar[t % STAGES]);  // strip t served output rows t-3 .. t: its slot may be refilled
+        ptx::umma_commit(&tmem_full_bar[as]);
+        if (++as == 2) { as = 0; aph ^= 1u; }
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int m = quad * 32 + lane;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int t = 0; t < n_rows; ++t) {
+      const int g = g_lo + t;
+      const int ow = ow0 + m;
+      const int n_img = g / p.Hq, oh = g - n_img * p.Hq;
+      const bool valid = (m < p.BW) && (n_img < p.Bn) && (oh < p.Ho) && (ow < p.Wo);
+      ptx::mbar_wait(&tmem_full_bar[as], aph);
+      ptx::tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)as * ACC_COLS;
+      const long long my_off = (((long long)n_img * p.out_Hp + oh + p.out_py) * p.out_Wp + ow + p.out_px) * 64;
+      uint32_t r[64];
+      ptx::tmem_ld_32x32(trow, r);
+      ptx::tmem_ld_32x32(trow + 32, r + 32);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
       epilogue_store64<SPLIT3>(r, bias_s, p.slope, epi + (warp - 2) * 4096, p.out_hi, p.out_lo, my_off, valid, lane, p.f16 != 0);
       if (++as == 2) { as = 0; aph ^= 1u; }
     }

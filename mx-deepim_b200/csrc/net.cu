@@ -17,15 +17,6 @@
 namespace dim {
 
 // --------------------------------------------------------------------------------- geometry
-static bool use_pair_kernel() {
-  static int v = -1;
-  if (v < 0) {
-    const char *e = getenv("DIM_CONV_PAIR");  // 1 enables the cta_group::2 kernel (A/B testing)
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v != 0;
-}
-
 static void build_geometry(NetState *ns, int H, int W) {
   int h = H, w = W;
   for (int i = 0; i < 10; ++i) {
@@ -70,43 +61,28 @@ static void build_geometry(NetState *ns, int H, int W) {
     }
     g.kblocks = g.KH * g.KW * (g.Ceff / g.BLOCK_K);
     g.occ = (i == 0) ? 2 : 1;
-    g.pair = (i >= 1 && use_pair_kernel()) ? 1 : 0;
-    // opt-in experiment for the next round (not yet measured): conv2 only on the CTA-pair kernel with a 3-stage ring so that
-    // two pairs are resident per SM pair (conv2 is bound by L2 -> SM operand traffic; a pair fetches each weight tile once)
-    static const bool conv2_pair = [] { const char *e = getenv("DIM_CONV2_PAIR"); return e && e[0] == '1'; }();
-    if (i == 1 && conv2_pair) g.pair = 2;
+    g.pair = 0;  // per-layer kernel choice is applied per batch size in effective_geom() (NetState::pair_mask)
     h = g.Ho; w = g.Wo;
   }
 }
 
-// Layers whose 128 x 256 tile count cannot fill the machine at this batch size run 128 x 128 tiles with
-// two CTAs per SM instead (twice the tiles, no or less split-K).
+// Kernel variant per layer.  bit i of NetState::pair_mask puts conv layer i (1..9) on the CTA-pair kernel
+// (cta_group::2, 256 x BLOCK_N tiles: each CTA stages its 128 activation rows and HALF of the weight tile, so the
+// shared-memory traffic per MMA drops from A + B to A + B/2 -- what bounds the N = 128 layer conv2).
 static LayerGeom effective_geom(const NetState *ns, int i, int B) {
   LayerGeom g = ns->g[i];
-  static const bool small_n = [] { const char *e = getenv("DIM_CONV_SMALL_BN128"); return e && e[0] == '1'; }();  // measured slower: opt-in
-  if (i >= 1 && g.BLOCK_N == 256 && !g.pair && small_n) {
-    const int tiles256 = cdiv(B * g.Hq, g.BH) * g.n_col_tiles * (g.Cout / 256);
-    if (tiles256 < ns->num_sms) { g.BLOCK_N = 128; g.occ = 2; }
-  }
-  if (i >= 1 && g.BLOCK_N == 128 && ns->g[i].BLOCK_N == 128) g.occ = 2;  // conv2
+  (void)B;
+  if (i >= 1 && ((ns->pair_mask >> i) & 1)) g.pair = (g.BLOCK_N == 128) ? 2 : 1;  // 2: 3-stage ring, two pairs per SM pair
+  if (i >= 1 && g.BLOCK_N == 128 && !g.pair) g.occ = 2;  // conv2 on the 1-CTA kernel: two CTAs per SM
   return g;
 }
 
-// split-K factor: maximise the fill of the last wave of the persistent grid (capacity = SMs x CTAs/SM)
-// with a small penalty per extra slice (fp32 partial traffic); every slice keeps >= 8 K-blocks.
-static bool use_tail_split() {
-  // opt-in: helps a single batch in flight by ~1%, costs ~5% when two batches overlap (the other stream
-  // already fills the tail-wave bubbles and the extra finalize launches / fp32 partials only add traffic)
-  static const bool v = [] { const char *e = getenv("DIM_CONV_TAILSPLIT"); return e && e[0] == '1'; }();
-  return v;
-}
-
+// split-K factor of the CTA-pair kernel (the 1-CTA persistent kernel never splits: see conv_igemm.cuh)
 static int choose_ksplit(const NetState *ns, const LayerGeom &g, int B) {
-  if (!g.pair) return 1;  // the persistent kernel splits only its tail tiles (see launch_conv2)
-  int tiles = cdiv(B * g.Hq, g.BH) * g.n_col_tiles * (g.Cout / g.BLOCK_N);
-  int cap = ns->num_sms * g.occ;
-  if (g.pair) { tiles = cdiv(cdiv(B * g.Hq, g.BH) * g.n_col_tiles, 2) * (g.Cout / g.BLOCK_N); cap = ns->num_sms / 2; }
-  if (tiles >= 2 * cap || g.kblocks < 16 || g.BLOCK_K == 32) return 1;  // conv1 keeps its weights resident: no split
+  if (!g.pair) return 1;
+  const int tiles = cdiv(cdiv(B * g.Hq, g.BH) * g.n_col_tiles, 2) * (g.Cout / g.BLOCK_N);
+  const int cap = ns->num_sms / 2;
+  if (tiles >= 2 * cap || g.kblocks < 16) return 1;
   int best = 1;
   double best_score = -1.0;
   for (int ks = 1; ks <= 8; ++ks) {
@@ -402,7 +378,9 @@ int net_create(dim_ctx *ctx) {
     if (int rc = dev_alloc(ctx, &ns->act_lo[i], per * ctx->max_batch, true)) return rc;
   }
   ns->net_ok = ns->act_elems_per_image[10] == (size_t)FC6_K;  // fc6 is 81920 -> 256: needs 480x640
-  size_t pmax = 0;
+  size_t pmax = 0;  // split-K partials of the CTA-pair kernel: sized for every layer on it (the choice may change at run time)
+  const int mask_now = ns->pair_mask;
+  ns->pair_mask = 0x3FE;
   for (int B = 1; B <= ctx->max_batch; ++B)
     for (int i = 0; i < 10; ++i) {
       int ks = choose_ksplit(ns, effective_geom(ns, i, B), B);
@@ -411,15 +389,19 @@ int net_create(dim_ctx *ctx) {
         pmax = e > pmax ? e : pmax;
       }
     }
+  ns->pair_mask = mask_now;
   ns->conv_partial_elems = pmax;
   if (pmax)
     if (int rc = dev_alloc(ctx, &ns->conv_partial, pmax, false)) return rc;
   if (int rc = dev_alloc(ctx, &ns->fc6_partial, (size_t)FC6_SPLITS * ctx->max_batch * 256, true)) return rc;
-  if (int rc = dev_alloc(ctx, &ns->tail_ws, (size_t)2 * ns->num_sms * 128 * 256, false)) return rc;
   return 0;
 }
 
 void net_destroy(dim_ctx *ctx) {
+  if (ctx->net && ctx->net->layer_events) {
+    for (int i = 0; i < 11; ++i) cudaEventDestroy(ctx->net->layer_events[i]);
+    delete[] ctx->net->layer_events;
+  }
   delete ctx->net;
   ctx->net = nullptr;
 }
@@ -549,27 +531,8 @@ static int launch_conv2(NetState *ns, const ConvKParams &kp, int total_tiles, in
     attr_set = true;
   }
   const int grid = total_tiles < cap ? total_tiles : cap;
-  // tail tiles (partial last wave, or the whole layer when it has fewer tiles than CTAs) are cut into
-  // ks K slices so that they fill the machine; every slice keeps >= 4 K-blocks
-  const int tail = (total_tiles < cap) ? total_tiles : total_tiles % cap;
-  int ks = 1;
-  if (use_tail_split() && tail > 0) {
-    ks = cap / tail;
-    if (ks > 8) ks = 8;
-    while (ks > 1 && kp.kblocks / ks < 4) --ks;
-    while (ks > 1 && (ks - 1) * cdiv(kp.kblocks, ks) >= kp.kblocks) --ks;
-  }
-  const int launch_grid = (ks > 1 && total_tiles < cap) ? tail * ks : grid;  // all-tail layers: one CTA per slice
-  conv_igemm_persistent_kernel<BN, BK, ST, S3, RES, KRES><<<launch_grid, 192, S::TOTAL, st>>>(kp, total_tiles, n_tiles, ks,
-                                                                                                ns->tail_ws);
+  conv_igemm_persistent_kernel<BN, BK, ST, S3, RES, KRES><<<grid, 192, S::TOTAL, st>>>(kp, total_tiles, n_tiles);
   DIM_LAUNCH_CHECK();
-  if (ks > 1) {
-    const int base_tile = (total_tiles / launch_grid) * launch_grid;
-    const size_t n = (size_t)tail * 128 * (BN / 4);
-    conv_tail_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(kp, ns->tail_ws, base_tile, tail, ks, n_tiles, BN,
-                                                                           S3 ? 1 : 0);
-    DIM_LAUNCH_CHECK();
-  }
   return 0;
 }
 
@@ -617,6 +580,7 @@ int net_forward(dim_ctx *ctx, int B, int precision, const float *zoom_factor, fl
     if (int rc = train_refresh_lo(ctx, st)) return rc;
   if (f16 && ns->f16_stale)
     if (int rc = net_refresh_f16(ctx, st)) return rc;
+  if (ns->layer_events) DIM_CHECK(cudaEventRecord(ns->layer_events[0], st));
   for (int i = 0; i < 10; ++i) {
     const LayerGeom &g = tm.g[i];
     const ConvKParams &kp = tm.kp[i];
@@ -624,7 +588,34 @@ int net_forward(dim_ctx *ctx, int B, int precision, const float *zoom_factor, fl
     const int total_tiles = cdiv(B * g.Hq, g.BH) * g.n_col_tiles * n_tiles * kp.ksplit;
     const int sms = ns->num_sms;
     int rc;
-    if (i == 0) {  // conv1: strip kernel (one TMA strip per filter row, shifted un-swizzled descriptors)
+    if (i == 0 && ns->conv1_roll) {
+      // conv1, rolling strips: a CTA walks down a run of output rows of one column tile, one new input strip per row
+      const int rows_total = B * g.Hq;
+      int chunks = sms / g.n_col_tiles;
+      if (chunks > cdiv(rows_total, 16)) chunks = cdiv(rows_total, 16);  // keep the 3-row halo below ~20 %
+      if (chunks < 1) chunks = 1;
+      const int rpc = cdiv(rows_total, chunks);
+      chunks = cdiv(rows_total, rpc);
+      const int strip_bytes = cdiv((g.BW + 3) * 64, 128) * 128;
+      const int grid = g.n_col_tiles * chunks;
+      if (s3) {
+        constexpr int ST = 5;
+        const int smem_bytes = 2 * 16 * 4096 + ST * 2 * strip_bytes + (4 * 4096 + 256) + 1024 + 512;
+        DIM_REQUIRE(smem_bytes <= 227 * 1024, "conv1 (bf16x3): image too wide for the rolling-strip ring");
+        static int set1 = 0;
+        if (set1 < smem_bytes) { DIM_CHECK(cudaFuncSetAttribute(conv1_roll_kernel<ST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); set1 = smem_bytes; }
+        conv1_roll_kernel<ST, true><<<grid, 192, smem_bytes, st>>>(kp, rows_total, rpc, chunks, strip_bytes);
+      } else {
+        constexpr int ST = 8;
+        const int smem_bytes = 16 * 4096 + ST * strip_bytes + (4 * 4096 + 256) + 1024 + 512;
+        static int set0 = 0;
+        if (set0 < smem_bytes) { DIM_CHECK(cudaFuncSetAttribute(conv1_roll_kernel<ST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); set0 = smem_bytes; }
+        conv1_roll_kernel<ST, false><<<grid, 192, smem_bytes, st>>>(kp, rows_total, rpc, chunks, strip_bytes);
+      }
+      DIM_LAUNCH_CHECK();
+      rc = 0;
+    }
+    else if (i == 0) {  // conv1: strip kernel (one TMA strip per filter row, shifted un-swizzled descriptors)
       const int tiles1 = B * g.Hq * g.n_col_tiles;
       if (s3) {
         using S1 = Conv1Smem<4, true>;
@@ -658,6 +649,7 @@ int net_forward(dim_ctx *ctx, int B, int precision, const float *zoom_factor, fl
       rc = s3 ? launch_conv2<256, 64, 2, true, false, 0>(ns, kp, total_tiles, n_tiles, sms, st)
               : launch_conv2<256, 64, 4, false, false, 0>(ns, kp, total_tiles, n_tiles, sms, st);
     if (rc) return rc;
+    if (ns->layer_events && i < 9) DIM_CHECK(cudaEventRecord(ns->layer_events[i + 1], st));
     if (kp.ksplit > 1) {
       const int npix = B * g.Ho * g.Wo;
       const size_t n4 = (size_t)npix * g.Cout / 4;
@@ -667,6 +659,7 @@ int net_forward(dim_ctx *ctx, int B, int precision, const float *zoom_factor, fl
       DIM_LAUNCH_CHECK();
     }
   }
+  if (ns->layer_events) DIM_CHECK(cudaEventRecord(ns->layer_events[10], st));
   if (after_conv) DIM_CHECK(cudaEventRecord(after_conv, st));
   if (s3)
     fc6_mma_kernel<true><<<FC6_SPLITS, 256, 0, st>>>(ns->act_hi[10], ns->act_lo[10], ns->fc6_w_hi, ns->fc6_w_lo, B,
@@ -682,6 +675,44 @@ int net_forward(dim_ctx *ctx, int B, int precision, const float *zoom_factor, fl
                                  ns->rot_b, ns->trans_w, ns->trans_b, zoom_factor, rot_out, trans_out, se3_out, ns->save_h6,
                                  ns->save_h7);
   DIM_LAUNCH_CHECK();
+  return 0;
+}
+
+// the refinement chain may be captured into a CUDA graph only when nothing host-dependent hangs on the forward pass
+bool net_graph_safe(dim_ctx *ctx) {
+  NetState *ns = ctx->net;
+  return ns && ns->loaded && !ns->layer_events && !ns->train_aliased;
+}
+
+// tuning hook (tools/conv_lab.py): kernel-variant switches at run time; cached launch descriptors are rebuilt
+int net_set_option(dim_ctx *ctx, const char *key, int value) {
+  NetState *ns = ctx->net;
+  DIM_REQUIRE(ns != nullptr, "net not created");
+  if (!strcmp(key, "pair_mask")) ns->pair_mask = value & 0x3FE;
+  else if (!strcmp(key, "conv1_roll")) ns->conv1_roll = value != 0;
+  else { set_error("dim_debug_set_option: unknown key '%s'", key); return 2; }
+  DIM_CHECK(cudaDeviceSynchronize());
+  ns->maps.clear();
+  return 0;
+}
+
+// tuning hook: per-layer device times of the LAST net_forward (11 events: before conv1, after each of the 10 layers)
+int net_layer_profile(dim_ctx *ctx, int enable, float *ms10) {
+  NetState *ns = ctx->net;
+  DIM_REQUIRE(ns != nullptr, "net not created");
+  if (enable && !ns->layer_events) {
+    ns->layer_events = new cudaEvent_t[11];
+    for (int i = 0; i < 11; ++i) DIM_CHECK(cudaEventCreate(&ns->layer_events[i]));
+  }
+  if (ms10 && ns->layer_events) {
+    DIM_CHECK(cudaDeviceSynchronize());
+    for (int i = 0; i < 10; ++i) DIM_CHECK(cudaEventElapsedTime(&ms10[i], ns->layer_events[i], ns->layer_events[i + 1]));
+  }
+  if (!enable && ns->layer_events) {
+    for (int i = 0; i < 11; ++i) cudaEventDestroy(ns->layer_events[i]);
+    delete[] ns->layer_events;
+    ns->layer_events = nullptr;
+  }
   return 0;
 }
 

@@ -52,7 +52,9 @@ struct NetState {
   float *fc6_partial = nullptr;  // [FC6_SPLITS][max_batch][256]
   float *conv_partial = nullptr;
   size_t conv_partial_elems = 0;
-  float *tail_ws = nullptr;  // K-slice partials of the tail tiles: [<= 2*SMs slots][128][256] fp32
+  bool conv1_roll = false;   // conv1 on the rolling-strip kernel (conv1_roll_kernel) instead of the per-row strip kernel
+  int pair_mask = 0;         // bit i: conv layer i runs on the CTA-pair (cta_group::2) kernel (effective_geom in net.cu)
+  cudaEvent_t *layer_events = nullptr;  // tuning hook: 11 events around the conv layers of the last forward
   bool loaded = false, net_ok = false;
   float *save_h6 = nullptr, *save_h7 = nullptr;
   cudaEvent_t repack_done = nullptr;  // training: the operand packs are refreshed on an internal stream after an update;

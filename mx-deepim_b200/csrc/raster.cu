@@ -17,7 +17,9 @@
 //                      texel -> writes RGB-mean / depth / mask (/ BGR) with 16-byte stores, resets
 //                      the visibility buffer, reduces the mask bbox.
 // Algorithmic HBM bytes per instance: 16 B/px written (RGB + depth); this version also
-// writes the mask plane (4 B/px) and touches the visibility buffer only inside the vertex box.
+// writes the mask plane (4 B/px) and touches the visibility buffer only inside the vertex box.  In the fused
+// refinement loop the only output is the pixel-interleaved (R,G,B,mask) image and it is written only inside the
+// projected-vertex box: the zoom kernel knows the box and substitutes the background constant outside it.
 #include "common.cuh"
 
 namespace dim {
@@ -41,6 +43,8 @@ struct RasterParams {
   int trunc_u8;
   float *out_image, *out_depth, *out_mask, *out_bgr;
   float4 *out_ren4;  // [B,H,W] (R-mean, G-mean, B-mean, mask): the fused loop's layout
+  int ren4_box_only; // 1: out_ren4 is written only inside the projected-vertex box (vbox); every pixel outside it is background
+                     //    by construction and the only consumer (zoom_fused_nhwc8_kernel) substitutes the constant itself
   // lit renderer (render_py_light_modelnet_multi.py): per-instance light position / intensity, a0 + a1 * brightness
   int lit;
   const float *light_pos, *light_int;
@@ -264,7 +268,8 @@ __global__ void __launch_bounds__(256) raster_resolve_kernel(RasterParams p) {
   for (int k = 0; k < 4; ++k) raw[k][0] = raw[k][1] = raw[k][2] = 0.f;
 
   int mx0 = 0x7fffffff, mx1 = -1, my0 = 0x7fffffff, my1 = -1;
-  if (in_range && i >= vy0 && i <= vy1 && j4 + 3 >= vx0 && j4 <= vx1) {
+  const bool in_box = in_range && i >= vy0 && i <= vy1 && j4 + 3 >= vx0 && j4 <= vx1;
+  if (in_box) {
     ulonglong2 k01 = *reinterpret_cast<const ulonglong2 *>(vis);
     ulonglong2 k23 = *reinterpret_cast<const ulonglong2 *>(vis + 2);
     unsigned long long keys[4] = {k01.x, k01.y, k23.x, k23.y};
@@ -363,7 +368,7 @@ __global__ void __launch_bounds__(256) raster_resolve_kernel(RasterParams p) {
       *reinterpret_cast<float4 *>(img + P + o) = make_float4(g[0], g[1], g[2], g[3]);
       *reinterpret_cast<float4 *>(img + 2 * P + o) = make_float4(bl[0], bl[1], bl[2], bl[3]);
     }
-    if (p.out_ren4) {
+    if (p.out_ren4 && (in_box || !p.ren4_box_only)) {
       float4 *o4 = p.out_ren4 + (size_t)b * P + o;
 #pragma unroll
       for (int k = 0; k < 4; ++k) o4[k] = make_float4(r[k], g[k], bl[k], mk[k]);
@@ -419,6 +424,7 @@ int render_launch(dim_ctx *ctx, const int *cls, const float *pose, int B, const 
   p.trunc_u8 = trunc_u8;
   p.out_image = out_image; p.out_depth = out_depth; p.out_mask = out_mask; p.out_bgr = out_bgr;
   p.out_ren4 = out_ren4;
+  p.ren4_box_only = (out_ren4 && !out_image && !out_depth && !out_mask && !out_bgr) ? 1 : 0;
   p.lit = lit ? 1 : 0;
   p.light_pos = lit ? lit->light_pos : nullptr; p.light_int = lit ? lit->light_int : nullptr;
   p.a0 = lit ? lit->a0 : 0.f; p.a1 = lit ? lit->a1 : 0.f;

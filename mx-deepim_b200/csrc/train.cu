@@ -932,7 +932,7 @@ static int launch_generic(const ConvKParams &kp, int total_tiles, int n_tiles, i
     attr_set = true;
   }
   const int grid = total_tiles < cap ? total_tiles : cap;
-  conv_igemm_persistent_kernel<BN, 64, ST, false, false, 0, 1><<<grid, 192, S::TOTAL, st>>>(kp, total_tiles, n_tiles, 1, nullptr);
+  conv_igemm_persistent_kernel<BN, 64, ST, false, false, 0, 1><<<grid, 192, S::TOTAL, st>>>(kp, total_tiles, n_tiles);
   DIM_LAUNCH_CHECK();
   return 0;
 }

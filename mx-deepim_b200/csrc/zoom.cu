@@ -301,6 +301,8 @@ struct FusedZoomParams {
   const float4 *obs4;   // [B,H,W,4] observed RGB-mean (w unused)
   const float4 *ren4;   // [B,H,W,4] rendered RGB-mean, w = mask_rendered (0/1)
   const int *bbox8;     // observed box = bb[0..3] (inclusive)
+  const int *vbox;      // [B,4] x0,x1,y0,y1: ren4 is only valid inside this box (rasteriser), background outside; nullable
+  float bg[3];          // background of the rendered image: (float)(0.0 - mean)
   const float *zoom_factor;
   int H, W, Hs, Ws, pad;  // conv1 input is space-to-depth: [B,Hs,Ws,(ph,pw,c)=32]
   float mean[3];
@@ -320,8 +322,16 @@ __device__ __forceinline__ void zoom_fused_pixel(const FusedZoomParams &p, int b
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   const float4 O00 = k00 ? __ldg(p.obs4 + base + o) : z4, O01 = k01 ? __ldg(p.obs4 + base + o + 1) : z4;
   const float4 O10 = k10 ? __ldg(p.obs4 + base + o + p.W) : z4, O11 = k11 ? __ldg(p.obs4 + base + o + p.W + 1) : z4;
-  const float4 R00 = k00 ? __ldg(p.ren4 + base + o) : z4, R01 = k01 ? __ldg(p.ren4 + base + o + 1) : z4;
-  const float4 R10 = k10 ? __ldg(p.ren4 + base + o + p.W) : z4, R11 = k11 ? __ldg(p.ren4 + base + o + p.W + 1) : z4;
+  // rendered taps: outside the rasteriser's vertex box the image is background by construction (and ren4 is not written there)
+  int vx0 = 0, vx1 = p.W, vy0 = 0, vy1 = p.H;
+  if (p.vbox) { vx0 = p.vbox[4 * b]; vx1 = p.vbox[4 * b + 1]; vy0 = p.vbox[4 * b + 2]; vy1 = p.vbox[4 * b + 3]; }
+  const float4 bg4 = make_float4(p.bg[0], p.bg[1], p.bg[2], 0.f);
+  const bool vxa = t.x0 >= vx0 && t.x0 <= vx1, vxb = t.x0 + 1 >= vx0 && t.x0 + 1 <= vx1;
+  const bool vya = t.y0 >= vy0 && t.y0 <= vy1, vyb = t.y0 + 1 >= vy0 && t.y0 + 1 <= vy1;
+  const float4 R00 = k00 ? ((vya && vxa) ? __ldg(p.ren4 + base + o) : bg4) : z4;
+  const float4 R01 = k01 ? ((vya && vxb) ? __ldg(p.ren4 + base + o + 1) : bg4) : z4;
+  const float4 R10 = k10 ? ((vyb && vxa) ? __ldg(p.ren4 + base + o + p.W) : bg4) : z4;
+  const float4 R11 = k11 ? ((vyb && vxb) ? __ldg(p.ren4 + base + o + p.W + 1) : bg4) : z4;
   const float wx1 = t.wx1, wy1 = t.wy1, ax = 1.0f - wx1, ay = 1.0f - wy1;
   const float wa = wy1 * wx1, wb = wy1 * ax, wc = ay * wx1, wd = ay * ax;
   float v[8];
@@ -396,10 +406,12 @@ __global__ void __launch_bounds__(128) zoom_fused_nhwc8_kernel(FusedZoomParams p
 
 int zoom_fused_launch(dim_ctx *ctx, const float4 *obs4, const float4 *ren4, const float *zoom_factor,
                       const float *means_rgb, int B, int Hs, int Ws, int pad, __nv_bfloat16 *hi, __nv_bfloat16 *lo,
-                      cudaStream_t st, int f16) {
+                      cudaStream_t st, int f16, const double *means_d) {
   FusedZoomParams p;
   p.obs4 = obs4; p.ren4 = ren4;
   p.bbox8 = ctx->bbox8; p.zoom_factor = zoom_factor;
+  p.vbox = means_d ? ctx->vbox : nullptr;  // means_d given: ren4 comes from the fused loop's box-only render
+  for (int c = 0; c < 3; ++c) p.bg[c] = means_d ? (float)(0.0 - means_d[c]) : 0.f;
   p.H = ctx->H; p.W = ctx->W; p.Hs = Hs; p.Ws = Ws; p.pad = pad;
   for (int c = 0; c < 3; ++c) p.mean[c] = means_rgb[c];
   p.stepx = (float)(2.0 / (double)(ctx->W - 1));

@@ -338,16 +338,25 @@ class Context:
 
     # ------------------------------------------------------------------------------ refine
     def refine(self, image_observed, cls_idx, pose_init, K, n_iter=4, znear=0.25, zfar=6.0,
-               pixel_means_rgb=(103.939, 116.779, 123.68), precision=capi.PREC_FP16, pose_override=None):
-        """Device-resident fused loop.  image_observed f32[B,3,H,W], cls_idx i32[B], pose_init f64[B,3,4]."""
+               pixel_means_rgb=(103.939, 116.779, 123.68), precision=capi.PREC_FP16, pose_override=None, out=None):
+        """Device-resident fused loop.  image_observed f32[B,3,H,W], cls_idx i32[B], pose_init f64[B,3,4].
+        out = the dict returned by an earlier call with the same shapes: results are written into those tensors again
+        (same device addresses -> the library replays its CUDA graph of the chain instead of re-enqueuing ~90 launches)."""
         B = image_observed.shape[0]
         _chk(image_observed, torch.float32, (B, 3, self.H, self.W), "image_observed")
         _chk(cls_idx, torch.int32, (B,), "cls_idx")
         _chk(pose_init, torch.float64, (B, 3, 4), "pose_init")
-        poses = self._new((n_iter, B, 3, 4), torch.float64)
-        se3 = self._new((n_iter, B, 7))
-        zf = self._new((n_iter, B, 4))
-        bbox = self._new((n_iter, B, 8), torch.int32)
+        if out is not None:
+            poses, se3, zf, bbox = out["poses"], out["se3"], out["zoom_factor"], out["bbox"]
+            _chk(poses, torch.float64, (n_iter, B, 3, 4), "out['poses']")
+            _chk(se3, torch.float32, (n_iter, B, 7), "out['se3']")
+            _chk(zf, torch.float32, (n_iter, B, 4), "out['zoom_factor']")
+            _chk(bbox, torch.int32, (n_iter, B, 8), "out['bbox']")
+        else:
+            poses = self._new((n_iter, B, 3, 4), torch.float64)
+            se3 = self._new((n_iter, B, 7))
+            zf = self._new((n_iter, B, 4))
+            bbox = self._new((n_iter, B, 8), torch.int32)
         if pose_override is not None:
             _chk(pose_override, torch.float64, (n_iter, B, 3, 4), "pose_override")
         check(lib.dim_refine(self._h, _p(image_observed), _p(cls_idx), _p(pose_init), B, n_iter,
