@@ -241,6 +241,13 @@ DIM_API int32_t dim_refine_host(dim_ctx *ctx, const uint8_t *image_observed_u8_h
                                 float zfar, const double *pixel_means_rgb_host, int32_t precision,
                                 double *poses_out_host, float *se3_out_host, void *stream);
 
+/* Per-iteration status of the LAST dim_refine / dim_refine_host(_async) call on this context, copied device -> host
+ * asynchronously on `stream` (the stream that call ran on): [min(n_iter,8), B] int32.  0 = ok; bit 0 = the rendered mask
+ * of that iteration was empty (the reference crashes there: np.min of an empty array, zoom_mask.py:55-58; here the
+ * fallback zoom factor was used and the instance's pose is meaningless); bit 1 = class index out of range or no mesh
+ * uploaded for that class (the reference indexes a python list and raises). */
+DIM_API int32_t dim_refine_status(dim_ctx *ctx, int32_t B, int32_t n_iter, int32_t *status_host, void *stream);
+
 /* Same as dim_refine_host but returns right after enqueueing the copies and kernels on `stream`
  * (no synchronisation): the host output buffers are valid once the stream has been synchronised.
  * Lets a caller overlap the H2D copy of batch k+1 (second context / stream) with the compute of k. */

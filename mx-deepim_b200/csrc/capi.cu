@@ -143,6 +143,8 @@ DIM_API int32_t dim_ctx_create(int32_t device, int32_t max_batch, int32_t H, int
   rc |= ctx_alloc(ctx, &ctx->vbox, Bm * 4);
   rc |= ctx_alloc(ctx, &ctx->bbox8, Bm * 8);
   rc |= ctx_alloc(ctx, &ctx->status, Bm);
+  rc |= ctx_alloc(ctx, &ctx->cls_flag, Bm);
+  rc |= ctx_alloc(ctx, &ctx->status_hist, 8 * Bm);
   rc |= ctx_alloc(ctx, &ctx->zoom_factor, Bm * 4);
   rc |= ctx_alloc(ctx, &ctx->image_rendered, Bm * 3 * P);
   rc |= ctx_alloc(ctx, &ctx->depth_rendered, Bm * P);
@@ -162,6 +164,8 @@ DIM_API int32_t dim_ctx_create(int32_t device, int32_t max_batch, int32_t H, int
   DIM_CHECK(cudaMemset(ctx->meshes, 0, sizeof(MeshDev) * max_classes));
   DIM_CHECK(cudaMemset(ctx->vis, 0xFF, sizeof(unsigned long long) * Bm * P));  // all pixels empty
   DIM_CHECK(cudaMemset(ctx->pverts, 0, sizeof(PVert) * Bm * max_verts));
+  DIM_CHECK(cudaMemset(ctx->cls_flag, 0, sizeof(int) * Bm));
+  DIM_CHECK(cudaMemset(ctx->status_hist, 0, sizeof(int) * 8 * Bm));
   if (net_create(ctx)) { dim_ctx_destroy(ctx); return 13; }
   DIM_CHECK(cudaDeviceSynchronize());
   *out = ctx;
@@ -400,7 +404,9 @@ static int refine_core(dim_ctx *ctx, const float4 *obs4, const int32_t *cls_idx,
     if (ev) DIM_CHECK(cudaEventRecord(ev[1], st));
     float *zf_it = zoom_factor ? zoom_factor + (size_t)it * B * 4 : ctx->zoom_factor;
     int *bbox_it = bbox ? bbox + (size_t)it * B * 8 : nullptr;
-    if (int rc = zoom_factor_from_ren_launch(ctx, ctx->bbox_ren, ctx->pose_cur_f32, B, K9, zf_it, bbox_it, ctx->status, st))
+    // per-iteration status (bit 0: rendered / observed mask empty -> fallback zoom factor; bit 1: bad class index)
+    if (int rc = zoom_factor_from_ren_launch(ctx, ctx->bbox_ren, ctx->pose_cur_f32, B, K9, zf_it, bbox_it,
+                                             ctx->status_hist + (size_t)(it < 8 ? it : 7) * B, st))
       return rc;
     if (int rc = zoom_fused_launch(ctx, obs4, ctx->ren4, zf_it, means_f, B, rows, cols, pad, hi,
                                    precision == DIM_PREC_BF16X3 ? lo : nullptr, st, precision == DIM_PREC_FP16, means))
@@ -492,6 +498,14 @@ DIM_API int32_t dim_refine_host_async(dim_ctx *ctx, const uint8_t *img_u8, const
   DIM_REQUIRE(ctx && img_u8 && cls_host && pose_host && K9 && means && poses_out, "dim_refine_host: NULL argument");
   DIM_REQUIRE(B >= 1 && B <= ctx->max_batch, "dim_refine_host: batch exceeds max_batch");
   DIM_REQUIRE(n_iter >= 1 && n_iter <= 8, "dim_refine_host: n_iter must be in [1,8]");
+  for (int32_t i = 0; i < B; ++i) {  // the class indices are on the host here: fail loudly (the reference indexes a python list)
+    const int32_t c = cls_host[i];
+    if (c < 0 || c >= ctx->max_classes || ctx->meshes_host[c].V <= 0) {
+      set_error("dim_refine_host: instance %d has class index %d: out of range [0,%d) or no mesh uploaded for it", (int)i, (int)c,
+                (int)ctx->max_classes);
+      return 2;
+    }
+  }
   cudaStream_t st = (cudaStream_t)stream;
   const size_t P = (size_t)ctx->H * ctx->W;
   DIM_CHECK(cudaMemcpyAsync(ctx->image_observed_u8, img_u8, (size_t)B * 3 * P, cudaMemcpyHostToDevice, st));
@@ -504,6 +518,18 @@ DIM_API int32_t dim_refine_host_async(dim_ctx *ctx, const uint8_t *img_u8, const
   DIM_CHECK(cudaMemcpyAsync(poses_out, ctx->poses_dev, sizeof(double) * (size_t)n_iter * B * 12, cudaMemcpyDeviceToHost, st));
   if (se3_out)
     DIM_CHECK(cudaMemcpyAsync(se3_out, ctx->se3_hist_dev, sizeof(float) * (size_t)n_iter * B * 7, cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
+// status of the LAST dim_refine / dim_refine_host(_async) call on this context: [min(n_iter, 8), B] int32, device -> host
+// (asynchronous on `stream`, which must be the stream that call ran on).  0 = ok; bit 0 = the rendered mask of that
+// iteration was empty (object left the frustum: the reference crashes in ZoomMask, np.min of an empty array; here the
+// fallback zoom factor (1,1,0,0) was used and the pose of that instance is meaningless); bit 1 = class index out of range
+// or no mesh uploaded for it.
+DIM_API int32_t dim_refine_status(dim_ctx *ctx, int32_t B, int32_t n_iter, int32_t *status_host, void *stream) {
+  DIM_REQUIRE(ctx && status_host && B >= 1 && B <= ctx->max_batch && n_iter >= 1, "dim_refine_status: bad argument");
+  const int n = n_iter < 8 ? n_iter : 8;
+  DIM_CHECK(cudaMemcpyAsync(status_host, ctx->status_hist, sizeof(int) * (size_t)n * B, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   return 0;
 }
 

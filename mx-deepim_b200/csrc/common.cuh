@@ -88,6 +88,8 @@ struct dim_ctx {
   // zoom scratch
   int *bbox8 = nullptr;      // [max_batch, 8]
   int *status = nullptr;     // [max_batch]
+  int *cls_flag = nullptr;   // [max_batch] rasteriser: 2 = class index out of range / mesh missing (raster.cu mesh_for)
+  int *status_hist = nullptr;  // [8, max_batch] per-iteration status of the last fused refinement (dim_refine_status)
   float *zoom_factor = nullptr;  // [max_batch,4]
   // refine-loop state
   float *image_rendered = nullptr, *depth_rendered = nullptr, *mask_rendered = nullptr;

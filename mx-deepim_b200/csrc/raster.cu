@@ -37,6 +37,8 @@ struct RasterParams {
   int *vbox;      // [B,4]
   int *bbox_ren;  // [B,4]
   int max_verts, max_faces, H, W;
+  int num_classes;  // size of the mesh table: class indices are range-checked on the device (mesh_for)
+  int *cls_flag;    // [B] 0 ok / 2 = class index out of range or no mesh uploaded for it (renders nothing); nullable
   float fx, fy, cx, cy, zn, zf;
   double mean[3];
   float bg[3];  // (float)(0.0 - mean)
@@ -50,6 +52,18 @@ struct RasterParams {
   const float *light_pos, *light_int;
   float a0, a1;
 };
+
+// class index -> mesh, range-checked: an out-of-range index (e.g. LINEMOD's 1-based class id) or a class whose mesh was never
+// uploaded renders nothing instead of reading out of bounds; raster_vertex_kernel flags the instance in cls_flag
+__device__ __forceinline__ MeshDev mesh_for(const RasterParams &p, int b) {
+  const int c = p.cls[b];
+  if (c < 0 || c >= p.num_classes) {
+    MeshDev e;
+    e.verts = nullptr; e.uvs = nullptr; e.faces = nullptr; e.tex = nullptr; e.V = e.F = e.Th = e.Tw = 0; e.normals = nullptr;
+    return e;
+  }
+  return p.meshes[c];
+}
 
 __global__ void raster_init_kernel(int *vbox, int *bbox_ren, int B, int H, int W) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -67,7 +81,8 @@ __global__ void raster_init_kernel(int *vbox, int *bbox_ren, int B, int H, int W
 __global__ void __launch_bounds__(256) raster_vertex_kernel(RasterParams p) {
   const int b = blockIdx.y;
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
-  const MeshDev m = p.meshes[p.cls[b]];
+  const MeshDev m = mesh_for(p, b);
+  if (p.cls_flag && v == 0) p.cls_flag[b] = m.V > 0 ? 0 : 2;
   const float *pose = p.pose + 12 * b;
   int ok = 0, X = 0, Y = 0;
   if (v < m.V) {
@@ -180,7 +195,7 @@ __global__ void __launch_bounds__(128) raster_coverage_kernel(RasterParams p) {
   const int b = blockIdx.y;
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
-  const MeshDev m = p.meshes[p.cls[b]];
+  const MeshDev m = mesh_for(p, b);
   const PVert *pv = p.pverts + (size_t)b * p.max_verts;
   unsigned long long *vis = p.vis + (size_t)b * p.H * p.W;
 
@@ -274,7 +289,7 @@ __global__ void __launch_bounds__(256) raster_resolve_kernel(RasterParams p) {
     ulonglong2 k23 = *reinterpret_cast<const ulonglong2 *>(vis + 2);
     unsigned long long keys[4] = {k01.x, k01.y, k23.x, k23.y};
     bool any = false;
-    const MeshDev m = p.meshes[p.cls[b]];
+    const MeshDev m = mesh_for(p, b);
     const PVert *pv = p.pverts + (size_t)b * p.max_verts;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -416,6 +431,7 @@ int render_launch(dim_ctx *ctx, const int *cls, const float *pose, int B, const 
   p.meshes = ctx->meshes; p.cls = cls; p.pose = pose; p.pverts = ctx->pverts; p.vis = ctx->vis;
   p.vbox = ctx->vbox; p.bbox_ren = ctx->bbox_ren;
   p.max_verts = ctx->max_verts; p.max_faces = ctx->max_faces; p.H = ctx->H; p.W = ctx->W;
+  p.num_classes = ctx->max_classes; p.cls_flag = ctx->cls_flag;
   p.fx = K9[0]; p.fy = K9[4]; p.cx = K9[2]; p.cy = K9[5]; p.zn = zn; p.zf = zf;
   for (int c = 0; c < 3; ++c) {
     p.mean[c] = means ? means[c] : 0.0;

@@ -63,9 +63,10 @@ __global__ void __launch_bounds__(160) mask_bbox_kernel(const float *mask_real, 
 // numpy 1.x: c = K.t and c_x = c0/c2 in float32, everything after in float64, stored as float32.
 __global__ void zoom_factor_kernel(int *bbox8, const float *src_pose, int B, int H, int W, float k0, float k1,
                                    float k2, float k3, float k4, float k5, float k6, float k7, float k8,
-                                   float *zoom_factor, int *bbox_out, int *status) {
+                                   float *zoom_factor, int *bbox_out, int *status, const int *cls_flag) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
+  const int cf = cls_flag ? cls_flag[b] : 0;  // rasteriser: bad class index (bit 1)
   int *bb = bbox8 + 8 * b;
   if (bb[1] < 0) bb[0] = bb[1] = bb[2] = bb[3] = -1;
   if (bb[5] < 0) bb[4] = bb[5] = bb[6] = bb[7] = -1;
@@ -75,10 +76,10 @@ __global__ void zoom_factor_kernel(int *bbox8, const float *src_pose, int B, int
   if (bb[1] < 0) {  // the reference raises (np.min of an empty array); flag it
     zf[0] = zf[1] = 1.f;
     zf[2] = zf[3] = 0.f;
-    if (status) status[b] = 1;
+    if (status) status[b] = 1 | cf;
     return;
   }
-  if (status) status[b] = 0;
+  if (status) status[b] = cf;
   const double real_x0 = bb[0], real_x1 = bb[1], real_y0 = bb[2], real_y1 = bb[3];
   const float *sp = src_pose + 12 * b;
   const float t0 = sp[3], t1 = sp[7], t2 = sp[11];
@@ -241,7 +242,7 @@ int zoom_factor_launch(dim_ctx *ctx, const float *mask_real, const float *mask_r
                                                        img_means ? img_means[1] : 0.f, img_means ? img_means[2] : 0.f);
   DIM_LAUNCH_CHECK();
   zoom_factor_kernel<<<cdiv(B, 64), 64, 0, st>>>(ctx->bbox8, src_pose, B, ctx->H, ctx->W, K9[0], K9[1], K9[2], K9[3],
-                                                  K9[4], K9[5], K9[6], K9[7], K9[8], zoom_factor, bbox_out, status);
+                                                  K9[4], K9[5], K9[6], K9[7], K9[8], zoom_factor, bbox_out, status, nullptr);
   DIM_LAUNCH_CHECK();
   return 0;
 }
@@ -267,7 +268,7 @@ int zoom_factor_from_ren_launch(dim_ctx *ctx, const int *bbox_ren, const float *
   zoom_factor_from_ren_kernel<<<cdiv(B, 64), 64, 0, st>>>(bbox_ren, ctx->bbox8, B);
   DIM_LAUNCH_CHECK();
   zoom_factor_kernel<<<cdiv(B, 64), 64, 0, st>>>(ctx->bbox8, src_pose, B, ctx->H, ctx->W, K9[0], K9[1], K9[2], K9[3],
-                                                  K9[4], K9[5], K9[6], K9[7], K9[8], zoom_factor, bbox_out, status);
+                                                  K9[4], K9[5], K9[6], K9[7], K9[8], zoom_factor, bbox_out, status, ctx->cls_flag);
   DIM_LAUNCH_CHECK();
   return 0;
 }
@@ -492,13 +493,14 @@ __global__ void __launch_bounds__(256) group_pick_kernel(const float *in, const 
     const int b = (int)(i / ((size_t)cg * n));
     const size_t r = i - (size_t)b * cg * n;
     const int g = (int)group_idx[b];
-    out[i] = in[((size_t)b * Ctot + (size_t)g * cg) * n + r];
+    // the reference asserts 0 <= g < group_num (group_picker.py:35); on the device an out-of-range index picks nothing
+    out[i] = (g >= 0 && g < groups) ? in[((size_t)b * Ctot + (size_t)g * cg) * n + r] : 0.f;
   } else {
     if (i >= (size_t)B * Ctot * n) return;
     const int b = (int)(i / ((size_t)Ctot * n));
     const size_t r = i - (size_t)b * Ctot * n;
     const int c = (int)(r / n), g = (int)group_idx[b];
-    out[i] = (c / cg == g) ? in[((size_t)b * cg + (c - g * cg)) * n + (r - (size_t)c * n)] : 0.f;
+    out[i] = (g >= 0 && g < groups && c / cg == g) ? in[((size_t)b * cg + (c - g * cg)) * n + (r - (size_t)c * n)] : 0.f;
   }
 }
 int group_pick_launch(const float *in, const float *group_idx, int B, int Ctot, int groups, size_t n, float *out, int backward,

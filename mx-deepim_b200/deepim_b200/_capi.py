@@ -53,6 +53,7 @@ SIGNATURES = {
     "dim_transform_image_u8": (i32, [vp, vp, i32, pf64, vp, vp]),
     "dim_debug_activation": (i32, [vp, i32, i32, vp, u64]),
     "dim_debug_layer_geometry": (i32, [vp, i32, C.POINTER(i32)]),
+    "dim_refine_status": (i32, [vp, i32, i32, vp, vp]),
     "dim_debug_set_option": (i32, [vp, C.c_char_p, i32]),
     "dim_debug_layer_profile": (i32, [vp, i32, pf32]),
     "dim_profile_enable": (i32, [vp, i32]),

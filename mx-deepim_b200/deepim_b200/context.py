@@ -385,6 +385,22 @@ class Context:
         return poses_out, se3_out
 
 
+def _refine_status(self, B, n_iter, out=None, sync=True):
+    """Per-iteration status of the last refine / refine_host call: int32 [min(n_iter,8), B]; 0 = ok, bit 0 = empty rendered
+    mask in that iteration (pose meaningless; the reference crashes there), bit 1 = bad class index.  `out`: pinned int32
+    tensor for an asynchronous copy on the current stream (sync=False)."""
+    n = min(int(n_iter), 8)
+    if out is None:
+        out = torch.empty((n, B), dtype=torch.int32).pin_memory()
+    check(lib.dim_refine_status(self._h, B, n_iter, C.c_void_p(out.data_ptr()), self._stream()))
+    if sync:
+        torch.cuda.current_stream(self.device).synchronize()
+    return out
+
+
+Context.refine_status = _refine_status
+
+
 def _profile_enable(self, on=True):
     check(lib.dim_profile_enable(self._h, int(on)))
 

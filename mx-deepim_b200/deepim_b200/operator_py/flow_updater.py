@@ -1,8 +1,11 @@
 """FlowUpdater -- mirrors the op surface of deepim/operator_py/flow_updater.py (prop l.111-125:
-depth_src, depth_tgt, pose_src, pose_tgt -> flow, flow_weights; attrs K, thresh, batch_size, height,
-width, wh_rep).  The reference registers it but never puts it in the graph; the
-device path is the reprojection-flow kernel of lib/flow_c (dim_flow_fwd) after composing
-KT = K . T_src->tgt on the host (calc_se3, RT_transform.py:176-187)."""
+depth_src, depth_tgt, pose_src, pose_tgt -> flow [B,2,H,W], flow_weights [B,2,H,W] (the validity plane tiled to both
+channels, l.98-99); attrs K, thresh, batch_size, height, width, wh_rep).  The reference registers it but never puts it
+in the graph.  NUMERICS FOLLOW lib/flow_c (gpu_flow), not flow_updater.py: the device path is the
+reprojection-flow kernel dim_flow_fwd -- sub-pixel flow h_proj - h, depth test at the rounded target pixel with the
+fixed 3e-3 threshold (gpu_flow_kernel.cu:45-58) -- where flow_updater.py rounds the projection to integer pixels and
+takes `thresh` as an attribute; any other thresh is refused.  KT = K . T_src->tgt is composed on the host (calc_se3,
+RT_transform.py:176-187), one small D2H read of the two pose blobs (the reference does the same with asnumpy())."""
 import numpy as np
 import torch
 
@@ -28,7 +31,7 @@ class FlowUpdaterOperator(CustomOp):
         if self.wh_rep:  # standard (dw, dh) channel order
             flow = flow.flip(1).contiguous()
         self.assign(out_data[0], req[0], flow)
-        self.assign(out_data[1], req[1], valid)
+        self.assign(out_data[1], req[1], valid.expand(-1, 2, -1, -1).contiguous())   # mx.nd.tile(valid, (1,2,1,1)), l.99
 
 
 @register("FlowUpdater")
@@ -47,7 +50,7 @@ class FlowUpdaterProp(CustomOpProp):
 
     def infer_shape(self, in_shape):
         b, _, h, w = in_shape[0]
-        return in_shape, [[b, 2, h, w], [b, 1, h, w]], []
+        return in_shape, [[b, 2, h, w], [b, 2, h, w]], []
 
     def create_operator(self, ctx, shapes, dtypes):
         return FlowUpdaterOperator(ctx, self.K, self.thresh, self.wh_rep)

@@ -35,6 +35,7 @@ class PoseRefiner:
                 "ctx": ctx, "stream": torch.cuda.Stream(device=ctx.device), "busy": False, "n": 0,
                 "poses": torch.empty((n_iter, max_batch, 3, 4), dtype=torch.float64).pin_memory(),
                 "se3": torch.empty((n_iter, max_batch, 7), dtype=torch.float32).pin_memory(),
+                "status": torch.zeros((min(n_iter, 8) * max_batch,), dtype=torch.int32).pin_memory(),
                 "img": None, "cls": None, "pose": None,
             })
         self.ctx = self.slots[0]["ctx"]
@@ -70,16 +71,27 @@ class PoseRefiner:
         with torch.cuda.stream(slot["stream"]):
             slot["ctx"].refine_host(img, cls, pose, self.K, self.n_iter, self.zn, self.zf, self.means, self.precision,
                                     poses_out=slot["poses"], se3_out=slot["se3"], sync=False)
+            slot["ctx"].refine_status(n, self.n_iter, out=slot["status"], sync=False)
         slot["busy"], slot["n"] = True, n
         self._next = (i + 1) % len(self.slots)
         return i
 
-    def result(self, ticket):
-        """Block until the batch is done; returns poses [n_iter, n, 3, 4] float64 (numpy copy)."""
+    def result(self, ticket, strict=True):
+        """Block until the batch is done; returns poses [n_iter, n, 3, 4] float64 (numpy copy).
+        The per-iteration device status is checked: an instance whose object left the view frustum (empty rendered mask;
+        the reference crashes in ZoomMask there) or whose class index is invalid raises DeepIMError when strict, else the
+        flags are left in `self.last_status` ([n_iter, n] int32) for the caller."""
         slot = self.slots[ticket]
         slot["stream"].synchronize()
         slot["busy"] = False
         n, B = slot["n"], self.max_batch
+        ni = min(self.n_iter, 8)
+        self.last_status = slot["status"][: ni * n].view(ni, n).numpy().copy()
+        if strict and self.last_status.any():
+            bad = sorted(set(np.nonzero(self.last_status)[1].tolist()))
+            raise capi.DeepIMError("PoseRefiner: instances %s of the batch have a non-zero device status (bit 0: empty rendered "
+                                   "mask -- object left the frustum; bit 1: bad class index): %s"
+                                   % (bad, self.last_status[:, bad].tolist()))
         # refine_host packs outputs densely as [n_iter, n, ...] at the start of the pinned buffer
         p = slot["poses"].view(-1)[: self.n_iter * n * 12].view(self.n_iter, n, 3, 4)
         return p.numpy().copy()

@@ -175,7 +175,7 @@ def test_flow_updater_and_shims(env):
     d_tgt = np.stack([O.render(meshes[1], obs[b], K)["depth"] for b in range(B)])[:, None]
     fu = ops.create("FlowUpdater", K=KSTR, thresh="3e-3", batch_size=str(B), height="480", width="640")
     fl, va = _run(fu, [dev(d_src), dev(d_tgt), dev(ini.astype(np.float32)), dev(obs.astype(np.float32))],
-                  [(B, 2, H, W), (B, 1, H, W)])
+                  [(B, 2, H, W), (B, 2, H, W)])      # flow_weights = the validity plane tiled to 2 channels (flow_updater.py:98-99)
     K64 = K.astype(np.float64)
     KT = np.zeros((B, 3, 4), np.float32)
     for b in range(B):
@@ -185,7 +185,7 @@ def test_flow_updater_and_shims(env):
     Kinv = np.linalg.inv(K64).astype(np.float32)
     ofl, ova = O.flow(d_src, d_tgt, KT, Kinv)
     assert ova.sum() > 1000
-    assert np.array_equal(va.cpu().numpy(), ova) and np.array_equal(fl.cpu().numpy(), ofl)
+    assert np.array_equal(va.cpu().numpy(), np.tile(ova, (1, 2, 1, 1))) and np.array_equal(fl.cpu().numpy(), ofl)
     # gpu_flow shim (lib/flow_c/gpu_flow.pyx signature): numpy in / numpy out
     f2, v2 = gpu_flow(d_src, d_tgt, KT, Kinv, 0)
     assert np.array_equal(f2, ofl) and np.array_equal(v2, ova)

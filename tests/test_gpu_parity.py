@@ -459,6 +459,42 @@ def test_errors_are_loud(ctx):
         ctx.zoom_trans(torch.zeros(2, 4, device=DEV), torch.zeros(2, 3, dtype=torch.float64, device=DEV), True)
 
 
+def test_bad_class_index_and_lost_object_are_flagged(ctx, meshes, weights, loop_case):
+    """Class indices are range-checked (the reference indexes a python list and raises): on the host entry point the call
+    fails; on the device entry point the instance renders nothing and is flagged (status bit 1).  An object that leaves the
+    view frustum gives an empty rendered mask: the reference crashes in ZoomMask (np.min of an empty array), here the
+    iteration is flagged (bit 0) and PoseRefiner.result() raises."""
+    from deepim_b200.refiner import PoseRefiner
+    c = loop_case
+    u8 = np.zeros((c["B"], H, W, 3), np.uint8)
+    bad = c["cls"].copy()
+    bad[2] = 7                                         # ctx has max_classes = 4
+    with pytest.raises(capi.DeepIMError):
+        ctx.refine_host(u8, bad, c["ini"], K, 2, pixel_means_rgb=MEANS)
+    bad[2] = 3                                         # in range, but no mesh uploaded for class 3
+    with pytest.raises(capi.DeepIMError):
+        ctx.refine_host(u8, bad, c["ini"], K, 2, pixel_means_rgb=MEANS)
+    res = ctx.refine(dev(c["img"]), dev(bad), dev(c["ini"]), K, 2, pixel_means_rgb=MEANS)
+    st = ctx.refine_status(c["B"], 2).numpy()
+    assert np.isfinite(res["poses"].cpu().numpy()[:, [0, 1, 3]]).all()
+    assert (st[:, 2] & 2).all() and not (st[:, [0, 1, 3]] & 2).any()
+    # the good instances are untouched by their bad neighbour
+    good = ctx.refine(dev(c["img"]), dev(c["cls"]), dev(c["ini"]), K, 2, pixel_means_rgb=MEANS)
+    assert torch.equal(good["poses"][:, [0, 1, 3]], res["poses"][:, [0, 1, 3]])
+    assert not ctx.refine_status(c["B"], 2).numpy().any()
+    # object far outside the frame
+    lost = c["ini"].copy()
+    lost[1, 0, 3] = 5.0
+    ref = PoseRefiner(meshes, weights, K, device=0, max_batch=4, n_iter=2, n_slots=1)
+    t = ref.submit(u8, c["cls"], lost)
+    with pytest.raises(capi.DeepIMError):
+        ref.result(t)
+    t = ref.submit(u8, c["cls"], lost)
+    ref.result(t, strict=False)
+    assert (ref.last_status[:, 1] & 1).all() and not ref.last_status[:, [0, 2, 3]].any()
+    ref.close()
+
+
 # ------------------------------------------------------------------- BASELINE.json configs C3 / C5
 def test_config_c3_thirteen_meshes_sharded_batch(weights):
     """C3: 13 LINEMOD-scale meshes, instances round-robin over classes, batch split into device batches

@@ -4,13 +4,19 @@ import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "mx-deepim_b200"))
 import torch, torch.distributed as dist
-from deepim_b200.grad_allreduce import GradBuckets
+from deepim_b200 import trainer
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 res = {}
 for mb in (8, 32, 231):
-    gb = GradBuckets(torch.device("cuda", lr), bucket_mb=mb)
+    class GB:  # the flat gradient vector + the buckets Trainer.allreduce_overlapped walks (trainer.make_buckets)
+        pass
+    gb = GB()
+    gb.buckets, _ = trainer.make_buckets(float(mb))
+    gb.numel = sum(n for _, n in trainer.tensor_sizes())
+    gb.flat = torch.empty(gb.numel, device=torch.device("cuda", lr))
+    gb.allreduce = lambda d: [d.all_reduce(gb.flat[lo:hi], op=d.ReduceOp.SUM) for lo, hi in gb.buckets]
     gb.flat.normal_()
     for _ in range(3):
         gb.allreduce(dist)
