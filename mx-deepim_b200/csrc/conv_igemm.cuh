@@ -64,13 +64,46 @@ namespace ptx {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a CONVERGED warp.  The TMA-producer and MMA-issuer warps run their loops with all 32 lanes (warp-uniform
+// control flow and operands) and only the instruction that must be issued once sits under elect.sync: descriptors,
+// coordinates and barrier addresses then live in uniform registers.  Issuing from inside `if (lane == 0)` instead made the
+// compiler wrap EVERY tcgen05.mma / TMA instruction in an ELECT + R2UR.BROADCAST + BRA.U.ANY loop (~17 SASS instructions
+// per MMA on one thread): slower than the 32-cycle N = 64 MMA it issues, and the limiter of conv1 / conv2 in round 1.
+// Every function below that says "elected lane" must be called by all 32 lanes of the warp.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+__device__ __forceinline__ void mbar_expect_tx_raw(uint64_t *bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_raw(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_raw(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+          "r"(smem_u32(dst)),
+      "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// elected lane
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  if (elect_one())
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
@@ -86,19 +119,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)m) : "memory");
 }
+// elected lane
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
+  if (elect_one())
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
 }
+// elected lane
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
-          "r"(smem_u32(dst)),
-      "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
+  if (elect_one())
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+            "r"(smem_u32(dst)),
+        "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
 }
 
 // --- TMEM
@@ -114,9 +151,11 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32, issued by ONE thread
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                         uint32_t accumulate) {
+// raw variants for callers that already sit inside `if (elect_one()) { ... }` (one election per K-block instead of one per
+// instruction).  A descriptor advanced by `bytes` inside its tile is desc + (bytes >> 4): the 14-bit start-address field
+// cannot carry for shared-memory addresses below 256 KB.
+__device__ __forceinline__ void umma_f16_raw(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
@@ -126,10 +165,30 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
       : "memory");
 }
-// arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+__device__ __forceinline__ void umma_commit_raw(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 (or fp16 x fp16: idesc) -> fp32, issued by the elected lane
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  if (elect_one())
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+// arrive on an mbarrier when all previously issued tcgen05.mma of the elected lane have completed (elect.sync picks the same
+// lane for the same member mask, so this tracks the MMAs issued through umma_f16)
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  if (elect_one())
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
 }
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (lane i of the warp's quadrant)
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t *r) {
@@ -344,8 +403,8 @@ __global__ void __launch_bounds__(192) conv_igemm_persistent_kernel(const __grid
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (whole warp, elected lane issues)
+    {
       if (RESIDENT_B) {
         ptx::mbar_expect_tx(res_bar, (uint32_t)S::RES_BYTES);
         for (int kb = 0; kb < KBLOCKS_RES; ++kb) {
@@ -371,25 +430,28 @@ __global__ void __launch_bounds__(192) conv_igemm_persistent_kernel(const __grid
             dc = kw >> 1;
           }
           uint8_t *st = smem + s * S::STAGE_BYTES;
-          ptx::mbar_expect_tx(&full_bar[s], tx);
           if (EPI) { dr += p.in_off_r; dc += p.in_off_c; }
-          ptx::tma_load_3d(st, &p.a_map[view], &full_bar[s], cc * BLOCK_K, ow0 + dc, g0 + dr);
-          uint8_t *nxt = st + S::A_BYTES;
-          if (!RESIDENT_B) {
-            ptx::tma_load_2d(nxt, &p.b_map, &full_bar[s], kb * BLOCK_K, n0);
-            nxt += S::B_BYTES;
+          if (ptx::elect_one()) {
+            ptx::mbar_expect_tx_raw(&full_bar[s], tx);
+            ptx::tma_load_3d_raw(st, &p.a_map[view], &full_bar[s], cc * BLOCK_K, ow0 + dc, g0 + dr);
+            uint8_t *nxt = st + S::A_BYTES;
+            if (!RESIDENT_B) {
+              ptx::tma_load_2d_raw(nxt, &p.b_map, &full_bar[s], kb * BLOCK_K, n0);
+              nxt += S::B_BYTES;
+            }
+            if (SPLIT3) {
+              ptx::tma_load_3d_raw(nxt, &p.a_lo_map[view], &full_bar[s], cc * BLOCK_K, ow0 + dc, g0 + dr);
+              if (!RESIDENT_B) ptx::tma_load_2d_raw(nxt + S::A_BYTES, &p.b_lo_map, &full_bar[s], kb * BLOCK_K, n0);
+            }
           }
-          if (SPLIT3) {
-            ptx::tma_load_3d(nxt, &p.a_lo_map[view], &full_bar[s], cc * BLOCK_K, ow0 + dc, g0 + dr);
-            if (!RESIDENT_B) ptx::tma_load_2d(nxt + S::A_BYTES, &p.b_lo_map, &full_bar[s], kb * BLOCK_K, n0);
-          }
+          __syncwarp();
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp, elected lane issues)
+    {
       if (RESIDENT_B) {
         ptx::mbar_wait(res_bar, 0);
         ptx::tc_fence_after();
@@ -414,20 +476,22 @@ __global__ void __launch_bounds__(192) conv_igemm_persistent_kernel(const __grid
             a_lo = b_hi + S::B_BYTES;
             b_lo = a_lo + S::A_BYTES;
           }
+          if (ptx::elect_one()) {
+            const uint64_t da0 = ptx::umma_desc(a_hi, SBO, LAYOUT), db0 = ptx::umma_desc(b_hi, SBO, LAYOUT);
+            const uint64_t dal0 = ptx::umma_desc(a_lo, SBO, LAYOUT), dbl0 = ptx::umma_desc(b_lo, SBO, LAYOUT);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
-            const uint64_t da = ptx::umma_desc(a_hi + k * 32, SBO, LAYOUT);
-            const uint64_t db = ptx::umma_desc(b_hi + k * 32, SBO, LAYOUT);
-            ptx::umma_f16(tmem_acc, da, db, p.idesc, acc);
-            if (SPLIT3) {
-              const uint64_t dal = ptx::umma_desc(a_lo + k * 32, SBO, LAYOUT);
-              const uint64_t dbl = ptx::umma_desc(b_lo + k * 32, SBO, LAYOUT);
-              ptx::umma_f16(tmem_acc, dal, db, p.idesc, 1u);
-              ptx::umma_f16(tmem_acc, da, dbl, p.idesc, 1u);
+            for (int k = 0; k < BLOCK_K / 16; ++k) {
+              const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
+              const uint64_t da = da0 + (uint64_t)(2 * k), db = db0 + (uint64_t)(2 * k);  // + k * 32 bytes
+              ptx::umma_f16_raw(tmem_acc, da, db, p.idesc, acc);
+              if (SPLIT3) {
+                ptx::umma_f16_raw(tmem_acc, dal0 + (uint64_t)(2 * k), db, p.idesc, 1u);
+                ptx::umma_f16_raw(tmem_acc, da, dbl0 + (uint64_t)(2 * k), p.idesc, 1u);
+              }
             }
+            ptx::umma_commit_raw(&empty_bar[s]);
           }
-          ptx::umma_commit(&empty_bar[s]);
+          __syncwarp();
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
         ptx::umma_commit(&tmem_full_bar[as]);
@@ -517,8 +581,10 @@ __global__ void __launch_bounds__(192) conv_igemm_persistent_kernel(const __grid
 // Input buffer layout (written by the zoom kernel): [B*Hs rows][4 chunks][Ws cols][8 ch] bf16.
 // Tile = one output row x BW output columns (BW <= 128; MMA rows >= BW are don't-care).
 // Weights: the whole 64 x 512 matrix stays resident in shared memory (64B-swizzled, 16 tap tiles).
+// elected lane
 __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2,
                                             int c3) {
+  if (ptx::elect_one())
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
           "r"(ptx::smem_u32(dst)),
@@ -590,7 +656,7 @@ __global__ void __launch_bounds__(192) conv1_strip_kernel(const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       ptx::mbar_expect_tx(res_bar, (uint32_t)S::RES_BYTES);
       for (int kb = 0; kb < 16; ++kb) {
         ptx::tma_load_2d(res + kb * S::B_BYTES, &p.b_map, res_bar, kb * 32, 0);
@@ -613,7 +679,7 @@ __global__ void __launch_bounds__(192) conv1_strip_kernel(const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       ptx::mbar_wait(res_bar, 0);
       ptx::tc_fence_after();
       int s = 0, as = 0;
@@ -627,26 +693,31 @@ __global__ void __launch_bounds__(192) conv1_strip_kernel(const __grid_constant_
           ptx::tc_fence_after();
           const uint32_t a_hi = ptx::smem_u32(ring + s * S::STAGE_BYTES);
           const uint32_t a_lo = a_hi + S::A_BYTES;
+          if (ptx::elect_one()) {
+            // one election per strip; every descriptor = base + (byte offset >> 4): dw shifts the strip by one pixel (16 B),
+            // k selects the pair of 8-channel chunks (2 * LBO bytes), the weight tile of tap (dh, dw) is 4 KB further
+            const uint64_t da0 = umma_desc_interleave(a_hi, LBO, 128), dal0 = umma_desc_interleave(a_lo, LBO, 128);
+            const uint64_t db0 = ptx::umma_desc(ptx::smem_u32(res) + dh * 4 * S::B_BYTES, 512, 4u);
+            const uint64_t dbl0 = ptx::umma_desc(ptx::smem_u32(res) + (16 + dh * 4) * S::B_BYTES, 512, 4u);
+            const uint64_t kstep = (uint64_t)(2u * LBO >> 4);
 #pragma unroll
-          for (int dw = 0; dw < 4; ++dw) {
-            const uint32_t b_hi = ptx::smem_u32(res + (dh * 4 + dw) * S::B_BYTES);
-            const uint32_t b_lo = ptx::smem_u32(res + (16 + dh * 4 + dw) * S::B_BYTES);
+            for (int dw = 0; dw < 4; ++dw) {
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {  // 16 channels = 2 chunks per UMMA: k = 0 -> row parity 0, k = 1 -> row parity 1
-              if (dh == 3 && k == 1) continue;  // kh = 2*3 + 1 = 7 lies outside the 7x7 filter: all-zero weights, skip the MMA
-              const uint32_t acc = (dh | dw | k) ? 1u : 0u;
-              const uint64_t da = umma_desc_interleave(a_hi + dw * 16 + k * 2 * LBO, LBO, 128);
-              const uint64_t db = ptx::umma_desc(b_hi + k * 32, 512, 4u);
-              ptx::umma_f16(tmem_acc, da, db, p.idesc, acc);
-              if (SPLIT3) {
-                const uint64_t dal = umma_desc_interleave(a_lo + dw * 16 + k * 2 * LBO, LBO, 128);
-                const uint64_t dbl = ptx::umma_desc(b_lo + k * 32, 512, 4u);
-                ptx::umma_f16(tmem_acc, dal, db, p.idesc, 1u);
-                ptx::umma_f16(tmem_acc, da, dbl, p.idesc, 1u);
+              for (int k = 0; k < 2; ++k) {  // 16 channels = 2 chunks per UMMA: k = 0 -> row parity 0, k = 1 -> row parity 1
+                if (dh == 3 && k == 1) continue;  // kh = 2*3 + 1 = 7 lies outside the 7x7 filter: all-zero weights, skip the MMA
+                const uint32_t acc = (dh | dw | k) ? 1u : 0u;
+                const uint64_t da = da0 + (uint64_t)dw + (uint64_t)k * kstep;
+                const uint64_t db = db0 + (uint64_t)(dw * (S::B_BYTES >> 4) + 2 * k);
+                ptx::umma_f16_raw(tmem_acc, da, db, p.idesc, acc);
+                if (SPLIT3) {
+                  ptx::umma_f16_raw(tmem_acc, dal0 + (uint64_t)dw + (uint64_t)k * kstep, db, p.idesc, 1u);
+                  ptx::umma_f16_raw(tmem_acc, da, dbl0 + (uint64_t)(dw * (S::B_BYTES >> 4) + 2 * k), p.idesc, 1u);
+                }
               }
             }
+            ptx::umma_commit_raw(&empty_bar[s]);
           }
-          ptx::umma_commit(&empty_bar[s]);
+          __syncwarp();
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
         ptx::umma_commit(&tmem_full_bar[as]);
@@ -747,7 +818,7 @@ __global__ void __launch_bounds__(192) conv1_roll_kernel(const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0 && n_rows > 0) {
+    if (n_rows > 0) {
       ptx::mbar_expect_tx(res_bar, (uint32_t)RES_BYTES);
       for (int kb = 0; kb < 16; ++kb) {
         ptx::tma_load_2d(res + kb * B_BYTES, &p.b_map, res_bar, kb * 32, 0);
@@ -764,7 +835,7 @@ __global__ void __launch_bounds__(192) conv1_roll_kernel(const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && n_rows > 0) {
+    if (n_rows > 0) {
       ptx::mbar_wait(res_bar, 0);
       ptx::tc_fence_after();
       int as = 0, waited = 0;
@@ -782,28 +853,33 @@ __global__ void __launch_bounds__(192) conv1_roll_kernel(const __grid_constant__
           }
           const uint32_t a_hi = ptx::smem_u32(ring + slot * stage_bytes);
           const uint32_t a_lo = a_hi + (uint32_t)strip_bytes;
+          if (ptx::elect_one()) {
+            const uint64_t da0 = umma_desc_interleave(a_hi, LBO, 128), dal0 = umma_desc_interleave(a_lo, LBO, 128);
+            const uint64_t db0 = ptx::umma_desc(ptx::smem_u32(res) + dh * 4 * B_BYTES, 512, 4u);
+            const uint64_t dbl0 = ptx::umma_desc(ptx::smem_u32(res) + (16 + dh * 4) * B_BYTES, 512, 4u);
+            const uint64_t kstep = (uint64_t)(2u * LBO >> 4);
 #pragma unroll
-          for (int dw = 0; dw < 4; ++dw) {
-            const uint32_t b_hi = ptx::smem_u32(res + (dh * 4 + dw) * B_BYTES);
-            const uint32_t b_lo = ptx::smem_u32(res + (16 + dh * 4 + dw) * B_BYTES);
+            for (int dw = 0; dw < 4; ++dw) {
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              if (dh == 3 && k == 1) continue;  // kh = 7: outside the 7x7 filter, all-zero weights
-              const uint32_t acc = (dh | dw | k) ? 1u : 0u;
-              const uint64_t da = umma_desc_interleave(a_hi + dw * 16 + k * 2 * LBO, LBO, 128);
-              const uint64_t db = ptx::umma_desc(b_hi + k * 32, 512, 4u);
-              ptx::umma_f16(tmem_acc, da, db, p.idesc, acc);
-              if (SPLIT3) {
-                const uint64_t dal = umma_desc_interleave(a_lo + dw * 16 + k * 2 * LBO, LBO, 128);
-                const uint64_t dbl = ptx::umma_desc(b_lo + k * 32, 512, 4u);
-                ptx::umma_f16(tmem_acc, dal, db, p.idesc, 1u);
-                ptx::umma_f16(tmem_acc, da, dbl, p.idesc, 1u);
+              for (int k = 0; k < 2; ++k) {
+                if (dh == 3 && k == 1) continue;  // kh = 7: outside the 7x7 filter, all-zero weights
+                const uint32_t acc = (dh | dw | k) ? 1u : 0u;
+                const uint64_t da = da0 + (uint64_t)dw + (uint64_t)k * kstep;
+                const uint64_t db = db0 + (uint64_t)(dw * (B_BYTES >> 4) + 2 * k);
+                ptx::umma_f16_raw(tmem_acc, da, db, p.idesc, acc);
+                if (SPLIT3) {
+                  ptx::umma_f16_raw(tmem_acc, dal0 + (uint64_t)dw + (uint64_t)k * kstep, db, p.idesc, 1u);
+                  ptx::umma_f16_raw(tmem_acc, da, dbl0 + (uint64_t)(dw * (B_BYTES >> 4) + 2 * k), p.idesc, 1u);
+                }
               }
             }
+            if (dh == 3) {
+              ptx::umma_commit_raw(&empty_bar[t % STAGES]);  // strip t served output rows t-3 .. t: its slot may be refilled
+              ptx::umma_commit_raw(&tmem_full_bar[as]);
+            }
           }
+          __syncwarp();
         }
-        ptx::umma_commit(&empty_bar[t % STAGES]);  // strip t served output rows t-3 .. t: its slot may be refilled
-        ptx::umma_commit(&tmem_full_bar[as]);
         if (++as == 2) { as = 0; aph ^= 1u; }
       }
     }
@@ -861,6 +937,7 @@ __device__ __forceinline__ void cluster_sync() {
 }
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // cute::Sm100MmaPeerBitMask: address of CTA 0's copy
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+  if (ptx::elect_one())
   asm volatile(
       "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
           "r"(ptx::smem_u32(dst)),
@@ -868,6 +945,7 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
       : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+  if (ptx::elect_one())
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
           "r"(ptx::smem_u32(dst)),
@@ -883,8 +961,8 @@ __device__ __forceinline__ void tmem_alloc(uint32_t *slot_smem, uint32_t ncols) 
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                         uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16_raw(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
@@ -896,12 +974,15 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       : "memory");
 }
 // arrive on the barrier at this smem offset in BOTH CTAs when the issued MMAs have completed
-__device__ __forceinline__ void umma_commit_mc(uint64_t *bar) {
+__device__ __forceinline__ void umma_commit_mc_raw(uint64_t *bar) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
           ptx::smem_u32(bar)),
       "h"((uint16_t)3)
       : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t *bar) {  // elected lane
+  if (ptx::elect_one()) umma_commit_mc_raw(bar);
 }
 // arrive on the leader CTA's copy of a barrier
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) {
@@ -967,8 +1048,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192)
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs; whole warp, elected lane issues)
+    {
       const uint32_t tx_cta = (uint32_t)(p.BW * p.BH * 64 * 2 + (BLOCK_N / 2) * 64 * 2) * S::NPREC;
       int s = 0;
       uint32_t ph = 0;
@@ -990,7 +1071,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192)
             dc = kw >> 1;
           }
           uint8_t *st = smem + s * S::STAGE_BYTES;
-          if (leader) ptx::mbar_expect_tx(&full_bar[s], 2u * tx_cta);  // bytes landing in both CTAs
+          if (leader) ptx::mbar_expect_tx(&full_bar[s], 2u * tx_cta);  // bytes landing in both CTAs (leader: CTA-uniform)
           ptx2::tma_load_3d(st, &p.a_map[view], &full_bar[s], cc * 64, ow0 + dc, g0 + dr);
           ptx2::tma_load_2d(st + S::A_BYTES, &p.b2_map, &full_bar[s], kb * 64, n0);
           if (SPLIT3) {
@@ -1002,8 +1083,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192)
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (leader && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only; whole warp)
+    if (leader) {
       int s = 0, as = 0;
       uint32_t ph = 0, aph = 0;
       for (int tile = pair; tile < total_pair_tiles; tile += npairs) {
@@ -1019,20 +1100,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192)
           const uint32_t b_hi = a_hi + S::A_BYTES;
           const uint32_t a_lo = b_hi + S::B_BYTES;
           const uint32_t b_lo = a_lo + S::A_BYTES;
+          if (ptx::elect_one()) {
+            const uint64_t da0 = ptx::umma_desc(a_hi, SBO, LAYOUT), db0 = ptx::umma_desc(b_hi, SBO, LAYOUT);
+            const uint64_t dal0 = ptx::umma_desc(a_lo, SBO, LAYOUT), dbl0 = ptx::umma_desc(b_lo, SBO, LAYOUT);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
-            const uint64_t da = ptx::umma_desc(a_hi + k * 32, SBO, LAYOUT);
-            const uint64_t db = ptx::umma_desc(b_hi + k * 32, SBO, LAYOUT);
-            ptx2::umma_f16(tmem_acc, da, db, p.idesc, acc);
-            if (SPLIT3) {
-              const uint64_t dal = ptx::umma_desc(a_lo + k * 32, SBO, LAYOUT);
-              const uint64_t dbl = ptx::umma_desc(b_lo + k * 32, SBO, LAYOUT);
-              ptx2::umma_f16(tmem_acc, dal, db, p.idesc, 1u);
-              ptx2::umma_f16(tmem_acc, da, dbl, p.idesc, 1u);
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
+              const uint64_t da = da0 + (uint64_t)(2 * k), db = db0 + (uint64_t)(2 * k);
+              ptx2::umma_f16_raw(tmem_acc, da, db, p.idesc, acc);
+              if (SPLIT3) {
+                ptx2::umma_f16_raw(tmem_acc, dal0 + (uint64_t)(2 * k), db, p.idesc, 1u);
+                ptx2::umma_f16_raw(tmem_acc, da, dbl0 + (uint64_t)(2 * k), p.idesc, 1u);
+              }
             }
+            ptx2::umma_commit_mc_raw(&empty_bar[s]);
           }
-          ptx2::umma_commit_mc(&empty_bar[s]);
+          __syncwarp();
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
         ptx2::umma_commit_mc(&tmem_full_bar[as]);

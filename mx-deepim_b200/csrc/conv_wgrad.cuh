@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(192) conv_wgrad_kernel(const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {  // whole warp; the elected lane issues (conv_igemm.cuh ptx::elect_one)
       const int kh = tap / p.KW, kw = tap - kh * p.KW;
       int view = 0, dr = kh, dc = kw;
       if (p.stride == 2) {
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(192) conv_wgrad_kernel(const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // whole warp; the elected lane issues
       int s = 0;
       uint32_t ph = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(192) conv1_wgrad_kernel(const __grid_constant_
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (warp == 0) {
-    if (lane == 0) {
+    {  // whole warp; the elected lane issues (conv_igemm.cuh ptx::elect_one)
       int s = 0;
       uint32_t ph = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(192) conv1_wgrad_kernel(const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // whole warp; the elected lane issues
       int s = 0;
       uint32_t ph = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
