@@ -292,6 +292,13 @@ DIM_API int32_t dim_pose_error(dim_ctx *ctx, const double *poses_est, const doub
                                const double *points, int32_t N, int32_t symmetric, double *err,
                                void *stream);
 
+/* Average 2D re-projection error and rotation / translation distances of pose pairs (float64, device pointers):
+ * err3[m] = { arp_2d (pixels; lib/utils/pose_error.py:55-69), rotation distance in degrees, translation distance in metres
+ * (lib/pair_matching/RT_transform.py:162-173 calc_rt_dist_m) } -- the inputs of LM6D_REFINE.evaluate_pose (5 cm 5 deg,
+ * lib/dataset/LM6D_REFINE.py:278-371) and evaluate_pose_arp_2d (Proj. 2D, l.514-). K9_dev: 9 doubles on the device. */
+DIM_API int32_t dim_pose_error_2d(dim_ctx *ctx, const double *poses_est, const double *poses_gt, int32_t M, const double *points,
+                                  int32_t N, const double *K9_dev, double *err3, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Training step of the refiner network (train graph: deepim/symbols/deepIM_flownet.py:121-365 decoder,
  * flow / mask / point-matching losses; optimiser: deepim/train.py:296-304 SGD-momentum, one update per inner

@@ -25,6 +25,7 @@ int zoom_gather_launch(dim_ctx *, int mode, const float *src, float *dst, const 
 int zoom_factor_launch(dim_ctx *, const float *, const float *, int C, const float *, int B, const float *K9, float *,
                        int *, int *, cudaStream_t, const float *img_means = nullptr);
 int pose_error_launch(const double *, const double *, int M, const double *, int N, int symmetric, double *, cudaStream_t);
+int pose_error2d_launch(const double *, const double *, int M, const double *, int N, const double *K9, double *, cudaStream_t);
 int group_pick_launch(const float *, const float *, int B, int Ctot, int groups, size_t n, float *, int backward, cudaStream_t);
 int zoom_factor_from_ren_launch(dim_ctx *, const int *, const float *, int B, const float *K9, float *, int *, int *,
                                 cudaStream_t);
@@ -430,7 +431,9 @@ static int refine_graphed(dim_ctx *ctx, const float4 *obs4, const int32_t *cls_i
                           int32_t n_iter, const float *K9, float zn, float zf, const double *means, int32_t precision,
                           const double *pose_override, double *poses, float *se3, float *zoom_factor, int32_t *bbox,
                           cudaStream_t st) {
-  if (!ctx->use_graph || ctx->prof || !net_graph_safe(ctx))
+  // the legacy default stream (and the per-thread default stream handle) cannot be captured
+  const bool capturable = st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;
+  if (!ctx->use_graph || ctx->prof || !capturable || !net_graph_safe(ctx))
     return refine_core(ctx, obs4, cls_idx, pose_init, B, n_iter, K9, zn, zf, means, precision, pose_override, poses, se3,
                        zoom_factor, bbox, st);
   std::vector<unsigned char> key;
@@ -637,6 +640,13 @@ DIM_API int32_t dim_pose_error(dim_ctx *ctx, const double *poses_est, const doub
                                int32_t N, int32_t symmetric, double *err, void *stream) {
   DIM_REQUIRE(ctx && poses_est && poses_gt && points && err && M >= 1 && N >= 1, "dim_pose_error: bad argument");
   return pose_error_launch(poses_est, poses_gt, M, points, N, symmetric, err, (cudaStream_t)stream);
+}
+
+// Proj. 2D / (rot, trans) distances (lib/utils/pose_error.py:55-69, lib/pair_matching/RT_transform.py:162-173)
+DIM_API int32_t dim_pose_error_2d(dim_ctx *ctx, const double *poses_est, const double *poses_gt, int32_t M, const double *points,
+                                  int32_t N, const double *K9_dev, double *err3, void *stream) {
+  DIM_REQUIRE(ctx && poses_est && poses_gt && points && K9_dev && err3 && M >= 1 && N >= 1, "dim_pose_error_2d: bad argument");
+  return pose_error2d_launch(poses_est, poses_gt, M, points, N, K9_dev, err3, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------ training step

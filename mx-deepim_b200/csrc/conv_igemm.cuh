@@ -286,6 +286,49 @@ __device__ __forceinline__ void epilogue_store64(const uint32_t *r, const float 
   }
 }
 
+// 32-column variant (conv1 with two epilogue warps per TMEM lane quadrant): 32 fp32 columns -> 64 bytes per row, staged
+// through a per-warp 2 KB XOR-swizzled tile; lane l then writes 16 B of row i*8 + l/4 (8 rows x 64 B per instruction).
+template <bool SPLIT3>
+__device__ __forceinline__ void epilogue_store32(const uint32_t *r, const float *bias_s, float slope, uint8_t *stage,
+                                                 __nv_bfloat16 *out_hi, __nv_bfloat16 *out_lo, long long my_off,
+                                                 bool my_valid, int lane, bool f16) {
+  __align__(16) uint32_t h[16];
+  __align__(16) uint32_t l[SPLIT3 ? 16 : 4];
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    float v0 = __uint_as_float(r[j]) + bias_s[j], v1 = __uint_as_float(r[j + 1]) + bias_s[j + 1];
+    v0 = v0 > 0.f ? v0 : v0 * slope;
+    v1 = v1 > 0.f ? v1 : v1 * slope;
+    if (!SPLIT3 && f16) {
+      h[j >> 1] = pack2_f16(v0, v1);
+    } else {
+      const uint32_t hh = pack2_bf16(v0, v1);
+      h[j >> 1] = hh;
+      if (SPLIT3) l[j >> 1] = pack2_bf16(v0 - __uint_as_float(hh << 16), v1 - __uint_as_float(hh & 0xFFFF0000u));
+    }
+  }
+  const unsigned vmask = __ballot_sync(0xffffffffu, my_valid);
+  const int ch = lane & 3;
+#pragma unroll
+  for (int pass = 0; pass < (SPLIT3 ? 2 : 1); ++pass) {
+    const uint32_t *src = pass ? l : h;
+    __nv_bfloat16 *out = pass ? out_lo : out_hi;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      *reinterpret_cast<uint4 *>(stage + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) = *reinterpret_cast<const uint4 *>(src + c * 4);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = i * 8 + (lane >> 2);
+      const long long off = __shfl_sync(0xffffffffu, my_off, row);
+      if ((vmask >> row) & 1u)
+        *reinterpret_cast<uint4 *>(out + off + ch * 8) =
+            *reinterpret_cast<const uint4 *>(stage + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));
+    }
+    __syncwarp();
+  }
+}
+
 // generic epilogue of the training-step kernels (see ConvKParams): 64 channels of one output pixel per thread
 __device__ __forceinline__ void epilogue_generic64(const uint32_t *r, const ConvKParams &p, const float *bias_s, uint8_t *stage,
                                                    long long my_off, long long add_off, long long mask_off, bool my_valid,
@@ -764,9 +807,11 @@ __global__ void __launch_bounds__(192) conv1_strip_kernel(const __grid_constant_
 // Strip s of the chunk (input row g_lo + s) lives in ring slot s % STAGES from its TMA fill until the MMAs of output
 // row s (its last user) have completed (tcgen05.commit -> empty barrier).  L2 -> SM traffic and the TMA writes into
 // shared memory drop 4x (plus a 3-row halo per chunk); MMA sequence, accumulators, epilogue are those of the strip
-// kernel.  One CTA per SM (64 KB resident weights + an 8-deep ring), grid = column tiles x chunks.
+// kernel.  One CTA per SM (64 KB resident weights + an 8-deep ring), grid = column tiles x chunks.  With a single CTA per SM the
+// per-tile epilogue (64 columns: ~2.6k cycles on 4 warps) is longer than the tile's 0.9k cycles of MMAs, so EIGHT epilogue
+// warps share it: two per TMEM lane quadrant, 32 accumulator columns each (320 threads).
 template <int STAGES, bool SPLIT3>
-__global__ void __launch_bounds__(192) conv1_roll_kernel(const __grid_constant__ ConvKParams p, const int rows_total,
+__global__ void __launch_bounds__(320) conv1_roll_kernel(const __grid_constant__ ConvKParams p, const int rows_total,
                                                          const int rows_per_chunk, const int chunks_per_col,
                                                          const int strip_bytes /*per precision, multiple of 128*/) {
   constexpr uint32_t ACC_COLS = 64, TMEM_COLS = 128;
@@ -803,7 +848,7 @@ __global__ void __launch_bounds__(192) conv1_roll_kernel(const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);
-      ptx::mbar_init(&tmem_empty_bar[a], 4);
+      ptx::mbar_init(&tmem_empty_bar[a], 8);  // 8 epilogue warps
     }
     ptx::mbar_init(res_bar, 1);
     ptx::fence_barrier_init();
@@ -884,8 +929,9 @@ __global__ void __launch_bounds__(192) conv1_roll_kernel(const __grid_constant__
       }
     }
   } else {
-    const int quad = warp & 3;
+    const int quad = warp & 3, half = (warp - 2) >> 2;  // TMEM lane quadrant of this warp, its 32-column half
     const int m = quad * 32 + lane;
+    uint8_t *stg = epi + (warp - 2) * 2048;
     int as = 0;
     uint32_t aph = 0;
     for (int t = 0; t < n_rows; ++t) {
@@ -895,15 +941,14 @@ __global__ void __launch_bounds__(192) conv1_roll_kernel(const __grid_constant__
       const bool valid = (m < p.BW) && (n_img < p.Bn) && (oh < p.Ho) && (ow < p.Wo);
       ptx::mbar_wait(&tmem_full_bar[as], aph);
       ptx::tc_fence_after();
-      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)as * ACC_COLS;
-      const long long my_off = (((long long)n_img * p.out_Hp + oh + p.out_py) * p.out_Wp + ow + p.out_px) * 64;
-      uint32_t r[64];
+      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)as * ACC_COLS + (uint32_t)half * 32u;
+      const long long my_off = (((long long)n_img * p.out_Hp + oh + p.out_py) * p.out_Wp + ow + p.out_px) * 64 + half * 32;
+      uint32_t r[32];
       ptx::tmem_ld_32x32(trow, r);
-      ptx::tmem_ld_32x32(trow + 32, r + 32);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
-      epilogue_store64<SPLIT3>(r, bias_s, p.slope, epi + (warp - 2) * 4096, p.out_hi, p.out_lo, my_off, valid, lane, p.f16 != 0);
+      epilogue_store32<SPLIT3>(r, bias_s + half * 32, p.slope, stg, p.out_hi, p.out_lo, my_off, valid, lane, p.f16 != 0);
       if (++as == 2) { as = 0; aph ^= 1u; }
     }
   }

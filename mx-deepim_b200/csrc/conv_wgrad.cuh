@@ -132,14 +132,16 @@ __global__ void __launch_bounds__(192) conv_wgrad_kernel(const __grid_constant__
         ptx::tc_fence_after();
         const uint32_t a0 = ptx::smem_u32(smem + s * S::STAGE_BYTES);
         const uint32_t b0 = a0 + S::A_BYTES;
+        if (ptx::elect_one()) {  // one election per K-block; descriptors advance by (bytes >> 4)
+          const uint64_t da0 = ptx::umma_desc_mn(a0, 8192, 1024, 2u);
+          const uint64_t db0 = BN >= 64 ? ptx::umma_desc_mn(b0, 8192, 1024, 2u) : ptx::umma_desc_mn(b0, 4096, 512, 4u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {  // 64 pixels = 4 x UMMA_K 16
-          const uint64_t da = ptx::umma_desc_mn(a0 + k * 2048, 8192, 1024, 2u);
-          const uint64_t db = BN >= 64 ? ptx::umma_desc_mn(b0 + k * 2048, 8192, 1024, 2u)
-                                       : ptx::umma_desc_mn(b0 + k * 1024, 4096, 512, 4u);
-          ptx::umma_f16(tmem_base, da, db, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)  // 64 pixels = 4 x UMMA_K 16
+            ptx::umma_f16_raw(tmem_base, da0 + (uint64_t)(k * 128), db0 + (uint64_t)(k * (BN >= 64 ? 128 : 64)), p.idesc,
+                              (kb > kb0 || k > 0) ? 1u : 0u);
+          ptx::umma_commit_raw(&empty_bar[s]);
         }
-        ptx::umma_commit(&empty_bar[s]);
+        __syncwarp();
         if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
       ptx::umma_commit(done_bar);
@@ -274,13 +276,14 @@ __global__ void __launch_bounds__(192) conv1_wgrad_kernel(const __grid_constant_
         ptx::tc_fence_after();
         const uint32_t a0 = ptx::smem_u32(smem + s * S::STAGE_BYTES);
         const uint32_t b0 = a0 + S::A_BYTES;
+        if (ptx::elect_one()) {
+          const uint64_t da0 = ptx::umma_desc_mn(a0, 4096, 512, 4u), db0 = ptx::umma_desc_mn(b0, 8192, 1024, 2u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t da = ptx::umma_desc_mn(a0 + k * 1024, 4096, 512, 4u);
-          const uint64_t db = ptx::umma_desc_mn(b0 + k * 2048, 8192, 1024, 2u);
-          ptx::umma_f16(tmem_base, da, db, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)
+            ptx::umma_f16_raw(tmem_base, da0 + (uint64_t)(k * 64), db0 + (uint64_t)(k * 128), p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          ptx::umma_commit_raw(&empty_bar[s]);
         }
-        ptx::umma_commit(&empty_bar[s]);
+        __syncwarp();
         if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
       ptx::umma_commit(done_bar);

@@ -577,6 +577,63 @@ __global__ void __launch_bounds__(256) pose_error_kernel(const double *pose_est,
   }
   if (threadIdx.x == 0) out[m] = red[0] / (double)N;
 }
+// Average re-projection error in 2D (lib/utils/pose_error.py:27-69 `arp_2d`: mean_p | proj(K (R^ p + t^)) - proj(K (R p + t)) |,
+// pixels) and the rotation / translation distance of LM6D_REFINE.evaluate_pose (lib/pair_matching/RT_transform.py:162-173
+// `calc_rt_dist_m`: geodesic angle of R_est^T R_gt in degrees -- the reference's |logm(.)|_F / sqrt(2) -- and |t_gt - t_est|).
+// One block per pose pair; out2 = [M,3]: arp_2d, rot_deg, trans_m.  float64, fixed-order reduction.
+__global__ void __launch_bounds__(256) pose_error2d_kernel(const double *pose_est, const double *pose_gt, const double *pts, int N,
+                                                           const double *K9, double *out3) {
+  __shared__ double Pe[12], Pg[12], Kk[9];
+  __shared__ double red[256];
+  const int m = blockIdx.x;
+  if (threadIdx.x < 12) { Pe[threadIdx.x] = pose_est[12 * m + threadIdx.x]; Pg[threadIdx.x] = pose_gt[12 * m + threadIdx.x]; }
+  if (threadIdx.x < 9) Kk[threadIdx.x] = K9[threadIdx.x];
+  __syncthreads();
+  double acc = 0.0;
+  for (int n = threadIdx.x; n < N; n += 256) {
+    const double x = pts[3 * n], y = pts[3 * n + 1], z = pts[3 * n + 2];
+    double e[3], g[3], ce[3], cg[3];
+    for (int r = 0; r < 3; ++r) {
+      e[r] = ((Pe[4 * r] * x + Pe[4 * r + 1] * y) + Pe[4 * r + 2] * z) + Pe[4 * r + 3];
+      g[r] = ((Pg[4 * r] * x + Pg[4 * r + 1] * y) + Pg[4 * r + 2] * z) + Pg[4 * r + 3];
+    }
+    for (int r = 0; r < 3; ++r) {
+      ce[r] = (Kk[3 * r] * e[0] + Kk[3 * r + 1] * e[1]) + Kk[3 * r + 2] * e[2];
+      cg[r] = (Kk[3 * r] * g[0] + Kk[3 * r + 1] * g[1]) + Kk[3 * r + 2] * g[2];
+    }
+    const double du = ce[0] / ce[2] - cg[0] / cg[2], dv = ce[1] / ce[2] - cg[1] / cg[2];
+    acc += sqrt(du * du + dv * dv);
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out3[3 * m] = N > 0 ? red[0] / (double)N : 0.0;
+    // trace(R_est^T R_gt) = sum_ij R_est[i][j] R_gt[i][j]; the off-diagonal antisymmetric part gives sin for small angles
+    double tr = 0.0;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) tr += Pe[4 * i + j] * Pg[4 * i + j];
+    // M = R_est^T R_gt; sin(theta) = |axis part| = 0.5 * |(M32-M23, M13-M31, M21-M12)|: atan2 keeps precision near 0 and 180
+    double Mx[3][3];
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) Mx[a][b] = (Pe[a] * Pg[b] + Pe[4 + a] * Pg[4 + b]) + Pe[8 + a] * Pg[8 + b];
+    const double sx = Mx[2][1] - Mx[1][2], sy = Mx[0][2] - Mx[2][0], sz = Mx[1][0] - Mx[0][1];
+    const double sn = 0.5 * sqrt((sx * sx + sy * sy) + sz * sz), cs = 0.5 * (tr - 1.0);
+    out3[3 * m + 1] = atan2(sn, cs) * (180.0 / 3.14159265358979323846);
+    const double dx = Pg[3] - Pe[3], dy = Pg[7] - Pe[7], dz = Pg[11] - Pe[11];
+    out3[3 * m + 2] = sqrt((dx * dx + dy * dy) + dz * dz);
+  }
+}
+int pose_error2d_launch(const double *pose_est, const double *pose_gt, int M, const double *pts, int N, const double *K9,
+                        double *out3, cudaStream_t st) {
+  pose_error2d_kernel<<<M, 256, 0, st>>>(pose_est, pose_gt, pts, N, K9, out3);
+  DIM_LAUNCH_CHECK();
+  return 0;
+}
+
 int pose_error_launch(const double *pose_est, const double *pose_gt, int M, const double *pts, int N, int symmetric, double *out,
                       cudaStream_t st) {
   pose_error_kernel<<<M, 256, 0, st>>>(pose_est, pose_gt, pts, N, symmetric, out);

@@ -604,13 +604,13 @@ int net_forward(dim_ctx *ctx, int B, int precision, const float *zoom_factor, fl
         DIM_REQUIRE(smem_bytes <= 227 * 1024, "conv1 (bf16x3): image too wide for the rolling-strip ring");
         static int set1 = 0;
         if (set1 < smem_bytes) { DIM_CHECK(cudaFuncSetAttribute(conv1_roll_kernel<ST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); set1 = smem_bytes; }
-        conv1_roll_kernel<ST, true><<<grid, 192, smem_bytes, st>>>(kp, rows_total, rpc, chunks, strip_bytes);
+        conv1_roll_kernel<ST, true><<<grid, 320, smem_bytes, st>>>(kp, rows_total, rpc, chunks, strip_bytes);
       } else {
         constexpr int ST = 8;
         const int smem_bytes = 16 * 4096 + ST * strip_bytes + (4 * 4096 + 256) + 1024 + 512;
         static int set0 = 0;
         if (set0 < smem_bytes) { DIM_CHECK(cudaFuncSetAttribute(conv1_roll_kernel<ST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); set0 = smem_bytes; }
-        conv1_roll_kernel<ST, false><<<grid, 192, smem_bytes, st>>>(kp, rows_total, rpc, chunks, strip_bytes);
+        conv1_roll_kernel<ST, false><<<grid, 320, smem_bytes, st>>>(kp, rows_total, rpc, chunks, strip_bytes);
       }
       DIM_LAUNCH_CHECK();
       rc = 0;

@@ -52,8 +52,10 @@ struct NetState {
   float *fc6_partial = nullptr;  // [FC6_SPLITS][max_batch][256]
   float *conv_partial = nullptr;
   size_t conv_partial_elems = 0;
-  bool conv1_roll = false;   // conv1 on the rolling-strip kernel (conv1_roll_kernel) instead of the per-row strip kernel
-  int pair_mask = 0;         // bit i: conv layer i runs on the CTA-pair (cta_group::2) kernel (effective_geom in net.cu)
+  // kernel variants; defaults = the measured-best set (tools/conv_lab.py, profiles/r02_conv_lab.json), switchable at run
+  // time through dim_debug_set_option for A/B measurements
+  bool conv1_roll = true;    // conv1 on the rolling-strip kernel (conv1_roll_kernel) instead of the per-row strip kernel
+  int pair_mask = 1 << 1;    // bit i: conv layer i runs on the CTA-pair (cta_group::2) kernel; default: conv2 (N = 128)
   cudaEvent_t *layer_events = nullptr;  // tuning hook: 11 events around the conv layers of the last forward
   bool loaded = false, net_ok = false;
   float *save_h6 = nullptr, *save_h7 = nullptr;

@@ -364,6 +364,23 @@ def refine(weights, meshes, cls_idx, image_observed, pose_init, K, n_iter=4, mea
 
 
 # ---------------------------------------------------------------------------------------- ADD / ADI
+def rt_dist(pose_est, pose_gt):
+    """calc_rt_dist_m (lib/pair_matching/RT_transform.py:162-173): (rotation distance in degrees, translation distance).
+    The reference takes |logm(R_est^T R_gt)|_F / sqrt(2); for rotation matrices that is the geodesic angle, evaluated here
+    as atan2(|axis part|, (trace - 1) / 2)."""
+    M = pose_est[:, :3].T @ pose_gt[:, :3]
+    s = 0.5 * np.linalg.norm([M[2, 1] - M[1, 2], M[0, 2] - M[2, 0], M[1, 0] - M[0, 1]])
+    return float(np.degrees(np.arctan2(s, 0.5 * (np.trace(M) - 1.0)))), float(np.linalg.norm(pose_gt[:, 3] - pose_est[:, 3]))
+
+
+def arp_2d(pose_est, pose_gt, pts, K):
+    """lib/utils/pose_error.py:27-69: mean 2D distance between the projections of the model points under the two poses"""
+    def proj(P):
+        c = (np.asarray(K, np.float64) @ (P[:, :3] @ pts.T + P[:, 3:4])).T
+        return c[:, :2] / c[:, 2:3]
+    return float(np.linalg.norm(proj(pose_est) - proj(pose_gt), axis=1).mean())
+
+
 def add_metric(R_est, t_est, R_gt, t_gt, pts):
     """lib/utils/pose_error.py:72-87"""
     pe = pts @ np.asarray(R_est).T + np.asarray(t_est).reshape(1, 3)

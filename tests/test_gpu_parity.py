@@ -437,6 +437,36 @@ def test_refine_is_deterministic_and_batch_consistent(ctx, loop_case):
         assert (s["poses"][:, 0] - full["poses"][:, 1]).abs().max().item() < tol
 
 
+def test_refine_cuda_graph_replay_equals_eager(ctx, loop_case):
+    """With the caller's buffers reused (`out=`) on a non-default stream the library captures the 4-iteration chain into a
+    CUDA graph on the second call and replays it afterwards: results must be bit-identical to the eagerly enqueued chain,
+    and new inputs written into the same buffers must be honoured by the replay."""
+    from deepim_b200._capi import check, lib
+    c = loop_case
+    img, cls, ini = dev(c["img"]), dev(c["cls"]), dev(c["ini"])
+    check(lib.dim_debug_set_option(ctx._h, b"graph", 0))
+    eager = ctx.refine(img, cls, ini, K, 4, pixel_means_rgb=MEANS)
+    ini2 = dev(c["ini"][[1, 0, 3, 2]])
+    cls2 = dev(c["cls"][[1, 0, 3, 2]])
+    img2 = dev(c["img"][[1, 0, 3, 2]])
+    eager2 = ctx.refine(img2, cls2, ini2, K, 4, pixel_means_rgb=MEANS)
+    check(lib.dim_debug_set_option(ctx._h, b"graph", 1))
+    side = torch.cuda.Stream(device=DEV)
+    out = None
+    for it in range(4):            # eager warm-up, capture + launch, replay, replay
+        with torch.cuda.stream(side):
+            out = ctx.refine(img, cls, ini, K, 4, pixel_means_rgb=MEANS, out=out)
+        side.synchronize()
+        for k in ("poses", "se3", "zoom_factor", "bbox"):
+            assert torch.equal(out[k], eager[k]), (it, k)
+    with torch.cuda.stream(side):  # same addresses, new contents: the replayed graph reads the buffers, not captured values
+        img.copy_(img2); cls.copy_(cls2); ini.copy_(ini2)
+        out = ctx.refine(img, cls, ini, K, 4, pixel_means_rgb=MEANS, out=out)
+    side.synchronize()
+    for k in ("poses", "se3", "zoom_factor", "bbox"):
+        assert torch.equal(out[k], eager2[k]), k
+
+
 def test_refine_host_matches_device_path(ctx, meshes, loop_case):
     c = loop_case
     B = c["B"]

@@ -63,9 +63,14 @@ def main():
         check(lib.dim_debug_set_option(ctx._h, b"graph", 0))
         eager = ctx.refine(img, cls, pose, K, 4, pixel_means_rgb=means)
         check(lib.dim_debug_set_option(ctx._h, b"graph", 1))
+        out = ctx.refine(img, cls, pose, K, 4, pixel_means_rgb=means)   # legacy default stream: never captured, must just work
+        torch.cuda.synchronize()
+        fails += 0 if torch.equal(eager["poses"], out["poses"]) else 1
         out = None
+        side = torch.cuda.Stream(device=dev)
         for it in range(4):  # 1st call eager warm-up, 2nd captures + launches, 3rd / 4th replay
-            out = ctx.refine(img, cls, pose, K, 4, pixel_means_rgb=means, out=out)
+            with torch.cuda.stream(side):
+                out = ctx.refine(img, cls, pose, K, 4, pixel_means_rgb=means, out=out)
             torch.cuda.synchronize()
             ok = all(torch.equal(eager[k], out[k]) for k in ("poses", "se3", "zoom_factor", "bbox"))
             print("B=%d graph call %d: %s" % (B, it, "bitwise-equal to eager" if ok else "DIFFERENT"), flush=True)
