@@ -299,6 +299,12 @@ DIM_API int32_t dim_pose_error(dim_ctx *ctx, const double *poses_est, const doub
 DIM_API int32_t dim_pose_error_2d(dim_ctx *ctx, const double *poses_est, const double *poses_gt, int32_t M, const double *points,
                                   int32_t N, const double *K9_dev, double *err3, void *stream);
 
+/* End-point error of a predicted flow (deepim/core/tester.py:573-589 calc_EPE_one_pair; the non-FAST_TEST evaluation):
+ * flows [B,2,H,W], visible / bg [B,1,H,W] float32 device; out6 [B,6] float64 device =
+ * { sum |gt - pred| over all pixels, pixel count, sum over visible == 1, sum(visible), sum over visible | bg, count }. */
+DIM_API int32_t dim_flow_epe(dim_ctx *ctx, const float *flow_pred, const float *flow_gt, const float *visible, const float *bg,
+                             int32_t B, double *out6, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Training step of the refiner network (train graph: deepim/symbols/deepIM_flownet.py:121-365 decoder,
  * flow / mask / point-matching losses; optimiser: deepim/train.py:296-304 SGD-momentum, one update per inner

@@ -25,6 +25,7 @@ int zoom_gather_launch(dim_ctx *, int mode, const float *src, float *dst, const 
 int zoom_factor_launch(dim_ctx *, const float *, const float *, int C, const float *, int B, const float *K9, float *,
                        int *, int *, cudaStream_t, const float *img_means = nullptr);
 int pose_error_launch(const double *, const double *, int M, const double *, int N, int symmetric, double *, cudaStream_t);
+int epe_launch(const float *, const float *, const float *, const float *, int B, int P, double *, cudaStream_t);
 int pose_error2d_launch(const double *, const double *, int M, const double *, int N, const double *K9, double *, cudaStream_t);
 int group_pick_launch(const float *, const float *, int B, int Ctot, int groups, size_t n, float *, int backward, cudaStream_t);
 int zoom_factor_from_ren_launch(dim_ctx *, const int *, const float *, int B, const float *K9, float *, int *, int *,
@@ -640,6 +641,13 @@ DIM_API int32_t dim_pose_error(dim_ctx *ctx, const double *poses_est, const doub
                                int32_t N, int32_t symmetric, double *err, void *stream) {
   DIM_REQUIRE(ctx && poses_est && poses_gt && points && err && M >= 1 && N >= 1, "dim_pose_error: bad argument");
   return pose_error_launch(poses_est, poses_gt, M, points, N, symmetric, err, (cudaStream_t)stream);
+}
+
+// flow end-point error sums (deepim/core/tester.py:573-589)
+DIM_API int32_t dim_flow_epe(dim_ctx *ctx, const float *flow_pred, const float *flow_gt, const float *visible, const float *bg,
+                             int32_t B, double *out6, void *stream) {
+  DIM_REQUIRE(ctx && flow_pred && flow_gt && visible && bg && out6 && B >= 1, "dim_flow_epe: bad argument");
+  return epe_launch(flow_pred, flow_gt, visible, bg, B, ctx->H * ctx->W, out6, (cudaStream_t)stream);
 }
 
 // Proj. 2D / (rot, trans) distances (lib/utils/pose_error.py:55-69, lib/pair_matching/RT_transform.py:162-173)

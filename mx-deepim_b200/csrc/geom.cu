@@ -577,6 +577,43 @@ __global__ void __launch_bounds__(256) pose_error_kernel(const double *pose_est,
   }
   if (threadIdx.x == 0) out[m] = red[0] / (double)N;
 }
+// End-point error of a predicted flow field (deepim/core/tester.py:573-589 calc_EPE_one_pair): per instance the sums of
+// |flow_gt - flow_pred| over all pixels / the visible ones / visible-or-background, and the three pixel counts.
+// flows [B,2,H,W] (plane order as the graph emits them), visible / bg [B,1,H,W].  out [B,6] float64:
+// epe_all, num_all, epe_viz, num_viz, epe_vizbg, num_vizbg.  One block per instance, fixed-order reduction.
+__global__ void __launch_bounds__(256) epe_kernel(const float *pred, const float *gt, const float *visible, const float *bg, int P,
+                                                  double *out) {
+  __shared__ double red[5][256];
+  const int b = blockIdx.x;
+  const float *p0 = pred + (size_t)b * 2 * P, *g0 = gt + (size_t)b * 2 * P, *v = visible + (size_t)b * P, *bgp = bg + (size_t)b * P;
+  double s_all = 0, s_viz = 0, n_viz = 0, s_vb = 0, n_vb = 0;
+  for (int q = threadIdx.x; q < P; q += 256) {
+    const float dx = g0[q] - p0[q], dy = g0[P + q] - p0[P + q];
+    const double d = (double)sqrtf(dx * dx + dy * dy);  // np.sqrt(np.square(x) + np.square(y)) on float32 arrays
+    const bool vz = v[q] == 1.0f, vb = (v[q] != 0.0f) || (bgp[q] != 0.0f);
+    s_all += d;
+    if (vz) s_viz += d;
+    n_viz += (double)v[q];
+    if (vb) { s_vb += d; n_vb += 1.0; }
+  }
+  red[0][threadIdx.x] = s_all; red[1][threadIdx.x] = s_viz; red[2][threadIdx.x] = n_viz; red[3][threadIdx.x] = s_vb; red[4][threadIdx.x] = n_vb;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s)
+      for (int k = 0; k < 5; ++k) red[k][threadIdx.x] += red[k][threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out[6 * b] = red[0][0]; out[6 * b + 1] = (double)P; out[6 * b + 2] = red[1][0]; out[6 * b + 3] = red[2][0];
+    out[6 * b + 4] = red[3][0]; out[6 * b + 5] = red[4][0];
+  }
+}
+int epe_launch(const float *pred, const float *gt, const float *visible, const float *bg, int B, int P, double *out, cudaStream_t st) {
+  epe_kernel<<<B, 256, 0, st>>>(pred, gt, visible, bg, P, out);
+  DIM_LAUNCH_CHECK();
+  return 0;
+}
+
 // Average re-projection error in 2D (lib/utils/pose_error.py:27-69 `arp_2d`: mean_p | proj(K (R^ p + t^)) - proj(K (R p + t)) |,
 // pixels) and the rotation / translation distance of LM6D_REFINE.evaluate_pose (lib/pair_matching/RT_transform.py:162-173
 // `calc_rt_dist_m`: geodesic angle of R_est^T R_gt in degrees -- the reference's |logm(.)|_F / sqrt(2) -- and |t_gt - t_est|).

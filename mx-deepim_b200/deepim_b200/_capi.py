@@ -61,6 +61,7 @@ SIGNATURES = {
     "dim_launch_count": (i64, [i32]),
     "dim_pose_error": (i32, [vp, vp, vp, i32, vp, i32, i32, vp, vp]),
     "dim_pose_error_2d": (i32, [vp, vp, vp, i32, vp, i32, vp, vp, vp]),
+    "dim_flow_epe": (i32, [vp, vp, vp, vp, vp, i32, vp, vp]),
     "dim_train_create": (i32, [vp, i32]),
     "dim_train_param_count": (i64, [vp]),
     "dim_train_param_info": (i32, [i32, C.POINTER(C.c_char_p), C.POINTER(i64), C.POINTER(i64)]),

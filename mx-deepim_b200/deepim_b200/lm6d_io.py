@@ -167,7 +167,9 @@ class LM6DRefine:
 def evaluate(dataset: LM6DRefine, weights, K, symmetric=("eggbox", "glue", "bowl", "cup"), n_iter=4, max_batch=16, device=0,
              precision="fp16"):
     """Batched pred_eval (deepim/core/tester.py:50-527 without its batch = 1 limit): refine every pair of the image set
-    and score ADD (ADI for the symmetric classes).  Returns (evaluate_pose_add result, poses_est [n_iter,M,3,4], poses_gt)."""
+    and score it the way the reference's dataset class does: ADD / ADI accuracy + AUC (evaluate_pose_add), 5 cm 5 deg
+    (evaluate_pose) and Proj. 2D (evaluate_pose_arp_2d); the last two under res["rot_trans"] / res["arp_2d"].
+    Returns (evaluate_pose_add result + the two extra tables, poses_est [n_iter,M,3,4], poses_gt)."""
     from . import pose_eval
     from .refiner import PoseRefiner
     meshes = [dataset.mesh(c) for c in dataset.classes]
@@ -185,5 +187,8 @@ def evaluate(dataset: LM6DRefine, weights, K, symmetric=("eggbox", "glue", "bowl
     poses = ref.refine(imgs, cls_idx, init)
     res = pose_eval.evaluate_pose_add(ref.ctx, poses, gt, cls_idx, [dataset.points(c) for c in dataset.classes],
                                       [dataset.diameters[c] for c in dataset.classes], [c in symmetric for c in dataset.classes])
+    pts_all = [dataset.points(c) for c in dataset.classes]
+    res["rot_trans"] = pose_eval.evaluate_pose(ref.ctx, poses, gt, cls_idx, pts_all, K, class_names=list(dataset.classes))
+    res["arp_2d"] = pose_eval.evaluate_pose_arp_2d(ref.ctx, poses, gt, cls_idx, pts_all, K, class_names=list(dataset.classes))
     ref.close()
     return res, poses, gt

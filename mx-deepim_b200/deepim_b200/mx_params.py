@@ -126,3 +126,93 @@ def save_checkpoint(prefix, epoch, arg_params, aux_params=None):
     d = {"arg:" + k: v for k, v in arg_params.items()}
     d.update({"aux:" + k: v for k, v in (aux_params or {}).items()})
     save("%s-%04d.params" % (prefix, epoch), d)
+
+
+# ----------------------------------------------------------------------------------------- <prefix>-symbol.json
+# MXNet writes the network graph next to the checkpoint (`Module.save_checkpoint` -> `<prefix>-symbol.json`): a JSON object
+# {"nodes": [{"op": "null" | "<Operator>", "name": ..., "attrs" (>= 1.0) | "attr" | "param" (older): {str: str},
+#             "inputs": [[node_id, output_index, version], ...]}, ...],
+#  "arg_nodes": [ids of the "null" nodes = variables], "node_row_ptr": [...], "heads": [[node_id, index, version], ...],
+#  "attrs": {"mxnet_version": ["int", 10200]}}.
+# The B200 path does not execute the graph (it IS the FlowNetS tower of deepim/symbols/deepIM_flownet.py:53-116); reading the
+# file serves to CHECK that a checkpoint belongs to this architecture before its tensors are repacked.
+def load_symbol_json(path_or_text):
+    import json
+    import os
+    text = open(path_or_text).read() if os.path.exists(str(path_or_text)) else path_or_text
+    g = json.loads(text)
+    if "nodes" not in g or "arg_nodes" not in g:
+        raise ValueError("not an MXNet symbol file (no 'nodes' / 'arg_nodes')")
+    nodes = []
+    for n in g["nodes"]:
+        attrs = n.get("attrs", n.get("attr", n.get("param", {}))) or {}
+        nodes.append({"op": n["op"], "name": n["name"], "attrs": {str(k): str(v) for k, v in attrs.items()},
+                      "inputs": [int(i[0]) for i in n.get("inputs", [])]})
+    return {"nodes": nodes, "arg_nodes": [int(i) for i in g["arg_nodes"]], "heads": [int(h[0]) for h in g.get("heads", [])],
+            "arguments": [nodes[int(i)]["name"] for i in g["arg_nodes"]]}
+
+
+def _tuple_attr(v):
+    return tuple(int(x) for x in v.strip("()[] ").replace(" ", "").split(",") if x != "")
+
+
+def check_flownet_symbol(sym, conv_specs=None):
+    """Raise ValueError unless every Convolution of the FlowNetS tower (name, num_filter, kernel, stride, pad as in
+    deepIM_flownet.py:63-107) and fc6 / fc7 (FullyConnected, 256 hidden) are present in the symbol with those attributes."""
+    from . import synth
+    conv_specs = conv_specs or synth.CONV_SPECS
+    by_name = {n["name"]: n for n in sym["nodes"]}
+    for name, cout, cin, k, s, p in conv_specs:
+        n = by_name.get(name)
+        if n is None or n["op"] != "Convolution":
+            raise ValueError("symbol has no Convolution named %r" % name)
+        a = n["attrs"]
+        got = (int(a.get("num_filter", -1)), _tuple_attr(a.get("kernel", "()")), _tuple_attr(a.get("stride", "(1,1)")),
+               _tuple_attr(a.get("pad", "(0,0)")))
+        if got != (cout, (k, k), (s, s), (p, p)):
+            raise ValueError("%s: symbol says %r, FlowNetS expects %r" % (name, got, (cout, (k, k), (s, s), (p, p))))
+        if name + "_weight" not in sym["arguments"]:
+            raise ValueError("%s_weight is not an argument of the symbol" % name)
+    for name in ("fc6", "fc7"):
+        n = by_name.get(name)
+        if n is None or n["op"] != "FullyConnected" or int(n["attrs"].get("num_hidden", -1)) != 256:
+            raise ValueError("symbol has no FullyConnected %r with 256 hidden units" % name)
+    return True
+
+
+def save_symbol_json(path, conv_specs=None):
+    """Write the FAST_TEST inference graph (tower + fc6 / fc7 + rot / trans heads) in MXNet's symbol-file layout (testing aid)."""
+    import json
+    from . import synth
+    conv_specs = conv_specs or synth.CONV_SPECS
+    nodes, args = [], []
+
+    def var(name):
+        nodes.append({"op": "null", "name": name, "inputs": []})
+        args.append(len(nodes) - 1)
+        return len(nodes) - 1
+
+    def op(kind, name, inputs, attrs):
+        nodes.append({"op": kind, "name": name, "attrs": attrs, "inputs": [[i, 0, 0] for i in inputs]})
+        return len(nodes) - 1
+
+    x = var("data")
+    for name, cout, cin, k, s, p in conv_specs:
+        w, b = var(name + "_weight"), var(name + "_bias")
+        x = op("Convolution", name, [x, w, b], {"num_filter": str(cout), "kernel": "(%d, %d)" % (k, k), "stride": "(%d, %d)" % (s, s),
+                                                 "pad": "(%d, %d)" % (p, p)})
+        x = op("LeakyReLU", "ReLU_" + name, [x], {"act_type": "leaky", "slope": "0.1"})
+    x = op("Flatten", "flatten", [x], {})
+    for name in ("fc6", "fc7"):
+        w, b = var(name + "_weight"), var(name + "_bias")
+        x = op("FullyConnected", name, [x, w, b], {"num_hidden": "256"})
+        x = op("LeakyReLU", "ReLU_" + name, [x], {"act_type": "leaky", "slope": "0.1"})
+    heads = []
+    for name, nh in (("rot", 4), ("trans", 3)):
+        w, b = var(name + "_weight"), var(name + "_bias")
+        heads.append(op("FullyConnected", name, [x, w, b], {"num_hidden": str(nh)}))
+    g = {"nodes": nodes, "arg_nodes": args, "node_row_ptr": list(range(len(nodes) + 1)), "heads": [[h, 0, 0] for h in heads],
+         "attrs": {"mxnet_version": ["int", 10200]}}
+    with open(path, "w") as f:
+        json.dump(g, f)
+    return path

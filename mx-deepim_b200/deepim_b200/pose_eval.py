@@ -59,6 +59,21 @@ def pose_errors_2d(ctx, poses_est, poses_gt, points, K):
     return out
 
 
+def flow_epe(ctx, flow_pred, flow_gt, visible, bg):
+    """calc_EPE_one_pair (deepim/core/tester.py:573-589) for a batch on the device: float32 CUDA tensors flow_* [B,2,H,W],
+    visible / bg [B,1,H,W].  Returns a dict of float64 numpy arrays [B]: epe_all, num_all, epe_viz, num_viz, epe_vizbg,
+    num_vizbg (sums, as the reference accumulates them before dividing)."""
+    B = flow_pred.shape[0]
+    for t in (flow_pred, flow_gt, visible, bg):
+        if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+            raise TypeError("flow_epe expects contiguous float32 CUDA tensors")
+    out = torch.empty((B, 6), dtype=torch.float64, device=ctx.device)
+    check(lib.dim_flow_epe(ctx._h, _p(flow_pred), _p(flow_gt), _p(visible), _p(bg), B, _p(out),
+                           C.c_void_p(torch.cuda.current_stream(ctx.device).cuda_stream)))
+    o = out.cpu().numpy()
+    return {k: o[:, i] for i, k in enumerate(("epe_all", "num_all", "epe_viz", "num_viz", "epe_vizbg", "num_vizbg"))}
+
+
 RT_Z_FLIP = np.array([[-1.0, 0, 0, 0], [0, -1.0, 0, 0], [0, 0, 1.0, 0]])  # eggbox: 180 deg about z (LM6D_REFINE.py:304-307)
 
 

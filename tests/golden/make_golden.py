@@ -129,6 +129,32 @@ def main():
     np.savez_compressed(os.path.join(HERE, "ref_pose_error.npz"), pts=pts, R_est=Re, t_est=te, R_gt=Rg, t_gt=tg,
                         add=pose_error.add(Re, te, Rg, tg, pts), adi=pose_error.adi(Re, te, Rg, tg, pts))
 
+    # ---- rotation / translation distance + average 2D re-projection error: the inputs of LM6D_REFINE.evaluate_pose
+    # (5 cm 5 deg, lib/dataset/LM6D_REFINE.py:278-371) and evaluate_pose_arp_2d (Proj. 2D, l.514-)
+    rng2 = np.random.default_rng(77)
+    M = 48
+    Kc = np.array([[572.4114, 0, 325.2611], [0, 573.57043, 242.04899], [0, 0, 1.0]])
+    pts2 = rng2.normal(size=(300, 3)) * 0.04
+    est, gt = np.zeros((M, 3, 4)), np.zeros((M, 3, 4))
+    rd, td, arp, re_deg = np.zeros(M), np.zeros(M), np.zeros(M), np.zeros(M)
+    for k in range(M):
+        Rg = rand_rot(rng2)
+        ang = rng2.normal(0, [0.5, 4.0, 30.0][k % 3], size=3) * np.pi / 180.0      # tiny / moderate / large perturbations
+        cx, cy, cz = np.cos(ang); sx, sy, sz = np.sin(ang)
+        Rd = (np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]]) @ np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+              @ np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]]))
+        if k == M - 1:
+            Rd = np.diag([-1.0, -1.0, 1.0])                                             # exactly 180 degrees
+        if k == M - 2:
+            Rd = np.eye(3)                                                              # identical rotation
+        gt[k, :, :3], gt[k, :, 3] = Rg, [rng2.uniform(-.1, .1), rng2.uniform(-.1, .1), rng2.uniform(.5, 1.1)]
+        est[k, :, :3], est[k, :, 3] = Rd @ Rg, gt[k, :, 3] + rng2.normal(0, [0.002, 0.02, 0.06][k % 3], size=3)
+        rd[k], td[k] = RT.calc_rt_dist_m(est[k], gt[k])
+        re_deg[k] = pose_error.re(est[k, :, :3], gt[k, :, :3])
+        arp[k] = pose_error.arp_2d(est[k, :, :3], est[k, :, 3], gt[k, :, :3], gt[k, :, 3], pts2, Kc)
+    np.savez_compressed(os.path.join(HERE, "ref_pose_eval.npz"), pts=pts2, K=Kc, poses_est=est, poses_gt=gt, rot_deg=np.real(rd),
+                        trans_m=td, re_deg=np.real(re_deg), arp_2d=arp)
+
     # ---- image.transform (lib/utils/image.py:583-594)
     try:
         from lib.utils.image import transform

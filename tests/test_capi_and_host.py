@@ -205,3 +205,29 @@ def test_simpson_rule_and_obj_parser(tmp_path):
     assert np.array_equal(m.verts[3:6], np.array([[0, 0, 0], [1, 1, 0], [0, 1, 0]], np.float32))
     assert np.array_equal(m.verts[6:9], m.verts[[0, 1, 2]]) and np.array_equal(m.normals, np.tile([[0, 0, 1]], (9, 1)))
     assert np.array_equal(m.uvs[2], [1, 1])
+
+
+def test_symbol_json_reader_and_architecture_check(tmp_path):
+    """<prefix>-symbol.json (MXNet's graph file next to <prefix>-%04d.params): read the node / attribute layout of MXNet >= 1.0
+    ("attrs") and of older files ("attr" / "param"), and refuse a checkpoint whose graph is not the FlowNetS tower."""
+    import json
+    from deepim_b200 import mx_params, synth
+    path = mx_params.save_symbol_json(os.path.join(str(tmp_path), "deepim-symbol.json"))
+    sym = mx_params.load_symbol_json(path)
+    assert mx_params.check_flownet_symbol(sym)
+    assert sym["arguments"][0] == "data" and "fc6_weight" in sym["arguments"] and "rot_bias" in sym["arguments"]
+    assert [sym["nodes"][h]["name"] for h in sym["heads"]] == ["rot", "trans"]
+    w = synth.make_weights(0)
+    assert all(a in w for a in sym["arguments"] if a != "data")          # argument names = checkpoint keys (load_model.py:19-27)
+    g = json.load(open(path))
+    for n in g["nodes"]:                                                  # pre-1.0 spelling of the attribute dict
+        if "attrs" in n:
+            n["attr"] = n.pop("attrs")
+    assert mx_params.check_flownet_symbol(mx_params.load_symbol_json(json.dumps(g)))
+    for n in g["nodes"]:
+        if n["name"] == "conv3":
+            n["attr"]["stride"] = "(1, 1)"
+    with pytest.raises(ValueError):
+        mx_params.check_flownet_symbol(mx_params.load_symbol_json(json.dumps(g)))
+    with pytest.raises(ValueError):
+        mx_params.load_symbol_json(json.dumps({"foo": 1}))

@@ -38,3 +38,61 @@ def test_evaluate_dataset_directory(tmp_path):
     direct = ref.refine(imgs, np.array([0, 0, 1, 1], np.int32), init)
     ref.close()
     assert np.abs(direct - poses).max() < 1e-9
+
+
+def test_rot_trans_distance_and_arp_2d_against_reference_golden(golden_dir):
+    """dim_pose_error_2d against the live reference's calc_rt_dist_m / re / arp_2d (tests/golden/ref_pose_eval.npz), then the
+    5 cm 5 deg and Proj. 2D tables (LM6D_REFINE.evaluate_pose / evaluate_pose_arp_2d) recomputed from the fixture's errors."""
+    import os
+    from deepim_b200 import pose_eval
+    from deepim_b200.context import Context
+    g = np.load(os.path.join(golden_dir, "ref_pose_eval.npz"))
+    ctx = Context(0, max_batch=1, height=64, width=64, max_classes=1, max_verts=8, max_faces=8)
+    e = pose_eval.pose_errors_2d(ctx, g["poses_est"], g["poses_gt"], g["pts"], g["K"]).cpu().numpy()
+    assert np.abs(e[:, 0] - g["arp_2d"]).max() < 1e-9
+    assert np.abs(e[:, 1] - g["rot_deg"]).max() < 1e-7 and np.abs(e[:, 1] - g["re_deg"]).max() < 1e-7
+    assert np.abs(e[:, 2] - g["trans_m"]).max() < 1e-13
+    M = len(e)
+    cls = (np.arange(M) % 2).astype(np.int32)
+    est2 = np.stack([g["poses_est"], g["poses_gt"]])                 # "iteration 2" = perfect poses
+    rt = pose_eval.evaluate_pose(ctx, est2, g["poses_gt"], cls, [g["pts"], g["pts"]], g["K"], class_names=["a", "b"])
+    for c in (0, 1):
+        sel = cls == c
+        want = 100.0 * np.logical_and(g["rot_deg"][sel] < 5, g["trans_m"][sel] < 0.05).mean()
+        assert abs(rt["classes"][c]["space_acc"][0, 4] - want) < 1e-9
+        assert rt["classes"][c]["space_acc"][1, 4] == 100.0
+    assert abs(rt["mean"]["5cm5deg"][0] - np.mean([rt["classes"][c]["space_acc"][0, 4] for c in (0, 1)])) < 1e-9
+    a2 = pose_eval.evaluate_pose_arp_2d(ctx, est2, g["poses_gt"], cls, [g["pts"], g["pts"]], g["K"])
+    for c in (0, 1):
+        sel = cls == c
+        assert abs(a2["classes"][c]["5"][0] - 100.0 * (g["arp_2d"][sel] < 5).mean()) < 1e-9
+        assert a2["classes"][c]["5"][1] == 100.0 and 0.0 <= a2["classes"][c]["auc"][0] <= a2["classes"][c]["auc"][1] <= 100.0
+    # eggbox: an estimate off by 180 degrees about z is scored after the symmetry flip (LM6D_REFINE.py:304-307)
+    flip = g["poses_gt"][:4].copy()
+    flip[:, :, :3] = flip[:, :, :3] @ np.diag([-1.0, -1.0, 1.0])
+    r_e = pose_eval.evaluate_pose(ctx, flip[None], g["poses_gt"][:4], np.zeros(4, np.int32), [g["pts"]], g["K"], class_names=["eggbox"])
+    r_n = pose_eval.evaluate_pose(ctx, flip[None], g["poses_gt"][:4], np.zeros(4, np.int32), [g["pts"]], g["K"], class_names=["ape"])
+    assert r_e["classes"][0]["rot_acc"][0, 0] == 100.0 and r_n["classes"][0]["rot_acc"][0, 9] == 0.0
+    ctx.close()
+
+
+def test_flow_epe_matches_the_reference_formula():
+    """dim_flow_epe = calc_EPE_one_pair (deepim/core/tester.py:573-589), restated in numpy on the same arrays."""
+    from deepim_b200 import pose_eval
+    from deepim_b200.context import Context
+    H, W, B = 60, 80, 3
+    ctx = Context(0, max_batch=B, height=H, width=W, max_classes=1, max_verts=8, max_faces=8)
+    rng = np.random.default_rng(4)
+    pred = (rng.normal(size=(B, 2, H, W)) * 3).astype(np.float32)
+    gt = (rng.normal(size=(B, 2, H, W)) * 3).astype(np.float32)
+    vis = (rng.uniform(size=(B, 1, H, W)) > 0.6).astype(np.float32)
+    bg = np.logical_and(vis == 0, rng.uniform(size=(B, 1, H, W)) > 0.5).astype(np.float32)
+    dev = torch.device("cuda", 0)
+    got = pose_eval.flow_epe(ctx, *[torch.from_numpy(a).to(dev) for a in (pred, gt, vis, bg)])
+    for b in range(B):
+        d = np.sqrt(np.square(gt[b, 0] - pred[b, 0]) + np.square(gt[b, 1] - pred[b, 1]))
+        v, vb = vis[b, 0] == 1, np.logical_or(vis[b, 0], bg[b, 0])
+        assert abs(got["epe_all"][b] - d.astype(np.float64).sum()) < 1e-6 * d.sum() and got["num_all"][b] == d.size
+        assert abs(got["epe_viz"][b] - d[v].astype(np.float64).sum()) < 1e-6 * d.sum() and got["num_viz"][b] == v.sum()
+        assert abs(got["epe_vizbg"][b] - d[vb].astype(np.float64).sum()) < 1e-6 * d.sum() and got["num_vizbg"][b] == vb.sum()
+    ctx.close()

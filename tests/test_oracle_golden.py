@@ -90,3 +90,15 @@ def test_train_labels_match_reference(golden_dir):
         np.testing.assert_allclose(Td, g["label_trans"][k], atol=1e-12)
         KT = g["label_K"] @ O.calc_se3_f32(g["pose_src"][k], tgt32[k]).astype(np.float64)
         np.testing.assert_allclose(KT, g["label_KT"][k], rtol=0, atol=2e-4)  # float32 se3 storage, BLAS order
+
+
+def test_rt_dist_and_arp_2d_against_reference_golden(golden_dir):
+    """calc_rt_dist_m (RT_transform.py:162-173), re and arp_2d (pose_error.py:27-69, 127-132) of the live reference on 48
+    pose pairs (0.5 / 4 / 30 degree perturbations, an exact 180 degree and an identity case): the inputs of the 5 cm 5 deg and
+    Proj. 2D tables (LM6D_REFINE.evaluate_pose / evaluate_pose_arp_2d)."""
+    g = np.load(os.path.join(golden_dir, "ref_pose_eval.npz"))
+    for k in range(len(g["rot_deg"])):
+        rd, td = O.rt_dist(g["poses_est"][k], g["poses_gt"][k])
+        assert abs(rd - g["rot_deg"][k]) < 1e-9 and abs(rd - g["re_deg"][k]) < 1e-9
+        assert abs(td - g["trans_m"][k]) < 1e-14
+        assert abs(O.arp_2d(g["poses_est"][k], g["poses_gt"][k], g["pts"], g["K"]) - g["arp_2d"][k]) < 1e-10
