@@ -32,7 +32,7 @@ def test_evaluate_dataset_directory(tmp_path):
     assert len(res["mean"]["auc"]) == 4
     # the meshes loaded from disk (un-rolled OBJ) drive the same refinement as the in-memory ones
     from deepim_b200.refiner import PoseRefiner
-    ref = PoseRefiner([meshes[c] for c in classes], w, max_batch=4, n_iter=4)
+    ref = PoseRefiner([meshes[c] for c in classes], w, max_batch=3, n_iter=4)   # same device batches (3 + 1) as evaluate()
     imgs = np.stack([ds.load_pair(c, p)["image_observed"] for c in classes for p in ds.pairs(c)])
     init = np.stack([ds.load_pair(c, p)["pose_rendered"] for c in classes for p in ds.pairs(c)])
     direct = ref.refine(imgs, np.array([0, 0, 1, 1], np.int32), init)

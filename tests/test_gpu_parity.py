@@ -428,9 +428,10 @@ def test_refine_is_deterministic_and_batch_consistent(ctx, loop_case):
                    precision=capi.PREC_FP16)
     assert torch.equal(p["bbox"], a["bbox"][:, perm])
     assert (p["poses"] - a["poses"][:, perm]).abs().max().item() < 1e-5
-    # a single instance alone (different tile / split-K schedule -> different fp32 summation order;
-    # the difference is then carried through 4 render-and-compare iterations)
-    for prec, tol in ((capi.PREC_BF16X3, 1e-4), (capi.PREC_FP16, 1e-4), (capi.PREC_BF16, 2e-3)):
+    # a single instance alone: the CTA-pair kernel of conv2 and fc6 pick their split-K by batch size -> a different fp32
+    # summation order, i.e. rounding-level differences in se3 that 4 FREE-RUNNING render-and-compare iterations amplify
+    # (one silhouette pixel of the uint8 re-render).  Not a parity bound: those are the teacher-forced tests.
+    for prec, tol in ((capi.PREC_BF16X3, 5e-4), (capi.PREC_FP16, 5e-4), (capi.PREC_BF16, 2e-3)):
         full = ctx.refine(*args, pixel_means_rgb=MEANS, precision=prec)
         s = ctx.refine(dev(c["img"][1:2]), dev(c["cls"][1:2]), dev(c["ini"][1:2]), K, 4, pixel_means_rgb=MEANS,
                        precision=prec)

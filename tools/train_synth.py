@@ -36,6 +36,9 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--out", default="gpurun_out/train_synth.json")
     ap.add_argument("--save", default="", help="optional .npz path for the trained inference weights")
+    ap.add_argument("--overfit", action="store_true", help="train on ONE fixed batch and evaluate on exactly those pairs (sanity: "
+                    "train graph and test graph agree on every convention)")
+    ap.add_argument("--clean-eval", action="store_true", help="evaluate on clean renders (black background) like the training pairs")
     args = ap.parse_args()
     import torch
     from deepim_b200 import _capi as capi
@@ -53,7 +56,9 @@ def main():
     pts = mesh.verts.astype(np.float64)
 
     # held-out evaluation pairs: observed = render composited over noise (what the refiner sees at test time)
-    obs, ini = synth.sample_pose_pairs(args.eval_n, 900001)
+    if args.overfit:
+        args.eval_n = B
+    obs, ini = synth.sample_pose_pairs(args.eval_n, (10_000 + 1) if args.overfit else 900001)
     ev = []
     for a in range(0, args.eval_n, 16):
         n = min(16, args.eval_n - a)
@@ -61,6 +66,8 @@ def main():
         r = ctx.render(cls, torch.from_numpy(obs[a:a + n].astype(np.float32)).to(dev), K, want=("bgr", "mask"))
         g = torch.Generator(device=dev); g.manual_seed(a)
         bg = torch.randint(0, 256, r["bgr"].shape, generator=g, device=dev, dtype=torch.int32).to(torch.uint8)
+        if args.overfit or args.clean_eval:
+            bg = torch.zeros_like(bg)
         u8 = torch.where(r["mask"].permute(0, 2, 3, 1) > 0, r["bgr"].to(torch.uint8), bg).contiguous()
         ev.append((ctx.transform_image_u8(u8, means), cls, torch.from_numpy(ini[a:a + n]).to(dev), a, n))
 
@@ -87,7 +94,7 @@ def main():
     print("step 0", log["evals"][-1]["add_mean_m"], flush=True)
     t0 = time.time()
     for step in range(1, args.steps + 1):
-        batch, cls, tgt, depth_gt = trainer.make_device_batch(ctx, [mesh], B, 10_000 + step, K, means)
+        batch, cls, tgt, depth_gt = trainer.make_device_batch(ctx, [mesh], B, 10_000 + (1 if args.overfit else step), K, means)
         objs = trainer.fit_batch(tr, batch, cls, tgt, depth_gt, K, n_inner=4)
         if step % 10 == 0 or step == 1:
             o = [round(float(v), 5) for v in objs.cpu().numpy()]
