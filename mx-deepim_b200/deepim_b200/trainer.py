@@ -241,10 +241,12 @@ class Trainer:
         return (raw.astype(np.uint32) << 16).view(np.float32), (py, px, H, W)
 
 
-def make_device_batch(ctx, meshes, B, seed, K, pixel_means_rgb, num_points=3000):
+def make_device_batch(ctx, meshes, B, seed, K, pixel_means_rgb, num_points=3000, init_mask="box_gt"):
     """Synthetic training batch built with the device kernels only (config C4: rendered pairs, labels from
     dim_train_update, INIT_MASK box_gt without dilation, 3000 sampled model points as get_point_cloud_model,
-    lib/utils/image.py:452-478).  Returns (batch dict of CUDA tensors, cls int32[B], tgt_pose f32[B,3,4], depth_gt)."""
+    lib/utils/image.py:452-478).  init_mask = "box_gt" (the reference's training config: mask_observed = box of the GT mask)
+    or "box_rendered" (the TEST-time convention, yaml:118: box of the rendered mask -- train / test inputs then match).
+    Returns (batch dict of CUDA tensors, cls int32[B], tgt_pose f32[B,3,4], depth_gt)."""
     from . import synth
     obs, ini = synth.sample_pose_pairs(B, seed)
     dev = ctx.device
@@ -263,7 +265,8 @@ def make_device_batch(ctx, meshes, B, seed, K, pixel_means_rgb, num_points=3000)
         pts[b, :, :len(keep)] = v[keep].T
         pw[b, :, :len(keep)] = 1
     pobs = np.stack([obs[b, :, :3].astype(np.float32) @ pts[b] + obs[b, :, 3:4].astype(np.float32) for b in range(B)]).astype(np.float32)
-    batch = {"image_observed": r["image"], "image_rendered": upd["image_rendered"], "mask_observed": ctx.update_mask_box(r["bbox"]),
+    box = r["bbox"] if init_mask == "box_gt" else ctx.render(cls, upd["src_pose"], K, pixel_means_rgb=pixel_means_rgb, want=("mask",))["bbox"]
+    batch = {"image_observed": r["image"], "image_rendered": upd["image_rendered"], "mask_observed": ctx.update_mask_box(box),
              "mask_gt_observed": r["mask"], "mask_rendered": upd["mask_rendered"], "src_pose": upd["src_pose"], "flow": upd["flow"],
              "flow_weights": upd["flow_weights"], "point_cloud_model": torch.from_numpy(pts).to(dev),
              "point_cloud_weights": torch.from_numpy(pw).to(dev), "point_cloud_observed": torch.from_numpy(pobs).to(dev),
@@ -271,7 +274,7 @@ def make_device_batch(ctx, meshes, B, seed, K, pixel_means_rgb, num_points=3000)
     return batch, cls, tgt, r["depth"]
 
 
-def fit_batch(trainer, batch, cls, tgt_pose, depth_gt, K, n_inner=4, dist=None):
+def fit_batch(trainer, batch, cls, tgt_pose, depth_gt, K, n_inner=4, dist=None, update_mask="fixed"):
     """One data batch of Module.fit (deepim/core/module.py:1131-1137): n_inner x (forward_backward, update), the
     batch re-rendered at the predicted pose in between (batchUpdaterPyMulti.forward -> Context.train_update).
     Returns the objective of every inner iteration (device tensor [n_inner])."""
@@ -287,4 +290,8 @@ def fit_batch(trainer, batch, cls, tgt_pose, depth_gt, K, n_inner=4, dist=None):
                                    pixel_means_rgb=batch["pixel_means_rgb"])
             for k in ("image_rendered", "mask_rendered", "src_pose", "flow", "flow_weights"):
                 b[k] = upd[k]
+            if update_mask == "box_rendered":  # what update_data_batch does at test time (data_pair.py:93-105); the reference's
+                # training loop keeps mask_observed fixed (batch_updater_py_multi.py:267-301)
+                rb = ctx.render(cls, upd["src_pose"], K, pixel_means_rgb=batch["pixel_means_rgb"], want=("mask",))["bbox"]
+                b["mask_observed"] = ctx.update_mask_box(rb)
     return torch.stack(objs)

@@ -36,6 +36,9 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--out", default="gpurun_out/train_synth.json")
     ap.add_argument("--save", default="", help="optional .npz path for the trained inference weights")
+    ap.add_argument("--mask", default="box_gt", choices=["box_gt", "box_rendered"],
+                    help="mask_observed convention during training: the reference's training config (box of the GT mask) or the "
+                         "test-time convention (box of the rendered mask, refreshed every inner iteration)")
     ap.add_argument("--overfit", action="store_true", help="train on ONE fixed batch and evaluate on exactly those pairs (sanity: "
                     "train graph and test graph agree on every convention)")
     ap.add_argument("--clean-eval", action="store_true", help="evaluate on clean renders (black background) like the training pairs")
@@ -87,15 +90,17 @@ def main():
                 "acc_pct_at_0.02_0.05_0.10_d": [[round(100.0 * float((e < f * d).mean()), 2) for f in (0.02, 0.05, 0.10)] for e in errs],
                 "rows": "initial pose, then after iteration 1..4"}
 
-    log = {"recipe": {k: getattr(args, k) for k in ("steps", "batch", "lr", "momentum", "wd", "seed")},
+    log = {"recipe": {k: getattr(args, k) for k in ("steps", "batch", "lr", "momentum", "wd", "seed", "mask", "overfit")},
            "workload": "C2 mesh (%d verts), training pairs from synth.sample_pose_pairs(seed = step), 4 inner updates per batch" % len(mesh.verts),
            "diameter_m": float(mesh.diameter), "evals": [], "loss": []}
     log["evals"].append({"step": 0, **evaluate()})
     print("step 0", log["evals"][-1]["add_mean_m"], flush=True)
     t0 = time.time()
     for step in range(1, args.steps + 1):
-        batch, cls, tgt, depth_gt = trainer.make_device_batch(ctx, [mesh], B, 10_000 + (1 if args.overfit else step), K, means)
-        objs = trainer.fit_batch(tr, batch, cls, tgt, depth_gt, K, n_inner=4)
+        batch, cls, tgt, depth_gt = trainer.make_device_batch(ctx, [mesh], B, 10_000 + (1 if args.overfit else step), K, means,
+                                                              init_mask=args.mask)
+        objs = trainer.fit_batch(tr, batch, cls, tgt, depth_gt, K, n_inner=4,
+                                 update_mask="box_rendered" if args.mask == "box_rendered" else "fixed")
         if step % 10 == 0 or step == 1:
             o = [round(float(v), 5) for v in objs.cpu().numpy()]
             log["loss"].append({"step": step, "objective_per_inner_iteration": o})
