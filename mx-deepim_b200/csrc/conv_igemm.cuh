@@ -288,10 +288,13 @@ __device__ __forceinline__ void epilogue_store64(const uint32_t *r, const float 
 
 // 32-column variant (conv1 with two epilogue warps per TMEM lane quadrant): 32 fp32 columns -> 64 bytes per row, staged
 // through a per-warp 2 KB XOR-swizzled tile; lane l then writes 16 B of row i*8 + l/4 (8 rows x 64 B per instruction).
-template <bool SPLIT3>
+// LINEAR: the 32 rows of the warp are consecutive pixels of one output row (conv1): row r lives at my_off(row 0) + r * row_stride
+// elements and rows [0, n_valid) are valid -- no per-row offset shuffle, no ballot (my_off / my_valid are then warp-uniform:
+// offset of the warp's row 0 and unused).
+template <bool SPLIT3, bool LINEAR = false>
 __device__ __forceinline__ void epilogue_store32(const uint32_t *r, const float *bias_s, float slope, uint8_t *stage,
                                                  __nv_bfloat16 *out_hi, __nv_bfloat16 *out_lo, long long my_off,
-                                                 bool my_valid, int lane, bool f16) {
+                                                 bool my_valid, int lane, bool f16, int n_valid = 32, int row_stride = 0) {
   __align__(16) uint32_t h[16];
   __align__(16) uint32_t l[SPLIT3 ? 16 : 4];
 #pragma unroll
@@ -307,7 +310,7 @@ __device__ __forceinline__ void epilogue_store32(const uint32_t *r, const float 
       if (SPLIT3) l[j >> 1] = pack2_bf16(v0 - __uint_as_float(hh << 16), v1 - __uint_as_float(hh & 0xFFFF0000u));
     }
   }
-  const unsigned vmask = __ballot_sync(0xffffffffu, my_valid);
+  const unsigned vmask = LINEAR ? 0u : __ballot_sync(0xffffffffu, my_valid);
   const int ch = lane & 3;
 #pragma unroll
   for (int pass = 0; pass < (SPLIT3 ? 2 : 1); ++pass) {
@@ -320,10 +323,16 @@ __device__ __forceinline__ void epilogue_store32(const uint32_t *r, const float 
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int row = i * 8 + (lane >> 2);
-      const long long off = __shfl_sync(0xffffffffu, my_off, row);
-      if ((vmask >> row) & 1u)
-        *reinterpret_cast<uint4 *>(out + off + ch * 8) =
-            *reinterpret_cast<const uint4 *>(stage + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));
+      if (LINEAR) {
+        if (row < n_valid)
+          *reinterpret_cast<uint4 *>(out + my_off + (long long)row * row_stride + ch * 8) =
+              *reinterpret_cast<const uint4 *>(stage + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));
+      } else {
+        const long long off = __shfl_sync(0xffffffffu, my_off, row);
+        if ((vmask >> row) & 1u)
+          *reinterpret_cast<uint4 *>(out + off + ch * 8) =
+              *reinterpret_cast<const uint4 *>(stage + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));
+      }
     }
     __syncwarp();
   }
@@ -883,12 +892,26 @@ __global__ void __launch_bounds__(320) conv1_roll_kernel(const __grid_constant__
     if (n_rows > 0) {
       ptx::mbar_wait(res_bar, 0);
       ptx::tc_fence_after();
+      // everything that does not depend on the tile is formed once: ring-slot descriptor = dring + slot * slot_step, the four
+      // filter-row weight descriptors, the k step.  The MMA warp is one instruction stream; every scalar instruction
+      // between two MMA groups is exposed latency (measured: 2.5k cycles per tile for 0.9k cycles of MMAs).
+      const uint64_t dring = umma_desc_interleave(ptx::smem_u32(ring), LBO, 128);
+      const uint64_t dring_lo = umma_desc_interleave(ptx::smem_u32(ring) + (uint32_t)strip_bytes, LBO, 128);
+      const uint64_t slot_step = (uint64_t)((uint32_t)stage_bytes >> 4);
+      const uint64_t kstep = (uint64_t)(2u * LBO >> 4);
+      uint64_t dbh[4], dbl[4];
+#pragma unroll
+      for (int dh = 0; dh < 4; ++dh) {
+        dbh[dh] = ptx::umma_desc(ptx::smem_u32(res) + dh * 4 * B_BYTES, 512, 4u);
+        dbl[dh] = ptx::umma_desc(ptx::smem_u32(res) + (16 + dh * 4) * B_BYTES, 512, 4u);
+      }
       int as = 0, waited = 0;
       uint32_t aph = 0;
       for (int t = 0; t < n_rows; ++t) {
         ptx::mbar_wait(&tmem_empty_bar[as], aph ^ 1u);
         ptx::tc_fence_after();
         const uint32_t tmem_acc = tmem_base + (uint32_t)as * ACC_COLS;
+#pragma unroll
         for (int dh = 0; dh < 4; ++dh) {
           const int s = t + dh, slot = s % STAGES;
           if (s >= waited) {  // first use of this strip
@@ -896,13 +919,8 @@ __global__ void __launch_bounds__(320) conv1_roll_kernel(const __grid_constant__
             ptx::tc_fence_after();
             waited = s + 1;
           }
-          const uint32_t a_hi = ptx::smem_u32(ring + slot * stage_bytes);
-          const uint32_t a_lo = a_hi + (uint32_t)strip_bytes;
           if (ptx::elect_one()) {
-            const uint64_t da0 = umma_desc_interleave(a_hi, LBO, 128), dal0 = umma_desc_interleave(a_lo, LBO, 128);
-            const uint64_t db0 = ptx::umma_desc(ptx::smem_u32(res) + dh * 4 * B_BYTES, 512, 4u);
-            const uint64_t dbl0 = ptx::umma_desc(ptx::smem_u32(res) + (16 + dh * 4) * B_BYTES, 512, 4u);
-            const uint64_t kstep = (uint64_t)(2u * LBO >> 4);
+            const uint64_t da0 = dring + (uint64_t)slot * slot_step, dal0 = dring_lo + (uint64_t)slot * slot_step;
 #pragma unroll
             for (int dw = 0; dw < 4; ++dw) {
 #pragma unroll
@@ -910,11 +928,11 @@ __global__ void __launch_bounds__(320) conv1_roll_kernel(const __grid_constant__
                 if (dh == 3 && k == 1) continue;  // kh = 7: outside the 7x7 filter, all-zero weights
                 const uint32_t acc = (dh | dw | k) ? 1u : 0u;
                 const uint64_t da = da0 + (uint64_t)dw + (uint64_t)k * kstep;
-                const uint64_t db = db0 + (uint64_t)(dw * (B_BYTES >> 4) + 2 * k);
+                const uint64_t db = dbh[dh] + (uint64_t)(dw * (B_BYTES >> 4) + 2 * k);
                 ptx::umma_f16_raw(tmem_acc, da, db, p.idesc, acc);
                 if (SPLIT3) {
                   ptx::umma_f16_raw(tmem_acc, dal0 + (uint64_t)dw + (uint64_t)k * kstep, db, p.idesc, 1u);
-                  ptx::umma_f16_raw(tmem_acc, da, dbl0 + (uint64_t)(dw * (B_BYTES >> 4) + 2 * k), p.idesc, 1u);
+                  ptx::umma_f16_raw(tmem_acc, da, dbl[dh] + (uint64_t)(dw * (B_BYTES >> 4) + 2 * k), p.idesc, 1u);
                 }
               }
             }
@@ -934,21 +952,24 @@ __global__ void __launch_bounds__(320) conv1_roll_kernel(const __grid_constant__
     uint8_t *stg = epi + (warp - 2) * 2048;
     int as = 0;
     uint32_t aph = 0;
+    // the tile is ONE output row: the warp's 32 rows are the consecutive pixels ow0 + quad*32 .. +31, 64 channels (128 B) apart
+    const int n_cols_valid = min(p.BW, p.Wo - ow0) - quad * 32;  // valid rows of this warp's quadrant (may be <= 0)
     for (int t = 0; t < n_rows; ++t) {
       const int g = g_lo + t;
-      const int ow = ow0 + m;
       const int n_img = g / p.Hq, oh = g - n_img * p.Hq;
-      const bool valid = (m < p.BW) && (n_img < p.Bn) && (oh < p.Ho) && (ow < p.Wo);
+      const bool row_ok = (n_img < p.Bn) && (oh < p.Ho);
       ptx::mbar_wait(&tmem_full_bar[as], aph);
       ptx::tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)as * ACC_COLS + (uint32_t)half * 32u;
-      const long long my_off = (((long long)n_img * p.out_Hp + oh + p.out_py) * p.out_Wp + ow + p.out_px) * 64 + half * 32;
+      const long long warp_off =
+          (((long long)n_img * p.out_Hp + oh + p.out_py) * p.out_Wp + (ow0 + quad * 32) + p.out_px) * 64 + half * 32;
       uint32_t r[32];
       ptx::tmem_ld_32x32(trow, r);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
-      epilogue_store32<SPLIT3>(r, bias_s + half * 32, p.slope, stg, p.out_hi, p.out_lo, my_off, valid, lane, p.f16 != 0);
+      epilogue_store32<SPLIT3, true>(r, bias_s + half * 32, p.slope, stg, p.out_hi, p.out_lo, warp_off, true, lane, p.f16 != 0,
+                                     row_ok ? n_cols_valid : 0, 64);
       if (++as == 2) { as = 0; aph ^= 1u; }
     }
   }

@@ -241,16 +241,19 @@ class Trainer:
         return (raw.astype(np.uint32) << 16).view(np.float32), (py, px, H, W)
 
 
-def make_device_batch(ctx, meshes, B, seed, K, pixel_means_rgb, num_points=3000, init_mask="box_gt"):
+def make_device_batch(ctx, meshes, B, seed, K, pixel_means_rgb, num_points=3000, init_mask="box_gt", poses=None,
+                      image_observed=None, cls_np=None):
     """Synthetic training batch built with the device kernels only (config C4: rendered pairs, labels from
     dim_train_update, INIT_MASK box_gt without dilation, 3000 sampled model points as get_point_cloud_model,
     lib/utils/image.py:452-478).  init_mask = "box_gt" (the reference's training config: mask_observed = box of the GT mask)
     or "box_rendered" (the TEST-time convention, yaml:118: box of the rendered mask -- train / test inputs then match).
+    poses = (pose_observed, pose_init) [B,3,4] instead of sampling them from `seed`; image_observed = the observed blob to
+    train on (float32 [B,3,H,W] RGB - mean, e.g. a render composited over a background) instead of the clean render.
     Returns (batch dict of CUDA tensors, cls int32[B], tgt_pose f32[B,3,4], depth_gt)."""
     from . import synth
-    obs, ini = synth.sample_pose_pairs(B, seed)
+    obs, ini = synth.sample_pose_pairs(B, seed) if poses is None else poses
     dev = ctx.device
-    cls_np = (np.arange(B) % len(meshes)).astype(np.int32)
+    cls_np = (np.arange(B) % len(meshes)).astype(np.int32) if cls_np is None else np.asarray(cls_np, np.int32)
     cls = torch.from_numpy(cls_np).to(dev)
     tgt = torch.from_numpy(obs.astype(np.float32)).to(dev)
     src = torch.from_numpy(ini.astype(np.float32)).to(dev)
@@ -266,7 +269,7 @@ def make_device_batch(ctx, meshes, B, seed, K, pixel_means_rgb, num_points=3000,
         pw[b, :, :len(keep)] = 1
     pobs = np.stack([obs[b, :, :3].astype(np.float32) @ pts[b] + obs[b, :, 3:4].astype(np.float32) for b in range(B)]).astype(np.float32)
     box = r["bbox"] if init_mask == "box_gt" else ctx.render(cls, upd["src_pose"], K, pixel_means_rgb=pixel_means_rgb, want=("mask",))["bbox"]
-    batch = {"image_observed": r["image"], "image_rendered": upd["image_rendered"], "mask_observed": ctx.update_mask_box(box),
+    batch = {"image_observed": r["image"] if image_observed is None else image_observed, "image_rendered": upd["image_rendered"], "mask_observed": ctx.update_mask_box(box),
              "mask_gt_observed": r["mask"], "mask_rendered": upd["mask_rendered"], "src_pose": upd["src_pose"], "flow": upd["flow"],
              "flow_weights": upd["flow_weights"], "point_cloud_model": torch.from_numpy(pts).to(dev),
              "point_cloud_weights": torch.from_numpy(pw).to(dev), "point_cloud_observed": torch.from_numpy(pobs).to(dev),

@@ -451,6 +451,7 @@ def test_refine_cuda_graph_replay_equals_eager(ctx, loop_case):
     cls2 = dev(c["cls"][[1, 0, 3, 2]])
     img2 = dev(c["img"][[1, 0, 3, 2]])
     eager2 = ctx.refine(img2, cls2, ini2, K, 4, pixel_means_rgb=MEANS)
+    torch.cuda.synchronize()       # a context is driven from ONE stream at a time: finish the default-stream work first
     check(lib.dim_debug_set_option(ctx._h, b"graph", 1))
     side = torch.cuda.Stream(device=DEV)
     out = None
@@ -466,6 +467,7 @@ def test_refine_cuda_graph_replay_equals_eager(ctx, loop_case):
     side.synchronize()
     for k in ("poses", "se3", "zoom_factor", "bbox"):
         assert torch.equal(out[k], eager2[k]), k
+    torch.cuda.synchronize()
 
 
 def test_refine_host_matches_device_path(ctx, meshes, loop_case):
