@@ -322,7 +322,7 @@ def run_b200(args):
         result = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K_steps,
             "warmup": W_steps, "ms_per_step": round(ms_total / K_steps, 4), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": args.precision,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": args.precision,
             "data": "synthetic",
             "config": {"workload": workload, "batch_per_gpu": B, "batches_per_step": SB, "n_iter": N_ITER,
                        "precision": args.precision, "batches_in_flight": args.slots,
@@ -548,6 +548,8 @@ def main():
                     help="untimed set-up: train the network for this many batches (x 4 inner updates) on the bench's own input pairs so "
                          "that the ADD sanity of the line means something; 0 = random-init weights")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="label only: weak = per-GPU batch fixed (default); strong = the caller divides a fixed total over the GPUs (C5 sweep)")
     ap.add_argument("--slots", type=int, default=4, help="independent batches in flight per GPU (streams)")
     ap.add_argument("--config", default="c2", choices=["c2", "c3", "c5"],
                     help="c2 = headline config (default); c3 = 13 meshes round-robin; c5 = 50k-vert rasteriser stress mesh")
