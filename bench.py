@@ -544,7 +544,7 @@ def main():
                     help="fp16 = headline (single tcgen05 pass, meets 1e-4 rot / 1e-3 trans); bf16x3 = 3-pass; bf16 = fast mode")
     ap.add_argument("--step-batches", type=int, default=STEP_BATCHES, help="device batches per bench step")
     ap.add_argument("--no-fast-mode", action="store_true", help="skip the secondary bf16 fast-mode pass")
-    ap.add_argument("--train-steps", type=int, default=240,
+    ap.add_argument("--train-steps", type=int, default=900,
                     help="untimed set-up: train the network for this many batches (x 4 inner updates) on the bench's own input pairs so "
                          "that the ADD sanity of the line means something; 0 = random-init weights")
     ap.add_argument("--no-cpu-baseline", action="store_true")

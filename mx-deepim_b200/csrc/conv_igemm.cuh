@@ -290,8 +290,9 @@ __device__ __forceinline__ void epilogue_store64(const uint32_t *r, const float 
 // through a per-warp 2 KB XOR-swizzled tile; lane l then writes 16 B of row i*8 + l/4 (8 rows x 64 B per instruction).
 // LINEAR: the 32 rows of the warp are consecutive pixels of one output row (conv1): row r lives at my_off(row 0) + r * row_stride
 // elements and rows [0, n_valid) are valid -- no per-row offset shuffle, no ballot (my_off / my_valid are then warp-uniform:
-// offset of the warp's row 0 and unused).
-template <bool SPLIT3, bool LINEAR = false>
+// offset of the warp's row 0 and unused).  HALF_STAGE: the staging tile is 1 KB (32 rows x 32 B) and the 32 columns go out in two
+// 16-column passes (used with LINEAR by the 2-CTAs-per-SM conv1 kernel, whose shared memory is tight).
+template <bool SPLIT3, bool LINEAR = false, bool HALF_STAGE = false>
 __device__ __forceinline__ void epilogue_store32(const uint32_t *r, const float *bias_s, float slope, uint8_t *stage,
                                                  __nv_bfloat16 *out_hi, __nv_bfloat16 *out_lo, long long my_off,
                                                  bool my_valid, int lane, bool f16, int n_valid = 32, int row_stride = 0) {
@@ -311,6 +312,29 @@ __device__ __forceinline__ void epilogue_store32(const uint32_t *r, const float 
     }
   }
   const unsigned vmask = LINEAR ? 0u : __ballot_sync(0xffffffffu, my_valid);
+  if (HALF_STAGE) {  // LINEAR only
+#pragma unroll
+    for (int pass = 0; pass < (SPLIT3 ? 2 : 1); ++pass) {
+      const uint32_t *src = pass ? l : h;
+      __nv_bfloat16 *out = pass ? out_lo : out_hi;
+#pragma unroll
+      for (int hc = 0; hc < 2; ++hc) {  // columns [16 hc, 16 hc + 16): 32 B per row
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+          *reinterpret_cast<uint4 *>(stage + lane * 32 + ((c ^ ((lane >> 2) & 1)) << 4)) = *reinterpret_cast<const uint4 *>(src + hc * 8 + c * 4);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int row = i * 16 + (lane >> 1), ch2 = lane & 1;
+          if (row < n_valid)
+            *reinterpret_cast<uint4 *>(out + my_off + (long long)row * row_stride + hc * 16 + ch2 * 8) =
+                *reinterpret_cast<const uint4 *>(stage + row * 32 + ((ch2 ^ ((row >> 2) & 1)) << 4));
+        }
+        __syncwarp();
+      }
+    }
+    return;
+  }
   const int ch = lane & 3;
 #pragma unroll
   for (int pass = 0; pass < (SPLIT3 ? 2 : 1); ++pass) {
@@ -819,20 +843,23 @@ __global__ void __launch_bounds__(192) conv1_strip_kernel(const __grid_constant_
 // kernel.  One CTA per SM (64 KB resident weights + an 8-deep ring), grid = column tiles x chunks.  With a single CTA per SM the
 // per-tile epilogue (64 columns: ~2.6k cycles on 4 warps) is longer than the tile's 0.9k cycles of MMAs, so EIGHT epilogue
 // warps share it: two per TMEM lane quadrant, 32 accumulator columns each (320 threads).
-template <int STAGES, bool SPLIT3>
-__global__ void __launch_bounds__(320) conv1_roll_kernel(const __grid_constant__ ConvKParams p, const int rows_total,
+template <int STAGES, bool SPLIT3, bool OCC2 = false>
+__global__ void __launch_bounds__(320, OCC2 ? 2 : 1) conv1_roll_kernel(const __grid_constant__ ConvKParams p, const int rows_total,
                                                          const int rows_per_chunk, const int chunks_per_col,
                                                          const int strip_bytes /*per precision, multiple of 128*/) {
   constexpr uint32_t ACC_COLS = 64, TMEM_COLS = 128;
   constexpr int NPREC = SPLIT3 ? 2 : 1;
-  constexpr int B_BYTES = 64 * 32 * 2, RES_BYTES = 16 * B_BYTES * NPREC, EPI_BYTES = 4 * 4096 + 256;
+  // OCC2: two CTAs per SM (each MMA warp is one latency-bound instruction stream; a second CTA hides it): 5-deep ring,
+  // 1 KB staging tile per epilogue warp, 128-byte alignment of the dynamic shared memory is enough (no swizzle-128 tiles)
+  constexpr int STG = OCC2 ? 1024 : 2048;
+  constexpr int B_BYTES = 64 * 32 * 2, RES_BYTES = 16 * B_BYTES * NPREC, EPI_BYTES = 8 * STG + 256;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 511) & ~(uintptr_t)511);
   uint8_t *res = smem;
   uint8_t *ring = smem + RES_BYTES;
   const int stage_bytes = strip_bytes * NPREC;
   uint8_t *epi = ring + STAGES * stage_bytes;
-  float *bias_s = reinterpret_cast<float *>(epi + 4 * 4096);
+  float *bias_s = reinterpret_cast<float *>(epi + 8 * STG);
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(epi + EPI_BYTES);
   uint64_t *empty_bar = full_bar + STAGES;
   uint64_t *tmem_full_bar = empty_bar + STAGES;
@@ -949,7 +976,7 @@ __global__ void __launch_bounds__(320) conv1_roll_kernel(const __grid_constant__
   } else {
     const int quad = warp & 3, half = (warp - 2) >> 2;  // TMEM lane quadrant of this warp, its 32-column half
     const int m = quad * 32 + lane;
-    uint8_t *stg = epi + (warp - 2) * 2048;
+    uint8_t *stg = epi + (warp - 2) * STG;
     int as = 0;
     uint32_t aph = 0;
     // the tile is ONE output row: the warp's 32 rows are the consecutive pixels ow0 + quad*32 .. +31, 64 channels (128 B) apart
@@ -968,8 +995,8 @@ __global__ void __launch_bounds__(320) conv1_roll_kernel(const __grid_constant__
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
-      epilogue_store32<SPLIT3, true>(r, bias_s + half * 32, p.slope, stg, p.out_hi, p.out_lo, warp_off, true, lane, p.f16 != 0,
-                                     row_ok ? n_cols_valid : 0, 64);
+      epilogue_store32<SPLIT3, true, OCC2>(r, bias_s + half * 32, p.slope, stg, p.out_hi, p.out_lo, warp_off, true, lane, p.f16 != 0,
+                                           row_ok ? n_cols_valid : 0, 64);
       if (++as == 2) { as = 0; aph ^= 1u; }
     }
   }

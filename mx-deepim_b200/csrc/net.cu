@@ -605,6 +605,19 @@ int net_forward(dim_ctx *ctx, int B, int precision, const float *zoom_factor, fl
         static int set1 = 0;
         if (set1 < smem_bytes) { DIM_CHECK(cudaFuncSetAttribute(conv1_roll_kernel<ST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); set1 = smem_bytes; }
         conv1_roll_kernel<ST, true><<<grid, 320, smem_bytes, st>>>(kp, rows_total, rpc, chunks, strip_bytes);
+      } else if (ns->conv1_occ2) {
+        // two CTAs per SM: 64 KB weights + 5 strips + 8 KB staging = ~108 KB each; twice the chunks (shorter runs, 7.5 % halo)
+        constexpr int ST = 5;
+        int chunks2 = (2 * sms) / g.n_col_tiles;
+        if (chunks2 > cdiv(rows_total, 16)) chunks2 = cdiv(rows_total, 16);
+        if (chunks2 < 1) chunks2 = 1;
+        const int rpc2 = cdiv(rows_total, chunks2);
+        chunks2 = cdiv(rows_total, rpc2);
+        const int smem_bytes = 16 * 4096 + ST * strip_bytes + (8 * 1024 + 256) + 512 + 512;
+        DIM_REQUIRE(smem_bytes <= 113 * 1024, "conv1: image too wide for two rolling-strip CTAs per SM");
+        static int set2 = 0;
+        if (set2 < smem_bytes) { DIM_CHECK(cudaFuncSetAttribute(conv1_roll_kernel<ST, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); set2 = smem_bytes; }
+        conv1_roll_kernel<ST, false, true><<<g.n_col_tiles * chunks2, 320, smem_bytes, st>>>(kp, rows_total, rpc2, chunks2, strip_bytes);
       } else {
         constexpr int ST = 8;
         const int smem_bytes = 16 * 4096 + ST * strip_bytes + (4 * 4096 + 256) + 1024 + 512;
@@ -690,6 +703,7 @@ int net_set_option(dim_ctx *ctx, const char *key, int value) {
   DIM_REQUIRE(ns != nullptr, "net not created");
   if (!strcmp(key, "pair_mask")) ns->pair_mask = value & 0x3FE;
   else if (!strcmp(key, "conv1_roll")) ns->conv1_roll = value != 0;
+  else if (!strcmp(key, "conv1_occ2")) ns->conv1_occ2 = value != 0;
   else { set_error("dim_debug_set_option: unknown key '%s'", key); return 2; }
   DIM_CHECK(cudaDeviceSynchronize());
   ns->maps.clear();
