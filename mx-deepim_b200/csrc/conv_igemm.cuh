@@ -205,6 +205,17 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t *r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// zero 32 lanes x 32 consecutive fp32 columns of TMEM (the accumulator block is handed back cleared)
+__device__ __forceinline__ void tmem_zero_32x32(uint32_t taddr) {
+  const uint32_t z = 0u;
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+      "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(z)
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
 // K-major swizzled operand descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp): start>>4 in
 // [0,14), LBO [16,30) (unused for swizzled K-major, set 1), SBO>>4 in [32,46) = 8 rows * row bytes,
 // version 1 at [46,48), layout type at [61,64) (2 = SWIZZLE_128B, 4 = SWIZZLE_64B).
@@ -998,6 +1009,165 @@ __global__ void __launch_bounds__(320, OCC2 ? 2 : 1) conv1_roll_kernel(const __g
       epilogue_store32<SPLIT3, true, OCC2>(r, bias_s + half * 32, p.slope, stg, p.out_hi, p.out_lo, warp_off, true, lane, p.f16 != 0,
                                            row_ok ? n_cols_valid : 0, 64);
       if (++as == 2) { as = 0; aph ^= 1u; }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// conv1, stacked-filter-rows variant (single-pass precisions).  With Cout = 64 an MMA is 128 x 64 x 16: its A operand
+// (4 KB) is re-read from shared memory for 32 cycles of tensor work and the kernel is bound by shared-memory bandwidth
+// (measured 2.1k cycles per output row for 0.9k cycles of MMAs, on one CTA or two per SM alike).  Here the FOUR filter
+// rows are stacked along N: B = [W_dh3; W_dh2; W_dh1; W_dh0] (256 x 16 per (dw, k) step), so one 128 x 256 x 16 MMA of
+// input strip s adds its contribution to the four output rows s-3 .. s at once and A is read once instead of four
+// times.  The accumulators live in eight 64-column TMEM blocks (all 512 columns): virtual row v (= output row g_lo + v - 3)
+// sits in block v mod 8; strip s touches the blocks of rows s .. s+3 -- ascending rows are descending dh, which is why B's
+// order is fixed -- starts row s+3 and completes row s.  Every MMA accumulates (no per-block overwrite exists): a block is
+// handed back ZEROED by the epilogue warps (tcgen05.st) after they drain it, four strips before it is needed again.  When
+// the 4-block window wraps past column 512 the MMA is split in two (N = 64 n1 + 64 (4 - n1)).  Every strip is loaded and
+// consumed exactly once; the 3-row halo of a chunk costs three extra strips whose partial rows are discarded.
+template <int STAGES>
+__global__ void __launch_bounds__(320) conv1_stack_kernel(const __grid_constant__ ConvKParams p, const int rows_total,
+                                                          const int rows_per_chunk, const int chunks_per_col,
+                                                          const int strip_bytes /*multiple of 128*/) {
+  constexpr uint32_t TMEM_COLS = 512;
+  constexpr int B_BYTES = 64 * 32 * 2 /*one (dh, dw) tile: 64 couts x 32 K*/, DW_BYTES = 4 * B_BYTES, RES_BYTES = 4 * DW_BYTES;
+  constexpr int EPI_BYTES = 8 * 2048 + 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 511) & ~(uintptr_t)511);
+  uint8_t *res = smem;                       // [dw][dh = 3,2,1,0][64 couts][32 K] SW64
+  uint8_t *ring = smem + RES_BYTES;
+  uint8_t *epi = ring + STAGES * strip_bytes;
+  float *bias_s = reinterpret_cast<float *>(epi + 8 * 2048);
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(epi + EPI_BYTES);
+  uint64_t *empty_bar = full_bar + STAGES;
+  uint64_t *acc_full_bar = empty_bar + STAGES;   // [8] row block complete (MMA warp -> epilogue)
+  uint64_t *acc_empty_bar = acc_full_bar + 8;    // [8] block drained and zeroed (8 epilogue warps -> MMA warp)
+  uint64_t *res_bar = acc_empty_bar + 8;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(res_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int R = p.BW + 3;
+  const uint32_t LBO = (uint32_t)R * 16u;
+  const int ct = blockIdx.x / chunks_per_col, ck = blockIdx.x - ct * chunks_per_col;
+  const int g_lo = ck * rows_per_chunk;
+  const int g_hi = min(rows_total, g_lo + rows_per_chunk);
+  const int n_rows = max(0, g_hi - g_lo);
+  const int n_strips = n_rows > 0 ? n_rows + 3 : 0;   // strip s = input row g_lo + s; it completes virtual row v = s
+  const int ow0 = ct * p.BW;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 8; ++a) {
+      ptx::mbar_init(&acc_full_bar[a], 1);
+      ptx::mbar_init(&acc_empty_bar[a], 8);
+    }
+    ptx::mbar_init(res_bar, 1);
+    ptx::fence_barrier_init();
+    ptx::prefetch_tmap(&p.b_map);
+    ptx::prefetch_tmap(&p.a_map[0]);
+  }
+  if (threadIdx.x < 64) bias_s[threadIdx.x] = p.bias[threadIdx.x];
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp >= 2) {  // all eight accumulator blocks start cleared: each epilogue warp zeroes its lane quadrant x column half
+    const int quad = warp & 3, half = (warp - 2) >> 2;
+    for (int b = 0; b < 8; ++b) ptx::tmem_zero_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * 64 + half * 32));
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+
+  if (warp == 0) {
+    if (n_rows > 0) {
+      if (ptx::elect_one()) {
+        ptx::mbar_expect_tx_raw(res_bar, (uint32_t)RES_BYTES);
+        for (int dh = 0; dh < 4; ++dh)
+          for (int dw = 0; dw < 4; ++dw)  // global K order is (dh, dw, 32); resident order is [dw][3 - dh]
+            ptx::tma_load_2d_raw(res + dw * DW_BYTES + (3 - dh) * B_BYTES, &p.b_map, res_bar, (dh * 4 + dw) * 32, 0);
+      }
+      __syncwarp();
+      const uint32_t tx = (uint32_t)(R * 64);
+      for (int s = 0; s < n_strips; ++s) {
+        const int slot = s % STAGES;
+        ptx::mbar_wait(&empty_bar[slot], (((uint32_t)(s / STAGES)) & 1u) ^ 1u);
+        ptx::mbar_expect_tx(&full_bar[slot], tx);
+        tma_load_4d(ring + slot * strip_bytes, &p.a_map[0], &full_bar[slot], 0, ow0, 0, g_lo + s);
+      }
+    }
+  } else if (warp == 1) {
+    if (n_rows > 0) {
+      ptx::mbar_wait(res_bar, 0);
+      ptx::tc_fence_after();
+      const uint64_t dring = umma_desc_interleave(ptx::smem_u32(ring), LBO, 128);
+      const uint64_t slot_step = (uint64_t)((uint32_t)strip_bytes >> 4);
+      const uint64_t kstep = (uint64_t)(2u * LBO >> 4);
+      const uint64_t dres = ptx::umma_desc(ptx::smem_u32(res), 512, 4u);
+      const uint32_t idesc0 = p.idesc & ~(0x3Fu << 17);  // N field cleared; N >> 3 goes to bits [17, 23)
+      for (int s = 0; s < n_strips; ++s) {
+        const int slot = s % STAGES;
+        const int vnew = s + 3;  // the row this strip starts: its block must have been drained and zeroed
+        ptx::mbar_wait(&acc_empty_bar[vnew & 7], (((uint32_t)(vnew >> 3)) & 1u) ^ 1u);
+        ptx::mbar_wait(&full_bar[slot], ((uint32_t)(s / STAGES)) & 1u);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint64_t da0 = dring + (uint64_t)slot * slot_step;
+          const int b0 = s & 7;                         // first block of the window (row v = s, filter row dh = 3)
+          const int n1 = b0 <= 4 ? 4 : 8 - b0;          // blocks before the window wraps past column 512
+          const uint32_t d1 = tmem_base + (uint32_t)b0 * 64u, id1 = idesc0 | ((uint32_t)(n1 * 64 >> 3) << 17);
+          const uint32_t id2 = idesc0 | ((uint32_t)((4 - n1) * 64 >> 3) << 17);
+#pragma unroll
+          for (int dw = 0; dw < 4; ++dw) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const uint64_t da = da0 + (uint64_t)dw + (uint64_t)k * kstep;
+              const uint64_t db = dres + (uint64_t)(dw * (DW_BYTES >> 4) + 2 * k);
+              ptx::umma_f16_raw(d1, da, db, id1, 1u);
+              if (n1 < 4) ptx::umma_f16_raw(tmem_base, da, db + (uint64_t)(n1 * (B_BYTES >> 4)), id2, 1u);
+            }
+          }
+          ptx::umma_commit_raw(&empty_bar[slot]);        // the strip is consumed
+          ptx::umma_commit_raw(&acc_full_bar[s & 7]);    // row v = s has all four contributions
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    const int quad = warp & 3, half = (warp - 2) >> 2;
+    uint8_t *stg = epi + (warp - 2) * 2048;
+    const int n_cols_valid = min(p.BW, p.Wo - ow0) - quad * 32;
+    for (int v = 0; v < n_strips; ++v) {  // one completed row per strip; rows v < 3 belong to the previous chunk: discarded
+      const int g = g_lo + v - 3;
+      const bool mine = v >= 3;  // v - 3 < n_rows holds by construction
+      int n_img = 0, oh = 0;
+      if (mine) { n_img = g / p.Hq; oh = g - n_img * p.Hq; }
+      const bool row_ok = mine && (n_img < p.Bn) && (oh < p.Ho);
+      ptx::mbar_wait(&acc_full_bar[v & 7], ((uint32_t)(v >> 3)) & 1u);
+      ptx::tc_fence_after();
+      const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((v & 7) * 64 + half * 32);
+      uint32_t r[32];
+      if (row_ok) ptx::tmem_ld_32x32(tcol, r);
+      ptx::tmem_zero_32x32(tcol);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty_bar[v & 7]);
+      if (row_ok) {
+        const long long warp_off =
+            (((long long)n_img * p.out_Hp + oh + p.out_py) * p.out_Wp + (ow0 + quad * 32) + p.out_px) * 64 + half * 32;
+        epilogue_store32<false, true>(r, bias_s + half * 32, p.slope, stg, p.out_hi, p.out_lo, warp_off, true, lane, p.f16 != 0,
+                                      n_cols_valid, 64);
+      }
     }
   }
   ptx::tc_fence_before();

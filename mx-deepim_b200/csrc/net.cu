@@ -605,6 +605,13 @@ int net_forward(dim_ctx *ctx, int B, int precision, const float *zoom_factor, fl
         static int set1 = 0;
         if (set1 < smem_bytes) { DIM_CHECK(cudaFuncSetAttribute(conv1_roll_kernel<ST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); set1 = smem_bytes; }
         conv1_roll_kernel<ST, true><<<grid, 320, smem_bytes, st>>>(kp, rows_total, rpc, chunks, strip_bytes);
+      } else if (ns->conv1_stack) {
+        // stacked filter rows: one 128 x 256 MMA per (dw, k) step feeds four output rows (A read once instead of four times)
+        constexpr int ST = 6;
+        const int smem_bytes = 16 * 4096 + ST * strip_bytes + (8 * 2048 + 256) + 512 + 512;
+        static int set3 = 0;
+        if (set3 < smem_bytes) { DIM_CHECK(cudaFuncSetAttribute(conv1_stack_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); set3 = smem_bytes; }
+        conv1_stack_kernel<ST><<<grid, 320, smem_bytes, st>>>(kp, rows_total, rpc, chunks, strip_bytes);
       } else if (ns->conv1_occ2) {
         // two CTAs per SM: 64 KB weights + 5 strips + 8 KB staging = ~108 KB each; twice the chunks (shorter runs, 7.5 % halo)
         constexpr int ST = 5;
@@ -704,6 +711,7 @@ int net_set_option(dim_ctx *ctx, const char *key, int value) {
   if (!strcmp(key, "pair_mask")) ns->pair_mask = value & 0x3FE;
   else if (!strcmp(key, "conv1_roll")) ns->conv1_roll = value != 0;
   else if (!strcmp(key, "conv1_occ2")) ns->conv1_occ2 = value != 0;
+  else if (!strcmp(key, "conv1_stack")) ns->conv1_stack = value != 0;
   else { set_error("dim_debug_set_option: unknown key '%s'", key); return 2; }
   DIM_CHECK(cudaDeviceSynchronize());
   ns->maps.clear();

@@ -65,7 +65,8 @@ def main():
         # mask bits 1..9: conv layer on the CTA-pair kernel; bit 10 (1024): conv1 on the rolling-strip kernel; bit 11 (2048): no CUDA graph
         set_opt(b"pair_mask", m & 0x3FE)
         set_opt(b"conv1_roll", (m >> 10) & 1)
-        set_opt(b"conv1_occ2", (m >> 12) & 1)   # bit 12 (4096): rolling conv1 kernel with two CTAs per SM
+        set_opt(b"conv1_occ2", (m >> 12) & 1)
+        set_opt(b"conv1_stack", (m >> 13) & 1)  # bit 13 (8192): stacked-filter-rows conv1 kernel   # bit 12 (4096): rolling conv1 kernel with two CTAs per SM
         set_opt(b"graph", 0 if (m >> 11) & 1 else 1)
 
     def layer_times(n=7):
