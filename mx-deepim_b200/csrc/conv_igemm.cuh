@@ -895,7 +895,7 @@ __global__ void __launch_bounds__(320, OCC2 ? 2 : 1) conv1_roll_kernel(const __g
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);
-      ptx::mbar_init(&tmem_empty_bar[a], 8);  // 8 epilogue warps
+      ptx::mbar_init(&tmem_empty_bar[a], 4);  // the four warps of the set that owns this stage
     }
     ptx::mbar_init(res_bar, 1);
     ptx::fence_barrier_init();
@@ -985,30 +985,35 @@ __global__ void __launch_bounds__(320, OCC2 ? 2 : 1) conv1_roll_kernel(const __g
       }
     }
   } else {
-    const int quad = warp & 3, half = (warp - 2) >> 2;  // TMEM lane quadrant of this warp, its 32-column half
-    const int m = quad * 32 + lane;
+    // Two warp SETS of four (one warp per TMEM lane quadrant, all 64 columns): set k owns the tiles t = k (mod 2), i.e.
+    // accumulator stage k.  The epilogue of one tile is a LATENCY chain (barrier wake-up, tcgen05.ld, convert, stage, store:
+    // ~2k cycles measured) rather than a throughput limit; with alternating sets each chain has two tile periods to finish.
+    const int quad = warp & 3, set = (warp - 2) >> 2;
     uint8_t *stg = epi + (warp - 2) * STG;
-    int as = 0;
+    const int as = set;
     uint32_t aph = 0;
     // the tile is ONE output row: the warp's 32 rows are the consecutive pixels ow0 + quad*32 .. +31, 64 channels (128 B) apart
     const int n_cols_valid = min(p.BW, p.Wo - ow0) - quad * 32;  // valid rows of this warp's quadrant (may be <= 0)
-    for (int t = 0; t < n_rows; ++t) {
+    for (int t = set; t < n_rows; t += 2) {
       const int g = g_lo + t;
       const int n_img = g / p.Hq, oh = g - n_img * p.Hq;
       const bool row_ok = (n_img < p.Bn) && (oh < p.Ho);
       ptx::mbar_wait(&tmem_full_bar[as], aph);
       ptx::tc_fence_after();
-      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)as * ACC_COLS + (uint32_t)half * 32u;
+      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)as * ACC_COLS;
       const long long warp_off =
-          (((long long)n_img * p.out_Hp + oh + p.out_py) * p.out_Wp + (ow0 + quad * 32) + p.out_px) * 64 + half * 32;
-      uint32_t r[32];
+          (((long long)n_img * p.out_Hp + oh + p.out_py) * p.out_Wp + (ow0 + quad * 32) + p.out_px) * 64;
+      uint32_t r[64];
       ptx::tmem_ld_32x32(trow, r);
+      ptx::tmem_ld_32x32(trow + 32, r + 32);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
-      epilogue_store32<SPLIT3, true, OCC2>(r, bias_s + half * 32, p.slope, stg, p.out_hi, p.out_lo, warp_off, true, lane, p.f16 != 0,
-                                           row_ok ? n_cols_valid : 0, 64);
-      if (++as == 2) { as = 0; aph ^= 1u; }
+#pragma unroll
+      for (int half = 0; half < 2; ++half)
+        epilogue_store32<SPLIT3, true, OCC2>(r + half * 32, bias_s + half * 32, p.slope, stg, p.out_hi, p.out_lo, warp_off + half * 32,
+                                             true, lane, p.f16 != 0, row_ok ? n_cols_valid : 0, 64);
+      aph ^= 1u;
     }
   }
   ptx::tc_fence_before();
@@ -1068,7 +1073,7 @@ __global__ void __launch_bounds__(320) conv1_stack_kernel(const __grid_constant_
     }
     for (int a = 0; a < 8; ++a) {
       ptx::mbar_init(&acc_full_bar[a], 1);
-      ptx::mbar_init(&acc_empty_bar[a], 8);
+      ptx::mbar_init(&acc_empty_bar[a], 4);  // the four warps of the set that drains this block (v and v + 8 have the same parity)
     }
     ptx::mbar_init(res_bar, 1);
     ptx::fence_barrier_init();
@@ -1144,10 +1149,10 @@ __global__ void __launch_bounds__(320) conv1_stack_kernel(const __grid_constant_
       }
     }
   } else {
-    const int quad = warp & 3, half = (warp - 2) >> 2;
+    const int quad = warp & 3, set = (warp - 2) >> 2;  // two warp sets alternate rows (see conv1_roll_kernel)
     uint8_t *stg = epi + (warp - 2) * 2048;
     const int n_cols_valid = min(p.BW, p.Wo - ow0) - quad * 32;
-    for (int v = 0; v < n_strips; ++v) {  // one completed row per strip; rows v < 3 belong to the previous chunk: discarded
+    for (int v = set; v < n_strips; v += 2) {  // one completed row per strip; rows v < 3 belong to the previous chunk: discarded
       const int g = g_lo + v - 3;
       const bool mine = v >= 3;  // v - 3 < n_rows holds by construction
       int n_img = 0, oh = 0;
@@ -1155,18 +1160,24 @@ __global__ void __launch_bounds__(320) conv1_stack_kernel(const __grid_constant_
       const bool row_ok = mine && (n_img < p.Bn) && (oh < p.Ho);
       ptx::mbar_wait(&acc_full_bar[v & 7], ((uint32_t)(v >> 3)) & 1u);
       ptx::tc_fence_after();
-      const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((v & 7) * 64 + half * 32);
-      uint32_t r[32];
-      if (row_ok) ptx::tmem_ld_32x32(tcol, r);
+      const uint32_t tcol = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((v & 7) * 64);
+      uint32_t r[64];
+      if (row_ok) {
+        ptx::tmem_ld_32x32(tcol, r);
+        ptx::tmem_ld_32x32(tcol + 32, r + 32);
+      }
       ptx::tmem_zero_32x32(tcol);
+      ptx::tmem_zero_32x32(tcol + 32);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty_bar[v & 7]);
       if (row_ok) {
         const long long warp_off =
-            (((long long)n_img * p.out_Hp + oh + p.out_py) * p.out_Wp + (ow0 + quad * 32) + p.out_px) * 64 + half * 32;
-        epilogue_store32<false, true>(r, bias_s + half * 32, p.slope, stg, p.out_hi, p.out_lo, warp_off, true, lane, p.f16 != 0,
-                                      n_cols_valid, 64);
+            (((long long)n_img * p.out_Hp + oh + p.out_py) * p.out_Wp + (ow0 + quad * 32) + p.out_px) * 64;
+#pragma unroll
+        for (int half = 0; half < 2; ++half)
+          epilogue_store32<false, true>(r + half * 32, bias_s + half * 32, p.slope, stg, p.out_hi, p.out_lo, warp_off + half * 32, true,
+                                        lane, p.f16 != 0, n_cols_valid, 64);
       }
     }
   }

@@ -311,10 +311,17 @@ struct FusedZoomParams {
   __nv_bfloat16 *hi, *lo;
 };
 
+// per-instance constants of the fused zoom, loaded once per thread (not once per output pixel)
+struct ZoomInst {
+  float zf[4];
+  int bx0, bx1, by0, by1;  // observed box (inclusive), bx1 < 0: empty
+  int vx0, vx1, vy0, vy1;  // region in which ren4 is valid (rasteriser's vertex box); background outside
+};
+
 template <bool LO, bool F16>
-__device__ __forceinline__ void zoom_fused_pixel(const FusedZoomParams &p, int b, int i, int j, const float *zf,
+__device__ __forceinline__ void zoom_fused_pixel(const FusedZoomParams &p, int b, int i, int j, const ZoomInst &ic,
                                                  __nv_bfloat16 *h, __nv_bfloat16 *l) {
-  const Tap t = src_coord(i, j, zf[0], zf[1], zf[2], zf[3], p.H, p.W, p.stepx, p.stepy);
+  const Tap t = src_coord(i, j, ic.zf[0], ic.zf[1], ic.zf[2], ic.zf[3], p.H, p.W, p.stepx, p.stepy);
   const bool x0ok = t.x0 >= 0 && t.x0 <= p.W - 1, x1ok = t.x0 + 1 >= 0 && t.x0 + 1 <= p.W - 1;
   const bool y0ok = t.y0 >= 0 && t.y0 <= p.H - 1, y1ok = t.y0 + 1 >= 0 && t.y0 + 1 <= p.H - 1;
   const bool k00 = y0ok && x0ok, k01 = y0ok && x1ok, k10 = y1ok && x0ok, k11 = y1ok && x1ok;
@@ -324,8 +331,7 @@ __device__ __forceinline__ void zoom_fused_pixel(const FusedZoomParams &p, int b
   const float4 O00 = k00 ? __ldg(p.obs4 + base + o) : z4, O01 = k01 ? __ldg(p.obs4 + base + o + 1) : z4;
   const float4 O10 = k10 ? __ldg(p.obs4 + base + o + p.W) : z4, O11 = k11 ? __ldg(p.obs4 + base + o + p.W + 1) : z4;
   // rendered taps: outside the rasteriser's vertex box the image is background by construction (and ren4 is not written there)
-  int vx0 = 0, vx1 = p.W, vy0 = 0, vy1 = p.H;
-  if (p.vbox) { vx0 = p.vbox[4 * b]; vx1 = p.vbox[4 * b + 1]; vy0 = p.vbox[4 * b + 2]; vy1 = p.vbox[4 * b + 3]; }
+  const int vx0 = ic.vx0, vx1 = ic.vx1, vy0 = ic.vy0, vy1 = ic.vy1;
   const float4 bg4 = make_float4(p.bg[0], p.bg[1], p.bg[2], 0.f);
   const bool vxa = t.x0 >= vx0 && t.x0 <= vx1, vxb = t.x0 + 1 >= vx0 && t.x0 + 1 <= vx1;
   const bool vya = t.y0 >= vy0 && t.y0 <= vy1, vyb = t.y0 + 1 >= vy0 && t.y0 + 1 <= vy1;
@@ -336,10 +342,15 @@ __device__ __forceinline__ void zoom_fused_pixel(const FusedZoomParams &p, int b
   const float wx1 = t.wx1, wy1 = t.wy1, ax = 1.0f - wx1, ay = 1.0f - wy1;
   const float wa = wy1 * wx1, wb = wy1 * ax, wc = ay * wx1, wd = ay * ax;
   float v[8];
-  // (img + mean) sampled with zero padding, then - mean, then the graph's /255
+  // (img + mean) sampled with zero padding, then - mean, then the graph's /255.  The IEEE division is spelled out as
+  // q = x * (1/255); q += (x - q * 255) * (1/255) with two fused multiply-adds: the correctly rounded quotient for every
+  // |x| < 2^10 (exhaustively compared with x / 255.0f on 2e7 samples + all integer texels), at 3 instructions instead of ~10
+  const float rcp255 = 1.0f / 255.0f;
   auto img = [&](float tl, float tr, float bl, float br, float m) -> float {
     tl = k00 ? tl + m : 0.f; tr = k01 ? tr + m : 0.f; bl = k10 ? bl + m : 0.f; br = k11 ? br + m : 0.f;
-    return (fmaf(br, wd, fmaf(bl, wc, fmaf(tr, wb, tl * wa))) - m) / 255.0f;
+    const float x = fmaf(br, wd, fmaf(bl, wc, fmaf(tr, wb, tl * wa))) - m;
+    const float q = x * rcp255;
+    return fmaf(fmaf(-q, 255.0f, x), rcp255, q);
   };
   v[0] = img(O00.x, O01.x, O10.x, O11.x, p.mean[0]);
   v[1] = img(O00.y, O01.y, O10.y, O11.y, p.mean[1]);
@@ -348,8 +359,7 @@ __device__ __forceinline__ void zoom_fused_pixel(const FusedZoomParams &p, int b
   v[4] = img(R00.y, R01.y, R10.y, R11.y, p.mean[1]);
   v[5] = img(R00.z, R01.z, R10.z, R11.z, p.mean[2]);
   {  // observed mask = rectangle; bb holds its inclusive bbox (x0, x1-1, y0, y1-1)
-    const int *bb = p.bbox8 + 8 * b;
-    const int bx0 = bb[0], bx1 = bb[1], by0 = bb[2], by1 = bb[3];
+    const int bx0 = ic.bx0, bx1 = ic.bx1, by0 = ic.by0, by1 = ic.by1;
     const bool cx0 = t.x0 >= bx0 && t.x0 <= bx1, cx1 = t.x0 + 1 >= bx0 && t.x0 + 1 <= bx1;
     const bool cy0 = t.y0 >= by0 && t.y0 <= by1, cy1 = t.y0 + 1 >= by0 && t.y0 + 1 <= by1;
     const bool any = bx1 >= 0;
@@ -383,14 +393,25 @@ __global__ void __launch_bounds__(128) zoom_fused_nhwc8_kernel(FusedZoomParams p
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= p.Hs * p.Ws) return;
   const int sr = q / p.Ws, sc = q - sr * p.Ws;
-  const float *zf = p.zoom_factor + 4 * b;
+  ZoomInst ic;
+  {
+    const float4 z = __ldg(reinterpret_cast<const float4 *>(p.zoom_factor) + b);
+    ic.zf[0] = z.x; ic.zf[1] = z.y; ic.zf[2] = z.z; ic.zf[3] = z.w;
+    const int4 bb = __ldg(reinterpret_cast<const int4 *>(p.bbox8) + 2 * b);
+    ic.bx0 = bb.x; ic.bx1 = bb.y; ic.by0 = bb.z; ic.by1 = bb.w;
+    ic.vx0 = 0; ic.vx1 = p.W; ic.vy0 = 0; ic.vy1 = p.H;
+    if (p.vbox) {
+      const int4 vb = __ldg(reinterpret_cast<const int4 *>(p.vbox) + b);
+      ic.vx0 = vb.x; ic.vx1 = vb.y; ic.vy0 = vb.z; ic.vy1 = vb.w;
+    }
+  }
   __align__(16) __nv_bfloat16 h[4][8];
   __align__(16) __nv_bfloat16 l[4][8];
 #pragma unroll
   for (int s = 0; s < 4; ++s) {
     const int i = 2 * sr + (s >> 1) - p.pad, j = 2 * sc + (s & 1) - p.pad;
     if (i >= 0 && i < p.H && j >= 0 && j < p.W) {
-      zoom_fused_pixel<LO, F16>(p, b, i, j, zf, h[s], l[s]);
+      zoom_fused_pixel<LO, F16>(p, b, i, j, ic, h[s], l[s]);
     } else {
 #pragma unroll
       for (int c = 0; c < 8; ++c) { h[s][c] = __float2bfloat16_rn(0.f); l[s][c] = __float2bfloat16_rn(0.f); }
