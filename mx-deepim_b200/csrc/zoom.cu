@@ -326,29 +326,30 @@ __device__ __forceinline__ void zoom_fused_pixel(const FusedZoomParams &p, int b
   const bool y0ok = t.y0 >= 0 && t.y0 <= p.H - 1, y1ok = t.y0 + 1 >= 0 && t.y0 + 1 <= p.H - 1;
   const bool k00 = y0ok && x0ok, k01 = y0ok && x1ok, k10 = y1ok && x0ok, k11 = y1ok && x1ok;
   const size_t base = (size_t)b * p.H * p.W;
+  // Zero padding is folded into the tap WEIGHTS: an out-of-frame tap gets weight 0 and its (in-bounds, arbitrary) value
+  // contributes exactly +-0, the same sum as the sampler's "value 0" -- no per-channel selects, no predicated loads.
   const long o = (long)t.y0 * p.W + t.x0;
-  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float4 O00 = k00 ? __ldg(p.obs4 + base + o) : z4, O01 = k01 ? __ldg(p.obs4 + base + o + 1) : z4;
-  const float4 O10 = k10 ? __ldg(p.obs4 + base + o + p.W) : z4, O11 = k11 ? __ldg(p.obs4 + base + o + p.W + 1) : z4;
+  const long o00 = k00 ? o : 0, o01 = k01 ? o + 1 : 0, o10 = k10 ? o + p.W : 0, o11 = k11 ? o + p.W + 1 : 0;
+  const float4 O00 = __ldg(p.obs4 + base + o00), O01 = __ldg(p.obs4 + base + o01);
+  const float4 O10 = __ldg(p.obs4 + base + o10), O11 = __ldg(p.obs4 + base + o11);
   // rendered taps: outside the rasteriser's vertex box the image is background by construction (and ren4 is not written there)
   const int vx0 = ic.vx0, vx1 = ic.vx1, vy0 = ic.vy0, vy1 = ic.vy1;
   const float4 bg4 = make_float4(p.bg[0], p.bg[1], p.bg[2], 0.f);
   const bool vxa = t.x0 >= vx0 && t.x0 <= vx1, vxb = t.x0 + 1 >= vx0 && t.x0 + 1 <= vx1;
   const bool vya = t.y0 >= vy0 && t.y0 <= vy1, vyb = t.y0 + 1 >= vy0 && t.y0 + 1 <= vy1;
-  const float4 R00 = k00 ? ((vya && vxa) ? __ldg(p.ren4 + base + o) : bg4) : z4;
-  const float4 R01 = k01 ? ((vya && vxb) ? __ldg(p.ren4 + base + o + 1) : bg4) : z4;
-  const float4 R10 = k10 ? ((vyb && vxa) ? __ldg(p.ren4 + base + o + p.W) : bg4) : z4;
-  const float4 R11 = k11 ? ((vyb && vxb) ? __ldg(p.ren4 + base + o + p.W + 1) : bg4) : z4;
+  const float4 R00 = (k00 && vya && vxa) ? __ldg(p.ren4 + base + o) : bg4;
+  const float4 R01 = (k01 && vya && vxb) ? __ldg(p.ren4 + base + o + 1) : bg4;
+  const float4 R10 = (k10 && vyb && vxa) ? __ldg(p.ren4 + base + o + p.W) : bg4;
+  const float4 R11 = (k11 && vyb && vxb) ? __ldg(p.ren4 + base + o + p.W + 1) : bg4;
   const float wx1 = t.wx1, wy1 = t.wy1, ax = 1.0f - wx1, ay = 1.0f - wy1;
-  const float wa = wy1 * wx1, wb = wy1 * ax, wc = ay * wx1, wd = ay * ax;
+  const float wa = k00 ? wy1 * wx1 : 0.f, wb = k01 ? wy1 * ax : 0.f, wc = k10 ? ay * wx1 : 0.f, wd = k11 ? ay * ax : 0.f;
   float v[8];
   // (img + mean) sampled with zero padding, then - mean, then the graph's /255.  The IEEE division is spelled out as
   // q = x * (1/255); q += (x - q * 255) * (1/255) with two fused multiply-adds: the correctly rounded quotient for every
   // |x| < 2^10 (exhaustively compared with x / 255.0f on 2e7 samples + all integer texels), at 3 instructions instead of ~10
   const float rcp255 = 1.0f / 255.0f;
   auto img = [&](float tl, float tr, float bl, float br, float m) -> float {
-    tl = k00 ? tl + m : 0.f; tr = k01 ? tr + m : 0.f; bl = k10 ? bl + m : 0.f; br = k11 ? br + m : 0.f;
-    const float x = fmaf(br, wd, fmaf(bl, wc, fmaf(tr, wb, tl * wa))) - m;
+    const float x = fmaf(br + m, wd, fmaf(bl + m, wc, fmaf(tr + m, wb, (tl + m) * wa))) - m;
     const float q = x * rcp255;
     return fmaf(fmaf(-q, 255.0f, x), rcp255, q);
   };
@@ -358,18 +359,18 @@ __device__ __forceinline__ void zoom_fused_pixel(const FusedZoomParams &p, int b
   v[3] = img(R00.x, R01.x, R10.x, R11.x, p.mean[0]);
   v[4] = img(R00.y, R01.y, R10.y, R11.y, p.mean[1]);
   v[5] = img(R00.z, R01.z, R10.z, R11.z, p.mean[2]);
-  {  // observed mask = rectangle; bb holds its inclusive bbox (x0, x1-1, y0, y1-1)
+  {  // observed mask = rectangle; bb holds its inclusive bbox (x0, x1-1, y0, y1-1); out-of-frame taps carry weight 0
     const int bx0 = ic.bx0, bx1 = ic.bx1, by0 = ic.by0, by1 = ic.by1;
     const bool cx0 = t.x0 >= bx0 && t.x0 <= bx1, cx1 = t.x0 + 1 >= bx0 && t.x0 + 1 <= bx1;
     const bool cy0 = t.y0 >= by0 && t.y0 <= by1, cy1 = t.y0 + 1 >= by0 && t.y0 + 1 <= by1;
     const bool any = bx1 >= 0;
-    const float tl = (any && k00 && cy0 && cx0) ? 1.f : 0.f, tr = (any && k01 && cy0 && cx1) ? 1.f : 0.f;
-    const float bl = (any && k10 && cy1 && cx0) ? 1.f : 0.f, br = (any && k11 && cy1 && cx1) ? 1.f : 0.f;
+    const float tl = (any && cy0 && cx0) ? 1.f : 0.f, tr = (any && cy0 && cx1) ? 1.f : 0.f;
+    const float bl = (any && cy1 && cx0) ? 1.f : 0.f, br = (any && cy1 && cx1) ? 1.f : 0.f;
     v[6] = roundf(fmaf(br, wd, fmaf(bl, wc, fmaf(tr, wb, tl * wa))));
   }
   {  // rendered mask, binarised at 0.2 (zoom_mask.py:39-41)
-    const float tl = (k00 && R00.w > 0.2f) ? 1.f : 0.f, tr = (k01 && R01.w > 0.2f) ? 1.f : 0.f;
-    const float bl = (k10 && R10.w > 0.2f) ? 1.f : 0.f, br = (k11 && R11.w > 0.2f) ? 1.f : 0.f;
+    const float tl = R00.w > 0.2f ? 1.f : 0.f, tr = R01.w > 0.2f ? 1.f : 0.f;
+    const float bl = R10.w > 0.2f ? 1.f : 0.f, br = R11.w > 0.2f ? 1.f : 0.f;
     v[7] = roundf(fmaf(br, wd, fmaf(bl, wc, fmaf(tr, wb, tl * wa))));
   }
 #pragma unroll
