@@ -231,6 +231,24 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo_bytes
 
 }  // namespace ptx
 
+// explicit shared-state-space accesses for the epilogues.  The staging tiles and the bias vector live in DYNAMIC shared memory
+// reached through an aligned generic pointer; the compiler cannot prove the address space and emitted generic LD / ST for them
+// (ncu: 8.6 M shared-load bank conflicts per conv1 launch, ~800 wasted shared-memory cycles per output tile on the pipe the
+// tensor core reads its operands through).  These go straight to LDS / STS.
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
 // two fp32 -> packed 16-bit pair (element 0 in the low half).  fp16 saturates to +-65504 instead of
 // overflowing to inf (the reference computes in fp32: a finite value must stay finite).
 __device__ __forceinline__ uint32_t pack2_f16(float a, float b) {
@@ -256,23 +274,27 @@ __device__ __forceinline__ void epilogue_store64(const uint32_t *r, const float 
                                                  bool my_valid, int lane, bool f16 = false) {
   __align__(16) uint32_t h[32];
   __align__(16) uint32_t l[SPLIT3 ? 32 : 4];
-  if (!SPLIT3 && f16) {
+  const uint32_t ba = ptx::smem_u32(bias_s), sa = ptx::smem_u32(stage);
 #pragma unroll
-    for (int j = 0; j < 64; j += 2) {
-      float v0 = __uint_as_float(r[j]) + bias_s[j], v1 = __uint_as_float(r[j + 1]) + bias_s[j + 1];
-      v0 = v0 > 0.f ? v0 : v0 * slope;
-      v1 = v1 > 0.f ? v1 : v1 * slope;
+  for (int j = 0; j < 64; j += 4) {
+    const float4 b4 = lds128f(ba + j * 4);
+    float v0 = __uint_as_float(r[j]) + b4.x, v1 = __uint_as_float(r[j + 1]) + b4.y;
+    float v2 = __uint_as_float(r[j + 2]) + b4.z, v3 = __uint_as_float(r[j + 3]) + b4.w;
+    v0 = v0 > 0.f ? v0 : v0 * slope;
+    v1 = v1 > 0.f ? v1 : v1 * slope;
+    v2 = v2 > 0.f ? v2 : v2 * slope;
+    v3 = v3 > 0.f ? v3 : v3 * slope;
+    if (!SPLIT3 && f16) {
       h[j >> 1] = pack2_f16(v0, v1);
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 64; j += 2) {
-      float v0 = __uint_as_float(r[j]) + bias_s[j], v1 = __uint_as_float(r[j + 1]) + bias_s[j + 1];
-      v0 = v0 > 0.f ? v0 : v0 * slope;
-      v1 = v1 > 0.f ? v1 : v1 * slope;
-      const uint32_t hh = pack2_bf16(v0, v1);
-      h[j >> 1] = hh;
-      if (SPLIT3) l[j >> 1] = pack2_bf16(v0 - __uint_as_float(hh << 16), v1 - __uint_as_float(hh & 0xFFFF0000u));
+      h[(j >> 1) + 1] = pack2_f16(v2, v3);
+    } else {
+      const uint32_t h0 = pack2_bf16(v0, v1), h1 = pack2_bf16(v2, v3);
+      h[j >> 1] = h0;
+      h[(j >> 1) + 1] = h1;
+      if (SPLIT3) {
+        l[j >> 1] = pack2_bf16(v0 - __uint_as_float(h0 << 16), v1 - __uint_as_float(h0 & 0xFFFF0000u));
+        l[(j >> 1) + 1] = pack2_bf16(v2 - __uint_as_float(h1 << 16), v3 - __uint_as_float(h1 & 0xFFFF0000u));
+      }
     }
   }
   const unsigned vmask = __ballot_sync(0xffffffffu, my_valid);
@@ -283,22 +305,19 @@ __device__ __forceinline__ void epilogue_store64(const uint32_t *r, const float 
     __nv_bfloat16 *out = pass ? out_lo : out_hi;
 #pragma unroll
     for (int c = 0; c < 8; ++c)
-      *reinterpret_cast<uint4 *>(stage + lane * 128 + ((c ^ (lane & 7)) << 4)) = *reinterpret_cast<const uint4 *>(src + c * 4);
+      sts128(sa + lane * 128 + ((c ^ (lane & 7)) << 4), *reinterpret_cast<const uint4 *>(src + c * 4));
     __syncwarp();
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int row = i * 4 + (lane >> 3);
       const long long off = __shfl_sync(0xffffffffu, my_off, row);
-      if ((vmask >> row) & 1u)
-        *reinterpret_cast<uint4 *>(out + off + ch * 8) =
-            *reinterpret_cast<const uint4 *>(stage + row * 128 + ((ch ^ (row & 7)) << 4));
+      const uint4 v = lds128(sa + row * 128 + ((ch ^ (row & 7)) << 4));
+      if ((vmask >> row) & 1u) *reinterpret_cast<uint4 *>(out + off + ch * 8) = v;
     }
     __syncwarp();
   }
 }
 
-// 32-column variant (conv1 with two epilogue warps per TMEM lane quadrant): 32 fp32 columns -> 64 bytes per row, staged
-// through a per-warp 2 KB XOR-swizzled tile; lane l then writes 16 B of row i*8 + l/4 (8 rows x 64 B per instruction).
 // LINEAR: the 32 rows of the warp are consecutive pixels of one output row (conv1): row r lives at my_off(row 0) + r * row_stride
 // elements and rows [0, n_valid) are valid -- no per-row offset shuffle, no ballot (my_off / my_valid are then warp-uniform:
 // offset of the warp's row 0 and unused).  HALF_STAGE: the staging tile is 1 KB (32 rows x 32 B) and the 32 columns go out in two
@@ -309,17 +328,27 @@ __device__ __forceinline__ void epilogue_store32(const uint32_t *r, const float 
                                                  bool my_valid, int lane, bool f16, int n_valid = 32, int row_stride = 0) {
   __align__(16) uint32_t h[16];
   __align__(16) uint32_t l[SPLIT3 ? 16 : 4];
+  const uint32_t ba = ptx::smem_u32(bias_s), sa = ptx::smem_u32(stage);
 #pragma unroll
-  for (int j = 0; j < 32; j += 2) {
-    float v0 = __uint_as_float(r[j]) + bias_s[j], v1 = __uint_as_float(r[j + 1]) + bias_s[j + 1];
+  for (int j = 0; j < 32; j += 4) {
+    const float4 b4 = lds128f(ba + j * 4);
+    float v0 = __uint_as_float(r[j]) + b4.x, v1 = __uint_as_float(r[j + 1]) + b4.y;
+    float v2 = __uint_as_float(r[j + 2]) + b4.z, v3 = __uint_as_float(r[j + 3]) + b4.w;
     v0 = v0 > 0.f ? v0 : v0 * slope;
     v1 = v1 > 0.f ? v1 : v1 * slope;
+    v2 = v2 > 0.f ? v2 : v2 * slope;
+    v3 = v3 > 0.f ? v3 : v3 * slope;
     if (!SPLIT3 && f16) {
       h[j >> 1] = pack2_f16(v0, v1);
+      h[(j >> 1) + 1] = pack2_f16(v2, v3);
     } else {
-      const uint32_t hh = pack2_bf16(v0, v1);
-      h[j >> 1] = hh;
-      if (SPLIT3) l[j >> 1] = pack2_bf16(v0 - __uint_as_float(hh << 16), v1 - __uint_as_float(hh & 0xFFFF0000u));
+      const uint32_t h0 = pack2_bf16(v0, v1), h1 = pack2_bf16(v2, v3);
+      h[j >> 1] = h0;
+      h[(j >> 1) + 1] = h1;
+      if (SPLIT3) {
+        l[j >> 1] = pack2_bf16(v0 - __uint_as_float(h0 << 16), v1 - __uint_as_float(h0 & 0xFFFF0000u));
+        l[(j >> 1) + 1] = pack2_bf16(v2 - __uint_as_float(h1 << 16), v3 - __uint_as_float(h1 & 0xFFFF0000u));
+      }
     }
   }
   const unsigned vmask = LINEAR ? 0u : __ballot_sync(0xffffffffu, my_valid);
@@ -332,14 +361,13 @@ __device__ __forceinline__ void epilogue_store32(const uint32_t *r, const float 
       for (int hc = 0; hc < 2; ++hc) {  // columns [16 hc, 16 hc + 16): 32 B per row
 #pragma unroll
         for (int c = 0; c < 2; ++c)
-          *reinterpret_cast<uint4 *>(stage + lane * 32 + ((c ^ ((lane >> 2) & 1)) << 4)) = *reinterpret_cast<const uint4 *>(src + hc * 8 + c * 4);
+          sts128(sa + lane * 32 + ((c ^ ((lane >> 2) & 1)) << 4), *reinterpret_cast<const uint4 *>(src + hc * 8 + c * 4));
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           const int row = i * 16 + (lane >> 1), ch2 = lane & 1;
-          if (row < n_valid)
-            *reinterpret_cast<uint4 *>(out + my_off + (long long)row * row_stride + hc * 16 + ch2 * 8) =
-                *reinterpret_cast<const uint4 *>(stage + row * 32 + ((ch2 ^ ((row >> 2) & 1)) << 4));
+          const uint4 v = lds128(sa + row * 32 + ((ch2 ^ ((row >> 2) & 1)) << 4));
+          if (row < n_valid) *reinterpret_cast<uint4 *>(out + my_off + (long long)row * row_stride + hc * 16 + ch2 * 8) = v;
         }
         __syncwarp();
       }
@@ -353,20 +381,17 @@ __device__ __forceinline__ void epilogue_store32(const uint32_t *r, const float 
     __nv_bfloat16 *out = pass ? out_lo : out_hi;
 #pragma unroll
     for (int c = 0; c < 4; ++c)
-      *reinterpret_cast<uint4 *>(stage + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) = *reinterpret_cast<const uint4 *>(src + c * 4);
+      sts128(sa + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4), *reinterpret_cast<const uint4 *>(src + c * 4));
     __syncwarp();
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int row = i * 8 + (lane >> 2);
+      const uint4 v = lds128(sa + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));
       if (LINEAR) {
-        if (row < n_valid)
-          *reinterpret_cast<uint4 *>(out + my_off + (long long)row * row_stride + ch * 8) =
-              *reinterpret_cast<const uint4 *>(stage + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));
+        if (row < n_valid) *reinterpret_cast<uint4 *>(out + my_off + (long long)row * row_stride + ch * 8) = v;
       } else {
         const long long off = __shfl_sync(0xffffffffu, my_off, row);
-        if ((vmask >> row) & 1u)
-          *reinterpret_cast<uint4 *>(out + off + ch * 8) =
-              *reinterpret_cast<const uint4 *>(stage + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));
+        if ((vmask >> row) & 1u) *reinterpret_cast<uint4 *>(out + off + ch * 8) = v;
       }
     }
     __syncwarp();
@@ -381,17 +406,23 @@ __device__ __forceinline__ void epilogue_generic64(const uint32_t *r, const Conv
   const bool has_bias = p.bias != nullptr;
   const bool has_add = p.addend.p != nullptr && my_valid && chan_ok;
   const bool has_mask = p.mask.p != nullptr && my_valid && use_mask && chan_ok;
+  const uint32_t ba = ptx::smem_u32(bias_s), sa = ptx::smem_u32(stage);
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     __align__(16) __nv_bfloat16 a8[8];
     __align__(16) __nv_bfloat16 m8[8];
+    float b8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (has_bias) {
+      const float4 b0 = lds128f(ba + q * 32), b1 = lds128f(ba + q * 32 + 16);
+      b8[0] = b0.x; b8[1] = b0.y; b8[2] = b0.z; b8[3] = b0.w; b8[4] = b1.x; b8[5] = b1.y; b8[6] = b1.z; b8[7] = b1.w;
+    }
     if (has_add) *reinterpret_cast<uint4 *>(a8) = *reinterpret_cast<const uint4 *>(p.addend.p + add_off + q * 8);
     if (has_mask) *reinterpret_cast<uint4 *>(m8) = *reinterpret_cast<const uint4 *>(p.mask.p + mask_off + q * 8);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int j = q * 8 + e;
       float v = __uint_as_float(r[j]);
-      if (has_bias) v += bias_s[j];
+      if (has_bias) v += b8[e];
       if (has_add) v += __bfloat162float(a8[e]);
       if (p.mask.p != nullptr) {
         if (has_mask && !(__bfloat162float(m8[e]) > 0.f)) v *= p.slope;
@@ -404,16 +435,14 @@ __device__ __forceinline__ void epilogue_generic64(const uint32_t *r, const Conv
   const unsigned vmask = __ballot_sync(0xffffffffu, my_valid && chan_ok);
   const int ch = lane & 7;
 #pragma unroll
-  for (int c = 0; c < 8; ++c)
-    *reinterpret_cast<uint4 *>(stage + lane * 128 + ((c ^ (lane & 7)) << 4)) = *reinterpret_cast<const uint4 *>(h + c * 8);
+  for (int c = 0; c < 8; ++c) sts128(sa + lane * 128 + ((c ^ (lane & 7)) << 4), *reinterpret_cast<const uint4 *>(h + c * 8));
   __syncwarp();
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int row = i * 4 + (lane >> 3);
     const long long off = __shfl_sync(0xffffffffu, my_off, row);
-    if ((vmask >> row) & 1u)
-      *reinterpret_cast<uint4 *>(p.out_hi + off + ch * 8) =
-          *reinterpret_cast<const uint4 *>(stage + row * 128 + ((ch ^ (row & 7)) << 4));
+    const uint4 v = lds128(sa + row * 128 + ((ch ^ (row & 7)) << 4));
+    if ((vmask >> row) & 1u) *reinterpret_cast<uint4 *>(p.out_hi + off + ch * 8) = v;
   }
   __syncwarp();
 }
