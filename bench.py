@@ -336,7 +336,7 @@ def run_b200(args):
                     "d2h_bytes_per_step": int(SB * N_ITER * B * (96 + 28)), "ms_per_step": round(ms_e2e / K_steps, 4),
                     "api": "PoseRefiner.submit/result -> dim_refine_host_async (uint8 BGR HWC pinned host images in, float64 poses out; %d batches in flight)" % args.slots, "timer": "host wall clock around K steps, bracketed by barrier + cuda synchronize"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "conv1_strip_kernel + conv_igemm_persistent_kernel (10 launches per batch-iteration)",
+            "roofline": {"bound": "tensor", "kernel": "conv1_stack_kernel + conv_igemm_pair_kernel (conv2) + conv_igemm_persistent_kernel x8 (10 launches per batch-iteration)",
                          "achieved": round(step_tflops, 2), "peak": peak, "unit": "TFLOP/s",
                          "frac": round(step_tflops / peak, 4), "traffic": traffic,
                          "how": "algorithmic conv FLOPs of the timed region (38.79 GFLOP x %d instances x %d iterations x %d batches x %d steps) / "

@@ -320,9 +320,8 @@ __device__ __forceinline__ void epilogue_store64(const uint32_t *r, const float 
 
 // LINEAR: the 32 rows of the warp are consecutive pixels of one output row (conv1): row r lives at my_off(row 0) + r * row_stride
 // elements and rows [0, n_valid) are valid -- no per-row offset shuffle, no ballot (my_off / my_valid are then warp-uniform:
-// offset of the warp's row 0 and unused).  HALF_STAGE: the staging tile is 1 KB (32 rows x 32 B) and the 32 columns go out in two
-// 16-column passes (used with LINEAR by the 2-CTAs-per-SM conv1 kernel, whose shared memory is tight).
-template <bool SPLIT3, bool LINEAR = false, bool HALF_STAGE = false>
+// offset of the warp's row 0 and unused).
+template <bool SPLIT3, bool LINEAR = false>
 __device__ __forceinline__ void epilogue_store32(const uint32_t *r, const float *bias_s, float slope, uint8_t *stage,
                                                  __nv_bfloat16 *out_hi, __nv_bfloat16 *out_lo, long long my_off,
                                                  bool my_valid, int lane, bool f16, int n_valid = 32, int row_stride = 0) {
@@ -352,28 +351,6 @@ __device__ __forceinline__ void epilogue_store32(const uint32_t *r, const float 
     }
   }
   const unsigned vmask = LINEAR ? 0u : __ballot_sync(0xffffffffu, my_valid);
-  if (HALF_STAGE) {  // LINEAR only
-#pragma unroll
-    for (int pass = 0; pass < (SPLIT3 ? 2 : 1); ++pass) {
-      const uint32_t *src = pass ? l : h;
-      __nv_bfloat16 *out = pass ? out_lo : out_hi;
-#pragma unroll
-      for (int hc = 0; hc < 2; ++hc) {  // columns [16 hc, 16 hc + 16): 32 B per row
-#pragma unroll
-        for (int c = 0; c < 2; ++c)
-          sts128(sa + lane * 32 + ((c ^ ((lane >> 2) & 1)) << 4), *reinterpret_cast<const uint4 *>(src + hc * 8 + c * 4));
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int row = i * 16 + (lane >> 1), ch2 = lane & 1;
-          const uint4 v = lds128(sa + row * 32 + ((ch2 ^ ((row >> 2) & 1)) << 4));
-          if (row < n_valid) *reinterpret_cast<uint4 *>(out + my_off + (long long)row * row_stride + hc * 16 + ch2 * 8) = v;
-        }
-        __syncwarp();
-      }
-    }
-    return;
-  }
   const int ch = lane & 3;
 #pragma unroll
   for (int pass = 0; pass < (SPLIT3 ? 2 : 1); ++pass) {
@@ -716,182 +693,22 @@ __device__ __forceinline__ uint64_t umma_desc_interleave(uint32_t saddr, uint32_
   return d;
 }
 
-template <int STAGES, bool SPLIT3>
-struct Conv1Smem {
-  static constexpr int MAXR = 128 + 3;                      // strip pixels incl. halo
-  static constexpr int A_BYTES = ((MAXR * 64 + 127) / 128) * 128;  // one strip (4 chunks x R x 16 B), 128-B aligned
-  static constexpr int NPREC = SPLIT3 ? 2 : 1;
-  static constexpr int STAGE_BYTES = A_BYTES * NPREC;
-  static constexpr int B_BYTES = 64 * 32 * 2;               // one tap tile of the weights
-  static constexpr int RES_BYTES = 16 * B_BYTES * NPREC;
-  static constexpr int TAIL = 0;  // don't-care rows of the last strip are read past it, into the staging tiles (harmless)
-  static constexpr int EPI_BYTES = 4 * 4096 + 256;  // per-warp staging tiles + 64 bias floats
-  static constexpr int TOTAL = RES_BYTES + STAGES * STAGE_BYTES + TAIL + EPI_BYTES + 1024 + 512;
-};
-
-template <int STAGES, bool SPLIT3>
-__global__ void __launch_bounds__(192) conv1_strip_kernel(const __grid_constant__ ConvKParams p, const int total_tiles) {
-  using S = Conv1Smem<STAGES, SPLIT3>;
-  constexpr uint32_t ACC_COLS = 64, TMEM_COLS = 128;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t *res = smem;                       // resident weights, SW64 tiles (512-B aligned)
-  uint8_t *ring = smem + S::RES_BYTES;       // strips
-  uint8_t *epi = ring + STAGES * S::STAGE_BYTES + S::TAIL;
-  float *bias_s = reinterpret_cast<float *>(epi + 4 * 4096);
-  uint64_t *full_bar = reinterpret_cast<uint64_t *>(epi + S::EPI_BYTES);
-  uint64_t *empty_bar = full_bar + STAGES;
-  uint64_t *tmem_full_bar = empty_bar + STAGES;
-  uint64_t *tmem_empty_bar = tmem_full_bar + 2;
-  uint64_t *res_bar = tmem_empty_bar + 2;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(res_bar + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int R = p.BW + 3;                    // strip width in pixels
-  const uint32_t LBO = (uint32_t)R * 16u;    // distance between 8-channel chunks
-
-  if (warp == 0 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      ptx::mbar_init(&tmem_full_bar[a], 1);
-      ptx::mbar_init(&tmem_empty_bar[a], 4);
-    }
-    ptx::mbar_init(res_bar, 1);
-    ptx::fence_barrier_init();
-    ptx::prefetch_tmap(&p.b_map);
-    ptx::prefetch_tmap(&p.a_map[0]);
-  }
-  if (threadIdx.x < 64) bias_s[threadIdx.x] = p.bias[threadIdx.x];
-  if (warp == 1) ptx::tmem_alloc(tmem_slot, TMEM_COLS);
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    {
-      ptx::mbar_expect_tx(res_bar, (uint32_t)S::RES_BYTES);
-      for (int kb = 0; kb < 16; ++kb) {
-        ptx::tma_load_2d(res + kb * S::B_BYTES, &p.b_map, res_bar, kb * 32, 0);
-        if (SPLIT3) ptx::tma_load_2d(res + (16 + kb) * S::B_BYTES, &p.b_lo_map, res_bar, kb * 32, 0);
-      }
-      const uint32_t tx = (uint32_t)(R * 64) * S::NPREC;
-      int s = 0;
-      uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int ct = tile % p.n_col_tiles, g = tile / p.n_col_tiles;
-        const int ow0 = ct * p.BW;
-        for (int dh = 0; dh < 4; ++dh) {
-          ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
-          uint8_t *st = ring + s * S::STAGE_BYTES;
-          ptx::mbar_expect_tx(&full_bar[s], tx);
-          tma_load_4d(st, &p.a_map[0], &full_bar[s], 0, ow0, 0, g + dh);
-          if (SPLIT3) tma_load_4d(st + S::A_BYTES, &p.a_lo_map[0], &full_bar[s], 0, ow0, 0, g + dh);
-          if (++s == STAGES) { s = 0; ph ^= 1u; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    {
-      ptx::mbar_wait(res_bar, 0);
-      ptx::tc_fence_after();
-      int s = 0, as = 0;
-      uint32_t ph = 0, aph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        ptx::mbar_wait(&tmem_empty_bar[as], aph ^ 1u);
-        ptx::tc_fence_after();
-        const uint32_t tmem_acc = tmem_base + (uint32_t)as * ACC_COLS;
-        for (int dh = 0; dh < 4; ++dh) {
-          ptx::mbar_wait(&full_bar[s], ph);
-          ptx::tc_fence_after();
-          const uint32_t a_hi = ptx::smem_u32(ring + s * S::STAGE_BYTES);
-          const uint32_t a_lo = a_hi + S::A_BYTES;
-          if (ptx::elect_one()) {
-            // one election per strip; every descriptor = base + (byte offset >> 4): dw shifts the strip by one pixel (16 B),
-            // k selects the pair of 8-channel chunks (2 * LBO bytes), the weight tile of tap (dh, dw) is 4 KB further
-            const uint64_t da0 = umma_desc_interleave(a_hi, LBO, 128), dal0 = umma_desc_interleave(a_lo, LBO, 128);
-            const uint64_t db0 = ptx::umma_desc(ptx::smem_u32(res) + dh * 4 * S::B_BYTES, 512, 4u);
-            const uint64_t dbl0 = ptx::umma_desc(ptx::smem_u32(res) + (16 + dh * 4) * S::B_BYTES, 512, 4u);
-            const uint64_t kstep = (uint64_t)(2u * LBO >> 4);
-#pragma unroll
-            for (int dw = 0; dw < 4; ++dw) {
-#pragma unroll
-              for (int k = 0; k < 2; ++k) {  // 16 channels = 2 chunks per UMMA: k = 0 -> row parity 0, k = 1 -> row parity 1
-                if (dh == 3 && k == 1) continue;  // kh = 2*3 + 1 = 7 lies outside the 7x7 filter: all-zero weights, skip the MMA
-                const uint32_t acc = (dh | dw | k) ? 1u : 0u;
-                const uint64_t da = da0 + (uint64_t)dw + (uint64_t)k * kstep;
-                const uint64_t db = db0 + (uint64_t)(dw * (S::B_BYTES >> 4) + 2 * k);
-                ptx::umma_f16_raw(tmem_acc, da, db, p.idesc, acc);
-                if (SPLIT3) {
-                  ptx::umma_f16_raw(tmem_acc, dal0 + (uint64_t)dw + (uint64_t)k * kstep, db, p.idesc, 1u);
-                  ptx::umma_f16_raw(tmem_acc, da, dbl0 + (uint64_t)(dw * (S::B_BYTES >> 4) + 2 * k), p.idesc, 1u);
-                }
-              }
-            }
-            ptx::umma_commit_raw(&empty_bar[s]);
-          }
-          __syncwarp();
-          if (++s == STAGES) { s = 0; ph ^= 1u; }
-        }
-        ptx::umma_commit(&tmem_full_bar[as]);
-        if (++as == 2) { as = 0; aph ^= 1u; }
-      }
-    }
-  } else {
-    const int quad = warp & 3;
-    const int m = quad * 32 + lane;
-    int as = 0;
-    uint32_t aph = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int ct = tile % p.n_col_tiles, g = tile / p.n_col_tiles;
-      const int ow = ct * p.BW + m;
-      const int n_img = g / p.Hq, oh = g - n_img * p.Hq;
-      const bool valid = (m < p.BW) && (n_img < p.Bn) && (oh < p.Ho) && (ow < p.Wo);
-      ptx::mbar_wait(&tmem_full_bar[as], aph);
-      ptx::tc_fence_after();
-      const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)as * ACC_COLS;
-      const long long my_off = (((long long)n_img * p.out_Hp + oh + p.out_py) * p.out_Wp + ow + p.out_px) * 64;
-      uint32_t r[64];
-      ptx::tmem_ld_32x32(trow, r);
-      ptx::tmem_ld_32x32(trow + 32, r + 32);
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);  // accumulator stage is free again
-      epilogue_store64<SPLIT3>(r, bias_s, p.slope, epi + (warp - 2) * 4096, p.out_hi, p.out_lo, my_off, valid, lane, p.f16 != 0);
-      if (++as == 2) { as = 0; aph ^= 1u; }
-    }
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// conv1, rolling-strip variant.  The strip kernel above gives every output row its own four input strips, so each
-// strip travels L2 -> shared memory four times (once per filter row dh) -- 0.68 GB per launch against 0.16 GB of
-// input.  Here a CTA owns one column tile and a CONTIGUOUS run of output rows [g_lo, g_hi) and walks down it: output
-// row g uses strips g .. g+3, so moving to row g+1 needs ONE new strip; the other three are still in the ring.
+// conv1, rolling strips (used by the hi/lo precision; the single-pass precisions run conv1_stack_kernel below).  A CTA owns
+// one column tile and a CONTIGUOUS run of output rows [g_lo, g_hi) and walks down it: output row g uses the input strips
+// g .. g+3 (one per filter row dh), so moving to row g+1 needs ONE new strip; the other three are still in the ring --
+// every strip travels L2 -> shared memory once (plus a 3-row halo per chunk) instead of once per filter row.
 // Strip s of the chunk (input row g_lo + s) lives in ring slot s % STAGES from its TMA fill until the MMAs of output
-// row s (its last user) have completed (tcgen05.commit -> empty barrier).  L2 -> SM traffic and the TMA writes into
-// shared memory drop 4x (plus a 3-row halo per chunk); MMA sequence, accumulators, epilogue are those of the strip
-// kernel.  One CTA per SM (64 KB resident weights + an 8-deep ring), grid = column tiles x chunks.  With a single CTA per SM the
-// per-tile epilogue (64 columns: ~2.6k cycles on 4 warps) is longer than the tile's 0.9k cycles of MMAs, so EIGHT epilogue
-// warps share it: two per TMEM lane quadrant, 32 accumulator columns each (320 threads).
-template <int STAGES, bool SPLIT3, bool OCC2 = false>
-__global__ void __launch_bounds__(320, OCC2 ? 2 : 1) conv1_roll_kernel(const __grid_constant__ ConvKParams p, const int rows_total,
+// row s (its last user) have completed (tcgen05.commit -> empty barrier).  Per output row: 4 dh x 4 dw x 2 K-halves of
+// 128 x 64 x 16 MMAs into one of two 64-column accumulator stages.  One CTA per SM (64 KB resident weights per precision
+// + the ring), grid = column tiles x chunks.  The per-row epilogue is a latency chain longer than the row's MMAs, so
+// EIGHT epilogue warps in two alternating sets of four (one warp per TMEM lane quadrant) drain the rows (320 threads).
+template <int STAGES, bool SPLIT3>
+__global__ void __launch_bounds__(320) conv1_roll_kernel(const __grid_constant__ ConvKParams p, const int rows_total,
                                                          const int rows_per_chunk, const int chunks_per_col,
                                                          const int strip_bytes /*per precision, multiple of 128*/) {
   constexpr uint32_t ACC_COLS = 64, TMEM_COLS = 128;
   constexpr int NPREC = SPLIT3 ? 2 : 1;
-  // OCC2: two CTAs per SM (each MMA warp is one latency-bound instruction stream; a second CTA hides it): 5-deep ring,
-  // 1 KB staging tile per epilogue warp, 128-byte alignment of the dynamic shared memory is enough (no swizzle-128 tiles)
-  constexpr int STG = OCC2 ? 1024 : 2048;
+  constexpr int STG = 2048;  // staging tile per epilogue warp
   constexpr int B_BYTES = 64 * 32 * 2, RES_BYTES = 16 * B_BYTES * NPREC, EPI_BYTES = 8 * STG + 256;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 511) & ~(uintptr_t)511);
@@ -1040,7 +857,7 @@ __global__ void __launch_bounds__(320, OCC2 ? 2 : 1) conv1_roll_kernel(const __g
       if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
 #pragma unroll
       for (int half = 0; half < 2; ++half)
-        epilogue_store32<SPLIT3, true, OCC2>(r + half * 32, bias_s + half * 32, p.slope, stg, p.out_hi, p.out_lo, warp_off + half * 32,
+        epilogue_store32<SPLIT3, true>(r + half * 32, bias_s + half * 32, p.slope, stg, p.out_hi, p.out_lo, warp_off + half * 32,
                                              true, lane, p.f16 != 0, row_ok ? n_cols_valid : 0, 64);
       aph ^= 1u;
     }

@@ -1,8 +1,8 @@
 // net.cu -- FlowNetS encoder + fc + heads on the device (deepim/symbols/deepIM_flownet.py:53-116 and
 // 716-726), weight repacking, tensor-map construction and layer scheduling.
 //
-//   conv tower : conv1_strip_kernel + 9 x conv_igemm_persistent_kernel (tcgen05 + TMA, conv_igemm.cuh), split-K + finalize for the
-//                layers whose tile count cannot fill 148 SMs
+//   conv tower : conv1_stack_kernel / conv1_roll_kernel + 9 x conv_igemm_persistent_kernel / conv_igemm_pair_kernel (tcgen05 + TMA,
+//                conv_igemm.cuh), split-K + finalize for the layers whose tile count cannot fill 148 SMs
 //   fc6        : 81920 -> 256, a pure weight stream (HBM-bound): split-K mma.sync kernel (batch = M = 16),
 //                deterministic two-pass reduction (partials reduced in fixed order by the head kernel)
 //   head       : fc6 reduce + bias + LeakyReLU -> fc7 -> LeakyReLU -> rot(4), trans(3) ->
@@ -588,8 +588,8 @@ int net_forward(dim_ctx *ctx, int B, int precision, const float *zoom_factor, fl
     const int total_tiles = cdiv(B * g.Hq, g.BH) * g.n_col_tiles * n_tiles * kp.ksplit;
     const int sms = ns->num_sms;
     int rc;
-    if (i == 0 && ns->conv1_roll) {
-      // conv1, rolling strips: a CTA walks down a run of output rows of one column tile, one new input strip per row
+    if (i == 0) {
+      // conv1: a CTA walks down a run of output rows of one column tile, one new input strip per row
       const int rows_total = B * g.Hq;
       int chunks = sms / g.n_col_tiles;
       if (chunks > cdiv(rows_total, 16)) chunks = cdiv(rows_total, 16);  // keep the 3-row halo below ~20 %
@@ -598,9 +598,9 @@ int net_forward(dim_ctx *ctx, int B, int precision, const float *zoom_factor, fl
       chunks = cdiv(rows_total, rpc);
       const int strip_bytes = cdiv((g.BW + 3) * 64, 128) * 128;
       const int grid = g.n_col_tiles * chunks;
-      if (s3) {
+      if (s3) {  // hi/lo operands: rolling strips, three MMA passes per step
         constexpr int ST = 5;
-        const int smem_bytes = 2 * 16 * 4096 + ST * 2 * strip_bytes + (4 * 4096 + 256) + 1024 + 512;
+        const int smem_bytes = 2 * 16 * 4096 + ST * 2 * strip_bytes + (8 * 2048 + 256) + 1024 + 512;
         DIM_REQUIRE(smem_bytes <= 227 * 1024, "conv1 (bf16x3): image too wide for the rolling-strip ring");
         static int set1 = 0;
         if (set1 < smem_bytes) { DIM_CHECK(cudaFuncSetAttribute(conv1_roll_kernel<ST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); set1 = smem_bytes; }
@@ -612,41 +612,12 @@ int net_forward(dim_ctx *ctx, int B, int precision, const float *zoom_factor, fl
         static int set3 = 0;
         if (set3 < smem_bytes) { DIM_CHECK(cudaFuncSetAttribute(conv1_stack_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); set3 = smem_bytes; }
         conv1_stack_kernel<ST><<<grid, 320, smem_bytes, st>>>(kp, rows_total, rpc, chunks, strip_bytes);
-      } else if (ns->conv1_occ2) {
-        // two CTAs per SM: 64 KB weights + 5 strips + 8 KB staging = ~108 KB each; twice the chunks (shorter runs, 7.5 % halo)
-        constexpr int ST = 5;
-        int chunks2 = (2 * sms) / g.n_col_tiles;
-        if (chunks2 > cdiv(rows_total, 16)) chunks2 = cdiv(rows_total, 16);
-        if (chunks2 < 1) chunks2 = 1;
-        const int rpc2 = cdiv(rows_total, chunks2);
-        chunks2 = cdiv(rows_total, rpc2);
-        const int smem_bytes = 16 * 4096 + ST * strip_bytes + (8 * 1024 + 256) + 512 + 512;
-        DIM_REQUIRE(smem_bytes <= 113 * 1024, "conv1: image too wide for two rolling-strip CTAs per SM");
-        static int set2 = 0;
-        if (set2 < smem_bytes) { DIM_CHECK(cudaFuncSetAttribute(conv1_roll_kernel<ST, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); set2 = smem_bytes; }
-        conv1_roll_kernel<ST, false, true><<<g.n_col_tiles * chunks2, 320, smem_bytes, st>>>(kp, rows_total, rpc2, chunks2, strip_bytes);
       } else {
         constexpr int ST = 8;
-        const int smem_bytes = 16 * 4096 + ST * strip_bytes + (4 * 4096 + 256) + 1024 + 512;
+        const int smem_bytes = 16 * 4096 + ST * strip_bytes + (8 * 2048 + 256) + 1024 + 512;
         static int set0 = 0;
         if (set0 < smem_bytes) { DIM_CHECK(cudaFuncSetAttribute(conv1_roll_kernel<ST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); set0 = smem_bytes; }
         conv1_roll_kernel<ST, false><<<grid, 320, smem_bytes, st>>>(kp, rows_total, rpc, chunks, strip_bytes);
-      }
-      DIM_LAUNCH_CHECK();
-      rc = 0;
-    }
-    else if (i == 0) {  // conv1: strip kernel (one TMA strip per filter row, shifted un-swizzled descriptors)
-      const int tiles1 = B * g.Hq * g.n_col_tiles;
-      if (s3) {
-        using S1 = Conv1Smem<4, true>;
-        static bool set1 = false;
-        if (!set1) { DIM_CHECK(cudaFuncSetAttribute(conv1_strip_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S1::TOTAL)); set1 = true; }
-        conv1_strip_kernel<4, true><<<tiles1 < sms ? tiles1 : sms, 192, S1::TOTAL, st>>>(kp, tiles1);
-      } else {
-        using S1 = Conv1Smem<3, false>;
-        static bool set0 = false;
-        if (!set0) { DIM_CHECK(cudaFuncSetAttribute(conv1_strip_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S1::TOTAL)); set0 = true; }
-        conv1_strip_kernel<3, false><<<tiles1 < 2 * sms ? tiles1 : 2 * sms, 192, S1::TOTAL, st>>>(kp, tiles1);
       }
       DIM_LAUNCH_CHECK();
       rc = 0;
@@ -709,8 +680,6 @@ int net_set_option(dim_ctx *ctx, const char *key, int value) {
   NetState *ns = ctx->net;
   DIM_REQUIRE(ns != nullptr, "net not created");
   if (!strcmp(key, "pair_mask")) ns->pair_mask = value & 0x3FE;
-  else if (!strcmp(key, "conv1_roll")) ns->conv1_roll = value != 0;
-  else if (!strcmp(key, "conv1_occ2")) ns->conv1_occ2 = value != 0;
   else if (!strcmp(key, "conv1_stack")) ns->conv1_stack = value != 0;
   else { set_error("dim_debug_set_option: unknown key '%s'", key); return 2; }
   DIM_CHECK(cudaDeviceSynchronize());

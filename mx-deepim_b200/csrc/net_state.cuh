@@ -54,9 +54,7 @@ struct NetState {
   size_t conv_partial_elems = 0;
   // kernel variants; defaults = the measured-best set (tools/conv_lab.py, profiles/r02_conv_lab.json), switchable at run
   // time through dim_debug_set_option for A/B measurements
-  bool conv1_roll = true;    // conv1 on the rolling-strip kernel (conv1_roll_kernel) instead of the per-row strip kernel
-  bool conv1_stack = false;  // conv1 (single-pass precisions) on the stacked-filter-rows kernel (conv1_stack_kernel)
-  bool conv1_occ2 = false;   // rolling-strip kernel with two CTAs per SM (5-deep ring, 1 KB staging tiles)
+  bool conv1_stack = true;   // conv1 (single-pass precisions) on conv1_stack_kernel; false: conv1_roll_kernel (always used by bf16x3)
   int pair_mask = 1 << 1;    // bit i: conv layer i runs on the CTA-pair (cta_group::2) kernel; default: conv2 (N = 128)
   cudaEvent_t *layer_events = nullptr;  // tuning hook: 11 events around the conv layers of the last forward
   bool loaded = false, net_ok = false;

@@ -29,8 +29,8 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--step-batches", type=int, default=32)
     ap.add_argument("--precision", default="fp16")
-    ap.add_argument("--masks", default="0,2,1024,1026,1030,3074")
-    ap.add_argument("--full", default="0,2,1024,1026,1030,3074", help="masks that also get the multi-stream throughput pass")
+    ap.add_argument("--masks", default="2,8194,8192,0")
+    ap.add_argument("--full", default="2,8194", help="masks that also get the multi-stream throughput pass")
     args = ap.parse_args()
     import torch
     import bench
@@ -62,11 +62,10 @@ def main():
             check(lib.dim_debug_set_option(c._h, key, int(v)))
 
     def set_mask(m):
-        # mask bits 1..9: conv layer on the CTA-pair kernel; bit 10 (1024): conv1 on the rolling-strip kernel; bit 11 (2048): no CUDA graph
+        # mask bits 1..9: conv layer on the CTA-pair kernel; bit 11 (2048): no CUDA graph; bit 13 (8192): conv1 on the
+        # stacked-filter-rows kernel (else rolling strips)
         set_opt(b"pair_mask", m & 0x3FE)
-        set_opt(b"conv1_roll", (m >> 10) & 1)
-        set_opt(b"conv1_occ2", (m >> 12) & 1)
-        set_opt(b"conv1_stack", (m >> 13) & 1)  # bit 13 (8192): stacked-filter-rows conv1 kernel   # bit 12 (4096): rolling conv1 kernel with two CTAs per SM
+        set_opt(b"conv1_stack", (m >> 13) & 1)
         set_opt(b"graph", 0 if (m >> 11) & 1 else 1)
 
     def layer_times(n=7):

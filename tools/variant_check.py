@@ -43,18 +43,16 @@ def main():
                 acts = [ctx.debug_activation(i, B)[0].copy() for i in (1, 2, 3, 10)]
                 return rot.cpu().numpy(), trans.cpu().numpy(), acts
 
-            base = run({b"pair_mask": 0, b"conv1_roll": 0, b"conv1_occ2": 0, b"conv1_stack": 0})
-            for name, opts in (("conv1_roll", {b"conv1_roll": 1}), ("conv2_pair", {b"conv1_roll": 0, b"pair_mask": 2}),
-                               ("roll+conv2,3 pair", {b"conv1_roll": 1, b"pair_mask": 6}),
-                               ("roll occ2", {b"conv1_roll": 1, b"conv1_occ2": 1, b"pair_mask": 0}),
-                               ("stack", {b"conv1_roll": 1, b"conv1_occ2": 0, b"conv1_stack": 1, b"pair_mask": 0})):
+            base = run({b"pair_mask": 0, b"conv1_stack": 0})
+            for name, opts in (("conv2_pair", {b"pair_mask": 2}), ("conv2,3 pair", {b"pair_mask": 6}),
+                               ("stack", {b"conv1_stack": 1, b"pair_mask": 0}), ("stack+conv2 pair", {b"conv1_stack": 1, b"pair_mask": 2})):
                 got = run(opts)
                 ok = all(np.array_equal(a, b) for a, b in zip(base[2], got[2])) and np.array_equal(base[0], got[0]) and np.array_equal(base[1], got[1])
                 d = max(float(np.abs(a - b).max()) for a, b in zip(base[2], got[2]))
                 print("B=%d %-6s %-18s %s  max|dact|=%.3g  max|drot|=%.3g" % (B, prec_name, name, "bitwise-equal" if ok else "DIFFERENT", d,
                                                                               float(np.abs(base[0] - got[0]).max())), flush=True)
                 fails += 0 if ok else 1
-            run({b"pair_mask": 0, b"conv1_roll": 0, b"conv1_occ2": 0, b"conv1_stack": 0})
+            run({b"pair_mask": 2, b"conv1_stack": 1})
         # CUDA graph replay vs eager chain
         K, means = synth.K_LINEMOD, synth.PIXEL_MEANS_RGB
         obs, ini = synth.sample_pose_pairs(B, 5)
