@@ -351,6 +351,24 @@ DIM_API int32_t dim_train_forward_backward(
     float *flow_est, float *mask_prob, float *losses4, float *grads, float *rot_raw,
     void *const *bucket_events,
     const int32_t *bucket_first_tensor, int32_t n_buckets, void *stream);
+/* Loss weights / normalisers of the training step and the pose parameterisation shared with the refinement loop: the
+ * values the reference reads from its yaml (experiments/deepim/cfgs/...: train.LW_FLOW / LW_MASK / LW_PM, NUM_3D_SAMPLE,
+ * NORMALIZE_3D_POINT, NORMALIZE_FLOW, network.TRANS_MEANS / TRANS_STDS, ROT_COORD).  Defaults = the shipped LM6d config
+ * (0.25, 0.03, 0.1, 3000, 0.1, 20, means 0, stds 1, CAMERA).  The MakeLoss grad_scale of the point-matching loss is
+ * lw_pm / num_3d_sample whatever the number of points passed per call (deepIM_flownet.py:330-336).
+ * dim_train_set_config applies to dim_train_forward_backward of this context; trans_means / trans_stds / rot_coord also
+ * drive dim_refine / dim_refine_host (RT_transform with T_means / T_stds / rot_coord, tester.py:452-461) and may be set
+ * without dim_train_create (the other fields are then stored and used once a training state exists). */
+typedef struct dim_train_config {
+  float lw_flow, lw_mask, lw_pm;
+  float num_3d_sample;
+  float normalize_3d_point;
+  float normalize_flow;
+  float trans_means[3], trans_stds[3];
+  int32_t rot_coord; /* 0 = MODEL, 1 = CAMERA */
+} dim_train_config;
+DIM_API int32_t dim_train_set_config(dim_ctx *ctx, const dim_train_config *cfg);
+DIM_API int32_t dim_train_get_config(dim_ctx *ctx, dim_train_config *cfg);
 /* mom = momentum*mom - lr*(rescale_grad*grad + wd*w); w += mom  (wd on *_weight only; the two bilinear kernels
  * are frozen), then refreshes every bf16 operand pack of the context from the new master weights. */
 DIM_API int32_t dim_train_sgd_update(dim_ctx *ctx, const float *grads, float lr, float momentum, float wd,

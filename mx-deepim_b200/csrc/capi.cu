@@ -33,7 +33,7 @@ int zoom_factor_from_ren_launch(dim_ctx *, const int *, const float *, int B, co
 int box_mask_launch(dim_ctx *, const int *, int B, float *, cudaStream_t);
 int zoom_fused_launch(dim_ctx *, const float4 *, const float4 *, const float *, const float *, int B, int Hs, int Ws,
                       int pad, __nv_bfloat16 *, __nv_bfloat16 *, cudaStream_t, int f16, const double *means_d);
-int pack_obs4_launch(dim_ctx *, const float *, int B, float4 *, cudaStream_t);
+int pack_obs4_launch(dim_ctx *, const float *, int B, float4 *, const double *means, cudaStream_t);
 int transform_u8_obs4_launch(dim_ctx *, const uint8_t *, int B, const double *, float4 *, cudaStream_t);
 int pack_nhwc8_launch(dim_ctx *, const float *, const float *, const float *, const float *, int B, int Hs, int Ws,
                       int pad, __nv_bfloat16 *, __nv_bfloat16 *, cudaStream_t, int f16);
@@ -378,7 +378,8 @@ static int refine_core(dim_ctx *ctx, const float4 *obs4, const int32_t *cls_idx,
                        int32_t n_iter, const float *K9, float zn, float zf, const double *means, int32_t precision,
                        const double *pose_override, double *poses, float *se3, float *zoom_factor, int32_t *bbox,
                        cudaStream_t st) {
-  const double Tm[3] = {0, 0, 0}, Ts[3] = {1, 1, 1};  // trans_means / trans_stds of the shipped config
+  const double Tm[3] = {ctx->cfg.trans_means[0], ctx->cfg.trans_means[1], ctx->cfg.trans_means[2]};
+  const double Ts[3] = {ctx->cfg.trans_stds[0], ctx->cfg.trans_stds[1], ctx->cfg.trans_stds[2]};
   const float means_f[3] = {(float)means[0], (float)means[1], (float)means[2]};
   int rows, cols, pad; __nv_bfloat16 *hi, *lo;
   net_input_geometry(ctx, &rows, &cols, &pad, &hi, &lo);
@@ -417,7 +418,7 @@ static int refine_core(dim_ctx *ctx, const float4 *obs4, const int32_t *cls_idx,
     float *se3_it = se3 ? se3 + (size_t)it * B * 7 : ctx->se3_cur;
     if (int rc = net_forward(ctx, B, precision, zf_it, nullptr, nullptr, se3_it, st, ev ? ev[3] : nullptr)) return rc;
     double *pose_out = poses + (size_t)it * B * 12;
-    if (int rc = se3_compose_launch(pose_src, se3_it, B, Tm, Ts, 1 /*CAMERA*/, pose_out, nullptr, st)) return rc;
+    if (int rc = se3_compose_launch(pose_src, se3_it, B, Tm, Ts, ctx->cfg.rot_coord, pose_out, nullptr, st)) return rc;
     if (ev) DIM_CHECK(cudaEventRecord(ev[4], st));
     pose_src = pose_out;
   }
@@ -490,7 +491,7 @@ DIM_API int32_t dim_refine(dim_ctx *ctx, const float *image_observed, const int3
   DIM_REQUIRE(B >= 1 && B <= ctx->max_batch, "dim_refine: batch exceeds max_batch");
   DIM_REQUIRE(n_iter >= 1, "dim_refine: n_iter must be >= 1");
   cudaStream_t st = (cudaStream_t)stream;
-  if (int rc = pack_obs4_launch(ctx, image_observed, B, ctx->obs4, st)) return rc;
+  if (int rc = pack_obs4_launch(ctx, image_observed, B, ctx->obs4, means, st)) return rc;
   return refine_graphed(ctx, ctx->obs4, cls_idx, pose_init, B, n_iter, K9, zn, zf, means, precision, pose_override, poses,
                         se3, zoom_factor, bbox, st);
 }
@@ -690,6 +691,21 @@ DIM_API int32_t dim_train_forward_backward(dim_ctx *ctx, const float *zio, const
              rot_est_norm, trans_est, flow_est, mask_prob, losses4, grads, rot_raw, bucket_events, bucket_first_tensor,
              (bucket_events && bucket_first_tensor) ? n_buckets : 0};
   return train_forward_backward(ctx, io, (cudaStream_t)stream);
+}
+DIM_API int32_t dim_train_set_config(dim_ctx *ctx, const dim_train_config *cfg) {
+  DIM_REQUIRE(ctx && cfg, "dim_train_set_config: NULL argument");
+  DIM_REQUIRE(cfg->rot_coord == 0 || cfg->rot_coord == 1, "dim_train_set_config: rot_coord must be 0 (MODEL) or 1 (CAMERA)");
+  DIM_REQUIRE(cfg->num_3d_sample > 0.f && cfg->normalize_3d_point > 0.f && cfg->normalize_flow > 0.f,
+              "dim_train_set_config: num_3d_sample, normalize_3d_point and normalize_flow must be positive");
+  for (int i = 0; i < 3; ++i) DIM_REQUIRE(cfg->trans_stds[i] != 0.f, "dim_train_set_config: trans_stds must be non-zero");
+  ctx->cfg = *cfg;
+  drop_graphs(ctx);  // the captured refinement chains carry trans_means / trans_stds / rot_coord as kernel arguments
+  return 0;
+}
+DIM_API int32_t dim_train_get_config(dim_ctx *ctx, dim_train_config *cfg) {
+  DIM_REQUIRE(ctx && cfg, "dim_train_get_config: NULL argument");
+  *cfg = ctx->cfg;
+  return 0;
 }
 DIM_API int32_t dim_train_sgd_update(dim_ctx *ctx, const float *grads, float lr, float momentum, float wd, float rescale_grad,
                                      void *stream) {

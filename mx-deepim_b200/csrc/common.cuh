@@ -111,6 +111,8 @@ struct dim_ctx {
   };
   std::vector<RefineGraph> graphs;
   bool use_graph = true;
+  // loss weights / normalisers / pose parameterisation (dim_train_set_config); defaults = the shipped LM6d config
+  dim_train_config cfg = {0.25f, 0.03f, 0.1f, 3000.f, 0.1f, 20.f, {0.f, 0.f, 0.f}, {1.f, 1.f, 1.f}, 1};
   // stage profiling (dim_profile_enable)
   bool prof = false;
   std::vector<cudaEvent_t> prof_events;  // 5 per recorded iteration

@@ -497,15 +497,16 @@ int transform_u8_launch(dim_ctx *ctx, const uint8_t *bgr, int B, const double *m
   return 0;
 }
 
-// u8 BGR HWC -> pixel-interleaved float4 RGB-mean (w = 0): dim_refine_host's input transform
+// u8 BGR HWC -> pixel-interleaved float4 (RGB - mean) + mean (w = 0): dim_refine_host's input transform (float64 subtraction
+// cast to float32, lib/utils/image.py:583-594) followed by the zoom sampler's float32 "+ mean" (zoom_image_with_factor.py:44)
 __global__ void __launch_bounds__(256) transform_u8_obs4_kernel(const uint8_t *bgr, int P, double m0, double m1,
                                                                 double m2, float4 *out) {
   const int b = blockIdx.y;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= P) return;
   const uint8_t *px = bgr + ((size_t)b * P + q) * 3;
-  out[(size_t)b * P + q] = make_float4((float)((double)px[2] - m0), (float)((double)px[1] - m1),
-                                       (float)((double)px[0] - m2), 0.f);
+  out[(size_t)b * P + q] = make_float4((float)((double)px[2] - m0) + (float)m0, (float)((double)px[1] - m1) + (float)m1,
+                                       (float)((double)px[0] - m2) + (float)m2, 0.f);
 }
 int transform_u8_obs4_launch(dim_ctx *ctx, const uint8_t *bgr, int B, const double *means, float4 *out, cudaStream_t st) {
   const int P = ctx->H * ctx->W;

@@ -44,7 +44,8 @@ struct RasterParams {
   float bg[3];  // (float)(0.0 - mean)
   int trunc_u8;
   float *out_image, *out_depth, *out_mask, *out_bgr;
-  float4 *out_ren4;  // [B,H,W] (R-mean, G-mean, B-mean, mask): the fused loop's layout
+  float4 *out_ren4;  // [B,H,W] ((R-mean)+mean, (G-mean)+mean, (B-mean)+mean, mask): the fused loop's layout -- the "+ mean" is
+                     // the zoom sampler's first float32 step (zoom_image_with_factor.py:44), applied here once per pixel
   int ren4_box_only; // 1: out_ren4 is written only inside the projected-vertex box (vbox); every pixel outside it is background
                      //    by construction and the only consumer (zoom_fused_nhwc8_kernel) substitutes the constant itself
   // lit renderer (render_py_light_modelnet_multi.py): per-instance light position / intensity, a0 + a1 * brightness
@@ -386,7 +387,8 @@ __global__ void __launch_bounds__(256) raster_resolve_kernel(RasterParams p) {
     if (p.out_ren4 && (in_box || !p.ren4_box_only)) {
       float4 *o4 = p.out_ren4 + (size_t)b * P + o;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) o4[k] = make_float4(r[k], g[k], bl[k], mk[k]);
+      for (int k = 0; k < 4; ++k)
+        o4[k] = make_float4(r[k] + (float)p.mean[0], g[k] + (float)p.mean[1], bl[k] + (float)p.mean[2], mk[k]);
     }
     if (p.out_depth) *reinterpret_cast<float4 *>(p.out_depth + (size_t)b * P + o) = make_float4(d[0], d[1], d[2], d[3]);
     if (p.out_mask) *reinterpret_cast<float4 *>(p.out_mask + (size_t)b * P + o) = make_float4(mk[0], mk[1], mk[2], mk[3]);

@@ -1325,8 +1325,9 @@ int train_forward_backward(dim_ctx *ctx, const TrainIO &io, cudaStream_t st) {
   float *G = io.grads;
   const LayerGeom *g = ns->g;
   const int h6 = g[9].Ho, w6 = g[9].Wo, h5 = g[7].Ho, w5 = g[7].Wo, h4 = g[5].Ho, w4 = g[5].Wo;
-  const float gs_flow = 0.25f / (float)(H * W), gs_mask = 0.03f / (float)(H * W), gs_pm = 0.1f / 3000.f;
-  const float Tm[3] = {0, 0, 0}, Tsd[3] = {1, 1, 1};
+  const dim_train_config &cfg = ctx->cfg;
+  const float gs_flow = cfg.lw_flow / (float)(H * W), gs_mask = cfg.lw_mask / (float)(H * W), gs_pm = cfg.lw_pm / cfg.num_3d_sample;
+  const float *Tm = cfg.trans_means, *Tsd = cfg.trans_stds;
 
   // ---------------- forward
   DIM_CHECK(cudaEventRecord(ts->ev_phase[0], st));
@@ -1357,15 +1358,15 @@ int train_forward_backward(dim_ctx *ctx, const TrainIO &io, cudaStream_t st) {
   DIM_LAUNCH_CHECK();
   DIM_CHECK(cudaEventRecord(ts->ev_phase[2], st));
   fullres_loss_kernel<<<LOSS_BLOCKS, 256, 0, st>>>(ts->flow4, ts->mask4, h4, w4, M + ts->off[P_UPS].w, M + ts->off[P_MUPS].w, io.zflow,
-                                                   io.zfw, io.zmask_gt, B, H, W, 20.0f, gs_flow, gs_mask, io.flow_est, io.mask_prob,
+                                                   io.zfw, io.zmask_gt, B, H, W, cfg.normalize_flow, gs_flow, gs_mask, io.flow_est, io.mask_prob,
                                                    ts->dfull, ts->loss_part);
   DIM_LAUNCH_CHECK();
   pose_head_fwd_kernel<<<1, 32, 0, st>>>(ts->rot_raw, ts->ztrans, io.zoom_factor, B, ts->rot_n, ts->trans_est);
   DIM_LAUNCH_CHECK();
   const int pm_blocks = 64;
   if (io.pc_model) {
-    if (int rc = transform3d_fwd_launch(io.pc_model, ts->rot_n, ts->trans_est, io.src_pose, B, io.N, Tm, Tsd, 1, ts->pts_est, st)) return rc;
-    pm_loss_kernel<<<pm_blocks, 256, 0, st>>>(ts->pts_est, io.pc_observed, io.pc_weights, (size_t)B * 3 * io.N, 0.1f, gs_pm, ts->dpts, ts->loss_part);
+    if (int rc = transform3d_fwd_launch(io.pc_model, ts->rot_n, ts->trans_est, io.src_pose, B, io.N, Tm, Tsd, cfg.rot_coord, ts->pts_est, st)) return rc;
+    pm_loss_kernel<<<pm_blocks, 256, 0, st>>>(ts->pts_est, io.pc_observed, io.pc_weights, (size_t)B * 3 * io.N, cfg.normalize_3d_point, gs_pm, ts->dpts, ts->loss_part);
     DIM_LAUNCH_CHECK();
   }
   if (io.losses) {
@@ -1381,7 +1382,7 @@ int train_forward_backward(dim_ctx *ctx, const TrainIO &io, cudaStream_t st) {
   // ---------------- backward
   DIM_CHECK(cudaMemsetAsync(G + ts->off[P_UPS].w, 0, (ts->off[P_UPS].wn + ts->off[P_MUPS].wn) * sizeof(float), st));  // frozen (lr_mult 0)
   // pose heads
-  if (int rc = transform3d_bwd_launch(ts->dpts, io.pc_model, ts->rot_n, ts->trans_est, io.src_pose, B, io.N, Tm, Tsd, 1, ts->drot_n, ts->dtrans, st)) return rc;
+  if (int rc = transform3d_bwd_launch(ts->dpts, io.pc_model, ts->rot_n, ts->trans_est, io.src_pose, B, io.N, Tm, Tsd, cfg.rot_coord, ts->drot_n, ts->dtrans, st)) return rc;
   pose_head_bwd_kernel<<<1, 32, 0, st>>>(ts->rot_raw, ts->rot_n, ts->drot_n, B, ts->drot);
   DIM_LAUNCH_CHECK();
   fc_heads_bwd_kernel<<<B, 256, 0, st>>>(ts->drot, ts->dtrans, M + ts->off[P_ROT].w, M + ts->off[P_TRANS].w, M + ts->off[P_FC7].w, ts->h6,

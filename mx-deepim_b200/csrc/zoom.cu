@@ -293,17 +293,19 @@ int box_mask_launch(dim_ctx *ctx, const int *bbox, int B, float *mask, cudaStrea
 }
 
 // ---------------------------------------------------------------------------- fused zoom -> NHWC8
-// One thread per output pixel: samples the 6 image planes (with the +mean / -mean dance of
+// One thread per 2x2 quad of output pixels: samples the 6 image planes (with the +mean / -mean dance of
 // zoom_image_with_factor.py:44-62), the rendered mask and the analytic observed box mask with the
-// same taps, applies the graph's /255 (deepIM_flownet.py:53-60) and writes the 8-channel pixel as
-// bf16 (16 B) straight into conv1's zero-bordered, space-to-depth input buffer; `lo` (optional) receives the
+// same taps, applies the graph's /255 (deepIM_flownet.py:53-60) and writes the 8-channel pixels as
+// bf16 / fp16 (16 B each) straight into conv1's zero-bordered, space-to-depth input buffer; `lo` (optional) receives the
 // bf16 residual for the bf16x3 precision mode.
+// The two source images already hold (image + mean) -- the sampler's first step, done once by their producers with the
+// same float32 addition -- so a tap costs no arithmetic before its weight.
 struct FusedZoomParams {
-  const float4 *obs4;   // [B,H,W,4] observed RGB-mean (w unused)
-  const float4 *ren4;   // [B,H,W,4] rendered RGB-mean, w = mask_rendered (0/1)
+  const float4 *obs4;   // [B,H,W,4] observed (RGB - mean) + mean (w unused)
+  const float4 *ren4;   // [B,H,W,4] rendered (RGB - mean) + mean, w = mask_rendered (0/1)
   const int *bbox8;     // observed box = bb[0..3] (inclusive)
   const int *vbox;      // [B,4] x0,x1,y0,y1: ren4 is only valid inside this box (rasteriser), background outside; nullable
-  float bg[3];          // background of the rendered image: (float)(0.0 - mean)
+  float bg[3];          // background of the rendered image + mean: (float)(0.0 - mean) + (float)mean
   const float *zoom_factor;
   int H, W, Hs, Ws, pad;  // conv1 input is space-to-depth: [B,Hs,Ws,(ph,pw,c)=32]
   float mean[3];
@@ -311,47 +313,65 @@ struct FusedZoomParams {
   __nv_bfloat16 *hi, *lo;
 };
 
-// per-instance constants of the fused zoom, loaded once per thread (not once per output pixel)
-struct ZoomInst {
-  float zf[4];
-  int bx0, bx1, by0, by1;  // observed box (inclusive), bx1 < 0: empty
-  int vx0, vx1, vy0, vy1;  // region in which ren4 is valid (rasteriser's vertex box); background outside
+__device__ __forceinline__ uint32_t pack2_f16(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t *>(&h);
+}
+
+// One axis of the sampler (mx.sym.GridGenerator affine + BilinearSampler, same float32 sequence as src_coord): the two
+// taps c0, c0 + 1 of output coordinate `o`, their weights with zero padding folded in (an out-of-frame tap gets weight 0
+// and an arbitrary in-bounds address: it contributes exactly +0, the sampler's "value 0"), whether each tap lies in the
+// rendered image's valid box [v0, v1] and in the observed box [m0, m1].
+struct AxisTap {
+  int a0, a1;      // clamped tap coordinates (in frame)
+  float w0, w1;    // tap weights, 0 outside the frame
+  bool r0, r1;     // tap in frame and inside the rendered-valid box
+  bool m0, m1;     // tap inside the observed box (out-of-frame taps carry weight 0, so the frame test is not needed)
 };
+__device__ __forceinline__ AxisTap axis_tap(int o, float w, float t, int N, float step, int v0, int v1, int m0, int m1) {
+  const float ct = -1.0f + (float)o * step;
+  const float cs = w * ct + t;
+  const float cr = ((cs + 1.0f) * (float)(N - 1)) / 2.0f;
+  const float f0 = floorf(cr);
+  const int c0 = f0 < -4.0f ? -4 : (f0 > (float)(N + 4) ? N + 4 : (int)f0);
+  const float wa = 1.0f - (cr - f0), wb = 1.0f - wa;
+  const bool ok0 = c0 >= 0 && c0 <= N - 1, ok1 = c0 + 1 >= 0 && c0 + 1 <= N - 1;
+  AxisTap a;
+  a.a0 = ok0 ? c0 : 0;
+  a.a1 = ok1 ? c0 + 1 : 0;
+  a.w0 = ok0 ? wa : 0.f;
+  a.w1 = ok1 ? wb : 0.f;
+  a.r0 = ok0 && c0 >= v0 && c0 <= v1;
+  a.r1 = ok1 && c0 + 1 >= v0 && c0 + 1 <= v1;
+  a.m0 = c0 >= m0 && c0 <= m1;
+  a.m1 = c0 + 1 >= m0 && c0 + 1 <= m1;
+  return a;
+}
 
 template <bool LO, bool F16>
-__device__ __forceinline__ void zoom_fused_pixel(const FusedZoomParams &p, int b, int i, int j, const ZoomInst &ic,
-                                                 __nv_bfloat16 *h, __nv_bfloat16 *l) {
-  const Tap t = src_coord(i, j, ic.zf[0], ic.zf[1], ic.zf[2], ic.zf[3], p.H, p.W, p.stepx, p.stepy);
-  const bool x0ok = t.x0 >= 0 && t.x0 <= p.W - 1, x1ok = t.x0 + 1 >= 0 && t.x0 + 1 <= p.W - 1;
-  const bool y0ok = t.y0 >= 0 && t.y0 <= p.H - 1, y1ok = t.y0 + 1 >= 0 && t.y0 + 1 <= p.H - 1;
-  const bool k00 = y0ok && x0ok, k01 = y0ok && x1ok, k10 = y1ok && x0ok, k11 = y1ok && x1ok;
-  const size_t base = (size_t)b * p.H * p.W;
-  // Zero padding is folded into the tap WEIGHTS: an out-of-frame tap gets weight 0 and its (in-bounds, arbitrary) value
-  // contributes exactly +-0, the same sum as the sampler's "value 0" -- no per-channel selects, no predicated loads.
-  const long o = (long)t.y0 * p.W + t.x0;
-  const long o00 = k00 ? o : 0, o01 = k01 ? o + 1 : 0, o10 = k10 ? o + p.W : 0, o11 = k11 ? o + p.W + 1 : 0;
-  const float4 O00 = __ldg(p.obs4 + base + o00), O01 = __ldg(p.obs4 + base + o01);
-  const float4 O10 = __ldg(p.obs4 + base + o10), O11 = __ldg(p.obs4 + base + o11);
+__device__ __forceinline__ void zoom_fused_pixel(const FusedZoomParams &p, const float4 *__restrict__ ob,
+                                                 const float4 *__restrict__ rn, const AxisTap &x, const AxisTap &y,
+                                                 uint4 &h, uint4 &l) {
+  const int W = p.W;
+  const int y0 = y.a0 * W, y1 = y.a1 * W;
+  const float4 O00 = __ldg(ob + (y0 + x.a0)), O01 = __ldg(ob + (y0 + x.a1));
+  const float4 O10 = __ldg(ob + (y1 + x.a0)), O11 = __ldg(ob + (y1 + x.a1));
   // rendered taps: outside the rasteriser's vertex box the image is background by construction (and ren4 is not written there)
-  const int vx0 = ic.vx0, vx1 = ic.vx1, vy0 = ic.vy0, vy1 = ic.vy1;
   const float4 bg4 = make_float4(p.bg[0], p.bg[1], p.bg[2], 0.f);
-  const bool vxa = t.x0 >= vx0 && t.x0 <= vx1, vxb = t.x0 + 1 >= vx0 && t.x0 + 1 <= vx1;
-  const bool vya = t.y0 >= vy0 && t.y0 <= vy1, vyb = t.y0 + 1 >= vy0 && t.y0 + 1 <= vy1;
-  const float4 R00 = (k00 && vya && vxa) ? __ldg(p.ren4 + base + o) : bg4;
-  const float4 R01 = (k01 && vya && vxb) ? __ldg(p.ren4 + base + o + 1) : bg4;
-  const float4 R10 = (k10 && vyb && vxa) ? __ldg(p.ren4 + base + o + p.W) : bg4;
-  const float4 R11 = (k11 && vyb && vxb) ? __ldg(p.ren4 + base + o + p.W + 1) : bg4;
-  const float wx1 = t.wx1, wy1 = t.wy1, ax = 1.0f - wx1, ay = 1.0f - wy1;
-  const float wa = k00 ? wy1 * wx1 : 0.f, wb = k01 ? wy1 * ax : 0.f, wc = k10 ? ay * wx1 : 0.f, wd = k11 ? ay * ax : 0.f;
+  const float4 R00 = (y.r0 && x.r0) ? __ldg(rn + (y0 + x.a0)) : bg4;
+  const float4 R01 = (y.r0 && x.r1) ? __ldg(rn + (y0 + x.a1)) : bg4;
+  const float4 R10 = (y.r1 && x.r0) ? __ldg(rn + (y1 + x.a0)) : bg4;
+  const float4 R11 = (y.r1 && x.r1) ? __ldg(rn + (y1 + x.a1)) : bg4;
+  const float wa = y.w0 * x.w0, wb = y.w0 * x.w1, wc = y.w1 * x.w0, wd = y.w1 * x.w1;
   float v[8];
   // (img + mean) sampled with zero padding, then - mean, then the graph's /255.  The IEEE division is spelled out as
   // q = x * (1/255); q += (x - q * 255) * (1/255) with two fused multiply-adds: the correctly rounded quotient for every
   // |x| < 2^10 (exhaustively compared with x / 255.0f on 2e7 samples + all integer texels), at 3 instructions instead of ~10
   const float rcp255 = 1.0f / 255.0f;
   auto img = [&](float tl, float tr, float bl, float br, float m) -> float {
-    const float x = fmaf(br + m, wd, fmaf(bl + m, wc, fmaf(tr + m, wb, (tl + m) * wa))) - m;
-    const float q = x * rcp255;
-    return fmaf(fmaf(-q, 255.0f, x), rcp255, q);
+    const float s = fmaf(br, wd, fmaf(bl, wc, fmaf(tr, wb, tl * wa))) - m;
+    const float q = s * rcp255;
+    return fmaf(fmaf(-q, 255.0f, s), rcp255, q);
   };
   v[0] = img(O00.x, O01.x, O10.x, O11.x, p.mean[0]);
   v[1] = img(O00.y, O01.y, O10.y, O11.y, p.mean[1]);
@@ -359,13 +379,9 @@ __device__ __forceinline__ void zoom_fused_pixel(const FusedZoomParams &p, int b
   v[3] = img(R00.x, R01.x, R10.x, R11.x, p.mean[0]);
   v[4] = img(R00.y, R01.y, R10.y, R11.y, p.mean[1]);
   v[5] = img(R00.z, R01.z, R10.z, R11.z, p.mean[2]);
-  {  // observed mask = rectangle; bb holds its inclusive bbox (x0, x1-1, y0, y1-1); out-of-frame taps carry weight 0
-    const int bx0 = ic.bx0, bx1 = ic.bx1, by0 = ic.by0, by1 = ic.by1;
-    const bool cx0 = t.x0 >= bx0 && t.x0 <= bx1, cx1 = t.x0 + 1 >= bx0 && t.x0 + 1 <= bx1;
-    const bool cy0 = t.y0 >= by0 && t.y0 <= by1, cy1 = t.y0 + 1 >= by0 && t.y0 + 1 <= by1;
-    const bool any = bx1 >= 0;
-    const float tl = (any && cy0 && cx0) ? 1.f : 0.f, tr = (any && cy0 && cx1) ? 1.f : 0.f;
-    const float bl = (any && cy1 && cx0) ? 1.f : 0.f, br = (any && cy1 && cx1) ? 1.f : 0.f;
+  {  // observed mask = rectangle (an empty box has m0 > m1 on both axes)
+    const float tl = (y.m0 && x.m0) ? 1.f : 0.f, tr = (y.m0 && x.m1) ? 1.f : 0.f;
+    const float bl = (y.m1 && x.m0) ? 1.f : 0.f, br = (y.m1 && x.m1) ? 1.f : 0.f;
     v[6] = roundf(fmaf(br, wd, fmaf(bl, wc, fmaf(tr, wb, tl * wa))));
   }
   {  // rendered mask, binarised at 0.2 (zoom_mask.py:39-41)
@@ -373,57 +389,58 @@ __device__ __forceinline__ void zoom_fused_pixel(const FusedZoomParams &p, int b
     const float bl = R10.w > 0.2f ? 1.f : 0.f, br = R11.w > 0.2f ? 1.f : 0.f;
     v[7] = roundf(fmaf(br, wd, fmaf(bl, wc, fmaf(tr, wb, tl * wa))));
   }
+  if (F16) {  // |v| <= 1: always in range
+    h = make_uint4(pack2_f16(v[0], v[1]), pack2_f16(v[2], v[3]), pack2_f16(v[4], v[5]), pack2_f16(v[6], v[7]));
+  } else {
+    uint32_t hh[4], ll[4];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    if (F16) {
-      reinterpret_cast<__half *>(h)[c] = __float2half_rn(v[c]);  // |v| <= 1: always in range
-    } else {
-      h[c] = __float2bfloat16_rn(v[c]);
-      if (LO) l[c] = __float2bfloat16_rn(v[c] - __bfloat162float(h[c]));
+    for (int c = 0; c < 4; ++c) {
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * c]), h1 = __float2bfloat16_rn(v[2 * c + 1]);
+      hh[c] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      if (LO) {
+        const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * c] - __bfloat162float(h0));
+        const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * c + 1] - __bfloat162float(h1));
+        ll[c] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+      }
     }
+    h = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+    if (LO) l = make_uint4(ll[0], ll[1], ll[2], ll[3]);
   }
 }
 
 // one thread per space-to-depth pixel = a 2x2 quad of output pixels = the four 16-byte channel chunks
 // of conv1's strip layout (consecutive threads write consecutive 16 B of each chunk plane); border
-// slots are rewritten with zeros.  Sources are the
-// pixel-interleaved float4 images, so each tap is one 16-byte load per image.
+// slots are rewritten with zeros.  Sources are the pixel-interleaved float4 images, so each tap is one 16-byte load
+// per image; the column taps of the quad's two columns and the row taps of its two rows are computed once each.
 template <bool LO, bool F16>
-__global__ void __launch_bounds__(128) zoom_fused_nhwc8_kernel(FusedZoomParams p) {
+__global__ void __launch_bounds__(128, 8) zoom_fused_nhwc8_kernel(FusedZoomParams p) {
   const int b = blockIdx.y;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= p.Hs * p.Ws) return;
   const int sr = q / p.Ws, sc = q - sr * p.Ws;
-  ZoomInst ic;
-  {
-    const float4 z = __ldg(reinterpret_cast<const float4 *>(p.zoom_factor) + b);
-    ic.zf[0] = z.x; ic.zf[1] = z.y; ic.zf[2] = z.z; ic.zf[3] = z.w;
-    const int4 bb = __ldg(reinterpret_cast<const int4 *>(p.bbox8) + 2 * b);
-    ic.bx0 = bb.x; ic.bx1 = bb.y; ic.by0 = bb.z; ic.by1 = bb.w;
-    ic.vx0 = 0; ic.vx1 = p.W; ic.vy0 = 0; ic.vy1 = p.H;
-    if (p.vbox) {
-      const int4 vb = __ldg(reinterpret_cast<const int4 *>(p.vbox) + b);
-      ic.vx0 = vb.x; ic.vx1 = vb.y; ic.vy0 = vb.z; ic.vy1 = vb.w;
-    }
-  }
-  __align__(16) __nv_bfloat16 h[4][8];
-  __align__(16) __nv_bfloat16 l[4][8];
+  const float4 z = __ldg(reinterpret_cast<const float4 *>(p.zoom_factor) + b);
+  int4 bb = __ldg(reinterpret_cast<const int4 *>(p.bbox8) + 2 * b);  // observed box (inclusive); bb.y < 0: empty
+  if (bb.y < 0) { bb.x = 1; bb.y = 0; bb.z = 1; bb.w = 0; }
+  int4 vb = make_int4(0, p.W, 0, p.H);
+  if (p.vbox) vb = __ldg(reinterpret_cast<const int4 *>(p.vbox) + b);
+  const int i0 = 2 * sr - p.pad, j0 = 2 * sc - p.pad;
+  AxisTap xt[2], yt[2];
 #pragma unroll
-  for (int s = 0; s < 4; ++s) {
-    const int i = 2 * sr + (s >> 1) - p.pad, j = 2 * sc + (s & 1) - p.pad;
-    if (i >= 0 && i < p.H && j >= 0 && j < p.W) {
-      zoom_fused_pixel<LO, F16>(p, b, i, j, ic, h[s], l[s]);
-    } else {
-#pragma unroll
-      for (int c = 0; c < 8; ++c) { h[s][c] = __float2bfloat16_rn(0.f); l[s][c] = __float2bfloat16_rn(0.f); }
-    }
+  for (int k = 0; k < 2; ++k) {
+    xt[k] = axis_tap(j0 + k, z.x, z.z, p.W, p.stepx, vb.x, vb.y, bb.x, bb.y);
+    yt[k] = axis_tap(i0 + k, z.y, z.w, p.H, p.stepy, vb.z, vb.w, bb.z, bb.w);
   }
+  const size_t base = (size_t)b * p.H * p.W;
+  const float4 *ob = p.obs4 + base, *rn = p.ren4 + base;
   // conv1 strip layout: [B*Hs rows][4 chunks (= quad slot)][Ws cols][8 ch]
 #pragma unroll
   for (int s = 0; s < 4; ++s) {
+    const int i = i0 + (s >> 1), j = j0 + (s & 1);
+    uint4 h = make_uint4(0u, 0u, 0u, 0u), l = make_uint4(0u, 0u, 0u, 0u);  // zero bits are the same in both formats
+    if (i >= 0 && i < p.H && j >= 0 && j < p.W) zoom_fused_pixel<LO, F16>(p, ob, rn, xt[s & 1], yt[s >> 1], h, l);
     const size_t o = ((((size_t)b * p.Hs + sr) * 4 + s) * p.Ws + sc) * 8;
-    *reinterpret_cast<uint4 *>(p.hi + o) = *reinterpret_cast<const uint4 *>(h[s]);
-    if (LO) *reinterpret_cast<uint4 *>(p.lo + o) = *reinterpret_cast<const uint4 *>(l[s]);
+    *reinterpret_cast<uint4 *>(p.hi + o) = h;
+    if (LO) *reinterpret_cast<uint4 *>(p.lo + o) = l;
   }
 }
 
@@ -434,7 +451,7 @@ int zoom_fused_launch(dim_ctx *ctx, const float4 *obs4, const float4 *ren4, cons
   p.obs4 = obs4; p.ren4 = ren4;
   p.bbox8 = ctx->bbox8; p.zoom_factor = zoom_factor;
   p.vbox = means_d ? ctx->vbox : nullptr;  // means_d given: ren4 comes from the fused loop's box-only render
-  for (int c = 0; c < 3; ++c) p.bg[c] = means_d ? (float)(0.0 - means_d[c]) : 0.f;
+  for (int c = 0; c < 3; ++c) p.bg[c] = (means_d ? (float)(0.0 - means_d[c]) : 0.f) + means_rgb[c];
   p.H = ctx->H; p.W = ctx->W; p.Hs = Hs; p.Ws = Ws; p.pad = pad;
   for (int c = 0; c < 3; ++c) p.mean[c] = means_rgb[c];
   p.stepx = (float)(2.0 / (double)(ctx->W - 1));
@@ -448,17 +465,18 @@ int zoom_fused_launch(dim_ctx *ctx, const float4 *obs4, const float4 *ren4, cons
   return 0;
 }
 
-// NCHW f32 (3 planes) -> pixel-interleaved float4 (x,y,z = planes, w = 0): once per dim_refine call
-__global__ void __launch_bounds__(256) pack_obs4_kernel(const float *img, int P, float4 *out) {
+// NCHW f32 (3 planes, image - mean) -> pixel-interleaved float4 (x,y,z = plane + mean: the sampler's first step, w = 0):
+// once per dim_refine call
+__global__ void __launch_bounds__(256) pack_obs4_kernel(const float *img, int P, float4 *out, float m0, float m1, float m2) {
   const int b = blockIdx.y;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= P) return;
   const float *s = img + (size_t)b * 3 * P;
-  out[(size_t)b * P + q] = make_float4(s[q], s[P + q], s[2 * (size_t)P + q], 0.f);
+  out[(size_t)b * P + q] = make_float4(s[q] + m0, s[P + q] + m1, s[2 * (size_t)P + q] + m2, 0.f);
 }
-int pack_obs4_launch(dim_ctx *ctx, const float *img, int B, float4 *out, cudaStream_t st) {
+int pack_obs4_launch(dim_ctx *ctx, const float *img, int B, float4 *out, const double *means, cudaStream_t st) {
   const int P = ctx->H * ctx->W;
-  pack_obs4_kernel<<<dim3(cdiv(P, 256), B), 256, 0, st>>>(img, P, out);
+  pack_obs4_kernel<<<dim3(cdiv(P, 256), B), 256, 0, st>>>(img, P, out, (float)means[0], (float)means[1], (float)means[2]);
   DIM_LAUNCH_CHECK();
   return 0;
 }

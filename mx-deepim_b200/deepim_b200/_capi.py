@@ -19,6 +19,12 @@ vp, i32, i64, u64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float
 pf32 = C.POINTER(C.c_float)
 pf64 = C.POINTER(C.c_double)
 
+class TrainConfig(C.Structure):
+    """dim_train_config (include/deepim_b200.h): loss weights / normalisers / pose parameterisation of the yaml"""
+    _fields_ = [("lw_flow", f32), ("lw_mask", f32), ("lw_pm", f32), ("num_3d_sample", f32), ("normalize_3d_point", f32),
+                ("normalize_flow", f32), ("trans_means", f32 * 3), ("trans_stds", f32 * 3), ("rot_coord", i32)]
+
+
 # name -> (restype, argtypes); every symbol declared in include/deepim_b200.h
 SIGNATURES = {
     "dim_abi_version": (i32, []),
@@ -68,6 +74,8 @@ SIGNATURES = {
     "dim_train_load_params": (i32, [vp, vp, i64, vp]),
     "dim_train_get_params": (i32, [vp, vp, i64, i32, vp]),
     "dim_train_forward_backward": (i32, [vp] + [vp] * 12 + [i32, i32] + [vp] * 7 + [vp, vp, i32] + [vp]),
+    "dim_train_set_config": (i32, [vp, C.POINTER(TrainConfig)]),
+    "dim_train_get_config": (i32, [vp, C.POINTER(TrainConfig)]),
     "dim_train_sgd_update": (i32, [vp, vp, f32, f32, f32, f32, vp]),
     "dim_train_debug_tensor": (i32, [vp, i32, vp, C.c_uint64]),
     "dim_train_debug_phases": (i32, [vp, pf32]),

@@ -337,6 +337,31 @@ class Context:
         return f.reshape(B, rows, cols, ch), tuple(g)
 
     # ------------------------------------------------------------------------------ refine
+    def get_config(self) -> dict:
+        """dim_train_get_config: loss weights / normalisers / pose parameterisation in effect on this context"""
+        cfg = capi.TrainConfig()
+        check(lib.dim_train_get_config(self._h, C.byref(cfg)))
+        return {"lw_flow": cfg.lw_flow, "lw_mask": cfg.lw_mask, "lw_pm": cfg.lw_pm, "num_3d_sample": cfg.num_3d_sample,
+                "normalize_3d_point": cfg.normalize_3d_point, "normalize_flow": cfg.normalize_flow,
+                "trans_means": list(cfg.trans_means), "trans_stds": list(cfg.trans_stds),
+                "rot_coord": "CAMERA" if cfg.rot_coord == 1 else "MODEL"}
+
+    def set_config(self, **fields):
+        """dim_train_set_config: override some of the yaml-level constants (see get_config for the names).  trans_means /
+        trans_stds / rot_coord also drive refine(); the rest applies to the training step."""
+        cfg = capi.TrainConfig()
+        check(lib.dim_train_get_config(self._h, C.byref(cfg)))
+        for k, v in fields.items():
+            if k in ("trans_means", "trans_stds"):
+                setattr(cfg, k, (C.c_float * 3)(*[float(x) for x in v]))
+            elif k == "rot_coord":
+                cfg.rot_coord = capi.ROT_COORD[v.lower()] if isinstance(v, str) else int(v)
+            elif hasattr(cfg, k):
+                setattr(cfg, k, float(v))
+            else:
+                raise ValueError("unknown config field %r" % k)
+        check(lib.dim_train_set_config(self._h, C.byref(cfg)))
+
     def refine(self, image_observed, cls_idx, pose_init, K, n_iter=4, znear=0.25, zfar=6.0,
                pixel_means_rgb=(103.939, 116.779, 123.68), precision=capi.PREC_FP16, pose_override=None, out=None):
         """Device-resident fused loop.  image_observed f32[B,3,H,W], cls_idx i32[B], pose_init f64[B,3,4].

@@ -92,9 +92,14 @@ def _p(t):
 
 
 class Trainer:
-    def __init__(self, ctx, weights: dict, max_points=3000, lr=1e-4, momentum=0.975, wd=5e-4, bucket_mb=32.0):
+    def __init__(self, ctx, weights: dict, max_points=3000, lr=1e-4, momentum=0.975, wd=5e-4, bucket_mb=32.0, config=None):
+        """config: optional dict overriding fields of dim_train_config (lw_flow, lw_mask, lw_pm, num_3d_sample,
+        normalize_3d_point, normalize_flow, trans_means, trans_stds, rot_coord = 'MODEL' | 'CAMERA'): the yaml's train.LW_* /
+        NUM_3D_SAMPLE / NORMALIZE_* / network.TRANS_MEANS / TRANS_STDS / ROT_COORD.  Default: the shipped LM6d values."""
         self.ctx, self.lr, self.momentum, self.wd = ctx, lr, momentum, wd
         check(lib.dim_train_create(ctx._h, max_points))
+        if config:
+            ctx.set_config(**config)
         self.n = int(lib.dim_train_param_count(ctx._h))
         self.table = param_table()
         flat = flatten_params(weights)

@@ -109,6 +109,40 @@ def test_training_step_matches_oracle(setup):
         assert max(np.abs(buf[:, 0]).max(), np.abs(buf[:, -1]).max(), np.abs(buf[:, :, 0]).max(), np.abs(buf[:, :, -1]).max()) == 0.0
 
 
+def test_loss_weights_follow_the_config(setup, monkeypatch):
+    """dim_train_set_config (the yaml's LW_FLOW / LW_MASK / LW_PM / NUM_3D_SAMPLE): objective and gradients follow the
+    configured loss weights instead of the compiled-in LM6d defaults; bad values are rejected."""
+    B, meshes, w, batch, ctx, tr = setup
+    cfg0 = ctx.get_config()
+    assert cfg0["lw_flow"] == 0.25 and abs(cfg0["lw_pm"] - 0.1) < 1e-8 and cfg0["num_3d_sample"] == 3000.0 and cfg0["rot_coord"] == "CAMERA"
+    with pytest.raises(Exception):
+        ctx.set_config(num_3d_sample=0.0)
+    with pytest.raises(Exception):
+        ctx.set_config(rot_coord=3)
+    new = dict(lw_flow=0.6, lw_mask=0.01, lw_pm=0.3, num_3d_sample=1000.0)
+    monkeypatch.setattr(T, "LW_FLOW", 0.6)
+    monkeypatch.setattr(T, "LW_MASK", 0.01)
+    monkeypatch.setattr(T, "LW_PM", 0.3)
+    monkeypatch.setattr(T, "NUM_3D_SAMPLE", 1000)
+    out, g, zin, lab = T.forward_backward(w, batch, K, MEANS)
+    b = {k: dev(v) for k, v in batch.items()}
+    b["pixel_means_rgb"] = MEANS.astype(np.float32)
+    z = tr.zoom_front(b, K)
+    try:
+        ctx.set_config(**new)
+        res = tr.forward_backward(z)
+        torch.cuda.synchronize()
+        losses = res["losses"].cpu().numpy()
+        assert abs(losses[3] - out["objective"]) < 2e-3 * out["objective"]
+        gd = tr.grads_dict()
+        for k in ("fc7_weight", "conv6_1_weight", "flow_conv1_weight", "Convolution3_weight", "mask_conv3_weight"):
+            c = G.cmp(gd[k], g[k])
+            assert c["cos"] > 0.995 and c["rel"] < 0.15, (k, c)
+    finally:
+        ctx.set_config(**{k: cfg0[k] for k in new})
+    assert ctx.get_config() == cfg0
+
+
 def test_sgd_update_and_repack(setup):
     """mom = m*mom - lr*(g + wd*w), w += mom on the flat vector (wd on weights only, bilinear kernels frozen);
     the bf16 operand packs follow the master weights: the next forward pass uses the updated network."""
