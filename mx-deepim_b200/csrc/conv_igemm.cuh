@@ -978,15 +978,20 @@ __global__ void __launch_bounds__(320) conv1_stack_kernel(const __grid_constant_
           const int n1 = b0 <= 4 ? 4 : 8 - b0;          // blocks before the window wraps past column 512
           const uint32_t d1 = tmem_base + (uint32_t)b0 * 64u, id1 = idesc0 | ((uint32_t)(n1 * 64 >> 3) << 17);
           const uint32_t id2 = idesc0 | ((uint32_t)((4 - n1) * 64 >> 3) << 17);
+          // K half k = 1 holds the odd input rows (ph = 1): filter row 2 * 3 + 1 = 7 does not exist, W_dh3 is zero there, so
+          // those steps skip the window's first block: rows s+1 .. s+3 <- [W_dh2; W_dh1; W_dh0] (N = 192)
+          const int c0 = (b0 + 1) & 7;
+          const int m1 = c0 <= 5 ? 3 : 8 - c0;
+          const uint32_t e1 = tmem_base + (uint32_t)c0 * 64u, ie1 = idesc0 | ((uint32_t)(m1 * 64 >> 3) << 17);
+          const uint32_t ie2 = idesc0 | ((uint32_t)((3 - m1) * 64 >> 3) << 17);
 #pragma unroll
           for (int dw = 0; dw < 4; ++dw) {
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              const uint64_t da = da0 + (uint64_t)dw + (uint64_t)k * kstep;
-              const uint64_t db = dres + (uint64_t)(dw * (DW_BYTES >> 4) + 2 * k);
-              ptx::umma_f16_raw(d1, da, db, id1, 1u);
-              if (n1 < 4) ptx::umma_f16_raw(tmem_base, da, db + (uint64_t)(n1 * (B_BYTES >> 4)), id2, 1u);
-            }
+            const uint64_t da = da0 + (uint64_t)dw;
+            const uint64_t db = dres + (uint64_t)(dw * (DW_BYTES >> 4));
+            ptx::umma_f16_raw(d1, da, db, id1, 1u);
+            if (n1 < 4) ptx::umma_f16_raw(tmem_base, da, db + (uint64_t)(n1 * (B_BYTES >> 4)), id2, 1u);
+            ptx::umma_f16_raw(e1, da + kstep, db + (uint64_t)(2 + (B_BYTES >> 4)), ie1, 1u);
+            if (m1 < 3) ptx::umma_f16_raw(tmem_base, da + kstep, db + (uint64_t)(2 + (1 + m1) * (B_BYTES >> 4)), ie2, 1u);
           }
           ptx::umma_commit_raw(&empty_bar[slot]);        // the strip is consumed
           ptx::umma_commit_raw(&acc_full_bar[s & 7]);    // row v = s has all four contributions
