@@ -781,6 +781,10 @@ __global__ void __launch_bounds__(320) conv1_roll_kernel(const __grid_constant__
       // between two MMA groups is exposed latency (measured: 2.5k cycles per tile for 0.9k cycles of MMAs).
       const uint64_t dring = umma_desc_interleave(ptx::smem_u32(ring), LBO, 128);
       const uint64_t dring_lo = umma_desc_interleave(ptx::smem_u32(ring) + (uint32_t)strip_bytes, LBO, 128);
+      // dw = 3 (kw = 6, 7): the odd input column (pw = 1) is outside the 7x7 filter, so its K step pairs the two pw = 0
+      // chunks (0 and 2: chunk stride 2 LBO) against weights packed in that order (conv1_kslot) and the other step is dropped
+      const uint64_t dring3 = umma_desc_interleave(ptx::smem_u32(ring), 2u * LBO, 128);
+      const uint64_t dring3_lo = umma_desc_interleave(ptx::smem_u32(ring) + (uint32_t)strip_bytes, 2u * LBO, 128);
       const uint64_t slot_step = (uint64_t)((uint32_t)stage_bytes >> 4);
       const uint64_t kstep = (uint64_t)(2u * LBO >> 4);
       uint64_t dbh[4], dbl[4];
@@ -805,17 +809,18 @@ __global__ void __launch_bounds__(320) conv1_roll_kernel(const __grid_constant__
           }
           if (ptx::elect_one()) {
             const uint64_t da0 = dring + (uint64_t)slot * slot_step, dal0 = dring_lo + (uint64_t)slot * slot_step;
+            const uint64_t da3 = dring3 + (uint64_t)slot * slot_step + 3u, dal3 = dring3_lo + (uint64_t)slot * slot_step + 3u;
 #pragma unroll
             for (int dw = 0; dw < 4; ++dw) {
 #pragma unroll
               for (int k = 0; k < 2; ++k) {
-                if (dh == 3 && k == 1) continue;  // kh = 7: outside the 7x7 filter, all-zero weights
+                if ((dh == 3 || dw == 3) && k == 1) continue;  // kh = 7 / kw = 7: outside the 7x7 filter, all-zero weights
                 const uint32_t acc = (dh | dw | k) ? 1u : 0u;
-                const uint64_t da = da0 + (uint64_t)dw + (uint64_t)k * kstep;
+                const uint64_t da = dw == 3 ? da3 : da0 + (uint64_t)dw + (uint64_t)k * kstep;
                 const uint64_t db = dbh[dh] + (uint64_t)(dw * (B_BYTES >> 4) + 2 * k);
                 ptx::umma_f16_raw(tmem_acc, da, db, p.idesc, acc);
                 if (SPLIT3) {
-                  ptx::umma_f16_raw(tmem_acc, dal0 + (uint64_t)dw + (uint64_t)k * kstep, db, p.idesc, 1u);
+                  ptx::umma_f16_raw(tmem_acc, dw == 3 ? dal3 : dal0 + (uint64_t)dw + (uint64_t)k * kstep, db, p.idesc, 1u);
                   ptx::umma_f16_raw(tmem_acc, da, dbl[dh] + (uint64_t)(dw * (B_BYTES >> 4) + 2 * k), p.idesc, 1u);
                 }
               }
@@ -962,6 +967,7 @@ __global__ void __launch_bounds__(320) conv1_stack_kernel(const __grid_constant_
       ptx::mbar_wait(res_bar, 0);
       ptx::tc_fence_after();
       const uint64_t dring = umma_desc_interleave(ptx::smem_u32(ring), LBO, 128);
+      const uint64_t dring3 = umma_desc_interleave(ptx::smem_u32(ring), 2u * LBO, 128);  // dw = 3: chunks 0 and 2 (see conv1_roll_kernel)
       const uint64_t slot_step = (uint64_t)((uint32_t)strip_bytes >> 4);
       const uint64_t kstep = (uint64_t)(2u * LBO >> 4);
       const uint64_t dres = ptx::umma_desc(ptx::smem_u32(res), 512, 4u);
@@ -986,10 +992,11 @@ __global__ void __launch_bounds__(320) conv1_stack_kernel(const __grid_constant_
           const uint32_t ie2 = idesc0 | ((uint32_t)((3 - m1) * 64 >> 3) << 17);
 #pragma unroll
           for (int dw = 0; dw < 4; ++dw) {
-            const uint64_t da = da0 + (uint64_t)dw;
+            const uint64_t da = dw == 3 ? dring3 + (uint64_t)slot * slot_step + 3u : da0 + (uint64_t)dw;
             const uint64_t db = dres + (uint64_t)(dw * (DW_BYTES >> 4));
             ptx::umma_f16_raw(d1, da, db, id1, 1u);
             if (n1 < 4) ptx::umma_f16_raw(tmem_base, da, db + (uint64_t)(n1 * (B_BYTES >> 4)), id2, 1u);
+            if (dw == 3) continue;  // kw = 7 does not exist: the (chunk 1, chunk 3) step of dw = 3 has all-zero weights
             ptx::umma_f16_raw(e1, da + kstep, db + (uint64_t)(2 + (B_BYTES >> 4)), ie1, 1u);
             if (m1 < 3) ptx::umma_f16_raw(tmem_base, da + kstep, db + (uint64_t)(2 + (1 + m1) * (B_BYTES >> 4)), ie2, 1u);
           }

@@ -468,7 +468,7 @@ int net_load(dim_ctx *ctx, const float *const *W, const float *const *Bv) {
     std::vector<float> packed((size_t)g.Cout * Ktot, 0.f);
     const float *w = W[i];  // [Cout][Cin][k][k]
     if (i == 0) {
-      // space-to-depth repack: W'[co][dh][dw][ph*16+pw*8+c] = W[co][c][2dh+ph][2dw+pw] (0 beyond 7x7)
+      // space-to-depth repack: W'[co][dh][dw][conv1_kslot(dw,ph,pw)+c] = W[co][c][2dh+ph][2dw+pw] (0 beyond 7x7)
       for (int co = 0; co < g.Cout; ++co)
         for (int dh = 0; dh < 4; ++dh)
           for (int dw = 0; dw < 4; ++dw)
@@ -477,7 +477,7 @@ int net_load(dim_ctx *ctx, const float *const *W, const float *const *Bv) {
                 for (int c = 0; c < 8; ++c) {
                   const int kh = 2 * dh + ph, kw = 2 * dw + pw;
                   if (kh >= 7 || kw >= 7) continue;
-                  packed[(size_t)co * Ktot + (size_t)(dh * 4 + dw) * 32 + ph * 16 + pw * 8 + c] =
+                  packed[(size_t)co * Ktot + (size_t)(dh * 4 + dw) * 32 + conv1_kslot(dw, ph, pw) + c] =
                       w[(((size_t)co * 8 + c) * 7 + kh) * 7 + kw];
                 }
     } else {

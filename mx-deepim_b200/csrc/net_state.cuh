@@ -35,6 +35,11 @@ struct TensorMaps {
   LayerGeom g[10];  // per-batch-size effective geometry (tile width may depend on the batch)
 };
 
+// conv1 operand K order inside one (dh, dw) tap of the space-to-depth form: the four 8-channel chunks (ph, pw) sit at
+// ph*16 + pw*8 -- the order of the input strip's chunk planes -- except for dw = 3, where the two pw = 0 chunks come first
+// (the pw = 1 half is kw = 7, outside the filter): the kernels feed that K step from chunk planes 0 and 2 and drop the other.
+__host__ __device__ inline int conv1_kslot(int dw, int ph, int pw) { return dw == 3 ? pw * 16 + ph * 8 : ph * 16 + pw * 8; }
+
 struct NetState {
   LayerGeom g[10];
   __nv_bfloat16 *w_hi[10] = {}, *w_lo[10] = {};

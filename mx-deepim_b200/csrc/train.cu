@@ -638,7 +638,7 @@ __global__ void __launch_bounds__(256) pack_conv1_kernel(const float *w, __nv_bf
   if (i >= 64 * 512) return;
   const int c = i & 7, pw = (i >> 3) & 1, ph = (i >> 4) & 1, dw = (i >> 5) & 3, dh = (i >> 7) & 3, co = i >> 9;
   const int kh = 2 * dh + ph, kw = 2 * dw + pw;
-  store_split(hi, lo, i, (kh < 7 && kw < 7) ? w[((co * 8 + c) * 7 + kh) * 7 + kw] : 0.f);
+  store_split(hi, lo, (i & ~31) + conv1_kslot(dw, ph, pw) + c, (kh < 7 && kw < 7) ? w[((co * 8 + c) * 7 + kh) * 7 + kw] : 0.f);
 }
 // data-gradient packs of ALL parity classes of one layer: class (ry, rx) is [Cin][Ty][Tx][Cout] with ky = ry + s*(Ty-1-ty).
 // block = (ci, 64 output channels): reads 64 rows of k*k floats, writes 64 consecutive bf16 per (class, tap)
