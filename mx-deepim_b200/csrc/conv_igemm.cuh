@@ -321,16 +321,17 @@ __device__ __forceinline__ void epilogue_store64(const uint32_t *r, const float 
 // LINEAR: the 32 rows of the warp are consecutive pixels of one output row (conv1): row r lives at my_off(row 0) + r * row_stride
 // elements and rows [0, n_valid) are valid -- no per-row offset shuffle, no ballot (my_off / my_valid are then warp-uniform:
 // offset of the warp's row 0 and unused).
-template <bool SPLIT3, bool LINEAR = false>
+// BIAS_REG: bias_s points at 32 floats the caller keeps in registers (a fully unrolled local array) instead of shared memory.
+template <bool SPLIT3, bool LINEAR = false, bool BIAS_REG = false>
 __device__ __forceinline__ void epilogue_store32(const uint32_t *r, const float *bias_s, float slope, uint8_t *stage,
                                                  __nv_bfloat16 *out_hi, __nv_bfloat16 *out_lo, long long my_off,
                                                  bool my_valid, int lane, bool f16, int n_valid = 32, int row_stride = 0) {
   __align__(16) uint32_t h[16];
   __align__(16) uint32_t l[SPLIT3 ? 16 : 4];
-  const uint32_t ba = ptx::smem_u32(bias_s), sa = ptx::smem_u32(stage);
+  const uint32_t ba = BIAS_REG ? 0u : ptx::smem_u32(bias_s), sa = ptx::smem_u32(stage);
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
-    const float4 b4 = lds128f(ba + j * 4);
+    const float4 b4 = BIAS_REG ? make_float4(bias_s[j], bias_s[j + 1], bias_s[j + 2], bias_s[j + 3]) : lds128f(ba + j * 4);
     float v0 = __uint_as_float(r[j]) + b4.x, v1 = __uint_as_float(r[j + 1]) + b4.y;
     float v2 = __uint_as_float(r[j + 2]) + b4.z, v3 = __uint_as_float(r[j + 3]) + b4.w;
     v0 = v0 > 0.f ? v0 : v0 * slope;
@@ -811,9 +812,9 @@ __global__ void __launch_bounds__(320) conv1_roll_kernel(const __grid_constant__
             const uint64_t da0 = dring + (uint64_t)slot * slot_step, dal0 = dring_lo + (uint64_t)slot * slot_step;
             const uint64_t da3 = dring3 + (uint64_t)slot * slot_step + 3u, dal3 = dring3_lo + (uint64_t)slot * slot_step + 3u;
 #pragma unroll
-            for (int dw = 0; dw < 4; ++dw) {
+            for (int k = 0; k < 2; ++k) {  // k-major like conv1_stack_kernel: same accumulation order, bitwise-equal results
 #pragma unroll
-              for (int k = 0; k < 2; ++k) {
+              for (int dw = 0; dw < 4; ++dw) {
                 if ((dh == 3 || dw == 3) && k == 1) continue;  // kh = 7 / kw = 7: outside the 7x7 filter, all-zero weights
                 const uint32_t acc = (dh | dw | k) ? 1u : 0u;
                 const uint64_t da = dw == 3 ? da3 : da0 + (uint64_t)dw + (uint64_t)k * kstep;
@@ -990,15 +991,27 @@ __global__ void __launch_bounds__(320) conv1_stack_kernel(const __grid_constant_
           const int m1 = c0 <= 5 ? 3 : 8 - c0;
           const uint32_t e1 = tmem_base + (uint32_t)c0 * 64u, ie1 = idesc0 | ((uint32_t)(m1 * 64 >> 3) << 17);
           const uint32_t ie2 = idesc0 | ((uint32_t)((3 - m1) * 64 >> 3) << 17);
+          // MMAs that share an instruction descriptor and an accumulator window are issued back to back (k-major order):
+          // alternating N = 256 / 192 / split shapes from one MMA to the next cost the tensor pipe a drain each time
+          uint64_t da[4], db[4];
 #pragma unroll
           for (int dw = 0; dw < 4; ++dw) {
-            const uint64_t da = dw == 3 ? dring3 + (uint64_t)slot * slot_step + 3u : da0 + (uint64_t)dw;
-            const uint64_t db = dres + (uint64_t)(dw * (DW_BYTES >> 4));
-            ptx::umma_f16_raw(d1, da, db, id1, 1u);
-            if (n1 < 4) ptx::umma_f16_raw(tmem_base, da, db + (uint64_t)(n1 * (B_BYTES >> 4)), id2, 1u);
-            if (dw == 3) continue;  // kw = 7 does not exist: the (chunk 1, chunk 3) step of dw = 3 has all-zero weights
-            ptx::umma_f16_raw(e1, da + kstep, db + (uint64_t)(2 + (B_BYTES >> 4)), ie1, 1u);
-            if (m1 < 3) ptx::umma_f16_raw(tmem_base, da + kstep, db + (uint64_t)(2 + (1 + m1) * (B_BYTES >> 4)), ie2, 1u);
+            da[dw] = dw == 3 ? dring3 + (uint64_t)slot * slot_step + 3u : da0 + (uint64_t)dw;
+            db[dw] = dres + (uint64_t)(dw * (DW_BYTES >> 4));
+          }
+#pragma unroll
+          for (int dw = 0; dw < 4; ++dw) ptx::umma_f16_raw(d1, da[dw], db[dw], id1, 1u);
+          if (n1 < 4) {
+#pragma unroll
+            for (int dw = 0; dw < 4; ++dw) ptx::umma_f16_raw(tmem_base, da[dw], db[dw] + (uint64_t)(n1 * (B_BYTES >> 4)), id2, 1u);
+          }
+          // K half 1; dw = 3 has none (kw = 7 does not exist: its (chunk 1, chunk 3) step has all-zero weights)
+#pragma unroll
+          for (int dw = 0; dw < 3; ++dw) ptx::umma_f16_raw(e1, da[dw] + kstep, db[dw] + (uint64_t)(2 + (B_BYTES >> 4)), ie1, 1u);
+          if (m1 < 3) {
+#pragma unroll
+            for (int dw = 0; dw < 3; ++dw)
+              ptx::umma_f16_raw(tmem_base, da[dw] + kstep, db[dw] + (uint64_t)(2 + (1 + m1) * (B_BYTES >> 4)), ie2, 1u);
           }
           ptx::umma_commit_raw(&empty_bar[slot]);        // the strip is consumed
           ptx::umma_commit_raw(&acc_full_bar[s & 7]);    // row v = s has all four contributions
@@ -1010,6 +1023,9 @@ __global__ void __launch_bounds__(320) conv1_stack_kernel(const __grid_constant_
     const int quad = warp & 3, set = (warp - 2) >> 2;  // two warp sets alternate rows (see conv1_roll_kernel)
     uint8_t *stg = epi + (warp - 2) * 2048;
     const int n_cols_valid = min(p.BW, p.Wo - ow0) - quad * 32;
+    float breg[64];  // the 64 biases live in registers: the shared-memory pipe belongs to the tensor core's operand reads
+#pragma unroll
+    for (int j = 0; j < 64; ++j) breg[j] = bias_s[j];
     for (int v = set; v < n_strips; v += 2) {  // one completed row per strip; rows v < 3 belong to the previous chunk: discarded
       const int g = g_lo + v - 3;
       const bool mine = v >= 3;  // v - 3 < n_rows holds by construction
@@ -1034,8 +1050,8 @@ __global__ void __launch_bounds__(320) conv1_stack_kernel(const __grid_constant_
             (((long long)n_img * p.out_Hp + oh + p.out_py) * p.out_Wp + (ow0 + quad * 32) + p.out_px) * 64;
 #pragma unroll
         for (int half = 0; half < 2; ++half)
-          epilogue_store32<false, true>(r + half * 32, bias_s + half * 32, p.slope, stg, p.out_hi, p.out_lo, warp_off + half * 32, true,
-                                        lane, p.f16 != 0, n_cols_valid, 64);
+          epilogue_store32<false, true, true>(r + half * 32, breg + half * 32, p.slope, stg, p.out_hi, p.out_lo, warp_off + half * 32,
+                                              true, lane, p.f16 != 0, n_cols_valid, 64);
       }
     }
   }

@@ -1,7 +1,7 @@
 """End-to-end parity report on a larger sample (config C3-like: 13 meshes, 64 instances, 4 iterations).
 
-    gpurun:  python tools/parity_report.py gpu      -> gpurun_out/parity_gpu.npz   (both precision modes)
-    here:    python tools/parity_report.py compare  -> profiles/r01_parity_report.json (oracle runs on CPU)
+    gpurun:  python tools/parity_report.py gpu      -> gpurun_out/parity_gpu.npz   (all three precision modes)
+    here:    python tools/parity_report.py compare  -> profiles/r02_parity_report.json (oracle runs on CPU)
 """
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -28,7 +28,7 @@ def gpu():
     w = synth.make_weights(0)
     dev = torch.device("cuda", 0)
     out = {}
-    for prec in ("bf16x3", "bf16"):
+    for prec in ("fp16", "bf16x3", "bf16"):
         r = PoseRefiner(meshes, w, K, device=0, max_batch=16, n_iter=N_ITER, precision=prec, n_slots=2)
         # observed images: GPU render of the observed pose composited over seeded noise (bit-exact vs oracle render)
         u8 = np.zeros((N, 480, 640, 3), np.uint8)
@@ -64,7 +64,7 @@ def compare():
         ref[:, a:a + 8] = res["poses"]
         print("oracle", a, flush=True)
     report = {"config": "13 synthetic LINEMOD-scale meshes, %d instances, %d iterations, random-init FlowNetS" % (N, N_ITER)}
-    for prec in ("bf16x3", "bf16"):
+    for prec in ("fp16", "bf16x3", "bf16"):
         p = g["poses_" + prec]
         add_g, add_o, acc_g, acc_o = [], [], [], []
         for b in range(N):
@@ -82,7 +82,7 @@ def compare():
             "ADD_abs_diff_over_diameter_max": float(np.max(np.abs(np.array(add_g) - np.array(add_o)))),
             "ADD_0.1d_accuracy_pct_gpu": 100.0 * float(np.mean(acc_g)), "ADD_0.1d_accuracy_pct_oracle": 100.0 * float(np.mean(acc_o)),
         }
-    json.dump(report, open(os.path.join(ROOT, "profiles", "r01_parity_report.json"), "w"), indent=1)
+    json.dump(report, open(os.path.join(ROOT, "profiles", "r02_parity_report.json"), "w"), indent=1)
     print(json.dumps(report, indent=1))
 
 
