@@ -981,7 +981,7 @@ __global__ void __launch_bounds__(320) conv1_stack_kernel(const __grid_constant_
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
           const uint64_t da0 = dring + (uint64_t)slot * slot_step;
-          const int b0 = p.mask_climit == 12345 ? ((s & 1) << 2) : (s & 7);  // DEBUG-ALIGN (timing experiment only: wrong results)
+          const int b0 = s & 7;                         // first block of the window (row v = s, filter row dh = 3)
           const int n1 = b0 <= 4 ? 4 : 8 - b0;          // blocks before the window wraps past column 512
           const uint32_t d1 = tmem_base + (uint32_t)b0 * 64u, id1 = idesc0 | ((uint32_t)(n1 * 64 >> 3) << 17);
           const uint32_t id2 = idesc0 | ((uint32_t)((4 - n1) * 64 >> 3) << 17);

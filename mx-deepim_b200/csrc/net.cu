@@ -611,9 +611,7 @@ int net_forward(dim_ctx *ctx, int B, int precision, const float *zoom_factor, fl
         const int smem_bytes = 16 * 4096 + ST * strip_bytes + (8 * 2048 + 256) + 512 + 512;
         static int set3 = 0;
         if (set3 < smem_bytes) { DIM_CHECK(cudaFuncSetAttribute(conv1_stack_kernel<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); set3 = smem_bytes; }
-        ConvKParams kq = kp;
-        if (getenv("DIM_CONV1_DBG_ALIGN")) kq.mask_climit = 12345;
-        conv1_stack_kernel<ST><<<grid, 320, smem_bytes, st>>>(kq, rows_total, rpc, chunks, strip_bytes);
+        conv1_stack_kernel<ST><<<grid, 320, smem_bytes, st>>>(kp, rows_total, rpc, chunks, strip_bytes);
       } else {
         constexpr int ST = 8;
         const int smem_bytes = 16 * 4096 + ST * strip_bytes + (8 * 2048 + 256) + 1024 + 512;

@@ -63,7 +63,11 @@ def compare():
         res = O.refine(w, meshes, cls[a:a + 8], np.stack(imgs[a:a + 8]), ini[a:a + 8], K, N_ITER, MEANS.astype(np.float32))
         ref[:, a:a + 8] = res["poses"]
         print("oracle", a, flush=True)
-    report = {"config": "13 synthetic LINEMOD-scale meshes, %d instances, %d iterations, random-init FlowNetS" % (N, N_ITER)}
+    report = {"config": "13 synthetic LINEMOD-scale meshes, %d instances, %d iterations, random-init FlowNetS" % (N, N_ITER),
+              "note": "FREE-RUNNING comparison: the CUDA path and the oracle each follow their own pose trajectory, so a difference "
+                      "of iteration k moves the integer bbox / zoom of iteration k+1 and compounds (a random-init network is not "
+                      "contractive); the north-star tolerance (1e-4 rot / 1e-3 trans on the regressed se3) is per iteration on the "
+                      "same inputs and is asserted in tests/test_gpu_headline_b16.py and tests/test_gpu_parity.py"}
     for prec in ("fp16", "bf16x3", "bf16"):
         p = g["poses_" + prec]
         add_g, add_o, acc_g, acc_o = [], [], [], []
