@@ -244,6 +244,12 @@ def test_flow_bit_exact_and_reference_golden(ctx, meshes, golden_dir):
     assert int((va2.cpu().numpy()[0, 0] != vis).sum()) == 0
     assert np.abs(fl2.cpu().numpy()[0][:, vis == 1] - f["flow"].transpose(2, 0, 1)[:, vis == 1]).max() < 5e-5
     c2.close()
+    # the reference's own CUDA kernel (lib/flow_c/gpu_flow_kernel.cu compiled unmodified, oracle/build_ref.py) on a rendered
+    # 480 x 640 pair: identical validity mask, flow within 2 ulp of the pixel coordinate (FMA contraction of its build)
+    g = np.load(os.path.join(golden_dir, "ref_flow_cuda.npz"))
+    fl3, va3 = ctx.flow(dev(g["depth_src"]), dev(g["depth_tgt"]), dev(g["KT"]), g["Kinv"])
+    assert np.array_equal(va3.cpu().numpy(), g["valid"]) and g["valid"].sum() > 5000
+    assert np.abs(fl3.cpu().numpy() - g["flow"]).max() < 2.5e-4
 
 
 def test_transform3d_forward_backward(ctx):

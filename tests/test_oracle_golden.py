@@ -68,6 +68,22 @@ def test_flow_matches_reference_calc_flow(golden_dir):
     assert np.all(fl[0][:, ~both] == 0)
 
 
+def test_flow_matches_the_reference_cuda_kernel(golden_dir):
+    """a13, second pin: the reference's UNMODIFIED lib/flow_c/gpu_flow_kernel.cu (compiled by oracle/build_ref.py into
+    oracle/_ref, executed on a B200 by tests/golden/make_golden_flow_cuda.py -> ref_flow_cuda.npz) against the C restatement:
+    the validity masks are identical; the flow differs by at most 2 ulp of the pixel coordinate (the reference build lets nvcc
+    contract multiply-adds, the restatement is compiled without contraction so that the CUDA path can be bit-exact to IT)."""
+    g = np.load(os.path.join(golden_dir, "ref_flow_cuda.npz"))
+    f = np.load(os.path.join(golden_dir, "ref_flow.npz"))
+    fl, va = O.flow(f["depth_src"][None, None], f["depth_tgt"][None, None], g["small_KT"], g["small_Kinv"])
+    assert np.array_equal(va, g["small_valid"]) and g["small_valid"].sum() > 500
+    assert np.abs(fl - g["small_flow"]).max() < 2e-5
+    fl, va = O.flow(g["depth_src"], g["depth_tgt"], g["KT"], g["Kinv"])
+    assert np.array_equal(va, g["valid"]) and g["valid"].sum() > 5000
+    assert np.abs(fl - g["flow"]).max() < 2.5e-4 and np.abs(g["flow"]).max() > 10.0   # 2 ulp at coordinates of ~600 px
+    assert np.all(fl[np.broadcast_to(va == 0, fl.shape)] == 0)
+
+
 def test_add_adi_match_reference(golden_dir):
     pe = np.load(os.path.join(golden_dir, "ref_pose_error.npz"))
     assert abs(O.add_metric(pe["R_est"], pe["t_est"], pe["R_gt"], pe["t_gt"], pe["pts"]) - pe["add"]) < 1e-15
