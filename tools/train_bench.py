@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--out", default="")
+    ap.add_argument("--bucket-mb", type=float, default=None, help="gradient bucket size of the overlapped all-reduce (default: Trainer's)")
     ap.add_argument("--no-overlap", action="store_true", help="all-reduce after the backward pass instead of bucket by bucket during it")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -43,7 +44,7 @@ def main():
                   max_faces=max(len(m.faces) for m in meshes))
     for i, m in enumerate(meshes):
         ctx.upload_mesh(i, m)
-    tr = Trainer(ctx, synth.make_train_weights(0))
+    tr = Trainer(ctx, synth.make_train_weights(0), **({"bucket_mb": a.bucket_mb} if a.bucket_mb else {}))
     batch, cls, tgt, depth = make_device_batch(ctx, meshes, a.batch, 3 + rank, K, MEANS)
     if a.no_overlap:
         step0 = tr.step
@@ -83,7 +84,8 @@ def main():
                                                                    "allreduce": ev[1].elapsed_time(ev[2]), "sgd_update_repack": ev[2].elapsed_time(ev[3]),
                                                                    "host_enqueue_forward_backward": (c1 - c0) * 1e3, "host_enqueue_update": (c2 - c1) * 1e3},
             "dtype": "bf16 activations/gradients, fp32 master", "data": "synthetic", "scaling": "weak",
-            "config": {"workload": "C4 training step", "allreduce_overlap": (not a.no_overlap) and world > 1, "per_gpu_batch": a.batch, "inner_iterations": 4, "grad_bytes": tr.n * 4},
+            "config": {"workload": "C4 training step", "allreduce_overlap": (not a.no_overlap) and world > 1, "per_gpu_batch": a.batch, "inner_iterations": 4, "grad_bytes": tr.n * 4,
+                       "buckets_mb": [round((hi - lo) * 4 / 2 ** 20, 1) for lo, hi in tr.buckets]},
             "phases_ms": dict(zip(["encoder_fwd", "decoder_fwd", "losses_heads", "fc_bwd", "decoder_bwd", "encoder_dgrad_chain", "wait_wgrad_stream"], [round(float(x), 4) for x in ph])),
             "objective_last_batch": [float(v) for v in objs.cpu()]}
     if rank == 0:
