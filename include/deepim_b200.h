@@ -270,8 +270,10 @@ DIM_API int32_t dim_debug_activation(dim_ctx *ctx, int32_t idx, int32_t lo, void
                                      uint64_t bytes);
 DIM_API int32_t dim_debug_layer_geometry(dim_ctx *ctx, int32_t idx, int32_t *out8);
 /* tuning hooks (tools/conv_lab.py; not part of the drop-in surface).
- * dim_debug_set_option: run-time kernel-variant switch; key "pair_mask": bit i puts conv layer i (1..9) on the
- *   cta_group::2 kernel.  Synchronises the device and drops the cached launch descriptors.
+ * dim_debug_set_option: run-time kernel-variant switch.  Keys: "pair_mask": bit i puts conv layer i (1..9) on the
+ *   cta_group::2 kernel (default: conv2); "conv1_stack": 1 (default) = stacked-filter-rows conv1 kernel for the
+ *   single-pass precisions, 0 = rolling-strip kernel; "graph": 1 (default) = replay the refinement chain as a CUDA graph.
+ *   Synchronises the device and drops the cached launch descriptors / graphs.
  * dim_debug_layer_profile: enable = 1 records CUDA events around each conv layer of every dim_net_fwd / dim_refine
  *   iteration; ms10 (nullable) receives the 10 layer times of the LAST forward pass; enable = 0 stops. */
 DIM_API int32_t dim_debug_set_option(dim_ctx *ctx, const char *key, int32_t value);
