@@ -937,22 +937,17 @@ static int launch_generic(const ConvKParams &kp, int total_tiles, int n_tiles, i
   return 0;
 }
 
-// N <= 128 tiles are bound by L2 -> shared-memory operand traffic, not by the tensor pipe.  Two resident CTAs per SM with a
-// shallow ring (what conv2 of the forward tower uses) measured the same as one CTA with a deep ring for the data-gradient
-// classes (265.7 vs 266.0 instances/s at B = 4), so the deep ring stays the default; DIM_TRAIN_OCC2=1 selects the other.
-static bool train_occ2() {
-  static const bool v = [] { const char *e = getenv("DIM_TRAIN_OCC2"); return e && e[0] == '1'; }();
-  return v;
-}
-
+// N <= 128 tiles are bound by shared-memory operand traffic, not by the tensor pipe.  Two resident CTAs per SM with a shallow
+// ring (what conv2 of the forward tower used before its CTA-pair kernel) measured the same as one CTA with a deep ring for
+// the data-gradient classes (265.7 vs 266.0 instances/s at B = 4): one CTA per SM, deep ring.
 static int run_generic(dim_ctx *ctx, const ConvKParams &kp, const LayerGeom &g, int B, cudaStream_t st) {
   const int n_tiles = cdiv(g.Cout, g.BLOCK_N);
   const int total = cdiv(B * g.Hq, g.BH) * g.n_col_tiles * n_tiles;
   const int sms = ctx->num_sms;
   if (g.BLOCK_N == 256) return launch_generic<256, 4>(kp, total, n_tiles, sms, st);
   if (g.BLOCK_N == 128)
-    return train_occ2() ? launch_generic<128, 2>(kp, total, n_tiles, 2 * sms, st) : launch_generic<128, 5>(kp, total, n_tiles, sms, st);
-  return train_occ2() ? launch_generic<64, 3>(kp, total, n_tiles, 2 * sms, st) : launch_generic<64, 6>(kp, total, n_tiles, sms, st);
+    return launch_generic<128, 5>(kp, total, n_tiles, sms, st);
+  return launch_generic<64, 6>(kp, total, n_tiles, sms, st);
 }
 
 // Describe one launch of the generic kernel.
@@ -1084,20 +1079,12 @@ static int make_wgrad(TrainState *ts, WgradParams &p, int &BN, int B, const Buf 
 
 static int run_wgrad(const WgradParams &p, int BN, int kind, int D0, int D1, int k, float *grad, cudaStream_t st) {
   int rc;
-  // Two resident CTAs per SM with half-depth rings (the same bytes in flight per SM): the barrier-init / TMEM-alloc
-  // prologue and the fp32 epilogue of one CTA overlap the K loop of the other.  DIM_WGRAD_OCC2=0: one CTA, deep ring.
-  static const bool occ2 = [] { const char *e = getenv("DIM_WGRAD_OCC2"); return !(e && e[0] == '0'); }();
-  if (occ2) {
-    if (BN == 256) rc = launch_wgrad<256, 2>(p, st);
-    else if (BN == 128) rc = launch_wgrad<128, 3>(p, st);
-    else if (BN == 64) rc = launch_wgrad<64, 4>(p, st);
-    else rc = launch_wgrad<32, 4>(p, st);
-  } else {
-    if (BN == 256) rc = launch_wgrad<256, 4>(p, st);
-    else if (BN == 128) rc = launch_wgrad<128, 6>(p, st);
-    else if (BN == 64) rc = launch_wgrad<64, 8>(p, st);
-    else rc = launch_wgrad<32, 8>(p, st);
-  }
+  // Two resident CTAs per SM with half-depth rings (the same bytes in flight per SM as one CTA with a deep ring): the
+  // barrier-init / TMEM-alloc prologue and the fp32 epilogue of one CTA overlap the K loop of the other (measured +4 %).
+  if (BN == 256) rc = launch_wgrad<256, 2>(p, st);
+  else if (BN == 128) rc = launch_wgrad<128, 3>(p, st);
+  else if (BN == 64) rc = launch_wgrad<64, 4>(p, st);
+  else rc = launch_wgrad<32, 4>(p, st);
   if (rc) return rc;
   const size_t total = (size_t)p.KH * p.KW * p.m_tiles * 128 * p.n_tiles * BN;
   wgrad_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p.partial, p.kslices, p.KH * p.KW, p.m_tiles * 128,
