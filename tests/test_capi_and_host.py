@@ -27,6 +27,38 @@ def test_library_exports_every_declared_symbol(root):
     assert lib.dim_abi_version() == 2
 
 
+def test_library_is_sm100a_native_tcgen05_and_tma(root):
+    """The hot kernels of the shipped library are Blackwell-native: the conv tower issues tcgen05.mma (SASS UTCHMMA) on operands
+    staged by TMA (UTMALDG) with accumulators read back from tensor memory (LDTM), and the only architecture in the fatbin is
+    sm_100a.  (tools/sass_counts.py writes the per-kernel listing kept in profiles/r02_sass_counts.txt.)"""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    so = os.path.join(root, "mx-deepim_b200", "libdeepim_b200.so")
+    elf = subprocess.run(["cuobjdump", "-lelf", so], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\w+)\.cubin", elf))
+    assert archs == {"100a"}, archs
+    sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
+    per_kernel, cur = {}, None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            per_kernel[cur] = {"UTCHMMA": 0, "UTMALDG": 0, "LDTM": 0}
+        elif cur:
+            for k in per_kernel[cur]:
+                if re.search(r"\b%s\b" % k, line):
+                    per_kernel[cur][k] += 1
+    def of(name):
+        return [v for k, v in per_kernel.items() if name in k]
+    for name in ("conv_igemm_persistent_kernel", "conv_igemm_pair_kernel", "conv1_stack_kernel", "conv1_roll_kernel", "conv_wgrad_kernel"):
+        ks = [v for v in of(name) if v["UTCHMMA"]]     # (cuobjdump also lists empty stubs under the same name)
+        assert ks, name
+        for v in ks:
+            assert v["UTCHMMA"] >= 4 and v["UTMALDG"] >= 2 and v["LDTM"] >= 1, (name, v)
+
+
 def test_ctypes_binding_covers_the_header(root):
     from deepim_b200 import _capi
     assert sorted(_capi.SIGNATURES) == declared_symbols(root)
