@@ -38,15 +38,16 @@ __global__ void __launch_bounds__(256) flow_kernel(const float *__restrict__ dep
     const float y = (((float)w * i3 + (float)h * i4) + i5) * d;
     const float z = d;
     fh[k] = 0.f; fw[k] = 0.f; ok[k] = 0.f;
-    if (d > 1e-3f) {
+    // the reference compares / offsets against DOUBLE literals (gpu_flow_kernel.cu:45,49,56): float operands are promoted
+    if ((double)d > 1e-3) {
       const float xp = ((x * k0 + y * k1) + z * k2) + k3;
       const float yp = ((x * k4 + y * k5) + z * k6) + k7;
-      const float zp = (((x * k8 + y * k9) + z * k10) + k11) + 1e-15f;
+      const float zp = (float)((double)(((x * k8 + y * k9) + z * k10) + k11) + 1e-15);
       const float wp = xp / zp, hp = yp / zp;
       if (wp >= 0.f && wp <= (float)(W - 1) && hp >= 0.f && hp <= (float)(H - 1)) {
         const int wi = (int)roundf(wp), hi = (int)roundf(hp);
         const float dt = __ldg(depth_tgt + (size_t)b * P + (size_t)hi * W + wi);
-        if (fabsf(zp - dt) < 3e-3f) {
+        if ((double)fabsf(zp - dt) < 3e-3) {
           fh[k] = hp - (float)h;
           fw[k] = wp - (float)w;
           ok[k] = 1.f;

@@ -655,15 +655,16 @@ ORC_API void orc_flow(const float *depth_src, const float *depth_tgt, const floa
         float y = (((float)w * Kinv[3] + (float)h * Kinv[4]) + Kinv[5]) * d;
         float z = d;
         float fh = 0.f, fw = 0.f, ok = 0.f;
-        if (d > 1e-3f) {
+        /* double literals in the reference (gpu_flow_kernel.cu:45,49,56): the float operands are promoted */
+        if ((double)d > 1e-3) {
           float xp = ((x * kt[0] + y * kt[1]) + z * kt[2]) + kt[3];
           float yp = ((x * kt[4] + y * kt[5]) + z * kt[6]) + kt[7];
-          float zp = (((x * kt[8] + y * kt[9]) + z * kt[10]) + kt[11]) + 1e-15f;
+          float zp = (float)((double)(((x * kt[8] + y * kt[9]) + z * kt[10]) + kt[11]) + 1e-15);
           float wp = xp / zp, hp = yp / zp;
           if (wp >= 0.f && wp <= (float)(W - 1) && hp >= 0.f && hp <= (float)(H - 1)) {
             int32_t wi = (int32_t)roundf(wp), hi = (int32_t)roundf(hp);
             float dt = depth_tgt[((size_t)b * H + hi) * W + wi];
-            if (fabsf(zp - dt) < 3e-3f) {
+            if ((double)fabsf(zp - dt) < 3e-3) {
               fh = hp - (float)h;
               fw = wp - (float)w;
               ok = 1.f;
