@@ -12,6 +12,7 @@ Nothing from the reference is copied: this script only *calls* it and stores inp
 """
 import doctest
 import os
+import math
 import sys
 
 import numpy as np
@@ -154,6 +155,41 @@ def main():
         arp[k] = pose_error.arp_2d(est[k, :, :3], est[k, :, 3], gt[k, :, :3], gt[k, :, 3], pts2, Kc)
     np.savez_compressed(os.path.join(HERE, "ref_pose_eval.npz"), pts=pts2, K=Kc, poses_est=est, poses_gt=gt, rot_deg=np.real(rd),
                         trans_m=td, re_deg=np.real(re_deg), arp_2d=arp)
+
+    # ---- static-xyz euler helpers (RT_transform.py:240-360, 512-560) + the rendered-pose sampling loop of
+    # toolkit/LM6d_1_gen_rendered_pose.py:77-125 written with the reference's own helpers and its np.random.seed(2333) stream
+    rng3 = np.random.default_rng(99)
+    ang = rng3.uniform(-math.pi, math.pi, size=(40, 3))
+    ang[:, 1] = rng3.uniform(-math.pi / 2, math.pi / 2, size=40)
+    ang[0] = [0.3, math.pi / 2, -0.2]                       # gimbal case
+    mats = np.stack([RT.euler2mat(a[0], a[1], a[2]) for a in ang])
+    back = np.stack([np.array(RT.mat2euler(m)) for m in mats])
+    quats = np.stack([RT.euler2quat(a[0], a[1], a[2]) for a in ang])
+    Kl = np.array([[572.4114, 0, 325.2611], [0, 573.57043, 242.04899], [0, 0, 1]])
+    obs = np.zeros((3, 3, 4))
+    for k in range(3):
+        obs[k, :, :3] = rand_rot(rng3)
+        obs[k, :, 3] = [rng3.uniform(-0.1, 0.1), rng3.uniform(-0.08, 0.08), rng3.uniform(0.7, 1.1)]
+    np.random.seed(2333)
+    angle_std, angle_max, x_std, y_std, z_std = [15.0, 45.0, 0.01, 0.01, 0.05]
+    ren = np.zeros((3, 4, 3, 4))
+    for a in range(3):
+        src_pose_m = obs[a]
+        src_euler = np.squeeze(RT.mat2euler(src_pose_m[:3, :3]))
+        src_trans = src_pose_m[:, 3]
+        for k in range(4):
+            while True:
+                tgt_euler = src_euler + np.random.normal(0, angle_std / 180 * math.pi, 3)
+                tgt_trans = src_trans + np.array([np.random.normal(0, x_std, 1)[0], np.random.normal(0, y_std, 1)[0],
+                                                  np.random.normal(0, z_std, 1)[0]])
+                tgt_pose_m = np.hstack((RT.euler2mat(tgt_euler[0], tgt_euler[1], tgt_euler[2]), tgt_trans.reshape((3, 1))))
+                r_dist, t_dist = RT.calc_rt_dist_m(tgt_pose_m, src_pose_m)
+                c = np.matmul(Kl, tgt_trans.reshape(3, 1))
+                if not (r_dist > angle_max or not (16 < c[0] / c[2] < (640 - 16) and 16 < c[1] / c[2] < (480 - 16))):
+                    break
+            ren[a, k] = tgt_pose_m
+    np.savez_compressed(os.path.join(HERE, "ref_euler.npz"), angles=ang, mats=mats, back=back, quats=quats, K=Kl,
+                        poses_observed=obs, poses_rendered=ren)
 
     # ---- image.transform (lib/utils/image.py:583-594)
     try:

@@ -1,5 +1,7 @@
 """GPU: batched pred_eval over an LM6d_refine-style directory: disk formats -> PoseRefiner ->
 device ADD / ADI -> accuracy / AUC tables."""
+import os
+
 import numpy as np
 import pytest
 
@@ -96,3 +98,42 @@ def test_flow_epe_matches_the_reference_formula():
         assert abs(got["epe_viz"][b] - d[v].astype(np.float64).sum()) < 1e-6 * d.sum() and got["num_viz"][b] == v.sum()
         assert abs(got["epe_vizbg"][b] - d[vb].astype(np.float64).sum()) < 1e-6 * d.sum() and got["num_vizbg"][b] == vb.sum()
     ctx.close()
+
+
+def test_toolkit_writes_a_rendered_set_the_loader_reads_back(tmp_path):
+    """deepim_b200/toolkit.py (toolkit/LM6d_1_gen_rendered_pose.py + LM6d_2_gen_rendered.py on the CUDA rasteriser): perturbed
+    rendered poses around the observed ones, their renders / depth / pose files and the pair list, read back through the
+    LM6d_refine loader and pushed through the batched evaluation."""
+    import cv2
+    from deepim_b200 import toolkit
+    from deepim_b200.context import Context
+    classes, meshes = lm6d_fixture.build(str(tmp_path), n_per_class=2)
+    ds = lm6d_io.LM6DRefine(str(tmp_path), classes, "val")
+    K = synth.K_LINEMOD
+    dev = torch.device("cuda", 0)
+    ctx = Context(0, max_batch=4, max_classes=2, max_verts=max(len(ds.mesh(c).verts) for c in classes),
+                  max_faces=max(len(ds.mesh(c).faces) for c in classes))
+    for ci, c in enumerate(classes):
+        ctx.upload_mesh(ci, ds.mesh(c))
+    for ci, c in enumerate(classes):
+        obs_idx = [p[0] for p in ds.pairs(c)]
+        gt = np.stack([ds.load_pair(c, p)["pose_observed"] for p in ds.pairs(c)])
+        ren = toolkit.gen_rendered_poses(gt, K, n_per_observed=3, seed=5 + ci)
+        lines = toolkit.write_rendered_set(str(tmp_path), ctx, c, ci + 1, ci, obs_idx, ren, K, set_name="train", batch=4)
+        assert len(lines) == 6
+        for i in range(2):
+            for k in range(3):
+                base = os.path.join(str(tmp_path), "data", "rendered", c, "%s_%d" % (obs_idx[i].split("/")[1], k))
+                np.testing.assert_allclose(lm6d_io.read_pose(base + "-pose.txt"), ren[i, k], rtol=0, atol=1e-9)
+                r = ctx.render(torch.tensor([ci], dtype=torch.int32, device=dev), torch.from_numpy(ren[i, k][None].astype(np.float32)).to(dev),
+                               K, trunc_u8=False, want=("bgr", "depth"))
+                assert np.array_equal(cv2.imread(base + "-color.png"), r["bgr"][0].cpu().numpy().astype(np.uint8))
+                assert np.array_equal(cv2.imread(base + "-depth.png", cv2.IMREAD_UNCHANGED),
+                                      (r["depth"][0, 0].cpu().numpy() * 1000.0).astype(np.uint16))
+                assert toolkit.rot_dist_deg(ren[i, k, :, :3], gt[i, :, :3]) <= 45.0
+    ctx.close()
+    ds2 = lm6d_io.LM6DRefine(str(tmp_path), classes, "train")
+    assert [len(ds2.pairs(c)) for c in classes] == [6, 6]
+    res, poses, gt2 = lm6d_io.evaluate(ds2, synth.make_weights(0), K, n_iter=1, max_batch=4)
+    assert poses.shape == (1, 12, 3, 4) and np.isfinite(poses).all() and len(res["classes"]) == 2
+
