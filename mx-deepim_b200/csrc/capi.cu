@@ -385,6 +385,7 @@ static int refine_core(dim_ctx *ctx, const float4 *obs4, const int32_t *cls_idx,
   net_input_geometry(ctx, &rows, &cols, &pad, &hi, &lo);
   const double *pose_src = pose_init;
   for (int it = 0; it < n_iter; ++it) {
+    DimNvtxRange r_it("dim_refine iteration");
     cudaEvent_t *ev = nullptr;
     if (ctx->prof) {
       while (ctx->prof_events.size() < ctx->prof_used + 5) {
@@ -401,24 +402,36 @@ static int refine_core(dim_ctx *ctx, const float4 *obs4, const int32_t *cls_idx,
     if (int rc = f64_to_f32_launch(pose_src, ctx->pose_cur_f32, B * 12, st)) return rc;
     // render at the current pose (tester.py:427-442) straight into the pixel-interleaved
     // (R,G,B,mask) image the zoom kernel samples; mask_observed := box(mask_rendered) is analytic
-    if (int rc = render_launch(ctx, cls_idx, ctx->pose_cur_f32, B, K9, zn, zf, means, 1, nullptr, nullptr, nullptr,
-                               nullptr, nullptr, ctx->ren4, st))
-      return rc;
+    {
+      DimNvtxRange r("render");
+      if (int rc = render_launch(ctx, cls_idx, ctx->pose_cur_f32, B, K9, zn, zf, means, 1, nullptr, nullptr, nullptr,
+                                 nullptr, nullptr, ctx->ren4, st))
+        return rc;
+    }
     if (ev) DIM_CHECK(cudaEventRecord(ev[1], st));
     float *zf_it = zoom_factor ? zoom_factor + (size_t)it * B * 4 : ctx->zoom_factor;
     int *bbox_it = bbox ? bbox + (size_t)it * B * 8 : nullptr;
     // per-iteration status (bit 0: rendered / observed mask empty -> fallback zoom factor; bit 1: bad class index)
-    if (int rc = zoom_factor_from_ren_launch(ctx, ctx->bbox_ren, ctx->pose_cur_f32, B, K9, zf_it, bbox_it,
-                                             ctx->status_hist + (size_t)(it < 8 ? it : 7) * B, st))
-      return rc;
-    if (int rc = zoom_fused_launch(ctx, obs4, ctx->ren4, zf_it, means_f, B, rows, cols, pad, hi,
-                                   precision == DIM_PREC_BF16X3 ? lo : nullptr, st, precision == DIM_PREC_FP16, means))
-      return rc;
+    {
+      DimNvtxRange r("bbox + zoom");
+      if (int rc = zoom_factor_from_ren_launch(ctx, ctx->bbox_ren, ctx->pose_cur_f32, B, K9, zf_it, bbox_it,
+                                               ctx->status_hist + (size_t)(it < 8 ? it : 7) * B, st))
+        return rc;
+      if (int rc = zoom_fused_launch(ctx, obs4, ctx->ren4, zf_it, means_f, B, rows, cols, pad, hi,
+                                     precision == DIM_PREC_BF16X3 ? lo : nullptr, st, precision == DIM_PREC_FP16, means))
+        return rc;
+    }
     if (ev) DIM_CHECK(cudaEventRecord(ev[2], st));
     float *se3_it = se3 ? se3 + (size_t)it * B * 7 : ctx->se3_cur;
-    if (int rc = net_forward(ctx, B, precision, zf_it, nullptr, nullptr, se3_it, st, ev ? ev[3] : nullptr)) return rc;
+    {
+      DimNvtxRange r("FlowNetS tower + heads");
+      if (int rc = net_forward(ctx, B, precision, zf_it, nullptr, nullptr, se3_it, st, ev ? ev[3] : nullptr)) return rc;
+    }
     double *pose_out = poses + (size_t)it * B * 12;
-    if (int rc = se3_compose_launch(pose_src, se3_it, B, Tm, Ts, ctx->cfg.rot_coord, pose_out, nullptr, st)) return rc;
+    {
+      DimNvtxRange r("SE(3) compose");
+      if (int rc = se3_compose_launch(pose_src, se3_it, B, Tm, Ts, ctx->cfg.rot_coord, pose_out, nullptr, st)) return rc;
+    }
     if (ev) DIM_CHECK(cudaEventRecord(ev[4], st));
     pose_src = pose_out;
   }

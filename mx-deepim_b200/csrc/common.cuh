@@ -7,7 +7,21 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only; no-ops unless a profiler injects itself
+
 #include "../../include/deepim_b200.h"
+
+// NVTX range for the host-side enqueue of one stage (Nsight Systems timelines: SURVEY 5 "tracing"): scoped push / pop
+struct DimNvtxRange {
+  bool open = true;
+  explicit DimNvtxRange(const char *name) { nvtxRangePushA(name); }
+  void end() {  // close before the scope does (ranges must nest: end inner ranges first)
+    if (open) { nvtxRangePop(); open = false; }
+  }
+  ~DimNvtxRange() { end(); }
+  DimNvtxRange(const DimNvtxRange &) = delete;
+  DimNvtxRange &operator=(const DimNvtxRange &) = delete;
+};
 
 namespace dim {
 

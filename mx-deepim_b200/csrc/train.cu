@@ -1317,6 +1317,7 @@ int train_forward_backward(dim_ctx *ctx, const TrainIO &io, cudaStream_t st) {
   const float *Tm = cfg.trans_means, *Tsd = cfg.trans_stds;
 
   // ---------------- forward
+  DimNvtxRange r_fwd("dim_train forward + losses");
   DIM_CHECK(cudaEventRecord(ts->ev_phase[0], st));
   if (int rc = pack_nhwc8_launch(ctx, io.zio, io.zir, io.zmo, io.zmr, B, g[0].rows, g[0].cols, g[0].py, ns->act_hi[0], nullptr, st, 0)) return rc;
   if (int rc = net_forward(ctx, B, DIM_PREC_BF16, nullptr, ts->rot_raw, ts->ztrans, nullptr, st, nullptr)) return rc;
@@ -1364,9 +1365,11 @@ int train_forward_backward(dim_ctx *ctx, const TrainIO &io, cudaStream_t st) {
   if (io.rot_est_norm) DIM_CHECK(cudaMemcpyAsync(io.rot_est_norm, ts->rot_n, (size_t)B * 16, cudaMemcpyDeviceToDevice, st));
   if (io.trans_est) DIM_CHECK(cudaMemcpyAsync(io.trans_est, ts->trans_est, (size_t)B * 12, cudaMemcpyDeviceToDevice, st));
   DIM_CHECK(cudaEventRecord(ts->ev_phase[3], st));
+  r_fwd.end();
   if (G == nullptr) return 0;  // forward only (non-FAST_TEST outputs)
 
   // ---------------- backward
+  DimNvtxRange r_bwd("dim_train backward");
   DIM_CHECK(cudaMemsetAsync(G + ts->off[P_UPS].w, 0, (ts->off[P_UPS].wn + ts->off[P_MUPS].wn) * sizeof(float), st));  // frozen (lr_mult 0)
   // pose heads
   if (int rc = transform3d_bwd_launch(ts->dpts, io.pc_model, ts->rot_n, ts->trans_est, io.src_pose, B, io.N, Tm, Tsd, cfg.rot_coord, ts->drot_n, ts->dtrans, st)) return rc;
