@@ -888,6 +888,10 @@ __global__ void __launch_bounds__(320) conv1_roll_kernel(const __grid_constant__
 // handed back ZEROED by the epilogue warps (tcgen05.st) after they drain it, four strips before it is needed again.  When
 // the 4-block window wraps past column 512 the MMA is split in two (N = 64 n1 + 64 (4 - n1)).  Every strip is loaded and
 // consumed exactly once; the 3-row halo of a chunk costs three extra strips whose partial rows are discarded.
+// Structurally-zero K steps are not issued: filter row 7 (dh = 3, odd input row) and filter column 7 (dw = 3, odd input
+// column) lie outside the 7 x 7 filter, so the k = 1 steps run on [W_dh2; W_dh1; W_dh0] only (N = 192, window shifted by
+// one block) and dw = 3 has ONE step over the input chunks (0, 2) (weights packed in that order: conv1_kslot) -- 1600
+// instead of 2048 MMA columns per strip.  MMAs of one shape / accumulator window are issued back to back (k-major).
 template <int STAGES>
 __global__ void __launch_bounds__(320) conv1_stack_kernel(const __grid_constant__ ConvKParams p, const int rows_total,
                                                           const int rows_per_chunk, const int chunks_per_col,
