@@ -59,6 +59,24 @@ def test_library_is_sm100a_native_tcgen05_and_tma(root):
             assert v["UTCHMMA"] >= 4 and v["UTMALDG"] >= 2 and v["LDTM"] >= 1, (name, v)
 
 
+def test_train_config_struct_layout_matches_the_header(root, tmp_path):
+    """dim_train_config crosses the C ABI by pointer: the ctypes mirror must have the C compiler's layout of the header's struct."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not on PATH")
+    from deepim_b200 import _capi
+    src = tmp_path / "layout.c"
+    fields = [f for f, _ in _capi.TrainConfig._fields_]
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "deepim_b200.h"\nint main(void) {\n  printf("%zu", sizeof(dim_train_config));\n'
+                   + "".join('  printf(" %%zu", offsetof(dim_train_config, %s));\n' % f for f in fields) + "  return 0;\n}\n")
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)])
+    nums = [int(x) for x in subprocess.check_output([str(exe)]).decode().split()]
+    assert nums[0] == ctypes.sizeof(_capi.TrainConfig)
+    assert nums[1:] == [getattr(_capi.TrainConfig, f).offset for f in fields]
+
+
 def test_ctypes_binding_covers_the_header(root):
     from deepim_b200 import _capi
     assert sorted(_capi.SIGNATURES) == declared_symbols(root)
